@@ -1,0 +1,90 @@
+"""ctypes binding of the C-ABI library (include/cwfa_b200.h).
+
+There is NO CPU fallback: if the shared library cannot be built/loaded the import of the
+compute path fails loudly, and every op refuses non-CUDA tensors.
+"""
+import ctypes as C
+import os
+import threading
+
+from . import _build
+
+_lock = threading.Lock()
+_lib = None
+
+i32, i64, f32, f64, vp = C.c_int, C.c_int64, C.c_float, C.c_double, C.c_void_p
+
+# name -> argtypes (restype is int unless listed in _RESTYPES)
+_SIGS = {
+    "cwfa_device_check": [],
+    "cwfa_haar1d_fwd": [vp, vp, vp, i32, i32, i64, i64, i64, vp],
+    "cwfa_haar1d_inv": [vp, vp, vp, i32, i32, i64, i64, i64, vp],
+    "cwfa_haar2d_down": [vp, vp, i32, i32, i32, i32, i32, f32, vp],
+    "cwfa_haar2d_up": [vp, vp, i32, i32, i32, i32, i32, f32, vp],
+    "cwfa_permute": [vp, vp, vp, i32, i32, i32, i32, i32, vp],
+    "cwfa_affine_workspace_blocks": [],
+    "cwfa_affine": [vp, vp, vp, vp, vp, vp, vp, i32, i32, i64, i64, i64, f32, f32, f32, i32, vp],
+    "cwfa_conv2d_f32": [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp],
+    "cwfa_convT2x2_f32": [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],
+    "cwfa_depth_stencil3d_f32": [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],
+    "cwfa_stats_workspace_blocks": [],
+    "cwfa_channel_stats_f32": [vp, vp, vp, i32, i32, i64, vp],
+    "cwfa_bn_finalize_f32": [vp, vp, vp, vp, vp, i32, f64, f32, vp],
+    "cwfa_scale_shift_f32": [vp, vp, vp, vp, i32, i32, i64, vp],
+    "cwfa_maxpool2_f32": [vp, vp, i32, i32, i32, i32, vp],
+    "cwfa_layernorm_workspace_blocks": [],
+    "cwfa_layernorm_chw_f32": [vp, vp, vp, vp, vp, i32, i64, f32, vp],
+    "cwfa_gate_add_f32": [vp, vp, vp, i64, vp],
+}
+_RESTYPES = {"cwfa_version": C.c_char_p, "cwfa_last_error": C.c_char_p}
+_OPTIONAL = {}
+
+
+def exported_symbols():
+    """Every symbol include/cwfa_b200.h declares (used by the CPU-side ABI test)."""
+    return sorted(list(_SIGS) + list(_RESTYPES) + list(_OPTIONAL))
+
+
+def lib_path() -> str:
+    return _build.LIB_PATH
+
+
+def load():
+    """Load (building first if the .so is missing or stale and nvcc is present)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        path = _build.LIB_PATH
+        try:
+            path = _build.build()
+        except Exception as e:  # stale-but-present library is still usable
+            if not os.path.exists(path):
+                raise RuntimeError(
+                    "cwfa_b200: CUDA library missing and could not be built "
+                    f"({e}); there is no CPU fallback") from e
+        lib = C.CDLL(path)
+        for name, args in {**_SIGS, **_OPTIONAL}.items():
+            fn = getattr(lib, name)
+            fn.argtypes = args
+            fn.restype = C.c_int
+        for name, rt in _RESTYPES.items():
+            fn = getattr(lib, name)
+            fn.argtypes = []
+            fn.restype = rt
+        _lib = lib
+    return _lib
+
+
+class CwfaError(RuntimeError):
+    pass
+
+
+def call(name: str, *args) -> None:
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        msg = lib.cwfa_last_error().decode(errors="replace")
+        raise CwfaError(f"{name} failed (code {rc}): {msg}")

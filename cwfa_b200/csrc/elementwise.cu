@@ -1,0 +1,529 @@
+// Memory-bound kernels of the CWFA path: Haar DWT/IDWT (1-D depth-wise and FrEIA 2-D),
+// permutations, affine coupling with fused per-sample log-det, normalisation helpers.
+// All are single-pass, 128-bit vectorised where alignment allows, grid sized in multiples
+// of the SM count.  Reference arithmetic cited per function in include/cwfa_b200.h.
+#include <stdarg.h>
+#include "common.cuh"
+
+namespace cwfa {
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: %s", what, cudaGetErrorString(e));
+        return CWFA_ECUDA;
+    }
+    return CWFA_OK;
+}
+}  // namespace cwfa
+using namespace cwfa;
+
+extern "C" const char* cwfa_version(void) { return "cwfa_b200 0.1 (sm_100a)"; }
+extern "C" const char* cwfa_last_error(void) { return cwfa::g_err; }
+extern "C" int cwfa_device_check(void) {
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { set_error("no CUDA device"); return CWFA_ECUDA; }
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    if (major != 10) { set_error("device is sm_%d0, need sm_100", major); return CWFA_ENOTSUP; }
+    return CWFA_OK;
+}
+
+#define INV_SQRT2 0.70710678118654752440f
+
+// ------------------------------------------------------------------------------------------
+// K1: depth-wise Haar
+// ------------------------------------------------------------------------------------------
+template <int VEC, bool INV>
+__global__ void __launch_bounds__(256) haar1d_kernel(const float* __restrict__ a, const float* __restrict__ b2,
+                                                     float* __restrict__ o1, float* __restrict__ o2,
+                                                     int B, int h, int64_t P, int64_t ld_lo, int64_t ld_hi) {
+    // fwd: a = x (B,2h,P), o1 = lo, o2 = hi.   inv: a = lo, b2 = hi, o1 = x.
+    const int64_t Pv = P / VEC;
+    const int64_t total = (int64_t)B * h * Pv;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t p = (idx % Pv) * VEC;
+        const int64_t r = idx / Pv;
+        const int i = (int)(r % h);
+        const int b = (int)(r / h);
+        const int64_t xo = ((int64_t)b * 2 * h + 2 * i) * P + p;
+        const int64_t lo_o = (int64_t)b * ld_lo + (int64_t)i * P + p;
+        const int64_t hi_o = (int64_t)b * ld_hi + (int64_t)i * P + p;
+        if constexpr (VEC == 4) {
+            if constexpr (!INV) {
+                const float4 e = __ldg(reinterpret_cast<const float4*>(a + xo));
+                const float4 o = __ldg(reinterpret_cast<const float4*>(a + xo + P));
+                float4 l, hh;
+                l.x = (e.x + o.x) * INV_SQRT2; hh.x = (e.x - o.x) * INV_SQRT2;
+                l.y = (e.y + o.y) * INV_SQRT2; hh.y = (e.y - o.y) * INV_SQRT2;
+                l.z = (e.z + o.z) * INV_SQRT2; hh.z = (e.z - o.z) * INV_SQRT2;
+                l.w = (e.w + o.w) * INV_SQRT2; hh.w = (e.w - o.w) * INV_SQRT2;
+                *reinterpret_cast<float4*>(o1 + lo_o) = l;
+                *reinterpret_cast<float4*>(o2 + hi_o) = hh;
+            } else {
+                const float4 l = __ldg(reinterpret_cast<const float4*>(a + lo_o));
+                const float4 hh = __ldg(reinterpret_cast<const float4*>(b2 + hi_o));
+                float4 e, o;
+                e.x = (l.x + hh.x) * INV_SQRT2; o.x = (l.x - hh.x) * INV_SQRT2;
+                e.y = (l.y + hh.y) * INV_SQRT2; o.y = (l.y - hh.y) * INV_SQRT2;
+                e.z = (l.z + hh.z) * INV_SQRT2; o.z = (l.z - hh.z) * INV_SQRT2;
+                e.w = (l.w + hh.w) * INV_SQRT2; o.w = (l.w - hh.w) * INV_SQRT2;
+                *reinterpret_cast<float4*>(o1 + xo) = e;
+                *reinterpret_cast<float4*>(o1 + xo + P) = o;
+            }
+        } else {
+            if constexpr (!INV) {
+                const float e = a[xo], o = a[xo + P];
+                o1[lo_o] = (e + o) * INV_SQRT2;
+                o2[hi_o] = (e - o) * INV_SQRT2;
+            } else {
+                const float l = a[lo_o], hh = b2[hi_o];
+                o1[xo] = (l + hh) * INV_SQRT2;
+                o1[xo + P] = (l - hh) * INV_SQRT2;
+            }
+        }
+    }
+}
+
+static int haar1d_launch(bool inv, const float* x_or_lo, const float* hi_in, float* o1, float* o2, int B, int C,
+                         int64_t P, int64_t ld_lo, int64_t ld_hi, cudaStream_t st) {
+    if (B <= 0 || C <= 0 || (C & 1) || P <= 0) { set_error("haar1d: bad shape B=%d C=%d", B, C); return CWFA_EINVAL; }
+    const int h = C / 2;
+    const bool vec = (P % 4 == 0) && (ld_lo % 4 == 0) && (ld_hi % 4 == 0) && aligned16(x_or_lo) && aligned16(o1) &&
+                     (inv ? aligned16(hi_in) : aligned16(o2));
+    const int64_t total = (int64_t)B * h * (vec ? P / 4 : P);
+    int blocks = (int)((total + 255) / 256);
+    const int maxb = kNumSMs * 16;
+    if (blocks > maxb) blocks = maxb;
+    if (blocks < 1) blocks = 1;
+    if (vec) {
+        if (inv) haar1d_kernel<4, true><<<blocks, 256, 0, st>>>(x_or_lo, hi_in, o1, o2, B, h, P, ld_lo, ld_hi);
+        else haar1d_kernel<4, false><<<blocks, 256, 0, st>>>(x_or_lo, hi_in, o1, o2, B, h, P, ld_lo, ld_hi);
+    } else {
+        if (inv) haar1d_kernel<1, true><<<blocks, 256, 0, st>>>(x_or_lo, hi_in, o1, o2, B, h, P, ld_lo, ld_hi);
+        else haar1d_kernel<1, false><<<blocks, 256, 0, st>>>(x_or_lo, hi_in, o1, o2, B, h, P, ld_lo, ld_hi);
+    }
+    return check_launch("haar1d");
+}
+
+extern "C" int cwfa_haar1d_fwd(const float* x, float* lo, float* hi, int B, int C, int64_t P, int64_t ld_lo,
+                               int64_t ld_hi, void* stream) {
+    return haar1d_launch(false, x, nullptr, lo, hi, B, C, P, ld_lo, ld_hi, (cudaStream_t)stream);
+}
+extern "C" int cwfa_haar1d_inv(const float* lo, const float* hi, float* x, int B, int C, int64_t P, int64_t ld_lo,
+                               int64_t ld_hi, void* stream) {
+    return haar1d_launch(true, lo, hi, x, nullptr, B, C, P, ld_lo, ld_hi, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------
+// K1b: FrEIA 2-D Haar.  One thread per 2x2 input block (one output pixel of 4 wavelets).
+// ------------------------------------------------------------------------------------------
+template <bool UP>
+__global__ void __launch_bounds__(256) haar2d_kernel(const float* __restrict__ src, float* __restrict__ dst, int B,
+                                                     int C, int H2, int W2, int by_wavelet, float fac) {
+    // Fine grid is (B,C,2*H2,2*W2); coarse grid is (B,4C,H2,W2).
+    const int64_t total = (int64_t)B * C * H2 * W2;
+    const int64_t plane = (int64_t)H2 * W2;
+    const int W = 2 * W2;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int w2 = (int)(idx % W2);
+        const int h2 = (int)((idx / W2) % H2);
+        const int c = (int)((idx / plane) % C);
+        const int b = (int)(idx / (plane * C));
+        const int64_t fine = (((int64_t)b * C + c) * (2 * H2) + 2 * h2) * W + 2 * w2;
+        int64_t co[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int ch = by_wavelet ? k * C + c : 4 * c + k;
+            co[k] = (((int64_t)b * 4 * C + ch) * H2 + h2) * W2 + w2;
+        }
+        if constexpr (!UP) {
+            const float2 r0 = __ldg(reinterpret_cast<const float2*>(src + fine));
+            const float2 r1 = __ldg(reinterpret_cast<const float2*>(src + fine + W));
+            const float a = r0.x, bb = r0.y, cc = r1.x, d = r1.y;
+            dst[co[0]] = fac * (a + bb + cc + d);
+            dst[co[1]] = fac * (a - bb + cc - d);
+            dst[co[2]] = fac * (a + bb - cc - d);
+            dst[co[3]] = fac * (a - bb - cc + d);
+        } else {
+            const float y0 = fac * __ldg(src + co[0]), y1 = fac * __ldg(src + co[1]);
+            const float y2 = fac * __ldg(src + co[2]), y3 = fac * __ldg(src + co[3]);
+            float2 r0, r1;
+            r0.x = y0 + y1 + y2 + y3;
+            r0.y = y0 - y1 + y2 - y3;
+            r1.x = y0 + y1 - y2 - y3;
+            r1.y = y0 - y1 - y2 + y3;
+            *reinterpret_cast<float2*>(dst + fine) = r0;
+            *reinterpret_cast<float2*>(dst + fine + W) = r1;
+        }
+    }
+}
+
+static int haar2d_launch(bool up, const float* src, float* dst, int B, int C, int H, int W, int obw, float fac,
+                         cudaStream_t st) {
+    // (C,H,W) always describe the FINE tensor.
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || (H & 1) || (W & 1)) {
+        set_error("haar2d: H and W must be even (got %dx%d)", H, W);
+        return CWFA_EINVAL;
+    }
+    const int64_t total = (int64_t)B * C * (H / 2) * (W / 2);
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    if (up) haar2d_kernel<true><<<blocks, 256, 0, st>>>(src, dst, B, C, H / 2, W / 2, obw, fac);
+    else haar2d_kernel<false><<<blocks, 256, 0, st>>>(src, dst, B, C, H / 2, W / 2, obw, fac);
+    return check_launch("haar2d");
+}
+extern "C" int cwfa_haar2d_down(const float* x, float* y, int B, int C, int H, int W, int obw, float fac,
+                                void* stream) {
+    return haar2d_launch(false, x, y, B, C, H, W, obw, fac, (cudaStream_t)stream);
+}
+extern "C" int cwfa_haar2d_up(const float* y, float* x, int B, int C, int H, int W, int obw, float fac,
+                              void* stream) {
+    return haar2d_launch(true, y, x, B, C, H, W, obw, fac, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------
+// K4: permutations (gather along one axis)
+// ------------------------------------------------------------------------------------------
+template <int AXIS, int VEC>
+__global__ void __launch_bounds__(256) permute_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                      const int32_t* __restrict__ perm, int B, int C, int H, int W) {
+    const int Wv = W / VEC;
+    const int64_t total = (int64_t)B * C * H * Wv;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int w = (int)(idx % Wv) * VEC;
+        const int h = (int)((idx / Wv) % H);
+        const int c = (int)((idx / ((int64_t)Wv * H)) % C);
+        const int b = (int)(idx / ((int64_t)Wv * H * C));
+        int sc = c, sh = h, sw = w;
+        if (AXIS == 1) sc = __ldg(perm + c);
+        if (AXIS == 2) sh = __ldg(perm + h);
+        if (AXIS == 3) sw = __ldg(perm + w);
+        const int64_t so = (((int64_t)b * C + sc) * H + sh) * W + sw;
+        const int64_t dofs = (((int64_t)b * C + c) * H + h) * W + w;
+        if constexpr (VEC == 4) {
+            *reinterpret_cast<float4*>(y + dofs) = __ldg(reinterpret_cast<const float4*>(x + so));
+        } else {
+            y[dofs] = __ldg(x + so);
+        }
+    }
+}
+
+extern "C" int cwfa_permute(const float* x, float* y, const int32_t* perm, int axis, int B, int C, int H, int W,
+                            void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (axis < 1 || axis > 3 || B <= 0 || C <= 0 || H <= 0 || W <= 0) { set_error("permute: bad args"); return CWFA_EINVAL; }
+    const bool vec = axis != 3 && (W % 4 == 0) && aligned16(x) && aligned16(y);
+    const int64_t total = (int64_t)B * C * H * (vec ? W / 4 : W);
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    if (axis == 1) {
+        if (vec) permute_kernel<1, 4><<<blocks, 256, 0, st>>>(x, y, perm, B, C, H, W);
+        else permute_kernel<1, 1><<<blocks, 256, 0, st>>>(x, y, perm, B, C, H, W);
+    } else if (axis == 2) {
+        if (vec) permute_kernel<2, 4><<<blocks, 256, 0, st>>>(x, y, perm, B, C, H, W);
+        else permute_kernel<2, 1><<<blocks, 256, 0, st>>>(x, y, perm, B, C, H, W);
+    } else {
+        permute_kernel<3, 1><<<blocks, 256, 0, st>>>(x, y, perm, B, C, H, W);
+    }
+    return check_launch("permute");
+}
+
+// ------------------------------------------------------------------------------------------
+// K3: affine coupling + per-sample log-det (+ sum of squares).  Deterministic two-stage sum.
+// ------------------------------------------------------------------------------------------
+constexpr int kAffineBlocks = kNumSMs * 2;   // blocks per sample
+
+template <int VEC, bool INV>
+__global__ void __launch_bounds__(256) affine_kernel(const float* __restrict__ x, const float* __restrict__ a_s,
+                                                     const float* __restrict__ a_t, float* __restrict__ y,
+                                                     float* __restrict__ ws, int ch, int64_t P, int64_t ld_s,
+                                                     int64_t ld_t, float kk, float t_scale, int raw) {
+    const int b = blockIdx.y;
+    const int64_t n = (int64_t)ch * P;           // elements of this sample
+    const float* xs = x ? x + (int64_t)b * n : nullptr;
+    const float* ss = a_s + (int64_t)b * ld_s;
+    const float* ts = a_t + (int64_t)b * ld_t;
+    float* ys = y + (int64_t)b * n;
+    float sum_s = 0.f, sum_q = 0.f;
+    for (int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * VEC; i < n;
+         i += (int64_t)gridDim.x * blockDim.x * VEC) {
+        float xv[VEC], sv[VEC], tv[VEC], yv[VEC];
+        if constexpr (VEC == 4) {
+            const float4 s4 = __ldg(reinterpret_cast<const float4*>(ss + i));
+            const float4 t4 = __ldg(reinterpret_cast<const float4*>(ts + i));
+            sv[0] = s4.x; sv[1] = s4.y; sv[2] = s4.z; sv[3] = s4.w;
+            tv[0] = t4.x; tv[1] = t4.y; tv[2] = t4.z; tv[3] = t4.w;
+            if (xs) {
+                const float4 x4 = __ldg(reinterpret_cast<const float4*>(xs + i));
+                xv[0] = x4.x; xv[1] = x4.y; xv[2] = x4.z; xv[3] = x4.w;
+            } else {
+                xv[0] = xv[1] = xv[2] = xv[3] = 0.f;
+            }
+        } else {
+            sv[0] = ss[i]; tv[0] = ts[i]; xv[0] = xs ? xs[i] : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+            const float s = raw ? sv[k] : kk * atanf(sv[k]);
+            const float t = t_scale * tv[k];
+            sum_s += s;
+            yv[k] = INV ? (xv[k] - t) * expf(-s) : expf(s) * xv[k] + t;
+            sum_q += yv[k] * yv[k];
+        }
+        if constexpr (VEC == 4) {
+            *reinterpret_cast<float4*>(ys + i) = make_float4(yv[0], yv[1], yv[2], yv[3]);
+        } else {
+            ys[i] = yv[0];
+        }
+    }
+    block_sum2(sum_s, sum_q);
+    if (threadIdx.x == 0) {
+        ws[((int64_t)b * gridDim.x + blockIdx.x) * 2 + 0] = INV ? -sum_s : sum_s;
+        ws[((int64_t)b * gridDim.x + blockIdx.x) * 2 + 1] = sum_q;
+    }
+}
+
+__global__ void affine_finalize_kernel(const float* __restrict__ ws, float* __restrict__ logdet,
+                                       float* __restrict__ sumsq, int nblocks) {
+    // one warp per sample; fixed summation order -> bit-reproducible
+    const int b = blockIdx.x;
+    double s = 0.0, q = 0.0;
+    for (int i = threadIdx.x; i < nblocks; i += 32) {
+        s += (double)ws[((int64_t)b * nblocks + i) * 2 + 0];
+        q += (double)ws[((int64_t)b * nblocks + i) * 2 + 1];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    if (threadIdx.x == 0) {
+        logdet[b] = (float)s;
+        if (sumsq) sumsq[b] = (float)q;
+    }
+}
+
+extern "C" int cwfa_affine_workspace_blocks(void) { return kAffineBlocks; }
+
+extern "C" int cwfa_affine(const float* x, const float* a_s, const float* a_t, float* y, float* logdet, float* sumsq,
+                           float* workspace, int B, int ch, int64_t P, int64_t ld_s, int64_t ld_t, float clamp,
+                           float k_atan, float t_scale, int flags, void* stream) {
+    const int inverse = flags & 1, raw = (flags >> 1) & 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (B <= 0 || ch <= 0 || P <= 0 || !a_s || !a_t || !y || !logdet || !workspace) {
+        set_error("affine: bad args");
+        return CWFA_EINVAL;
+    }
+    if (!x && !inverse) { set_error("affine: x may be NULL only in inverse mode"); return CWFA_EINVAL; }
+    const int64_t n = (int64_t)ch * P;
+    const bool vec = (n % 4 == 0) && (ld_s % 4 == 0) && (ld_t % 4 == 0) && aligned16(a_s) && aligned16(a_t) &&
+                     aligned16(y) && (!x || aligned16(x));
+    dim3 grid(kAffineBlocks, B);
+    const float kk = clamp * k_atan;
+    if (vec) {
+        if (inverse) affine_kernel<4, true><<<grid, 256, 0, st>>>(x, a_s, a_t, y, workspace, ch, P, ld_s, ld_t, kk, t_scale, raw);
+        else affine_kernel<4, false><<<grid, 256, 0, st>>>(x, a_s, a_t, y, workspace, ch, P, ld_s, ld_t, kk, t_scale, raw);
+    } else {
+        if (inverse) affine_kernel<1, true><<<grid, 256, 0, st>>>(x, a_s, a_t, y, workspace, ch, P, ld_s, ld_t, kk, t_scale, raw);
+        else affine_kernel<1, false><<<grid, 256, 0, st>>>(x, a_s, a_t, y, workspace, ch, P, ld_s, ld_t, kk, t_scale, raw);
+    }
+    int rc = check_launch("affine");
+    if (rc) return rc;
+    affine_finalize_kernel<<<B, 32, 0, st>>>(workspace, logdet, sumsq, kAffineBlocks);
+    return check_launch("affine_finalize");
+}
+
+// ------------------------------------------------------------------------------------------
+// Normalisation / pooling helpers (LRNN)
+// ------------------------------------------------------------------------------------------
+constexpr int kStatsBlocks = 32;   // blocks per channel
+
+__global__ void __launch_bounds__(256) channel_stats_kernel(const float* __restrict__ x, float* __restrict__ ws, int N,
+                                                            int C, int64_t P) {
+    const int c = blockIdx.y;
+    float s = 0.f, q = 0.f;
+    const int64_t per = (int64_t)N * P;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < per; i += (int64_t)gridDim.x * blockDim.x) {
+        const int n = (int)(i / P);
+        const int64_t p = i % P;
+        const float v = __ldg(x + ((int64_t)n * C + c) * P + p);
+        s += v;
+        q += v * v;
+    }
+    block_sum2(s, q);
+    if (threadIdx.x == 0) {
+        ws[((int64_t)c * gridDim.x + blockIdx.x) * 2 + 0] = s;
+        ws[((int64_t)c * gridDim.x + blockIdx.x) * 2 + 1] = q;
+    }
+}
+__global__ void stats_finalize_kernel(const float* __restrict__ ws, float* __restrict__ stats, int C, int nblocks) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s = 0.0, q = 0.0;
+    for (int i = 0; i < nblocks; ++i) {
+        s += (double)ws[((int64_t)c * nblocks + i) * 2 + 0];
+        q += (double)ws[((int64_t)c * nblocks + i) * 2 + 1];
+    }
+    stats[c] = (float)s;
+    stats[C + c] = (float)q;
+}
+extern "C" int cwfa_stats_workspace_blocks(void) { return kStatsBlocks; }
+extern "C" int cwfa_channel_stats_f32(const float* x, float* stats, float* workspace, int N, int C, int64_t P,
+                                      void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N <= 0 || C <= 0 || P <= 0) { set_error("channel_stats: bad shape"); return CWFA_EINVAL; }
+    channel_stats_kernel<<<dim3(kStatsBlocks, C), 256, 0, st>>>(x, workspace, N, C, P);
+    int rc = check_launch("channel_stats");
+    if (rc) return rc;
+    stats_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(workspace, stats, C, kStatsBlocks);
+    return check_launch("stats_finalize");
+}
+
+__global__ void bn_finalize_kernel(const float* __restrict__ stats, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ scale, float* __restrict__ shift,
+                                   int C, double count, float eps) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const double mean = (double)stats[c] / count;
+    double var = (double)stats[C + c] / count - mean * mean;   // biased, as BatchNorm normalises with
+    if (var < 0.0) var = 0.0;
+    const double sc = (double)gamma[c] / sqrt(var + (double)eps);
+    scale[c] = (float)sc;
+    shift[c] = (float)((double)beta[c] - mean * sc);
+}
+extern "C" int cwfa_bn_finalize_f32(const float* stats, const float* gamma, const float* beta, float* scale,
+                                    float* shift, int C, double count, float eps, void* stream) {
+    bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(stats, gamma, beta, scale, shift, C, count, eps);
+    return check_launch("bn_finalize");
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256) scale_shift_kernel(const float* __restrict__ x, const float* __restrict__ scale,
+                                                          const float* __restrict__ shift, float* __restrict__ y,
+                                                          int64_t NC, int C, int64_t P) {
+    const int64_t Pv = P / VEC;
+    const int64_t total = NC * Pv;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t nc = idx / Pv;
+        const int c = (int)(nc % C);
+        const float sc = __ldg(scale + c), sh = __ldg(shift + c);
+        const int64_t o = nc * P + (idx % Pv) * VEC;
+        if constexpr (VEC == 4) {
+            float4 v = __ldg(reinterpret_cast<const float4*>(x + o));
+            v.x = v.x * sc + sh; v.y = v.y * sc + sh; v.z = v.z * sc + sh; v.w = v.w * sc + sh;
+            *reinterpret_cast<float4*>(y + o) = v;
+        } else {
+            y[o] = x[o] * sc + sh;
+        }
+    }
+}
+extern "C" int cwfa_scale_shift_f32(const float* x, const float* scale, const float* shift, float* y, int N, int C,
+                                    int64_t P, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool vec = (P % 4 == 0) && aligned16(x) && aligned16(y);
+    const int64_t total = (int64_t)N * C * (vec ? P / 4 : P);
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    if (vec) scale_shift_kernel<4><<<blocks, 256, 0, st>>>(x, scale, shift, y, (int64_t)N * C, C, P);
+    else scale_shift_kernel<1><<<blocks, 256, 0, st>>>(x, scale, shift, y, (int64_t)N * C, C, P);
+    return check_launch("scale_shift");
+}
+
+__global__ void __launch_bounds__(256) maxpool2_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                       int64_t NC, int H2, int W2) {
+    const int64_t total = NC * H2 * W2;
+    const int W = 2 * W2;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int w2 = (int)(idx % W2);
+        const int h2 = (int)((idx / W2) % H2);
+        const int64_t nc = idx / ((int64_t)W2 * H2);
+        const float* p = x + (nc * (2 * H2) + 2 * h2) * W + 2 * w2;
+        const float2 a = __ldg(reinterpret_cast<const float2*>(p));
+        const float2 b = __ldg(reinterpret_cast<const float2*>(p + W));
+        y[idx] = fmaxf(fmaxf(a.x, a.y), fmaxf(b.x, b.y));
+    }
+}
+extern "C" int cwfa_maxpool2_f32(const float* x, float* y, int N, int C, int H, int W, void* stream) {
+    if ((H & 1) || (W & 1)) { set_error("maxpool2: odd size"); return CWFA_EINVAL; }
+    const int64_t total = (int64_t)N * C * (H / 2) * (W / 2);
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    maxpool2_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, y, (int64_t)N * C, H / 2, W / 2);
+    return check_launch("maxpool2");
+}
+
+// LayerNorm over (C,H,W): stage 1 partial sums, stage 2 normalise with element-wise affine.
+constexpr int kLNBlocks = kNumSMs * 2;
+__global__ void __launch_bounds__(256) ln_stats_kernel(const float* __restrict__ x, float* __restrict__ ws, int64_t n) {
+    const int b = blockIdx.y;
+    const float* xs = x + (int64_t)b * n;
+    float s = 0.f, q = 0.f;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float v = __ldg(xs + i);
+        s += v;
+        q += v * v;
+    }
+    block_sum2(s, q);
+    if (threadIdx.x == 0) {
+        ws[((int64_t)b * gridDim.x + blockIdx.x) * 2 + 0] = s;
+        ws[((int64_t)b * gridDim.x + blockIdx.x) * 2 + 1] = q;
+    }
+}
+__global__ void __launch_bounds__(256) ln_apply_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, float* __restrict__ y,
+                                                       const float* __restrict__ ws, int64_t n, float eps) {
+    const int b = blockIdx.y;
+    __shared__ float s_mean, s_rstd;
+    if (threadIdx.x == 0) {
+        double s = 0.0, q = 0.0;
+        for (int i = 0; i < kLNBlocks; ++i) {
+            s += (double)ws[((int64_t)b * kLNBlocks + i) * 2 + 0];
+            q += (double)ws[((int64_t)b * kLNBlocks + i) * 2 + 1];
+        }
+        const double mean = s / (double)n;
+        double var = q / (double)n - mean * mean;
+        if (var < 0.0) var = 0.0;
+        s_mean = (float)mean;
+        s_rstd = (float)(1.0 / sqrt(var + (double)eps));
+    }
+    __syncthreads();
+    const float mean = s_mean, rstd = s_rstd;
+    const float* xs = x + (int64_t)b * n;
+    float* ys = y + (int64_t)b * n;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        ys[i] = (__ldg(xs + i) - mean) * rstd * __ldg(gamma + i) + __ldg(beta + i);
+}
+extern "C" int cwfa_layernorm_chw_f32(const float* x, const float* gamma, const float* beta, float* y,
+                                      float* workspace, int N, int64_t CHW, float eps, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N <= 0 || CHW <= 0) { set_error("layernorm: bad shape"); return CWFA_EINVAL; }
+    ln_stats_kernel<<<dim3(kLNBlocks, N), 256, 0, st>>>(x, workspace, CHW);
+    int rc = check_launch("ln_stats");
+    if (rc) return rc;
+    ln_apply_kernel<<<dim3(kLNBlocks, N), 256, 0, st>>>(x, gamma, beta, y, workspace, CHW, eps);
+    return check_launch("ln_apply");
+}
+
+__global__ void __launch_bounds__(256) gate_add_kernel(float* __restrict__ x, const float* __restrict__ m,
+                                                       const float* __restrict__ g, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        x[i] += m[i] * 2.f * (g[i] - 0.5f);
+}
+extern "C" int cwfa_gate_add_f32(float* x, const float* m, const float* g, int64_t n, void* stream) {
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    gate_add_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, m, g, n);
+    return check_launch("gate_add");
+}
+extern "C" int cwfa_layernorm_workspace_blocks(void) { return kLNBlocks; }

@@ -1,0 +1,433 @@
+"""Invertible modules of the CWFA path with the FrEIA ``InvertibleModule`` contract.
+
+Contract (FrEIA/modules/base.py:7-112): constructed as
+``module(dims_in, dims_c=None, **args)`` with shapes that exclude the batch axis;
+``forward(x_or_z: tuple, c: tuple = None, rev=False, jac=True) -> (sequence_of_tensors, jac)``
+where ``jac`` is a ``(B,)`` tensor or a python number, ``+J`` forward and ``-J`` in reverse;
+``output_dims(input_dims)`` for shape inference.  Inputs are never mutated.
+
+Every ``forward`` launches hand-written CUDA kernels through the C ABI (cwfa_b200/ops.py);
+tensors must live on a CUDA device.  ``state_dict`` keys and shapes equal the reference's
+(``perm`` / ``perm_inv`` are ``nn.Parameter(LongTensor, requires_grad=False)``;
+sub-networks keep the unused ``block_grad_up`` / ``block1|block12`` / ``block7|block72``
+weights), so reference checkpoints load unchanged.
+"""
+from __future__ import annotations
+
+import math
+import warnings
+from typing import Callable, Iterable, List, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops
+
+
+class InvertibleModule(nn.Module):
+    """Base class (FrEIA/modules/base.py:7-112)."""
+
+    def __init__(self, dims_in: Iterable[Tuple[int]], dims_c: Iterable[Tuple[int]] = None):
+        super().__init__()
+        self.dims_in = list(dims_in)
+        self.dims_c = [] if dims_c is None else list(dims_c)
+
+    def forward(self, x_or_z, c=None, rev: bool = False, jac: bool = True):
+        raise NotImplementedError(f"{self.__class__.__name__} does not provide forward(...) method")
+
+    def log_jacobian(self, *args, **kwargs):
+        raise DeprecationWarning("module.log_jacobian(...) is deprecated. module.forward(..., jac=True) "
+                                 "returns a tuple (out, jacobian) now.")
+
+    def output_dims(self, input_dims: List[Tuple[int]]) -> List[Tuple[int]]:
+        raise NotImplementedError(f"{self.__class__.__name__} does not provide output_dims(...)")
+
+
+# ---------------------------------------------------------------------------------------------
+# Haar transforms
+# ---------------------------------------------------------------------------------------------
+class HaarTransform1D(InvertibleModule):
+    """Depth-wise (channel-axis) Haar DWT: lo -> first half of the channels, hi -> second half.
+    Shape is unchanged.  Reference: INN_utils.py:126-174 (``order_by_wavelet`` is accepted and
+    ignored there too; ``rebalance`` only enters the reported log-det, :135-140,152)."""
+
+    def __init__(self, dims_in, dims_c=None, order_by_wavelet: bool = False, rebalance: float = 1.0):
+        super().__init__(dims_in, dims_c)
+        self.fac_fwd = 0.5 * rebalance
+        self.fac_rev = 0.5 / rebalance
+        self.jac_fwd = (np.log(16.0) + 4 * np.log(self.fac_fwd)) / 4.0
+        self.jac_rev = (np.log(16.0) + 4 * np.log(self.fac_rev)) / 4.0
+
+    def forward(self, x_in, c=None, jac=True, rev=False):
+        x = x_in[0]
+        ndims = x[0].numel()
+        if not rev:
+            return (ops.haar1d_forward(x),), ndims * self.jac_fwd
+        return (ops.haar1d_inverse(x),), -ndims * self.jac_rev
+
+    def output_dims(self, input_dims):
+        if len(input_dims) != 1:
+            raise ValueError("HaarDownsampling must have exactly 1 input")
+        if len(input_dims[0]) != 3:
+            raise ValueError("HaarDownsampling can only transform 2D images of the shape CxWxH (channels, width, height)")
+        c, w, h = input_dims[0]
+        return ((c, w, h),)
+
+
+class HaarDownsampling(InvertibleModule):
+    """FrEIA 2-D Haar: (C,H,W) -> (4C,H/2,W/2).  FrEIA/modules/reshapes.py:191-316.
+    Unlike the reference (reshapes.py:297) the reverse pass does not scale its input in place."""
+
+    def __init__(self, dims_in, dims_c=None, order_by_wavelet: bool = False, rebalance: float = 1.0):
+        super().__init__(dims_in, dims_c)
+        if rebalance == 0:
+            raise ValueError("'rebalance' argument must be != 0.")
+        self.in_channels = dims_in[0][0]
+        self.fac_fwd = 0.5 * rebalance
+        self.jac_fwd = (np.log(16.0) + 4 * np.log(self.fac_fwd)) / 4.0
+        self.fac_rev = 0.5 / rebalance
+        self.jac_rev = (np.log(16.0) + 4 * np.log(self.fac_rev)) / 4.0
+        # kept for state_dict parity with the reference (a frozen nn.Parameter there, :240-253)
+        w = torch.ones(4, 1, 2, 2)
+        w[1, 0, 0, 1] = w[1, 0, 1, 1] = -1
+        w[2, 0, 1, 0] = w[2, 0, 1, 1] = -1
+        w[3, 0, 1, 0] = w[3, 0, 0, 1] = -1
+        self.haar_weights = nn.Parameter(torch.cat([w] * self.in_channels, 0), requires_grad=False)
+        self.permute = order_by_wavelet
+
+    def forward(self, x, c=None, jac=True, rev=False):
+        inp = x[0]
+        ndims = inp[0].numel()
+        if not rev:
+            return (ops.haar2d_down(inp, self.permute, self.fac_fwd),), ndims * self.jac_fwd
+        return (ops.haar2d_up(inp, self.permute, self.fac_rev),), ndims * self.jac_rev
+
+    def output_dims(self, input_dims):
+        if len(input_dims) != 1:
+            raise ValueError("HaarDownsampling must have exactly 1 input")
+        if len(input_dims[0]) != 3:
+            raise ValueError("HaarDownsampling can only transform 2D images of the shape CxWxH (channels, width, height)")
+        c, w, h = input_dims[0]
+        c2, w2, h2 = c * 4, w // 2, h // 2
+        if c * h * w != c2 * h2 * w2:
+            raise ValueError("Input cannot be cleanly reshaped, most likely because the input height or width are an odd number")
+        return ((c2, w2, h2),)
+
+
+class HaarUpsampling(HaarDownsampling):
+    """Inverse of HaarDownsampling: (4C,H,W) -> (C,2H,2W).  reshapes.py:319-374."""
+
+    def __init__(self, dims_in, dims_c=None, order_by_wavelet: bool = False, rebalance: float = 1.0):
+        inv_shape = self.output_dims(dims_in)
+        super().__init__(inv_shape, dims_c, order_by_wavelet, rebalance)
+
+    def forward(self, x, c=None, jac=True, rev=False):
+        return super().forward(x, c=None, rev=not rev)
+
+    def output_dims(self, input_dims):
+        if len(input_dims) != 1:
+            raise ValueError("i-revnet downsampling must have exactly 1 input")
+        if len(input_dims[0]) != 3:
+            raise ValueError("i-revnet downsampling can only tranform 2d images of the shape cxwxh (channels, width, height)")
+        c, w, h = input_dims[0]
+        c2, w2, h2 = c // 4, w * 2, h * 2
+        if c * h * w != c2 * h2 * w2:
+            raise ValueError("input cannot be cleanly reshaped, most likely because the input height or width are an odd number")
+        return ((c2, w2, h2),)
+
+
+# ---------------------------------------------------------------------------------------------
+# Split / Concat
+# ---------------------------------------------------------------------------------------------
+class Split(InvertibleModule):
+    """Invertible split along one non-batch axis (FrEIA/modules/graph_topology.py:10-89).
+    Forward returns views; reverse concatenates."""
+
+    def __init__(self, dims_in, section_sizes=None, n_sections: int = 2, dim: int = 0):
+        super().__init__(dims_in)
+        assert len(dims_in) == 1, "Split layer takes exactly one input tensor"
+        assert len(dims_in[0]) >= dim, "Split dimension index out of range"
+        self.dim = dim
+        l_dim = dims_in[0][dim]
+        if section_sizes is None:
+            assert 2 <= n_sections, "'n_sections' must be a least 2"
+            if l_dim % n_sections != 0:
+                warnings.warn("Split will create sections of unequal size")
+            self.split_size_or_sections = ([l_dim // n_sections + 1] * (l_dim % n_sections)
+                                           + [l_dim // n_sections] * (n_sections - l_dim % n_sections))
+        else:
+            if isinstance(section_sizes, int):
+                assert section_sizes < l_dim, "'section_sizes' too large"
+            else:
+                assert isinstance(section_sizes, (list, tuple)), "'section_sizes' must be either int or list/tuple of int"
+                assert sum(section_sizes) <= l_dim, "'section_sizes' too large"
+                if sum(section_sizes) < l_dim:
+                    warnings.warn("'section_sizes' too small, adding additional section")
+                    section_sizes = list(section_sizes) + [l_dim - sum(section_sizes)]
+            self.split_size_or_sections = section_sizes
+
+    def forward(self, x, rev=False, jac=True):
+        if rev:
+            return [torch.cat(list(x), dim=self.dim + 1)], 0
+        return torch.split(x[0], self.split_size_or_sections, dim=self.dim + 1), 0
+
+    def output_dims(self, input_dims):
+        assert len(input_dims) == 1, "Split layer takes exactly one input tensor"
+        sizes = self.split_size_or_sections
+        if isinstance(sizes, int):
+            l_dim = input_dims[0][self.dim]
+            sizes = [sizes] * (l_dim // sizes) + ([l_dim % sizes] if l_dim % sizes else [])
+        return [tuple(s if j == self.dim else input_dims[0][j] for j in range(len(input_dims[0]))) for s in sizes]
+
+
+class Concat(InvertibleModule):
+    """Invertible concatenation (FrEIA/modules/graph_topology.py:92-152)."""
+
+    def __init__(self, dims_in, dim: int = 0):
+        super().__init__(dims_in)
+        assert len(dims_in) > 1, "Concatenation only makes sense for multiple inputs"
+        assert len(dims_in[0]) >= dim, "Merge dimension index out of range"
+        assert all(len(dims_in[i]) == len(dims_in[0]) for i in range(len(dims_in))), \
+            "All input tensors must have same number of dimensions"
+        assert all(dims_in[i][j] == dims_in[0][j] for i in range(len(dims_in))
+                   for j in range(len(dims_in[i])) if j != dim), \
+            "All input tensor dimensions except merge dimension must be identical"
+        self.dim = dim
+        self.split_size_or_sections = [dims_in[i][dim] for i in range(len(dims_in))]
+
+    def forward(self, x, rev=False, jac=True):
+        if rev:
+            return torch.split(x[0], self.split_size_or_sections, dim=self.dim + 1), 0
+        return [torch.cat(list(x), dim=self.dim + 1)], 0
+
+    def output_dims(self, input_dims):
+        assert len(input_dims) > 1, "Concatenation only makes sense for multiple inputs"
+        out = list(input_dims[0])
+        out[self.dim] = sum(d[self.dim] for d in input_dims)
+        return [tuple(out)]
+
+
+# ---------------------------------------------------------------------------------------------
+# Permutations
+# ---------------------------------------------------------------------------------------------
+def _make_perm(n: int):
+    perm = np.random.permutation(n)
+    inv = np.zeros_like(perm)
+    inv[perm] = np.arange(n)
+    return (nn.Parameter(torch.LongTensor(perm), requires_grad=False),
+            nn.Parameter(torch.LongTensor(inv), requires_grad=False))
+
+
+class PermuteRandom(InvertibleModule):
+    """Fixed random channel permutation: y = x[:, perm].  fixed_transforms.py:11-46.
+    numpy's global RNG is (re)seeded exactly as the reference does so that the same ``seed``
+    yields the same permutation."""
+
+    def __init__(self, dims_in, dims_c=None, seed: Union[int, None] = None):
+        super().__init__(dims_in, dims_c)
+        self.in_channels = dims_in[0][0]
+        if seed is not None:
+            np.random.seed(seed)
+        self.perm, self.perm_inv = _make_perm(self.in_channels)
+
+    def forward(self, x, rev=False, jac=True):
+        return [ops.permute(x[0], self.perm_inv if rev else self.perm, 1)], 0.0
+
+    def output_dims(self, input_dims):
+        if len(input_dims) != 1:
+            raise ValueError(f"{self.__class__.__name__} can only use 1 input")
+        return input_dims
+
+
+class PermuteDim(InvertibleModule):
+    """Fixed random permutation of rows (tensor dim 2) or columns (dim 3).  INN_utils.py:46-87.
+    As in the reference the axis is drawn from numpy's RNG BEFORE seeding (:61-64) and is not
+    part of ``state_dict``; pass ``axis=2|3`` to pin it (e.g. when loading a checkpoint)."""
+
+    def __init__(self, dims_in, dims_c=None, dims_to_permute=[1, 2], seed: Union[int, None] = None,
+                 axis: Union[int, None] = None):
+        super().__init__(dims_in, dims_c)
+        choices = [[1, 2], [1, 3]]
+        self.in_channels = dims_in[0][0]
+        drawn = choices[np.random.randint(0, len(choices))]
+        self.dims_to_permute = drawn if axis is None else [1, int(axis)]
+        if seed is not None:
+            np.random.seed(seed)
+        self.perm, self.perm_inv = _make_perm(dims_in[0][self.dims_to_permute[1] - 1])
+
+    @property
+    def axis(self) -> int:
+        return int(self.dims_to_permute[1])
+
+    def forward(self, x, rev=False, jac=True):
+        return [ops.permute(x[0], self.perm_inv if rev else self.perm, self.axis)], 0.0
+
+    def output_dims(self, input_dims):
+        if len(input_dims) != 1:
+            raise ValueError(f"{self.__class__.__name__} can only use 1 input")
+        return input_dims
+
+
+# ---------------------------------------------------------------------------------------------
+# Coupling blocks
+# ---------------------------------------------------------------------------------------------
+class _BaseCouplingBlock(InvertibleModule):
+    """Dimension checks, split sizes and the soft clamp (coupling_layers.py:8-121).
+
+    Only ``clamp_activation="ATAN"`` runs in the fused CUDA coupling kernel; other clamp
+    functions are part of upstream FrEIA's API but are not used by CWFA and are rejected."""
+
+    def __init__(self, dims_in, dims_c=[], clamp: float = 2.0, clamp_activation: Union[str, Callable] = "ATAN"):
+        super().__init__(dims_in, dims_c)
+        self.channels = dims_in[0][0]
+        self.ndims = len(dims_in[0])
+        self.split_len1 = self.channels // 2
+        self.split_len2 = self.channels - self.channels // 2
+        self.clamp = clamp
+        assert all(tuple(dims_c[i][1:]) == tuple(dims_in[0][1:]) for i in range(len(dims_c))), \
+            "Dimensions of input and one or more conditions don't agree."
+        self.conditional = len(dims_c) > 0
+        self.condition_length = sum(dims_c[i][0] for i in range(len(dims_c)))
+        if clamp_activation != "ATAN":
+            raise ValueError(f'clamp activation "{clamp_activation}" is not implemented by the CUDA coupling '
+                             'kernel; CWFA uses "ATAN" (coupling_layers.py:52)')
+        self.clamp_activation = clamp_activation
+
+    def output_dims(self, input_dims):
+        if len(input_dims) != 1:
+            raise ValueError("Can only use 1 input")
+        return input_dims
+
+    # ---- shared two-sided driver (coupling_layers.py:62-87) ----
+    def forward(self, x, c=[], rev=False, jac=True):
+        x1, x2 = torch.split(x[0], [self.split_len1, self.split_len2], dim=1)
+        c = list(c) if c is not None else []
+        if not rev:
+            x2_c = torch.cat([x2, *c], 1) if self.conditional else x2
+            y1, j1 = self._coupling1(x1, x2_c)
+            y1_c = torch.cat([y1, *c], 1) if self.conditional else y1
+            y2, j2 = self._coupling2(x2, y1_c)
+        else:
+            x1_c = torch.cat([x1, *c], 1) if self.conditional else x1
+            y2, j2 = self._coupling2(x2, x1_c, rev=True)
+            y2_c = torch.cat([y2, *c], 1) if self.conditional else y2
+            y1, j1 = self._coupling1(x1, y2_c, rev=True)
+        return (torch.cat((y1, y2), 1),), j1 + j2
+
+    def _affine_from(self, x_active, a, n_out, rev, gin=False):
+        s_raw, t = a[:, :n_out], a[:, n_out:]
+        if gin:
+            # volume preserving: s -= mean over channels (coupling_layers.py:361)
+            s = self.clamp * ops.K_ATAN * torch.atan(s_raw)
+            s = s - s.mean(1, keepdim=True)
+            y, _ = ops.affine(x_active, s.contiguous(), t, inverse=rev, clamp=self.clamp, s_is_final=True)
+            return y, 0.0
+        y, j = ops.affine(x_active, s_raw, t, inverse=rev, clamp=self.clamp)
+        return y, j
+
+
+class NICECouplingBlock(_BaseCouplingBlock):
+    """Additive coupling (coupling_layers.py:124-157): the affine kernel with s = 0."""
+
+    def __init__(self, dims_in, dims_c=[], subnet_constructor: Callable = None):
+        super().__init__(dims_in, dims_c, clamp=0.0)
+        self.F = subnet_constructor(self.split_len2 + self.condition_length, self.split_len1)
+        self.G = subnet_constructor(self.split_len1 + self.condition_length, self.split_len2)
+
+    def _coupling1(self, x1, u2, rev=False):
+        t = self.F(u2)
+        y, _ = ops.affine(x1, t, t, inverse=rev, clamp=0.0)
+        return y, 0.0
+
+    def _coupling2(self, x2, u1, rev=False):
+        t = self.G(u1)
+        y, _ = ops.affine(x2, t, t, inverse=rev, clamp=0.0)
+        return y, 0.0
+
+
+class RNVPCouplingBlock(_BaseCouplingBlock):
+    """RealNVP-style block with four sub-networks (coupling_layers.py:160-229)."""
+
+    def __init__(self, dims_in, dims_c=[], subnet_constructor: Callable = None, clamp: float = 2.0,
+                 clamp_activation: Union[str, Callable] = "ATAN"):
+        super().__init__(dims_in, dims_c, clamp, clamp_activation)
+        self.subnet_s1 = subnet_constructor(self.split_len1 + self.condition_length, self.split_len2)
+        self.subnet_t1 = subnet_constructor(self.split_len1 + self.condition_length, self.split_len2)
+        self.subnet_s2 = subnet_constructor(self.split_len2 + self.condition_length, self.split_len1)
+        self.subnet_t2 = subnet_constructor(self.split_len2 + self.condition_length, self.split_len1)
+
+    def _coupling1(self, x1, u2, rev=False):
+        return ops.affine(x1, self.subnet_s2(u2), self.subnet_t2(u2), inverse=rev, clamp=self.clamp)
+
+    def _coupling2(self, x2, u1, rev=False):
+        return ops.affine(x2, self.subnet_s1(u1), self.subnet_t1(u1), inverse=rev, clamp=self.clamp)
+
+
+class GLOWCouplingBlock(_BaseCouplingBlock):
+    """GLOW-style block: one sub-network predicts [s, t] jointly (coupling_layers.py:232-302)."""
+
+    def __init__(self, dims_in, dims_c=[], subnet_constructor: Callable = None, clamp: float = 2.0,
+                 clamp_activation: Union[str, Callable] = "ATAN"):
+        super().__init__(dims_in, dims_c, clamp, clamp_activation)
+        self.subnet1 = subnet_constructor(self.split_len1 + self.condition_length, self.split_len2 * 2)
+        self.subnet2 = subnet_constructor(self.split_len2 + self.condition_length, self.split_len1 * 2)
+        self._gin = False
+
+    def _coupling1(self, x1, u2, rev=False):
+        return self._affine_from(x1, self.subnet2(u2), self.split_len1, rev, self._gin)
+
+    def _coupling2(self, x2, u1, rev=False):
+        return self._affine_from(x2, self.subnet1(u1), self.split_len2, rev, self._gin)
+
+
+class GINCouplingBlock(GLOWCouplingBlock):
+    """Volume-preserving GLOW variant (coupling_layers.py:305-381)."""
+
+    def __init__(self, dims_in, dims_c=[], subnet_constructor: Callable = None, clamp: float = 2.0,
+                 clamp_activation: Union[str, Callable] = "ATAN"):
+        super().__init__(dims_in, dims_c, subnet_constructor, clamp, clamp_activation)
+        self._gin = True
+
+
+class AffineCouplingOneSided(_BaseCouplingBlock):
+    """Half of a GLOW block (coupling_layers.py:384-437)."""
+
+    def __init__(self, dims_in, dims_c=[], subnet_constructor: Callable = None, clamp: float = 2.0,
+                 clamp_activation: Union[str, Callable] = "ATAN"):
+        super().__init__(dims_in, dims_c, clamp, clamp_activation)
+        self.subnet = subnet_constructor(self.split_len1 + self.condition_length, 2 * self.split_len2)
+
+    def forward(self, x, c=[], rev=False, jac=True):
+        x1, x2 = torch.split(x[0], [self.split_len1, self.split_len2], dim=1)
+        x1_c = torch.cat([x1, *c], 1) if self.conditional else x1
+        y2, j = self._affine_from(x2, self.subnet(x1_c), self.split_len2, rev)
+        return (torch.cat((x1, y2), 1),), j
+
+
+class ConditionalAffineTransform(_BaseCouplingBlock):
+    """CWFA's default block ("CAT"): s, t predicted from the CONDITION only and applied to the
+    whole input (coupling_layers.py:440-500).  ``y = exp(s) x + t`` / ``y = (x - t) exp(-s)``,
+    ``s = clamp * 0.636 * atan(a[:, :ch])``, log-det = +-sum(s) per sample -- one fused kernel.
+
+    When the sub-network is CWFA's ``_first`` variant (t = -meanvol/sqrt2, networks.py:653-671)
+    the shift half is never materialised: the kernel reads the condition with t_scale=-1/sqrt2.
+    """
+
+    def __init__(self, dims_in, dims_c=[], subnet_constructor: Callable = None, clamp: float = 2.0,
+                 clamp_activation: Union[str, Callable] = "ATAN"):
+        super().__init__(dims_in, dims_c, clamp, clamp_activation)
+        if not self.conditional:
+            raise ValueError("ConditionalAffineTransform must have a condition")
+        self.subnet = subnet_constructor(self.condition_length, 2 * self.channels)
+
+    def forward(self, x, c=[], rev=False, jac=True):
+        cond = torch.cat(list(c), 1) if len(c) > 1 else c[0]
+        split_fn = getattr(self.subnet, "forward_split", None)
+        if split_fn is not None:
+            a_s, a_t, t_scale = split_fn(cond)
+        else:
+            a = self.subnet(cond)
+            a_s, a_t, t_scale = a[:, :self.channels], a[:, self.channels:], 1.0
+        y, j = ops.affine(x[0], a_s, a_t, inverse=rev, clamp=self.clamp, t_scale=t_scale)
+        return (y,), j

@@ -1,0 +1,287 @@
+"""Tensor-level wrappers over the C ABI (torch is used only for device memory and streams).
+
+Every function takes contiguous fp32 CUDA tensors in the reference's NCHW layout, launches
+on the CURRENT torch stream and returns freshly allocated tensors.  Non-CUDA tensors are
+rejected: there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+ACT_NONE, ACT_ELU, ACT_PRELU, ACT_RELU, ACT_GELU, ACT_SIGMOID = range(6)
+
+CLAMP_DEFAULT = 2.0
+K_ATAN = 0.636          # FrEIA/modules/coupling_layers.py:52
+
+
+def _ck(t: torch.Tensor, name: str = "tensor", dtype=torch.float32) -> torch.Tensor:
+    if not torch.is_tensor(t):
+        raise TypeError(f"{name}: expected a tensor")
+    if not t.is_cuda:
+        raise RuntimeError(f"cwfa_b200: {name} is on {t.device}; the CUDA kernels are the only "
+                           "implementation (no CPU fallback)")
+    if t.dtype != dtype:
+        t = t.to(dtype)
+    return t.contiguous()
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+_perm_cache = {}
+
+
+def perm_i32(perm: torch.Tensor, device) -> torch.Tensor:
+    """int32 device copy of a LongTensor permutation (cached per version)."""
+    key = (perm.data_ptr(), str(device), perm._version, perm.numel())
+    hit = _perm_cache.get(key)
+    if hit is None:
+        if len(_perm_cache) > 4096:
+            _perm_cache.clear()
+        hit = perm.detach().to(device=device, dtype=torch.int32).contiguous()
+        _perm_cache[key] = hit
+    return hit
+
+
+# ---------------------------------------------------------------------------------------------
+def haar1d_forward(x: torch.Tensor) -> torch.Tensor:
+    """(B,C,H,W) -> (B,C,H,W) with [:, :C/2] = lo, [:, C/2:] = hi.  INN_utils.py:153-156."""
+    x = _ck(x, "x")
+    B, C = x.shape[0], x.shape[1]
+    P = x[0, 0].numel()
+    out = torch.empty_like(x)
+    h = C // 2
+    _lib.call("cwfa_haar1d_fwd", x.data_ptr(), out.data_ptr(), out.data_ptr() + 4 * h * P,
+              B, C, P, C * P, C * P, _stream())
+    return out
+
+
+def haar1d_inverse(x: torch.Tensor) -> torch.Tensor:
+    """Inverse of haar1d_forward on one (B,C,H,W) tensor.  INN_utils.py:157-160."""
+    x = _ck(x, "x")
+    B, C = x.shape[0], x.shape[1]
+    P = x[0, 0].numel()
+    out = torch.empty_like(x)
+    h = C // 2
+    _lib.call("cwfa_haar1d_inv", x.data_ptr(), x.data_ptr() + 4 * h * P, out.data_ptr(),
+              B, C, P, C * P, C * P, _stream())
+    return out
+
+
+def haar1d_merge(lo: torch.Tensor, hi: torch.Tensor) -> torch.Tensor:
+    """Fused Split^-1 + IDWT: two (B,C/2,H,W) tensors -> (B,C,H,W) without the concat copy."""
+    lo, hi = _ck(lo, "lo"), _ck(hi, "hi")
+    B, h = lo.shape[0], lo.shape[1]
+    P = lo[0, 0].numel()
+    out = torch.empty((B, 2 * h) + tuple(lo.shape[2:]), device=lo.device, dtype=torch.float32)
+    _lib.call("cwfa_haar1d_inv", lo.data_ptr(), hi.data_ptr(), out.data_ptr(), B, 2 * h, P, h * P, h * P, _stream())
+    return out
+
+
+def haar1d_split(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Fused DWT + Split: (B,C,H,W) -> separate contiguous (lo, hi)."""
+    x = _ck(x, "x")
+    B, C = x.shape[0], x.shape[1]
+    P = x[0, 0].numel()
+    h = C // 2
+    lo = torch.empty((B, h) + tuple(x.shape[2:]), device=x.device, dtype=torch.float32)
+    hi = torch.empty_like(lo)
+    _lib.call("cwfa_haar1d_fwd", x.data_ptr(), lo.data_ptr(), hi.data_ptr(), B, C, P, h * P, h * P, _stream())
+    return lo, hi
+
+
+def haar2d_down(x: torch.Tensor, order_by_wavelet: bool, fac: float) -> torch.Tensor:
+    x = _ck(x, "x")
+    B, C, H, W = x.shape
+    y = torch.empty((B, 4 * C, H // 2, W // 2), device=x.device, dtype=torch.float32)
+    _lib.call("cwfa_haar2d_down", x.data_ptr(), y.data_ptr(), B, C, H, W, int(order_by_wavelet), float(fac), _stream())
+    return y
+
+
+def haar2d_up(y: torch.Tensor, order_by_wavelet: bool, fac: float) -> torch.Tensor:
+    y = _ck(y, "y")
+    B, C4, H2, W2 = y.shape
+    C = C4 // 4
+    x = torch.empty((B, C, 2 * H2, 2 * W2), device=y.device, dtype=torch.float32)
+    _lib.call("cwfa_haar2d_up", y.data_ptr(), x.data_ptr(), B, C, 2 * H2, 2 * W2, int(order_by_wavelet), float(fac), _stream())
+    return x
+
+
+def permute(x: torch.Tensor, perm: torch.Tensor, axis: int) -> torch.Tensor:
+    """y = x.index_select(axis, perm) for axis in {1,2,3} of a (B,C,H,W) tensor."""
+    x = _ck(x, "x")
+    if x.dim() != 4:
+        x4 = x.reshape(x.shape[0], x.shape[1], 1, -1)
+    else:
+        x4 = x
+    B, C, H, W = x4.shape
+    p = perm_i32(perm, x.device)
+    if p.numel() != x4.shape[axis]:
+        raise ValueError(f"permutation of length {p.numel()} applied to axis {axis} of size {x4.shape[axis]}")
+    y = torch.empty_like(x4)
+    _lib.call("cwfa_permute", x4.data_ptr(), y.data_ptr(), p.data_ptr(), axis, B, C, H, W, _stream())
+    return y.view(x.shape)
+
+
+def affine(x: Optional[torch.Tensor], a_s: torch.Tensor, a_t: torch.Tensor, *, inverse: bool,
+           clamp: float = CLAMP_DEFAULT, t_scale: float = 1.0, want_sumsq: bool = False,
+           k_atan: float = K_ATAN, s_is_final: bool = False):
+    """Affine coupling with fused log-det.  a_s / a_t: (B,ch,H,W) views whose inner (ch,H,W)
+    block is contiguous (e.g. the two channel halves of one subnet output)."""
+    if not a_s.is_cuda:
+        raise RuntimeError("cwfa_b200: affine needs CUDA tensors (no CPU fallback)")
+    B, ch = a_s.shape[0], a_s.shape[1]
+    P = a_s[0, 0].numel()
+
+    def prep(t, name):
+        if t.dtype != torch.float32:
+            t = t.float()
+        inner_ok = t[0].is_contiguous() if B > 0 else True
+        if not inner_ok or (B > 1 and t.stride(0) < ch * P):
+            t = t.contiguous()
+        return t, (t.stride(0) if B > 1 else ch * P)
+
+    a_s, ld_s = prep(a_s, "a_s")
+    a_t, ld_t = prep(a_t, "a_t")
+    xx = None if x is None else _ck(x, "x")
+    y = torch.empty((B, ch) + tuple(a_s.shape[2:]), device=a_s.device, dtype=torch.float32)
+    logdet = torch.empty(B, device=a_s.device, dtype=torch.float32)
+    sumsq = torch.empty(B, device=a_s.device, dtype=torch.float32) if want_sumsq else None
+    nblk = _lib.load().cwfa_affine_workspace_blocks()
+    ws = torch.empty(2 * B * nblk, device=a_s.device, dtype=torch.float32)
+    _lib.call("cwfa_affine", _p(xx), a_s.data_ptr(), a_t.data_ptr(), y.data_ptr(), logdet.data_ptr(), _p(sumsq),
+              ws.data_ptr(), B, ch, P, ld_s, ld_t, float(clamp), float(k_atan), float(t_scale), int(inverse) | (2 if s_is_final else 0), _stream())
+    return (y, logdet, sumsq) if want_sumsq else (y, logdet)
+
+
+def conv2d(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, act: int = ACT_NONE,
+           slope: Optional[torch.Tensor] = None, res: Optional[torch.Tensor] = None, res_mode: int = 0) -> torch.Tensor:
+    """fp32 'same' convolution, stride 1.  v = conv+bias; (res_mode 1: +res); act; (res_mode 2: +res)."""
+    x, w = _ck(x, "x"), _ck(w, "w")
+    N, Cin, H, W = x.shape
+    Cout, Cin_w, KH, KW = w.shape
+    if Cin_w != Cin:
+        raise ValueError(f"conv2d: weight expects {Cin_w} input channels, got {Cin}")
+    bias = None if bias is None else _ck(bias, "bias")
+    res = None if res is None else _ck(res, "res")
+    slope = None if slope is None else _ck(slope, "slope")
+    y = torch.empty((N, Cout, H, W), device=x.device, dtype=torch.float32)
+    _lib.call("cwfa_conv2d_f32", x.data_ptr(), w.data_ptr(), _p(bias), _p(res), _p(slope), y.data_ptr(),
+              N, Cin, H, W, Cout, KH, KW, act, res_mode if res is not None else 0, _stream())
+    return y
+
+
+def conv1d_flat(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], act: int) -> torch.Tensor:
+    """Conv1d over the flattened H*W axis (GlobalAttention, networks.py:250-262): (B,C,L)."""
+    B, C, L = x.shape
+    k = w.shape[-1]
+    y = conv2d(x.reshape(B, C, 1, L), w.reshape(w.shape[0], w.shape[1], 1, k), bias, act=act)
+    return y.reshape(B, w.shape[0], L)
+
+
+def conv_transpose2x2(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
+                      skip: Optional[torch.Tensor] = None) -> torch.Tensor:
+    x, w = _ck(x, "x"), _ck(w, "w")
+    N, Cin, H, W = x.shape
+    Cout = w.shape[1]
+    bias = None if bias is None else _ck(bias, "bias")
+    skip = None if skip is None else _ck(skip, "skip")
+    y = torch.empty((N, Cout, 2 * H, 2 * W), device=x.device, dtype=torch.float32)
+    _lib.call("cwfa_convT2x2_f32", x.data_ptr(), w.data_ptr(), _p(bias), _p(skip), y.data_ptr(), N, Cin, H, W, Cout, _stream())
+    return y
+
+
+def depth_stencil3d(x: torch.Tensor, w1, b1, slope, w2, b2) -> torch.Tensor:
+    """Conv3d(1->Cm,3,p1) + PReLU + Conv3d(Cm->1,3,p1) over (H,W,depth) of a (B,ch,H,W) tensor."""
+    x = _ck(x, "x")
+    B, ch, H, W = x.shape
+    w1, b1, w2, b2, slope = (_ck(t) for t in (w1, b1, w2, b2, slope))
+    Cm = w1.shape[0]
+    y = torch.empty_like(x)
+    _lib.call("cwfa_depth_stencil3d_f32", x.data_ptr(), w1.data_ptr(), b1.data_ptr(), slope.data_ptr(), w2.data_ptr(),
+              b2.data_ptr(), y.data_ptr(), B, ch, H, W, Cm, _stream())
+    return y
+
+
+def channel_stats(x: torch.Tensor) -> torch.Tensor:
+    """Per-channel (sum, sumsq) over (N,H,W) -> tensor (2,C)."""
+    x = _ck(x, "x")
+    N, C = x.shape[0], x.shape[1]
+    P = x[0, 0].numel()
+    stats = torch.empty(2 * C, device=x.device, dtype=torch.float32)
+    ws = torch.empty(2 * C * _lib.load().cwfa_stats_workspace_blocks(), device=x.device, dtype=torch.float32)
+    _lib.call("cwfa_channel_stats_f32", x.data_ptr(), stats.data_ptr(), ws.data_ptr(), N, C, P, _stream())
+    return stats.view(2, C)
+
+
+def batchnorm(x: torch.Tensor, gamma, beta, running_mean=None, running_var=None, *, batch_stats: bool,
+              eps: float = 1e-5) -> torch.Tensor:
+    """nn.BatchNorm2d forward: batch statistics (training-mode normalisation, what the reference's
+    LRNN runs at inference, CWFA.py:531-532) or running statistics (eval mode)."""
+    x = _ck(x, "x")
+    N, C = x.shape[0], x.shape[1]
+    P = x[0, 0].numel()
+    scale = torch.empty(C, device=x.device, dtype=torch.float32)
+    shift = torch.empty(C, device=x.device, dtype=torch.float32)
+    if batch_stats:
+        stats = channel_stats(x).reshape(-1)
+        count = float(N * P)
+    else:
+        rm, rv = _ck(running_mean), _ck(running_var)
+        stats = torch.cat([rm, rv + rm * rm]).contiguous()     # as (sum, sumsq) with count 1
+        count = 1.0
+    _lib.call("cwfa_bn_finalize_f32", stats.data_ptr(), _ck(gamma).data_ptr(), _ck(beta).data_ptr(), scale.data_ptr(),
+              shift.data_ptr(), C, count, float(eps), _stream())
+    y = torch.empty_like(x)
+    _lib.call("cwfa_scale_shift_f32", x.data_ptr(), scale.data_ptr(), shift.data_ptr(), y.data_ptr(), N, C, P, _stream())
+    return y
+
+
+def maxpool2(x: torch.Tensor) -> torch.Tensor:
+    x = _ck(x, "x")
+    N, C, H, W = x.shape
+    y = torch.empty((N, C, H // 2, W // 2), device=x.device, dtype=torch.float32)
+    _lib.call("cwfa_maxpool2_f32", x.data_ptr(), y.data_ptr(), N, C, H, W, _stream())
+    return y
+
+
+def layernorm_chw(x: torch.Tensor, gamma, beta, eps: float = 1e-5) -> torch.Tensor:
+    x = _ck(x, "x")
+    N = x.shape[0]
+    n = x[0].numel()
+    y = torch.empty_like(x)
+    ws = torch.empty(2 * N * _lib.load().cwfa_layernorm_workspace_blocks(), device=x.device, dtype=torch.float32)
+    _lib.call("cwfa_layernorm_chw_f32", x.data_ptr(), _ck(gamma).data_ptr(), _ck(beta).data_ptr(), y.data_ptr(),
+              ws.data_ptr(), N, n, float(eps), _stream())
+    return y
+
+
+def gate_add_(x: torch.Tensor, m: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
+    """x += m * 2 * (g - 0.5) in place (networks.py:554)."""
+    m, g = _ck(m, "m"), _ck(g, "g")
+    if not (x.is_cuda and x.is_contiguous() and x.dtype == torch.float32):
+        raise RuntimeError("gate_add_: x must be a contiguous fp32 CUDA tensor")
+    _lib.call("cwfa_gate_add_f32", x.data_ptr(), m.data_ptr(), g.data_ptr(), x.numel(), _stream())
+    return x
+
+
+def sum_squares(x: torch.Tensor) -> torch.Tensor:
+    """Per-sample sum of squares over all non-batch axes -> (B,) (the ||z||^2 of CWFA.py:183)."""
+    x = _ck(x, "x")
+    B = x.shape[0]
+    n = x[0].numel()
+    # samples play the role of channels: view as (N=1, C=B, P=n)
+    stats = torch.empty(2 * B, device=x.device, dtype=torch.float32)
+    ws = torch.empty(2 * B * _lib.load().cwfa_stats_workspace_blocks(), device=x.device, dtype=torch.float32)
+    _lib.call("cwfa_channel_stats_f32", x.data_ptr(), stats.data_ptr(), ws.data_ptr(), 1, B, n, _stream())
+    return stats[B:]

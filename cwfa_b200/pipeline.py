@@ -1,0 +1,126 @@
+"""Model assembly and the drivers of the hot path: inverse reconstruction and forward NLL.
+
+Mirrors the parts of the reference's ``run_CWFA`` that touch the flow:
+model assembly CWFA.py:478-529, inverse loop CWFA.py:865-924, forward pyramid / NLL
+CWFA.py:156-196 and :966-978.  Training loop, metrics, TIFF/TensorBoard output are out of
+scope.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, asdict
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import networks, ops
+
+
+@dataclass
+class CWFAConfig:
+    """Shape-relevant flags of the reference's argparse namespace (main.py:65-110 defaults)."""
+    n_depths: int = 96
+    volume_side_size: int = 512
+    INN_max_down_steps: int = 5
+    INN_n_blocks: int = 4
+    INN_internal_chans: int = 64
+    INN_cond_chans: int = 32
+    INN_block_type: str = "CAT"
+    INN_use_perm: int = 1
+    INN_use_bias: int = 1
+    INN_z_temperature: float = 0.0
+    disable_low_res_input: int = 0
+    n_views: int = 29
+
+
+class CWFAModel(nn.Module):
+    """``conv_inn[n]`` (flow level n, n < L-1), ``cond_nets[n]`` (conditioning nets, last one is the
+    LRNN ``Encoder``) exactly as ``run_CWFA`` assembles them (CWFA.py:478-529)."""
+
+    def __init__(self, cfg: Optional[CWFAConfig] = None, seed: Optional[int] = None, **overrides):
+        super().__init__()
+        cfg = cfg or CWFAConfig()
+        for k, v in overrides.items():
+            if not hasattr(cfg, k):
+                raise TypeError(f"unknown config field {k!r}")
+            setattr(cfg, k, v)
+        self.cfg = cfg
+        if cfg.disable_low_res_input:
+            raise NotImplementedError("disable_low_res_input=1 is not wired in the pipeline driver")
+        if seed is not None:
+            torch.manual_seed(seed)
+            np.random.seed(seed)
+        D, S, L = cfg.n_depths, cfg.volume_side_size, cfg.INN_max_down_steps
+        if D % (2 ** (L - 1)) != 0:
+            raise ValueError(f"n_depths={D} is not divisible by 2^{L-1}")
+        self.conv_inn = nn.ModuleList()
+        self.cond_nets = nn.ModuleList()
+        for ix in range(L - 1):
+            ch = D // 2 ** (ix + 1)
+            ctor = lambda ch=ch, ix=ix: networks.cond_network(cfg.n_views, ch, ix + 1, L, [], cfg.INN_cond_chans)
+            cn, graphs = networks.conditional_wavelet_flow(
+                input_volume_shape=[D, S, S], condition_shape=[1, cfg.n_views, S, S],
+                st_subnet=networks.wavelet_flow_subnetwork2D, conditional_network=ctor,
+                n_internal_ch=cfg.INN_internal_chans, n_down_steps=ix + 1,
+                use_permutations=cfg.INN_use_perm == 1, block_type=cfg.INN_block_type,
+                n_blocks=cfg.INN_n_blocks, disable_low_res_input=False)
+            self.conv_inn.append(graphs[ix])
+            self.cond_nets.append(cn)
+        self.cond_nets.append(networks.Encoder(cfg.n_views, D // 2 ** (L - 1), L, cfg.INN_internal_chans,
+                                               cfg.INN_use_bias, size=S))
+        # reference: everything .eval(), then the LRNN back to .train() (CWFA.py:528-532)
+        self.eval()
+        self.cond_nets[-1].train()
+
+    @property
+    def n_levels(self) -> int:
+        return len(self.conv_inn)
+
+    # ---- inverse reconstruction (CWFA.py:865-924) -------------------------------------------
+    @torch.no_grad()
+    def reconstruct(self, views: torch.Tensor, mean_vols: Sequence[Optional[torch.Tensor]],
+                    zs: Optional[Sequence[torch.Tensor]] = None, return_all: bool = False):
+        """views (B,29,S,S) normalised lenslet views; mean_vols[n] the mean-volume delta condition of
+        level n (n < L-1) and optionally mean_vols[L-1] the LRNN's mean volume.  z = 0 unless ``zs``
+        is given (INN_z_temperature = 0, CWFA.py:906-907)."""
+        L1 = self.n_levels
+        mv_last = mean_vols[L1] if len(mean_vols) > L1 else None
+        vol = self.cond_nets[L1](views, mv_last)[-1]
+        outs, jacs = {L1: vol}, {}
+        for n in range(L1 - 1, -1, -1):
+            c0 = self.cond_nets[n](views)[-1]
+            inn = self.conv_inn[n]
+            if zs is None:
+                z = torch.zeros((vol.shape[0],) + tuple(inn.global_out_shapes[0]), device=vol.device, dtype=vol.dtype)
+            else:
+                z = zs[n]
+            vol, jac = inn([z, vol], c=[c0, mean_vols[n]], rev=True)
+            outs[n], jacs[n] = vol, jac
+        return (outs, jacs) if return_all else vol
+
+    # ---- forward pyramid + NLL (CWFA.py:156-196, :966-978) -------------------------------------
+    @torch.no_grad()
+    def forward_nll(self, volume: torch.Tensor, views: torch.Tensor, mean_vols: Sequence[torch.Tensor]):
+        """Per level: z, lo, logdet[B], sumsq[B], nll_per_sample[B] = (0.5*sumsq - logdet)/(ch*P) and the
+        reference's batch-coupled ``nll_ref`` = (0.5*||Z||^2_batch - logdet)/lo.numel() (CWFA.py:183-189)."""
+        res = []
+        x = volume
+        for n in range(self.n_levels):
+            c0 = self.cond_nets[n](views)[-1]
+            (z, lo), jac = self.conv_inn[n](x, c=[c0, mean_vols[n]])
+            sumsq = ops.sum_squares(z)
+            per = (0.5 * sumsq - jac) / z[0].numel()
+            ref = (0.5 * sumsq.sum() - jac) / lo.numel()
+            res.append(dict(z=z, lo=lo, logdet=jac, sumsq=sumsq, nll_per_sample=per, nll_ref=ref))
+            x = lo
+        return res
+
+    # ---- test / bench helper ---------------------------------------------------------------
+    def export_for_oracle(self) -> dict:
+        """CPU copies of all state_dicts plus the per-level node specs, in the structure
+        oracle/cwfa_oracle.py consumes.  (The oracle itself is never imported by this package.)"""
+        cpu = lambda sd: {k: v.detach().cpu().clone() for k, v in sd.items()}
+        levels = [dict(inn=cpu(self.conv_inn[n].state_dict()), cond=cpu(self.cond_nets[n].state_dict()),
+                       spec=networks.level_spec(self.conv_inn[n])) for n in range(self.n_levels)]
+        return dict(levels=levels, lrnn=cpu(self.cond_nets[-1].state_dict()), config=asdict(self.cfg))

@@ -1,0 +1,130 @@
+/*
+ * cwfa_b200 C ABI -- the drop-in boundary of the B200-native CWFA hot path.
+ *
+ * Every entry point is `extern "C"`, takes raw DEVICE pointers, sizes and a cudaStream_t
+ * (passed as void*), allocates nothing, takes no ownership, is safe to call concurrently
+ * on distinct streams, and returns 0 on success or a CWFA_E* code.  No torch types.
+ * The reference (pvjosue/CWFA) is pure Python, so there is no FFI in it to replace; each
+ * function instead names the reference Python function whose arithmetic it implements
+ * (file:line into the reference tree).  The Python mirror of the reference module API
+ * (cwfa_b200/modules.py, networks.py) is the only caller.  See INTEGRATION.md.
+ *
+ * Layouts:
+ *   "NCHW"  fp32, contiguous, the reference's tensor layout (API side).
+ *   "C8"    bf16 (or fp16), [N][Cp/8][H][W][8] with Cp = channels padded to a multiple
+ *           of 16 with zeros -- the tensor-core side layout.
+ */
+#ifndef CWFA_B200_H
+#define CWFA_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CWFA_OK 0
+#define CWFA_EINVAL 1   /* bad argument / unsupported shape */
+#define CWFA_ECUDA 2    /* CUDA runtime / launch error (see cwfa_last_error) */
+#define CWFA_ENOTSUP 3  /* device is not sm_100 */
+
+/* activation codes used by conv epilogues */
+#define CWFA_ACT_NONE 0
+#define CWFA_ACT_ELU 1      /* alpha = 1   (networks.py:620) */
+#define CWFA_ACT_PRELU 2    /* scalar slope read from device pointer (nn.PReLU(), networks.py:209, unet.py:22) */
+#define CWFA_ACT_RELU 3
+#define CWFA_ACT_GELU 4     /* exact erf GELU (networks.py:492) */
+#define CWFA_ACT_SIGMOID 5
+
+const char* cwfa_version(void);
+const char* cwfa_last_error(void);
+/* 0 if the current device is compute capability 10.x, else CWFA_ENOTSUP. */
+int cwfa_device_check(void);
+
+/* ---- K1: depth-wise Haar DWT / IDWT  (INN_utils.py:142-161 HaarTransform1D.forward,
+ *      absorbs Split/cat of FrEIA/modules/graph_topology.py:73-80) ------------------------
+ * fwd: lo[b,i,p] = (x[b,2i,p]+x[b,2i+1,p])/sqrt2, hi[b,i,p] = (x[b,2i,p]-x[b,2i+1,p])/sqrt2
+ * inv: x[b,2i,p] = (lo+hi)/sqrt2, x[b,2i+1,p] = (lo-hi)/sqrt2
+ * x is (B,C,P) contiguous; lo/hi are (B,C/2,P) with batch strides ld_lo/ld_hi (elements),
+ * so one (B,C,P) buffer (lo=out, hi=out+C/2*P, ld=C*P) or two separate buffers both work. */
+int cwfa_haar1d_fwd(const float* x, float* lo, float* hi, int B, int C, int64_t P,
+                    int64_t ld_lo, int64_t ld_hi, void* stream);
+int cwfa_haar1d_inv(const float* lo, const float* hi, float* x, int B, int C, int64_t P,
+                    int64_t ld_lo, int64_t ld_hi, void* stream);
+
+/* ---- K1b: FrEIA 2-D Haar down/up-sampling (FrEIA/modules/reshapes.py:273-300) ------------
+ * down: x (B,C,H,W) -> y (B,4C,H/2,W/2); channel of (c, wavelet k): 4c+k, or k*C+c when
+ * order_by_wavelet != 0.  y = fac * haar(x).  up is the exact inverse map with factor fac. */
+int cwfa_haar2d_down(const float* x, float* y, int B, int C, int H, int W,
+                     int order_by_wavelet, float fac, void* stream);
+int cwfa_haar2d_up(const float* y, float* x, int B, int C, int H, int W,
+                   int order_by_wavelet, float fac, void* stream);
+
+/* ---- K4: permutations (fixed_transforms.py:37-41 PermuteRandom; INN_utils.py:73-81 PermuteDim)
+ * axis 1: y[b,c,h,w] = x[b,perm[c],h,w]; axis 2: x[b,c,perm[h],w]; axis 3: x[b,c,h,perm[w]].
+ * perm is int32 on the device, length = size of that axis. */
+int cwfa_permute(const float* x, float* y, const int32_t* perm, int axis,
+                 int B, int C, int H, int W, void* stream);
+
+/* ---- K3: affine coupling + per-sample log-det (+ optional sum of squares of the output)
+ *      (FrEIA/modules/coupling_layers.py:490-500, clamp const :52) ---------------------------
+ * s = clamp * k_atan * atan(a_s[b,c,p]);  t = t_scale * a_t[b,c,p]
+ * fwd: y = exp(s)*x + t, logdet[b] = +sum s;   inv: y = (x - t)*exp(-s), logdet[b] = -sum s.
+ * a_s/a_t have batch strides ld_s/ld_t (elements) so they may alias the two halves of one
+ * subnet output, or a_t may be the mean-volume condition with t_scale = -1/sqrt2
+ * (networks.py:671).  x may be NULL in inv mode (z = 0, CWFA.py:906-907).
+ * flags: bit0 = inverse; bit1 = a_s already holds the final s (no clamp applied; GIN blocks,
+ * coupling_layers.py:360-361).
+ * logdet (B) and sumsq (B, may be NULL: sum over c,p of y^2, CWFA.py:183) are OVERWRITTEN;
+ * workspace must hold 2*B*cwfa_affine_workspace_blocks() floats (deterministic 2-stage sum). */
+int cwfa_affine_workspace_blocks(void);
+int cwfa_affine(const float* x, const float* a_s, const float* a_t, float* y,
+                float* logdet, float* sumsq, float* workspace,
+                int B, int ch, int64_t P, int64_t ld_s, int64_t ld_t,
+                float clamp, float k_atan, float t_scale, int flags, void* stream);
+
+/* ---- generic fp32 direct convolution, NCHW, stride 1, "same" zero padding (KH,KW odd) -----
+ * y = act2( act1(conv(x,w)+bias [+ res if res_mode==1]) [+ res if res_mode==2] ) ... precisely:
+ *   v = conv + bias; if (res_mode==1) v += res; v = act(v); if (res_mode==2) v += res.
+ * Covers every Conv2d/Conv1d of the path at reference precision
+ * (networks.py:211-219,250-254,488-492,537,621-638; unet.py:67,99,104).
+ * w is (Cout,Cin,KH,KW); bias may be NULL; slope = device pointer to the PReLU scalar. */
+int cwfa_conv2d_f32(const float* x, const float* w, const float* bias, const float* res,
+                    const float* slope, float* y, int N, int Cin, int H, int W, int Cout,
+                    int KH, int KW, int act, int res_mode, void* stream);
+/* ConvTranspose2d(k=2,s=2) (unet.py:166): x (N,Cin,H,W), w (Cin,Cout,2,2) -> y (N,Cout,2H,2W);
+ * optional skip tensor added (unet.py:190). */
+int cwfa_convT2x2_f32(const float* x, const float* w, const float* bias, const float* skip,
+                      float* y, int N, int Cin, int H, int W, int Cout, void* stream);
+
+/* ---- conditioning network's depth stencil: Conv3d(1,Cm,3,p1) -> PReLU -> Conv3d(Cm,1,3,p1)
+ *      applied to (B,ch,H,W) viewed as a (H,W,ch) volume (networks.py:221-225,239) ---------
+ * w1 (Cm,1,3,3,3) b1 (Cm) over (kh,kw,kd); w2 (1,Cm,3,3,3) b2 (1). Fused; the Cm-channel
+ * hidden volume is never written to HBM. */
+int cwfa_depth_stencil3d_f32(const float* x, const float* w1, const float* b1,
+                             const float* slope, const float* w2, const float* b2, float* y,
+                             int B, int ch, int H, int W, int Cm, void* stream);
+
+/* ---- normalisation / pooling helpers of the LRNN (unet.py:72-113, networks.py:490) --------
+ * channel_stats: per-channel sum and sum of squares over (N,H,W) -> stats[2*C] (overwritten;
+ * workspace >= 2*C*cwfa_stats_workspace_blocks() floats).  bn_finalize turns them (or running
+ * stats) into scale/shift.  scale_shift applies y = x*scale[c]+shift[c]. */
+int cwfa_stats_workspace_blocks(void);
+int cwfa_channel_stats_f32(const float* x, float* stats, float* workspace,
+                           int N, int C, int64_t P, void* stream);
+int cwfa_bn_finalize_f32(const float* stats, const float* gamma, const float* beta,
+                         float* scale, float* shift, int C, double count, float eps, void* stream);
+int cwfa_scale_shift_f32(const float* x, const float* scale, const float* shift, float* y,
+                         int N, int C, int64_t P, void* stream);
+int cwfa_maxpool2_f32(const float* x, float* y, int N, int C, int H, int W, void* stream);
+/* LayerNorm over (C,H,W) per sample with element-wise affine (networks.py:490);
+ * workspace >= 2*N*cwfa_layernorm_workspace_blocks() floats. */
+int cwfa_layernorm_workspace_blocks(void);
+int cwfa_layernorm_chw_f32(const float* x, const float* gamma, const float* beta, float* y,
+                           float* workspace, int N, int64_t CHW, float eps, void* stream);
+/* x += m * 2 * (g - 0.5)   (networks.py:554) */
+int cwfa_gate_add_f32(float* x, const float* m, const float* g, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CWFA_B200_H */

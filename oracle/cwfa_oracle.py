@@ -1,0 +1,395 @@
+"""CPU oracle for the CWFA conditional-wavelet-flow hot path.
+
+TEST INFRASTRUCTURE -- NOT PRODUCT CODE.  Only tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs may import this file.  Nothing under
+cwfa_b200/ imports it; the product path fails loudly when its CUDA library is missing.
+
+What it is: a functional restatement, on CPU tensors, of the arithmetic of the reference
+path (pvjosue/CWFA).  It works on plain ``state_dict``s that use the reference's own key
+names plus a small ``spec`` dict describing the node sequence of one flow level (the
+things the reference does not serialise: PermuteDim axis, block type).  Every function
+cites the reference file:line it restates.  Convolutions etc. use torch's CPU functional
+ops -- the same ATen ops the reference itself runs on CPU -- so the oracle follows the
+reference bit-for-bit in fp32 wherever the op order is the same.
+
+Parity pinning: the reference ships NO tests, golden vectors or fixtures
+(SURVEY.md section 4 / 8c), so the oracle is pinned against OUTPUTS OF THE REFERENCE ITSELF:
+tests/golden/make_golden.py imports the unmodified reference in the build container,
+runs the tiny config and a set of per-module cases, and commits inputs, state_dicts and
+outputs under tests/golden/.  tests/test_oracle_golden.py replays them through this file.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn.functional as F
+
+Tensor = torch.Tensor
+SD = Dict[str, Tensor]
+
+CLAMP = 2.0          # FrEIA/modules/coupling_layers.py:17 (clamp default)
+K_ATAN = 0.636       # FrEIA/modules/coupling_layers.py:52 (NOT 2/pi)
+INV_SQRT2 = 1.0 / math.sqrt(2.0)
+
+
+# ----------------------------------------------------------------------------------------
+# Haar transforms
+# ----------------------------------------------------------------------------------------
+def haar1d(x: Tensor, rev: bool = False) -> Tuple[Tensor, float]:
+    """Depth-wise (channel axis) Haar DWT / IDWT.  INN_utils.py:142-161.
+
+    fwd: out[:, i] = (x[:, 2i] + x[:, 2i+1]) / sqrt2 ; out[:, h+i] = (x[:, 2i] - x[:, 2i+1]) / sqrt2
+    rev: out[:, 2i] = (x[:, i] + x[:, h+i]) / sqrt2 ; out[:, 2i+1] = (x[:, i] - x[:, h+i]) / sqrt2
+    log-det is exactly 0 for rebalance=1 (INN_utils.py:135-140).
+    """
+    h = x.shape[1] // 2
+    out = torch.zeros_like(x)
+    if not rev:
+        out[:, :h] = x[:, ::2] + x[:, 1::2]
+        out[:, h:] = x[:, ::2] - x[:, 1::2]
+    else:
+        out[:, ::2] = x[:, :h] + x[:, h:]
+        out[:, 1::2] = x[:, :h] - x[:, h:]
+    return out * INV_SQRT2, 0.0
+
+
+def _haar2d_weights(c: int, dtype) -> Tensor:
+    """FrEIA/modules/reshapes.py:240-252."""
+    w = torch.ones(4, 1, 2, 2, dtype=dtype)
+    w[1, 0, 0, 1] = -1
+    w[1, 0, 1, 1] = -1
+    w[2, 0, 1, 0] = -1
+    w[2, 0, 1, 1] = -1
+    w[3, 0, 1, 0] = -1
+    w[3, 0, 0, 1] = -1
+    return torch.cat([w] * c, 0)
+
+
+def haar2d(x: Tensor, rev: bool = False, order_by_wavelet: bool = False,
+           rebalance: float = 1.0) -> Tuple[Tensor, float]:
+    """FrEIA 2-D HaarDownsampling (rev=False) / its inverse.  reshapes.py:273-300.
+
+    Input is NOT mutated (the reference mutates it in rev when order_by_wavelet=False,
+    reshapes.py:297 -- a bug we deliberately do not replicate).
+    """
+    fac_fwd = 0.5 * rebalance
+    fac_rev = 0.5 / rebalance
+    ndims = x[0].numel()
+    if not rev:
+        c = x.shape[1]
+        jac = ndims * (math.log(16.0) + 4 * math.log(fac_fwd)) / 4.0
+        out = F.conv2d(x, _haar2d_weights(c, x.dtype), None, stride=2, groups=c)
+        if order_by_wavelet:
+            perm = torch.tensor([i + 4 * j for i in range(4) for j in range(c)])
+            out = out[:, perm]
+        return out * fac_fwd, jac
+    c = x.shape[1] // 4
+    jac = ndims * (math.log(16.0) + 4 * math.log(fac_rev)) / 4.0
+    if order_by_wavelet:
+        perm = torch.tensor([i + 4 * j for i in range(4) for j in range(c)])
+        perm_inv = torch.empty_like(perm)
+        perm_inv[perm] = torch.arange(4 * c)
+        x = x[:, perm_inv]
+    out = F.conv_transpose2d(x * fac_rev, _haar2d_weights(c, x.dtype), stride=2, groups=c)
+    return out, jac
+
+
+# ----------------------------------------------------------------------------------------
+# Permutations
+# ----------------------------------------------------------------------------------------
+def permute_random(x: Tensor, perm: Tensor, perm_inv: Tensor, rev: bool = False) -> Tensor:
+    """Channel gather.  FrEIA/modules/fixed_transforms.py:37-41."""
+    return x[:, perm_inv if rev else perm]
+
+
+def permute_dim(x: Tensor, perm: Tensor, perm_inv: Tensor, axis: int, rev: bool = False) -> Tensor:
+    """Row (axis=2) or column (axis=3) gather.  INN_utils.py:73-81."""
+    p = perm_inv if rev else perm
+    return x.index_select(axis, p)
+
+
+# ----------------------------------------------------------------------------------------
+# Coupling sub-network (the conv trunk that predicts s, t)
+# ----------------------------------------------------------------------------------------
+def subnet(sd: SD, pre: str, inp: Tensor, normal: bool) -> Tensor:
+    """wavelet_flow_subnetwork.forward, networks.py:641-671 (2-D variants :673-706).
+
+    normal=True  (wavelet_flow_subnetwork2D):       b1 = block12(inp),  out = block72(b6)
+    normal=False (wavelet_flow_subnetwork2D_first): low, cond = inp[:, :-n], inp[:, -n:]
+                 b1 = block1(cond), out = cat(block7(b6), -low / sqrt2)
+    """
+    def conv(name, t, pad):
+        return F.conv2d(t, sd[pre + name + ".weight"], sd[pre + name + ".bias"], padding=pad)
+
+    low = None
+    if normal:
+        b1 = conv("block12", inp, 0)
+    else:
+        n = sd[pre + "block1.weight"].shape[1]          # c_in // 2
+        low, cond = inp[:, :-n], inp[:, -n:]
+        b1 = conv("block1", cond, 0)
+    b = b1
+    for blk in ("block2", "block4", "block6"):
+        t = conv(blk + ".0", b, 1)
+        t = F.elu(t)
+        t = conv(blk + ".2", t, 0)
+        b = t + b
+        if blk != "block6":
+            b = F.elu(b)
+    if normal:
+        return conv("block72.1", F.elu(b), 1)
+    b7 = conv("block7.1", F.elu(b), 1)
+    return torch.cat((b7, -low / math.sqrt(2)), 1)
+
+
+def affine(x: Tensor, a: Tensor, rev: bool, clamp: float = CLAMP) -> Tuple[Tensor, Tensor]:
+    """s = clamp * 0.636 * atan(a[:, :ch]); t = a[:, ch:]; coupling_layers.py:490-500.
+
+    fwd: y = exp(s) * x + t, J = +sum(s);  rev: y = (x - t) * exp(-s), J = -sum(s).
+    """
+    ch = x.shape[1]
+    s, t = a[:, :ch], a[:, ch:]
+    s = clamp * (K_ATAN * torch.atan(s))
+    j = torch.sum(s, dim=tuple(range(1, x.dim())))
+    if rev:
+        return (x - t) * torch.exp(-s), -j
+    return torch.exp(s) * x + t, j
+
+
+def cat_block(sd: SD, pre: str, x: Tensor, conds: Sequence[Tensor], rev: bool,
+              first: bool) -> Tuple[Tensor, Tensor]:
+    """ConditionalAffineTransform.forward, coupling_layers.py:475-500."""
+    cond = torch.cat(list(conds), 1) if len(conds) > 1 else conds[0]
+    a = subnet(sd, pre + "subnet.", cond, normal=not first)
+    return affine(x, a, rev)
+
+
+def glow_block(sd: SD, pre: str, x: Tensor, conds: Sequence[Tensor], rev: bool,
+               kind: str = "GLOW") -> Tuple[Tensor, Tensor]:
+    """_BaseCouplingBlock.forward + GLOW/GIN/RNVP couplings.  coupling_layers.py:62-87,
+    :160-229 (RNVP), :232-302 (GLOW), :305-381 (GIN)."""
+    l1 = x.shape[1] // 2
+    l2 = x.shape[1] - l1
+    x1, x2 = x[:, :l1], x[:, l1:]
+    nd = tuple(range(1, x.dim()))
+
+    def st(which, u, n_out):
+        if kind == "RNVP":
+            s = subnet(sd, f"{pre}subnet_s{which}.", u, True)
+            t = subnet(sd, f"{pre}subnet_t{which}.", u, True)
+        else:
+            a = subnet(sd, f"{pre}subnet{which}.", u, True)
+            s, t = a[:, :n_out], a[:, n_out:]
+        s = CLAMP * (K_ATAN * torch.atan(s))
+        if kind == "GIN":
+            s = s - s.mean(1, keepdim=True)
+            return s, t, 0.0
+        return s, t, torch.sum(s, dim=nd)
+
+    def c1(x1_, u2, r):     # uses subnet2 (coupling_layers.py:268-289)
+        s, t, j = st(2, u2, l1)
+        return ((x1_ - t) * torch.exp(-s), -j) if r else (torch.exp(s) * x1_ + t, j)
+
+    def c2(x2_, u1, r):     # uses subnet1 (coupling_layers.py:291-302)
+        s, t, j = st(1, u1, l2)
+        return ((x2_ - t) * torch.exp(-s), -j) if r else (torch.exp(s) * x2_ + t, j)
+
+    cc = list(conds)
+    if not rev:
+        y1, j1 = c1(x1, torch.cat([x2, *cc], 1), False)
+        y2, j2 = c2(x2, torch.cat([y1, *cc], 1), False)
+    else:
+        y2, j2 = c2(x2, torch.cat([x1, *cc], 1), True)
+        y1, j1 = c1(x1, torch.cat([y2, *cc], 1), True)
+    j = j1 + j2
+    if not torch.is_tensor(j):
+        j = torch.zeros(x.shape[0], dtype=x.dtype) + j
+    return torch.cat((y1, y2), 1), j
+
+
+# ----------------------------------------------------------------------------------------
+# One flow level (GraphINN of networks.py:305-366)
+# ----------------------------------------------------------------------------------------
+def _run_node(sd: SD, node: dict, x: Tensor, c_lf: Tensor, c_mean: Optional[Tensor], rev: bool):
+    i = node["idx"]
+    pre = f"module_list.{i}."
+    kind = node["type"]
+    zero = torch.zeros(x.shape[0], dtype=x.dtype)
+    if kind == "cat_first":
+        # node conditions = [Condition (mean-vol delta), Condition I (LF)], networks.py:329-339
+        return cat_block(sd, pre, x, [c_mean, c_lf], rev, first=True)
+    if kind == "cat":
+        return cat_block(sd, pre, x, [c_lf], rev, first=False)
+    if kind in ("GLOW", "GIN", "RNVP"):
+        return glow_block(sd, pre, x, [c_lf], rev, kind)
+    if kind == "perm_chan":
+        return permute_random(x, sd[pre + "perm"], sd[pre + "perm_inv"], rev), zero
+    if kind == "perm_dim":
+        return permute_dim(x, sd[pre + "perm"], sd[pre + "perm_inv"], node["axis"], rev), zero
+    raise ValueError(kind)
+
+
+def level_forward(sd: SD, spec: dict, x: Tensor, c_lf: Tensor, c_mean: Optional[Tensor]):
+    """GraphINN.forward(rev=False) of one level: returns (z, lo, logdet[B]).
+    graph_inn.py:242-326; node order networks.py:305-366."""
+    y, _ = haar1d(x, rev=False)
+    h = y.shape[1] // 2
+    lo, hi = y[:, :h], y[:, h:]                           # Split, graph_topology.py:73-80
+    jac = torch.zeros(x.shape[0], dtype=x.dtype)
+    for node in spec["nodes"]:
+        hi, j = _run_node(sd, node, hi, c_lf, c_mean, rev=False)
+        jac = jac + j
+    return hi, lo, jac
+
+
+def level_inverse(sd: SD, spec: dict, z: Tensor, lo: Tensor, c_lf: Tensor, c_mean: Optional[Tensor]):
+    """GraphINN.forward(rev=True): returns (x, logdet[B])."""
+    hi = z
+    jac = torch.zeros(z.shape[0], dtype=z.dtype)
+    for node in reversed(spec["nodes"]):
+        hi, j = _run_node(sd, node, hi, c_lf, c_mean, rev=True)
+        jac = jac + j
+    x, _ = haar1d(torch.cat((lo, hi), 1), rev=True)
+    return x, jac
+
+
+# ----------------------------------------------------------------------------------------
+# Conditioning network (networks.py:165-242)
+# ----------------------------------------------------------------------------------------
+def cond_network(sd: SD, views: Tensor) -> Tensor:
+    """cond_network.forward -> ResidualBlock.forward (eval mode: Dropout3d = identity).
+    networks.py:195-196, :229-242.  The PReLU module is one shared instance
+    (default-arg nn.PReLU(), networks.py:209) stored under three keys."""
+    p = "subnetworks.0."
+    out = F.conv2d(views, sd[p + "conv1.0.weight"], sd[p + "conv1.0.bias"], padding=1)
+    out = F.prelu(out, sd[p + "conv1.1.weight"])
+    out = F.conv2d(out, sd[p + "conv2.0.weight"], sd[p + "conv2.0.bias"], padding=1)
+    res = F.conv2d(views, sd[p + "downsample.0.weight"], sd[p + "downsample.0.bias"], padding=1)
+    out = F.prelu(out + res, sd[p + "relu.weight"])
+    v = out.permute(0, 2, 3, 1).unsqueeze(1)                 # (B,1,H,W,ch)
+    v = F.conv3d(v, sd[p + "conv3d.0.weight"], sd[p + "conv3d.0.bias"], padding=1)
+    v = F.prelu(v, sd[p + "conv3d.1.weight"])
+    v = F.conv3d(v, sd[p + "conv3d.3.weight"], sd[p + "conv3d.3.bias"], padding=1)
+    return v[:, 0].permute(0, 3, 1, 2).contiguous()
+
+
+# ----------------------------------------------------------------------------------------
+# LRNN (networks.py:505-584, unet.py)
+# ----------------------------------------------------------------------------------------
+def _bn(sd: SD, pre: str, x: Tensor, mode: str, eps: float = 1e-5) -> Tensor:
+    """nn.BatchNorm2d.  mode='batch' = training-mode batch statistics (what the reference
+    runs at inference, CWFA.py:531-532); mode='running' = eval-mode running stats."""
+    w, b = sd[pre + "weight"], sd[pre + "bias"]
+    if mode == "batch":
+        return F.batch_norm(x, None, None, w, b, training=True, eps=eps)
+    return F.batch_norm(x, sd[pre + "running_mean"], sd[pre + "running_var"], w, b,
+                        training=False, eps=eps)
+
+
+def _unet_block(sd: SD, pre: str, x: Tensor, bn_mode: str) -> Tensor:
+    """UNetConvBlock: [conv3x3, PReLU, BN] x2.  unet.py:94-113."""
+    for ci, ai, bi in ((0, 1, 2), (3, 4, 5)):
+        x = F.conv2d(x, sd[f"{pre}block.{ci}.weight"], sd.get(f"{pre}block.{ci}.bias"), padding=1)
+        x = F.prelu(x, sd[f"{pre}block.{ai}.weight"])
+        x = _bn(sd, f"{pre}block.{bi}.", x, bn_mode)
+    return x
+
+
+def unet(sd: SD, pre: str, x: Tensor, bn_mode: str = "batch") -> Tensor:
+    """UNet.forward with drop_out pinned to 0 (the reference's F.dropout2d is always
+    active with p=0.005, unet.py:80,86 -- stochastic, so parity pins p=0).  unet.py:72-91."""
+    depth = 1 + max(int(k[len(pre) + 10:].split(".")[0]) for k in sd if k.startswith(pre + "down_path."))
+    blocks = []
+    for i in range(depth):
+        x = _unet_block(sd, f"{pre}down_path.{i}.", x, bn_mode)
+        if i != depth - 1:
+            blocks.append(x)
+            x = F.adaptive_max_pool2d(x, x.shape[-1] // 2)
+    for i in range(depth - 1):
+        p = f"{pre}up_path.{i}."
+        up = F.conv_transpose2d(x, sd[p + "up.weight"], sd.get(p + "up.bias"), stride=2)
+        x = _unet_block(sd, p + "conv_block.", up + blocks[-i - 1], bn_mode)     # skip ADD, unet.py:190
+    x = F.conv2d(x, sd[pre + "last.0.weight"], sd.get(pre + "last.0.bias"))
+    return F.prelu(x, sd[pre + "last.1.weight"])
+
+
+def convnext(sd: SD, pre: str, x: Tensor) -> Tensor:
+    """ConvNeXt.forward in eval mode (drop_path = identity).  networks.py:486-503."""
+    up = F.conv2d(x, sd[pre + "input.weight"], sd[pre + "input.bias"])
+    m = F.conv2d(up, sd[pre + "m.0.weight"], sd[pre + "m.0.bias"], padding=3)
+    m = F.layer_norm(m, m.shape[1:], sd[pre + "m.1.weight"], sd[pre + "m.1.bias"], 1e-5)
+    m = F.conv2d(m, sd[pre + "m.2.weight"], sd[pre + "m.2.bias"])
+    m = F.gelu(m)
+    return m + up
+
+
+def global_attention(sd: SD, pre: str, x: Tensor) -> Tensor:
+    """GlobalAttention.forward: Conv1d(k=3) over the FLATTENED H*W axis.  networks.py:250-262."""
+    f = x.reshape(x.shape[0], x.shape[1], -1)
+    f = F.conv1d(f, sd[pre + "m.0.weight"], sd[pre + "m.0.bias"], padding=1)
+    f = F.relu(f)
+    f = F.conv1d(f, sd[pre + "m.2.weight"], sd[pre + "m.2.bias"])
+    return torch.sigmoid(f).reshape(x.shape)
+
+
+def lrnn(sd: SD, views: Tensor, mean_vol: Optional[Tensor] = None, bn_mode: str = "batch") -> Tensor:
+    """Encoder.forward -> LRNN.forward.  networks.py:573-584, :544-555."""
+    p = "net."
+    x = F.conv2d(views, sd[p + "deconv.0.weight"], sd.get(p + "deconv.0.bias"))
+    x = unet(sd, p + "deconv.1.", x, bn_mode)
+    if mean_vol is not None:
+        mp = convnext(sd, p + "conv3d.1.", convnext(sd, p + "conv3d.0.", mean_vol))
+        x = x + mp * 2 * (global_attention(sd, p + "attention_3d.", mean_vol) - 0.5)
+    return x
+
+
+# ----------------------------------------------------------------------------------------
+# Whole-pipeline drivers
+# ----------------------------------------------------------------------------------------
+def reconstruct(model: dict, views: Tensor, mean_vols: Sequence[Optional[Tensor]],
+                zs: Optional[Sequence[Tensor]] = None, bn_mode: str = "batch",
+                return_all: bool = False):
+    """Inverse reconstruction, CWFA.py:865-924: LRNN low-res volume, then each flow level
+    n = L-1 .. 0 with z = 0 (INN_z_temperature = 0, CWFA.py:906-907).
+
+    model = {"levels": [{"inn": sd, "cond": sd, "spec": spec}, ...], "lrnn": sd}
+    mean_vols[n] is the mean-volume delta condition of level n (n < L) and mean_vols[L]
+    (may be None) the LRNN's mean volume (CWFA.py:882 passes mean_vols_cache[n_net-1]).
+    """
+    levels = model["levels"]
+    L = len(levels)
+    vol = lrnn(model["lrnn"], views, mean_vols[L] if len(mean_vols) > L else None, bn_mode)
+    outs = {L: vol}
+    jacs = {}
+    for n in range(L - 1, -1, -1):
+        lv = levels[n]
+        c_lf = cond_network(lv["cond"], views)
+        z = torch.zeros_like(vol) if zs is None else zs[n]
+        vol, jac = level_inverse(lv["inn"], lv["spec"], z, vol, c_lf, mean_vols[n])
+        outs[n] = vol
+        jacs[n] = jac
+    return (outs, jacs) if return_all else vol
+
+
+def forward_nll(model: dict, volume: Tensor, views: Tensor, mean_vols: Sequence[Tensor]):
+    """Forward pyramid with REAL conditions + per-level NLL (CWFA.py:966-978; pyramid
+    structure of evaluate_INN_forward, CWFA.py:156-196).
+
+    Returns a list per level of dicts: z, lo, logdet[B], sumsq[B],
+    nll_per_sample[B] = (0.5*sumsq_b - logdet_b) / (ch*P),
+    nll_ref = the reference's batch-coupled formula (0.5*||Z||^2 - logdet) / Z[-1].numel()
+    (CWFA.py:183-189: ||Z||^2 over the WHOLE batch, numel of the lo tensor incl. batch).
+    """
+    res = []
+    x = volume
+    for lv, mv in zip(model["levels"], mean_vols):
+        c_lf = cond_network(lv["cond"], views)
+        z, lo, jac = level_forward(lv["inn"], lv["spec"], x, c_lf, mv)
+        sumsq = (z.double() ** 2).flatten(1).sum(1).to(z.dtype)
+        per = (0.5 * sumsq - jac) / z[0].numel()
+        ref = (0.5 * torch.norm(z) ** 2 - jac) / lo.numel()
+        res.append(dict(z=z, lo=lo, logdet=jac, sumsq=sumsq, nll_per_sample=per, nll_ref=ref))
+        x = lo
+    return res
