@@ -55,7 +55,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError("nvcc failed: " + " ".join(cmd) + "\n" + out)
         if verbose and out:
             print(out)
-    link = [nvcc, "-shared", "-o", LIB_PATH] + objs + ["-lcudart"]
+    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH] + objs
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed: " + " ".join(link) + "\n" + r.stdout)
