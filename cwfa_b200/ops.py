@@ -38,19 +38,18 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
-_perm_cache = {}
-
-
 def perm_i32(perm: torch.Tensor, device) -> torch.Tensor:
-    """int32 device copy of a LongTensor permutation (cached per version)."""
-    key = (perm.data_ptr(), str(device), perm._version, perm.numel())
-    hit = _perm_cache.get(key)
-    if hit is None:
-        if len(_perm_cache) > 4096:
-            _perm_cache.clear()
-        hit = perm.detach().to(device=device, dtype=torch.int32).contiguous()
-        _perm_cache[key] = hit
-    return hit
+    """int32 device copy of a LongTensor permutation, cached ON the source tensor object (keyed by
+    device and in-place version) so that the cache can never outlive or alias the permutation."""
+    cache = getattr(perm, "_cwfa_i32", None)
+    key = (str(device), perm._version)
+    if cache is None or cache[0] != key:
+        cache = (key, perm.detach().to(device=device, dtype=torch.int32).contiguous())
+        try:
+            perm._cwfa_i32 = cache
+        except AttributeError:      # plain tensors without __dict__ support: do not cache
+            pass
+    return cache[1]
 
 
 # ---------------------------------------------------------------------------------------------
