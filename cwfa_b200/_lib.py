@@ -35,14 +35,20 @@ _SIGS = {
     "cwfa_layernorm_workspace_blocks": [],
     "cwfa_layernorm_chw_f32": [vp, vp, vp, vp, vp, i32, i64, f32, vp],
     "cwfa_gate_add_f32": [vp, vp, vp, i64, vp],
+    "cwfa_tc_kc": [i32],
+    "cwfa_tc_pack_weights": [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp],
+    "cwfa_conv_tc": [vp, vp, vp, vp, vp, vp] + [i32] * 15 + [vp],
+    "cwfa_nchw_to_c8": [vp, vp, i32, i32, i32, i64, i32, vp],
+    "cwfa_c8_to_nchw": [vp, vp, i32, i32, i32, i64, i32, vp],
 }
+_I64_FUNCS = {"cwfa_tc_packed_weight_elems": [i32, i32, i32, i32, i32]}
 _RESTYPES = {"cwfa_version": C.c_char_p, "cwfa_last_error": C.c_char_p}
 _OPTIONAL = {}
 
 
 def exported_symbols():
     """Every symbol include/cwfa_b200.h declares (used by the CPU-side ABI test)."""
-    return sorted(list(_SIGS) + list(_RESTYPES) + list(_OPTIONAL))
+    return sorted(list(_SIGS) + list(_RESTYPES) + list(_OPTIONAL) + list(_I64_FUNCS))
 
 
 def lib_path() -> str:
@@ -70,6 +76,10 @@ def load():
             fn = getattr(lib, name)
             fn.argtypes = args
             fn.restype = C.c_int
+        for name, args in _I64_FUNCS.items():
+            fn = getattr(lib, name)
+            fn.argtypes = args
+            fn.restype = C.c_int64
         for name, rt in _RESTYPES.items():
             fn = getattr(lib, name)
             fn.argtypes = []

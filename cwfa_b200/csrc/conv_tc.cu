@@ -1,0 +1,529 @@
+// tcgen05 / TMEM / TMA implicit-GEMM convolution for sm_100a  (K2 of DESIGN.md).
+//
+// Layout ("C8"): activations are bf16/fp16 [N][Cp/8][H][W][8].  One TMA box load brings a halo tile
+// [k-chunks][BH][BW][8] into shared memory; in that layout pixel q of a chunk sits at q*16 bytes, so
+// it IS the canonical no-swizzle K-major UMMA operand layout with
+//     SBO (8-row group stride) = BW*16   -> an M=128 block is 16 image rows x 8 columns
+//     LBO (K-chunk stride)     = BH*BW*16
+// and every filter tap (kh,kw) is just a different descriptor START ADDRESS into the same tile:
+// the input is read once per tile (halo overhead only), never once per tap.
+// Weights are pre-packed per (n-block, k-block, tap) as [chunk][BN][8] and streamed with 1-D bulk
+// copies.  Accumulators live in TMEM (128 lanes x BN fp32 columns per M-block).
+//
+// Warp roles (192 threads): warp0 = TMA producer, warp1 = TMEM alloc + MMA issuer (one elected
+// lane), warps2-5 = epilogue (tcgen05.ld -> bias/activation/residual -> global).
+#include <cuda.h>
+#include "common.cuh"
+using namespace cwfa;
+
+namespace {
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
+// Bounded wait: a protocol bug must never hang the GPU -- trap instead (the host sees an error).
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 26)) {
+            printf("cwfa conv_tc: mbarrier timeout (block %d,%d thread %d bar %u parity %u)\n", blockIdx.x, blockIdx.y,
+                   threadIdx.x, bar, parity);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tmap, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                           uint32_t accumulate) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// No-swizzle K-major shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
+// [0,14) start>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version = 1, layout_type [61,64) = 0.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+
+struct TcParams {
+    int N, H, W;
+    int Cout, Cout_p;          // true / padded output channels
+    int KH, KW;
+    int tiles_x, tiles_y;
+    int KCc;                   // 8-channel chunks per k-block
+    int num_kb;
+    int BH, BW;
+    int MB, BN;
+    uint32_t a_bytes, a_stride, b_bytes;
+    int a_stages, b_stages;
+    int act, res_mode, out_mode;   // out_mode 0: C8 half   1: NCHW fp32   2: C8 half, 2x2 transposed-conv scatter
+    int is_bf16;
+    const uint8_t* w_packed;
+    const float* bias;
+    const float* slope;
+    const uint8_t* res;
+    void* out;
+};
+
+constexpr int kMaxBStages = 8;
+constexpr int kThreads = 192;
+
+template <bool BF16>
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+    if constexpr (BF16) {
+        __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&v);
+    } else {
+        __half2 v = __floats2half2_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&v);
+    }
+}
+template <bool BF16>
+__device__ __forceinline__ float2 unpack2(uint32_t u) {
+    if constexpr (BF16) {
+        return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
+    } else {
+        return __half22float2(*reinterpret_cast<__half2*>(&u));
+    }
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // [0,256): barriers + tmem slot; then A ring, then B ring
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+    const uint32_t bar0 = smem_u32(bars);
+    auto a_full = [&](int s) { return bar0 + 8u * s; };                 // 2
+    auto a_empty = [&](int s) { return bar0 + 8u * (2 + s); };          // 2
+    auto b_full = [&](int s) { return bar0 + 8u * (4 + s); };           // 8
+    auto b_empty = [&](int s) { return bar0 + 8u * (12 + s); };         // 8
+    const uint32_t acc_full = bar0 + 8u * 20;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 8 * 24);
+    const uint32_t a_base = smem_u32(smem + 256);
+    const uint32_t b_base = a_base + p.a_stages * p.a_stride;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles = p.tiles_x * p.tiles_y;
+    const int n = blockIdx.x / tiles;
+    const int t = blockIdx.x % tiles;
+    const int h0 = (t / p.tiles_x) * 16;
+    const int w0 = (t % p.tiles_x) * 8 * p.MB;
+    const int nblk = blockIdx.y;
+    const int T = p.KH * p.KW;
+    const int tmem_cols_needed = p.MB * p.BN;
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < tmem_cols_needed) tmem_cols <<= 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < 2; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
+        for (int s = 0; s < kMaxBStages; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
+        mbar_init(acc_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            const int ph = p.KH / 2, pw = p.KW / 2;
+            for (int kb = 0; kb < p.num_kb; ++kb) {
+                const int sa = kb % p.a_stages;
+                mbar_wait(a_empty(sa), ((kb / p.a_stages) & 1) ^ 1);
+                mbar_expect_tx(a_full(sa), p.a_bytes);
+                tma_load_4d(a_base + sa * p.a_stride, &tmap, a_full(sa), (w0 - pw) * 8, h0 - ph, kb * p.KCc, n);
+                for (int tap = 0; tap < T; ++tap) {
+                    const int it = kb * T + tap;
+                    const int sb = it % p.b_stages;
+                    mbar_wait(b_empty(sb), ((it / p.b_stages) & 1) ^ 1);
+                    mbar_expect_tx(b_full(sb), p.b_bytes);
+                    const uint8_t* src = p.w_packed + ((size_t)(nblk * p.num_kb + kb) * T + tap) * p.b_bytes;
+                    bulk_load(b_base + sb * p.b_bytes, src, p.b_bytes, b_full(sb));
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t fmt = p.is_bf16 ? 1u : 0u;
+            const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t a_sbo = p.BW * 16, a_lbo = p.BH * p.BW * 16;
+            const uint32_t b_sbo = 128, b_lbo = p.BN * 16;
+            const int ksteps = p.KCc / 2;
+            for (int kb = 0; kb < p.num_kb; ++kb) {
+                const int sa = kb % p.a_stages;
+                mbar_wait(a_full(sa), (kb / p.a_stages) & 1);
+                const uint32_t a_s = a_base + sa * p.a_stride;
+                for (int tap = 0; tap < T; ++tap) {
+                    const int it = kb * T + tap;
+                    const int sb = it % p.b_stages;
+                    mbar_wait(b_full(sb), (it / p.b_stages) & 1);
+                    tc_fence_after();
+                    const int kh = tap / p.KW, kw = tap % p.KW;
+                    const uint32_t b_s = b_base + sb * p.b_bytes;
+                    for (int mb = 0; mb < p.MB; ++mb) {
+                        const uint32_t a_tap = a_s + (uint32_t)((kh * p.BW + mb * 8 + kw) * 16);
+                        for (int kk = 0; kk < ksteps; ++kk) {
+                            const uint64_t ad = make_desc(a_tap + kk * 2 * a_lbo, a_lbo, a_sbo);
+                            const uint64_t bd = make_desc(b_s + kk * 2 * b_lbo, b_lbo, b_sbo);
+                            tc_mma_f16(tmem_base + mb * p.BN, ad, bd, idesc, (kb | tap | kk) ? 1u : 0u);
+                        }
+                    }
+                    tc_commit(b_empty(sb));
+                }
+                tc_commit(a_empty(sa));
+            }
+            tc_commit(acc_full);
+        }
+        __syncwarp();
+    } else {
+        // ===================== epilogue =====================
+        const int q = warp & 3;                  // TMEM lane quadrant this warp may access
+        const int m = q * 32 + lane;
+        const int orow = h0 + (m >> 3);
+        const bool row_ok = orow < p.H;
+        const float slope = (p.act == CWFA_ACT_PRELU && p.slope) ? __ldg(p.slope) : 0.f;
+        const size_t plane = (size_t)p.H * p.W;
+        mbar_wait(acc_full, 0);
+        tc_fence_after();
+        for (int mb = 0; mb < p.MB; ++mb) {
+            const int ocol = w0 + mb * 8 + (m & 7);
+            const bool ok = row_ok && ocol < p.W;
+            const size_t pix = (size_t)orow * p.W + ocol;
+            for (int c0 = 0; c0 < p.BN; c0 += 16) {
+                uint32_t r[16];
+                __syncwarp();
+                tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mb * p.BN + c0), r);
+                const int cg = nblk * p.BN + c0;             // first global (padded) output channel of this group
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + cg + j) : 0.f);
+                if (!ok) {
+                    // masked pixel (image edge inside the tile): nothing to store
+                } else if (p.out_mode == 1) {
+                    // NCHW fp32 (res, if any, is NCHW fp32 too)
+                    float* out = reinterpret_cast<float*>(p.out);
+                    const float* res = reinterpret_cast<const float*>(p.res);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int co = cg + j;
+                        if (co < p.Cout) {
+                            const size_t o = ((size_t)n * p.Cout + co) * plane + pix;
+                            float x = v[j];
+                            if (p.res_mode == 1) x += __ldg(res + o);
+                            x = apply_act(x, p.act, slope);
+                            if (p.res_mode == 2) x += __ldg(res + o);
+                            out[o] = x;
+                        }
+                    }
+                } else {
+                    // C8 half output: two 16-byte chunks
+                    const int cchunks = p.Cout_p >> 3;
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        const size_t o = (((size_t)n * cchunks + (cg >> 3) + hh) * plane + pix) * 8;   // element offset
+                        float x[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) x[j] = v[hh * 8 + j];
+                        if (p.res_mode != 0) {
+                            const uint4 rr = __ldg(reinterpret_cast<const uint4*>(p.res + o * 2));
+                            const float2 r0 = unpack2<BF16>(rr.x), r1 = unpack2<BF16>(rr.y), r2 = unpack2<BF16>(rr.z),
+                                         r3 = unpack2<BF16>(rr.w);
+                            const float rv[8] = {r0.x, r0.y, r1.x, r1.y, r2.x, r2.y, r3.x, r3.y};
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                if (p.res_mode == 1) x[j] = apply_act(x[j] + rv[j], p.act, slope);
+                                else x[j] = apply_act(x[j], p.act, slope) + rv[j];
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) x[j] = apply_act(x[j], p.act, slope);
+                        }
+                        uint4 ov;
+                        ov.x = pack2<BF16>(x[0], x[1]);
+                        ov.y = pack2<BF16>(x[2], x[3]);
+                        ov.z = pack2<BF16>(x[4], x[5]);
+                        ov.w = pack2<BF16>(x[6], x[7]);
+                        *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.out) + o * 2) = ov;
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+int pick_kc(int cin_p) {
+    for (int kc = 64; kc >= 16; kc -= 16)
+        if (cin_p % kc == 0) return kc;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int cwfa_tc_kc(int cin_p) { return pick_kc(cin_p); }
+
+// Packs fp32 (Cout,Cin,KH,KW) weights into the streamed layout [nblk][kb][tap][chunk][BN][8] (half).
+// transposed != 0: input is ConvTranspose2d(k=2,s=2) weights (Cin,Cout,2,2), packed as a 1x1 conv with
+// 4*Cout_p output channels ordered (i*2+j)*Cout_p + co.
+template <bool BF16>
+__global__ void pack_weights_kernel(const float* __restrict__ w, uint16_t* __restrict__ out, int Cout, int Cin, int T,
+                                    int KC, int num_kb, int BN, int nblks, int transposed, int Cout_p) {
+    const int KCc = KC / 8;
+    const size_t total = (size_t)nblks * num_kb * T * KCc * BN * 8;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int e = (int)(i % 8);
+        const int nn = (int)((i / 8) % BN);
+        const int chunk = (int)((i / (8 * (size_t)BN)) % KCc);
+        const int tap = (int)((i / (8 * (size_t)BN * KCc)) % T);
+        const int kb = (int)((i / (8 * (size_t)BN * KCc * T)) % num_kb);
+        const int nb = (int)(i / (8 * (size_t)BN * KCc * T * num_kb));
+        const int co = nb * BN + nn;
+        const int ci = kb * KC + chunk * 8 + e;
+        float v = 0.f;
+        if (!transposed) {
+            if (co < Cout && ci < Cin) v = w[((size_t)co * Cin + ci) * T + tap];
+        } else {
+            const int ij = co / Cout_p, c = co % Cout_p;
+            if (ij < 4 && c < Cout && ci < Cin) v = w[((size_t)ci * Cout + c) * 4 + ij];
+        }
+        uint16_t bits;
+        if constexpr (BF16) {
+            __nv_bfloat16 h = __float2bfloat16_rn(v);
+            bits = *reinterpret_cast<uint16_t*>(&h);
+        } else {
+            __half h = __float2half_rn(v);
+            bits = *reinterpret_cast<uint16_t*>(&h);
+        }
+        out[i] = bits;
+    }
+}
+
+extern "C" int64_t cwfa_tc_packed_weight_elems(int Cin_p, int Cout_tot_p, int KH, int KW, int BN) {
+    const int KC = pick_kc(Cin_p);
+    if (!KC || Cout_tot_p % BN) return -1;
+    return (int64_t)(Cout_tot_p / BN) * (Cin_p / KC) * KH * KW * (KC / 8) * BN * 8;
+}
+
+extern "C" int cwfa_tc_pack_weights(const float* w, void* packed, int Cout, int Cin, int KH, int KW, int Cin_p,
+                                    int Cout_p, int BN, int transposed, int is_bf16, void* stream) {
+    const int KC = pick_kc(Cin_p);
+    const int tot_p = transposed ? 4 * Cout_p : Cout_p;
+    if (!KC || tot_p % BN || Cin > Cin_p || Cout > Cout_p || (transposed && (KH != 1 || KW != 1))) {
+        set_error("tc_pack_weights: bad shape");
+        return CWFA_EINVAL;
+    }
+    const int T = KH * KW, num_kb = Cin_p / KC, nblks = tot_p / BN;
+    const size_t total = (size_t)nblks * num_kb * T * (KC / 8) * BN * 8;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+    if (is_bf16)
+        pack_weights_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(w, (uint16_t*)packed, Cout, Cin, T, KC, num_kb, BN, nblks, transposed, Cout_p);
+    else
+        pack_weights_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(w, (uint16_t*)packed, Cout, Cin, T, KC, num_kb, BN, nblks, transposed, Cout_p);
+    return check_launch("tc_pack_weights");
+}
+
+extern "C" int cwfa_conv_tc(const void* x_c8, const void* w_packed, const float* bias, const float* slope,
+                            const void* res, void* out, int N, int H, int W, int Cin_p, int Cout, int Cout_p, int KH,
+                            int KW, int BN, int MB, int act, int res_mode, int out_mode, int is_bf16, void* stream) {
+    const int KC = pick_kc(Cin_p);
+    if (N <= 0 || H <= 0 || W <= 0 || !KC || (Cin_p % 16) || (Cout_p % BN) || (BN % 16) || BN < 16 || BN > 256 ||
+        (MB != 1 && MB != 2) || MB * BN > 512 || !(KH & 1) || !(KW & 1) || KH > 7 || KW > 7 || out_mode < 0 ||
+        out_mode > 1) {
+        set_error("conv_tc: unsupported configuration (Cin_p=%d Cout_p=%d BN=%d MB=%d K=%dx%d)", Cin_p, Cout_p, BN, MB, KH, KW);
+        return CWFA_EINVAL;
+    }
+    if (res_mode != 0 && !res) { set_error("conv_tc: res_mode set but res is NULL"); return CWFA_EINVAL; }
+    if ((reinterpret_cast<uintptr_t>(x_c8) & 15) || (reinterpret_cast<uintptr_t>(w_packed) & 15) ||
+        (reinterpret_cast<uintptr_t>(out) & 15)) {
+        set_error("conv_tc: pointers must be 16-byte aligned");
+        return CWFA_EINVAL;
+    }
+    EncodeTiledFn encode = get_encode();
+    if (!encode) { set_error("conv_tc: cuTensorMapEncodeTiled not available"); return CWFA_ECUDA; }
+
+    TcParams p{};
+    p.N = N; p.H = H; p.W = W; p.Cout = Cout; p.Cout_p = Cout_p; p.KH = KH; p.KW = KW;
+    p.MB = MB; p.BN = BN;
+    p.tiles_x = ceil_div(W, 8 * MB);
+    p.tiles_y = ceil_div(H, 16);
+    p.KCc = KC / 8;
+    p.num_kb = Cin_p / KC;
+    p.BH = 16 + KH - 1;
+    p.BW = 8 * MB + KW - 1;
+    p.a_bytes = (uint32_t)p.KCc * p.BH * p.BW * 16;
+    p.a_stride = (p.a_bytes + 127u) & ~127u;
+    p.b_bytes = (uint32_t)p.KCc * BN * 16;
+    p.a_stages = p.num_kb > 1 ? 2 : 1;
+    const int total_b = p.num_kb * KH * KW;
+    // keep a CTA under ~100 KB when possible so two CTAs co-reside (one's epilogue overlaps the other's MMAs)
+    const uint32_t budget_small = 100 * 1024, budget_max = 225 * 1024;
+    const uint32_t fixed = 1024 + 256 + p.a_stages * p.a_stride;
+    int bs = total_b < kMaxBStages ? total_b : kMaxBStages;
+    while (bs > 3 && fixed + bs * p.b_bytes > budget_small) --bs;
+    while (bs > 1 && fixed + bs * p.b_bytes > budget_max) --bs;
+    if (fixed + bs * p.b_bytes > budget_max) { set_error("conv_tc: tile does not fit shared memory"); return CWFA_EINVAL; }
+    p.b_stages = bs;
+    p.act = act; p.res_mode = res_mode; p.out_mode = out_mode; p.is_bf16 = is_bf16;
+    p.w_packed = (const uint8_t*)w_packed; p.bias = bias; p.slope = slope; p.res = (const uint8_t*)res; p.out = out;
+    const size_t smem = fixed + (size_t)bs * p.b_bytes;
+
+    CUtensorMap tmap;
+    const cuuint64_t gdim[4] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)(Cin_p / 8), (cuuint64_t)N};
+    const cuuint64_t gstr[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)(Cin_p / 8) * H * W * 16};
+    const cuuint32_t box[4] = {(cuuint32_t)p.BW * 8, (cuuint32_t)p.BH, (cuuint32_t)p.KCc, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult cr = encode(&tmap, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4,
+                         const_cast<void*>(x_c8), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) { set_error("conv_tc: cuTensorMapEncodeTiled failed (%d)", (int)cr); return CWFA_ECUDA; }
+
+    auto kern = is_bf16 ? conv_tc_kernel<true> : conv_tc_kernel<false>;
+    static bool attr_done[2] = {false, false};
+    if (!attr_done[is_bf16 ? 1 : 0]) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        attr_done[is_bf16 ? 1 : 0] = true;
+    }
+    const int64_t gx = (int64_t)p.tiles_x * p.tiles_y * N;
+    if (gx > 0x7fffffff) { set_error("conv_tc: grid too large"); return CWFA_EINVAL; }
+    dim3 grid((unsigned)gx, Cout_p / BN);
+    kern<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmap, p);
+    return check_launch("conv_tc");
+}
+
+// ------------------------------------------------------------------ layout converters
+template <bool BF16>
+__global__ void __launch_bounds__(256) nchw_to_c8_kernel(const float* __restrict__ x, uint4* __restrict__ y, int N, int C,
+                                                         int Cp, int64_t P) {
+    const int chunks = Cp / 8;
+    const int64_t total = (int64_t)N * chunks * P;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t pix = i % P;
+        const int ch = (int)((i / P) % chunks);
+        const int n = (int)(i / (P * chunks));
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = ch * 8 + j;
+            v[j] = c < C ? __ldg(x + ((int64_t)n * C + c) * P + pix) : 0.f;
+        }
+        uint4 o;
+        o.x = pack2<BF16>(v[0], v[1]); o.y = pack2<BF16>(v[2], v[3]);
+        o.z = pack2<BF16>(v[4], v[5]); o.w = pack2<BF16>(v[6], v[7]);
+        y[i] = o;
+    }
+}
+template <bool BF16>
+__global__ void __launch_bounds__(256) c8_to_nchw_kernel(const uint4* __restrict__ x, float* __restrict__ y, int N, int C,
+                                                         int Cp, int64_t P) {
+    const int chunks = Cp / 8;
+    const int64_t total = (int64_t)N * chunks * P;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t pix = i % P;
+        const int ch = (int)((i / P) % chunks);
+        const int n = (int)(i / (P * chunks));
+        const uint4 u = __ldg(x + i);
+        const float2 a = unpack2<BF16>(u.x), b = unpack2<BF16>(u.y), c = unpack2<BF16>(u.z), d = unpack2<BF16>(u.w);
+        const float v[8] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int cc = ch * 8 + j;
+            if (cc < C) y[((int64_t)n * C + cc) * P + pix] = v[j];
+        }
+    }
+}
+extern "C" int cwfa_nchw_to_c8(const float* x, void* y, int N, int C, int Cp, int64_t P, int is_bf16, void* stream) {
+    if (N <= 0 || C <= 0 || Cp < C || (Cp % 8) || P <= 0) { set_error("nchw_to_c8: bad shape"); return CWFA_EINVAL; }
+    const int64_t total = (int64_t)N * (Cp / 8) * P;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    if (is_bf16) nchw_to_c8_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, (uint4*)y, N, C, Cp, P);
+    else nchw_to_c8_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, (uint4*)y, N, C, Cp, P);
+    return check_launch("nchw_to_c8");
+}
+extern "C" int cwfa_c8_to_nchw(const void* x, float* y, int N, int C, int Cp, int64_t P, int is_bf16, void* stream) {
+    if (N <= 0 || C <= 0 || Cp < C || (Cp % 8) || P <= 0) { set_error("c8_to_nchw: bad shape"); return CWFA_EINVAL; }
+    const int64_t total = (int64_t)N * (Cp / 8) * P;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    if (is_bf16) c8_to_nchw_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>((const uint4*)x, y, N, C, Cp, P);
+    else c8_to_nchw_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>((const uint4*)x, y, N, C, Cp, P);
+    return check_launch("c8_to_nchw");
+}

@@ -1,0 +1,126 @@
+"""Tensor-core side: C8 half-precision tensors, packed weights and the tcgen05 convolution wrapper.
+
+C8 layout: [N][Cp/8][H][W][8] bf16 (default) or fp16, Cp = channels rounded up to a multiple of 16.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib
+from .ops import _ck, _p, _stream
+
+_DTYPES = {"bf16": (torch.bfloat16, 1), "fp16": (torch.float16, 0)}
+
+
+def pad16(c: int) -> int:
+    return (c + 15) // 16 * 16
+
+
+class C8:
+    """A (N, C, H, W) activation stored as [N][Cp/8][H][W][8] half precision."""
+
+    __slots__ = ("data", "C", "kind")
+
+    def __init__(self, data: torch.Tensor, C: int, kind: str):
+        self.data, self.C, self.kind = data, C, kind
+
+    @property
+    def N(self): return self.data.shape[0]
+    @property
+    def Cp(self): return self.data.shape[1] * 8
+    @property
+    def H(self): return self.data.shape[2]
+    @property
+    def W(self): return self.data.shape[3]
+    @property
+    def is_bf16(self): return _DTYPES[self.kind][1]
+
+    @staticmethod
+    def empty(N, C, H, W, device, kind="bf16", Cp: Optional[int] = None) -> "C8":
+        Cp = pad16(C) if Cp is None else Cp
+        return C8(torch.empty((N, Cp // 8, H, W, 8), device=device, dtype=_DTYPES[kind][0]), C, kind)
+
+
+def to_c8(x: torch.Tensor, kind: str = "bf16", Cp: Optional[int] = None) -> C8:
+    x = _ck(x, "x")
+    N, C, H, W = x.shape
+    out = C8.empty(N, C, H, W, x.device, kind, Cp)
+    _lib.call("cwfa_nchw_to_c8", x.data_ptr(), out.data.data_ptr(), N, C, out.Cp, H * W, out.is_bf16, _stream())
+    return out
+
+
+def from_c8(x: C8) -> torch.Tensor:
+    y = torch.empty((x.N, x.C, x.H, x.W), device=x.data.device, dtype=torch.float32)
+    _lib.call("cwfa_c8_to_nchw", x.data.data_ptr(), y.data_ptr(), x.N, x.C, x.Cp, x.H * x.W, x.is_bf16, _stream())
+    return y
+
+
+def pick_bn(cout_p: int) -> int:
+    """Largest legal N tile (multiple of 16, <= 256) that divides the padded output channels."""
+    for bn in (256, 128, 96, 64, 48, 32, 16):
+        if cout_p % bn == 0:
+            return bn
+    raise ValueError(cout_p)
+
+
+class PackedConv:
+    """Weights of one Conv2d packed for the streamed B operand, plus padded bias."""
+
+    def __init__(self, weight: torch.Tensor, bias: Optional[torch.Tensor], kind: str = "bf16", bn: Optional[int] = None,
+                 cin_p: Optional[int] = None, transposed: bool = False):
+        w = _ck(weight.detach(), "weight")
+        if transposed:                      # ConvTranspose2d(k=2,s=2): (Cin, Cout, 2, 2) -> 1x1 conv to 4*Cout_p channels
+            Cin, Cout = w.shape[0], w.shape[1]
+            KH = KW = 1
+        else:
+            Cout, Cin, KH, KW = w.shape
+        self.Cin, self.Cout, self.KH, self.KW, self.kind = Cin, Cout, KH, KW, kind
+        self.transposed = transposed
+        self.Cin_p = pad16(Cin) if cin_p is None else cin_p
+        self.Cout_p = pad16(Cout)
+        tot_p = 4 * self.Cout_p if transposed else self.Cout_p
+        self.BN = pick_bn(tot_p if not transposed else self.Cout_p) if bn is None else bn
+        self.tot_p = tot_p
+        lib = _lib.load()
+        n = lib.cwfa_tc_packed_weight_elems(self.Cin_p, tot_p, KH, KW, self.BN)
+        if n < 0:
+            raise ValueError(f"cannot pack conv Cin_p={self.Cin_p} Cout_p={tot_p} BN={self.BN}")
+        self.packed = torch.empty(n, device=w.device, dtype=_DTYPES[kind][0])
+        _lib.call("cwfa_tc_pack_weights", w.data_ptr(), self.packed.data_ptr(), Cout, Cin, KH, KW, self.Cin_p, self.Cout_p,
+                  self.BN, int(transposed), _DTYPES[kind][1], _stream())
+        self.bias = None
+        if bias is not None:
+            b = torch.zeros(tot_p, device=w.device, dtype=torch.float32)
+            if transposed:
+                b.view(4, self.Cout_p)[:, :Cout] = bias.detach().float()
+            else:
+                b[:Cout] = bias.detach().float()
+            self.bias = b
+
+
+def conv_tc(x: C8, pc: PackedConv, *, act: int = 0, slope: Optional[torch.Tensor] = None, res=None, res_mode: int = 0,
+            out_nchw: bool = False, mb: Optional[int] = None):
+    """Implicit-GEMM convolution on the tensor cores.  Returns a C8 tensor (or NCHW fp32 if out_nchw)."""
+    if x.Cp != pc.Cin_p or x.kind != pc.kind:
+        raise ValueError(f"conv_tc: input has Cp={x.Cp}/{x.kind}, weights expect Cin_p={pc.Cin_p}/{pc.kind}")
+    if pc.transposed:
+        raise ValueError("use conv_transpose_tc for transposed weights")
+    N, H, W = x.N, x.H, x.W
+    if mb is None:
+        mb = 2 if (pc.BN * 2 <= 512 and W > 8) else 1
+    dev = x.data.device
+    if out_nchw:
+        out = torch.empty((N, pc.Cout, H, W), device=dev, dtype=torch.float32)
+        out_ptr, res_ptr = out.data_ptr(), (None if res is None else _ck(res, "res").data_ptr())
+    else:
+        out = C8.empty(N, pc.Cout, H, W, dev, x.kind, pc.Cout_p)
+        out_ptr, res_ptr = out.data.data_ptr(), (None if res is None else res.data.data_ptr())
+        if res is not None and (res.Cp != pc.Cout_p or res.kind != x.kind):
+            raise ValueError("conv_tc: residual layout mismatch")
+    slope_t = None if slope is None else _ck(slope.detach(), "slope")
+    _lib.call("cwfa_conv_tc", x.data.data_ptr(), pc.packed.data_ptr(), _p(pc.bias), _p(slope_t), res_ptr, out_ptr,
+              N, H, W, pc.Cin_p, pc.Cout, pc.Cout_p, pc.KH, pc.KW, pc.BN, mb, act, res_mode if res is not None else 0,
+              1 if out_nchw else 0, x.is_bf16, _stream())
+    return out

@@ -124,6 +124,27 @@ int cwfa_layernorm_chw_f32(const float* x, const float* gamma, const float* beta
 /* x += m * 2 * (g - 0.5)   (networks.py:554) */
 int cwfa_gate_add_f32(float* x, const float* m, const float* g, int64_t n, void* stream);
 
+/* ---- K2: tcgen05 / TMEM / TMA implicit-GEMM convolution (bf16 or fp16 operands, fp32 accumulate) --
+ * The throughput path for every wide convolution of the path: coupling sub-network trunk
+ * (networks.py:621-638), conditioning-net 2-D convs (:211-219), LRNN U-Net (unet.py:99-104,166) and
+ * the ConvNeXt 7x7 (networks.py:489).  'same' zero padding, stride 1, KH/KW odd <= 7.
+ * x_c8: C8 activations with Cin_p channels (multiple of 16).  w_packed: from cwfa_tc_pack_weights.
+ * bias: Cout_p floats (zero padded) or NULL.  v = conv + bias; res_mode 1: v += res; v = act(v);
+ * res_mode 2: v += res.  out_mode 0: C8 (Cout_p channels; res is C8), out_mode 1: NCHW fp32 with Cout
+ * channels (res is NCHW fp32).  BN = output channels per CTA (multiple of 16, <= 256, divides Cout_p),
+ * MB = number of 16x8-pixel M=128 blocks per CTA (1 or 2), MB*BN <= 512 TMEM columns. */
+int cwfa_tc_kc(int cin_p);
+int64_t cwfa_tc_packed_weight_elems(int Cin_p, int Cout_tot_p, int KH, int KW, int BN);
+int cwfa_tc_pack_weights(const float* w, void* packed, int Cout, int Cin, int KH, int KW, int Cin_p,
+                         int Cout_p, int BN, int transposed, int is_bf16, void* stream);
+int cwfa_conv_tc(const void* x_c8, const void* w_packed, const float* bias, const float* slope,
+                 const void* res, void* out, int N, int H, int W, int Cin_p, int Cout, int Cout_p,
+                 int KH, int KW, int BN, int MB, int act, int res_mode, int out_mode, int is_bf16,
+                 void* stream);
+/* Layout converters NCHW fp32 <-> C8 half (channels padded with zeros up to Cp). */
+int cwfa_nchw_to_c8(const float* x, void* y, int N, int C, int Cp, int64_t P, int is_bf16, void* stream);
+int cwfa_c8_to_nchw(const void* x, float* y, int N, int C, int Cp, int64_t P, int is_bf16, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
