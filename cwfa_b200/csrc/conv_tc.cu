@@ -74,6 +74,20 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+__device__ __forceinline__ void tc_mma_f16_split(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                                 uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n.reg .pred p;\n.reg .b64 da, db;\nsetp.ne.b32 p, %6, 0;\n"
+        "mov.b64 da, {%1, %2};\nmov.b64 db, {%3, %4};\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n}" ::"r"(tmem_d),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+    return pred;
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -108,10 +122,21 @@ struct TcParams {
     const float* slope;
     const uint8_t* res;
     void* out;
+    unsigned long long* dbg;      // optional: 8 globaltimer stamps per CTA (profiling aid, NULL = off)
 };
 
+__device__ __forceinline__ void stamp(const TcParams& p, int slot) {
+    if (p.dbg) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.dbg[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 + slot] = t;
+    }
+}
+
 constexpr int kMaxBStages = 8;
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;        // warp0 TMA, warp1 MMA, warps 2..9 epilogue
+constexpr int kEpiThreads = 256;
+constexpr int kHeaderBytes = 2048;   // barriers, tmem slot, bias stage
 
 template <bool BF16>
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
@@ -132,11 +157,40 @@ __device__ __forceinline__ float2 unpack2(uint32_t u) {
     }
 }
 
+// Activation on a register vector; the (warp-uniform) switch sits OUTSIDE the element loop.
+// ELU uses ex2.approx (error << the half-precision store rounding of this path).
+template <int NV>
+__device__ __forceinline__ void act_vec(float (&x)[NV], int act, float slope) {
+    switch (act) {
+        case CWFA_ACT_ELU:
+#pragma unroll
+            for (int j = 0; j < NV; ++j) x[j] = x[j] > 0.f ? x[j] : __expf(x[j]) - 1.f;
+            break;
+        case CWFA_ACT_PRELU:
+#pragma unroll
+            for (int j = 0; j < NV; ++j) x[j] = x[j] >= 0.f ? x[j] : slope * x[j];
+            break;
+        case CWFA_ACT_RELU:
+#pragma unroll
+            for (int j = 0; j < NV; ++j) x[j] = fmaxf(x[j], 0.f);
+            break;
+        case CWFA_ACT_GELU:
+#pragma unroll
+            for (int j = 0; j < NV; ++j) x[j] = 0.5f * x[j] * (1.f + erff(x[j] * 0.70710678118654752440f));
+            break;
+        case CWFA_ACT_SIGMOID:
+#pragma unroll
+            for (int j = 0; j < NV; ++j) x[j] = 1.f / (1.f + __expf(-x[j]));
+            break;
+        default: break;
+    }
+}
+
 template <bool BF16>
 __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    // [0,256): barriers + tmem slot; then A ring, then B ring
+    // [0,2048): barriers + tmem slot + bias stage; then A ring, then B ring
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
     const uint32_t bar0 = smem_u32(bars);
     auto a_full = [&](int s) { return bar0 + 8u * s; };                 // 2
@@ -145,7 +199,8 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
     auto b_empty = [&](int s) { return bar0 + 8u * (12 + s); };         // 8
     const uint32_t acc_full = bar0 + 8u * 20;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 8 * 24);
-    const uint32_t a_base = smem_u32(smem + 256);
+    float* s_bias = reinterpret_cast<float*>(smem + 1024);           // up to 256 floats
+    const uint32_t a_base = smem_u32(smem + kHeaderBytes);
     const uint32_t b_base = a_base + p.a_stages * p.a_stride;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -160,6 +215,7 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
     uint32_t tmem_cols = 32;
     while ((int)tmem_cols < tmem_cols_needed) tmem_cols <<= 1;
 
+    if (threadIdx.x == 0) stamp(p, 0);
     if (threadIdx.x == 0) {
         for (int s = 0; s < 2; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
         for (int s = 0; s < kMaxBStages; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
@@ -176,6 +232,7 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) stamp(p, 1);
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -198,114 +255,145 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
-            const uint32_t fmt = p.is_bf16 ? 1u : 0u;
-            const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
-            const uint32_t a_sbo = p.BW * 16, a_lbo = p.BH * p.BW * 16;
-            const uint32_t b_sbo = 128, b_lbo = p.BN * 16;
-            const int ksteps = p.KCc / 2;
-            for (int kb = 0; kb < p.num_kb; ++kb) {
-                const int sa = kb % p.a_stages;
-                mbar_wait(a_full(sa), (kb / p.a_stages) & 1);
-                const uint32_t a_s = a_base + sa * p.a_stride;
-                for (int tap = 0; tap < T; ++tap) {
-                    const int it = kb * T + tap;
+        // The whole warp walks the pipeline (uniform control flow, descriptor arithmetic in 32-bit);
+        // one elected lane issues the tcgen05.mma / tcgen05.commit instructions.
+        const uint32_t fmt = p.is_bf16 ? 1u : 0u;
+        const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
+        const uint32_t a_lbo = p.BH * p.BW * 16, b_lbo = p.BN * 16;
+        const uint32_t a_hi = ((uint32_t)(p.BW * 16) >> 4) | (1u << 14);       // SBO | version
+        const uint32_t b_hi = (128u >> 4) | (1u << 14);
+        const uint32_t a_lbo_enc = ((a_lbo >> 4) & 0x3FFFu) << 16, b_lbo_enc = ((b_lbo >> 4) & 0x3FFFu) << 16;
+        const uint32_t a_kstep = (2 * a_lbo) >> 4, b_kstep = (2 * b_lbo) >> 4;   // per K=16 step, in 16-byte units
+        const int ksteps = p.KCc / 2;
+        const uint32_t leader = elect_one();
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+            const int sa = kb % p.a_stages;
+            mbar_wait(a_full(sa), (kb / p.a_stages) & 1);
+            if (kb == 0 && leader) stamp(p, 2);
+            const uint32_t a_s = a_base + sa * p.a_stride;
+            int it = kb * T;
+            for (int kh = 0; kh < p.KH; ++kh) {
+                for (int kw = 0; kw < p.KW; ++kw, ++it) {
                     const int sb = it % p.b_stages;
                     mbar_wait(b_full(sb), (it / p.b_stages) & 1);
+                    if (it == 0 && leader) stamp(p, 3);
                     tc_fence_after();
-                    const int kh = tap / p.KW, kw = tap % p.KW;
-                    const uint32_t b_s = b_base + sb * p.b_bytes;
-                    for (int mb = 0; mb < p.MB; ++mb) {
-                        const uint32_t a_tap = a_s + (uint32_t)((kh * p.BW + mb * 8 + kw) * 16);
-                        for (int kk = 0; kk < ksteps; ++kk) {
-                            const uint64_t ad = make_desc(a_tap + kk * 2 * a_lbo, a_lbo, a_sbo);
-                            const uint64_t bd = make_desc(b_s + kk * 2 * b_lbo, b_lbo, b_sbo);
-                            tc_mma_f16(tmem_base + mb * p.BN, ad, bd, idesc, (kb | tap | kk) ? 1u : 0u);
+                    const uint32_t a_lo0 = (((a_s + (uint32_t)((kh * p.BW + kw) * 16)) & 0x3FFFFu) >> 4) | a_lbo_enc;
+                    const uint32_t b_lo0 = (((b_base + sb * p.b_bytes) & 0x3FFFFu) >> 4) | b_lbo_enc;
+                    if (leader) {
+                        for (int mb = 0; mb < p.MB; ++mb) {
+                            const uint32_t d = tmem_base + mb * p.BN;
+                            uint32_t al = a_lo0 + mb * 8, bl = b_lo0;
+                            for (int kk = 0; kk < ksteps; ++kk, al += a_kstep, bl += b_kstep)
+                                tc_mma_f16_split(d, al, a_hi, bl, b_hi, idesc, (it | kk) ? 1u : 0u);
                         }
+                        tc_commit(b_empty(sb));
                     }
-                    tc_commit(b_empty(sb));
+                    __syncwarp();
                 }
-                tc_commit(a_empty(sa));
             }
+            if (leader) tc_commit(a_empty(sa));
+            __syncwarp();
+        }
+        if (leader) {
+            stamp(p, 4);
             tc_commit(acc_full);
         }
         __syncwarp();
     } else {
-        // ===================== epilogue =====================
-        const int q = warp & 3;                  // TMEM lane quadrant this warp may access
+        // ===================== epilogue (8 warps) =====================
+        const int q = warp & 3;                      // TMEM lane quadrant this warp may access
+        const int half = (warp - 2) >> 2;            // two warps per quadrant split the column groups
         const int m = q * 32 + lane;
         const int orow = h0 + (m >> 3);
         const bool row_ok = orow < p.H;
         const float slope = (p.act == CWFA_ACT_PRELU && p.slope) ? __ldg(p.slope) : 0.f;
         const size_t plane = (size_t)p.H * p.W;
+        for (int i = threadIdx.x - 64; i < p.BN; i += kEpiThreads) s_bias[i] = p.bias ? __ldg(p.bias + nblk * p.BN + i) : 0.f;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         mbar_wait(acc_full, 0);
         tc_fence_after();
-        for (int mb = 0; mb < p.MB; ++mb) {
+        if (threadIdx.x == 64) stamp(p, 5);
+        const int gpm = p.BN >> 4;                   // 16-column groups per M-block
+        const int ngroups = p.MB * gpm;
+        for (int g = half; g < ngroups; g += 2) {
+            const int mb = g / gpm;
+            const int c0 = (g - mb * gpm) << 4;
             const int ocol = w0 + mb * 8 + (m & 7);
             const bool ok = row_ok && ocol < p.W;
             const size_t pix = (size_t)orow * p.W + ocol;
-            for (int c0 = 0; c0 < p.BN; c0 += 16) {
-                uint32_t r[16];
-                __syncwarp();
-                tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mb * p.BN + c0), r);
-                const int cg = nblk * p.BN + c0;             // first global (padded) output channel of this group
-                float v[16];
+            uint32_t r[16];
+            __syncwarp();
+            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mb * p.BN + c0), r);
+            const int cg = nblk * p.BN + c0;             // first global (padded) output channel of this group
+            float v[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + cg + j) : 0.f);
-                if (!ok) {
-                    // masked pixel (image edge inside the tile): nothing to store
-                } else if (p.out_mode == 1) {
-                    // NCHW fp32 (res, if any, is NCHW fp32 too)
-                    float* out = reinterpret_cast<float*>(p.out);
-                    const float* res = reinterpret_cast<const float*>(p.res);
+            for (int j = 0; j < 16; j += 4) {
+                const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c0 + j);
+                v[j] = __uint_as_float(r[j]) + b4.x;
+                v[j + 1] = __uint_as_float(r[j + 1]) + b4.y;
+                v[j + 2] = __uint_as_float(r[j + 2]) + b4.z;
+                v[j + 3] = __uint_as_float(r[j + 3]) + b4.w;
+            }
+            if (!ok) {
+                // masked pixel (image edge inside the tile): nothing to store
+            } else if (p.out_mode == 1) {
+                // NCHW fp32 (res, if any, is NCHW fp32 too)
+                float* out = reinterpret_cast<float*>(p.out);
+                const float* res = reinterpret_cast<const float*>(p.res);
+                const size_t o0 = ((size_t)n * p.Cout + cg) * plane + pix;
+                if (p.res_mode == 1) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int co = cg + j;
-                        if (co < p.Cout) {
-                            const size_t o = ((size_t)n * p.Cout + co) * plane + pix;
-                            float x = v[j];
-                            if (p.res_mode == 1) x += __ldg(res + o);
-                            x = apply_act(x, p.act, slope);
-                            if (p.res_mode == 2) x += __ldg(res + o);
-                            out[o] = x;
-                        }
-                    }
-                } else {
-                    // C8 half output: two 16-byte chunks
-                    const int cchunks = p.Cout_p >> 3;
+                    for (int j = 0; j < 16; ++j) if (cg + j < p.Cout) v[j] += __ldg(res + o0 + j * plane);
+                }
+                act_vec<16>(v, p.act, slope);
+                if (p.res_mode == 2) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) if (cg + j < p.Cout) v[j] += __ldg(res + o0 + j * plane);
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) if (cg + j < p.Cout) out[o0 + j * plane] = v[j];
+            } else {
+                // C8 half output: two 16-byte chunks per pixel
+                const int cchunks = p.Cout_p >> 3;
+                const size_t o = (((size_t)n * cchunks + (cg >> 3)) * plane + pix) * 16;   // byte offset of chunk 0
+                const size_t cstride = plane * 16;
+                float rv[16];
+                if (p.res_mode != 0) {
 #pragma unroll
                     for (int hh = 0; hh < 2; ++hh) {
-                        const size_t o = (((size_t)n * cchunks + (cg >> 3) + hh) * plane + pix) * 8;   // element offset
-                        float x[8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) x[j] = v[hh * 8 + j];
-                        if (p.res_mode != 0) {
-                            const uint4 rr = __ldg(reinterpret_cast<const uint4*>(p.res + o * 2));
-                            const float2 r0 = unpack2<BF16>(rr.x), r1 = unpack2<BF16>(rr.y), r2 = unpack2<BF16>(rr.z),
-                                         r3 = unpack2<BF16>(rr.w);
-                            const float rv[8] = {r0.x, r0.y, r1.x, r1.y, r2.x, r2.y, r3.x, r3.y};
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                if (p.res_mode == 1) x[j] = apply_act(x[j] + rv[j], p.act, slope);
-                                else x[j] = apply_act(x[j], p.act, slope) + rv[j];
-                            }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) x[j] = apply_act(x[j], p.act, slope);
-                        }
-                        uint4 ov;
-                        ov.x = pack2<BF16>(x[0], x[1]);
-                        ov.y = pack2<BF16>(x[2], x[3]);
-                        ov.z = pack2<BF16>(x[4], x[5]);
-                        ov.w = pack2<BF16>(x[6], x[7]);
-                        *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.out) + o * 2) = ov;
+                        const uint4 rr = __ldg(reinterpret_cast<const uint4*>(p.res + o + hh * cstride));
+                        const float2 r0 = unpack2<BF16>(rr.x), r1 = unpack2<BF16>(rr.y), r2 = unpack2<BF16>(rr.z),
+                                     r3 = unpack2<BF16>(rr.w);
+                        rv[hh * 8 + 0] = r0.x; rv[hh * 8 + 1] = r0.y; rv[hh * 8 + 2] = r1.x; rv[hh * 8 + 3] = r1.y;
+                        rv[hh * 8 + 4] = r2.x; rv[hh * 8 + 5] = r2.y; rv[hh * 8 + 6] = r3.x; rv[hh * 8 + 7] = r3.y;
                     }
+                }
+                if (p.res_mode == 1) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] += rv[j];
+                }
+                act_vec<16>(v, p.act, slope);
+                if (p.res_mode == 2) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] += rv[j];
+                }
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    uint4 ov;
+                    ov.x = pack2<BF16>(v[hh * 8 + 0], v[hh * 8 + 1]);
+                    ov.y = pack2<BF16>(v[hh * 8 + 2], v[hh * 8 + 3]);
+                    ov.z = pack2<BF16>(v[hh * 8 + 4], v[hh * 8 + 5]);
+                    ov.w = pack2<BF16>(v[hh * 8 + 6], v[hh * 8 + 7]);
+                    *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.out) + o + hh * cstride) = ov;
                 }
             }
         }
     }
+    if (threadIdx.x == 64) stamp(p, 6);
     tc_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) stamp(p, 7);
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
@@ -400,6 +488,9 @@ extern "C" int cwfa_tc_pack_weights(const float* w, void* packed, int Cout, int 
     return check_launch("tc_pack_weights");
 }
 
+static unsigned long long* g_tc_dbg = nullptr;
+extern "C" int cwfa_tc_set_debug_buffer(void* buf) { g_tc_dbg = (unsigned long long*)buf; return CWFA_OK; }
+
 extern "C" int cwfa_conv_tc(const void* x_c8, const void* w_packed, const float* bias, const float* slope,
                             const void* res, void* out, int N, int H, int W, int Cin_p, int Cout, int Cout_p, int KH,
                             int KW, int BN, int MB, int act, int res_mode, int out_mode, int is_bf16, void* stream) {
@@ -435,7 +526,7 @@ extern "C" int cwfa_conv_tc(const void* x_c8, const void* w_packed, const float*
     const int total_b = p.num_kb * KH * KW;
     // keep a CTA under ~100 KB when possible so two CTAs co-reside (one's epilogue overlaps the other's MMAs)
     const uint32_t budget_small = 100 * 1024, budget_max = 225 * 1024;
-    const uint32_t fixed = 1024 + 256 + p.a_stages * p.a_stride;
+    const uint32_t fixed = 1024 + kHeaderBytes + p.a_stages * p.a_stride;
     int bs = total_b < kMaxBStages ? total_b : kMaxBStages;
     while (bs > 3 && fixed + bs * p.b_bytes > budget_small) --bs;
     while (bs > 1 && fixed + bs * p.b_bytes > budget_max) --bs;
@@ -443,6 +534,7 @@ extern "C" int cwfa_conv_tc(const void* x_c8, const void* w_packed, const float*
     p.b_stages = bs;
     p.act = act; p.res_mode = res_mode; p.out_mode = out_mode; p.is_bf16 = is_bf16;
     p.w_packed = (const uint8_t*)w_packed; p.bias = bias; p.slope = slope; p.res = (const uint8_t*)res; p.out = out;
+    p.dbg = g_tc_dbg;
     const size_t smem = fixed + (size_t)bs * p.b_bytes;
 
     CUtensorMap tmap;

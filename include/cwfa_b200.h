@@ -141,6 +141,8 @@ int cwfa_conv_tc(const void* x_c8, const void* w_packed, const float* bias, cons
                  const void* res, void* out, int N, int H, int W, int Cin_p, int Cout, int Cout_p,
                  int KH, int KW, int BN, int MB, int act, int res_mode, int out_mode, int is_bf16,
                  void* stream);
+/* Profiling aid: when set (device buffer of 8 uint64 per CTA), conv_tc records globaltimer stamps. */
+int cwfa_tc_set_debug_buffer(void* buf);
 /* Layout converters NCHW fp32 <-> C8 half (channels padded with zeros up to Cp). */
 int cwfa_nchw_to_c8(const float* x, void* y, int N, int C, int Cp, int64_t P, int is_bf16, void* stream);
 int cwfa_c8_to_nchw(const void* x, float* y, int N, int C, int Cp, int64_t P, int is_bf16, void* stream);
