@@ -1,0 +1,169 @@
+// Memory-bound helpers on C8 half-precision tensors for the LRNN U-Net (unet.py:72-113):
+// per-channel batch statistics, BatchNorm apply fused with the 2x2 max-pool, both single pass,
+// 128-bit accesses (one 16-byte chunk = 8 channels of one pixel).
+#include "common.cuh"
+using namespace cwfa;
+
+namespace {
+template <bool BF16>
+__device__ __forceinline__ void unpack8(const uint4& u, float (&v)[8]) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float2 f;
+        if constexpr (BF16) f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+        else f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+        v[2 * i] = f.x;
+        v[2 * i + 1] = f.y;
+    }
+}
+template <bool BF16>
+__device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if constexpr (BF16) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+            w[i] = *reinterpret_cast<uint32_t*>(&h);
+        } else {
+            __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+            w[i] = *reinterpret_cast<uint32_t*>(&h);
+        }
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+constexpr int kC8StatBlocks = 64;    // blocks per chunk
+
+template <bool BF16>
+__global__ void __launch_bounds__(256) c8_stats_kernel(const uint4* __restrict__ x, float* __restrict__ ws, int N,
+                                                       int chunks, int64_t P) {
+    const int ch = blockIdx.y;
+    float s[8], q[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+    const int64_t per = (int64_t)N * P;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < per; i += (int64_t)gridDim.x * blockDim.x) {
+        const int n = (int)(i / P);
+        const int64_t pix = i % P;
+        float v[8];
+        unpack8<BF16>(__ldg(x + ((int64_t)n * chunks + ch) * P + pix), v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s[j] += v[j]; q[j] = fmaf(v[j], v[j], q[j]); }
+    }
+    __shared__ float red[8][16];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        s[j] = warp_sum(s[j]);
+        q[j] = warp_sum(q[j]);
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { red[w][j] = s[j]; red[w][8 + j] = q[j]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 16) {
+        float t = 0.f;
+        for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
+        ws[((int64_t)ch * gridDim.x + blockIdx.x) * 16 + threadIdx.x] = t;
+    }
+}
+__global__ void c8_stats_finalize_kernel(const float* __restrict__ ws, float* __restrict__ stats, int Cp, int nblocks) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= Cp) return;
+    const int ch = c >> 3, j = c & 7;
+    double s = 0.0, q = 0.0;
+    for (int i = 0; i < nblocks; ++i) {
+        s += (double)ws[((int64_t)ch * nblocks + i) * 16 + j];
+        q += (double)ws[((int64_t)ch * nblocks + i) * 16 + 8 + j];
+    }
+    stats[c] = (float)s;
+    stats[Cp + c] = (float)q;
+}
+
+// y = x*scale[c] + shift[c]; optionally also the 2x2 max-pooled tensor.  One thread per 2x2 pixel block
+// and chunk (or per pixel when POOL is false).
+template <bool BF16, bool POOL>
+__global__ void __launch_bounds__(256) c8_bn_apply_kernel(const uint4* __restrict__ x, const float* __restrict__ scale,
+                                                          const float* __restrict__ shift, uint4* __restrict__ y,
+                                                          uint4* __restrict__ ypool, int N, int chunks, int H, int W) {
+    const int H2 = POOL ? H / 2 : H, W2 = POOL ? W / 2 : W;
+    const int64_t total = (int64_t)N * chunks * H2 * W2;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int w2 = (int)(i % W2);
+        const int h2 = (int)((i / W2) % H2);
+        const int ch = (int)((i / ((int64_t)W2 * H2)) % chunks);
+        const int n = (int)(i / ((int64_t)W2 * H2 * chunks));
+        float sc[8], sh[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { sc[j] = __ldg(scale + ch * 8 + j); sh[j] = __ldg(shift + ch * 8 + j); }
+        const int64_t base = ((int64_t)n * chunks + ch) * H * W;
+        if constexpr (POOL) {
+            float mx[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) mx[j] = -INFINITY;
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 2; ++dx) {
+                    const int64_t o = base + (int64_t)(2 * h2 + dy) * W + 2 * w2 + dx;
+                    float v[8];
+                    unpack8<BF16>(__ldg(x + o), v);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { v[j] = fmaf(v[j], sc[j], sh[j]); }
+                    const uint4 pk = pack8<BF16>(v);
+                    y[o] = pk;
+                    float r[8];
+                    unpack8<BF16>(pk, r);      // pool the ROUNDED values so pooled == max of what is stored
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) mx[j] = fmaxf(mx[j], r[j]);
+                }
+            ypool[(((int64_t)n * chunks + ch) * H2 + h2) * W2 + w2] = pack8<BF16>(mx);
+        } else {
+            const int64_t o = base + (int64_t)h2 * W + w2;
+            float v[8];
+            unpack8<BF16>(__ldg(x + o), v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
+            y[o] = pack8<BF16>(v);
+        }
+    }
+}
+}  // namespace
+
+extern "C" int cwfa_c8_stats_workspace_floats(int Cp) { return (Cp / 8) * kC8StatBlocks * 16; }
+
+extern "C" int cwfa_c8_channel_stats(const void* x, float* stats, float* workspace, int N, int Cp, int64_t P,
+                                     int is_bf16, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N <= 0 || Cp <= 0 || (Cp % 8) || P <= 0) { set_error("c8_channel_stats: bad shape"); return CWFA_EINVAL; }
+    dim3 grid(kC8StatBlocks, Cp / 8);
+    if (is_bf16) c8_stats_kernel<true><<<grid, 256, 0, st>>>((const uint4*)x, workspace, N, Cp / 8, P);
+    else c8_stats_kernel<false><<<grid, 256, 0, st>>>((const uint4*)x, workspace, N, Cp / 8, P);
+    int rc = check_launch("c8_stats");
+    if (rc) return rc;
+    c8_stats_finalize_kernel<<<ceil_div(Cp, 128), 128, 0, st>>>(workspace, stats, Cp, kC8StatBlocks);
+    return check_launch("c8_stats_finalize");
+}
+
+extern "C" int cwfa_c8_bn_apply(const void* x, const float* scale, const float* shift, void* y, void* ypool, int N,
+                                int Cp, int H, int W, int is_bf16, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N <= 0 || Cp <= 0 || (Cp % 8) || H <= 0 || W <= 0) { set_error("c8_bn_apply: bad shape"); return CWFA_EINVAL; }
+    const bool pool = ypool != nullptr;
+    if (pool && ((H & 1) || (W & 1))) { set_error("c8_bn_apply: pooling needs even H, W"); return CWFA_EINVAL; }
+    const int64_t total = (int64_t)N * (Cp / 8) * (pool ? (H / 2) * (W / 2) : H * W);
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    const uint4* xi = (const uint4*)x;
+    uint4 *yo = (uint4*)y, *yp = (uint4*)ypool;
+    if (is_bf16) {
+        if (pool) c8_bn_apply_kernel<true, true><<<blocks, 256, 0, st>>>(xi, scale, shift, yo, yp, N, Cp / 8, H, W);
+        else c8_bn_apply_kernel<true, false><<<blocks, 256, 0, st>>>(xi, scale, shift, yo, yp, N, Cp / 8, H, W);
+    } else {
+        if (pool) c8_bn_apply_kernel<false, true><<<blocks, 256, 0, st>>>(xi, scale, shift, yo, yp, N, Cp / 8, H, W);
+        else c8_bn_apply_kernel<false, false><<<blocks, 256, 0, st>>>(xi, scale, shift, yo, yp, N, Cp / 8, H, W);
+    }
+    return check_launch("c8_bn_apply");
+}

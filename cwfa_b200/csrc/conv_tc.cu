@@ -354,10 +354,20 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
 #pragma unroll
                 for (int j = 0; j < 16; ++j) if (cg + j < p.Cout) out[o0 + j * plane] = v[j];
             } else {
-                // C8 half output: two 16-byte chunks per pixel
+                // C8 half output: two 16-byte chunks per pixel.  out_mode 2 = ConvTranspose2d(k=2,s=2) as a
+                // 1x1 conv to 4*Cout_p channels: channel block -> (i,j) sub-pixel, scattered to (2h+i, 2w+j).
                 const int cchunks = p.Cout_p >> 3;
-                const size_t o = (((size_t)n * cchunks + (cg >> 3)) * plane + pix) * 16;   // byte offset of chunk 0
-                const size_t cstride = plane * 16;
+                size_t o, cstride;
+                if (p.out_mode == 2) {
+                    const int ij = cg / p.Cout_p, co = cg - ij * p.Cout_p;
+                    const size_t plane2 = plane * 4;
+                    const size_t pix2 = (size_t)(2 * orow + (ij >> 1)) * (2 * p.W) + 2 * ocol + (ij & 1);
+                    o = (((size_t)n * cchunks + (co >> 3)) * plane2 + pix2) * 16;
+                    cstride = plane2 * 16;
+                } else {
+                    o = (((size_t)n * cchunks + (cg >> 3)) * plane + pix) * 16;   // byte offset of chunk 0
+                    cstride = plane * 16;
+                }
                 float rv[16];
                 if (p.res_mode != 0) {
 #pragma unroll
@@ -497,7 +507,7 @@ extern "C" int cwfa_conv_tc(const void* x_c8, const void* w_packed, const float*
     const int KC = pick_kc(Cin_p);
     if (N <= 0 || H <= 0 || W <= 0 || !KC || (Cin_p % 16) || (Cout_p % BN) || (BN % 16) || BN < 16 || BN > 256 ||
         (MB != 1 && MB != 2) || MB * BN > 512 || !(KH & 1) || !(KW & 1) || KH > 7 || KW > 7 || out_mode < 0 ||
-        out_mode > 1) {
+        out_mode > 2 || (out_mode == 2 && (KH != 1 || KW != 1))) {
         set_error("conv_tc: unsupported configuration (Cin_p=%d Cout_p=%d BN=%d MB=%d K=%dx%d)", Cin_p, Cout_p, BN, MB, KH, KW);
         return CWFA_EINVAL;
     }
@@ -555,7 +565,7 @@ extern "C" int cwfa_conv_tc(const void* x_c8, const void* w_packed, const float*
     }
     const int64_t gx = (int64_t)p.tiles_x * p.tiles_y * N;
     if (gx > 0x7fffffff) { set_error("conv_tc: grid too large"); return CWFA_EINVAL; }
-    dim3 grid((unsigned)gx, Cout_p / BN);
+    dim3 grid((unsigned)gx, (out_mode == 2 ? 4 : 1) * Cout_p / BN);
     kern<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmap, p);
     return check_launch("conv_tc");
 }

@@ -1,0 +1,266 @@
+"""Throughput engine for the CWFA hot path: the same arithmetic as ``CWFAModel.reconstruct`` /
+``forward_nll`` (pipeline.py) but with every wide convolution on the tcgen05 tensor-core kernel
+(C8 half-precision activations, fp32 accumulation), weights packed once, no per-call parameter
+handling, and optional whole-frame CUDA-graph replay.
+
+Numerics: operands are rounded to ``kind`` ('bf16' default, 'fp16'); the coupling coefficients
+(the last conv of every sub-network), the affine couplings, log-dets, the Haar transforms, the
+depth stencil of the conditioning net and the 6-channel mean-volume branch stay in fp32.
+Stated tolerance vs the fp32 reference: rel-L2 <= 2e-2 (bf16) / 3e-3 (fp16) on the reconstruction
+(tests/test_gpu_engine.py reports the measured values per level).
+
+Reference path: CWFA.py:865-924 (inverse), :156-196 / :966-978 (forward NLL).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import modules as Fm
+from . import networks, ops, tc
+from .pipeline import CWFAModel
+
+
+class _Subnet:
+    """Packed weights of one wavelet_flow_subnetwork2D(_first) (networks.py:586-706)."""
+
+    def __init__(self, sub, kind):
+        self.normal = sub.normal
+        first = sub.block12 if sub.normal else sub.block1
+        self.inp = tc.PackedConv(first.weight, first.bias, kind)
+        self.res = []
+        for name in ("block2", "block4", "block6"):
+            blk = getattr(sub, name)
+            self.res.append((tc.PackedConv(blk[0].weight, blk[0].bias, kind), tc.PackedConv(blk[2].weight, blk[2].bias, kind)))
+        last = sub.block72[1] if sub.normal else sub.block7[1]
+        self.out = tc.PackedConv(last.weight, last.bias, kind)
+
+    def __call__(self, lf8: tc.C8) -> torch.Tensor:
+        """LF condition (C8) -> fp32 NCHW coefficient tensor (2ch channels, or ch for the _first variant)."""
+        b = tc.conv_tc(lf8, self.inp)
+        for p3, p1 in self.res:
+            t = tc.conv_tc(b, p3, act=ops.ACT_ELU)
+            b = tc.conv_tc(t, p1, act=ops.ACT_ELU, res=b, res_mode=1)
+        return tc.conv_tc(b, self.out, out_nchw=True)
+
+
+class _CondNet:
+    """cond_network / ResidualBlock (networks.py:165-242): 2-D convs on tensor cores, depth stencil fp32."""
+
+    def __init__(self, net, kind):
+        rb = net.subnetworks[0]
+        self.rb = rb
+        self.c1 = tc.PackedConv(rb.conv1[0].weight, rb.conv1[0].bias, kind)
+        self.ds = tc.PackedConv(rb.downsample[0].weight, rb.downsample[0].bias, kind)
+        self.c2 = tc.PackedConv(rb.conv2[0].weight, rb.conv2[0].bias, kind)
+
+    def __call__(self, v8: tc.C8) -> torch.Tensor:
+        rb = self.rb
+        out = tc.conv_tc(v8, self.c1, act=ops.ACT_PRELU, slope=rb.conv1[1].weight)
+        res = tc.conv_tc(v8, self.ds, out_nchw=True)
+        out = tc.conv_tc(out, self.c2, act=ops.ACT_PRELU, slope=rb.relu.weight, res=res, res_mode=1, out_nchw=True)
+        c3 = rb.conv3d
+        return ops.depth_stencil3d(out, c3[0].weight, c3[0].bias, c3[1].weight, c3[3].weight, c3[3].bias)
+
+
+class _UNet:
+    """LRNN U-Net (unet.py:9-195) in C8: conv+PReLU on tensor cores, BatchNorm (+max-pool) fused passes."""
+
+    def __init__(self, unet, kind):
+        self.unet = unet
+
+        def block(b):
+            return [(tc.PackedConv(b.block[i].weight, b.block[i].bias, kind), b.block[i + 1], b.block[i + 2]) for i in (0, 3)]
+
+        self.down = [block(d) for d in unet.down_path]
+        self.up = [(tc.PackedConv(u.up.weight, u.up.bias, kind, transposed=True), block(u.conv_block)) for u in unet.up_path]
+        self.last = tc.PackedConv(unet.last[0].weight, unet.last[0].bias, kind)
+
+    def _block(self, x, blk, training, pool):
+        (p0, a0, n0), (p1, a1, n1) = blk
+        x = tc.conv_tc(x, p0, act=ops.ACT_PRELU, slope=a0.weight)
+        x = tc.batchnorm_c8(x, n0.weight, n0.bias, n0.running_mean, n0.running_var, batch_stats=training, eps=n0.eps)
+        x = tc.conv_tc(x, p1, act=ops.ACT_PRELU, slope=a1.weight)
+        return tc.batchnorm_c8(x, n1.weight, n1.bias, n1.running_mean, n1.running_var, batch_stats=training, eps=n1.eps,
+                               pool=pool)
+
+    def __call__(self, x8: tc.C8) -> torch.Tensor:
+        training = self.unet.training
+        skips = []
+        nd = len(self.down)
+        for i, blk in enumerate(self.down):
+            if i != nd - 1:
+                full, x8 = self._block(x8, blk, training, True)
+                skips.append(full)
+            else:
+                x8 = self._block(x8, blk, training, False)
+        for i, (up, blk) in enumerate(self.up):
+            x8 = tc.conv_transpose_tc(x8, up, skips[-i - 1])
+            x8 = self._block(x8, blk, training, False)
+        return tc.conv_tc(x8, self.last, act=ops.ACT_PRELU, slope=self.unet.last[1].weight, out_nchw=True)
+
+
+class _LRNN:
+    """Encoder/LRNN (networks.py:505-584)."""
+
+    def __init__(self, enc, kind):
+        net = enc.net
+        self.net = net
+        self.kind = kind
+        self.proj = tc.PackedConv(net.deconv[0].weight, net.deconv[0].bias, kind)
+        self.unet = _UNet(net.deconv[1], kind)
+        cn0 = net.conv3d[0]
+        self.cn0_7x7 = tc.PackedConv(cn0.m[0].weight, cn0.m[0].bias, kind)
+        self.cn0_1x1 = tc.PackedConv(cn0.m[2].weight, cn0.m[2].bias, kind)
+
+    def _convnext_wide(self, cn, x):
+        """ConvNeXt(6 -> 64): the 7x7 64->64 and 1x1 64->64 convs run on the tensor cores."""
+        up = ops.conv2d(x, cn.input.weight, cn.input.bias)
+        m = tc.conv_tc(tc.to_c8(up, self.kind), self.cn0_7x7, out_nchw=True)
+        m = ops.layernorm_chw(m, cn.m[1].weight, cn.m[1].bias, cn.m[1].eps)
+        return tc.conv_tc(tc.to_c8(m, self.kind), self.cn0_1x1, act=ops.ACT_GELU, res=up, res_mode=2, out_nchw=True)
+
+    def __call__(self, v8: tc.C8, mean_vol: Optional[torch.Tensor]) -> torch.Tensor:
+        x = self.unet(tc.conv_tc(v8, self.proj))
+        if mean_vol is not None:
+            mp = self.net.conv3d[1](self._convnext_wide(self.net.conv3d[0], mean_vol))   # 64 -> 6 channels: fp32 kernels
+            x = ops.gate_add_(x, mp, self.net.attention_3d(mean_vol))
+        return x
+
+
+class CWFAEngine:
+    """``engine = CWFAEngine(model); vol = engine.reconstruct(views, mean_vols)``.
+
+    The model's parameters are packed at construction; call ``refresh()`` after changing them."""
+
+    def __init__(self, model: CWFAModel, kind: str = "bf16"):
+        if kind not in ("bf16", "fp16"):
+            raise ValueError(kind)
+        if not next(model.parameters()).is_cuda:
+            raise RuntimeError("CWFAEngine needs the model on a CUDA device (no CPU fallback)")
+        self.model, self.kind = model, kind
+        self.refresh()
+
+    def refresh(self):
+        m, kind = self.model, self.kind
+        self.levels = []
+        for n in range(m.n_levels):
+            inn = m.conv_inn[n]
+            nodes = []
+            for mod in inn.module_list:
+                if isinstance(mod, Fm.ConditionalAffineTransform):
+                    nodes.append(("cat", mod, _Subnet(mod.subnet, kind)))
+                elif isinstance(mod, Fm.PermuteRandom):
+                    nodes.append(("perm", mod, 1))
+                elif isinstance(mod, Fm.PermuteDim):
+                    nodes.append(("perm", mod, mod.axis))
+                elif isinstance(mod, (Fm.HaarTransform1D, Fm.Split)):
+                    continue
+                else:
+                    raise NotImplementedError(f"CWFAEngine supports the default CAT graph; found {type(mod).__name__} "
+                                              "(use CWFAModel.reconstruct for other block types)")
+            self.levels.append(dict(nodes=nodes, cond=_CondNet(m.cond_nets[n], kind)))
+        self.lrnn = _LRNN(m.cond_nets[-1], kind)
+        self._graphs: Dict = {}
+
+    # -------------------------------------------------------------------------------------
+    def _coeffs(self, n: int, v8: tc.C8, mean_vol: torch.Tensor):
+        """Coupling coefficients of level n: they depend on the conditions only (CAT blocks,
+        coupling_layers.py:475-500), so forward and inverse share them."""
+        lv = self.levels[n]
+        lf = lv["cond"](v8)
+        lf8 = tc.to_c8(lf, self.kind)
+        out = []
+        for kind, mod, extra in lv["nodes"]:
+            if kind == "cat":
+                a = extra(lf8)
+                if extra.normal:
+                    ch = mod.channels
+                    out.append((mod, a[:, :ch], a[:, ch:], 1.0))
+                else:
+                    out.append((mod, a, mean_vol, -1.0 / math.sqrt(2)))
+            else:
+                out.append((mod, extra))
+        return out
+
+    def _level_inverse(self, n, lo, v8, mean_vol):
+        hi = None          # z = 0 (INN_z_temperature = 0, CWFA.py:906-907): never materialised
+        jac = None
+        for item in reversed(self._coeffs(n, v8, mean_vol)):
+            if len(item) == 4:
+                mod, a_s, a_t, ts = item
+                hi, j = ops.affine(hi, a_s, a_t, inverse=True, clamp=mod.clamp, t_scale=ts)
+                jac = j if jac is None else jac + j
+            elif hi is not None:
+                mod, axis = item
+                hi = ops.permute(hi, mod.perm_inv, axis)
+        return ops.haar1d_merge(lo, hi), jac
+
+    @torch.no_grad()
+    def reconstruct(self, views: torch.Tensor, mean_vols: Sequence[Optional[torch.Tensor]], return_all: bool = False):
+        """Inverse reconstruction (CWFA.py:865-924) at z = 0."""
+        L1 = self.model.n_levels
+        v8 = tc.to_c8(views, self.kind)
+        vol = self.lrnn(v8, mean_vols[L1] if len(mean_vols) > L1 else None)
+        outs, jacs = {L1: vol}, {}
+        for n in range(L1 - 1, -1, -1):
+            vol, jac = self._level_inverse(n, vol, v8, mean_vols[n])
+            outs[n], jacs[n] = vol, jac
+        return (outs, jacs) if return_all else vol
+
+    @torch.no_grad()
+    def forward_nll(self, volume: torch.Tensor, views: torch.Tensor, mean_vols: Sequence[torch.Tensor]):
+        """Forward pyramid + per-level NLL (CWFA.py:966-978); same outputs as CWFAModel.forward_nll."""
+        v8 = tc.to_c8(views, self.kind)
+        res = []
+        x = volume
+        for n in range(self.model.n_levels):
+            lo, hi = ops.haar1d_split(x)
+            jac, sumsq = None, None
+            items = self._coeffs(n, v8, mean_vols[n])
+            last_cat = max(i for i, it in enumerate(items) if len(it) == 4)
+            for i, item in enumerate(items):
+                if len(item) == 4:
+                    mod, a_s, a_t, ts = item
+                    r = ops.affine(hi, a_s, a_t, inverse=False, clamp=mod.clamp, t_scale=ts, want_sumsq=(i == last_cat))
+                    hi, j = r[0], r[1]
+                    if i == last_cat:
+                        sumsq = r[2]          # permutations after the last block do not change ||z||^2
+                    jac = j if jac is None else jac + j
+                else:
+                    mod, axis = item
+                    hi = ops.permute(hi, mod.perm, axis)
+            per = (0.5 * sumsq - jac) / hi[0].numel()
+            ref = (0.5 * sumsq.sum() - jac) / lo.numel()
+            res.append(dict(z=hi, lo=lo, logdet=jac, sumsq=sumsq, nll_per_sample=per, nll_ref=ref))
+            x = lo
+        return res
+
+    # ---- CUDA-graph replay of the whole frame -------------------------------------------
+    def reconstruct_graphed(self, views: torch.Tensor, mean_vols: Sequence[Optional[torch.Tensor]]) -> torch.Tensor:
+        """Same as ``reconstruct`` but replays a captured CUDA graph (static shapes; inputs are copied into
+        static buffers, the returned tensor is the graph's static output buffer)."""
+        key = (tuple(views.shape), tuple(None if m is None else tuple(m.shape) for m in mean_vols), views.device.index)
+        g = self._graphs.get(key)
+        if g is None:
+            sv = views.clone()
+            sm = [None if m is None else m.clone() for m in mean_vols]
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                for _ in range(2):
+                    self.reconstruct(sv, sm)
+            torch.cuda.current_stream().wait_stream(s)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = self.reconstruct(sv, sm)
+            g = self._graphs[key] = (graph, sv, sm, out)
+        graph, sv, sm, out = g
+        sv.copy_(views, non_blocking=True)
+        for d, s_ in zip(sm, mean_vols):
+            if d is not None:
+                d.copy_(s_, non_blocking=True)
+        graph.replay()
+        return out

@@ -124,3 +124,51 @@ def conv_tc(x: C8, pc: PackedConv, *, act: int = 0, slope: Optional[torch.Tensor
               N, H, W, pc.Cin_p, pc.Cout, pc.Cout_p, pc.KH, pc.KW, pc.BN, mb, act, res_mode if res is not None else 0,
               1 if out_nchw else 0, x.is_bf16, _stream())
     return out
+
+
+def conv_transpose_tc(x: C8, pc: PackedConv, skip: Optional[C8] = None, mb: Optional[int] = None) -> C8:
+    """ConvTranspose2d(k=2,s=2) (+ skip add) on the tensor cores: 1x1 conv to 4*Cout_p channels whose epilogue
+    scatters each channel block to its (i,j) sub-pixel of the (2H,2W) output (unet.py:166,190)."""
+    if not pc.transposed:
+        raise ValueError("conv_transpose_tc needs weights packed with transposed=True")
+    if x.Cp != pc.Cin_p or x.kind != pc.kind:
+        raise ValueError("conv_transpose_tc: input layout mismatch")
+    N, H, W = x.N, x.H, x.W
+    if mb is None:
+        mb = 2 if (pc.BN * 2 <= 512 and W > 8) else 1
+    out = C8.empty(N, pc.Cout, 2 * H, 2 * W, x.data.device, x.kind, pc.Cout_p)
+    if skip is not None and (skip.Cp != pc.Cout_p or skip.H != 2 * H or skip.W != 2 * W):
+        raise ValueError("conv_transpose_tc: skip tensor shape mismatch")
+    _lib.call("cwfa_conv_tc", x.data.data_ptr(), pc.packed.data_ptr(), _p(pc.bias), None,
+              None if skip is None else skip.data.data_ptr(), out.data.data_ptr(),
+              N, H, W, pc.Cin_p, pc.Cout, pc.Cout_p, 1, 1, pc.BN, mb, 0, 1 if skip is not None else 0, 2, x.is_bf16, _stream())
+    return out
+
+
+def batchnorm_c8(x: C8, gamma, beta, running_mean, running_var, *, batch_stats: bool, eps: float = 1e-5,
+                 pool: bool = False):
+    """BatchNorm2d on a C8 tensor (batch or running statistics); optionally also returns the 2x2 max-pooled
+    tensor (fused).  Channels must not be padded (Cp == C), true for the U-Net widths 256/512/1024."""
+    if x.Cp != x.C:
+        raise ValueError("batchnorm_c8: padded channel layouts are not supported")
+    dev = x.data.device
+    Cp, N, H, W = x.Cp, x.N, x.H, x.W
+    lib = _lib.load()
+    if batch_stats:
+        stats = torch.empty(2 * Cp, device=dev, dtype=torch.float32)
+        ws = torch.empty(lib.cwfa_c8_stats_workspace_floats(Cp), device=dev, dtype=torch.float32)
+        _lib.call("cwfa_c8_channel_stats", x.data.data_ptr(), stats.data_ptr(), ws.data_ptr(), N, Cp, H * W, x.is_bf16, _stream())
+        count = float(N * H * W)
+    else:
+        rm, rv = _ck(running_mean.detach()), _ck(running_var.detach())
+        stats = torch.cat([rm, rv + rm * rm]).contiguous()
+        count = 1.0
+    scale = torch.empty(Cp, device=dev, dtype=torch.float32)
+    shift = torch.empty(Cp, device=dev, dtype=torch.float32)
+    _lib.call("cwfa_bn_finalize_f32", stats.data_ptr(), _ck(gamma.detach()).data_ptr(), _ck(beta.detach()).data_ptr(),
+              scale.data_ptr(), shift.data_ptr(), Cp, count, float(eps), _stream())
+    y = C8.empty(N, x.C, H, W, dev, x.kind, Cp)
+    yp = C8.empty(N, x.C, H // 2, W // 2, dev, x.kind, Cp) if pool else None
+    _lib.call("cwfa_c8_bn_apply", x.data.data_ptr(), scale.data_ptr(), shift.data_ptr(), y.data.data_ptr(),
+              None if yp is None else yp.data.data_ptr(), N, Cp, H, W, x.is_bf16, _stream())
+    return (y, yp) if pool else y

@@ -131,7 +131,9 @@ int cwfa_gate_add_f32(float* x, const float* m, const float* g, int64_t n, void*
  * x_c8: C8 activations with Cin_p channels (multiple of 16).  w_packed: from cwfa_tc_pack_weights.
  * bias: Cout_p floats (zero padded) or NULL.  v = conv + bias; res_mode 1: v += res; v = act(v);
  * res_mode 2: v += res.  out_mode 0: C8 (Cout_p channels; res is C8), out_mode 1: NCHW fp32 with Cout
- * channels (res is NCHW fp32).  BN = output channels per CTA (multiple of 16, <= 256, divides Cout_p),
+ * channels (res is NCHW fp32), out_mode 2: ConvTranspose2d(k=2,s=2) (unet.py:166) run as a 1x1 conv to
+ * 4*Cout_p channels (weights packed with transposed=1) and scattered to a C8 (2H,2W) tensor, res = the
+ * skip tensor added at the output location (unet.py:190).  BN = output channels per CTA (multiple of 16, <= 256, divides Cout_p),
  * MB = number of 16x8-pixel M=128 blocks per CTA (1 or 2), MB*BN <= 512 TMEM columns. */
 int cwfa_tc_kc(int cin_p);
 int64_t cwfa_tc_packed_weight_elems(int Cin_p, int Cout_tot_p, int KH, int KW, int BN);
@@ -141,6 +143,14 @@ int cwfa_conv_tc(const void* x_c8, const void* w_packed, const float* bias, cons
                  const void* res, void* out, int N, int H, int W, int Cin_p, int Cout, int Cout_p,
                  int KH, int KW, int BN, int MB, int act, int res_mode, int out_mode, int is_bf16,
                  void* stream);
+/* ---- C8 helpers of the LRNN U-Net: per-channel (sum, sumsq) over (N,H,W) -> stats[2*Cp]
+ * (workspace >= cwfa_c8_stats_workspace_floats(Cp) floats; feed to cwfa_bn_finalize_f32), and BatchNorm
+ * apply y = x*scale+shift, optionally also writing the 2x2 max-pooled tensor (unet.py:79). */
+int cwfa_c8_stats_workspace_floats(int Cp);
+int cwfa_c8_channel_stats(const void* x, float* stats, float* workspace, int N, int Cp, int64_t P,
+                          int is_bf16, void* stream);
+int cwfa_c8_bn_apply(const void* x, const float* scale, const float* shift, void* y, void* ypool,
+                     int N, int Cp, int H, int W, int is_bf16, void* stream);
 /* Profiling aid: when set (device buffer of 8 uint64 per CTA), conv_tc records globaltimer stamps. */
 int cwfa_tc_set_debug_buffer(void* buf);
 /* Layout converters NCHW fp32 <-> C8 half (channels padded with zeros up to Cp). */

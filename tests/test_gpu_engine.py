@@ -1,0 +1,98 @@
+"""GPU: the tensor-core engine (bf16 / fp16 operands, fp32 accumulation) against the golden outputs of the
+unmodified reference on BASELINE.json configs[0], with the stated half-precision tolerances, reported per
+level (max-abs and rel-L2)."""
+import pytest
+import torch
+
+from conftest import max_abs, rel_l2
+from helpers import build_tiny_model, tiny_inputs
+from oracle.weights import seeded_randn
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TOL = {"bf16": 2e-2, "fp16": 3e-3}          # rel-L2 on volumes; log-det: same factor relative to |J|
+
+
+@pytest.fixture(scope="module")
+def model(golden_tiny):
+    return build_tiny_model(golden_tiny, DEV)
+
+
+@pytest.mark.parametrize("kind", ["bf16", "fp16"])
+@pytest.mark.parametrize("bn_mode", ["batch", "running"])
+@pytest.mark.parametrize("use_mv", [False, True])
+def test_engine_inverse_vs_reference(golden_tiny, model, kind, bn_mode, use_mv):
+    from cwfa_b200.engine import CWFAEngine
+    views, mean_vols = tiny_inputs(golden_tiny)
+    L = model.n_levels
+    mv = [t.to(DEV) for t in mean_vols[:L]] + ([mean_vols[L].to(DEV)] if use_mv else [])
+    model.cond_nets[-1].train(bn_mode == "batch")
+    eng = CWFAEngine(model, kind)
+    outs, jacs = eng.reconstruct(views.to(DEV), mv, return_all=True)
+    model.cond_nets[-1].train()
+    tag = f"recon/{bn_mode}/{'mv' if use_mv else 'nomv'}"
+    rep = {"lrnn": (rel_l2(outs[L], golden_tiny[f"{tag}/lrnn"]), max_abs(outs[L], golden_tiny[f"{tag}/lrnn"]))}
+    for n in range(L):
+        rep[n] = (rel_l2(outs[n], golden_tiny[f"{tag}/vol{n}"]), max_abs(outs[n], golden_tiny[f"{tag}/vol{n}"]))
+    print(kind, tag, {k: (f"{a:.2e}", f"{b:.2e}") for k, (a, b) in rep.items()})
+    assert all(a < TOL[kind] for a, _ in rep.values()), rep
+    for n in range(L):
+        ref = float(golden_tiny[f"{tag}/jac{n}"][0])
+        assert abs(float(jacs[n][0]) - ref) < TOL[kind] * max(1.0, abs(ref)), (n, float(jacs[n][0]), ref)
+
+
+@pytest.mark.parametrize("kind", ["bf16", "fp16"])
+def test_engine_forward_nll_vs_reference(golden_tiny, model, kind):
+    from cwfa_b200.engine import CWFAEngine
+    cfg = golden_tiny["config"]
+    B, D, S = 2, cfg["D"], cfg["S"]
+    x = seeded_randn((B, D, S, S), 2).to(DEV)
+    vB = seeded_randn((B, 29, S, S), 3).to(DEV)
+    _, mean_vols = tiny_inputs(golden_tiny)
+    eng = CWFAEngine(model, kind)
+    res = eng.forward_nll(x, vB, [mv.repeat(B, 1, 1, 1).to(DEV) for mv in mean_vols[:model.n_levels]])
+    for n, r in enumerate(res):
+        e = (rel_l2(r["z"], golden_tiny[f"fwd/z{n}"]), rel_l2(r["logdet"], golden_tiny[f"fwd/jac{n}"]),
+             rel_l2(r["nll_ref"], golden_tiny[f"fwd/nll_ref{n}"]))
+        print(kind, "fwd level", n, [f"{v:.2e}" for v in e])
+        assert e[0] < TOL[kind] and e[1] < TOL[kind] and e[2] < TOL[kind]
+        assert rel_l2(r["lo"], golden_tiny[f"fwd/lo{n}"]) < 1e-6
+
+
+def test_engine_matches_fp32_module_path_and_graph_replay(golden_tiny, model):
+    from cwfa_b200.engine import CWFAEngine
+    views, mean_vols = tiny_inputs(golden_tiny)
+    mv = [t.to(DEV) for t in mean_vols]
+    ref = model.reconstruct(views.to(DEV), mv)
+    eng = CWFAEngine(model, "bf16")
+    a = eng.reconstruct(views.to(DEV), mv)
+    assert rel_l2(a, ref) < TOL["bf16"]
+    g1 = eng.reconstruct_graphed(views.to(DEV), mv).clone()
+    g2 = eng.reconstruct_graphed(views.to(DEV), mv).clone()
+    assert torch.equal(g1, g2), "graph replay must be bit-reproducible"
+    assert torch.equal(g1, a), "graph replay must equal the eager engine bit for bit"
+
+
+def test_unet_pieces_c8(golden_tiny):
+    """convT scatter epilogue, C8 BatchNorm (+pool) against torch CPU ops."""
+    import torch.nn.functional as F
+    from cwfa_b200 import tc
+    x = seeded_randn((2, 32, 8, 16), 1).bfloat16().float()
+    w = (seeded_randn((32, 48, 2, 2), 2) * 0.2).bfloat16().float()
+    b = seeded_randn((48,), 3)
+    skip = seeded_randn((2, 48, 16, 32), 4).bfloat16().float()
+    ref = F.conv_transpose2d(x, w, b, stride=2) + skip
+    pc = tc.PackedConv(w.to(DEV), b.to(DEV), "bf16", transposed=True, bn=48)
+    y = tc.from_c8(tc.conv_transpose_tc(tc.to_c8(x.to(DEV)), pc, tc.to_c8(skip.to(DEV))))
+    assert rel_l2(y, ref) < 4e-3
+    xb = seeded_randn((2, 256, 8, 12), 5).bfloat16().float()
+    g, be = seeded_randn((256,), 6) * 0.2 + 1.0, seeded_randn((256,), 7)
+    refb = F.batch_norm(xb, None, None, g, be, training=True)
+    yb, yp = tc.batchnorm_c8(tc.to_c8(xb.to(DEV)), g.to(DEV), be.to(DEV), None, None, batch_stats=True, pool=True)
+    assert rel_l2(tc.from_c8(yb), refb) < 4e-3
+    assert rel_l2(tc.from_c8(yp), F.max_pool2d(refb, 2)) < 4e-3
+    assert torch.equal(tc.from_c8(yp).cpu(), F.max_pool2d(tc.from_c8(yb).cpu(), 2))
+    rm, rv = seeded_randn((256,), 8) * 0.1, seeded_randn((256,), 9).abs() + 0.5
+    refr = F.batch_norm(xb, rm, rv, g, be, training=False)
+    yr = tc.batchnorm_c8(tc.to_c8(xb.to(DEV)), g.to(DEV), be.to(DEV), rm.to(DEV), rv.to(DEV), batch_stats=False)
+    assert rel_l2(tc.from_c8(yr), refr) < 4e-3
