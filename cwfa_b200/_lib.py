@@ -96,9 +96,21 @@ class CwfaError(RuntimeError):
     pass
 
 
+# kernel launches issued per C-ABI call (for bench.py's "gpu_launches" claim)
+_LAUNCHES = {"cwfa_affine": 2, "cwfa_channel_stats_f32": 2, "cwfa_layernorm_chw_f32": 2, "cwfa_c8_channel_stats": 2,
+             "cwfa_tc_set_debug_buffer": 0, "cwfa_device_check": 0}
+launch_count = 0
+launch_hist = {}
+
+
 def call(name: str, *args) -> None:
+    global launch_count
     lib = load()
     rc = getattr(lib, name)(*args)
+    k = _LAUNCHES.get(name, 1)
+    launch_count += k
+    if k:
+        launch_hist[name] = launch_hist.get(name, 0) + k
     if rc != 0:
         msg = lib.cwfa_last_error().decode(errors="replace")
         raise CwfaError(f"{name} failed (code {rc}): {msg}")

@@ -264,3 +264,21 @@ class CWFAEngine:
                 d.copy_(s_, non_blocking=True)
         graph.replay()
         return out
+
+    # ---- reference-facing call with HOST buffers ------------------------------------------
+    def reconstruct_host(self, views_host: torch.Tensor, mean_vols: Sequence[Optional[torch.Tensor]],
+                         out_host: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """views on the HOST (pinned for full speed) -> H2D copy -> graph replay -> D2H copy of the
+        reconstructed volume into ``out_host``.  The mean-volume conditions are dataset constants and
+        stay resident on the device.  Returns ``out_host`` (synchronised)."""
+        dev = mean_vols[0].device
+        vd = getattr(self, "_views_dev", None)
+        if vd is None or vd.shape != views_host.shape:
+            vd = self._views_dev = torch.empty(views_host.shape, device=dev, dtype=torch.float32)
+        vd.copy_(views_host, non_blocking=True)
+        out = self.reconstruct_graphed(vd, mean_vols)
+        if out_host is None:
+            out_host = torch.empty(out.shape, dtype=torch.float32, pin_memory=True)
+        out_host.copy_(out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return out_host
