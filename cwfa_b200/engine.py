@@ -47,7 +47,13 @@ class _Subnet:
 
 
 class _CondNet:
-    """cond_network / ResidualBlock (networks.py:165-242): 2-D convs on tensor cores, depth stencil fp32."""
+    """cond_network / ResidualBlock (networks.py:165-242) entirely on the tensor cores.
+
+    The depth stencil Conv3d(1->Cm) -> PReLU -> Conv3d(Cm->1) over the (H, W, depth) volume
+    (networks.py:221-225,239) is executed as two ordinary 3x3 2-D convolutions whose channel axis
+    carries (depth, hidden-channel) and whose weights are the depth-banded expansion of the 3x3x3
+    kernels: W1[(d,c), d'] = w1[c, :, :, d'-d+1], W2[d, (d',c)] = w2[c, :, :, d'-d+1] for |d'-d| <= 1.
+    Zero padding in depth falls out of the band; zero padding in H, W is the conv's own padding."""
 
     def __init__(self, net, kind):
         rb = net.subnetworks[0]
@@ -55,14 +61,29 @@ class _CondNet:
         self.c1 = tc.PackedConv(rb.conv1[0].weight, rb.conv1[0].bias, kind)
         self.ds = tc.PackedConv(rb.downsample[0].weight, rb.downsample[0].bias, kind)
         self.c2 = tc.PackedConv(rb.conv2[0].weight, rb.conv2[0].bias, kind)
+        w1, b1 = rb.conv3d[0].weight.detach().float(), rb.conv3d[0].bias.detach().float()      # (Cm,1,3,3,3), (Cm)
+        w2, b2 = rb.conv3d[3].weight.detach().float(), rb.conv3d[3].bias.detach().float()      # (1,Cm,3,3,3), (1)
+        Cm, D = w1.shape[0], rb.out_channels
+        dev = w1.device
+        W1 = torch.zeros(D, Cm, D, 3, 3, device=dev)          # [d, c, d', ky, kx]
+        W2 = torch.zeros(D, D, Cm, 3, 3, device=dev)          # [d, d', c, ky, kx]
+        for kd in range(3):
+            for d in range(D):
+                dp = d + kd - 1
+                if 0 <= dp < D:
+                    W1[d, :, dp] = w1[:, 0, :, :, kd]
+                    W2[d, dp] = w2[0, :, :, :, kd]
+        self.s1 = tc.PackedConv(W1.reshape(D * Cm, D, 3, 3), b1.repeat(D), kind)
+        self.s2 = tc.PackedConv(W2.reshape(D, D * Cm, 3, 3), b2.repeat(D), kind)
 
-    def __call__(self, v8: tc.C8) -> torch.Tensor:
+    def __call__(self, v8: tc.C8) -> tc.C8:
+        """views (C8) -> LF condition (C8)."""
         rb = self.rb
         out = tc.conv_tc(v8, self.c1, act=ops.ACT_PRELU, slope=rb.conv1[1].weight)
-        res = tc.conv_tc(v8, self.ds, out_nchw=True)
-        out = tc.conv_tc(out, self.c2, act=ops.ACT_PRELU, slope=rb.relu.weight, res=res, res_mode=1, out_nchw=True)
-        c3 = rb.conv3d
-        return ops.depth_stencil3d(out, c3[0].weight, c3[0].bias, c3[1].weight, c3[3].weight, c3[3].bias)
+        res = tc.conv_tc(v8, self.ds)
+        out = tc.conv_tc(out, self.c2, act=ops.ACT_PRELU, slope=rb.relu.weight, res=res, res_mode=1)
+        hid = tc.conv_tc(out, self.s1, act=ops.ACT_PRELU, slope=rb.conv3d[1].weight)
+        return tc.conv_tc(hid, self.s2)
 
 
 class _UNet:
@@ -170,8 +191,7 @@ class CWFAEngine:
         """Coupling coefficients of level n: they depend on the conditions only (CAT blocks,
         coupling_layers.py:475-500), so forward and inverse share them."""
         lv = self.levels[n]
-        lf = lv["cond"](v8)
-        lf8 = tc.to_c8(lf, self.kind)
+        lf8 = lv["cond"](v8)
         out = []
         for kind, mod, extra in lv["nodes"]:
             if kind == "cat":
