@@ -39,6 +39,7 @@ _SIGS = {
     "cwfa_tc_pack_weights": [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp],
     "cwfa_conv_tc": [vp, vp, vp, vp, vp, vp] + [i32] * 14 + [vp],
     "cwfa_tc_set_debug_buffer": [vp],
+    "cwfa_resblock_tc": [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp],
     "cwfa_c8_stats_workspace_floats": [i32],
     "cwfa_c8_channel_stats": [vp, vp, vp, i32, i32, i64, i32, vp],
     "cwfa_c8_bn_apply": [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],

@@ -1,0 +1,296 @@
+// Fused, persistent residual block of the coupling sub-network trunk (networks.py:624-634, :659-663):
+//     y = ELU( W1x1 * ELU( W3x3 (*) x + b3 ) + b1 + x ),   64 -> 64 -> 64 channels, C8 in / C8 out.
+// One persistent CTA per SM walks 16x16-pixel tiles.  Per tile:
+//   TMA halo tile (18x18x64ch)  ->  GEMM1: 9 taps x (M=128,N=64,K=64) x 2 M-blocks into TMEM acc1
+//   EPI1 warps: acc1 -> +b3 -> ELU -> half -> shared memory in the K-major UMMA layout (A operand of GEMM2)
+//   GEMM2: (M=128,N=64,K=64) x 2 M-blocks into TMEM acc2 with the resident 1x1 weights
+//   EPI2 warps: acc2 -> +b1 + x (residual, L2-hot re-read) -> ELU -> half -> global (16-byte stores)
+// The 3x3->ELU->1x1 intermediate never leaves the SM; both weight sets stay resident in shared memory;
+// acc1/acc2 are double buffered in TMEM (512 columns) so GEMM1 of tile i+1 overlaps the epilogues of tile i.
+// Warp roles (320 threads): warp0 TMA producer, warp1 MMA issuer, warps2-5 EPI1, warps6-9 EPI2.
+#include "tc_common.cuh"
+using namespace cwfa;
+using namespace cwfa::tcx;
+
+namespace {
+
+constexpr int kC = 64, kChunks = 8;
+constexpr int kTH = 16, kTW = 16, kBH = 18, kBW = 18;
+constexpr uint32_t kA1Bytes = kChunks * kBH * kBW * 16;       // 41472
+constexpr uint32_t kTapBytes = kChunks * kC * 16;             // 8192
+constexpr uint32_t kW3Bytes = 9 * kTapBytes;                  // 73728
+constexpr uint32_t kW1Bytes = kTapBytes;                      // 8192
+constexpr uint32_t kA2MbBytes = kChunks * 128 * 16;           // 16384 per M-block
+constexpr uint32_t kHeader = 2048;
+constexpr uint32_t kOffW3 = kHeader, kOffW1 = kOffW3 + kW3Bytes, kOffA1 = kOffW1 + kW1Bytes,
+                   kOffA2 = kOffA1 + 2 * kA1Bytes, kSmemTotal = kOffA2 + 2 * kA2MbBytes;
+constexpr int kThreads = 320;
+
+struct RbParams {
+    int N, H, W, tiles_x, tiles_y, num_tiles;
+    int in_total_chunks, in_chunk_off, out_total_chunks, out_chunk_off;
+    const uint8_t* x;        // input C8 tensor base (also the residual)
+    uint8_t* y;              // output C8 tensor base
+    const uint8_t* w3;       // packed [9][8][64][8]
+    const uint8_t* w1;       // packed [8][64][8]
+    const float* b3;         // 64
+    const float* b1;         // 64
+};
+
+template <bool BF16>
+__global__ void __launch_bounds__(kThreads, 1) resblock_tc_kernel(const __grid_constant__ CUtensorMap tmap, const RbParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t s0 = smem_u32(smem);
+    // barriers (8 bytes each)
+    const uint32_t w_full = s0;
+    auto a1_full = [&](int b) { return s0 + 8u * (1 + b); };
+    auto a1_empty = [&](int b) { return s0 + 8u * (3 + b); };
+    auto acc1_full = [&](int b) { return s0 + 8u * (5 + b); };
+    auto acc1_empty = [&](int b) { return s0 + 8u * (7 + b); };
+    auto acc2_full = [&](int b) { return s0 + 8u * (9 + b); };
+    auto acc2_empty = [&](int b) { return s0 + 8u * (11 + b); };
+    const uint32_t a2_full = s0 + 8u * 13, a2_empty = s0 + 8u * 14;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 128);
+    float* s_b3 = reinterpret_cast<float*>(smem + 1024);
+    float* s_b1 = s_b3 + kC;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        mbar_init(w_full, 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(a1_full(b), 1);
+            mbar_init(a1_empty(b), 1);
+            mbar_init(acc1_full(b), 1);
+            mbar_init(acc1_empty(b), 128);
+            mbar_init(acc2_full(b), 1);
+            mbar_init(acc2_empty(b), 128);
+        }
+        mbar_init(a2_full, 128);
+        mbar_init(a2_empty, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (threadIdx.x >= 64 && threadIdx.x < 64 + 2 * kC) {
+        const int i = threadIdx.x - 64;
+        s_b3[i] = i < kC ? __ldg(p.b3 + i) : __ldg(p.b1 + i - kC);      // s_b1 follows s_b3
+    }
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const int my_tiles = (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int tiles_per_img = p.tiles_x * p.tiles_y;
+    const size_t plane = (size_t)p.H * p.W;
+
+    if (warp == 0) {
+        // ============================ TMA producer ============================
+        if (lane == 0) {
+            mbar_expect_tx(w_full, kW3Bytes + kW1Bytes);
+            bulk_load(s0 + kOffW3, p.w3, kW3Bytes, w_full);
+            bulk_load(s0 + kOffW1, p.w1, kW1Bytes, w_full);
+            for (int i = 0; i < my_tiles; ++i) {
+                const int t = blockIdx.x + i * gridDim.x;
+                const int n = t / tiles_per_img, r = t % tiles_per_img;
+                const int h0 = (r / p.tiles_x) * kTH, w0 = (r % p.tiles_x) * kTW;
+                const int b = i & 1;
+                mbar_wait(a1_empty(b), ((i >> 1) & 1) ^ 1);
+                mbar_expect_tx(a1_full(b), kA1Bytes);
+                tma_load_4d(s0 + kOffA1 + b * kA1Bytes, &tmap, a1_full(b), (w0 - 1) * 8, h0 - 1, p.in_chunk_off, n);
+            }
+        }
+    } else if (warp == 1) {
+        // ============================ MMA issuer ============================
+        const uint32_t idesc = idesc_f16(kC, BF16 ? 1 : 0);
+        constexpr uint32_t a1_lbo = kBH * kBW * 16, a1_sbo = kBW * 16;
+        constexpr uint32_t w_lbo = kC * 16, w_sbo = 128;
+        constexpr uint32_t a2_lbo = 128 * 16, a2_sbo = 128;
+        const uint32_t a1_hi = desc_hi(a1_sbo), w_hi = desc_hi(w_sbo), a2_hi = desc_hi(a2_sbo);
+        const uint32_t w3_lo0 = desc_lo(s0 + kOffW3, w_lbo), w1_lo0 = desc_lo(s0 + kOffW1, w_lbo);
+        const uint32_t leader = elect_one();
+        mbar_wait(w_full, 0);
+
+        auto gemm2 = [&](int j) {
+            const int bj = j & 1;
+            mbar_wait(a2_full, j & 1);
+            mbar_wait(acc2_empty(bj), ((j >> 1) & 1) ^ 1);
+            tc_fence_after();
+            if (leader) {
+#pragma unroll
+                for (int mb = 0; mb < 2; ++mb) {
+                    const uint32_t d = tmem + 256 + (bj * 2 + mb) * kC;
+                    const uint32_t a_lo0 = desc_lo(s0 + kOffA2 + mb * kA2MbBytes, a2_lbo);
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+                        tc_mma_f16_split(d, a_lo0 + kk * ((2 * a2_lbo) >> 4), a2_hi, w1_lo0 + kk * ((2 * w_lbo) >> 4), w_hi,
+                                         idesc, kk ? 1u : 0u);
+                }
+                tc_commit(a2_empty);
+                tc_commit(acc2_full(bj));
+            }
+            __syncwarp();
+        };
+
+        for (int i = 0; i < my_tiles; ++i) {
+            const int b = i & 1, ph = (i >> 1) & 1;
+            mbar_wait(a1_full(b), ph);
+            mbar_wait(acc1_empty(b), ph ^ 1);
+            tc_fence_after();
+            if (leader) {
+                const uint32_t a_base = s0 + kOffA1 + b * kA1Bytes;
+#pragma unroll 1
+                for (int tap = 0; tap < 9; ++tap) {
+                    const int kh = tap / 3, kw = tap - kh * 3;
+                    const uint32_t w_lo = w3_lo0 + tap * (kTapBytes >> 4);
+#pragma unroll
+                    for (int mb = 0; mb < 2; ++mb) {
+                        const uint32_t d = tmem + (b * 2 + mb) * kC;
+                        const uint32_t a_lo0 = desc_lo(a_base + (uint32_t)((kh * kBW + mb * 8 + kw) * 16), a1_lbo);
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk)
+                            tc_mma_f16_split(d, a_lo0 + kk * ((2 * a1_lbo) >> 4), a1_hi, w_lo + kk * ((2 * w_lbo) >> 4), w_hi,
+                                             idesc, (tap | kk) ? 1u : 0u);
+                    }
+                }
+                tc_commit(a1_empty(b));
+                tc_commit(acc1_full(b));
+            }
+            __syncwarp();
+            if (i >= 1) gemm2(i - 1);
+        }
+        if (my_tiles > 0) gemm2(my_tiles - 1);
+    } else if (warp < 6) {
+        // ============================ EPI1: acc1 -> ELU -> shared (A of GEMM2) ============================
+        const int q = warp & 3;
+        const int m = q * 32 + lane;
+        for (int i = 0; i < my_tiles; ++i) {
+            const int b = i & 1, ph = (i >> 1) & 1;
+            mbar_wait(acc1_full(b), ph);
+            mbar_wait(a2_empty, (i & 1) ^ 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int mb = 0; mb < 2; ++mb) {
+                uint8_t* a2 = smem + kOffA2 + mb * kA2MbBytes + m * 16;
+#pragma unroll 1
+                for (int c0 = 0; c0 < kC; c0 += 16) {
+                    uint32_t r[16];
+                    __syncwarp();
+                    tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((b * 2 + mb) * kC + c0), r);
+                    float v[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = elu_fast(__uint_as_float(r[j]) + s_b3[c0 + j]);
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        uint4 ov;
+                        ov.x = pack2<BF16>(v[hh * 8 + 0], v[hh * 8 + 1]);
+                        ov.y = pack2<BF16>(v[hh * 8 + 2], v[hh * 8 + 3]);
+                        ov.z = pack2<BF16>(v[hh * 8 + 4], v[hh * 8 + 5]);
+                        ov.w = pack2<BF16>(v[hh * 8 + 6], v[hh * 8 + 7]);
+                        *reinterpret_cast<uint4*>(a2 + ((c0 >> 3) + hh) * (128 * 16)) = ov;
+                    }
+                }
+            }
+            tc_fence_before();
+            fence_proxy_async();                // make the generic-proxy smem writes visible to the tensor core
+            mbar_arrive(acc1_empty(b));
+            mbar_arrive(a2_full);
+        }
+    } else {
+        // ============================ EPI2: acc2 + b1 + x -> ELU -> global ============================
+        const int q = warp & 3;
+        const int m = q * 32 + lane;
+        for (int i = 0; i < my_tiles; ++i) {
+            const int b = i & 1, ph = (i >> 1) & 1;
+            const int t = blockIdx.x + i * gridDim.x;
+            const int n = t / tiles_per_img, rr = t % tiles_per_img;
+            const int h0 = (rr / p.tiles_x) * kTH, w0 = (rr % p.tiles_x) * kTW;
+            const int orow = h0 + (m >> 3);
+            mbar_wait(acc2_full(b), ph);
+            tc_fence_after();
+#pragma unroll 1
+            for (int mb = 0; mb < 2; ++mb) {
+                const int ocol = w0 + mb * 8 + (m & 7);
+                const bool ok = orow < p.H && ocol < p.W;
+                const size_t pix = (size_t)orow * p.W + ocol;
+                const uint8_t* xin = p.x + (((size_t)n * p.in_total_chunks + p.in_chunk_off) * plane + pix) * 16;
+                uint8_t* yout = p.y + (((size_t)n * p.out_total_chunks + p.out_chunk_off) * plane + pix) * 16;
+#pragma unroll 1
+                for (int c0 = 0; c0 < kC; c0 += 16) {
+                    uint4 rx[2];
+                    if (ok) {
+                        rx[0] = __ldg(reinterpret_cast<const uint4*>(xin + (size_t)(c0 >> 3) * plane * 16));
+                        rx[1] = __ldg(reinterpret_cast<const uint4*>(xin + (size_t)((c0 >> 3) + 1) * plane * 16));
+                    } else {
+                        rx[0] = rx[1] = make_uint4(0, 0, 0, 0);
+                    }
+                    uint32_t r[16];
+                    __syncwarp();
+                    tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(256 + (b * 2 + mb) * kC + c0), r);
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        const uint32_t rw[4] = {rx[hh].x, rx[hh].y, rx[hh].z, rx[hh].w};
+                        uint32_t ow[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const float2 xr = unpack2<BF16>(rw[k]);
+                            const int j = hh * 8 + 2 * k;
+                            const float a = elu_fast(__uint_as_float(r[j]) + s_b1[c0 + j] + xr.x);
+                            const float c = elu_fast(__uint_as_float(r[j + 1]) + s_b1[c0 + j + 1] + xr.y);
+                            ow[k] = pack2<BF16>(a, c);
+                        }
+                        if (ok)
+                            *reinterpret_cast<uint4*>(yout + (size_t)((c0 >> 3) + hh) * plane * 16) =
+                                make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(acc2_empty(b));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 512);
+    }
+}
+
+}  // namespace
+
+extern "C" int cwfa_resblock_tc(const void* x_c8, void* y_c8, const void* w3_packed, const void* w1_packed, const float* b3,
+                                const float* b1, int N, int H, int W, int in_total_chunks, int in_chunk_off,
+                                int out_total_chunks, int out_chunk_off, int is_bf16, void* stream) {
+    if (N <= 0 || H <= 0 || W <= 0 || in_chunk_off < 0 || out_chunk_off < 0 || in_chunk_off + kChunks > in_total_chunks ||
+        out_chunk_off + kChunks > out_total_chunks || !b3 || !b1) {
+        set_error("resblock_tc: bad arguments");
+        return CWFA_EINVAL;
+    }
+    if ((reinterpret_cast<uintptr_t>(x_c8) & 15) || (reinterpret_cast<uintptr_t>(y_c8) & 15) ||
+        (reinterpret_cast<uintptr_t>(w3_packed) & 15) || (reinterpret_cast<uintptr_t>(w1_packed) & 15)) {
+        set_error("resblock_tc: pointers must be 16-byte aligned");
+        return CWFA_EINVAL;
+    }
+    RbParams p{};
+    p.N = N; p.H = H; p.W = W;
+    p.tiles_x = ceil_div(W, kTW); p.tiles_y = ceil_div(H, kTH);
+    const int64_t nt = (int64_t)p.tiles_x * p.tiles_y * N;
+    if (nt > 0x7fffffff) { set_error("resblock_tc: too many tiles"); return CWFA_EINVAL; }
+    p.num_tiles = (int)nt;
+    p.in_total_chunks = in_total_chunks; p.in_chunk_off = in_chunk_off;
+    p.out_total_chunks = out_total_chunks; p.out_chunk_off = out_chunk_off;
+    p.x = (const uint8_t*)x_c8; p.y = (uint8_t*)y_c8; p.w3 = (const uint8_t*)w3_packed; p.w1 = (const uint8_t*)w1_packed;
+    p.b3 = b3; p.b1 = b1;
+    CUtensorMap tmap;
+    int rc = make_c8_tensor_map(&tmap, x_c8, N, in_total_chunks, H, W, kBW, kBH, kChunks, is_bf16);
+    if (rc) return rc;
+    auto kern = is_bf16 ? resblock_tc_kernel<true> : resblock_tc_kernel<false>;
+    static bool attr_done[2] = {false, false};
+    if (!attr_done[is_bf16 ? 1 : 0]) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        attr_done[is_bf16 ? 1 : 0] = true;
+    }
+    const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
+    kern<<<grid, kThreads, kSmemTotal + 1024, (cudaStream_t)stream>>>(tmap, p);
+    return check_launch("resblock_tc");
+}

@@ -40,9 +40,13 @@ class _Subnet:
     def __call__(self, lf8: tc.C8) -> torch.Tensor:
         """LF condition (C8) -> fp32 NCHW coefficient tensor (2ch channels, or ch for the _first variant)."""
         b = tc.conv_tc(lf8, self.inp)
+        fused = b.Cp == 64
         for p3, p1 in self.res:
-            t = tc.conv_tc(b, p3, act=ops.ACT_ELU)
-            b = tc.conv_tc(t, p1, act=ops.ACT_ELU, res=b, res_mode=1)
+            if fused:
+                b = tc.resblock_tc(b, p3, p1)
+            else:
+                t = tc.conv_tc(b, p3, act=ops.ACT_ELU)
+                b = tc.conv_tc(t, p1, act=ops.ACT_ELU, res=b, res_mode=1)
         return tc.conv_tc(b, self.out, out_nchw=True)
 
 

@@ -143,6 +143,13 @@ int cwfa_conv_tc(const void* x_c8, const void* w_packed, const float* bias, cons
                  const void* res, void* out, int N, int H, int W, int Cin_p, int Cout, int Cout_p,
                  int KH, int KW, int BN, int MB, int act, int res_mode, int out_mode, int is_bf16,
                  void* stream);
+/* ---- fused persistent residual block of the coupling sub-network trunk (networks.py:624-634,659-663):
+ * y = ELU( W1x1 * ELU( W3x3 (*) x + b3 ) + b1 + x ), 64 -> 64 -> 64 channels.  x / y are 64-channel slices
+ * (8 chunks starting at *_chunk_off) of C8 tensors with *_total_chunks chunks; y must not alias x.
+ * w3_packed / w1_packed: cwfa_tc_pack_weights output with Cin_p = Cout_p = BN = 64. */
+int cwfa_resblock_tc(const void* x_c8, void* y_c8, const void* w3_packed, const void* w1_packed,
+                     const float* b3, const float* b1, int N, int H, int W, int in_total_chunks,
+                     int in_chunk_off, int out_total_chunks, int out_chunk_off, int is_bf16, void* stream);
 /* ---- C8 helpers of the LRNN U-Net: per-channel (sum, sumsq) over (N,H,W) -> stats[2*Cp]
  * (workspace >= cwfa_c8_stats_workspace_floats(Cp) floats; feed to cwfa_bn_finalize_f32), and BatchNorm
  * apply y = x*scale+shift, optionally also writing the 2x2 max-pooled tensor (unet.py:79). */

@@ -54,3 +54,26 @@ def test_conv_tc_vs_cpu(cin, cout, k, H, W, mb, bn, kind):
     ref2 = F.elu(ref + r)
     tol = 6e-3 if kind == "bf16" else 8e-4
     assert rel_l2(y2, ref2) < tol
+
+
+@pytest.mark.parametrize("kind", ["bf16", "fp16"])
+@pytest.mark.parametrize("N,H,W", [(1, 16, 16), (2, 48, 32), (1, 40, 24), (1, 128, 128), (3, 64, 80)])
+def test_fused_resblock_vs_unfused_and_cpu(kind, N, H, W):
+    """Fused persistent trunk block == the two-kernel sequence (same roundings) and ~= fp64 CPU."""
+    from cwfa_b200 import ops, tc
+    x = _round(seeded_randn((N, 64, H, W), 11), kind)
+    w3 = _round(seeded_randn((64, 64, 3, 3), 12, (1.0 / 576) ** 0.5), kind)
+    w1 = _round(seeded_randn((64, 64, 1, 1), 13, (1.0 / 64) ** 0.5), kind)
+    b3, b1 = seeded_randn((64,), 14, 0.1), seeded_randn((64,), 15, 0.1)
+    xc = tc.to_c8(x.to(DEV), kind)
+    p3, p1 = tc.PackedConv(w3.to(DEV), b3.to(DEV), kind, bn=64), tc.PackedConv(w1.to(DEV), b1.to(DEV), kind, bn=64)
+    y = tc.from_c8(tc.resblock_tc(xc, p3, p1))
+    t = tc.conv_tc(xc, p3, act=ops.ACT_ELU)
+    y_ref2 = tc.from_c8(tc.conv_tc(t, p1, act=ops.ACT_ELU, res=xc, res_mode=1))
+    torch.cuda.synchronize()
+    tmid = _round(F.elu(F.conv2d(x.double(), w3.double(), b3.double(), padding=1)).float(), kind)
+    ref = F.elu(F.conv2d(tmid.double(), w1.double(), b1.double()) + x.double()).float()
+    tol = 6e-3 if kind == "bf16" else 8e-4
+    print(f"resblock {kind} {N}x{H}x{W}: vs unfused {rel_l2(y, y_ref2):.2e}  vs cpu {rel_l2(y, ref):.2e}")
+    assert rel_l2(y, y_ref2) < tol
+    assert rel_l2(y, ref) < tol
