@@ -39,6 +39,7 @@ _SIGS = {
     "cwfa_tc_pack_weights": [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp],
     "cwfa_conv_tc": [vp, vp, vp, vp, vp, vp] + [i32] * 14 + [vp],
     "cwfa_tc_set_debug_buffer": [vp],
+    "cwfa_resblock_set_debug_buffer": [vp],
     "cwfa_resblock_tc": [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp],
     "cwfa_c8_stats_workspace_floats": [i32],
     "cwfa_c8_channel_stats": [vp, vp, vp, i32, i32, i64, i32, vp],
@@ -99,7 +100,7 @@ class CwfaError(RuntimeError):
 
 # kernel launches issued per C-ABI call (for bench.py's "gpu_launches" claim)
 _LAUNCHES = {"cwfa_affine": 2, "cwfa_channel_stats_f32": 2, "cwfa_layernorm_chw_f32": 2, "cwfa_c8_channel_stats": 2,
-             "cwfa_tc_set_debug_buffer": 0, "cwfa_device_check": 0}
+             "cwfa_tc_set_debug_buffer": 0, "cwfa_resblock_set_debug_buffer": 0, "cwfa_device_check": 0}
 launch_count = 0
 launch_hist = {}
 

@@ -164,7 +164,11 @@ __device__ __forceinline__ void act_vec(float (&x)[NV], int act, float slope) {
     switch (act) {
         case CWFA_ACT_ELU:
 #pragma unroll
-            for (int j = 0; j < NV; ++j) x[j] = x[j] > 0.f ? x[j] : __expf(x[j]) - 1.f;
+            for (int j = 0; j < NV; ++j) {          // branch-free: max(x,0) + (exp(min(x,0)) - 1)
+                float e;
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(x[j], 0.f) * 1.4426950408889634f));
+                x[j] = fmaxf(x[j], 0.f) + (e - 1.f);
+            }
             break;
         case CWFA_ACT_PRELU:
 #pragma unroll

@@ -7,7 +7,7 @@
 //   EPI2 warps: acc2 -> +b1 + x (residual, L2-hot re-read) -> ELU -> half -> global (16-byte stores)
 // The 3x3->ELU->1x1 intermediate never leaves the SM; both weight sets stay resident in shared memory;
 // acc1/acc2 are double buffered in TMEM (512 columns) so GEMM1 of tile i+1 overlaps the epilogues of tile i.
-// Warp roles (320 threads): warp0 TMA producer, warp1 MMA issuer, warps2-5 EPI1, warps6-9 EPI2.
+// Warp roles (448 threads): warp0 TMA producer, warp1 MMA issuer, warps2-5 EPI1, warps6-13 EPI2 (4 warps per M-block).
 #include "tc_common.cuh"
 using namespace cwfa;
 using namespace cwfa::tcx;
@@ -24,7 +24,7 @@ constexpr uint32_t kA2MbBytes = kChunks * 128 * 16;           // 16384 per M-blo
 constexpr uint32_t kHeader = 2048;
 constexpr uint32_t kOffW3 = kHeader, kOffW1 = kOffW3 + kW3Bytes, kOffA1 = kOffW1 + kW1Bytes,
                    kOffA2 = kOffA1 + 2 * kA1Bytes, kSmemTotal = kOffA2 + 2 * kA2MbBytes;
-constexpr int kThreads = 320;
+constexpr int kThreads = 448;        // warp0 TMA, warp1 MMA, warps2-5 EPI1, warps6-13 EPI2 (one M-block per warp set)
 
 struct RbParams {
     int N, H, W, tiles_x, tiles_y, num_tiles;
@@ -35,7 +35,15 @@ struct RbParams {
     const uint8_t* w1;       // packed [8][64][8]
     const float* b3;         // 64
     const float* b1;         // 64
+    unsigned long long* dbg;  // optional profiling stamps: [cta][tile<8][8]
 };
+__device__ __forceinline__ void rb_stamp(const RbParams& p, int tile, int slot) {
+    if (p.dbg && tile < 8) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.dbg[((size_t)blockIdx.x * 8 + tile) * 8 + slot] = t;
+    }
+}
 
 template <bool BF16>
 __global__ void __launch_bounds__(kThreads, 1) resblock_tc_kernel(const __grid_constant__ CUtensorMap tmap, const RbParams p) {
@@ -64,7 +72,7 @@ __global__ void __launch_bounds__(kThreads, 1) resblock_tc_kernel(const __grid_c
             mbar_init(acc1_full(b), 1);
             mbar_init(acc1_empty(b), 128);
             mbar_init(acc2_full(b), 1);
-            mbar_init(acc2_empty(b), 128);
+            mbar_init(acc2_empty(b), 256);
         }
         mbar_init(a2_full, 128);
         mbar_init(a2_empty, 1);
@@ -136,24 +144,26 @@ __global__ void __launch_bounds__(kThreads, 1) resblock_tc_kernel(const __grid_c
             mbar_wait(a1_full(b), ph);
             mbar_wait(acc1_empty(b), ph ^ 1);
             tc_fence_after();
+            if (leader) rb_stamp(p, i, 0);
             if (leader) {
                 const uint32_t a_base = s0 + kOffA1 + b * kA1Bytes;
 #pragma unroll 1
                 for (int tap = 0; tap < 9; ++tap) {
                     const int kh = tap / 3, kw = tap - kh * 3;
                     const uint32_t w_lo = w3_lo0 + tap * (kTapBytes >> 4);
+                    const uint32_t a_lo0 = desc_lo(a_base + (uint32_t)((kh * kBW + kw) * 16), a1_lbo);
+                    // interleave the two M-blocks: back-to-back MMAs never accumulate into the same TMEM tile
 #pragma unroll
-                    for (int mb = 0; mb < 2; ++mb) {
-                        const uint32_t d = tmem + (b * 2 + mb) * kC;
-                        const uint32_t a_lo0 = desc_lo(a_base + (uint32_t)((kh * kBW + mb * 8 + kw) * 16), a1_lbo);
+                    for (int kk = 0; kk < 4; ++kk) {
 #pragma unroll
-                        for (int kk = 0; kk < 4; ++kk)
-                            tc_mma_f16_split(d, a_lo0 + kk * ((2 * a1_lbo) >> 4), a1_hi, w_lo + kk * ((2 * w_lbo) >> 4), w_hi,
-                                             idesc, (tap | kk) ? 1u : 0u);
+                        for (int mb = 0; mb < 2; ++mb)
+                            tc_mma_f16_split(tmem + (b * 2 + mb) * kC, a_lo0 + mb * 8 + kk * ((2 * a1_lbo) >> 4), a1_hi,
+                                             w_lo + kk * ((2 * w_lbo) >> 4), w_hi, idesc, (tap | kk) ? 1u : 0u);
                     }
                 }
                 tc_commit(a1_empty(b));
                 tc_commit(acc1_full(b));
+                rb_stamp(p, i, 1);
             }
             __syncwarp();
             if (i >= 1) gemm2(i - 1);
@@ -166,34 +176,36 @@ __global__ void __launch_bounds__(kThreads, 1) resblock_tc_kernel(const __grid_c
         for (int i = 0; i < my_tiles; ++i) {
             const int b = i & 1, ph = (i >> 1) & 1;
             mbar_wait(acc1_full(b), ph);
+            if (threadIdx.x == 64) rb_stamp(p, i, 2);
             mbar_wait(a2_empty, (i & 1) ^ 1);
             tc_fence_after();
+            if (threadIdx.x == 64) rb_stamp(p, i, 3);
 #pragma unroll 1
             for (int mb = 0; mb < 2; ++mb) {
                 uint8_t* a2 = smem + kOffA2 + mb * kA2MbBytes + m * 16;
-#pragma unroll 1
-                for (int c0 = 0; c0 < kC; c0 += 16) {
-                    uint32_t r[16];
-                    __syncwarp();
-                    tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((b * 2 + mb) * kC + c0), r);
-                    float v[16];
+                uint32_t r[64];
+                __syncwarp();
+                const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((b * 2 + mb) * kC);
+                tmem_ld32_nowait(ta, r);
+                tmem_ld32_nowait(ta + 32, r + 32);
+                tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = elu_fast(__uint_as_float(r[j]) + s_b3[c0 + j]);
-#pragma unroll
-                    for (int hh = 0; hh < 2; ++hh) {
-                        uint4 ov;
-                        ov.x = pack2<BF16>(v[hh * 8 + 0], v[hh * 8 + 1]);
-                        ov.y = pack2<BF16>(v[hh * 8 + 2], v[hh * 8 + 3]);
-                        ov.z = pack2<BF16>(v[hh * 8 + 4], v[hh * 8 + 5]);
-                        ov.w = pack2<BF16>(v[hh * 8 + 6], v[hh * 8 + 7]);
-                        *reinterpret_cast<uint4*>(a2 + ((c0 >> 3) + hh) * (128 * 16)) = ov;
-                    }
+                for (int ch = 0; ch < 8; ++ch) {
+                    const float4 ba = *reinterpret_cast<const float4*>(s_b3 + ch * 8);
+                    const float4 bb = *reinterpret_cast<const float4*>(s_b3 + ch * 8 + 4);
+                    uint4 ov;
+                    ov.x = pack2<BF16>(elu_fast(__uint_as_float(r[ch * 8 + 0]) + ba.x), elu_fast(__uint_as_float(r[ch * 8 + 1]) + ba.y));
+                    ov.y = pack2<BF16>(elu_fast(__uint_as_float(r[ch * 8 + 2]) + ba.z), elu_fast(__uint_as_float(r[ch * 8 + 3]) + ba.w));
+                    ov.z = pack2<BF16>(elu_fast(__uint_as_float(r[ch * 8 + 4]) + bb.x), elu_fast(__uint_as_float(r[ch * 8 + 5]) + bb.y));
+                    ov.w = pack2<BF16>(elu_fast(__uint_as_float(r[ch * 8 + 6]) + bb.z), elu_fast(__uint_as_float(r[ch * 8 + 7]) + bb.w));
+                    *reinterpret_cast<uint4*>(a2 + ch * (128 * 16)) = ov;
                 }
             }
             tc_fence_before();
             fence_proxy_async();                // make the generic-proxy smem writes visible to the tensor core
             mbar_arrive(acc1_empty(b));
             mbar_arrive(a2_full);
+            if (threadIdx.x == 64) rb_stamp(p, i, 4);
         }
     } else {
         // ============================ EPI2: acc2 + b1 + x -> ELU -> global ============================
@@ -205,47 +217,47 @@ __global__ void __launch_bounds__(kThreads, 1) resblock_tc_kernel(const __grid_c
             const int n = t / tiles_per_img, rr = t % tiles_per_img;
             const int h0 = (rr / p.tiles_x) * kTH, w0 = (rr % p.tiles_x) * kTW;
             const int orow = h0 + (m >> 3);
+            const int mb = (warp - 6) >> 2;               // warps 6-9 -> M-block 0, warps 10-13 -> M-block 1
+            const int ocol = w0 + mb * 8 + (m & 7);
+            const bool ok = orow < p.H && ocol < p.W;
+            const size_t pix = (size_t)orow * p.W + ocol;
+            // prefetch the residual x BEFORE waiting on the accumulator (L2-hot: the halo tile of this very tile
+            // was just fetched by TMA); 8 x 16-byte loads in flight per thread
+            uint4 rx[8];
+            {
+                const uint8_t* xin = p.x + (((size_t)n * p.in_total_chunks + p.in_chunk_off) * plane + pix) * 16;
+#pragma unroll
+                for (int ch = 0; ch < 8; ++ch)
+                    rx[ch] = ok ? __ldg(reinterpret_cast<const uint4*>(xin + (size_t)ch * plane * 16)) : make_uint4(0, 0, 0, 0);
+            }
             mbar_wait(acc2_full(b), ph);
             tc_fence_after();
-#pragma unroll 1
-            for (int mb = 0; mb < 2; ++mb) {
-                const int ocol = w0 + mb * 8 + (m & 7);
-                const bool ok = orow < p.H && ocol < p.W;
-                const size_t pix = (size_t)orow * p.W + ocol;
-                const uint8_t* xin = p.x + (((size_t)n * p.in_total_chunks + p.in_chunk_off) * plane + pix) * 16;
+            if (threadIdx.x == 192) rb_stamp(p, i, 5);
+            {
                 uint8_t* yout = p.y + (((size_t)n * p.out_total_chunks + p.out_chunk_off) * plane + pix) * 16;
-#pragma unroll 1
-                for (int c0 = 0; c0 < kC; c0 += 16) {
-                    uint4 rx[2];
-                    if (ok) {
-                        rx[0] = __ldg(reinterpret_cast<const uint4*>(xin + (size_t)(c0 >> 3) * plane * 16));
-                        rx[1] = __ldg(reinterpret_cast<const uint4*>(xin + (size_t)((c0 >> 3) + 1) * plane * 16));
-                    } else {
-                        rx[0] = rx[1] = make_uint4(0, 0, 0, 0);
-                    }
-                    uint32_t r[16];
-                    __syncwarp();
-                    tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(256 + (b * 2 + mb) * kC + c0), r);
+                uint32_t r[64];
+                __syncwarp();
+                const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(256 + (b * 2 + mb) * kC);
+                tmem_ld32_nowait(ta, r);
+                tmem_ld32_nowait(ta + 32, r + 32);
+                tmem_ld_wait();
 #pragma unroll
-                    for (int hh = 0; hh < 2; ++hh) {
-                        const uint32_t rw[4] = {rx[hh].x, rx[hh].y, rx[hh].z, rx[hh].w};
-                        uint32_t ow[4];
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const float2 xr = unpack2<BF16>(rw[k]);
-                            const int j = hh * 8 + 2 * k;
-                            const float a = elu_fast(__uint_as_float(r[j]) + s_b1[c0 + j] + xr.x);
-                            const float c = elu_fast(__uint_as_float(r[j + 1]) + s_b1[c0 + j + 1] + xr.y);
-                            ow[k] = pack2<BF16>(a, c);
-                        }
-                        if (ok)
-                            *reinterpret_cast<uint4*>(yout + (size_t)((c0 >> 3) + hh) * plane * 16) =
-                                make_uint4(ow[0], ow[1], ow[2], ow[3]);
-                    }
+                for (int ch = 0; ch < 8; ++ch) {
+                    const float4 ba = *reinterpret_cast<const float4*>(s_b1 + ch * 8);
+                    const float4 bb = *reinterpret_cast<const float4*>(s_b1 + ch * 8 + 4);
+                    const float2 x0 = unpack2<BF16>(rx[ch].x), x1 = unpack2<BF16>(rx[ch].y),
+                                 x2 = unpack2<BF16>(rx[ch].z), x3 = unpack2<BF16>(rx[ch].w);
+                    uint4 ov;
+                    ov.x = pack2<BF16>(elu_fast(__uint_as_float(r[ch * 8 + 0]) + ba.x + x0.x), elu_fast(__uint_as_float(r[ch * 8 + 1]) + ba.y + x0.y));
+                    ov.y = pack2<BF16>(elu_fast(__uint_as_float(r[ch * 8 + 2]) + ba.z + x1.x), elu_fast(__uint_as_float(r[ch * 8 + 3]) + ba.w + x1.y));
+                    ov.z = pack2<BF16>(elu_fast(__uint_as_float(r[ch * 8 + 4]) + bb.x + x2.x), elu_fast(__uint_as_float(r[ch * 8 + 5]) + bb.y + x2.y));
+                    ov.w = pack2<BF16>(elu_fast(__uint_as_float(r[ch * 8 + 6]) + bb.z + x3.x), elu_fast(__uint_as_float(r[ch * 8 + 7]) + bb.w + x3.y));
+                    if (ok) *reinterpret_cast<uint4*>(yout + (size_t)ch * plane * 16) = ov;
                 }
             }
             tc_fence_before();
             mbar_arrive(acc2_empty(b));
+            if (threadIdx.x == 192) rb_stamp(p, i, 6);
         }
     }
     tc_fence_before();
@@ -257,6 +269,9 @@ __global__ void __launch_bounds__(kThreads, 1) resblock_tc_kernel(const __grid_c
 }
 
 }  // namespace
+
+static unsigned long long* g_rb_dbg = nullptr;
+extern "C" int cwfa_resblock_set_debug_buffer(void* buf) { g_rb_dbg = (unsigned long long*)buf; return CWFA_OK; }
 
 extern "C" int cwfa_resblock_tc(const void* x_c8, void* y_c8, const void* w3_packed, const void* w1_packed, const float* b3,
                                 const float* b1, int N, int H, int W, int in_total_chunks, int in_chunk_off,
@@ -281,6 +296,7 @@ extern "C" int cwfa_resblock_tc(const void* x_c8, void* y_c8, const void* w3_pac
     p.out_total_chunks = out_total_chunks; p.out_chunk_off = out_chunk_off;
     p.x = (const uint8_t*)x_c8; p.y = (uint8_t*)y_c8; p.w3 = (const uint8_t*)w3_packed; p.w1 = (const uint8_t*)w1_packed;
     p.b3 = b3; p.b1 = b1;
+    p.dbg = g_rb_dbg;
     CUtensorMap tmap;
     int rc = make_c8_tensor_map(&tmap, x_c8, N, in_total_chunks, H, W, kBW, kBH, kChunks, is_bf16);
     if (rc) return rc;

@@ -160,6 +160,7 @@ int cwfa_c8_bn_apply(const void* x, const float* scale, const float* shift, void
                      int N, int Cp, int H, int W, int is_bf16, void* stream);
 /* Profiling aid: when set (device buffer of 8 uint64 per CTA), conv_tc records globaltimer stamps. */
 int cwfa_tc_set_debug_buffer(void* buf);
+int cwfa_resblock_set_debug_buffer(void* buf);   /* [cta][8 tiles][8 stamps] uint64 */
 /* Layout converters NCHW fp32 <-> C8 half (channels padded with zeros up to Cp). */
 int cwfa_nchw_to_c8(const float* x, void* y, int N, int C, int Cp, int64_t P, int is_bf16, void* stream);
 int cwfa_c8_to_nchw(const void* x, float* y, int N, int C, int Cp, int64_t P, int is_bf16, void* stream);
