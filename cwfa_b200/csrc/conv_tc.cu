@@ -333,7 +333,8 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
             float v[16];
 #pragma unroll
             for (int j = 0; j < 16; j += 4) {
-                const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c0 + j);
+                float4 b4;
+                asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w) : "r"(bar0 + 1024u + (uint32_t)(c0 + j) * 4u));
                 v[j] = __uint_as_float(r[j]) + b4.x;
                 v[j + 1] = __uint_as_float(r[j + 1]) + b4.y;
                 v[j + 2] = __uint_as_float(r[j + 2]) + b4.z;

@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(kThreads, 1) resblock_tc_kernel(const __grid_c
             if (threadIdx.x == 64) rb_stamp(p, i, 3);
 #pragma unroll 1
             for (int mb = 0; mb < 2; ++mb) {
-                uint8_t* a2 = smem + kOffA2 + mb * kA2MbBytes + m * 16;
+                const uint32_t a2 = s0 + kOffA2 + mb * kA2MbBytes + m * 16;
                 uint32_t r[64];
                 __syncwarp();
                 const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((b * 2 + mb) * kC);
@@ -191,14 +191,14 @@ __global__ void __launch_bounds__(kThreads, 1) resblock_tc_kernel(const __grid_c
                 tmem_ld_wait();
 #pragma unroll
                 for (int ch = 0; ch < 8; ++ch) {
-                    const float4 ba = *reinterpret_cast<const float4*>(s_b3 + ch * 8);
-                    const float4 bb = *reinterpret_cast<const float4*>(s_b3 + ch * 8 + 4);
+                    const float4 ba = lds128(s0 + 1024 + ch * 32);
+                    const float4 bb = lds128(s0 + 1024 + ch * 32 + 16);
                     uint4 ov;
                     ov.x = pack2<BF16>(elu_fast(__uint_as_float(r[ch * 8 + 0]) + ba.x), elu_fast(__uint_as_float(r[ch * 8 + 1]) + ba.y));
                     ov.y = pack2<BF16>(elu_fast(__uint_as_float(r[ch * 8 + 2]) + ba.z), elu_fast(__uint_as_float(r[ch * 8 + 3]) + ba.w));
                     ov.z = pack2<BF16>(elu_fast(__uint_as_float(r[ch * 8 + 4]) + bb.x), elu_fast(__uint_as_float(r[ch * 8 + 5]) + bb.y));
                     ov.w = pack2<BF16>(elu_fast(__uint_as_float(r[ch * 8 + 6]) + bb.z), elu_fast(__uint_as_float(r[ch * 8 + 7]) + bb.w));
-                    *reinterpret_cast<uint4*>(a2 + ch * (128 * 16)) = ov;
+                    sts128(a2 + ch * (128 * 16), ov);
                 }
             }
             tc_fence_before();
@@ -243,8 +243,8 @@ __global__ void __launch_bounds__(kThreads, 1) resblock_tc_kernel(const __grid_c
                 tmem_ld_wait();
 #pragma unroll
                 for (int ch = 0; ch < 8; ++ch) {
-                    const float4 ba = *reinterpret_cast<const float4*>(s_b1 + ch * 8);
-                    const float4 bb = *reinterpret_cast<const float4*>(s_b1 + ch * 8 + 4);
+                    const float4 ba = lds128(s0 + 1024 + 256 + ch * 32);
+                    const float4 bb = lds128(s0 + 1024 + 256 + ch * 32 + 16);
                     const float2 x0 = unpack2<BF16>(rx[ch].x), x1 = unpack2<BF16>(rx[ch].y),
                                  x2 = unpack2<BF16>(rx[ch].z), x3 = unpack2<BF16>(rx[ch].w);
                     uint4 ov;

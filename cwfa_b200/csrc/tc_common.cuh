@@ -126,6 +126,15 @@ __device__ __forceinline__ float2 unpack2(uint32_t u) {
         return __half22float2(*reinterpret_cast<__half2*>(&u));
     }
 }
+// Explicit shared-space accesses (a generic-pointer float4 access compiles to LD.E/ST.E: long-scoreboard latency).
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, const uint4& v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 // Branch-free ELU: max(x,0) + (exp(min(x,0)) - 1).  (A ternary makes the compiler emit a divergent
 // branch per element around the MUFU; measured 47 cycles/element in the epilogue.)
 __device__ __forceinline__ float elu_fast(float x) {
