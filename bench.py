@@ -235,7 +235,7 @@ def main():
         orig = _lib.call
 
         def timed_call(name, *a):
-            if name == "cwfa_conv_tc":
+            if name in ("cwfa_conv_tc", "cwfa_resblock_tc"):
                 s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 s.record()
                 orig(name, *a)
@@ -288,7 +288,7 @@ def main():
         "e2e": {"value": e2e_fps, "unit": UNIT, "h2d_bytes_per_step": views_host[0].numel() * 4, "d2h_bytes_per_step": out_host.numel() * 4,
                 "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": launches_per_step * args.steps,
-        "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv)", "achieved": achieved, "peak": peak_tf,
+        "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel + resblock_tc_kernel (tcgen05 implicit-GEMM convolutions)", "achieved": achieved, "peak": peak_tf,
                      "unit": "TFLOP/s", "frac": (achieved / peak_tf) if achieved else None, "traffic": traffic,
                      "launches_per_step": n_conv, "avg_launch_us": (conv_ms * 1e3 / n_conv) if n_conv else None,
                      "algorithmic_flop_per_step": conv_flop, "conv_ms_per_step": conv_ms, "peak_source": peak_src,

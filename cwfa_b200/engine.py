@@ -37,14 +37,18 @@ class _Subnet:
         last = sub.block72[1] if sub.normal else sub.block7[1]
         self.out = tc.PackedConv(last.weight, last.bias, kind)
 
-    def __call__(self, lf8: tc.C8) -> torch.Tensor:
-        """LF condition (C8) -> fp32 NCHW coefficient tensor (2ch channels, or ch for the _first variant)."""
-        b = tc.conv_tc(lf8, self.inp)
-        fused = b.Cp == 64
-        for p3, p1 in self.res:
+    def __call__(self, lf8: tc.C8, b: Optional[tc.C8] = None, chunk_off: int = 0) -> torch.Tensor:
+        """LF condition (C8) -> fp32 NCHW coefficient tensor (2ch channels, or ch for the _first variant).
+        ``b`` (optional): precomputed output of the input 1x1 conv, possibly a slice (``chunk_off``) of the
+        tensor produced by one batched conv over all sub-networks of the level."""
+        if b is None:
+            b = tc.conv_tc(lf8, self.inp)
+        fused = self.inp.Cout_p == 64
+        for i, (p3, p1) in enumerate(self.res):
             if fused:
-                b = tc.resblock_tc(b, p3, p1)
+                b = tc.resblock_tc(b, p3, p1, chunk_off if i == 0 else 0)
             else:
+                assert chunk_off == 0
                 t = tc.conv_tc(b, p3, act=ops.ACT_ELU)
                 b = tc.conv_tc(t, p1, act=ops.ACT_ELU, res=b, res_mode=1)
         return tc.conv_tc(b, self.out, out_nchw=True)
@@ -186,7 +190,14 @@ class CWFAEngine:
                 else:
                     raise NotImplementedError(f"CWFAEngine supports the default CAT graph; found {type(mod).__name__} "
                                               "(use CWFAModel.reconstruct for other block types)")
-            self.levels.append(dict(nodes=nodes, cond=_CondNet(m.cond_nets[n], kind)))
+            subs = [x[2] for x in nodes if x[0] == "cat"]
+            batched = None
+            if all(sn.inp.Cout_p == 64 and sn.inp.Cin_p == subs[0].inp.Cin_p for sn in subs):
+                # one 1x1 conv for the input layers of all sub-networks of the level (they all read the LF condition)
+                ws = [(mod.subnet.block12 if mod.subnet.normal else mod.subnet.block1) for k_, mod, _ in nodes if k_ == "cat"]
+                batched = tc.PackedConv(torch.cat([w.weight.detach() for w in ws], 0), torch.cat([w.bias.detach() for w in ws], 0),
+                                        kind, bn=64)
+            self.levels.append(dict(nodes=nodes, cond=_CondNet(m.cond_nets[n], kind), batched_in=batched))
         self.lrnn = _LRNN(m.cond_nets[-1], kind)
         self._graphs: Dict = {}
 
@@ -197,9 +208,12 @@ class CWFAEngine:
         lv = self.levels[n]
         lf8 = lv["cond"](v8)
         out = []
+        b_all = tc.conv_tc(lf8, lv["batched_in"]) if lv["batched_in"] is not None else None
+        k = 0
         for kind, mod, extra in lv["nodes"]:
             if kind == "cat":
-                a = extra(lf8)
+                a = extra(lf8, b_all, 8 * k) if b_all is not None else extra(lf8)
+                k += 1
                 if extra.normal:
                     ch = mod.channels
                     out.append((mod, a[:, :ch], a[:, ch:], 1.0))

@@ -174,14 +174,15 @@ def batchnorm_c8(x: C8, gamma, beta, running_mean, running_var, *, batch_stats: 
     return (y, yp) if pool else y
 
 
-def resblock_tc(x: C8, p3: PackedConv, p1: PackedConv) -> C8:
-    """Fused trunk residual block y = ELU(conv1x1(ELU(conv3x3(x))) + x) for 64 channels (one persistent kernel)."""
+def resblock_tc(x: C8, p3: PackedConv, p1: PackedConv, in_chunk_off: int = 0) -> C8:
+    """Fused trunk residual block y = ELU(conv1x1(ELU(conv3x3(x))) + x) for 64 channels (one persistent kernel).
+    ``x`` may be a wider C8 tensor; ``in_chunk_off`` selects the 64-channel slice (8 chunks) to read."""
     for pc, k in ((p3, 3), (p1, 1)):
         if pc.Cin_p != 64 or pc.Cout_p != 64 or pc.BN != 64 or pc.KH != k or pc.bias is None or pc.kind != x.kind:
             raise ValueError("resblock_tc: needs 64->64 convs (3x3 then 1x1) packed with BN=64 and biases")
-    if x.Cp != 64:
-        raise ValueError("resblock_tc: input must have 64 channels")
+    if x.Cp < 64 or in_chunk_off * 8 + 64 > x.Cp:
+        raise ValueError("resblock_tc: input slice out of range")
     y = C8.empty(x.N, 64, x.H, x.W, x.data.device, x.kind, 64)
     _lib.call("cwfa_resblock_tc", x.data.data_ptr(), y.data.data_ptr(), p3.packed.data_ptr(), p1.packed.data_ptr(),
-              p3.bias.data_ptr(), p1.bias.data_ptr(), x.N, x.H, x.W, 8, 0, 8, 0, x.is_bf16, _stream())
+              p3.bias.data_ptr(), p1.bias.data_ptr(), x.N, x.H, x.W, x.Cp // 8, in_chunk_off, 8, 0, x.is_bf16, _stream())
     return y
