@@ -170,6 +170,7 @@ class CWFAEngine:
         if not next(model.parameters()).is_cuda:
             raise RuntimeError("CWFAEngine needs the model on a CUDA device (no CPU fallback)")
         self.model, self.kind = model, kind
+        self.parallel_branches = True      # LRNN and per-level coefficient nets as parallel CUDA-graph branches
         self.refresh()
 
     def refresh(self):
@@ -223,10 +224,10 @@ class CWFAEngine:
                 out.append((mod, extra))
         return out
 
-    def _level_inverse(self, n, lo, v8, mean_vol):
+    def _level_inverse(self, n, lo, coeffs):
         hi = None          # z = 0 (INN_z_temperature = 0, CWFA.py:906-907): never materialised
         jac = None
-        for item in reversed(self._coeffs(n, v8, mean_vol)):
+        for item in reversed(coeffs):
             if len(item) == 4:
                 mod, a_s, a_t, ts = item
                 hi, j = ops.affine(hi, a_s, a_t, inverse=True, clamp=mod.clamp, t_scale=ts)
@@ -237,14 +238,37 @@ class CWFAEngine:
         return ops.haar1d_merge(lo, hi), jac
 
     @torch.no_grad()
-    def reconstruct(self, views: torch.Tensor, mean_vols: Sequence[Optional[torch.Tensor]], return_all: bool = False):
-        """Inverse reconstruction (CWFA.py:865-924) at z = 0."""
+    def reconstruct(self, views: torch.Tensor, mean_vols: Sequence[Optional[torch.Tensor]], return_all: bool = False,
+                    _side_streams=None):
+        """Inverse reconstruction (CWFA.py:865-924) at z = 0.
+
+        The LRNN and the coupling coefficients of every level depend only on the views / mean volumes, not on
+        each other, so under CUDA-graph capture they are issued on side streams (``_side_streams``) and become
+        parallel branches of the graph; only the short affine/Haar chain is sequential."""
         L1 = self.model.n_levels
         v8 = tc.to_c8(views, self.kind)
-        vol = self.lrnn(v8, mean_vols[L1] if len(mean_vols) > L1 else None)
+        mv_last = mean_vols[L1] if len(mean_vols) > L1 else None
+        jobs = [lambda: self.lrnn(v8, mv_last)] + [(lambda n=n: self._coeffs(n, v8, mean_vols[n])) for n in range(L1 - 1, -1, -1)]
+        if _side_streams:
+            main = torch.cuda.current_stream()
+            fork = torch.cuda.Event()
+            fork.record(main)
+            results, joins = [], []
+            for st, job in zip(_side_streams, jobs):
+                st.wait_event(fork)
+                with torch.cuda.stream(st):
+                    results.append(job())
+                    ev = torch.cuda.Event()
+                    ev.record(st)
+                joins.append(ev)
+            for ev in joins:
+                main.wait_event(ev)
+        else:
+            results = [job() for job in jobs]
+        vol = results[0]
         outs, jacs = {L1: vol}, {}
-        for n in range(L1 - 1, -1, -1):
-            vol, jac = self._level_inverse(n, vol, v8, mean_vols[n])
+        for k, n in enumerate(range(L1 - 1, -1, -1)):
+            vol, jac = self._level_inverse(n, vol, results[1 + k])
             outs[n], jacs[n] = vol, jac
         return (outs, jacs) if return_all else vol
 
@@ -292,8 +316,9 @@ class CWFAEngine:
                     self.reconstruct(sv, sm)
             torch.cuda.current_stream().wait_stream(s)
             graph = torch.cuda.CUDAGraph()
+            side = [torch.cuda.Stream() for _ in range(self.model.n_levels + 1)] if self.parallel_branches else None
             with torch.cuda.graph(graph):
-                out = self.reconstruct(sv, sm)
+                out = self.reconstruct(sv, sm, _side_streams=side)
             g = self._graphs[key] = (graph, sv, sm, out)
         graph, sv, sm, out = g
         sv.copy_(views, non_blocking=True)

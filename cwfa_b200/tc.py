@@ -81,7 +81,11 @@ class PackedConv:
         self.Cin_p = pad16(Cin) if cin_p is None else cin_p
         self.Cout_p = pad16(Cout)
         tot_p = 4 * self.Cout_p if transposed else self.Cout_p
-        self.BN = pick_bn(tot_p if not transposed else self.Cout_p) if bn is None else bn
+        if bn is None:
+            bn = pick_bn(tot_p if not transposed else self.Cout_p)
+            if self.Cin_p <= 64 and bn == 256:
+                bn = 128          # small-K convs are epilogue-bound: two co-resident CTAs (256 TMEM columns each) overlap
+        self.BN = bn
         self.tot_p = tot_p
         lib = _lib.load()
         n = lib.cwfa_tc_packed_weight_elems(self.Cin_p, tot_p, KH, KW, self.BN)

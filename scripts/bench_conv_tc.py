@@ -12,6 +12,8 @@ SHAPES = [  # cin, cout, k, H, W, mb, bn
     (256, 512, 3, 256, 256, 2, 256), (512, 512, 3, 256, 256, 2, 256),
     (512, 1024, 3, 128, 128, 2, 256), (1024, 1024, 3, 128, 128, 2, 256), (1024, 1024, 3, 128, 128, 1, 256),
     (64, 64, 7, 512, 512, 2, 64),
+    (256, 256, 3, 512, 512, 2, 128), (48, 1536, 3, 512, 512, 2, 256), (48, 1536, 3, 512, 512, 2, 128), (1536, 48, 3, 512, 512, 2, 48),
+    (1536, 48, 3, 512, 512, 1, 48), (16, 256, 3, 512, 512, 2, 128), (512, 512, 3, 256, 256, 2, 128), (64, 96, 3, 512, 512, 2, 96), (64, 96, 3, 512, 512, 1, 96), (64, 48, 3, 512, 512, 2, 48),
 ]
 
 def run(cin, cout, k, H, W, mb, bn, act=ops.ACT_ELU, reps=3):
@@ -39,4 +41,4 @@ def run(cin, cout, k, H, W, mb, bn, act=ops.ACT_ELU, reps=3):
 if __name__ == "__main__":
     sel = [int(a) for a in sys.argv[1:]] or range(len(SHAPES))
     for i in sel:
-        run(*SHAPES[i], reps=1 if len(sys.argv) > 1 else 3)
+        run(*SHAPES[i], reps=4)
