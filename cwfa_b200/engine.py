@@ -301,10 +301,10 @@ class CWFAEngine:
         return res
 
     # ---- CUDA-graph replay of the whole frame -------------------------------------------
-    def reconstruct_graphed(self, views: torch.Tensor, mean_vols: Sequence[Optional[torch.Tensor]]) -> torch.Tensor:
-        """Same as ``reconstruct`` but replays a captured CUDA graph (static shapes; inputs are copied into
-        static buffers, the returned tensor is the graph's static output buffer)."""
-        key = (tuple(views.shape), tuple(None if m is None else tuple(m.shape) for m in mean_vols), views.device.index)
+    def _graph_slot(self, views: torch.Tensor, mean_vols, slot: int = 0):
+        """(graph, static_views, static_mean_vols, static_out) for this shape; ``slot`` selects an independent
+        instance (own static buffers) so that several frames can be in flight."""
+        key = (tuple(views.shape), tuple(None if m is None else tuple(m.shape) for m in mean_vols), views.device.index, slot)
         g = self._graphs.get(key)
         if g is None:
             sv = views.clone()
@@ -320,7 +320,12 @@ class CWFAEngine:
             with torch.cuda.graph(graph):
                 out = self.reconstruct(sv, sm, _side_streams=side)
             g = self._graphs[key] = (graph, sv, sm, out)
-        graph, sv, sm, out = g
+        return g
+
+    def reconstruct_graphed(self, views: torch.Tensor, mean_vols: Sequence[Optional[torch.Tensor]]) -> torch.Tensor:
+        """Same as ``reconstruct`` but replays a captured CUDA graph (static shapes; inputs are copied into
+        static buffers, the returned tensor is the graph's static output buffer)."""
+        graph, sv, sm, out = self._graph_slot(views, mean_vols)
         sv.copy_(views, non_blocking=True)
         for d, s_ in zip(sm, mean_vols):
             if d is not None:
@@ -345,3 +350,54 @@ class CWFAEngine:
         out_host.copy_(out, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return out_host
+
+
+class StreamingReconstructor:
+    """Streaming reconstruction of a sequence of frames held in HOST memory (BASELINE.json configs[4]):
+    ``depth`` independent graph instances; the pinned H2D copy of frame i+1 and the D2H copy of frame i-1
+    overlap the graph replay of frame i (copy streams + events, no host synchronisation inside the loop).
+    The mean-volume pyramid is a dataset constant and stays on the device."""
+
+    def __init__(self, engine: CWFAEngine, views_shape, mean_vols: Sequence[Optional[torch.Tensor]], depth: int = 2):
+        self.eng, self.depth = engine, depth
+        dev = mean_vols[0].device
+        probe = torch.zeros(views_shape, device=dev, dtype=torch.float32)
+        self.slots = [engine._graph_slot(probe, mean_vols, slot=k) for k in range(depth)]
+        for (graph, sv, sm, out) in self.slots:
+            for d, s_ in zip(sm, mean_vols):
+                if d is not None:
+                    d.copy_(s_)
+        self.s_in, self.s_out, self.s_run = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        self.ev_in = [torch.cuda.Event() for _ in range(depth)]
+        self.ev_run = [torch.cuda.Event() for _ in range(depth)]
+        self.ev_out = [torch.cuda.Event() for _ in range(depth)]
+        torch.cuda.synchronize(dev)
+
+    def run(self, views_host: Sequence[torch.Tensor], out_host: Sequence[torch.Tensor]) -> None:
+        """Reconstructs ``views_host[i]`` into ``out_host[i]`` (both pinned host tensors); returns when every
+        output has landed in host memory."""
+        n = len(views_host)
+        cur = torch.cuda.current_stream()
+        for st in (self.s_in, self.s_out, self.s_run):
+            st.wait_stream(cur)
+        for i in range(n):
+            k = i % self.depth
+            graph, sv, sm, out = self.slots[k]
+            with torch.cuda.stream(self.s_in):
+                if i >= self.depth:
+                    self.s_in.wait_event(self.ev_run[k])      # previous replay of this slot has consumed its input
+                sv.copy_(views_host[i], non_blocking=True)
+                self.ev_in[k].record(self.s_in)
+            with torch.cuda.stream(self.s_run):
+                self.s_run.wait_event(self.ev_in[k])
+                if i >= self.depth:
+                    self.s_run.wait_event(self.ev_out[k])     # previous output of this slot has left the device
+                graph.replay()
+                self.ev_run[k].record(self.s_run)
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_event(self.ev_run[k])
+                out_host[i].copy_(out, non_blocking=True)
+                self.ev_out[k].record(self.s_out)
+        cur.wait_stream(self.s_out)
+        cur.wait_stream(self.s_run)
+        cur.synchronize()

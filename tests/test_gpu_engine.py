@@ -96,3 +96,19 @@ def test_unet_pieces_c8(golden_tiny):
     refr = F.batch_norm(xb, rm, rv, g, be, training=False)
     yr = tc.batchnorm_c8(tc.to_c8(xb.to(DEV)), g.to(DEV), be.to(DEV), rm.to(DEV), rv.to(DEV), batch_stats=False)
     assert rel_l2(tc.from_c8(yr), refr) < 4e-3
+
+
+def test_streaming_host_api_matches_engine(golden_tiny, model):
+    from cwfa_b200.engine import CWFAEngine, StreamingReconstructor
+    views, mean_vols = tiny_inputs(golden_tiny)
+    mv = [t.to(DEV) for t in mean_vols]
+    eng = CWFAEngine(model, "bf16")
+    frames = [seeded_randn(tuple(views.shape), 50 + i).pin_memory() for i in range(5)]
+    outs = [torch.empty((1, golden_tiny["config"]["D"], views.shape[2], views.shape[3]), dtype=torch.float32, pin_memory=True)
+            for _ in range(5)]
+    StreamingReconstructor(eng, tuple(views.shape), mv, depth=2).run(frames, outs)
+    for f, o in zip(frames, outs):
+        ref = eng.reconstruct(f.to(DEV), mv)
+        assert torch.equal(o, ref.cpu()), "streamed frames must equal the one-by-one result bit for bit"
+    one = eng.reconstruct_host(frames[2], mv)
+    assert torch.equal(one, outs[2])
