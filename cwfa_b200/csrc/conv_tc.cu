@@ -97,11 +97,43 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // No-swizzle K-major shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
 // [0,14) start>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version = 1, layout_type [61,64) = 0.
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
            ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+
+// atan(x) with |error| <= ~1e-7: odd minimax polynomial on [0,1] (Abramowitz & Stegun 4.4.49) + reciprocal
+// range reduction.  ~15 instructions instead of libdevice atanf's ~40 (the coupling epilogue is ALU-bound).
+__device__ __forceinline__ float atan_fast(float x) {
+    const float a = fabsf(x);
+    const bool big = a > 1.f;
+    const float z = big ? __frcp_rn(a) : a;
+    const float s = z * z;
+    float p = 0.0028662257f;
+    p = fmaf(p, s, -0.0161657367f);
+    p = fmaf(p, s, 0.0429096138f);
+    p = fmaf(p, s, -0.0752896400f);
+    p = fmaf(p, s, 0.1065626393f);
+    p = fmaf(p, s, -0.1420889944f);
+    p = fmaf(p, s, 0.1999355085f);
+    p = fmaf(p, s, -0.3333314528f);
+    p = fmaf(p * s, z, z);
+    const float r = big ? 1.57079632679489662f - p : p;
+    return copysignf(r, x);
+}
+__device__ __forceinline__ float exp_fast(float x) {      // |x| <= clamp (~2): no range handling needed
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 1.4426950408889634f));
+    return e;
 }
 
 struct TcParams {
@@ -123,6 +155,15 @@ struct TcParams {
     const uint8_t* res;
     void* out;
     unsigned long long* dbg;      // optional: 8 globaltimer stamps per CTA (profiling aid, NULL = off)
+    // out_mode 3: fused affine coupling (coupling_layers.py:490-500).  Columns [0,ch) = s_raw, [ch,2ch) = t unless
+    // cpl_t (external shift, scaled by cpl_tscale).  x is read through the preceding permutation (gather).
+    const float* cpl_x;           // (N,ch,H,W) fp32 or NULL (= zeros, z = 0)
+    float* cpl_y;                 // (N,ch,H,W) fp32
+    const float* cpl_t;           // external shift or NULL
+    const int* cpl_perm;          // gather indices along cpl_axis (1 chan, 2 row, 3 col) or NULL
+    float* cpl_ws;                // [grid.x][2] partial (sum s, sum y^2)
+    int cpl_ch, cpl_axis, cpl_inverse;
+    float cpl_kk, cpl_tscale;
 };
 
 __device__ __forceinline__ void stamp(const TcParams& p, int slot) {
@@ -190,8 +231,8 @@ __device__ __forceinline__ void act_vec(float (&x)[NV], int act, float slope) {
     }
 }
 
-template <bool BF16>
-__global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
+template <bool BF16, bool COUPLING>
+__global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     // [0,2048): barriers + tmem slot + bias stage; then A ring, then B ring
@@ -314,12 +355,98 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
         const float slope = (p.act == CWFA_ACT_PRELU && p.slope) ? __ldg(p.slope) : 0.f;
         const size_t plane = (size_t)p.H * p.W;
         for (int i = threadIdx.x - 64; i < p.BN; i += kEpiThreads) s_bias[i] = p.bias ? __ldg(p.bias + nblk * p.BN + i) : 0.f;
+        int* s_perm = reinterpret_cast<int*>(smem + 640);            // channel permutation (<= 64 entries) for out_mode 3
+        if (p.out_mode == 3 && p.cpl_perm && p.cpl_axis == 1)
+            for (int i = threadIdx.x - 64; i < p.cpl_ch; i += kEpiThreads) s_perm[i] = __ldg(p.cpl_perm + i);
         asm volatile("bar.sync 1, 256;" ::: "memory");
+        constexpr int kMaxG = 6;                     // coupling: <= 6 groups of 8 channels per thread (ch <= 48, MB = 2)
+        // coupling input x of channel group k, read through the preceding permutation's gather
+        auto load_x = [&](int k, float (&dst)[8]) {
+            const int ch = p.cpl_ch;
+            const int gpc = (ch + 7) >> 3;
+            const int g = half + 2 * k;
+            const int mb = g / gpc;
+            const int c0 = (g - mb * gpc) << 3;
+            const int ocol = w0 + mb * 8 + (m & 7);
+            const bool ok = g < p.MB * gpc && row_ok && ocol < p.W && p.cpl_x != nullptr;
+            int srow = orow, scol = ocol;
+            if (ok && p.cpl_perm && p.cpl_axis == 2) srow = __ldg(p.cpl_perm + orow);
+            if (ok && p.cpl_perm && p.cpl_axis == 3) scol = __ldg(p.cpl_perm + ocol);
+            const size_t spix = (size_t)srow * p.W + scol;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int c = c0 + j;
+                dst[j] = 0.f;
+                if (ok && c < ch) {
+                    const int sc = (p.cpl_perm && p.cpl_axis == 1) ? s_perm[c] : c;
+                    dst[j] = __ldg(p.cpl_x + ((size_t)n * ch + sc) * plane + spix);
+                }
+            }
+        };
+        float xa[8], xb[8];
+        if constexpr (COUPLING) load_x(0, xa);       // first group: latency hides behind the MMAs
         mbar_wait(acc_full, 0);
         tc_fence_after();
         if (threadIdx.x == 64) stamp(p, 5);
+        if constexpr (COUPLING) {
+            // ---------- fused affine coupling + log-det (K3 folded into the last conv of the sub-network) ----------
+            const int ch = p.cpl_ch;
+            const int gpc = (ch + 7) >> 3;               // 8-channel groups
+            float sum_s = 0.f, sum_q = 0.f;
+#pragma unroll
+            for (int k = 0; k < kMaxG; ++k) {
+                const int g = half + 2 * k;
+                if (g >= p.MB * gpc) break;
+                float (&xc)[8] = (k & 1) ? xb : xa;
+                float (&xn)[8] = (k & 1) ? xa : xb;
+                if (k + 1 < kMaxG) load_x(k + 1, xn);    // software pipeline: next group's gather in flight
+                const int mb = g / gpc;
+                const int c0 = (g - mb * gpc) << 3;
+                const int ocol = w0 + mb * 8 + (m & 7);
+                const bool ok = row_ok && ocol < p.W;
+                const size_t opix = (size_t)orow * p.W + ocol;
+                uint32_t rs[8], rt[8];
+                float tx[8];
+                if (p.cpl_t) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        tx[j] = (ok && c0 + j < ch) ? __ldg(p.cpl_t + ((size_t)n * ch + c0 + j) * plane + opix) : 0.f;
+                }
+                __syncwarp();
+                const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mb * p.BN + c0);
+                tmem_ld8_nowait(ta, rs);
+                if (!p.cpl_t) tmem_ld8_nowait(ta + ch, rt);
+                tmem_ld_wait();
+                if (ok) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int c = c0 + j;
+                        if (c < ch) {
+                            const float sv = p.cpl_kk * atan_fast(__uint_as_float(rs[j]) + s_bias[c]);
+                            const float tv = p.cpl_t ? p.cpl_tscale * tx[j] : __uint_as_float(rt[j]) + s_bias[ch + c];
+                            const float yv = p.cpl_inverse ? (xc[j] - tv) * exp_fast(-sv) : fmaf(exp_fast(sv), xc[j], tv);
+                            p.cpl_y[((size_t)n * ch + c) * plane + opix] = yv;
+                            sum_s += sv;
+                            sum_q = fmaf(yv, yv, sum_q);
+                        }
+                    }
+                }
+            }
+            // deterministic CTA partial: warp shuffle -> smem -> one thread
+            sum_s = warp_sum(sum_s);
+            sum_q = warp_sum(sum_q);
+            float* red = reinterpret_cast<float*>(smem + 512);      // 8 warps x 2 floats
+            if (lane == 0) { red[(warp - 2) * 2] = sum_s; red[(warp - 2) * 2 + 1] = sum_q; }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (threadIdx.x == 64) {
+                float a = 0.f, b = 0.f;
+                for (int k = 0; k < 8; ++k) { a += red[2 * k]; b += red[2 * k + 1]; }
+                p.cpl_ws[(size_t)blockIdx.x * 2] = p.cpl_inverse ? -a : a;
+                p.cpl_ws[(size_t)blockIdx.x * 2 + 1] = b;
+            }
+        }
         const int gpm = p.BN >> 4;                   // 16-column groups per M-block
-        const int ngroups = p.MB * gpm;
+        const int ngroups = COUPLING ? 0 : p.MB * gpm;
         for (int g = half; g < ngroups; g += 2) {
             const int mb = g / gpm;
             const int c0 = (g - mb * gpm) << 4;
@@ -506,19 +633,25 @@ extern "C" int cwfa_tc_pack_weights(const float* w, void* packed, int Cout, int 
 static unsigned long long* g_tc_dbg = nullptr;
 extern "C" int cwfa_tc_set_debug_buffer(void* buf) { g_tc_dbg = (unsigned long long*)buf; return CWFA_OK; }
 
-extern "C" int cwfa_conv_tc(const void* x_c8, const void* w_packed, const float* bias, const float* slope,
-                            const void* res, void* out, int N, int H, int W, int Cin_p, int Cout, int Cout_p, int KH,
-                            int KW, int BN, int MB, int act, int res_mode, int out_mode, int is_bf16, void* stream) {
+struct CouplingArgs {
+    const float* x; float* y; const float* t; const int* perm; float* ws;
+    int ch, axis, inverse; float kk, tscale;
+};
+
+static int conv_tc_launch(const void* x_c8, const void* w_packed, const float* bias, const float* slope,
+                          const void* res, void* out, int N, int H, int W, int Cin_p, int Cout, int Cout_p, int KH,
+                          int KW, int BN, int MB, int act, int res_mode, int out_mode, int is_bf16, void* stream,
+                          const CouplingArgs* cpl) {
     const int KC = pick_kc(Cin_p);
     if (N <= 0 || H <= 0 || W <= 0 || !KC || (Cin_p % 16) || (Cout_p % BN) || (BN % 16) || BN < 16 || BN > 256 ||
         (MB != 1 && MB != 2) || MB * BN > 512 || !(KH & 1) || !(KW & 1) || KH > 7 || KW > 7 || out_mode < 0 ||
-        out_mode > 2 || (out_mode == 2 && (KH != 1 || KW != 1))) {
+        out_mode > 3 || (out_mode == 2 && (KH != 1 || KW != 1)) || (out_mode == 3 && (!cpl || BN != Cout_p))) {
         set_error("conv_tc: unsupported configuration (Cin_p=%d Cout_p=%d BN=%d MB=%d K=%dx%d)", Cin_p, Cout_p, BN, MB, KH, KW);
         return CWFA_EINVAL;
     }
     if (res_mode != 0 && !res) { set_error("conv_tc: res_mode set but res is NULL"); return CWFA_EINVAL; }
     if ((reinterpret_cast<uintptr_t>(x_c8) & 15) || (reinterpret_cast<uintptr_t>(w_packed) & 15) ||
-        (reinterpret_cast<uintptr_t>(out) & 15)) {
+        (out_mode != 3 && (reinterpret_cast<uintptr_t>(out) & 15))) {
         set_error("conv_tc: pointers must be 16-byte aligned");
         return CWFA_EINVAL;
     }
@@ -550,6 +683,10 @@ extern "C" int cwfa_conv_tc(const void* x_c8, const void* w_packed, const float*
     p.act = act; p.res_mode = res_mode; p.out_mode = out_mode; p.is_bf16 = is_bf16;
     p.w_packed = (const uint8_t*)w_packed; p.bias = bias; p.slope = slope; p.res = (const uint8_t*)res; p.out = out;
     p.dbg = g_tc_dbg;
+    if (cpl) {
+        p.cpl_x = cpl->x; p.cpl_y = cpl->y; p.cpl_t = cpl->t; p.cpl_perm = cpl->perm; p.cpl_ws = cpl->ws;
+        p.cpl_ch = cpl->ch; p.cpl_axis = cpl->axis; p.cpl_inverse = cpl->inverse; p.cpl_kk = cpl->kk; p.cpl_tscale = cpl->tscale;
+    }
     const size_t smem = fixed + (size_t)bs * p.b_bytes;
 
     CUtensorMap tmap;
@@ -562,17 +699,70 @@ extern "C" int cwfa_conv_tc(const void* x_c8, const void* w_packed, const float*
                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) { set_error("conv_tc: cuTensorMapEncodeTiled failed (%d)", (int)cr); return CWFA_ECUDA; }
 
-    auto kern = is_bf16 ? conv_tc_kernel<true> : conv_tc_kernel<false>;
-    static bool attr_done[2] = {false, false};
-    if (!attr_done[is_bf16 ? 1 : 0]) {
+    auto kern = out_mode == 3 ? (is_bf16 ? conv_tc_kernel<true, true> : conv_tc_kernel<false, true>)
+                              : (is_bf16 ? conv_tc_kernel<true, false> : conv_tc_kernel<false, false>);
+    static bool attr_done[4] = {false, false, false, false};
+    const int ki = (out_mode == 3 ? 2 : 0) + (is_bf16 ? 1 : 0);
+    if (!attr_done[ki]) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        attr_done[is_bf16 ? 1 : 0] = true;
+        attr_done[ki] = true;
     }
     const int64_t gx = (int64_t)p.tiles_x * p.tiles_y * N;
     if (gx > 0x7fffffff) { set_error("conv_tc: grid too large"); return CWFA_EINVAL; }
     dim3 grid((unsigned)gx, (out_mode == 2 ? 4 : 1) * Cout_p / BN);
     kern<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmap, p);
     return check_launch("conv_tc");
+}
+
+extern "C" int cwfa_conv_tc(const void* x_c8, const void* w_packed, const float* bias, const float* slope,
+                            const void* res, void* out, int N, int H, int W, int Cin_p, int Cout, int Cout_p, int KH,
+                            int KW, int BN, int MB, int act, int res_mode, int out_mode, int is_bf16, void* stream) {
+    if (out_mode == 3) { set_error("conv_tc: use cwfa_conv_tc_coupling for the fused coupling epilogue"); return CWFA_EINVAL; }
+    return conv_tc_launch(x_c8, w_packed, bias, slope, res, out, N, H, W, Cin_p, Cout, Cout_p, KH, KW, BN, MB, act, res_mode,
+                          out_mode, is_bf16, stream, nullptr);
+}
+
+// Last conv of a coupling sub-network with the affine coupling fused into its epilogue.
+extern "C" int cwfa_conv_tc_coupling_tiles(int H, int W, int MB) { return ceil_div(W, 8 * MB) * ceil_div(H, 16); }
+
+extern "C" int cwfa_conv_tc_coupling(const void* x_c8, const void* w_packed, const float* bias, int N, int H, int W, int Cin_p,
+                                     int Cout, int Cout_p, int KH, int KW, int MB, const float* cx, float* cy,
+                                     const float* ct, float t_scale, const int32_t* perm, int perm_axis, int ch,
+                                     float clamp, float k_atan, int inverse, float* workspace, int is_bf16, void* stream) {
+    if (!cy || !workspace || ch <= 0 || ch > 48 || (MB != 1 && MB != 2) || (ct ? Cout < ch : Cout < 2 * ch) || (perm && (perm_axis < 1 || perm_axis > 3)) ||
+        (!cx && !inverse)) {
+        set_error("conv_tc_coupling: bad arguments");
+        return CWFA_EINVAL;
+    }
+    CouplingArgs c{cx, cy, ct, perm, workspace, ch, perm_axis, inverse, clamp * k_atan, t_scale};
+    return conv_tc_launch(x_c8, w_packed, bias, nullptr, nullptr, nullptr, N, H, W, Cin_p, Cout, Cout_p, KH, KW, Cout_p, MB,
+                          CWFA_ACT_NONE, 0, 3, is_bf16, stream, &c);
+}
+
+// Sums the per-CTA partials of cwfa_conv_tc_coupling per sample in a fixed order (bit-reproducible):
+// logdet[n] (+)= sum, sumsq[n] = sum y^2 (if not NULL).
+__global__ void coupling_finalize_kernel(const float* __restrict__ ws, float* __restrict__ logdet, float* __restrict__ sumsq,
+                                         int tiles, int accumulate) {
+    const int n = blockIdx.x;
+    double s = 0.0, q = 0.0;
+    for (int i = threadIdx.x; i < tiles; i += 32) {
+        s += (double)ws[((size_t)n * tiles + i) * 2];
+        q += (double)ws[((size_t)n * tiles + i) * 2 + 1];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    if (threadIdx.x == 0) {
+        logdet[n] = (accumulate ? logdet[n] : 0.f) + (float)s;
+        if (sumsq) sumsq[n] = (float)q;
+    }
+}
+extern "C" int cwfa_coupling_finalize(const float* workspace, float* logdet, float* sumsq, int N, int tiles, int accumulate,
+                                      void* stream) {
+    coupling_finalize_kernel<<<N, 32, 0, (cudaStream_t)stream>>>(workspace, logdet, sumsq, tiles, accumulate);
+    return check_launch("coupling_finalize");
 }
 
 // ------------------------------------------------------------------ layout converters

@@ -35,12 +35,12 @@ class _Subnet:
             blk = getattr(sub, name)
             self.res.append((tc.PackedConv(blk[0].weight, blk[0].bias, kind), tc.PackedConv(blk[2].weight, blk[2].bias, kind)))
         last = sub.block72[1] if sub.normal else sub.block7[1]
-        self.out = tc.PackedConv(last.weight, last.bias, kind)
+        self.out = tc.PackedConv(last.weight, last.bias, kind, bn=tc.pad16(last.weight.shape[0]))   # one N block: s and t in one CTA
 
-    def __call__(self, lf8: tc.C8, b: Optional[tc.C8] = None, chunk_off: int = 0) -> torch.Tensor:
-        """LF condition (C8) -> fp32 NCHW coefficient tensor (2ch channels, or ch for the _first variant).
-        ``b`` (optional): precomputed output of the input 1x1 conv, possibly a slice (``chunk_off``) of the
-        tensor produced by one batched conv over all sub-networks of the level."""
+    def trunk(self, lf8: tc.C8, b: Optional[tc.C8] = None, chunk_off: int = 0) -> tc.C8:
+        """LF condition (C8) -> ELU(b6) (C8, n hidden channels).  ``b`` (optional): precomputed output of the input
+        1x1 conv, possibly a slice (``chunk_off``) of the tensor produced by one batched conv over all
+        sub-networks of the level."""
         if b is None:
             b = tc.conv_tc(lf8, self.inp)
         fused = self.inp.Cout_p == 64
@@ -51,7 +51,11 @@ class _Subnet:
                 assert chunk_off == 0
                 t = tc.conv_tc(b, p3, act=ops.ACT_ELU)
                 b = tc.conv_tc(t, p1, act=ops.ACT_ELU, res=b, res_mode=1)
-        return tc.conv_tc(b, self.out, out_nchw=True)
+        return b
+
+    def __call__(self, lf8: tc.C8) -> torch.Tensor:
+        """LF condition -> fp32 NCHW coefficient tensor (unfused path)."""
+        return tc.conv_tc(self.trunk(lf8), self.out, out_nchw=True)
 
 
 class _CondNet:
@@ -203,39 +207,45 @@ class CWFAEngine:
         self._graphs: Dict = {}
 
     # -------------------------------------------------------------------------------------
-    def _coeffs(self, n: int, v8: tc.C8, mean_vol: torch.Tensor):
-        """Coupling coefficients of level n: they depend on the conditions only (CAT blocks,
-        coupling_layers.py:475-500), so forward and inverse share them."""
+    def _trunks(self, n: int, v8: tc.C8):
+        """Conditioning net + the trunks of all sub-networks of level n.  They depend on the conditions only (CAT
+        blocks, coupling_layers.py:475-500), so forward and inverse share them and levels are independent."""
         lv = self.levels[n]
         lf8 = lv["cond"](v8)
-        out = []
         b_all = tc.conv_tc(lf8, lv["batched_in"]) if lv["batched_in"] is not None else None
-        k = 0
+        out, k = [], 0
         for kind, mod, extra in lv["nodes"]:
             if kind == "cat":
-                a = extra(lf8, b_all, 8 * k) if b_all is not None else extra(lf8)
+                out.append(("cat", mod, extra, extra.trunk(lf8, b_all, 8 * k) if b_all is not None else extra.trunk(lf8)))
                 k += 1
-                if extra.normal:
-                    ch = mod.channels
-                    out.append((mod, a[:, :ch], a[:, ch:], 1.0))
-                else:
-                    out.append((mod, a, mean_vol, -1.0 / math.sqrt(2)))
             else:
-                out.append((mod, extra))
+                out.append(("perm", mod, extra, None))
         return out
 
-    def _level_inverse(self, n, lo, coeffs):
-        hi = None          # z = 0 (INN_z_temperature = 0, CWFA.py:906-907): never materialised
-        jac = None
-        for item in reversed(coeffs):
-            if len(item) == 4:
-                mod, a_s, a_t, ts = item
-                hi, j = ops.affine(hi, a_s, a_t, inverse=True, clamp=mod.clamp, t_scale=ts)
-                jac = j if jac is None else jac + j
+    def _couple(self, item, x, mean_vol, pending, inverse, logdet, sumsq=None):
+        """Final conv of one sub-network with the coupling fused in its epilogue."""
+        _, mod, sub, b8 = item
+        perm, axis = (None, 0) if pending is None else (ops.perm_i32(pending[0], b8.data.device), pending[1])
+        first = not sub.normal
+        return tc.conv_tc_coupling(b8, sub.out, x, ch=mod.channels, inverse=inverse, clamp=mod.clamp,
+                                   t_ext=mean_vol if first else None, t_scale=(-1.0 / math.sqrt(2)) if first else 1.0,
+                                   perm=perm, perm_axis=axis, logdet=logdet, sumsq=sumsq)
+
+    def _level_detail_inverse(self, n, v8, mean_vol):
+        """Detail half ``hi`` of level n in the inverse direction at z = 0 (INN_z_temperature = 0,
+        CWFA.py:906-907: z is never materialised) and its log-det.  Independent of the other levels."""
+        items = self._trunks(n, v8)
+        hi, pending = None, None
+        jac = torch.zeros(v8.N, device=v8.data.device, dtype=torch.float32)
+        for item in reversed(items):
+            if item[0] == "cat":
+                hi = self._couple(item, hi, mean_vol, pending, True, jac)
+                pending = None
             elif hi is not None:
-                mod, axis = item
-                hi = ops.permute(hi, mod.perm_inv, axis)
-        return ops.haar1d_merge(lo, hi), jac
+                pending = (item[1].perm_inv, item[2])       # gathered by the next coupling's epilogue
+        if pending is not None:
+            hi = ops.permute(hi, pending[0], pending[1])
+        return hi, jac
 
     @torch.no_grad()
     def reconstruct(self, views: torch.Tensor, mean_vols: Sequence[Optional[torch.Tensor]], return_all: bool = False,
@@ -244,11 +254,11 @@ class CWFAEngine:
 
         The LRNN and the coupling coefficients of every level depend only on the views / mean volumes, not on
         each other, so under CUDA-graph capture they are issued on side streams (``_side_streams``) and become
-        parallel branches of the graph; only the short affine/Haar chain is sequential."""
+        parallel branches of the graph; only the four Haar merges are sequential."""
         L1 = self.model.n_levels
         v8 = tc.to_c8(views, self.kind)
         mv_last = mean_vols[L1] if len(mean_vols) > L1 else None
-        jobs = [lambda: self.lrnn(v8, mv_last)] + [(lambda n=n: self._coeffs(n, v8, mean_vols[n])) for n in range(L1 - 1, -1, -1)]
+        jobs = [lambda: self.lrnn(v8, mv_last)] + [(lambda n=n: self._level_detail_inverse(n, v8, mean_vols[n])) for n in range(L1 - 1, -1, -1)]
         if _side_streams:
             main = torch.cuda.current_stream()
             fork = torch.cuda.Event()
@@ -268,7 +278,8 @@ class CWFAEngine:
         vol = results[0]
         outs, jacs = {L1: vol}, {}
         for k, n in enumerate(range(L1 - 1, -1, -1)):
-            vol, jac = self._level_inverse(n, vol, results[1 + k])
+            hi, jac = results[1 + k]
+            vol = ops.haar1d_merge(vol, hi)          # Split^-1 + IDWT: the only sequential part of the pyramid
             outs[n], jacs[n] = vol, jac
         return (outs, jacs) if return_all else vol
 
@@ -280,20 +291,17 @@ class CWFAEngine:
         x = volume
         for n in range(self.model.n_levels):
             lo, hi = ops.haar1d_split(x)
-            jac, sumsq = None, None
-            items = self._coeffs(n, v8, mean_vols[n])
-            last_cat = max(i for i, it in enumerate(items) if len(it) == 4)
-            for i, item in enumerate(items):
-                if len(item) == 4:
-                    mod, a_s, a_t, ts = item
-                    r = ops.affine(hi, a_s, a_t, inverse=False, clamp=mod.clamp, t_scale=ts, want_sumsq=(i == last_cat))
-                    hi, j = r[0], r[1]
-                    if i == last_cat:
-                        sumsq = r[2]          # permutations after the last block do not change ||z||^2
-                    jac = j if jac is None else jac + j
+            jac = torch.zeros(x.shape[0], device=x.device, dtype=torch.float32)
+            sumsq = torch.empty_like(jac)
+            pending = None
+            for item in self._trunks(n, v8):
+                if item[0] == "cat":
+                    hi = self._couple(item, hi, mean_vols[n], pending, False, jac, sumsq)   # sumsq: last coupling wins
+                    pending = None
                 else:
-                    mod, axis = item
-                    hi = ops.permute(hi, mod.perm, axis)
+                    pending = (item[1].perm, item[2])
+            if pending is not None:          # trailing permutation: does not change ||z||^2
+                hi = ops.permute(hi, pending[0], pending[1])
             per = (0.5 * sumsq - jac) / hi[0].numel()
             ref = (0.5 * sumsq.sum() - jac) / lo.numel()
             res.append(dict(z=hi, lo=lo, logdet=jac, sumsq=sumsq, nll_per_sample=per, nll_ref=ref))

@@ -190,3 +190,32 @@ def resblock_tc(x: C8, p3: PackedConv, p1: PackedConv, in_chunk_off: int = 0) ->
     _lib.call("cwfa_resblock_tc", x.data.data_ptr(), y.data.data_ptr(), p3.packed.data_ptr(), p1.packed.data_ptr(),
               p3.bias.data_ptr(), p1.bias.data_ptr(), x.N, x.H, x.W, x.Cp // 8, in_chunk_off, 8, 0, x.is_bf16, _stream())
     return y
+
+
+def conv_tc_coupling(b: C8, pc: PackedConv, x: Optional[torch.Tensor], *, ch: int, inverse: bool, clamp: float = 2.0,
+                     k_atan: float = 0.636, t_ext: Optional[torch.Tensor] = None, t_scale: float = 1.0,
+                     perm: Optional[torch.Tensor] = None, perm_axis: int = 0, logdet: torch.Tensor = None,
+                     sumsq: Optional[torch.Tensor] = None, accumulate: bool = True, mb: Optional[int] = None) -> torch.Tensor:
+    """Last conv of a coupling sub-network with the affine coupling, the log-det partial sums and the preceding
+    permutation (as a gather on ``x``) fused into its epilogue.  ``x`` None = zeros (z = 0, inverse only).
+    ``logdet`` (B,) is accumulated in place (fixed-order reduction); ``sumsq`` (B,) receives sum(y^2)."""
+    if b.Cp != pc.Cin_p or b.kind != pc.kind:
+        raise ValueError("conv_tc_coupling: input layout mismatch")
+    need = ch if t_ext is not None else 2 * ch
+    if pc.Cout != need or pc.BN != pc.Cout_p:
+        raise ValueError(f"conv_tc_coupling: weights give {pc.Cout} channels (BN {pc.BN}), need {need} in one N block")
+    N, H, W = b.N, b.H, b.W
+    if mb is None:
+        mb = 2 if W > 8 else 1
+    dev = b.data.device
+    y = torch.empty((N, ch, H, W), device=dev, dtype=torch.float32)
+    xx = None if x is None else _ck(x, "x")
+    tt = None if t_ext is None else _ck(t_ext, "t_ext")
+    lib = _lib.load()
+    tiles = lib.cwfa_conv_tc_coupling_tiles(H, W, mb)
+    ws = torch.empty(2 * N * tiles, device=dev, dtype=torch.float32)
+    _lib.call("cwfa_conv_tc_coupling", b.data.data_ptr(), pc.packed.data_ptr(), _p(pc.bias), N, H, W, pc.Cin_p, pc.Cout,
+              pc.Cout_p, pc.KH, pc.KW, mb, _p(xx), y.data_ptr(), _p(tt), float(t_scale), _p(perm), int(perm_axis), ch,
+              float(clamp), float(k_atan), int(inverse), ws.data_ptr(), b.is_bf16, _stream())
+    _lib.call("cwfa_coupling_finalize", ws.data_ptr(), logdet.data_ptr(), _p(sumsq), N, tiles, int(accumulate), _stream())
+    return y

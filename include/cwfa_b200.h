@@ -161,6 +161,20 @@ int cwfa_c8_bn_apply(const void* x, const float* scale, const float* shift, void
 /* Profiling aid: when set (device buffer of 8 uint64 per CTA), conv_tc records globaltimer stamps. */
 int cwfa_tc_set_debug_buffer(void* buf);
 int cwfa_resblock_set_debug_buffer(void* buf);   /* [cta][8 tiles][8 stamps] uint64 */
+/* ---- K2+K3+K4 fused: the LAST conv of a coupling sub-network (networks.py:635-638) with the affine coupling
+ * (coupling_layers.py:490-500), the per-sample log-det partial sums and the preceding permutation's gather
+ * (fixed_transforms.py:37-41, INN_utils.py:73-81) in its epilogue.  Conv columns [0,ch) = s_raw, [ch,2ch) = t,
+ * or t = t_scale * ct when ct != NULL (networks.py:671).  cx (may be NULL = zeros in inverse mode) is read as
+ * cx[gather]; cy is written densely.  workspace: 2 * N * cwfa_conv_tc_coupling_tiles(H,W,MB) floats; reduce it
+ * with cwfa_coupling_finalize (fixed order => bit-reproducible): logdet[n] (+)= sum s (sign per direction),
+ * sumsq[n] = sum y^2. */
+int cwfa_conv_tc_coupling_tiles(int H, int W, int MB);
+int cwfa_conv_tc_coupling(const void* x_c8, const void* w_packed, const float* bias, int N, int H, int W,
+                          int Cin_p, int Cout, int Cout_p, int KH, int KW, int MB, const float* cx, float* cy,
+                          const float* ct, float t_scale, const int32_t* perm, int perm_axis, int ch,
+                          float clamp, float k_atan, int inverse, float* workspace, int is_bf16, void* stream);
+int cwfa_coupling_finalize(const float* workspace, float* logdet, float* sumsq, int N, int tiles,
+                           int accumulate, void* stream);
 /* Layout converters NCHW fp32 <-> C8 half (channels padded with zeros up to Cp). */
 int cwfa_nchw_to_c8(const float* x, void* y, int N, int C, int Cp, int64_t P, int is_bf16, void* stream);
 int cwfa_c8_to_nchw(const void* x, float* y, int N, int C, int Cp, int64_t P, int is_bf16, void* stream);
