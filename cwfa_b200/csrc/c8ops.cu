@@ -33,7 +33,7 @@ __device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
     return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-constexpr int kC8StatBlocks = 64;    // blocks per chunk
+constexpr int kC8StatBlocks = 32;    // blocks per chunk
 
 template <bool BF16>
 __global__ void __launch_bounds__(256) c8_stats_kernel(const uint4* __restrict__ x, float* __restrict__ ws, int N,
@@ -43,11 +43,29 @@ __global__ void __launch_bounds__(256) c8_stats_kernel(const uint4* __restrict__
 #pragma unroll
     for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
     const int64_t per = (int64_t)N * P;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < per; i += (int64_t)gridDim.x * blockDim.x) {
-        const int n = (int)(i / P);
-        const int64_t pix = i % P;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    auto addr = [&](int64_t i) { return x + ((i / P) * chunks + ch) * P + (i % P); };
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < per; i += 4 * stride) {          // 4 independent 16-byte loads in flight per thread
+        const uint4 u0 = __ldg(addr(i)), u1 = __ldg(addr(i + stride)), u2 = __ldg(addr(i + 2 * stride)),
+                    u3 = __ldg(addr(i + 3 * stride));
         float v[8];
-        unpack8<BF16>(__ldg(x + ((int64_t)n * chunks + ch) * P + pix), v);
+        unpack8<BF16>(u0, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s[j] += v[j]; q[j] = fmaf(v[j], v[j], q[j]); }
+        unpack8<BF16>(u1, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s[j] += v[j]; q[j] = fmaf(v[j], v[j], q[j]); }
+        unpack8<BF16>(u2, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s[j] += v[j]; q[j] = fmaf(v[j], v[j], q[j]); }
+        unpack8<BF16>(u3, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s[j] += v[j]; q[j] = fmaf(v[j], v[j], q[j]); }
+    }
+    for (; i < per; i += stride) {
+        float v[8];
+        unpack8<BF16>(__ldg(addr(i)), v);
 #pragma unroll
         for (int j = 0; j < 8; ++j) { s[j] += v[j]; q[j] = fmaf(v[j], v[j], q[j]); }
     }

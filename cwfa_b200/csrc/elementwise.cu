@@ -527,3 +527,61 @@ extern "C" int cwfa_gate_add_f32(float* x, const float* m, const float* g, int64
     return check_launch("gate_add");
 }
 extern "C" int cwfa_layernorm_workspace_blocks(void) { return kLNBlocks; }
+
+// ------------------------------------------------------------------------------------------
+// GlobalAttention gate of the LRNN (networks.py:244-262, :554), fused:
+//   g = sigmoid(W2 * relu(W1 (*) v + b1) + b2)  with v = mean volume flattened over H*W (Conv1d k=3, zero pad),
+//   x += m * 2 * (g - 0.5)
+// One thread per sequence position; C <= 16 channels live in registers.
+// ------------------------------------------------------------------------------------------
+constexpr int kAttMaxC = 16;
+__global__ void __launch_bounds__(256) attention_gate_kernel(float* __restrict__ x, const float* __restrict__ m,
+                                                             const float* __restrict__ v, const float* __restrict__ w1,
+                                                             const float* __restrict__ b1, const float* __restrict__ w2,
+                                                             const float* __restrict__ b2, int C, int64_t L) {
+    __shared__ float sw1[kAttMaxC * kAttMaxC * 3], sw2[kAttMaxC * kAttMaxC], sb1[kAttMaxC], sb2[kAttMaxC];
+    for (int i = threadIdx.x; i < C * C * 3; i += blockDim.x) sw1[i] = __ldg(w1 + i);
+    for (int i = threadIdx.x; i < C * C; i += blockDim.x) sw2[i] = __ldg(w2 + i);
+    for (int i = threadIdx.x; i < C; i += blockDim.x) { sb1[i] = __ldg(b1 + i); sb2[i] = __ldg(b2 + i); }
+    __syncthreads();
+    const int b = blockIdx.y;
+    const float* vb = v + (int64_t)b * C * L;
+    for (int64_t l = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; l < L; l += (int64_t)gridDim.x * blockDim.x) {
+        float h[kAttMaxC];
+#pragma unroll
+        for (int o = 0; o < kAttMaxC; ++o) h[o] = o < C ? sb1[o] : 0.f;
+#pragma unroll
+        for (int c = 0; c < kAttMaxC; ++c) {
+            if (c < C) {
+                const float vm = l > 0 ? __ldg(vb + (int64_t)c * L + l - 1) : 0.f;
+                const float v0 = __ldg(vb + (int64_t)c * L + l);
+                const float vp = l + 1 < L ? __ldg(vb + (int64_t)c * L + l + 1) : 0.f;
+#pragma unroll
+                for (int o = 0; o < kAttMaxC; ++o)
+                    if (o < C) h[o] = fmaf(sw1[(o * C + c) * 3 + 2], vp, fmaf(sw1[(o * C + c) * 3 + 1], v0, fmaf(sw1[(o * C + c) * 3], vm, h[o])));
+            }
+        }
+#pragma unroll
+        for (int o = 0; o < kAttMaxC; ++o) h[o] = fmaxf(h[o], 0.f);
+#pragma unroll
+        for (int o = 0; o < kAttMaxC; ++o) {
+            if (o < C) {
+                float a = sb2[o];
+#pragma unroll
+                for (int c = 0; c < kAttMaxC; ++c)
+                    if (c < C) a = fmaf(sw2[o * C + c], h[c], a);
+                const float g = 1.f / (1.f + expf(-a));
+                const int64_t idx = ((int64_t)b * C + o) * L + l;
+                x[idx] += m[idx] * 2.f * (g - 0.5f);
+            }
+        }
+    }
+}
+extern "C" int cwfa_attention_gate_f32(float* x, const float* m, const float* v, const float* w1, const float* b1,
+                                       const float* w2, const float* b2, int B, int C, int64_t L, void* stream) {
+    if (B <= 0 || C <= 0 || C > kAttMaxC || L <= 0 || B > 65535) { set_error("attention_gate: unsupported shape (C <= 16)"); return CWFA_EINVAL; }
+    int blocks = (int)((L + 255) / 256);
+    if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+    attention_gate_kernel<<<dim3(blocks, B), 256, 0, (cudaStream_t)stream>>>(x, m, v, w1, b1, w2, b2, C, L);
+    return check_launch("attention_gate");
+}

@@ -144,22 +144,31 @@ class _LRNN:
         self.kind = kind
         self.proj = tc.PackedConv(net.deconv[0].weight, net.deconv[0].bias, kind)
         self.unet = _UNet(net.deconv[1], kind)
-        cn0 = net.conv3d[0]
-        self.cn0_7x7 = tc.PackedConv(cn0.m[0].weight, cn0.m[0].bias, kind)
-        self.cn0_1x1 = tc.PackedConv(cn0.m[2].weight, cn0.m[2].bias, kind)
+        cn0, cn1 = net.conv3d[0], net.conv3d[1]
+        self.cn0_in = tc.PackedConv(cn0.input.weight, cn0.input.bias, kind)          # 1x1  6 -> 64
+        self.cn0_7x7 = tc.PackedConv(cn0.m[0].weight, cn0.m[0].bias, kind)           # 7x7 64 -> 64
+        self.cn0_1x1 = tc.PackedConv(cn0.m[2].weight, cn0.m[2].bias, kind)           # 1x1 64 -> 64
+        self.cn1_in = tc.PackedConv(cn1.input.weight, cn1.input.bias, kind)          # 1x1 64 -> 6
+        self.cn1_7x7 = tc.PackedConv(cn1.m[0].weight, cn1.m[0].bias, kind)           # 7x7  6 -> 6
 
-    def _convnext_wide(self, cn, x):
-        """ConvNeXt(6 -> 64): the 7x7 64->64 and 1x1 64->64 convs run on the tensor cores."""
-        up = ops.conv2d(x, cn.input.weight, cn.input.bias)
-        m = tc.conv_tc(tc.to_c8(up, self.kind), self.cn0_7x7, out_nchw=True)
-        m = ops.layernorm_chw(m, cn.m[1].weight, cn.m[1].bias, cn.m[1].eps)
-        return tc.conv_tc(tc.to_c8(m, self.kind), self.cn0_1x1, act=ops.ACT_GELU, res=up, res_mode=2, out_nchw=True)
+    def _mean_branch(self, mean_vol: torch.Tensor) -> torch.Tensor:
+        """conv3d = ConvNeXt(6,64) -> ConvNeXt(64,6) on the mean volume (networks.py:486-503,527-530): every conv on
+        the tensor cores (channels padded to 16); LayerNorm([C,H,W]) and the final 6-channel 1x1 stay fp32."""
+        cn0, cn1 = self.net.conv3d[0], self.net.conv3d[1]
+        k = self.kind
+        up8 = tc.conv_tc(tc.to_c8(mean_vol, k), self.cn0_in)                                        # C8, 64 ch
+        m = tc.conv_tc(up8, self.cn0_7x7, out_nchw=True)
+        m = ops.layernorm_chw(m, cn0.m[1].weight, cn0.m[1].bias, cn0.m[1].eps)
+        y8 = tc.conv_tc(tc.to_c8(m, k), self.cn0_1x1, act=ops.ACT_GELU, res=up8, res_mode=2)        # GELU(.) + up
+        up1_8 = tc.conv_tc(y8, self.cn1_in)                                                         # C8, 6 (16) ch
+        m1 = tc.conv_tc(up1_8, self.cn1_7x7, out_nchw=True)
+        m1 = ops.layernorm_chw(m1, cn1.m[1].weight, cn1.m[1].bias, cn1.m[1].eps)
+        return ops.conv2d(m1, cn1.m[2].weight, cn1.m[2].bias, act=ops.ACT_GELU, res=tc.from_c8(up1_8), res_mode=2)
 
     def __call__(self, v8: tc.C8, mean_vol: Optional[torch.Tensor]) -> torch.Tensor:
         x = self.unet(tc.conv_tc(v8, self.proj))
         if mean_vol is not None:
-            mp = self.net.conv3d[1](self._convnext_wide(self.net.conv3d[0], mean_vol))   # 64 -> 6 channels: fp32 kernels
-            x = ops.gate_add_(x, mp, self.net.attention_3d(mean_vol))
+            x = ops.attention_gate_(x, self._mean_branch(mean_vol), mean_vol, self.net.attention_3d)
         return x
 
 

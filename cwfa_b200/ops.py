@@ -284,3 +284,17 @@ def sum_squares(x: torch.Tensor) -> torch.Tensor:
     ws = torch.empty(2 * B * _lib.load().cwfa_stats_workspace_blocks(), device=x.device, dtype=torch.float32)
     _lib.call("cwfa_channel_stats_f32", x.data_ptr(), stats.data_ptr(), ws.data_ptr(), 1, B, n, _stream())
     return stats[B:]
+
+
+def attention_gate_(x: torch.Tensor, m: torch.Tensor, v: torch.Tensor, att) -> torch.Tensor:
+    """x += m * 2 * (GlobalAttention(v) - 0.5) in one kernel (networks.py:244-262, :554).  ``att`` is the GlobalAttention
+    module (parameter holder: att.m[0] Conv1d k=3, att.m[2] Conv1d k=1)."""
+    m, v = _ck(m, "m"), _ck(v, "v")
+    if not (x.is_cuda and x.is_contiguous() and x.dtype == torch.float32):
+        raise RuntimeError("attention_gate_: x must be a contiguous fp32 CUDA tensor")
+    B, C = v.shape[0], v.shape[1]
+    L = v[0, 0].numel()
+    w1, b1, w2, b2 = (_ck(t.detach()) for t in (att.m[0].weight, att.m[0].bias, att.m[2].weight, att.m[2].bias))
+    _lib.call("cwfa_attention_gate_f32", x.data_ptr(), m.data_ptr(), v.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(),
+              b2.data_ptr(), B, C, L, _stream())
+    return x

@@ -121,6 +121,10 @@ int cwfa_maxpool2_f32(const float* x, float* y, int N, int C, int H, int W, void
 int cwfa_layernorm_workspace_blocks(void);
 int cwfa_layernorm_chw_f32(const float* x, const float* gamma, const float* beta, float* y,
                            float* workspace, int N, int64_t CHW, float eps, void* stream);
+/* Fused GlobalAttention gate (networks.py:244-262,554): g = sigmoid(Conv1d_1(relu(Conv1d_3(v flattened over H*W))));
+ * x += m * 2 * (g - 0.5).  v = mean volume (B,C,L), w1 (C,C,3), w2 (C,C,1), C <= 16. */
+int cwfa_attention_gate_f32(float* x, const float* m, const float* v, const float* w1, const float* b1,
+                            const float* w2, const float* b2, int B, int C, int64_t L, void* stream);
 /* x += m * 2 * (g - 0.5)   (networks.py:554) */
 int cwfa_gate_add_f32(float* x, const float* m, const float* g, int64_t n, void* stream);
 
