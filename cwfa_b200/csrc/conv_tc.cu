@@ -136,6 +136,17 @@ __device__ __forceinline__ float exp_fast(float x) {      // |x| <= clamp (~2): 
     return e;
 }
 
+__device__ __forceinline__ float lds_f32(uint32_t saddr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ int lds_s32(uint32_t saddr) {
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+
 struct TcParams {
     int N, H, W;
     int Cout, Cout_p;          // true / padded output channels
@@ -378,13 +389,14 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
                 const int c = c0 + j;
                 dst[j] = 0.f;
                 if (ok && c < ch) {
-                    const int sc = (p.cpl_perm && p.cpl_axis == 1) ? s_perm[c] : c;
+                    const int sc = (p.cpl_perm && p.cpl_axis == 1) ? lds_s32(bar0 + 640u + 4u * c) : c;
                     dst[j] = __ldg(p.cpl_x + ((size_t)n * ch + sc) * plane + spix);
                 }
             }
         };
         float xa[8], xb[8];
         if constexpr (COUPLING) load_x(0, xa);       // first group: latency hides behind the MMAs
+        (void)kMaxG;
         mbar_wait(acc_full, 0);
         tc_fence_after();
         if (threadIdx.x == 64) stamp(p, 5);
@@ -393,13 +405,11 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
             const int ch = p.cpl_ch;
             const int gpc = (ch + 7) >> 3;               // 8-channel groups
             float sum_s = 0.f, sum_q = 0.f;
-#pragma unroll
-            for (int k = 0; k < kMaxG; ++k) {
+#pragma unroll 1
+            for (int k = 0; half + 2 * k < p.MB * gpc; ++k) {
                 const int g = half + 2 * k;
-                if (g >= p.MB * gpc) break;
-                float (&xc)[8] = (k & 1) ? xb : xa;
-                float (&xn)[8] = (k & 1) ? xa : xb;
-                if (k + 1 < kMaxG) load_x(k + 1, xn);    // software pipeline: next group's gather in flight
+                float (&xc)[8] = xa;
+                load_x(k + 1, xb);                       // software pipeline: next group's gather in flight (masked past the end)
                 const int mb = g / gpc;
                 const int c0 = (g - mb * gpc) << 3;
                 const int ocol = w0 + mb * 8 + (m & 7);
@@ -422,8 +432,8 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
                     for (int j = 0; j < 8; ++j) {
                         const int c = c0 + j;
                         if (c < ch) {
-                            const float sv = p.cpl_kk * atan_fast(__uint_as_float(rs[j]) + s_bias[c]);
-                            const float tv = p.cpl_t ? p.cpl_tscale * tx[j] : __uint_as_float(rt[j]) + s_bias[ch + c];
+                            const float sv = p.cpl_kk * atan_fast(__uint_as_float(rs[j]) + lds_f32(bar0 + 1024u + 4u * c));
+                            const float tv = p.cpl_t ? p.cpl_tscale * tx[j] : __uint_as_float(rt[j]) + lds_f32(bar0 + 1024u + 4u * (ch + c));
                             const float yv = p.cpl_inverse ? (xc[j] - tv) * exp_fast(-sv) : fmaf(exp_fast(sv), xc[j], tv);
                             p.cpl_y[((size_t)n * ch + c) * plane + opix] = yv;
                             sum_s += sv;
@@ -431,6 +441,8 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
                         }
                     }
                 }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) xa[j] = xb[j];
             }
             // deterministic CTA partial: warp shuffle -> smem -> one thread
             sum_s = warp_sum(sum_s);
