@@ -131,6 +131,9 @@ def main():
     ap.add_argument("--down-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-nll", action="store_true")
+    ap.add_argument("--inflight", type=int, default=2, help="graph instances (frames) in flight per GPU")
+    ap.add_argument("--e2e-inflight", type=int, default=3, help="frames in flight in the host-buffer streaming measurement")
     args = ap.parse_args()
     cfg = dict(side=args.side, depths=args.depths, steps=args.down_steps)
     rank = int(os.environ.get("RANK", "0"))
@@ -194,9 +197,21 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    # ---- device-resident throughput
-    for i in range(max(3, args.warmup)):
-        run(views_dev[i % n_rot])
+    # ---- device-resident throughput: a stream of frames whose inputs are already in HBM; `depth` graph instances in
+    # flight (frames are independent; consecutive frames overlap on the GPU), outputs written to device buffers
+    from cwfa_b200.engine import StreamingReconstructor
+    depth = 1 if args.no_graph else args.inflight
+    streamer = StreamingReconstructor(eng, tuple(views_dev[0].shape), mvs_dev, depth=depth) if not args.no_graph else None
+    outs_dev = [torch.empty((1, args.depths, args.side, args.side), device=dev, dtype=torch.float32) for _ in range(2)]
+
+    def run_frames(k):
+        if streamer is None:
+            for i in range(k):
+                eng.reconstruct(views_dev[i % n_rot], mvs_dev)
+        else:
+            streamer.run([views_dev[i % n_rot] for i in range(k)], [outs_dev[i % 2] for i in range(k)])
+
+    run_frames(max(3, args.warmup))
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -204,23 +219,32 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
-    for i in range(args.steps):
-        run(views_dev[i % n_rot])
+    run_frames(args.steps)
     e1.record()
     barrier()
     elapsed_ms = e0.elapsed_time(e1)
+    # single-stream, one-graph-at-a-time latency of a frame (reported next to the throughput)
+    if streamer is not None:
+        l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0.record()
+        for i in range(5):
+            eng.reconstruct_graphed(views_dev[i % n_rot], mvs_dev)
+        l1.record()
+        torch.cuda.synchronize()
+        frame_latency_ms = l0.elapsed_time(l1) / 5
+    else:
+        frame_latency_ms = elapsed_ms / args.steps
 
     # ---- end to end through the host-buffer streaming API: every step copies its views H2D from pinned memory and
     # its reconstructed volume D2H into pinned memory; copies of neighbouring frames overlap the compute
-    from cwfa_b200.engine import StreamingReconstructor
-    streamer = StreamingReconstructor(eng, tuple(views_host[0].shape), mvs_dev, depth=2)
-    outs_host = [torch.empty((1, args.depths, args.side, args.side), dtype=torch.float32, pin_memory=True) for _ in range(2)]
-    streamer.run([views_host[i % n_rot] for i in range(3)], [outs_host[i % 2] for i in range(3)])
+    streamer = StreamingReconstructor(eng, tuple(views_host[0].shape), mvs_dev, depth=args.e2e_inflight)
+    outs_host = [torch.empty((1, args.depths, args.side, args.side), dtype=torch.float32, pin_memory=True) for _ in range(4)]
+    streamer.run([views_host[i % n_rot] for i in range(3)], [outs_host[i % 4] for i in range(3)])
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_host0 = time.perf_counter()
     e2.record()
-    streamer.run([views_host[i % n_rot] for i in range(args.steps)], [outs_host[i % 2] for i in range(args.steps)])
+    streamer.run([views_host[i % n_rot] for i in range(args.steps)], [outs_host[i % 4] for i in range(args.steps)])
     e3.record()
     barrier()
     e2e_ms = e2.elapsed_time(e3)
@@ -266,6 +290,25 @@ def main():
         conv_ms = sum(s.elapsed_time(e) for s, e in evs)
         n_conv = len(evs)
 
+    # ---- secondary metric of BASELINE.json: forward pass + per-level NLL / log-det (configs[2], batch 8), few steps
+    nll_fps = None
+    if rank == 0 and not args.no_nll:
+        B = 8
+        g = torch.Generator(device="cpu").manual_seed(7)
+        vol = torch.randn((B, args.depths, args.side, args.side), generator=g).to(dev)
+        vB = torch.randn((B, 29, args.side, args.side), generator=g).to(dev)
+        mvB = [m.repeat(B, 1, 1, 1) for m in mvs_dev[:model.n_levels]]
+        eng.forward_nll(vol, vB, mvB)
+        torch.cuda.synchronize()
+        n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0.record()
+        for _ in range(3):
+            res = eng.forward_nll(vol, vB, mvB)
+        n1.record()
+        torch.cuda.synchronize()
+        nll_fps = 3 * B / (n0.elapsed_time(n1) * 1e-3)
+        del vol, vB, mvB, res
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -292,11 +335,13 @@ def main():
         "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": fps / PUBLISHED_FPS, "dtype": args.kind, "data": "synthetic",
         "config": {"workload": workload, "frames_per_gpu_per_step": 1, "sharding": f"frames (1 per rank, {world} ranks), no data-path collective",
-                   "cuda_graph": not args.no_graph, "l2_policy": "per-step working set (activations ~3 GB) exceeds the 126 MB L2; inputs rotate over 4 buffers",
+                   "cuda_graph": not args.no_graph, "frames_in_flight": depth, "single_frame_latency_ms": frame_latency_ms, "l2_policy": "per-step working set (activations ~3 GB) exceeds the 126 MB L2; inputs rotate over 4 buffers",
                    "baseline_note": "README.md:29 publishes ~0.16 s/frame on unstated hardware"},
         "clocks": clocks,
+        "extra": {"forward_nll_frames_per_s_batch8": nll_fps,
+                  "forward_nll_note": "BASELINE.json configs[2]: 4-level forward pyramid + per-level log-det / sum z^2 / NLL, batch 8, eager (no graph), 1 GPU"},
         "e2e": {"value": e2e_fps, "unit": UNIT, "h2d_bytes_per_step": views_host[0].numel() * 4, "d2h_bytes_per_step": out_host.numel() * 4,
-                "ms_per_step": e2e_ms / args.steps, "api": "StreamingReconstructor.run (2 frames in flight)",
+                "ms_per_step": e2e_ms / args.steps, "api": f"StreamingReconstructor.run ({args.e2e_inflight} frames in flight)",
                 "sync_call_latency_ms": sync_latency_ms, "host_wall_ms_per_step": e2e_host_ms / args.steps},
         "gpu_launches": launches_per_step * args.steps,
         "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel + resblock_tc_kernel (tcgen05 implicit-GEMM convolutions)", "achieved": achieved, "peak": peak_tf,

@@ -370,9 +370,11 @@ class CWFAEngine:
 
 
 class StreamingReconstructor:
-    """Streaming reconstruction of a sequence of frames held in HOST memory (BASELINE.json configs[4]):
-    ``depth`` independent graph instances; the pinned H2D copy of frame i+1 and the D2H copy of frame i-1
-    overlap the graph replay of frame i (copy streams + events, no host synchronisation inside the loop).
+    """Streaming reconstruction of a sequence of frames (BASELINE.json configs[4]): ``depth`` independent graph
+    instances, each on its own stream, so that (a) the H2D copy of frame i+1 and the D2H copy of frame i-1 overlap
+    the replay of frame i, and (b) consecutive frames overlap on the GPU itself (the tail / dependency bubbles of
+    one frame's graph are filled by the next frame's kernels).  Frames are independent, results are bit-identical
+    to one-by-one reconstruction.  Inputs / outputs may live on the host (pinned) or on the device.
     The mean-volume pyramid is a dataset constant and stays on the device."""
 
     def __init__(self, engine: CWFAEngine, views_shape, mean_vols: Sequence[Optional[torch.Tensor]], depth: int = 2):
@@ -384,37 +386,38 @@ class StreamingReconstructor:
             for d, s_ in zip(sm, mean_vols):
                 if d is not None:
                     d.copy_(s_)
-        self.s_in, self.s_out, self.s_run = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        self.s_in = [torch.cuda.Stream(dev) for _ in range(depth)]
+        self.s_run = [torch.cuda.Stream(dev) for _ in range(depth)]
+        self.s_out = [torch.cuda.Stream(dev) for _ in range(depth)]
         self.ev_in = [torch.cuda.Event() for _ in range(depth)]
         self.ev_run = [torch.cuda.Event() for _ in range(depth)]
         self.ev_out = [torch.cuda.Event() for _ in range(depth)]
         torch.cuda.synchronize(dev)
 
-    def run(self, views_host: Sequence[torch.Tensor], out_host: Sequence[torch.Tensor]) -> None:
-        """Reconstructs ``views_host[i]`` into ``out_host[i]`` (both pinned host tensors); returns when every
-        output has landed in host memory."""
-        n = len(views_host)
+    def run(self, views: Sequence[torch.Tensor], outs: Sequence[torch.Tensor]) -> None:
+        """Reconstructs ``views[i]`` into ``outs[i]``; returns when every output has been written."""
+        n = len(views)
         cur = torch.cuda.current_stream()
-        for st in (self.s_in, self.s_out, self.s_run):
+        for st in self.s_in + self.s_run + self.s_out:
             st.wait_stream(cur)
         for i in range(n):
             k = i % self.depth
             graph, sv, sm, out = self.slots[k]
-            with torch.cuda.stream(self.s_in):
+            with torch.cuda.stream(self.s_in[k]):
                 if i >= self.depth:
-                    self.s_in.wait_event(self.ev_run[k])      # previous replay of this slot has consumed its input
-                sv.copy_(views_host[i], non_blocking=True)
-                self.ev_in[k].record(self.s_in)
-            with torch.cuda.stream(self.s_run):
-                self.s_run.wait_event(self.ev_in[k])
+                    self.s_in[k].wait_event(self.ev_run[k])      # previous replay of this slot has consumed its input
+                sv.copy_(views[i], non_blocking=True)
+                self.ev_in[k].record(self.s_in[k])
+            with torch.cuda.stream(self.s_run[k]):
+                self.s_run[k].wait_event(self.ev_in[k])
                 if i >= self.depth:
-                    self.s_run.wait_event(self.ev_out[k])     # previous output of this slot has left the device
+                    self.s_run[k].wait_event(self.ev_out[k])     # previous output of this slot has been copied out
                 graph.replay()
-                self.ev_run[k].record(self.s_run)
-            with torch.cuda.stream(self.s_out):
-                self.s_out.wait_event(self.ev_run[k])
-                out_host[i].copy_(out, non_blocking=True)
-                self.ev_out[k].record(self.s_out)
-        cur.wait_stream(self.s_out)
-        cur.wait_stream(self.s_run)
+                self.ev_run[k].record(self.s_run[k])
+            with torch.cuda.stream(self.s_out[k]):
+                self.s_out[k].wait_event(self.ev_run[k])
+                outs[i].copy_(out, non_blocking=True)
+                self.ev_out[k].record(self.s_out[k])
+        for st in self.s_out + self.s_run:
+            cur.wait_stream(st)
         cur.synchronize()
