@@ -216,10 +216,10 @@ __device__ __forceinline__ void act_vec(float (&x)[NV], int act, float slope) {
     switch (act) {
         case CWFA_ACT_ELU:
 #pragma unroll
-            for (int j = 0; j < NV; ++j) {          // branch-free: max(x,0) + (exp(min(x,0)) - 1)
+            for (int j = 0; j < NV; ++j) {          // branch-free, 5 instructions: max(x, min(exp(x) - 1, 0))
                 float e;
-                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(x[j], 0.f) * 1.4426950408889634f));
-                x[j] = fmaxf(x[j], 0.f) + (e - 1.f);
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x[j] * 1.4426950408889634f));
+                x[j] = fmaxf(x[j], fminf(e - 1.f, 0.f));
             }
             break;
         case CWFA_ACT_PRELU:

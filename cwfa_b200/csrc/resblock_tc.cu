@@ -22,8 +22,11 @@ constexpr uint32_t kW3Bytes = 9 * kTapBytes;                  // 73728
 constexpr uint32_t kW1Bytes = kTapBytes;                      // 8192
 constexpr uint32_t kA2MbBytes = kChunks * 128 * 16;           // 16384 per M-block
 constexpr uint32_t kHeader = 2048;
+constexpr uint32_t kOnesBytes = 2 * 128 * 16;                // A tile of the bias MMA: [2 chunks][128 rows][8], e0 = e1 = 1
+constexpr uint32_t kBiasBytes = 2 * kC * 16;                 // B tile of the bias MMA: [2 chunks][64 n][8], e0 = hi, e1 = lo
 constexpr uint32_t kOffW3 = kHeader, kOffW1 = kOffW3 + kW3Bytes, kOffA1 = kOffW1 + kW1Bytes,
-                   kOffA2 = kOffA1 + 2 * kA1Bytes, kSmemTotal = kOffA2 + 2 * kA2MbBytes;
+                   kOffA2 = kOffA1 + 2 * kA1Bytes, kOffOnes = kOffA2 + 2 * kA2MbBytes, kOffB3 = kOffOnes + kOnesBytes,
+                   kOffB1 = kOffB3 + kBiasBytes, kSmemTotal = kOffB1 + kBiasBytes;
 constexpr int kThreads = 448;        // warp0 TMA, warp1 MMA, warps2-5 EPI1, warps6-13 EPI2 (one M-block per warp set)
 
 struct RbParams {
@@ -60,8 +63,6 @@ __global__ void __launch_bounds__(kThreads, 1) resblock_tc_kernel(const __grid_c
     auto acc2_empty = [&](int b) { return s0 + 8u * (11 + b); };
     const uint32_t a2_full = s0 + 8u * 13, a2_empty = s0 + 8u * 14;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 128);
-    float* s_b3 = reinterpret_cast<float*>(smem + 1024);
-    float* s_b1 = s_b3 + kC;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -78,10 +79,27 @@ __global__ void __launch_bounds__(kThreads, 1) resblock_tc_kernel(const __grid_c
         mbar_init(a2_empty, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (threadIdx.x >= 64 && threadIdx.x < 64 + 2 * kC) {
-        const int i = threadIdx.x - 64;
-        s_b3[i] = i < kC ? __ldg(p.b3 + i) : __ldg(p.b1 + i - kC);      // s_b1 follows s_b3
+    // Biases enter the accumulators through one extra K=16 MMA per GEMM: A = "ones" tile (columns k=0,1 are 1),
+    // B rows k=0 / k=1 = bf16 hi / lo parts of the fp32 bias (hi + lo reproduces it to ~2^-17 relative).
+    for (int i = threadIdx.x; i < (int)(kOnesBytes + 2 * kBiasBytes) / 16; i += kThreads) {
+        uint4 v = make_uint4(0, 0, 0, 0);
+        const int ones_units = kOnesBytes / 16;
+        if (i < 128) {
+            v.x = pack2<BF16>(1.f, 1.f);                                  // chunk 0 of the ones tile: e0 = e1 = 1
+        } else if (i >= ones_units) {
+            const int j = i - ones_units;                                 // bias tiles: [b3 chunk0 | b3 chunk1 | b1 chunk0 | b1 chunk1]
+            const int which = j / (2 * kC), r = j % (2 * kC);
+            if (r < kC) {
+                const float bv = __ldg((which ? p.b1 : p.b3) + r);
+                float hi;
+                if constexpr (BF16) hi = __bfloat162float(__float2bfloat16_rn(bv));
+                else hi = __half2float(__float2half_rn(bv));
+                v.x = pack2<BF16>(hi, bv - hi);
+            }
+        }
+        *reinterpret_cast<uint4*>(smem + kOffOnes + (size_t)i * 16) = v;
     }
+    fence_proxy_async();
     if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
     tc_fence_before();
     __syncthreads();
@@ -115,6 +133,8 @@ __global__ void __launch_bounds__(kThreads, 1) resblock_tc_kernel(const __grid_c
         constexpr uint32_t a2_lbo = 128 * 16, a2_sbo = 128;
         const uint32_t a1_hi = desc_hi(a1_sbo), w_hi = desc_hi(w_sbo), a2_hi = desc_hi(a2_sbo);
         const uint32_t w3_lo0 = desc_lo(s0 + kOffW3, w_lbo), w1_lo0 = desc_lo(s0 + kOffW1, w_lbo);
+        const uint32_t ones_lo = desc_lo(s0 + kOffOnes, 128 * 16);         // same geometry as an A2 M-block (LBO 2048, SBO 128)
+        const uint32_t b3_lo = desc_lo(s0 + kOffB3, w_lbo), b1_lo = desc_lo(s0 + kOffB1, w_lbo);
         const uint32_t leader = elect_one();
         mbar_wait(w_full, 0);
 
@@ -128,10 +148,11 @@ __global__ void __launch_bounds__(kThreads, 1) resblock_tc_kernel(const __grid_c
                 for (int mb = 0; mb < 2; ++mb) {
                     const uint32_t d = tmem + 256 + (bj * 2 + mb) * kC;
                     const uint32_t a_lo0 = desc_lo(s0 + kOffA2 + mb * kA2MbBytes, a2_lbo);
+                    tc_mma_f16_split(d, ones_lo, a2_hi, b1_lo, w_hi, idesc, 0u);          // acc = bias1
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk)
                         tc_mma_f16_split(d, a_lo0 + kk * ((2 * a2_lbo) >> 4), a2_hi, w1_lo0 + kk * ((2 * w_lbo) >> 4), w_hi,
-                                         idesc, kk ? 1u : 0u);
+                                         idesc, 1u);
                 }
                 tc_commit(a2_empty);
                 tc_commit(acc2_full(bj));
@@ -147,6 +168,9 @@ __global__ void __launch_bounds__(kThreads, 1) resblock_tc_kernel(const __grid_c
             if (leader) rb_stamp(p, i, 0);
             if (leader) {
                 const uint32_t a_base = s0 + kOffA1 + b * kA1Bytes;
+#pragma unroll
+                for (int mb = 0; mb < 2; ++mb)                                             // acc = bias3
+                    tc_mma_f16_split(tmem + (b * 2 + mb) * kC, ones_lo, a2_hi, b3_lo, w_hi, idesc, 0u);
 #pragma unroll 1
                 for (int tap = 0; tap < 9; ++tap) {
                     const int kh = tap / 3, kw = tap - kh * 3;
@@ -158,7 +182,7 @@ __global__ void __launch_bounds__(kThreads, 1) resblock_tc_kernel(const __grid_c
 #pragma unroll
                         for (int mb = 0; mb < 2; ++mb)
                             tc_mma_f16_split(tmem + (b * 2 + mb) * kC, a_lo0 + mb * 8 + kk * ((2 * a1_lbo) >> 4), a1_hi,
-                                             w_lo + kk * ((2 * w_lbo) >> 4), w_hi, idesc, (tap | kk) ? 1u : 0u);
+                                             w_lo + kk * ((2 * w_lbo) >> 4), w_hi, idesc, 1u);
                     }
                 }
                 tc_commit(a1_empty(b));
@@ -191,13 +215,11 @@ __global__ void __launch_bounds__(kThreads, 1) resblock_tc_kernel(const __grid_c
                 tmem_ld_wait();
 #pragma unroll
                 for (int ch = 0; ch < 8; ++ch) {
-                    const float4 ba = lds128(s0 + 1024 + ch * 32);
-                    const float4 bb = lds128(s0 + 1024 + ch * 32 + 16);
                     uint4 ov;
-                    ov.x = pack2<BF16>(elu_fast(__uint_as_float(r[ch * 8 + 0]) + ba.x), elu_fast(__uint_as_float(r[ch * 8 + 1]) + ba.y));
-                    ov.y = pack2<BF16>(elu_fast(__uint_as_float(r[ch * 8 + 2]) + ba.z), elu_fast(__uint_as_float(r[ch * 8 + 3]) + ba.w));
-                    ov.z = pack2<BF16>(elu_fast(__uint_as_float(r[ch * 8 + 4]) + bb.x), elu_fast(__uint_as_float(r[ch * 8 + 5]) + bb.y));
-                    ov.w = pack2<BF16>(elu_fast(__uint_as_float(r[ch * 8 + 6]) + bb.z), elu_fast(__uint_as_float(r[ch * 8 + 7]) + bb.w));
+                    ov.x = pack2<BF16>(elu5(__uint_as_float(r[ch * 8 + 0])), elu5(__uint_as_float(r[ch * 8 + 1])));
+                    ov.y = pack2<BF16>(elu5(__uint_as_float(r[ch * 8 + 2])), elu5(__uint_as_float(r[ch * 8 + 3])));
+                    ov.z = pack2<BF16>(elu5(__uint_as_float(r[ch * 8 + 4])), elu5(__uint_as_float(r[ch * 8 + 5])));
+                    ov.w = pack2<BF16>(elu5(__uint_as_float(r[ch * 8 + 6])), elu5(__uint_as_float(r[ch * 8 + 7])));
                     sts128(a2 + ch * (128 * 16), ov);
                 }
             }
@@ -243,15 +265,13 @@ __global__ void __launch_bounds__(kThreads, 1) resblock_tc_kernel(const __grid_c
                 tmem_ld_wait();
 #pragma unroll
                 for (int ch = 0; ch < 8; ++ch) {
-                    const float4 ba = lds128(s0 + 1024 + 256 + ch * 32);
-                    const float4 bb = lds128(s0 + 1024 + 256 + ch * 32 + 16);
                     const float2 x0 = unpack2<BF16>(rx[ch].x), x1 = unpack2<BF16>(rx[ch].y),
                                  x2 = unpack2<BF16>(rx[ch].z), x3 = unpack2<BF16>(rx[ch].w);
                     uint4 ov;
-                    ov.x = pack2<BF16>(elu_fast(__uint_as_float(r[ch * 8 + 0]) + ba.x + x0.x), elu_fast(__uint_as_float(r[ch * 8 + 1]) + ba.y + x0.y));
-                    ov.y = pack2<BF16>(elu_fast(__uint_as_float(r[ch * 8 + 2]) + ba.z + x1.x), elu_fast(__uint_as_float(r[ch * 8 + 3]) + ba.w + x1.y));
-                    ov.z = pack2<BF16>(elu_fast(__uint_as_float(r[ch * 8 + 4]) + bb.x + x2.x), elu_fast(__uint_as_float(r[ch * 8 + 5]) + bb.y + x2.y));
-                    ov.w = pack2<BF16>(elu_fast(__uint_as_float(r[ch * 8 + 6]) + bb.z + x3.x), elu_fast(__uint_as_float(r[ch * 8 + 7]) + bb.w + x3.y));
+                    ov.x = pack2<BF16>(elu5(__uint_as_float(r[ch * 8 + 0]) + x0.x), elu5(__uint_as_float(r[ch * 8 + 1]) + x0.y));
+                    ov.y = pack2<BF16>(elu5(__uint_as_float(r[ch * 8 + 2]) + x1.x), elu5(__uint_as_float(r[ch * 8 + 3]) + x1.y));
+                    ov.z = pack2<BF16>(elu5(__uint_as_float(r[ch * 8 + 4]) + x2.x), elu5(__uint_as_float(r[ch * 8 + 5]) + x2.y));
+                    ov.w = pack2<BF16>(elu5(__uint_as_float(r[ch * 8 + 6]) + x3.x), elu5(__uint_as_float(r[ch * 8 + 7]) + x3.y));
                     if (ok) *reinterpret_cast<uint4*>(yout + (size_t)ch * plane * 16) = ov;
                 }
             }

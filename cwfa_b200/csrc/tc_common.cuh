@@ -135,6 +135,12 @@ __device__ __forceinline__ float4 lds128(uint32_t saddr) {
 __device__ __forceinline__ void sts128(uint32_t saddr, const uint4& v) {
     asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+// ELU(u) = max(u, min(exp(u) - 1, 0)): 5 instructions, branch-free (exp(u)-1 >= u everywhere; exp overflow -> min(inf,0) = 0).
+__device__ __forceinline__ float elu5(float u) {
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(u * 1.4426950408889634f));
+    return fmaxf(u, fminf(e - 1.f, 0.f));
+}
 // Branch-free ELU: max(x,0) + (exp(min(x,0)) - 1).  (A ternary makes the compiler emit a divergent
 // branch per element around the MUFU; measured 47 cycles/element in the epilogue.)
 __device__ __forceinline__ float elu_fast(float x) {
