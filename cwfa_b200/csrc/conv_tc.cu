@@ -97,6 +97,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&r)[8]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
@@ -186,8 +193,7 @@ __device__ __forceinline__ void stamp(const TcParams& p, int slot) {
 }
 
 constexpr int kMaxBStages = 8;
-constexpr int kThreads = 320;        // warp0 TMA, warp1 MMA, warps 2..9 epilogue
-constexpr int kEpiThreads = 256;
+constexpr int kThreads = 320;        // warp0 TMA, warp1 MMA, warps 2..9 epilogue (8 epilogue warps; the WIDE variant has 16)
 constexpr int kHeaderBytes = 2048;   // barriers, tmem slot, bias stage
 
 template <bool BF16>
@@ -242,8 +248,12 @@ __device__ __forceinline__ void act_vec(float (&x)[NV], int act, float slope) {
     }
 }
 
-template <bool BF16, bool COUPLING>
-__global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
+// WIDE: 16 epilogue warps (576 threads) for tiles that fill all 512 TMEM columns (one CTA per SM, nothing to
+// overlap the epilogue with): halves the non-overlapped drain time of the N=256 U-Net convolutions.
+template <bool BF16, bool COUPLING, bool WIDE>
+__global__ void __launch_bounds__(WIDE ? 576 : kThreads, WIDE ? 1 : 2) conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
+    constexpr int kEpiThreads = WIDE ? 512 : 256;
+    constexpr int kEpiSplit = WIDE ? 4 : 2;          // epilogue warps per TMEM lane quadrant
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     // [0,2048): barriers + tmem slot + bias stage; then A ring, then B ring
@@ -359,7 +369,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
     } else {
         // ===================== epilogue (8 warps) =====================
         const int q = warp & 3;                      // TMEM lane quadrant this warp may access
-        const int half = (warp - 2) >> 2;            // two warps per quadrant split the column groups
+        const int half = (warp - 2) >> 2;            // kEpiSplit warps per quadrant split the column groups
         const int m = q * 32 + lane;
         const int orow = h0 + (m >> 3);
         const bool row_ok = orow < p.H;
@@ -369,7 +379,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
         int* s_perm = reinterpret_cast<int*>(smem + 640);            // channel permutation (<= 64 entries) for out_mode 3
         if (p.out_mode == 3 && p.cpl_perm && p.cpl_axis == 1)
             for (int i = threadIdx.x - 64; i < p.cpl_ch; i += kEpiThreads) s_perm[i] = __ldg(p.cpl_perm + i);
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
         constexpr int kMaxG = 6;                     // coupling: <= 6 groups of 8 channels per thread (ch <= 48, MB = 2)
         // coupling input x of channel group k, read through the preceding permutation's gather
         auto load_x = [&](int k, float (&dst)[8]) {
@@ -459,15 +469,26 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
         }
         const int gpm = p.BN >> 4;                   // 16-column groups per M-block
         const int ngroups = COUPLING ? 0 : p.MB * gpm;
-        for (int g = half; g < ngroups; g += 2) {
+        // software-pipelined TMEM reads: the load of group g+2 is in flight while group g is processed
+        auto acc_addr = [&](int g) {
+            const int mb = g / gpm;
+            return tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mb * p.BN + ((g - mb * gpm) << 4));
+        };
+        uint32_t r[16], rnext[16];
+        if (half < ngroups) {
+            __syncwarp();
+            tmem_ld16_nowait(acc_addr(half), r);
+            tmem_ld_wait();
+        }
+        for (int g = half; g < ngroups; g += kEpiSplit) {
             const int mb = g / gpm;
             const int c0 = (g - mb * gpm) << 4;
             const int ocol = w0 + mb * 8 + (m & 7);
             const bool ok = row_ok && ocol < p.W;
             const size_t pix = (size_t)orow * p.W + ocol;
-            uint32_t r[16];
+            const bool more = g + kEpiSplit < ngroups;
             __syncwarp();
-            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mb * p.BN + c0), r);
+            if (more) tmem_ld16_nowait(acc_addr(g + kEpiSplit), rnext);
             const int cg = nblk * p.BN + c0;             // first global (padded) output channel of this group
             float v[16];
 #pragma unroll
@@ -541,6 +562,11 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
                     ov.w = pack2<BF16>(v[hh * 8 + 6], v[hh * 8 + 7]);
                     *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.out) + o + hh * cstride) = ov;
                 }
+            }
+            if (more) {
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) r[j] = rnext[j];
             }
         }
     }
@@ -711,10 +737,12 @@ static int conv_tc_launch(const void* x_c8, const void* w_packed, const float* b
                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) { set_error("conv_tc: cuTensorMapEncodeTiled failed (%d)", (int)cr); return CWFA_ECUDA; }
 
-    auto kern = out_mode == 3 ? (is_bf16 ? conv_tc_kernel<true, true> : conv_tc_kernel<false, true>)
-                              : (is_bf16 ? conv_tc_kernel<true, false> : conv_tc_kernel<false, false>);
-    static bool attr_done[4] = {false, false, false, false};
-    const int ki = (out_mode == 3 ? 2 : 0) + (is_bf16 ? 1 : 0);
+    const bool wide = out_mode != 3 && MB * BN > 256;      // > 256 TMEM columns: one CTA per SM anyway
+    auto kern = out_mode == 3 ? (is_bf16 ? conv_tc_kernel<true, true, false> : conv_tc_kernel<false, true, false>)
+                : wide        ? (is_bf16 ? conv_tc_kernel<true, false, true> : conv_tc_kernel<false, false, true>)
+                              : (is_bf16 ? conv_tc_kernel<true, false, false> : conv_tc_kernel<false, false, false>);
+    static bool attr_done[6] = {false, false, false, false, false, false};
+    const int ki = (out_mode == 3 ? 2 : wide ? 4 : 0) + (is_bf16 ? 1 : 0);
     if (!attr_done[ki]) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         attr_done[ki] = true;
@@ -722,7 +750,7 @@ static int conv_tc_launch(const void* x_c8, const void* w_packed, const float* b
     const int64_t gx = (int64_t)p.tiles_x * p.tiles_y * N;
     if (gx > 0x7fffffff) { set_error("conv_tc: grid too large"); return CWFA_EINVAL; }
     dim3 grid((unsigned)gx, (out_mode == 2 ? 4 : 1) * Cout_p / BN);
-    kern<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmap, p);
+    kern<<<grid, wide ? 576 : kThreads, smem, (cudaStream_t)stream>>>(tmap, p);
     return check_launch("conv_tc");
 }
 
