@@ -585,3 +585,45 @@ extern "C" int cwfa_attention_gate_f32(float* x, const float* m, const float* v,
     attention_gate_kernel<<<dim3(blocks, B), 256, 0, (cudaStream_t)stream>>>(x, m, v, w1, b1, w2, b2, C, L);
     return check_launch("attention_gate");
 }
+
+// ------------------------------------------------------------------------------------------
+// Lenslet crop + normalisation (the step right before the path):
+// XLFMDataset.extract_views (XLFMDataset.py:212-242) followed by (x - mean) / std (CWFA.py:797), one gather pass.
+// For lenslet n with centre (cy,cx): lower = max(c - S/2, 0), upper = min(c + S/2, image size); the patch is written
+// bottom/right aligned into the S x S view (reference quirk), the rest of the view is zero (then normalised too).
+// ------------------------------------------------------------------------------------------
+template <typename TIn>
+__global__ void __launch_bounds__(256) extract_views_kernel(const TIn* __restrict__ img, const int32_t* __restrict__ coords,
+                                                            float* __restrict__ out, int B, int Hi, int Wi, int L, int SH, int SW,
+                                                            float mean, float stdv, int normalise) {
+    const int64_t total = (int64_t)B * L * SH * SW;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int j = (int)(idx % SW);
+        const int i = (int)((idx / SW) % SH);
+        const int n = (int)((idx / ((int64_t)SW * SH)) % L);
+        const int b = (int)(idx / ((int64_t)SW * SH * L));
+        const int cy = __ldg(coords + 2 * n), cx = __ldg(coords + 2 * n + 1);
+        const int ly = max(cy - SH / 2, 0), lx = max(cx - SW / 2, 0);
+        const int uy = min(cy + SH / 2, Hi), ux = min(cx + SW / 2, Wi);
+        const int ph = max(uy - ly, 0), pw = max(ux - lx, 0);
+        float v = 0.f;
+        const int ii = i - (SH - ph), jj = j - (SW - pw);
+        if (ii >= 0 && jj >= 0 && ph > 0 && pw > 0) v = (float)img[((int64_t)b * Hi + ly + ii) * Wi + lx + jj];
+        out[idx] = normalise ? (v - mean) / stdv : v;
+    }
+}
+extern "C" int cwfa_extract_views(const void* image, int image_is_half, const int32_t* coords, float* out, int B, int Hi,
+                                  int Wi, int L, int SH, int SW, float mean, float stdv, int normalise, void* stream) {
+    if (B <= 0 || Hi <= 0 || Wi <= 0 || L <= 0 || SH <= 0 || SW <= 0 || (normalise && stdv == 0.f)) {
+        set_error("extract_views: bad arguments");
+        return CWFA_EINVAL;
+    }
+    const int64_t total = (int64_t)B * L * SH * SW;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    if (image_is_half)
+        extract_views_kernel<__half><<<blocks, 256, 0, (cudaStream_t)stream>>>((const __half*)image, coords, out, B, Hi, Wi, L, SH, SW, mean, stdv, normalise);
+    else
+        extract_views_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>((const float*)image, coords, out, B, Hi, Wi, L, SH, SW, mean, stdv, normalise);
+    return check_launch("extract_views");
+}

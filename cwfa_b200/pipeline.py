@@ -116,6 +116,36 @@ class CWFAModel(nn.Module):
             x = lo
         return res
 
+    # ---- the reference's GT-pyramid pass (CWFA.py:134-196) ----------------------------------------
+    @torch.no_grad()
+    def evaluate_INN_forward(self, gt_volume: torch.Tensor, extra_cond_in=None, fix_empty_depths: bool = True):
+        """``evaluate_INN_forward`` of the reference: the forward pyramid with ZERO LF conditions (and zero or given
+        mean-volume conditions), used to build the low-resolution ground-truth cache.  Returns
+        ``(losses, gt_cache, prior_errors, log_jacobians)`` with the reference's batch-coupled formulas
+        (CWFA.py:183-192).  ``check_empty_depths`` (CWFA.py:84-96) adds N(0, 1e-3) noise to all-constant depth
+        columns; disable it for deterministic runs."""
+        if fix_empty_depths:
+            gt_volume = check_empty_depths(gt_volume)
+        losses, prior_errors, log_jacobians = [], [], []
+        gt_cache = [None] * self.cfg.INN_max_down_steps
+        gt_cache[0] = gt_volume
+        for n in range(self.n_levels):
+            inn = self.conv_inn[n]
+            B = gt_volume.shape[0]
+            cond_in = [torch.zeros((B,) + tuple(inn.dims_c[0]), device=gt_volume.device)]
+            if len(inn.dims_c) > 1:
+                cond_in.append(torch.zeros((B,) + tuple(inn.dims_c[1]), device=gt_volume.device) if extra_cond_in is None
+                               else extra_cond_in[n].clone())
+            Z, log_jac_det = inn(gt_volume, c=cond_in)
+            err = ops.sum_squares(Z[0]).sum()                       # torch.norm(Z)**2 over the whole batch
+            loss = (0.5 * err - log_jac_det) / Z[-1].numel()
+            losses.append(loss.mean())
+            prior_errors.append(0.5 * err / Z[-1].numel())
+            log_jacobians.append(log_jac_det.mean() / Z[-1].numel())
+            gt_volume = Z[1]
+            gt_cache[n + 1] = gt_volume
+        return losses, gt_cache, prior_errors, log_jacobians
+
     # ---- test / bench helper ---------------------------------------------------------------
     def export_for_oracle(self) -> dict:
         """CPU copies of all state_dicts plus the per-level node specs, in the structure
@@ -124,3 +154,20 @@ class CWFAModel(nn.Module):
         levels = [dict(inn=cpu(self.conv_inn[n].state_dict()), cond=cpu(self.cond_nets[n].state_dict()),
                        spec=networks.level_spec(self.conv_inn[n])) for n in range(self.n_levels)]
         return dict(levels=levels, lrnn=cpu(self.cond_nets[-1].state_dict()), config=asdict(self.cfg))
+
+
+def check_empty_depths(gt_volume: torch.Tensor) -> torch.Tensor:
+    """CWFA.py:84-96: pixels whose depth column is constant get N(0, 1e-3) noise on all depths (host-level data hygiene)."""
+    empty = gt_volume.std(dim=1, keepdim=True) == 0
+    if bool(empty.any()):
+        gt_volume = gt_volume + empty * torch.normal(0.0, 0.001, gt_volume.shape, device=gt_volume.device)
+    return gt_volume
+
+
+def sample_z_truncated(shape, device="cpu", temperature: float = 1.0) -> torch.Tensor:
+    """CWFA.py:47-64: zeros at temperature 0, otherwise a normal truncated to [-T, T] with std T.  (The reference's
+    non-zero branch raises NameError because ``_no_grad_trunc_normal_`` is never imported)"""
+    z = torch.zeros(tuple(shape), device=device)
+    if temperature != 0:
+        torch.nn.init.trunc_normal_(z, mean=0.0, std=1.0, a=-temperature, b=temperature)
+    return z

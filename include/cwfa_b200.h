@@ -125,6 +125,11 @@ int cwfa_layernorm_chw_f32(const float* x, const float* gamma, const float* beta
  * x += m * 2 * (g - 0.5).  v = mean volume (B,C,L), w1 (C,C,3), w2 (C,C,1), C <= 16. */
 int cwfa_attention_gate_f32(float* x, const float* m, const float* v, const float* w1, const float* b1,
                             const float* w2, const float* b2, int B, int C, int64_t L, void* stream);
+/* Lenslet crop + normalisation in one gather (XLFMDataset.extract_views XLFMDataset.py:212-242 followed by
+ * (x - mean) / std, CWFA.py:797): image (B,1,Hi,Wi) fp32 or fp16 -> out (B,L,SH,SW) fp32; coords int32 (L,2) = (row, col)
+ * lenslet centres on the device; patches are bottom/right aligned in the view exactly as the reference does. */
+int cwfa_extract_views(const void* image, int image_is_half, const int32_t* coords, float* out, int B, int Hi,
+                       int Wi, int L, int SH, int SW, float mean, float stdv, int normalise, void* stream);
 /* x += m * 2 * (g - 0.5)   (networks.py:554) */
 int cwfa_gate_add_f32(float* x, const float* m, const float* g, int64_t n, void* stream);
 

@@ -393,3 +393,39 @@ def forward_nll(model: dict, volume: Tensor, views: Tensor, mean_vols: Sequence[
         res.append(dict(z=z, lo=lo, logdet=jac, sumsq=sumsq, nll_per_sample=per, nll_ref=ref))
         x = lo
     return res
+
+
+# ----------------------------------------------------------------------------------------
+# Either side of the path: lenslet crop before it, GT pyramid helper
+# ----------------------------------------------------------------------------------------
+def extract_views(image: Tensor, lenslet_coords, subimage_shape) -> Tensor:
+    """XLFMDatasetFull.extract_views, XLFMDataset.py:212-242: crop an S0 x S1 window around every lenslet centre,
+    clipped to the image, written bottom/right aligned into the view."""
+    h0, h1 = subimage_shape[0] // 2, subimage_shape[1] // 2
+    out = torch.zeros((image.shape[0], len(lenslet_coords), subimage_shape[0], subimage_shape[1]), dtype=image.dtype)
+    for n, c in enumerate(lenslet_coords):
+        cy, cx = int(c[0]), int(c[1])
+        ly, lx = max(cy - h0, 0), max(cx - h1, 0)
+        patch = image[:, 0, ly:cy + h0, lx:cx + h1]
+        out[:, n, subimage_shape[0] - patch.shape[1]:, subimage_shape[1] - patch.shape[2]:] = patch
+    return out
+
+
+def evaluate_inn_forward(model: dict, gt_volume: Tensor, extra_cond_in=None):
+    """evaluate_INN_forward with zero conditions, CWFA.py:134-196 (without the check_empty_depths noise).
+    Returns (losses, gt_cache, prior_errors, log_jacobians)."""
+    losses, prior, ljs = [], [], []
+    cache = [gt_volume]
+    x = gt_volume
+    for n, lv in enumerate(model["levels"]):
+        ch = x.shape[1] // 2
+        zeros = torch.zeros((x.shape[0], ch) + tuple(x.shape[2:]), dtype=x.dtype)
+        mv = zeros if extra_cond_in is None else extra_cond_in[n]
+        z, lo, jac = level_forward(lv["inn"], lv["spec"], x, zeros, mv)
+        err = torch.norm(z) ** 2
+        losses.append(((0.5 * err - jac) / lo.numel()).mean())
+        prior.append(0.5 * err.mean() / lo.numel())
+        ljs.append(jac.mean() / lo.numel())
+        x = lo
+        cache.append(lo)
+    return losses, cache, prior, ljs

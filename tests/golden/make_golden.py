@@ -124,6 +124,16 @@ def tiny_case():
         xr, jr = inns[n]([z, lo], c=[c0, mean_vols[n].repeat(B, 1, 1, 1)], rev=True)
         fx[f"fwd/roundtrip_err{n}"] = (xr - x).abs().max()
         x = lo
+    # --- the reference's own GT-pyramid helper (zero conditions), CWFA.py:134-196 ---
+    import types
+    ag = types.SimpleNamespace(force_all_steps_NF=0, INN_max_down_steps=MAX)
+    gt = seeded_randn((B, D, S, S), 4)
+    losses, gt_cache, prior_errors, ljs = CWFA.evaluate_INN_forward(inns, conds + [enc], ag, None, gt.clone(), vB,
+                                                                    (0.0, 1.0, 0.0, 1.0, 0.0, 1.0))
+    fx["evalfwd/losses"] = torch.stack([l.detach() for l in losses])
+    fx["evalfwd/prior"] = torch.stack([l.detach() for l in prior_errors])
+    fx["evalfwd/logjac"] = torch.stack([l.detach() for l in ljs])
+    fx["evalfwd/gt_last"] = gt_cache[MAX - 1].clone()
     torch.save(fx, os.path.join(HERE, "tiny.pt"))
     print("tiny.pt", {k: (tuple(v.shape) if torch.is_tensor(v) else "...") for k, v in fx.items()})
 
@@ -184,6 +194,12 @@ def module_cases():
         jr = jr if torch.is_tensor(jr) else torch.zeros(2) + jr
         fx[f"block/{name}/fwd"], fx[f"block/{name}/fwd_jac"] = y.clone(), j.clone()
         fx[f"block/{name}/rev"], fx[f"block/{name}/rev_jac"] = xr.clone(), jr.clone()
+    # lenslet view extraction incl. windows clipped by every image border (XLFMDataset.py:212-242)
+    import XLFMDataset
+    img = seeded_randn((2, 1, 90, 100), 30)
+    coords = [[45, 50], [10, 12], [85, 95], [5, 90], [80, 8], [32, 32], [0, 0], [89, 99]]
+    fx["extract_views/coords"] = torch.tensor(coords)
+    fx["extract_views/out"] = XLFMDataset.XLFMDatasetFull.extract_views(img, coords, [64, 64]).clone()
     # numerical log-det cross-check on a tiny graph (graph_inn.py:369-407)
     torch.manual_seed(0); np.random.seed(0)
     ctor = lambda: networks.cond_network(29, 2, 1, 3, [], 32)
