@@ -123,7 +123,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint
 __device__ __forceinline__ float atan_fast(float x) {
     const float a = fabsf(x);
     const bool big = a > 1.f;
-    const float z = big ? __frcp_rn(a) : a;
+    const float z = big ? __fdividef(1.f, a) : a;
     const float s = z * z;
     float p = 0.0028662257f;
     p = fmaf(p, s, -0.0161657367f);
@@ -146,6 +146,11 @@ __device__ __forceinline__ float exp_fast(float x) {      // |x| <= clamp (~2): 
 __device__ __forceinline__ float lds_f32(uint32_t saddr) {
     float v;
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ float4 lds128f(uint32_t saddr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
     return v;
 }
 __device__ __forceinline__ int lds_s32(uint32_t saddr) {
@@ -250,8 +255,13 @@ __device__ __forceinline__ void act_vec(float (&x)[NV], int act, float slope) {
 
 // WIDE: 16 epilogue warps (576 threads) for tiles that fill all 512 TMEM columns (one CTA per SM, nothing to
 // overlap the epilogue with): halves the non-overlapped drain time of the N=256 U-Net convolutions.
-template <bool BF16, bool COUPLING, bool WIDE>
+// CPL: 0 = plain conv; 1..4 = fused coupling epilogue with (direction, shift source) fixed at compile time
+// (1 fwd / conv t, 2 inv / conv t, 3 fwd / external t, 4 inv / external t) so the element loop carries no flag tests.
+template <bool BF16, int CPL, bool WIDE>
 __global__ void __launch_bounds__(WIDE ? 576 : kThreads, WIDE ? 1 : 2) conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
+    constexpr bool COUPLING = CPL != 0;
+    constexpr bool CPL_INV = CPL == 2 || CPL == 4;
+    constexpr bool CPL_EXT = CPL == 3 || CPL == 4;
     constexpr int kEpiThreads = WIDE ? 512 : 256;
     constexpr int kEpiSplit = WIDE ? 4 : 2;          // epilogue warps per TMEM lane quadrant
     extern __shared__ uint8_t smem_raw[];
@@ -377,8 +387,13 @@ __global__ void __launch_bounds__(WIDE ? 576 : kThreads, WIDE ? 1 : 2) conv_tc_k
         const size_t plane = (size_t)p.H * p.W;
         for (int i = threadIdx.x - 64; i < p.BN; i += kEpiThreads) s_bias[i] = p.bias ? __ldg(p.bias + nblk * p.BN + i) : 0.f;
         int* s_perm = reinterpret_cast<int*>(smem + 640);            // channel permutation (<= 64 entries) for out_mode 3
-        if (p.out_mode == 3 && p.cpl_perm && p.cpl_axis == 1)
-            for (int i = threadIdx.x - 64; i < p.cpl_ch; i += kEpiThreads) s_perm[i] = __ldg(p.cpl_perm + i);
+        if constexpr (COUPLING) {
+            for (int i = threadIdx.x - 64; i < 64; i += kEpiThreads) {
+                s_perm[i] = (i < p.cpl_ch && p.cpl_perm && p.cpl_axis == 1) ? __ldg(p.cpl_perm + i) : i;   // identity unless channel perm
+                // shift bias re-based at channel 0 (16-byte aligned groups): smem + 1536
+                reinterpret_cast<float*>(smem + 1536)[i] = (!CPL_EXT && p.bias && i < p.cpl_ch) ? __ldg(p.bias + nblk * p.BN + p.cpl_ch + i) : 0.f;
+            }
+        }
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
         constexpr int kMaxG = 6;                     // coupling: <= 6 groups of 8 channels per thread (ch <= 48, MB = 2)
         // coupling input x of channel group k, read through the preceding permutation's gather
@@ -393,15 +408,12 @@ __global__ void __launch_bounds__(WIDE ? 576 : kThreads, WIDE ? 1 : 2) conv_tc_k
             int srow = orow, scol = ocol;
             if (ok && p.cpl_perm && p.cpl_axis == 2) srow = __ldg(p.cpl_perm + orow);
             if (ok && p.cpl_perm && p.cpl_axis == 3) scol = __ldg(p.cpl_perm + ocol);
-            const size_t spix = (size_t)srow * p.W + scol;
+            const float* xb = p.cpl_x + (size_t)n * ch * plane + (size_t)srow * p.W + scol;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int c = c0 + j;
                 dst[j] = 0.f;
-                if (ok && c < ch) {
-                    const int sc = (p.cpl_perm && p.cpl_axis == 1) ? lds_s32(bar0 + 640u + 4u * c) : c;
-                    dst[j] = __ldg(p.cpl_x + ((size_t)n * ch + sc) * plane + spix);
-                }
+                if (ok && c < ch) dst[j] = __ldg(xb + (size_t)lds_s32(bar0 + 640u + 4u * c) * plane);
             }
         };
         float xa[8], xb[8];
@@ -427,7 +439,7 @@ __global__ void __launch_bounds__(WIDE ? 576 : kThreads, WIDE ? 1 : 2) conv_tc_k
                 const size_t opix = (size_t)orow * p.W + ocol;
                 uint32_t rs[8], rt[8];
                 float tx[8];
-                if (p.cpl_t) {
+                if constexpr (CPL_EXT) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
                         tx[j] = (ok && c0 + j < ch) ? __ldg(p.cpl_t + ((size_t)n * ch + c0 + j) * plane + opix) : 0.f;
@@ -435,17 +447,28 @@ __global__ void __launch_bounds__(WIDE ? 576 : kThreads, WIDE ? 1 : 2) conv_tc_k
                 __syncwarp();
                 const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mb * p.BN + c0);
                 tmem_ld8_nowait(ta, rs);
-                if (!p.cpl_t) tmem_ld8_nowait(ta + ch, rt);
+                if constexpr (!CPL_EXT) tmem_ld8_nowait(ta + ch, rt);
                 tmem_ld_wait();
                 if (ok) {
+                    float bs[8], bt[8];
+                    {
+                        const float4 a0 = lds128f(bar0 + 1024u + 4u * c0), a1 = lds128f(bar0 + 1024u + 4u * c0 + 16u);
+                        bs[0] = a0.x; bs[1] = a0.y; bs[2] = a0.z; bs[3] = a0.w; bs[4] = a1.x; bs[5] = a1.y; bs[6] = a1.z; bs[7] = a1.w;
+                        const float4 t0 = lds128f(bar0 + 1536u + 4u * c0), t1 = lds128f(bar0 + 1536u + 4u * c0 + 16u);
+                        bt[0] = t0.x; bt[1] = t0.y; bt[2] = t0.z; bt[3] = t0.w; bt[4] = t1.x; bt[5] = t1.y; bt[6] = t1.z; bt[7] = t1.w;
+                    }
+                    float* yp = p.cpl_y + ((size_t)n * ch + c0) * plane + opix;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const int c = c0 + j;
-                        if (c < ch) {
-                            const float sv = p.cpl_kk * atan_fast(__uint_as_float(rs[j]) + lds_f32(bar0 + 1024u + 4u * c));
-                            const float tv = p.cpl_t ? p.cpl_tscale * tx[j] : __uint_as_float(rt[j]) + lds_f32(bar0 + 1024u + 4u * (ch + c));
-                            const float yv = p.cpl_inverse ? (xc[j] - tv) * exp_fast(-sv) : fmaf(exp_fast(sv), xc[j], tv);
-                            p.cpl_y[((size_t)n * ch + c) * plane + opix] = yv;
+                        if (c0 + j < ch) {
+                            const float sv = p.cpl_kk * atan_fast(__uint_as_float(rs[j]) + bs[j]);
+                            float tv;
+                            if constexpr (CPL_EXT) tv = p.cpl_tscale * tx[j];
+                            else tv = __uint_as_float(rt[j]) + bt[j];
+                            float yv;
+                            if constexpr (CPL_INV) yv = (xc[j] - tv) * exp_fast(-sv);
+                            else yv = fmaf(exp_fast(sv), xc[j], tv);
+                            yp[(size_t)j * plane] = yv;
                             sum_s += sv;
                             sum_q = fmaf(yv, yv, sum_q);
                         }
@@ -463,7 +486,7 @@ __global__ void __launch_bounds__(WIDE ? 576 : kThreads, WIDE ? 1 : 2) conv_tc_k
             if (threadIdx.x == 64) {
                 float a = 0.f, b = 0.f;
                 for (int k = 0; k < 8; ++k) { a += red[2 * k]; b += red[2 * k + 1]; }
-                p.cpl_ws[(size_t)blockIdx.x * 2] = p.cpl_inverse ? -a : a;
+                p.cpl_ws[(size_t)blockIdx.x * 2] = CPL_INV ? -a : a;
                 p.cpl_ws[(size_t)blockIdx.x * 2 + 1] = b;
             }
         }
@@ -738,11 +761,24 @@ static int conv_tc_launch(const void* x_c8, const void* w_packed, const float* b
     if (cr != CUDA_SUCCESS) { set_error("conv_tc: cuTensorMapEncodeTiled failed (%d)", (int)cr); return CWFA_ECUDA; }
 
     const bool wide = out_mode != 3 && MB * BN > 256;      // > 256 TMEM columns: one CTA per SM anyway
-    auto kern = out_mode == 3 ? (is_bf16 ? conv_tc_kernel<true, true, false> : conv_tc_kernel<false, true, false>)
-                : wide        ? (is_bf16 ? conv_tc_kernel<true, false, true> : conv_tc_kernel<false, false, true>)
-                              : (is_bf16 ? conv_tc_kernel<true, false, false> : conv_tc_kernel<false, false, false>);
-    static bool attr_done[6] = {false, false, false, false, false, false};
-    const int ki = (out_mode == 3 ? 2 : wide ? 4 : 0) + (is_bf16 ? 1 : 0);
+    typedef void (*KernT)(const CUtensorMap, const TcParams);
+    KernT kern;
+    int ki;
+    if (out_mode == 3) {
+        const int cplmode = (cpl->t ? 2 : 0) + (cpl->inverse ? 1 : 0);       // 0 fwd, 1 inv, 2 fwd+ext, 3 inv+ext
+        static const KernT table[2][4] = {
+            {conv_tc_kernel<false, 1, false>, conv_tc_kernel<false, 2, false>, conv_tc_kernel<false, 3, false>, conv_tc_kernel<false, 4, false>},
+            {conv_tc_kernel<true, 1, false>, conv_tc_kernel<true, 2, false>, conv_tc_kernel<true, 3, false>, conv_tc_kernel<true, 4, false>}};
+        kern = table[is_bf16 ? 1 : 0][cplmode];
+        ki = 4 + (is_bf16 ? 4 : 0) + cplmode;
+    } else if (wide) {
+        kern = is_bf16 ? conv_tc_kernel<true, 0, true> : conv_tc_kernel<false, 0, true>;
+        ki = 2 + (is_bf16 ? 1 : 0);
+    } else {
+        kern = is_bf16 ? conv_tc_kernel<true, 0, false> : conv_tc_kernel<false, 0, false>;
+        ki = is_bf16 ? 1 : 0;
+    }
+    static bool attr_done[12] = {false, false, false, false, false, false, false, false, false, false, false, false};
     if (!attr_done[ki]) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         attr_done[ki] = true;
