@@ -66,14 +66,6 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                           uint32_t accumulate) {
-    asm volatile(
-        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
 __device__ __forceinline__ void tc_mma_f16_split(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
                                                  uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -111,12 +103,8 @@ __device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&r)[8]
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// No-swizzle K-major shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
-// [0,14) start>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version = 1, layout_type [61,64) = 0.
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
-           ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
-}
+// No-swizzle K-major shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor), built as 32-bit halves
+// in the MMA issuer: lo = [0,14) start>>4 | [16,30) LBO>>4;  hi = [0,14) SBO>>4 | version 1 at bit 14; layout_type 0.
 
 // atan(x) with |error| <= ~1e-7: odd minimax polynomial on [0,1] (Abramowitz & Stegun 4.4.49) + reciprocal
 // range reduction.  ~15 instructions instead of libdevice atanf's ~40 (the coupling epilogue is ALU-bound).
