@@ -131,6 +131,7 @@ __global__ void __launch_bounds__(256) haar2d_kernel(const float* __restrict__ s
     const int64_t total = (int64_t)B * C * H2 * W2;
     const int64_t plane = (int64_t)H2 * W2;
     const int W = 2 * W2;
+#pragma unroll 4
     for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
          idx += (int64_t)gridDim.x * blockDim.x) {
         const int w2 = (int)(idx % W2);
@@ -197,6 +198,7 @@ __global__ void __launch_bounds__(256) permute_kernel(const float* __restrict__ 
                                                       const int32_t* __restrict__ perm, int B, int C, int H, int W) {
     const int Wv = W / VEC;
     const int64_t total = (int64_t)B * C * H * Wv;
+#pragma unroll 4
     for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
          idx += (int64_t)gridDim.x * blockDim.x) {
         const int w = (int)(idx % Wv) * VEC;
@@ -597,6 +599,7 @@ __global__ void __launch_bounds__(256) extract_views_kernel(const TIn* __restric
                                                             float* __restrict__ out, int B, int Hi, int Wi, int L, int SH, int SW,
                                                             float mean, float stdv, int normalise) {
     const int64_t total = (int64_t)B * L * SH * SW;
+#pragma unroll 4
     for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
         const int j = (int)(idx % SW);
         const int i = (int)((idx / SW) % SH);

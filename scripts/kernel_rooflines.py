@@ -1,0 +1,97 @@
+"""Per-kernel roofline table at the full-config shapes (CUDA events around a CUDA-graph replay of the calls, best of 5, tensors rotated through > L2).
+Writes profiles/r01_kernel_rooflines.md.  HBM peak / tensor peak from MEASURED_PEAKS.json."""
+import json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from cwfa_b200 import ops, tc
+from cwfa_b200.data import extract_views
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+HBM, TF = pk.get("hbm_gbs", 6650.0), pk.get("bf16_tflops", 1590.0)
+DEV = "cuda:0"
+P = 512 * 512
+rows = []
+
+
+def timeit(fn, nbuf):
+    """Replays the nbuf calls from a CUDA graph so host launch overhead does not pollute short kernels."""
+    for i in range(nbuf):
+        fn(i)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        keep = [fn(i) for i in range(nbuf)]
+    g.replay()
+    torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1) / nbuf)
+    del keep, g
+    return best * 1e-3
+
+
+def hbm(name, bytes_, fn, nbuf):
+    t = timeit(fn, nbuf)
+    rows.append((name, "HBM", f"{bytes_/1e6:.1f} MB", f"{t*1e6:.1f}", f"{bytes_/t/1e9:.0f} GB/s", f"{bytes_/t/1e9/HBM:.2f}"))
+
+
+def tensor(name, flop, fn, nbuf):
+    t = timeit(fn, nbuf)
+    rows.append((name, "tensor", f"{flop/1e9:.1f} GFLOP", f"{t*1e6:.1f}", f"{flop/t/1e12:.0f} TFLOP/s", f"{flop/t/1e12/TF:.2f}"))
+
+
+nb = 4
+# K1 Haar (level 0: C = 96)
+xs = [torch.randn(1, 96, 512, 512, device=DEV) for _ in range(nb)]
+los = [torch.randn(1, 48, 512, 512, device=DEV) for _ in range(nb)]
+hbm("haar1d_fwd C=96 (level 0)", 2 * 96 * P * 4, lambda i: ops.haar1d_split(xs[i]), nb)
+hbm("haar1d_inv C=96 (level 0, Split^-1 fused)", 2 * 96 * P * 4, lambda i: ops.haar1d_merge(los[i], los[(i + 1) % nb]), nb)
+perm_c = torch.randperm(48)
+perm_s = torch.randperm(512)
+hbm("permute channels ch=48", 8 * 48 * P, lambda i: ops.permute(los[i], perm_c, 1), nb)
+hbm("permute rows ch=48", 8 * 48 * P, lambda i: ops.permute(los[i], perm_s, 2), nb)
+hbm("permute columns ch=48", 8 * 48 * P, lambda i: ops.permute(los[i], perm_s, 3), nb)
+hbm("affine (standalone K3) ch=48", 16 * 48 * P, lambda i: ops.affine(los[i], xs[i][:, :48], xs[i][:, 48:], inverse=True), nb)
+hbm("haar2d_down C=96", 2 * 96 * P * 4, lambda i: ops.haar2d_down(xs[i], True, 0.5), nb)
+c8s = [tc.to_c8(torch.randn(1, 256, 512, 512, device=DEV)) for _ in range(nb)]
+g = torch.ones(256, device=DEV); b = torch.zeros(256, device=DEV)
+hbm("c8 BatchNorm stats+apply+maxpool 256ch", int(256 * P * 2 * (1 + 2 + 0.25)), lambda i: tc.batchnorm_c8(c8s[i], g, b, None, None, batch_stats=True, pool=True), nb)
+hbm("nchw_to_c8 96ch", 96 * P * 6, lambda i: tc.to_c8(xs[i]), nb)
+imgs = [torch.rand(1, 1, 2160, 2160, device=DEV) for _ in range(nb)]
+coords = torch.tensor([[300 + 370 * (i // 6), 280 + 330 * (i % 6)] for i in range(29)], dtype=torch.int32, device=DEV)
+hbm("extract_views 2160^2 -> 29x512x512 (+normalise)", 29 * P * 8, lambda i: extract_views(imgs[i], coords, [512, 512], 0.1, 1.3), nb)
+del xs, los, c8s, imgs
+# tensor kernels
+def conv_case(cin, cout, k, H, W, bn=None, name=None):
+    per = H * W * (tc.pad16(cin) + tc.pad16(cout)) * 2
+    n = max(2, min(32, (300 << 20) // per + 1))
+    xin = [tc.to_c8(torch.randn(1, cin, H, W, device=DEV)) for _ in range(n)]
+    pc = tc.PackedConv(torch.randn(cout, cin, k, k, device=DEV) * 0.05, torch.zeros(cout, device=DEV), bn=bn)
+    tensor(name or f"conv_tc {cin}->{cout} {k}x{k} @{H}x{W}", 2.0 * H * W * cin * cout * k * k, lambda i: tc.conv_tc(xin[i], pc, act=ops.ACT_PRELU, slope=torch.tensor([0.2], device=DEV)) if False else tc.conv_tc(xin[i], pc, act=ops.ACT_ELU), n)
+conv_case(256, 256, 3, 512, 512)
+conv_case(512, 512, 3, 256, 256)
+conv_case(1024, 1024, 3, 128, 128)
+conv_case(64, 64, 7, 512, 512)
+n = 8
+xin = [tc.to_c8(torch.randn(1, 64, 512, 512, device=DEV)) for _ in range(n)]
+p3 = tc.PackedConv(torch.randn(64, 64, 3, 3, device=DEV) * 0.04, torch.zeros(64, device=DEV), bn=64)
+p1 = tc.PackedConv(torch.randn(64, 64, 1, 1, device=DEV) * 0.1, torch.zeros(64, device=DEV), bn=64)
+tensor("resblock_tc (3x3+ELU+1x1+res+ELU, 64 ch) @512x512", 2.0 * P * 64 * 64 * 10, lambda i: tc.resblock_tc(xin[i], p3, p1), n)
+pco = tc.PackedConv(torch.randn(96, 64, 3, 3, device=DEV) * 0.04, torch.zeros(96, device=DEV), bn=96)
+xs48 = [torch.randn(1, 48, 512, 512, device=DEV) for _ in range(n)]
+ld = torch.zeros(1, device=DEV)
+pi = torch.randperm(48).to(torch.int32).to(DEV)
+tensor("conv_tc + fused coupling (64->96, ch=48, channel perm)", 2.0 * P * 64 * 96 * 9, lambda i: tc.conv_tc_coupling(xin[i], pco, xs48[i], ch=48, inverse=True, perm=pi, perm_axis=1, logdet=ld), n)
+
+md = ["# Per-kernel roofline (round 1, one B200; CUDA events around a CUDA-graph replay, best of 5, tensors rotated through > L2)", "",
+      f"Peaks: HBM {HBM} GB/s, bf16 {TF} TFLOP/s burst (MEASURED_PEAKS.json; kernels timed in isolation).", "",
+      "| kernel | bound | algorithmic work | us | achieved | frac of measured peak |", "|---|---|---|---|---|---|"]
+md += ["| " + " | ".join(r) + " |" for r in rows]
+open(os.path.join(ROOT, "profiles", "r01_kernel_rooflines.md"), "w").write("\n".join(md) + "\n")
+print("\n".join(md))
