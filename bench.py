@@ -269,7 +269,7 @@ def main():
         orig = _lib.call
 
         def timed_call(name, *a):
-            if name in ("cwfa_conv_tc", "cwfa_resblock_tc"):
+            if name in ("cwfa_conv_tc", "cwfa_resblock_tc", "cwfa_conv_tc_coupling", "cwfa_coupling_tc"):
                 s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 s.record()
                 orig(name, *a)
@@ -344,7 +344,7 @@ def main():
                 "ms_per_step": e2e_ms / args.steps, "api": f"StreamingReconstructor.run ({args.e2e_inflight} frames in flight)",
                 "sync_call_latency_ms": sync_latency_ms, "host_wall_ms_per_step": e2e_host_ms / args.steps},
         "gpu_launches": launches_per_step * args.steps,
-        "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel + resblock_tc_kernel (tcgen05 implicit-GEMM convolutions)", "achieved": achieved, "peak": peak_tf,
+        "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel + resblock_tc_kernel + coupling_tc_kernel (all tcgen05 implicit-GEMM convolution launches of a frame)", "achieved": achieved, "peak": peak_tf,
                      "unit": "TFLOP/s", "frac": (achieved / peak_tf) if achieved else None, "traffic": traffic,
                      "launches_per_step": n_conv, "avg_launch_us": (conv_ms * 1e3 / n_conv) if n_conv else None,
                      "algorithmic_flop_per_step": conv_flop, "conv_ms_per_step": conv_ms, "peak_source": peak_src,

@@ -49,6 +49,8 @@ _SIGS = {
     "cwfa_conv_tc_coupling_tiles": [i32, i32, i32],
     "cwfa_conv_tc_coupling": [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, f32, vp, i32, i32, f32, f32,
                               i32, vp, i32, vp],
+    "cwfa_coupling_tc_tiles": [i32, i32],
+    "cwfa_coupling_tc": [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, f32, vp, i32, i32, f32, f32, i32, vp, i32, vp],
     "cwfa_coupling_finalize": [vp, vp, vp, i32, i32, i32, vp],
     "cwfa_nchw_to_c8": [vp, vp, i32, i32, i32, i64, i32, vp],
     "cwfa_c8_to_nchw": [vp, vp, i32, i32, i32, i64, i32, vp],
@@ -106,7 +108,7 @@ class CwfaError(RuntimeError):
 
 # kernel launches issued per C-ABI call (for bench.py's "gpu_launches" claim)
 _LAUNCHES = {"cwfa_affine": 2, "cwfa_channel_stats_f32": 2, "cwfa_layernorm_chw_f32": 2, "cwfa_c8_channel_stats": 2,
-             "cwfa_tc_set_debug_buffer": 0, "cwfa_resblock_set_debug_buffer": 0, "cwfa_device_check": 0, "cwfa_conv_tc_coupling_tiles": 0}
+             "cwfa_tc_set_debug_buffer": 0, "cwfa_resblock_set_debug_buffer": 0, "cwfa_device_check": 0, "cwfa_conv_tc_coupling_tiles": 0, "cwfa_coupling_tc_tiles": 0}
 launch_count = 0
 launch_hist = {}
 

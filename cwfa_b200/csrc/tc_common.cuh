@@ -135,6 +135,40 @@ __device__ __forceinline__ float4 lds128(uint32_t saddr) {
 __device__ __forceinline__ void sts128(uint32_t saddr, const uint4& v) {
     asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+// atan(x) with |error| <= ~1e-7: odd minimax polynomial on [0,1] (Abramowitz & Stegun 4.4.49) + reciprocal
+// range reduction.  ~15 instructions instead of libdevice atanf's ~40 (the coupling epilogue is ALU-bound).
+__device__ __forceinline__ float atan_fast(float x) {
+    const float a = fabsf(x);
+    const bool big = a > 1.f;
+    const float z = big ? __fdividef(1.f, a) : a;
+    const float s = z * z;
+    float p = 0.0028662257f;
+    p = fmaf(p, s, -0.0161657367f);
+    p = fmaf(p, s, 0.0429096138f);
+    p = fmaf(p, s, -0.0752896400f);
+    p = fmaf(p, s, 0.1065626393f);
+    p = fmaf(p, s, -0.1420889944f);
+    p = fmaf(p, s, 0.1999355085f);
+    p = fmaf(p, s, -0.3333314528f);
+    p = fmaf(p * s, z, z);
+    const float r = big ? 1.57079632679489662f - p : p;
+    return copysignf(r, x);
+}
+__device__ __forceinline__ float exp_fast(float x) {      // |x| <= clamp (~2): no range handling needed
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 1.4426950408889634f));
+    return e;
+}
+__device__ __forceinline__ int lds_s32(uint32_t saddr) {
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+}
 // ELU(u) = max(u, min(exp(u) - 1, 0)): 5 instructions, branch-free (exp(u)-1 >= u everywhere; exp overflow -> min(inf,0) = 0).
 __device__ __forceinline__ float elu5(float u) {
     float e;

@@ -195,7 +195,8 @@ def resblock_tc(x: C8, p3: PackedConv, p1: PackedConv, in_chunk_off: int = 0) ->
 def conv_tc_coupling(b: C8, pc: PackedConv, x: Optional[torch.Tensor], *, ch: int, inverse: bool, clamp: float = 2.0,
                      k_atan: float = 0.636, t_ext: Optional[torch.Tensor] = None, t_scale: float = 1.0,
                      perm: Optional[torch.Tensor] = None, perm_axis: int = 0, logdet: torch.Tensor = None,
-                     sumsq: Optional[torch.Tensor] = None, accumulate: bool = True, mb: Optional[int] = None) -> torch.Tensor:
+                     sumsq: Optional[torch.Tensor] = None, accumulate: bool = True, mb: Optional[int] = None,
+                     persistent: Optional[bool] = None) -> torch.Tensor:
     """Last conv of a coupling sub-network with the affine coupling, the log-det partial sums and the preceding
     permutation (as a gather on ``x``) fused into its epilogue.  ``x`` None = zeros (z = 0, inverse only).
     ``logdet`` (B,) is accumulated in place (fixed-order reduction); ``sumsq`` (B,) receives sum(y^2)."""
@@ -212,6 +213,16 @@ def conv_tc_coupling(b: C8, pc: PackedConv, x: Optional[torch.Tensor], *, ch: in
     xx = None if x is None else _ck(x, "x")
     tt = None if t_ext is None else _ck(t_ext, "t_ext")
     lib = _lib.load()
+    if persistent is None:
+        persistent = pc.Cin_p == 64 and pc.KH == 3 and pc.KW == 3 and pc.Cout_p <= 96 and ch <= 48
+    if persistent:
+        tiles = lib.cwfa_coupling_tc_tiles(H, W)
+        ws = torch.empty(2 * N * tiles, device=dev, dtype=torch.float32)
+        _lib.call("cwfa_coupling_tc", b.data.data_ptr(), pc.packed.data_ptr(), _p(pc.bias), N, H, W, pc.Cout, pc.Cout_p, _p(xx),
+                  y.data_ptr(), _p(tt), float(t_scale), _p(perm), int(perm_axis), ch, float(clamp), float(k_atan), int(inverse),
+                  ws.data_ptr(), b.is_bf16, _stream())
+        _lib.call("cwfa_coupling_finalize", ws.data_ptr(), logdet.data_ptr(), _p(sumsq), N, tiles, int(accumulate), _stream())
+        return y
     tiles = lib.cwfa_conv_tc_coupling_tiles(H, W, mb)
     ws = torch.empty(2 * N * tiles, device=dev, dtype=torch.float32)
     _lib.call("cwfa_conv_tc_coupling", b.data.data_ptr(), pc.packed.data_ptr(), _p(pc.bias), N, H, W, pc.Cin_p, pc.Cout,

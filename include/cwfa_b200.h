@@ -184,6 +184,14 @@ int cwfa_conv_tc_coupling(const void* x_c8, const void* w_packed, const float* b
                           float clamp, float k_atan, int inverse, float* workspace, int is_bf16, void* stream);
 int cwfa_coupling_finalize(const float* workspace, float* logdet, float* sumsq, int N, int tiles,
                            int accumulate, void* stream);
+/* Persistent variant of cwfa_conv_tc_coupling for the CWFA sub-network shape (3x3 conv from 64 hidden channels to
+ * Cout_p <= 96 in one N block, ch <= 48): weights resident in shared memory, accumulators double buffered in TMEM,
+ * 16 epilogue warps.  workspace: 2 * N * cwfa_coupling_tc_tiles(H, W) floats (reduce with cwfa_coupling_finalize). */
+int cwfa_coupling_tc_tiles(int H, int W);
+int cwfa_coupling_tc(const void* b_c8, const void* w_packed, const float* bias, int N, int H, int W, int Cout,
+                     int Cout_p, const float* cx, float* cy, const float* ct, float t_scale, const int32_t* perm,
+                     int perm_axis, int ch, float clamp, float k_atan, int inverse, float* workspace, int is_bf16,
+                     void* stream);
 /* Layout converters NCHW fp32 <-> C8 half (channels padded with zeros up to Cp). */
 int cwfa_nchw_to_c8(const float* x, void* y, int N, int C, int Cp, int64_t P, int is_bf16, void* stream);
 int cwfa_c8_to_nchw(const void* x, float* y, int N, int C, int Cp, int64_t P, int is_bf16, void* stream);

@@ -26,6 +26,10 @@ def timed(name, *a):
         N, H, W, Cin_p, Cout, Cout_p, KH, KW, BN, MB, act, res_mode, out_mode = a[6:19]
         key = f"conv_tc {Cin_p:4d}->{Cout_p:4d} k{KH} {H}x{W} BN{BN} MB{MB} out{out_mode} res{res_mode}"
         fl = 2.0 * H * W * Cin_p * Cout_p * KH * KW * (4 if out_mode == 2 else 1)
+    elif name == "cwfa_coupling_tc":
+        N, H, W, Cout, Cout_p = a[3:8]
+        key = f"coupling_tc 64->{Cout_p} ch{a[14]} axis{a[13]} x{'1' if a[8] else '0'}"
+        fl = 2.0 * H * W * 64 * Cout_p * 9
     elif name == "cwfa_conv_tc_coupling":
         N, H, W, Cin_p, Cout, Cout_p, KH, KW, MB = a[3:12]
         key = f"conv_tc_coupling {Cin_p}->{Cout_p} k{KH} ch{a[18]} axis{a[17]} x{'1' if a[12] else '0'}"
