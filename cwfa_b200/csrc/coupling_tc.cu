@@ -7,6 +7,7 @@
 // SIXTEEN epilogue warps (4 per TMEM lane quadrant) share each tile: the coupling epilogue is a latency chain per
 // thread (gather -> TMEM -> atan/exp -> store), so halving the chain length per thread matters more than anything.
 // Warp roles (576 threads): warp0 TMA producer, warp1 MMA issuer, warps 2-17 epilogue.
+#include <stdlib.h>
 #include "tc_common.cuh"
 using namespace cwfa;
 using namespace cwfa::tcx;
@@ -18,13 +19,15 @@ constexpr uint32_t kA1Bytes = kChunks * kBH * kBW * 16;      // 41472
 constexpr int kMaxBN = 96;
 constexpr uint32_t kWMax = 9 * kChunks * kMaxBN * 16;         // 110592
 constexpr uint32_t kHeader = 2048;
-constexpr uint32_t kOffW = kHeader, kOffA = kOffW + kWMax, kSmemTotal = kOffA + 2 * kA1Bytes;
+constexpr uint32_t kOffW = kHeader;       // weights (9*8*BN*16 bytes), then the A ring (2..4 stages, sized by the launcher)
+constexpr int kMaxAStages = 4;   // barrier slots; the launcher uses at most 3 stages (measured: 2..4 are within noise)
 constexpr int kThreads = 576, kEpiThreads = 512;
 constexpr int kMaxG = 3;                                      // 8-channel groups per epilogue thread (ch <= 48, 2 M-blocks, 4-way split)
 
 struct CpParams {
     int N, H, W, tiles_x, tiles_y, num_tiles;
-    int BN, ch, axis;
+    int BN, ch, axis, a_stages;
+    uint32_t off_a;
     const uint8_t* w;            // packed [9][8][BN][8]
     const float* bias;           // BN floats or NULL
     const float* x;              // (N,ch,H,W) or NULL
@@ -41,19 +44,21 @@ __global__ void __launch_bounds__(kThreads, 1) coupling_tc_kernel(const __grid_c
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const uint32_t s0 = smem_u32(smem);
     const uint32_t w_full = s0;
-    auto a_full = [&](int b) { return s0 + 8u * (1 + b); };
-    auto a_empty = [&](int b) { return s0 + 8u * (3 + b); };
-    auto acc_full = [&](int b) { return s0 + 8u * (5 + b); };
-    auto acc_empty = [&](int b) { return s0 + 8u * (7 + b); };
+    auto a_full = [&](int b) { return s0 + 8u * (1 + b); };          // up to 4
+    auto a_empty = [&](int b) { return s0 + 8u * (5 + b); };         // up to 4
+    auto acc_full = [&](int b) { return s0 + 8u * (9 + b); };
+    auto acc_empty = [&](int b) { return s0 + 8u * (11 + b); };
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 128);
     // smem + 256: red[2][16][2] floats (256 B); + 512: s_perm[64] ints; + 1024: s-bias[96]; + 1536: t-bias[64]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ch = p.ch;
     if (threadIdx.x == 0) {
         mbar_init(w_full, 1);
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < kMaxAStages; ++b) {
             mbar_init(a_full(b), 1);
             mbar_init(a_empty(b), 1);
+        }
+        for (int b = 0; b < 2; ++b) {
             mbar_init(acc_full(b), 1);
             mbar_init(acc_empty(b), kEpiThreads);
         }
@@ -85,10 +90,10 @@ __global__ void __launch_bounds__(kThreads, 1) coupling_tc_kernel(const __grid_c
                 const int t = blockIdx.x + i * gridDim.x;
                 const int n = t / tiles_per_img, r = t % tiles_per_img;
                 const int h0 = (r / p.tiles_x) * kTH, w0 = (r % p.tiles_x) * kTW;
-                const int b = i & 1;
-                mbar_wait(a_empty(b), ((i >> 1) & 1) ^ 1);
-                mbar_expect_tx(a_full(b), kA1Bytes);
-                tma_load_4d(s0 + kOffA + b * kA1Bytes, &tmap, a_full(b), (w0 - 1) * 8, h0 - 1, 0, n);
+                const int sa = i % p.a_stages;
+                mbar_wait(a_empty(sa), ((i / p.a_stages) & 1) ^ 1);
+                mbar_expect_tx(a_full(sa), kA1Bytes);
+                tma_load_4d(s0 + p.off_a + sa * kA1Bytes, &tmap, a_full(sa), (w0 - 1) * 8, h0 - 1, 0, n);
             }
         }
     } else if (warp == 1) {
@@ -101,11 +106,12 @@ __global__ void __launch_bounds__(kThreads, 1) coupling_tc_kernel(const __grid_c
         mbar_wait(w_full, 0);
         for (int i = 0; i < my_tiles; ++i) {
             const int b = i & 1, ph = (i >> 1) & 1;
-            mbar_wait(a_full(b), ph);
+            const int sa = i % p.a_stages;
+            mbar_wait(a_full(sa), (i / p.a_stages) & 1);
             mbar_wait(acc_empty(b), ph ^ 1);
             tc_fence_after();
             if (leader) {
-                const uint32_t a_base = s0 + kOffA + b * kA1Bytes;
+                const uint32_t a_base = s0 + p.off_a + sa * kA1Bytes;
 #pragma unroll 1
                 for (int tap = 0; tap < 9; ++tap) {
                     const int kh = tap / 3, kw = tap - kh * 3;
@@ -119,7 +125,7 @@ __global__ void __launch_bounds__(kThreads, 1) coupling_tc_kernel(const __grid_c
                                              w_lo + kk * ((2 * w_lbo) >> 4), w_hi, idesc, (tap | kk) ? 1u : 0u);
                     }
                 }
-                tc_commit(a_empty(b));
+                tc_commit(a_empty(sa));
                 tc_commit(acc_full(b));
             }
             __syncwarp();
@@ -150,13 +156,18 @@ __global__ void __launch_bounds__(kThreads, 1) coupling_tc_kernel(const __grid_c
                 int srow = orow, scol = ocol;
                 if (ok && p.perm && p.axis == 2) srow = __ldg(p.perm + orow);
                 if (ok && p.perm && p.axis == 3) scol = __ldg(p.perm + ocol);
-                const float* xb = p.x ? p.x + (size_t)n * ch * plane + (size_t)srow * p.W + scol : nullptr;
-                const float* tb = EXT ? p.t_ext + (size_t)n * ch * plane + (size_t)orow * p.W + ocol : nullptr;
+                // 32-bit offsets inside one sample (ch * H * W < 2^31 is checked by the launcher), 64-bit base per sample
+                const float* xs = p.x ? p.x + (size_t)n * ch * plane : nullptr;
+                const float* ts = EXT ? p.t_ext + (size_t)n * ch * plane : nullptr;
+                const uint32_t plane32 = (uint32_t)plane;
+                const uint32_t spix = (uint32_t)srow * (uint32_t)p.W + (uint32_t)scol;
+                const uint32_t opix = (uint32_t)orow * (uint32_t)p.W + (uint32_t)ocol;
+                const bool okx = ok && xs != nullptr;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const int c = c0 + j;
-                    xv[k][j] = (ok && xb && c < ch) ? __ldg(xb + (size_t)lds_s32(s0 + 512u + 4u * c) * plane) : 0.f;
-                    if constexpr (EXT) tx[k][j] = (ok && c < ch) ? __ldg(tb + (size_t)c * plane) : 0.f;
+                    xv[k][j] = (okx && c < ch) ? __ldg(xs + ((uint32_t)lds_s32(s0 + 512u + 4u * c) * plane32 + spix)) : 0.f;
+                    if constexpr (EXT) tx[k][j] = (ok && c < ch) ? __ldg(ts + ((uint32_t)c * plane32 + opix)) : 0.f;
                 }
             }
             mbar_wait(acc_full(b), ph);
@@ -180,7 +191,8 @@ __global__ void __launch_bounds__(kThreads, 1) coupling_tc_kernel(const __grid_c
                         const float bs[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
                         const float4 t0 = lds128(s0 + 1536u + 4u * c0), t1 = lds128(s0 + 1536u + 4u * c0 + 16u);
                         const float bt[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
-                        float* yp = p.y + ((size_t)n * ch + c0) * plane + (size_t)orow * p.W + ocol;
+                        float* yp = p.y + (size_t)n * ch * plane + ((uint32_t)c0 * (uint32_t)plane + (uint32_t)orow * (uint32_t)p.W + (uint32_t)ocol);
+                        const uint32_t plane32 = (uint32_t)plane;
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             if (c0 + j < ch) {
@@ -191,7 +203,7 @@ __global__ void __launch_bounds__(kThreads, 1) coupling_tc_kernel(const __grid_c
                                 float yv;
                                 if constexpr (INV) yv = (xv[k][j] - tv) * exp_fast(-sv);
                                 else yv = fmaf(exp_fast(sv), xv[k][j], tv);
-                                yp[(size_t)j * plane] = yv;
+                                yp[(uint32_t)j * plane32] = yv;
                                 sum_s += sv;
                                 sum_q = fmaf(yv, yv, sum_q);
                             }
@@ -232,7 +244,7 @@ extern "C" int cwfa_coupling_tc(const void* b_c8, const void* w_packed, const fl
                                 int Cout_p, const float* cx, float* cy, const float* ct, float t_scale, const int32_t* perm,
                                 int perm_axis, int ch, float clamp, float k_atan, int inverse, float* workspace, int is_bf16,
                                 void* stream) {
-    if (N <= 0 || H <= 0 || W <= 0 || !cy || !workspace || ch <= 0 || ch > 48 || Cout_p > kMaxBN || (Cout_p % 16) ||
+    if (N <= 0 || H <= 0 || W <= 0 || (int64_t)ch * H * W >= (1ll << 31) || !cy || !workspace || ch <= 0 || ch > 48 || Cout_p > kMaxBN || (Cout_p % 16) ||
         (ct ? Cout < ch : Cout < 2 * ch) || (perm && (perm_axis < 1 || perm_axis > 3)) || (!cx && !inverse)) {
         set_error("coupling_tc: unsupported arguments (needs 64 -> Cout_p <= 96, ch <= 48)");
         return CWFA_EINVAL;
@@ -265,7 +277,13 @@ extern "C" int cwfa_coupling_tc(const void* b_c8, const void* w_packed, const fl
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         attr_done[ki] = true;
     }
+    const uint32_t wbytes = 9u * kChunks * Cout_p * 16u;
+    p.off_a = (kOffW + wbytes + 127u) & ~127u;
+    int stages = (int)((227u * 1024u - 1024u - p.off_a) / kA1Bytes);
+    p.a_stages = stages > 3 ? 3 : stages;          // 2 at Cout_p = 96, 3 at Cout_p <= 64
+    if (const char* e = getenv("CWFA_CPL_STAGES")) { int v = atoi(e); if (v >= 2 && v <= p.a_stages) p.a_stages = v; }
+    const size_t smem_bytes = 1024 + p.off_a + (size_t)p.a_stages * kA1Bytes;
     const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
-    kern<<<grid, kThreads, kSmemTotal + 1024, (cudaStream_t)stream>>>(tmap, p);
+    kern<<<grid, kThreads, smem_bytes, (cudaStream_t)stream>>>(tmap, p);
     return check_launch("coupling_tc");
 }
