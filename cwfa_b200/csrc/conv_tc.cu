@@ -27,6 +27,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
@@ -158,6 +161,8 @@ struct TcParams {
     int MB, BN;
     uint32_t a_bytes, a_stride, b_bytes;
     int a_stages, b_stages;
+    int total_items;           // (n-block, sample, tile) work items, walked persistently with stride gridDim.x
+    int acc_bufs;              // TMEM accumulator buffers (2 = the MMAs of item i+1 overlap the epilogue of item i)
     int act, res_mode, out_mode;   // out_mode 0: C8 half   1: NCHW fp32   2: C8 half, 2x2 transposed-conv scatter
     int is_bf16;
     const uint8_t* w_packed;
@@ -181,7 +186,7 @@ __device__ __forceinline__ void stamp(const TcParams& p, int slot) {
     if (p.dbg) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        p.dbg[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 + slot] = t;
+        p.dbg[(size_t)blockIdx.x * 8 + slot] = t;
     }
 }
 
@@ -261,7 +266,8 @@ __global__ void __launch_bounds__(WIDE ? 576 : kThreads, WIDE ? 1 : 2) conv_tc_k
     auto a_empty = [&](int s) { return bar0 + 8u * (2 + s); };          // 2
     auto b_full = [&](int s) { return bar0 + 8u * (4 + s); };           // 8
     auto b_empty = [&](int s) { return bar0 + 8u * (12 + s); };         // 8
-    const uint32_t acc_full = bar0 + 8u * 20;
+    auto acc_full = [&](int b) { return bar0 + 8u * (20 + b); };        // 2
+    auto acc_empty = [&](int b) { return bar0 + 8u * (22 + b); };       // 2
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 8 * 24);
     float* s_bias = reinterpret_cast<float*>(smem + 1024);           // up to 256 floats
     const uint32_t a_base = smem_u32(smem + kHeaderBytes);
@@ -269,13 +275,21 @@ __global__ void __launch_bounds__(WIDE ? 576 : kThreads, WIDE ? 1 : 2) conv_tc_k
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles = p.tiles_x * p.tiles_y;
-    const int n = blockIdx.x / tiles;
-    const int t = blockIdx.x % tiles;
-    const int h0 = (t / p.tiles_x) * 16;
-    const int w0 = (t % p.tiles_x) * 8 * p.MB;
-    const int nblk = blockIdx.y;
+    const int per_nblk = tiles * p.N;
+    const int total = p.total_items;
+    const int acc_cols = p.MB * p.BN;
     const int T = p.KH * p.KW;
-    const int tmem_cols_needed = p.MB * p.BN;
+    const int tmem_cols_needed = p.acc_bufs * acc_cols;
+    // work item -> (n-block, sample, tile origin); n-block is the slowest index so neighbouring CTAs share weights in L2
+    auto decode = [&](int item, int& nblk, int& n, int& h0, int& w0) {
+        nblk = item / per_nblk;
+        const int r = item - nblk * per_nblk;
+        n = r / tiles;
+        const int t = r - n * tiles;
+        const int ty = t / p.tiles_x;
+        h0 = ty * 16;
+        w0 = (t - ty * p.tiles_x) * 8 * p.MB;
+    };
     uint32_t tmem_cols = 32;
     while ((int)tmem_cols < tmem_cols_needed) tmem_cols <<= 1;
 
@@ -283,7 +297,7 @@ __global__ void __launch_bounds__(WIDE ? 576 : kThreads, WIDE ? 1 : 2) conv_tc_k
     if (threadIdx.x == 0) {
         for (int s = 0; s < 2; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
         for (int s = 0; s < kMaxBStages; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
-        mbar_init(acc_full, 1);
+        for (int b = 0; b < 2; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), kEpiThreads / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -302,18 +316,22 @@ __global__ void __launch_bounds__(WIDE ? 576 : kThreads, WIDE ? 1 : 2) conv_tc_k
         // ===================== TMA producer =====================
         if (lane == 0) {
             const int ph = p.KH / 2, pw = p.KW / 2;
-            for (int kb = 0; kb < p.num_kb; ++kb) {
-                const int sa = kb % p.a_stages;
-                mbar_wait(a_empty(sa), ((kb / p.a_stages) & 1) ^ 1);
-                mbar_expect_tx(a_full(sa), p.a_bytes);
-                tma_load_4d(a_base + sa * p.a_stride, &tmap, a_full(sa), (w0 - pw) * 8, h0 - ph, kb * p.KCc, n);
-                for (int tap = 0; tap < T; ++tap) {
-                    const int it = kb * T + tap;
-                    const int sb = it % p.b_stages;
-                    mbar_wait(b_empty(sb), ((it / p.b_stages) & 1) ^ 1);
-                    mbar_expect_tx(b_full(sb), p.b_bytes);
-                    const uint8_t* src = p.w_packed + ((size_t)(nblk * p.num_kb + kb) * T + tap) * p.b_bytes;
-                    bulk_load(b_base + sb * p.b_bytes, src, p.b_bytes, b_full(sb));
+            int ia = 0, ib = 0;                      // running ring positions: the rings run straight through item boundaries,
+            for (int item = blockIdx.x; item < total; item += gridDim.x) {   // so the next item's operands load during this epilogue
+                int nblk, n, h0, w0;
+                decode(item, nblk, n, h0, w0);
+                for (int kb = 0; kb < p.num_kb; ++kb, ++ia) {
+                    const int sa = ia % p.a_stages;
+                    mbar_wait(a_empty(sa), ((ia / p.a_stages) & 1) ^ 1);
+                    mbar_expect_tx(a_full(sa), p.a_bytes);
+                    tma_load_4d(a_base + sa * p.a_stride, &tmap, a_full(sa), (w0 - pw) * 8, h0 - ph, kb * p.KCc, n);
+                    for (int tap = 0; tap < T; ++tap, ++ib) {
+                        const int sb = ib % p.b_stages;
+                        mbar_wait(b_empty(sb), ((ib / p.b_stages) & 1) ^ 1);
+                        mbar_expect_tx(b_full(sb), p.b_bytes);
+                        const uint8_t* src = p.w_packed + ((size_t)(nblk * p.num_kb + kb) * T + tap) * p.b_bytes;
+                        bulk_load(b_base + sb * p.b_bytes, src, p.b_bytes, b_full(sb));
+                    }
                 }
             }
         }
@@ -330,23 +348,30 @@ __global__ void __launch_bounds__(WIDE ? 576 : kThreads, WIDE ? 1 : 2) conv_tc_k
         const uint32_t a_kstep = (2 * a_lbo) >> 4, b_kstep = (2 * b_lbo) >> 4;   // per K=16 step, in 16-byte units
         const int ksteps = p.KCc / 2;
         const uint32_t leader = elect_one();
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-            const int sa = kb % p.a_stages;
-            mbar_wait(a_full(sa), (kb / p.a_stages) & 1);
-            if (kb == 0 && leader) stamp(p, 2);
+        int ia = 0, ib = 0, li = 0;
+        for (int item = blockIdx.x; item < total; item += gridDim.x, ++li) {
+        const int buf = p.acc_bufs == 2 ? (li & 1) : 0;
+        const int use = p.acc_bufs == 2 ? (li >> 1) : li;
+        mbar_wait(acc_empty(buf), (use & 1) ^ 1);                // epilogue has drained this accumulator buffer
+        tc_fence_after();
+        const uint32_t d_base = tmem_base + (uint32_t)(buf * acc_cols);
+        for (int kb = 0; kb < p.num_kb; ++kb, ++ia) {
+            const int sa = ia % p.a_stages;
+            mbar_wait(a_full(sa), (ia / p.a_stages) & 1);
+            if (ia == 0 && leader) stamp(p, 2);
             const uint32_t a_s = a_base + sa * p.a_stride;
             int it = kb * T;
             for (int kh = 0; kh < p.KH; ++kh) {
-                for (int kw = 0; kw < p.KW; ++kw, ++it) {
-                    const int sb = it % p.b_stages;
-                    mbar_wait(b_full(sb), (it / p.b_stages) & 1);
-                    if (it == 0 && leader) stamp(p, 3);
+                for (int kw = 0; kw < p.KW; ++kw, ++it, ++ib) {
+                    const int sb = ib % p.b_stages;
+                    mbar_wait(b_full(sb), (ib / p.b_stages) & 1);
+                    if (ib == 0 && leader) stamp(p, 3);
                     tc_fence_after();
                     const uint32_t a_lo0 = (((a_s + (uint32_t)((kh * p.BW + kw) * 16)) & 0x3FFFFu) >> 4) | a_lbo_enc;
                     const uint32_t b_lo0 = (((b_base + sb * p.b_bytes) & 0x3FFFFu) >> 4) | b_lbo_enc;
                     if (leader) {
                         for (int mb = 0; mb < p.MB; ++mb) {
-                            const uint32_t d = tmem_base + mb * p.BN;
+                            const uint32_t d = d_base + mb * p.BN;
                             uint32_t al = a_lo0 + mb * 8, bl = b_lo0;
                             for (int kk = 0; kk < ksteps; ++kk, al += a_kstep, bl += b_kstep)
                                 tc_mma_f16_split(d, al, a_hi, bl, b_hi, idesc, (it | kk) ? 1u : 0u);
@@ -360,29 +385,41 @@ __global__ void __launch_bounds__(WIDE ? 576 : kThreads, WIDE ? 1 : 2) conv_tc_k
             __syncwarp();
         }
         if (leader) {
-            stamp(p, 4);
-            tc_commit(acc_full);
+            if (li == 0) stamp(p, 4);
+            tc_commit(acc_full(buf));
         }
         __syncwarp();
+        }
     } else {
         // ===================== epilogue (8 warps) =====================
         const int q = warp & 3;                      // TMEM lane quadrant this warp may access
         const int half = (warp - 2) >> 2;            // kEpiSplit warps per quadrant split the column groups
         const int m = q * 32 + lane;
-        const int orow = h0 + (m >> 3);
-        const bool row_ok = orow < p.H;
         const float slope = (p.act == CWFA_ACT_PRELU && p.slope) ? __ldg(p.slope) : 0.f;
         const size_t plane = (size_t)p.H * p.W;
-        for (int i = threadIdx.x - 64; i < p.BN; i += kEpiThreads) s_bias[i] = p.bias ? __ldg(p.bias + nblk * p.BN + i) : 0.f;
         int* s_perm = reinterpret_cast<int*>(smem + 640);            // channel permutation (<= 64 entries) for out_mode 3
         if constexpr (COUPLING) {
             for (int i = threadIdx.x - 64; i < 64; i += kEpiThreads) {
                 s_perm[i] = (i < p.cpl_ch && p.cpl_perm && p.cpl_axis == 1) ? __ldg(p.cpl_perm + i) : i;   // identity unless channel perm
-                // shift bias re-based at channel 0 (16-byte aligned groups): smem + 1536
-                reinterpret_cast<float*>(smem + 1536)[i] = (!CPL_EXT && p.bias && i < p.cpl_ch) ? __ldg(p.bias + nblk * p.BN + p.cpl_ch + i) : 0.f;
+                // shift bias re-based at channel 0 (16-byte aligned groups): smem + 1536  (BN == Cout_p: one n-block)
+                reinterpret_cast<float*>(smem + 1536)[i] = (!CPL_EXT && p.bias && i < p.cpl_ch) ? __ldg(p.bias + p.cpl_ch + i) : 0.f;
             }
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+        int prev_nblk = -1, li = 0;
+        for (int item = blockIdx.x; item < total; item += gridDim.x, ++li) {
+        int nblk, n, h0, w0;
+        decode(item, nblk, n, h0, w0);
+        const int buf = p.acc_bufs == 2 ? (li & 1) : 0;
+        const int use = p.acc_bufs == 2 ? (li >> 1) : li;
+        const uint32_t acc_base = tmem_base + (uint32_t)(buf * acc_cols);
+        const int orow = h0 + (m >> 3);
+        const bool row_ok = orow < p.H;
+        if (nblk != prev_nblk) {                     // bias stage of this n-block (uniform over the epilogue warps, rare)
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+            for (int i = threadIdx.x - 64; i < p.BN; i += kEpiThreads) s_bias[i] = p.bias ? __ldg(p.bias + nblk * p.BN + i) : 0.f;
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+            prev_nblk = nblk;
+        }
         constexpr int kMaxG = 6;                     // coupling: <= 6 groups of 8 channels per thread (ch <= 48, MB = 2)
         // coupling input x of channel group k, read through the preceding permutation's gather
         auto load_x = [&](int k, float (&dst)[8]) {
@@ -407,9 +444,9 @@ __global__ void __launch_bounds__(WIDE ? 576 : kThreads, WIDE ? 1 : 2) conv_tc_k
         float xa[8], xb[8];
         if constexpr (COUPLING) load_x(0, xa);       // first group: latency hides behind the MMAs
         (void)kMaxG;
-        mbar_wait(acc_full, 0);
+        mbar_wait(acc_full(buf), use & 1);
         tc_fence_after();
-        if (threadIdx.x == 64) stamp(p, 5);
+        if (threadIdx.x == 64 && li == 0) stamp(p, 5);
         if constexpr (COUPLING) {
             // ---------- fused affine coupling + log-det (K3 folded into the last conv of the sub-network) ----------
             const int ch = p.cpl_ch;
@@ -433,7 +470,7 @@ __global__ void __launch_bounds__(WIDE ? 576 : kThreads, WIDE ? 1 : 2) conv_tc_k
                         tx[j] = (ok && c0 + j < ch) ? __ldg(p.cpl_t + ((size_t)n * ch + c0 + j) * plane + opix) : 0.f;
                 }
                 __syncwarp();
-                const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mb * p.BN + c0);
+                const uint32_t ta = acc_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mb * p.BN + c0);
                 tmem_ld8_nowait(ta, rs);
                 if constexpr (!CPL_EXT) tmem_ld8_nowait(ta + ch, rt);
                 tmem_ld_wait();
@@ -474,16 +511,17 @@ __global__ void __launch_bounds__(WIDE ? 576 : kThreads, WIDE ? 1 : 2) conv_tc_k
             if (threadIdx.x == 64) {
                 float a = 0.f, b = 0.f;
                 for (int k = 0; k < 8; ++k) { a += red[2 * k]; b += red[2 * k + 1]; }
-                p.cpl_ws[(size_t)blockIdx.x * 2] = CPL_INV ? -a : a;
-                p.cpl_ws[(size_t)blockIdx.x * 2 + 1] = b;
+                p.cpl_ws[(size_t)item * 2] = CPL_INV ? -a : a;
+                p.cpl_ws[(size_t)item * 2 + 1] = b;
             }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
         }
         const int gpm = p.BN >> 4;                   // 16-column groups per M-block
         const int ngroups = COUPLING ? 0 : p.MB * gpm;
         // software-pipelined TMEM reads: the load of group g+2 is in flight while group g is processed
         auto acc_addr = [&](int g) {
             const int mb = g / gpm;
-            return tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mb * p.BN + ((g - mb * gpm) << 4));
+            return acc_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mb * p.BN + ((g - mb * gpm) << 4));
         };
         uint32_t r[16], rnext[16];
         if (half < ngroups) {
@@ -579,6 +617,11 @@ __global__ void __launch_bounds__(WIDE ? 576 : kThreads, WIDE ? 1 : 2) conv_tc_k
 #pragma unroll
                 for (int j = 0; j < 16; ++j) r[j] = rnext[j];
             }
+        }
+        // all tcgen05.ld of this item have completed: hand the accumulator buffer back to the MMA issuer
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty(buf));
         }
     }
     if (threadIdx.x == 64) stamp(p, 6);
@@ -771,10 +814,16 @@ static int conv_tc_launch(const void* x_c8, const void* w_packed, const float* b
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         attr_done[ki] = true;
     }
-    const int64_t gx = (int64_t)p.tiles_x * p.tiles_y * N;
-    if (gx > 0x7fffffff) { set_error("conv_tc: grid too large"); return CWFA_EINVAL; }
-    dim3 grid((unsigned)gx, (out_mode == 2 ? 4 : 1) * Cout_p / BN);
-    kern<<<grid, wide ? 576 : kThreads, smem, (cudaStream_t)stream>>>(tmap, p);
+    const int64_t items = (int64_t)p.tiles_x * p.tiles_y * N * ((out_mode == 2 ? 4 : 1) * Cout_p / BN);
+    if (items > 0x7fffffff) { set_error("conv_tc: too many tiles"); return CWFA_EINVAL; }
+    p.total_items = (int)items;
+    // Persistent grid: each CTA walks items blockIdx.x, +grid, ... so TMEM allocation, barrier set-up and the
+    // first-operand TMA latency are paid once per CTA, and (MB*BN <= 128) two accumulator buffers overlap the
+    // MMAs of the next item with this item's epilogue.  The coupling variants keep one item per CTA.
+    p.acc_bufs = (out_mode != 3 && MB * BN <= 128) ? 2 : 1;
+    const int occ = (wide || smem > 113 * 1024) ? 1 : 2;
+    int64_t gx = out_mode == 3 ? items : (items < (int64_t)kNumSMs * occ ? items : (int64_t)kNumSMs * occ);
+    kern<<<(unsigned)gx, wide ? 576 : kThreads, smem, (cudaStream_t)stream>>>(tmap, p);
     return check_launch("conv_tc");
 }
 

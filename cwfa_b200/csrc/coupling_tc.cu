@@ -7,7 +7,6 @@
 // SIXTEEN epilogue warps (4 per TMEM lane quadrant) share each tile: the coupling epilogue is a latency chain per
 // thread (gather -> TMEM -> atan/exp -> store), so halving the chain length per thread matters more than anything.
 // Warp roles (576 threads): warp0 TMA producer, warp1 MMA issuer, warps 2-17 epilogue.
-#include <stdlib.h>
 #include "tc_common.cuh"
 using namespace cwfa;
 using namespace cwfa::tcx;
@@ -281,7 +280,6 @@ extern "C" int cwfa_coupling_tc(const void* b_c8, const void* w_packed, const fl
     p.off_a = (kOffW + wbytes + 127u) & ~127u;
     int stages = (int)((227u * 1024u - 1024u - p.off_a) / kA1Bytes);
     p.a_stages = stages > 3 ? 3 : stages;          // 2 at Cout_p = 96, 3 at Cout_p <= 64
-    if (const char* e = getenv("CWFA_CPL_STAGES")) { int v = atoi(e); if (v >= 2 && v <= p.a_stages) p.a_stages = v; }
     const size_t smem_bytes = 1024 + p.off_a + (size_t)p.a_stages * kA1Bytes;
     const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
     kern<<<grid, kThreads, smem_bytes, (cudaStream_t)stream>>>(tmap, p);
