@@ -41,16 +41,36 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
         : "memory");
     return ok;
 }
-// Bounded wait: a protocol bug must never hang the GPU -- trap instead (the host sees an error).
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+// Bounded wait: a protocol bug must never hang the GPU -- trap instead (the host sees an error).  try_wait carries a
+// suspend-time hint so a waiting warp sleeps in hardware instead of burning issue slots the epilogue warps need;
+// the 4 s bound is wall-clock (globaltimer), checked every 4096 polls.
+__device__ __forceinline__ uint32_t mbar_try_wait_hint(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+        "selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(2000u)
+        : "memory");
+    return ok;
+}
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
+    unsigned long long t0, t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     uint32_t spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 26)) {
-            printf("cwfa conv_tc: mbarrier timeout (block %d,%d thread %d bar %u parity %u)\n", blockIdx.x, blockIdx.y,
-                   threadIdx.x, bar, parity);
-            __trap();
+    while (!mbar_try_wait_hint(bar, parity)) {
+        if ((++spins & 4095u) == 0) {
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (t - t0 > 4000000000ull) {
+                printf("cwfa conv_tc: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+                __trap();
+            }
         }
     }
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity);
 }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tmap, uint32_t bar, int c0, int c1, int c2,
                                             int c3) {
@@ -250,7 +270,9 @@ __device__ __forceinline__ void act_vec(float (&x)[NV], int act, float slope) {
 // overlap the epilogue with): halves the non-overlapped drain time of the N=256 U-Net convolutions.
 // CPL: 0 = plain conv; 1..4 = fused coupling epilogue with (direction, shift source) fixed at compile time
 // (1 fwd / conv t, 2 inv / conv t, 3 fwd / external t, 4 inv / external t) so the element loop carries no flag tests.
-template <bool BF16, int CPL, bool WIDE>
+// FAST: 0 = generic epilogue (any activation / residual / output mode); 1, 2 = lean epilogue for the bandwidth-heavy
+// common case "C8 output, no residual" with activation none (1) or PReLU (2): ~3x fewer instructions per value.
+template <bool BF16, int CPL, bool WIDE, int FAST>
 __global__ void __launch_bounds__(WIDE ? 576 : kThreads, WIDE ? 1 : 2) conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
     constexpr bool COUPLING = CPL != 0;
     constexpr bool CPL_INV = CPL == 2 || CPL == 4;
@@ -280,15 +302,32 @@ __global__ void __launch_bounds__(WIDE ? 576 : kThreads, WIDE ? 1 : 2) conv_tc_k
     const int acc_cols = p.MB * p.BN;
     const int T = p.KH * p.KW;
     const int tmem_cols_needed = p.acc_bufs * acc_cols;
-    // work item -> (n-block, sample, tile origin); n-block is the slowest index so neighbouring CTAs share weights in L2
-    auto decode = [&](int item, int& nblk, int& n, int& h0, int& w0) {
-        nblk = item / per_nblk;
-        const int r = item - nblk * per_nblk;
-        n = r / tiles;
-        const int t = r - n * tiles;
-        const int ty = t / p.tiles_x;
-        h0 = ty * 16;
-        w0 = (t - ty * p.tiles_x) * 8 * p.MB;
+    // work item -> (n-block, sample, tile row, tile column) as a mixed-radix counter: n-block is the slowest digit so
+    // neighbouring CTAs share weights in L2.  The divisions happen once per thread; every further item adds the
+    // digits of gridDim.x with carries.
+    struct ItemPos { int nblk, n, ty, tx; };
+    auto split_digits = [&](int v) {
+        ItemPos d;
+        d.nblk = v / per_nblk;
+        const int r = v - d.nblk * per_nblk;
+        d.n = r / tiles;
+        const int t = r - d.n * tiles;
+        d.ty = t / p.tiles_x;
+        d.tx = t - d.ty * p.tiles_x;
+        return d;
+    };
+    const ItemPos step = split_digits((int)gridDim.x);
+    auto advance = [&](ItemPos& c) {
+        c.tx += step.tx;
+        int carry = c.tx >= p.tiles_x;
+        c.tx -= carry ? p.tiles_x : 0;
+        c.ty += step.ty + carry;
+        carry = c.ty >= p.tiles_y;
+        c.ty -= carry ? p.tiles_y : 0;
+        c.n += step.n + carry;
+        carry = c.n >= p.N;
+        c.n -= carry ? p.N : 0;
+        c.nblk += step.nblk + carry;
     };
     uint32_t tmem_cols = 32;
     while ((int)tmem_cols < tmem_cols_needed) tmem_cols <<= 1;
@@ -317,9 +356,9 @@ __global__ void __launch_bounds__(WIDE ? 576 : kThreads, WIDE ? 1 : 2) conv_tc_k
         if (lane == 0) {
             const int ph = p.KH / 2, pw = p.KW / 2;
             int ia = 0, ib = 0;                      // running ring positions: the rings run straight through item boundaries,
-            for (int item = blockIdx.x; item < total; item += gridDim.x) {   // so the next item's operands load during this epilogue
-                int nblk, n, h0, w0;
-                decode(item, nblk, n, h0, w0);
+            ItemPos pos = split_digits((int)blockIdx.x);
+            for (int item = blockIdx.x; item < total; item += gridDim.x, advance(pos)) {   // so the next item's operands load during this epilogue
+                const int nblk = pos.nblk, n = pos.n, h0 = pos.ty * 16, w0 = pos.tx * 8 * p.MB;
                 for (int kb = 0; kb < p.num_kb; ++kb, ++ia) {
                     const int sa = ia % p.a_stages;
                     mbar_wait(a_empty(sa), ((ia / p.a_stages) & 1) ^ 1);
@@ -406,9 +445,9 @@ __global__ void __launch_bounds__(WIDE ? 576 : kThreads, WIDE ? 1 : 2) conv_tc_k
             }
         }
         int prev_nblk = -1, li = 0;
-        for (int item = blockIdx.x; item < total; item += gridDim.x, ++li) {
-        int nblk, n, h0, w0;
-        decode(item, nblk, n, h0, w0);
+        ItemPos pos = split_digits((int)blockIdx.x);
+        for (int item = blockIdx.x; item < total; item += gridDim.x, ++li, advance(pos)) {
+        const int nblk = pos.nblk, n = pos.n, h0 = pos.ty * 16, w0 = pos.tx * 8 * p.MB;
         const int buf = p.acc_bufs == 2 ? (li & 1) : 0;
         const int use = p.acc_bufs == 2 ? (li >> 1) : li;
         const uint32_t acc_base = tmem_base + (uint32_t)(buf * acc_cols);
@@ -516,77 +555,160 @@ __global__ void __launch_bounds__(WIDE ? 576 : kThreads, WIDE ? 1 : 2) conv_tc_k
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");
         }
-        const int gpm = p.BN >> 4;                   // 16-column groups per M-block
-        const int ngroups = COUPLING ? 0 : p.MB * gpm;
-        // software-pipelined TMEM reads: the load of group g+2 is in flight while group g is processed
-        auto acc_addr = [&](int g) {
-            const int mb = g / gpm;
-            return acc_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mb * p.BN + ((g - mb * gpm) << 4));
-        };
-        uint32_t r[16], rnext[16];
-        if (half < ngroups) {
+        if constexpr (FAST != 0) {
+        // ---------- lean epilogue (C8 out, no residual, activation fixed at compile time): everything per item is hoisted,
+        // the group loop is LDS bias + FADD (+ PReLU) + pack + two 16-byte stores + one pointer increment ----------
+        const int gpm = p.BN >> 4;
+        const uint32_t lane_addr = acc_base + ((uint32_t)(q * 32) << 16);
+        const uint32_t cstride = (uint32_t)plane * 16u;
+        const uint32_t step_bytes = (uint32_t)(2 * kEpiSplit) * cstride;             // two chunks per 16-column group
+        uint8_t* const row_base = reinterpret_cast<uint8_t*>(p.out) +
+                                  (((size_t)n * (p.Cout_p >> 3) + ((nblk * p.BN) >> 3)) * plane + (size_t)orow * p.W) * 16;
+        int mb = 0, cgi = half;
+        while (cgi >= gpm) { cgi -= gpm; ++mb; }
+        const float pr_a = 0.5f * (1.f + slope), pr_b = 0.5f * (1.f - slope);
+        uint32_t ra[16], rb[16];                     // ping-pong TMEM read buffers (no register copies in the loop)
+        if (mb < p.MB) {
             __syncwarp();
-            tmem_ld16_nowait(acc_addr(half), r);
+            tmem_ld16_nowait(lane_addr + (uint32_t)(mb * p.BN + (cgi << 4)), ra);
             tmem_ld_wait();
         }
-        for (int g = half; g < ngroups; g += kEpiSplit) {
-            const int mb = g / gpm;
-            const int c0 = (g - mb * gpm) << 4;
-            const int ocol = w0 + mb * 8 + (m & 7);
-            const bool ok = row_ok && ocol < p.W;
-            const size_t pix = (size_t)orow * p.W + ocol;
-            const bool more = g + kEpiSplit < ngroups;
+        int ocol = w0 + mb * 8 + (m & 7);
+        bool ok = row_ok && ocol < p.W;
+        uint8_t* ptr = row_base + (size_t)ocol * 16 + (size_t)(2 * cgi) * cstride;
+        uint32_t bias_s = bar0 + 1024u + (uint32_t)cgi * 64u;
+        // one 16-column group: start the next group's TMEM read into `nxt`, finish `cur`; returns false after the last group
+        auto group = [&](uint32_t (&cur)[16], uint32_t (&nxt)[16]) -> bool {
+            int nmb = mb, ncgi = cgi + kEpiSplit;
+            while (ncgi >= gpm) { ncgi -= gpm; ++nmb; }
+            const bool more = nmb < p.MB;
             __syncwarp();
-            if (more) tmem_ld16_nowait(acc_addr(g + kEpiSplit), rnext);
-            const int cg = nblk * p.BN + c0;             // first global (padded) output channel of this group
+            if (more) tmem_ld16_nowait(lane_addr + (uint32_t)(nmb * p.BN + (ncgi << 4)), nxt);
             float v[16];
 #pragma unroll
             for (int j = 0; j < 16; j += 4) {
-                float4 b4;
-                asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w) : "r"(bar0 + 1024u + (uint32_t)(c0 + j) * 4u));
+                const float4 b4 = lds128f(bias_s + (uint32_t)j * 4u);
+                v[j] = __uint_as_float(cur[j]) + b4.x;
+                v[j + 1] = __uint_as_float(cur[j + 1]) + b4.y;
+                v[j + 2] = __uint_as_float(cur[j + 2]) + b4.z;
+                v[j + 3] = __uint_as_float(cur[j + 3]) + b4.w;
+            }
+            if constexpr (FAST == 2) {
+                // PReLU(x) = a x + b |x| with a = (1+slope)/2, b = (1-slope)/2: two FMA-pipe instructions (|x| is a free
+                // operand modifier), nothing on the half-rate compare/select pipe.  The result is rounded to half
+                // precision below, which absorbs the <= 1 ulp (fp32) difference to the select form.
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = fmaf(pr_b, fabsf(v[j]), pr_a * v[j]);
+            }
+            if (ok) {
+                uint4 o0, o1;
+                o0.x = pack2<BF16>(v[0], v[1]);   o0.y = pack2<BF16>(v[2], v[3]);
+                o0.z = pack2<BF16>(v[4], v[5]);   o0.w = pack2<BF16>(v[6], v[7]);
+                o1.x = pack2<BF16>(v[8], v[9]);   o1.y = pack2<BF16>(v[10], v[11]);
+                o1.z = pack2<BF16>(v[12], v[13]); o1.w = pack2<BF16>(v[14], v[15]);
+                *reinterpret_cast<uint4*>(ptr) = o0;
+                *reinterpret_cast<uint4*>(ptr + cstride) = o1;
+            }
+            if (nmb != mb) {                         // next M-block: new pixel column
+                ocol = w0 + nmb * 8 + (m & 7);
+                ok = row_ok && ocol < p.W;
+                ptr = row_base + (size_t)ocol * 16 + (size_t)(2 * ncgi) * cstride;
+            } else {
+                ptr += step_bytes;
+            }
+            bias_s = bar0 + 1024u + (uint32_t)ncgi * 64u;
+            if (more) tmem_ld_wait();
+            mb = nmb;
+            cgi = ncgi;
+            return more;
+        };
+        if (mb < p.MB) {
+            while (group(ra, rb) && group(rb, ra)) {}
+        }
+        }
+        if constexpr (!COUPLING && FAST == 0) {
+        // ---------- plain epilogue: bias + activation (+ residual) -> C8 / NCHW.  No divisions, 32-bit in-sample offsets,
+        // TMEM reads software-pipelined one 16-column group ahead. ----------
+        const int gpm = p.BN >> 4;                   // 16-column groups per M-block
+        const uint32_t lane_addr = acc_base + ((uint32_t)(q * 32) << 16);
+        const int cg0 = nblk * p.BN;                 // first global (padded) output channel of this n-block
+        const uint32_t plane32 = (uint32_t)plane;
+        // item-level bases (64-bit once per item); everything inside the loop is a 32-bit offset from them
+        size_t base_off;                             // bytes (C8) or elements (NCHW) of channel cg0 of sample n
+        uint32_t cstride;                            // C8: bytes between 8-channel chunks
+        int ij = 0;
+        if (p.out_mode == 1) {
+            base_off = ((size_t)n * p.Cout + cg0) * plane;
+            cstride = 0;
+        } else if (p.out_mode == 2) {
+            ij = cg0 / p.Cout_p;                     // BN divides Cout_p: one sub-pixel (i,j) per n-block
+            const int co0 = cg0 - ij * p.Cout_p;
+            base_off = (((size_t)n * (p.Cout_p >> 3) + (co0 >> 3)) * plane * 4) * 16;
+            cstride = plane32 * 64;
+        } else {
+            base_off = (((size_t)n * (p.Cout_p >> 3) + (cg0 >> 3)) * plane) * 16;
+            cstride = plane32 * 16;
+        }
+        uint8_t* const out_b = reinterpret_cast<uint8_t*>(p.out);
+        int mb = 0, cgi = half;
+        while (cgi >= gpm) { cgi -= gpm; ++mb; }
+        uint32_t r[16];
+        if (mb < p.MB) {
+            __syncwarp();
+            tmem_ld16_nowait(lane_addr + (uint32_t)(mb * p.BN + (cgi << 4)), r);
+            tmem_ld_wait();
+        }
+        while (mb < p.MB) {
+            int nmb = mb, ncgi = cgi + kEpiSplit;
+            while (ncgi >= gpm) { ncgi -= gpm; ++nmb; }
+            const bool more = nmb < p.MB;
+            const int c0 = cgi << 4;
+            const int ocol = w0 + mb * 8 + (m & 7);
+            const bool ok = row_ok && ocol < p.W;
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+                const float4 b4 = lds128f(bar0 + 1024u + (uint32_t)(c0 + j) * 4u);
                 v[j] = __uint_as_float(r[j]) + b4.x;
                 v[j + 1] = __uint_as_float(r[j + 1]) + b4.y;
                 v[j + 2] = __uint_as_float(r[j + 2]) + b4.z;
                 v[j + 3] = __uint_as_float(r[j + 3]) + b4.w;
             }
+            // r is consumed: the next group's TMEM read lands in it while this group is activated, packed and stored
+            __syncwarp();
+            if (more) tmem_ld16_nowait(lane_addr + (uint32_t)(nmb * p.BN + (ncgi << 4)), r);
             if (!ok) {
                 // masked pixel (image edge inside the tile): nothing to store
             } else if (p.out_mode == 1) {
                 // NCHW fp32 (res, if any, is NCHW fp32 too)
-                float* out = reinterpret_cast<float*>(p.out);
-                const float* res = reinterpret_cast<const float*>(p.res);
-                const size_t o0 = ((size_t)n * p.Cout + cg) * plane + pix;
+                float* out = reinterpret_cast<float*>(p.out) + base_off + (size_t)c0 * plane + (size_t)orow * p.W + ocol;
+                const float* res = reinterpret_cast<const float*>(p.res) + base_off + (size_t)c0 * plane + (size_t)orow * p.W + ocol;
+                const int cg = cg0 + c0;
                 if (p.res_mode == 1) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) if (cg + j < p.Cout) v[j] += __ldg(res + o0 + j * plane);
+                    for (int j = 0; j < 16; ++j) if (cg + j < p.Cout) v[j] += __ldg(res + j * plane);
                 }
                 act_vec<16>(v, p.act, slope);
                 if (p.res_mode == 2) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) if (cg + j < p.Cout) v[j] += __ldg(res + o0 + j * plane);
+                    for (int j = 0; j < 16; ++j) if (cg + j < p.Cout) v[j] += __ldg(res + j * plane);
                 }
 #pragma unroll
-                for (int j = 0; j < 16; ++j) if (cg + j < p.Cout) out[o0 + j * plane] = v[j];
+                for (int j = 0; j < 16; ++j) if (cg + j < p.Cout) out[j * plane] = v[j];
             } else {
                 // C8 half output: two 16-byte chunks per pixel.  out_mode 2 = ConvTranspose2d(k=2,s=2) as a
                 // 1x1 conv to 4*Cout_p channels: channel block -> (i,j) sub-pixel, scattered to (2h+i, 2w+j).
-                const int cchunks = p.Cout_p >> 3;
-                size_t o, cstride;
-                if (p.out_mode == 2) {
-                    const int ij = cg / p.Cout_p, co = cg - ij * p.Cout_p;
-                    const size_t plane2 = plane * 4;
-                    const size_t pix2 = (size_t)(2 * orow + (ij >> 1)) * (2 * p.W) + 2 * ocol + (ij & 1);
-                    o = (((size_t)n * cchunks + (co >> 3)) * plane2 + pix2) * 16;
-                    cstride = plane2 * 16;
-                } else {
-                    o = (((size_t)n * cchunks + (cg >> 3)) * plane + pix) * 16;   // byte offset of chunk 0
-                    cstride = plane * 16;
-                }
+                uint32_t off;
+                if (p.out_mode == 2)
+                    off = (uint32_t)(c0 >> 3) * cstride + ((uint32_t)(2 * orow + (ij >> 1)) * (uint32_t)(2 * p.W) + (uint32_t)(2 * ocol + (ij & 1))) * 16u;
+                else
+                    off = (uint32_t)(c0 >> 3) * cstride + ((uint32_t)orow * (uint32_t)p.W + (uint32_t)ocol) * 16u;
+                const size_t o = base_off + off;
                 float rv[16];
                 if (p.res_mode != 0) {
 #pragma unroll
                     for (int hh = 0; hh < 2; ++hh) {
-                        const uint4 rr = __ldg(reinterpret_cast<const uint4*>(p.res + o + hh * cstride));
+                        const uint4 rr = __ldg(reinterpret_cast<const uint4*>(p.res + o + (size_t)hh * cstride));
                         const float2 r0 = unpack2<BF16>(rr.x), r1 = unpack2<BF16>(rr.y), r2 = unpack2<BF16>(rr.z),
                                      r3 = unpack2<BF16>(rr.w);
                         rv[hh * 8 + 0] = r0.x; rv[hh * 8 + 1] = r0.y; rv[hh * 8 + 2] = r1.x; rv[hh * 8 + 3] = r1.y;
@@ -609,14 +731,13 @@ __global__ void __launch_bounds__(WIDE ? 576 : kThreads, WIDE ? 1 : 2) conv_tc_k
                     ov.y = pack2<BF16>(v[hh * 8 + 2], v[hh * 8 + 3]);
                     ov.z = pack2<BF16>(v[hh * 8 + 4], v[hh * 8 + 5]);
                     ov.w = pack2<BF16>(v[hh * 8 + 6], v[hh * 8 + 7]);
-                    *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.out) + o + hh * cstride) = ov;
+                    *reinterpret_cast<uint4*>(out_b + o + (size_t)hh * cstride) = ov;
                 }
             }
-            if (more) {
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 16; ++j) r[j] = rnext[j];
-            }
+            if (more) tmem_ld_wait();
+            mb = nmb;
+            cgi = ncgi;
+        }
         }
         // all tcgen05.ld of this item have completed: hand the accumulator buffer back to the MMA issuer
         tc_fence_before();
@@ -742,6 +863,10 @@ static int conv_tc_launch(const void* x_c8, const void* w_packed, const float* b
         return CWFA_EINVAL;
     }
     if (res_mode != 0 && !res) { set_error("conv_tc: res_mode set but res is NULL"); return CWFA_EINVAL; }
+    if (out_mode != 1 && out_mode != 3 && (int64_t)H * W * 2 * Cout_p * (out_mode == 2 ? 4 : 1) >= (int64_t)1 << 32) {
+        set_error("conv_tc: one output sample must stay below 4 GiB (32-bit in-sample offsets)");
+        return CWFA_EINVAL;
+    }
     if ((reinterpret_cast<uintptr_t>(x_c8) & 15) || (reinterpret_cast<uintptr_t>(w_packed) & 15) ||
         (out_mode != 3 && (reinterpret_cast<uintptr_t>(out) & 15))) {
         set_error("conv_tc: pointers must be 16-byte aligned");
@@ -762,7 +887,8 @@ static int conv_tc_launch(const void* x_c8, const void* w_packed, const float* b
     p.a_bytes = (uint32_t)p.KCc * p.BH * p.BW * 16;
     p.a_stride = (p.a_bytes + 127u) & ~127u;
     p.b_bytes = (uint32_t)p.KCc * BN * 16;
-    p.a_stages = p.num_kb > 1 ? 2 : 1;
+    p.a_stages = 2;            // persistent kernel: the next item's halo tile loads while this one is multiplied
+    if (p.num_kb == 1 && 1024 + kHeaderBytes + 2 * p.a_stride + 3 * p.b_bytes > 225 * 1024) p.a_stages = 1;
     const int total_b = p.num_kb * KH * KW;
     // keep a CTA under ~100 KB when possible so two CTAs co-reside (one's epilogue overlaps the other's MMAs)
     const uint32_t budget_small = 100 * 1024, budget_max = 225 * 1024;
@@ -795,21 +921,25 @@ static int conv_tc_launch(const void* x_c8, const void* w_packed, const float* b
     typedef void (*KernT)(const CUtensorMap, const TcParams);
     KernT kern;
     int ki;
+    // lean epilogue variants: C8 output, no residual, activation none / PReLU
+    const int fast = (out_mode == 0 && res_mode == 0) ? (act == CWFA_ACT_NONE ? 1 : (act == CWFA_ACT_PRELU && slope) ? 2 : 0) : 0;
     if (out_mode == 3) {
         const int cplmode = (cpl->t ? 2 : 0) + (cpl->inverse ? 1 : 0);       // 0 fwd, 1 inv, 2 fwd+ext, 3 inv+ext
         static const KernT table[2][4] = {
-            {conv_tc_kernel<false, 1, false>, conv_tc_kernel<false, 2, false>, conv_tc_kernel<false, 3, false>, conv_tc_kernel<false, 4, false>},
-            {conv_tc_kernel<true, 1, false>, conv_tc_kernel<true, 2, false>, conv_tc_kernel<true, 3, false>, conv_tc_kernel<true, 4, false>}};
+            {conv_tc_kernel<false, 1, false, 0>, conv_tc_kernel<false, 2, false, 0>, conv_tc_kernel<false, 3, false, 0>, conv_tc_kernel<false, 4, false, 0>},
+            {conv_tc_kernel<true, 1, false, 0>, conv_tc_kernel<true, 2, false, 0>, conv_tc_kernel<true, 3, false, 0>, conv_tc_kernel<true, 4, false, 0>}};
         kern = table[is_bf16 ? 1 : 0][cplmode];
-        ki = 4 + (is_bf16 ? 4 : 0) + cplmode;
-    } else if (wide) {
-        kern = is_bf16 ? conv_tc_kernel<true, 0, true> : conv_tc_kernel<false, 0, true>;
-        ki = 2 + (is_bf16 ? 1 : 0);
+        ki = 12 + (is_bf16 ? 4 : 0) + cplmode;
     } else {
-        kern = is_bf16 ? conv_tc_kernel<true, 0, false> : conv_tc_kernel<false, 0, false>;
-        ki = is_bf16 ? 1 : 0;
+        static const KernT table[2][2][3] = {
+            {{conv_tc_kernel<false, 0, false, 0>, conv_tc_kernel<false, 0, false, 1>, conv_tc_kernel<false, 0, false, 2>},
+             {conv_tc_kernel<false, 0, true, 0>, conv_tc_kernel<false, 0, true, 1>, conv_tc_kernel<false, 0, true, 2>}},
+            {{conv_tc_kernel<true, 0, false, 0>, conv_tc_kernel<true, 0, false, 1>, conv_tc_kernel<true, 0, false, 2>},
+             {conv_tc_kernel<true, 0, true, 0>, conv_tc_kernel<true, 0, true, 1>, conv_tc_kernel<true, 0, true, 2>}}};
+        kern = table[is_bf16 ? 1 : 0][wide ? 1 : 0][fast];
+        ki = (is_bf16 ? 6 : 0) + (wide ? 3 : 0) + fast;
     }
-    static bool attr_done[12] = {false, false, false, false, false, false, false, false, false, false, false, false};
+    static bool attr_done[20] = {};
     if (!attr_done[ki]) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         attr_done[ki] = true;

@@ -83,8 +83,12 @@ class PackedConv:
         tot_p = 4 * self.Cout_p if transposed else self.Cout_p
         if bn is None:
             bn = pick_bn(tot_p if not transposed else self.Cout_p)
-            if self.Cin_p <= 64 and bn == 256:
-                bn = 128          # small-K convs are epilogue-bound: two co-resident CTAs (256 TMEM columns each) overlap
+            if self.Cin_p <= 64 and not transposed:
+                # small-K convs are epilogue/bandwidth-bound; tile widths measured best on B200 (scripts/sweep_conv_tc.py)
+                for cand in (256, 128, 192, 64, 160, 96, 48, 32, 16):
+                    if tot_p % cand == 0:
+                        bn = cand
+                        break
         self.BN = bn
         self.tot_p = tot_p
         lib = _lib.load()
@@ -114,6 +118,8 @@ def conv_tc(x: C8, pc: PackedConv, *, act: int = 0, slope: Optional[torch.Tensor
     N, H, W = x.N, x.H, x.W
     if mb is None:
         mb = 2 if (pc.BN * 2 <= 512 and W > 8) else 1
+        if pc.BN >= 192 and pc.Cin_p <= 64:
+            mb = 1        # small-K, wide-N: 128-pixel tiles keep two CTAs per SM (<= 256 TMEM columns each)
     dev = x.data.device
     if out_nchw:
         out = torch.empty((N, pc.Cout, H, W), device=dev, dtype=torch.float32)
