@@ -355,21 +355,22 @@ __global__ void __launch_bounds__(WIDE ? 576 : kThreads, WIDE ? 1 : 2) conv_tc_k
         // ===================== TMA producer =====================
         if (lane == 0) {
             const int ph = p.KH / 2, pw = p.KW / 2;
-            int ia = 0, ib = 0;                      // running ring positions: the rings run straight through item boundaries,
+            int sa = 0, sb = 0;                      // running ring positions (no divisions): the rings run straight through item boundaries,
+            uint32_t pa = 0, pb = 0;                 // ring pass parities
             ItemPos pos = split_digits((int)blockIdx.x);
             for (int item = blockIdx.x; item < total; item += gridDim.x, advance(pos)) {   // so the next item's operands load during this epilogue
                 const int nblk = pos.nblk, n = pos.n, h0 = pos.ty * 16, w0 = pos.tx * 8 * p.MB;
-                for (int kb = 0; kb < p.num_kb; ++kb, ++ia) {
-                    const int sa = ia % p.a_stages;
-                    mbar_wait(a_empty(sa), ((ia / p.a_stages) & 1) ^ 1);
+                const uint8_t* src = p.w_packed + (size_t)nblk * p.num_kb * T * p.b_bytes;
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    mbar_wait(a_empty(sa), pa ^ 1);
                     mbar_expect_tx(a_full(sa), p.a_bytes);
                     tma_load_4d(a_base + sa * p.a_stride, &tmap, a_full(sa), (w0 - pw) * 8, h0 - ph, kb * p.KCc, n);
-                    for (int tap = 0; tap < T; ++tap, ++ib) {
-                        const int sb = ib % p.b_stages;
-                        mbar_wait(b_empty(sb), ((ib / p.b_stages) & 1) ^ 1);
+                    if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
+                    for (int tap = 0; tap < T; ++tap, src += p.b_bytes) {
+                        mbar_wait(b_empty(sb), pb ^ 1);
                         mbar_expect_tx(b_full(sb), p.b_bytes);
-                        const uint8_t* src = p.w_packed + ((size_t)(nblk * p.num_kb + kb) * T + tap) * p.b_bytes;
                         bulk_load(b_base + sb * p.b_bytes, src, p.b_bytes, b_full(sb));
+                        if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
                     }
                 }
             }
@@ -387,24 +388,23 @@ __global__ void __launch_bounds__(WIDE ? 576 : kThreads, WIDE ? 1 : 2) conv_tc_k
         const uint32_t a_kstep = (2 * a_lbo) >> 4, b_kstep = (2 * b_lbo) >> 4;   // per K=16 step, in 16-byte units
         const int ksteps = p.KCc / 2;
         const uint32_t leader = elect_one();
-        int ia = 0, ib = 0, li = 0;
+        int sa = 0, sb = 0, li = 0;
+        uint32_t pa = 0, pb = 0;
         for (int item = blockIdx.x; item < total; item += gridDim.x, ++li) {
         const int buf = p.acc_bufs == 2 ? (li & 1) : 0;
         const int use = p.acc_bufs == 2 ? (li >> 1) : li;
         mbar_wait(acc_empty(buf), (use & 1) ^ 1);                // epilogue has drained this accumulator buffer
         tc_fence_after();
         const uint32_t d_base = tmem_base + (uint32_t)(buf * acc_cols);
-        for (int kb = 0; kb < p.num_kb; ++kb, ++ia) {
-            const int sa = ia % p.a_stages;
-            mbar_wait(a_full(sa), (ia / p.a_stages) & 1);
-            if (ia == 0 && leader) stamp(p, 2);
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+            mbar_wait(a_full(sa), pa);
+            if (li == 0 && kb == 0 && leader) stamp(p, 2);
             const uint32_t a_s = a_base + sa * p.a_stride;
             int it = kb * T;
             for (int kh = 0; kh < p.KH; ++kh) {
-                for (int kw = 0; kw < p.KW; ++kw, ++it, ++ib) {
-                    const int sb = ib % p.b_stages;
-                    mbar_wait(b_full(sb), (ib / p.b_stages) & 1);
-                    if (ib == 0 && leader) stamp(p, 3);
+                for (int kw = 0; kw < p.KW; ++kw, ++it) {
+                    mbar_wait(b_full(sb), pb);
+                    if (li == 0 && it == 0 && leader) stamp(p, 3);
                     tc_fence_after();
                     const uint32_t a_lo0 = (((a_s + (uint32_t)((kh * p.BW + kw) * 16)) & 0x3FFFFu) >> 4) | a_lbo_enc;
                     const uint32_t b_lo0 = (((b_base + sb * p.b_bytes) & 0x3FFFFu) >> 4) | b_lbo_enc;
@@ -418,10 +418,12 @@ __global__ void __launch_bounds__(WIDE ? 576 : kThreads, WIDE ? 1 : 2) conv_tc_k
                         tc_commit(b_empty(sb));
                     }
                     __syncwarp();
+                    if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
                 }
             }
             if (leader) tc_commit(a_empty(sa));
             __syncwarp();
+            if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
         }
         if (leader) {
             if (li == 0) stamp(p, 4);

@@ -85,14 +85,16 @@ __global__ void __launch_bounds__(kThreads, 1) coupling_tc_kernel(const __grid_c
             const uint32_t wbytes = 9u * kChunks * p.BN * 16u;
             mbar_expect_tx(w_full, wbytes);
             bulk_load(s0 + kOffW, p.w, wbytes, w_full);
+            int sa = 0;
+            uint32_t pa = 0;
             for (int i = 0; i < my_tiles; ++i) {
                 const int t = blockIdx.x + i * gridDim.x;
                 const int n = t / tiles_per_img, r = t % tiles_per_img;
                 const int h0 = (r / p.tiles_x) * kTH, w0 = (r % p.tiles_x) * kTW;
-                const int sa = i % p.a_stages;
-                mbar_wait(a_empty(sa), ((i / p.a_stages) & 1) ^ 1);
+                mbar_wait(a_empty(sa), pa ^ 1);
                 mbar_expect_tx(a_full(sa), kA1Bytes);
                 tma_load_4d(s0 + p.off_a + sa * kA1Bytes, &tmap, a_full(sa), (w0 - 1) * 8, h0 - 1, 0, n);
+                if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
             }
         }
     } else if (warp == 1) {
@@ -103,10 +105,11 @@ __global__ void __launch_bounds__(kThreads, 1) coupling_tc_kernel(const __grid_c
         const uint32_t w_lo0 = desc_lo(s0 + kOffW, w_lbo);
         const uint32_t leader = elect_one();
         mbar_wait(w_full, 0);
+        int sa = 0;
+        uint32_t pa = 0;
         for (int i = 0; i < my_tiles; ++i) {
             const int b = i & 1, ph = (i >> 1) & 1;
-            const int sa = i % p.a_stages;
-            mbar_wait(a_full(sa), (i / p.a_stages) & 1);
+            mbar_wait(a_full(sa), pa);
             mbar_wait(acc_empty(b), ph ^ 1);
             tc_fence_after();
             if (leader) {
@@ -128,6 +131,7 @@ __global__ void __launch_bounds__(kThreads, 1) coupling_tc_kernel(const __grid_c
                 tc_commit(acc_full(b));
             }
             __syncwarp();
+            if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
         }
     } else {
         // ============================ epilogue: 16 warps ============================
@@ -149,7 +153,7 @@ __global__ void __launch_bounds__(kThreads, 1) coupling_tc_kernel(const __grid_c
 #pragma unroll
             for (int k = 0; k < kMaxG; ++k) {
                 const int g = sub + 4 * k;
-                const int mb = g / gpc, c0 = (g - mb * gpc) << 3;
+                const int mb = g >= gpc ? 1 : 0, c0 = (g - (mb ? gpc : 0)) << 3;      // two M-blocks: no division
                 const int ocol = w0 + mb * 8 + (m & 7);
                 const bool ok = g < ngroups && row_ok && ocol < p.W;
                 int srow = orow, scol = ocol;
@@ -176,7 +180,7 @@ __global__ void __launch_bounds__(kThreads, 1) coupling_tc_kernel(const __grid_c
             for (int k = 0; k < kMaxG; ++k) {
                 const int g = sub + 4 * k;
                 if (g < ngroups) {                          // warp-uniform
-                    const int mb = g / gpc, c0 = (g - mb * gpc) << 3;
+                    const int mb = g >= gpc ? 1 : 0, c0 = (g - (mb ? gpc : 0)) << 3;      // two M-blocks: no division
                     const int ocol = w0 + mb * 8 + (m & 7);
                     const bool ok = row_ok && ocol < p.W;
                     uint32_t rs[8], rt[8];
