@@ -42,32 +42,23 @@ __global__ void __launch_bounds__(256) c8_stats_kernel(const uint4* __restrict__
     float s[8], q[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
-    const int64_t per = (int64_t)N * P;
+    auto acc = [&](const uint4& u) {
+        float v[8];
+        unpack8<BF16>(u, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s[j] += v[j]; q[j] = fmaf(v[j], v[j], q[j]); }
+    };
+    // plane-by-plane walk (no per-element index division); 4 independent 16-byte loads in flight per thread
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    auto addr = [&](int64_t i) { return x + ((i / P) * chunks + ch) * P + (i % P); };
-    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    for (; i + 3 * stride < per; i += 4 * stride) {          // 4 independent 16-byte loads in flight per thread
-        const uint4 u0 = __ldg(addr(i)), u1 = __ldg(addr(i + stride)), u2 = __ldg(addr(i + 2 * stride)),
-                    u3 = __ldg(addr(i + 3 * stride));
-        float v[8];
-        unpack8<BF16>(u0, v);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { s[j] += v[j]; q[j] = fmaf(v[j], v[j], q[j]); }
-        unpack8<BF16>(u1, v);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { s[j] += v[j]; q[j] = fmaf(v[j], v[j], q[j]); }
-        unpack8<BF16>(u2, v);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { s[j] += v[j]; q[j] = fmaf(v[j], v[j], q[j]); }
-        unpack8<BF16>(u3, v);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { s[j] += v[j]; q[j] = fmaf(v[j], v[j], q[j]); }
-    }
-    for (; i < per; i += stride) {
-        float v[8];
-        unpack8<BF16>(__ldg(addr(i)), v);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { s[j] += v[j]; q[j] = fmaf(v[j], v[j], q[j]); }
+    for (int n = 0; n < N; ++n) {
+        const uint4* xp = x + ((int64_t)n * chunks + ch) * P;
+        int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+        for (; i + 3 * stride < P; i += 4 * stride) {
+            const uint4 u0 = __ldg(xp + i), u1 = __ldg(xp + i + stride), u2 = __ldg(xp + i + 2 * stride),
+                        u3 = __ldg(xp + i + 3 * stride);
+            acc(u0); acc(u1); acc(u2); acc(u3);
+        }
+        for (; i < P; i += stride) acc(__ldg(xp + i));
     }
     __shared__ float red[8][16];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -100,51 +91,55 @@ __global__ void c8_stats_finalize_kernel(const float* __restrict__ ws, float* __
     stats[Cp + c] = (float)q;
 }
 
-// y = x*scale[c] + shift[c]; optionally also the 2x2 max-pooled tensor.  One thread per 2x2 pixel block
-// and chunk (or per pixel when POOL is false).
+// y = x*scale[c] + shift[c]; optionally also the 2x2 max-pooled tensor.  blockIdx.y = (sample, chunk): the 8 scales
+// and shifts live in registers; blockIdx.x strides over (pooled) rows, threads over (pooled) columns -- no index
+// divisions.  POOL: one thread per 2x2 pixel block.
 template <bool BF16, bool POOL>
 __global__ void __launch_bounds__(256) c8_bn_apply_kernel(const uint4* __restrict__ x, const float* __restrict__ scale,
                                                           const float* __restrict__ shift, uint4* __restrict__ y,
-                                                          uint4* __restrict__ ypool, int N, int chunks, int H, int W) {
+                                                          uint4* __restrict__ ypool, int chunks, int H, int W) {
     const int H2 = POOL ? H / 2 : H, W2 = POOL ? W / 2 : W;
-    const int64_t total = (int64_t)N * chunks * H2 * W2;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int w2 = (int)(i % W2);
-        const int h2 = (int)((i / W2) % H2);
-        const int ch = (int)((i / ((int64_t)W2 * H2)) % chunks);
-        const int n = (int)(i / ((int64_t)W2 * H2 * chunks));
-        float sc[8], sh[8];
+    const int ch = blockIdx.y % chunks;
+    float sc[8], sh[8];
+    {
+        const float4 a0 = __ldg(reinterpret_cast<const float4*>(scale + ch * 8)), a1 = __ldg(reinterpret_cast<const float4*>(scale + ch * 8 + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(shift + ch * 8)), b1 = __ldg(reinterpret_cast<const float4*>(shift + ch * 8 + 4));
+        sc[0] = a0.x; sc[1] = a0.y; sc[2] = a0.z; sc[3] = a0.w; sc[4] = a1.x; sc[5] = a1.y; sc[6] = a1.z; sc[7] = a1.w;
+        sh[0] = b0.x; sh[1] = b0.y; sh[2] = b0.z; sh[3] = b0.w; sh[4] = b1.x; sh[5] = b1.y; sh[6] = b1.z; sh[7] = b1.w;
+    }
+    const int64_t base = (int64_t)blockIdx.y * H * W;             // blockIdx.y = n * chunks + ch
+    const uint4* xp = x + base;
+    uint4* yp = y + base;
+    for (int h2 = blockIdx.x; h2 < H2; h2 += gridDim.x) {
+        for (int w2 = threadIdx.x; w2 < W2; w2 += blockDim.x) {
+            if constexpr (POOL) {
+                const int o00 = (2 * h2) * W + 2 * w2;
+                const uint4 u[4] = {__ldg(xp + o00), __ldg(xp + o00 + 1), __ldg(xp + o00 + W), __ldg(xp + o00 + W + 1)};
+                float mx[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { sc[j] = __ldg(scale + ch * 8 + j); sh[j] = __ldg(shift + ch * 8 + j); }
-        const int64_t base = ((int64_t)n * chunks + ch) * H * W;
-        if constexpr (POOL) {
-            float mx[8];
+                for (int j = 0; j < 8; ++j) mx[j] = -INFINITY;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) mx[j] = -INFINITY;
-#pragma unroll
-            for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-                for (int dx = 0; dx < 2; ++dx) {
-                    const int64_t o = base + (int64_t)(2 * h2 + dy) * W + 2 * w2 + dx;
+                for (int k = 0; k < 4; ++k) {
                     float v[8];
-                    unpack8<BF16>(__ldg(x + o), v);
+                    unpack8<BF16>(u[k], v);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) { v[j] = fmaf(v[j], sc[j], sh[j]); }
+                    for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
                     const uint4 pk = pack8<BF16>(v);
-                    y[o] = pk;
+                    yp[o00 + (k >> 1) * W + (k & 1)] = pk;
                     float r[8];
                     unpack8<BF16>(pk, r);      // pool the ROUNDED values so pooled == max of what is stored
 #pragma unroll
                     for (int j = 0; j < 8; ++j) mx[j] = fmaxf(mx[j], r[j]);
                 }
-            ypool[(((int64_t)n * chunks + ch) * H2 + h2) * W2 + w2] = pack8<BF16>(mx);
-        } else {
-            const int64_t o = base + (int64_t)h2 * W + w2;
-            float v[8];
-            unpack8<BF16>(__ldg(x + o), v);
+                ypool[(int64_t)blockIdx.y * H2 * W2 + (int64_t)h2 * W2 + w2] = pack8<BF16>(mx);
+            } else {
+                const int o = h2 * W + w2;
+                float v[8];
+                unpack8<BF16>(__ldg(xp + o), v);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
-            y[o] = pack8<BF16>(v);
+                for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
+                yp[o] = pack8<BF16>(v);
+            }
         }
     }
 }
@@ -171,17 +166,23 @@ extern "C" int cwfa_c8_bn_apply(const void* x, const float* scale, const float* 
     if (N <= 0 || Cp <= 0 || (Cp % 8) || H <= 0 || W <= 0) { set_error("c8_bn_apply: bad shape"); return CWFA_EINVAL; }
     const bool pool = ypool != nullptr;
     if (pool && ((H & 1) || (W & 1))) { set_error("c8_bn_apply: pooling needs even H, W"); return CWFA_EINVAL; }
-    const int64_t total = (int64_t)N * (Cp / 8) * (pool ? (H / 2) * (W / 2) : H * W);
-    int blocks = (int)((total + 255) / 256);
-    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    if ((int64_t)H * W >= (1ll << 31) || (int64_t)N * (Cp / 8) > 65535) { set_error("c8_bn_apply: shape too large"); return CWFA_EINVAL; }
+    if ((reinterpret_cast<uintptr_t>(scale) & 15) || (reinterpret_cast<uintptr_t>(shift) & 15)) { set_error("c8_bn_apply: scale/shift must be 16-byte aligned"); return CWFA_EINVAL; }
+    const int planes = N * (Cp / 8);
+    const int H2 = pool ? H / 2 : H, W2 = pool ? W / 2 : W;
+    int gx = ceil_div(kNumSMs * 8, planes);                      // ~8 resident blocks per SM overall
+    if (gx > H2) gx = H2;
+    if (gx < 1) gx = 1;
+    const int threads = W2 >= 256 ? 256 : (W2 >= 128 ? 128 : 64);
+    dim3 grid(gx, planes);
     const uint4* xi = (const uint4*)x;
     uint4 *yo = (uint4*)y, *yp = (uint4*)ypool;
     if (is_bf16) {
-        if (pool) c8_bn_apply_kernel<true, true><<<blocks, 256, 0, st>>>(xi, scale, shift, yo, yp, N, Cp / 8, H, W);
-        else c8_bn_apply_kernel<true, false><<<blocks, 256, 0, st>>>(xi, scale, shift, yo, yp, N, Cp / 8, H, W);
+        if (pool) c8_bn_apply_kernel<true, true><<<grid, threads, 0, st>>>(xi, scale, shift, yo, yp, Cp / 8, H, W);
+        else c8_bn_apply_kernel<true, false><<<grid, threads, 0, st>>>(xi, scale, shift, yo, yp, Cp / 8, H, W);
     } else {
-        if (pool) c8_bn_apply_kernel<false, true><<<blocks, 256, 0, st>>>(xi, scale, shift, yo, yp, N, Cp / 8, H, W);
-        else c8_bn_apply_kernel<false, false><<<blocks, 256, 0, st>>>(xi, scale, shift, yo, yp, N, Cp / 8, H, W);
+        if (pool) c8_bn_apply_kernel<false, true><<<grid, threads, 0, st>>>(xi, scale, shift, yo, yp, Cp / 8, H, W);
+        else c8_bn_apply_kernel<false, false><<<grid, threads, 0, st>>>(xi, scale, shift, yo, yp, Cp / 8, H, W);
     }
     return check_launch("c8_bn_apply");
 }

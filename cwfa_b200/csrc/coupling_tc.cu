@@ -166,10 +166,14 @@ __global__ void __launch_bounds__(kThreads, 1) coupling_tc_kernel(const __grid_c
                 const uint32_t spix = (uint32_t)srow * (uint32_t)p.W + (uint32_t)scol;
                 const uint32_t opix = (uint32_t)orow * (uint32_t)p.W + (uint32_t)ocol;
                 const bool okx = ok && xs != nullptr;
+                // the 8 source channels of this group: two 16-byte shared loads (identity / permutation table, 64 entries)
+                const float4 pl = lds128(s0 + 512u + 4u * (uint32_t)c0), ph4 = lds128(s0 + 512u + 4u * (uint32_t)c0 + 16u);
+                const uint32_t src_c[8] = {__float_as_uint(pl.x), __float_as_uint(pl.y), __float_as_uint(pl.z), __float_as_uint(pl.w),
+                                           __float_as_uint(ph4.x), __float_as_uint(ph4.y), __float_as_uint(ph4.z), __float_as_uint(ph4.w)};
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const int c = c0 + j;
-                    xv[k][j] = (okx && c < ch) ? __ldg(xs + ((uint32_t)lds_s32(s0 + 512u + 4u * c) * plane32 + spix)) : 0.f;
+                    xv[k][j] = (okx && c < ch) ? __ldg(xs + (src_c[j] * plane32 + spix)) : 0.f;
                     if constexpr (EXT) tx[k][j] = (ok && c < ch) ? __ldg(ts + ((uint32_t)c * plane32 + opix)) : 0.f;
                 }
             }
@@ -196,19 +200,25 @@ __global__ void __launch_bounds__(kThreads, 1) coupling_tc_kernel(const __grid_c
                         const float bt[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
                         float* yp = p.y + (size_t)n * ch * plane + ((uint32_t)c0 * (uint32_t)plane + (uint32_t)orow * (uint32_t)p.W + (uint32_t)ocol);
                         const uint32_t plane32 = (uint32_t)plane;
+                        // straight-line over the 8 channels of the group (8 independent dependency chains in flight);
+                        // only the store and the sums are predicated on the channel being real
+                        float sv[8], yv[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) sv[j] = p.kk * atan_fast(__uint_as_float(rs[j]) + bs[j]);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            float tv;
+                            if constexpr (EXT) tv = p.tscale * tx[k][j];
+                            else tv = __uint_as_float(rt[j]) + bt[j];
+                            if constexpr (INV) yv[j] = (xv[k][j] - tv) * exp_fast(-sv[j]);
+                            else yv[j] = fmaf(exp_fast(sv[j]), xv[k][j], tv);
+                        }
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             if (c0 + j < ch) {
-                                const float sv = p.kk * atan_fast(__uint_as_float(rs[j]) + bs[j]);
-                                float tv;
-                                if constexpr (EXT) tv = p.tscale * tx[k][j];
-                                else tv = __uint_as_float(rt[j]) + bt[j];
-                                float yv;
-                                if constexpr (INV) yv = (xv[k][j] - tv) * exp_fast(-sv);
-                                else yv = fmaf(exp_fast(sv), xv[k][j], tv);
-                                yp[(uint32_t)j * plane32] = yv;
-                                sum_s += sv;
-                                sum_q = fmaf(yv, yv, sum_q);
+                                yp[(uint32_t)j * plane32] = yv[j];
+                                sum_s += sv[j];
+                                sum_q = fmaf(yv[j], yv[j], sum_q);
                             }
                         }
                     }

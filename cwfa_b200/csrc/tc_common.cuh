@@ -140,7 +140,9 @@ __device__ __forceinline__ void sts128(uint32_t saddr, const uint4& v) {
 __device__ __forceinline__ float atan_fast(float x) {
     const float a = fabsf(x);
     const bool big = a > 1.f;
-    const float z = big ? __fdividef(1.f, a) : a;
+    float inv;                                   // straight-line: one MUFU, no denormal fix-up path, no branch
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(a));
+    const float z = big ? inv : a;
     const float s = z * z;
     float p = 0.0028662257f;
     p = fmaf(p, s, -0.0161657367f);

@@ -161,7 +161,8 @@ int cwfa_resblock_tc(const void* x_c8, void* y_c8, const void* w3_packed, const 
                      int in_chunk_off, int out_total_chunks, int out_chunk_off, int is_bf16, void* stream);
 /* ---- C8 helpers of the LRNN U-Net: per-channel (sum, sumsq) over (N,H,W) -> stats[2*Cp]
  * (workspace >= cwfa_c8_stats_workspace_floats(Cp) floats; feed to cwfa_bn_finalize_f32), and BatchNorm
- * apply y = x*scale+shift, optionally also writing the 2x2 max-pooled tensor (unet.py:79). */
+ * apply y = x*scale+shift, optionally also writing the 2x2 max-pooled tensor (unet.py:79).
+ * scale / shift must be 16-byte aligned; N * Cp/8 <= 65535. */
 int cwfa_c8_stats_workspace_floats(int Cp);
 int cwfa_c8_channel_stats(const void* x, float* stats, float* workspace, int N, int Cp, int64_t P,
                           int is_bf16, void* stream);
