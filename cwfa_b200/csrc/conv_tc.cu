@@ -654,8 +654,27 @@ __global__ void __launch_bounds__(WIDE ? 576 : kThreads, WIDE ? 1 : 2) conv_tc_k
         uint8_t* const out_b = reinterpret_cast<uint8_t*>(p.out);
         int mb = 0, cgi = half;
         while (cgi >= gpm) { cgi -= gpm; ++mb; }
+        // C8 modes: in-sample byte offset of the first chunk of group (mb_, cgi_) for this lane's pixel
+        auto c8_off = [&](int mb_, int cgi_, bool& ok_) -> uint32_t {
+            const int oc = w0 + mb_ * 8 + (m & 7);
+            ok_ = row_ok && oc < p.W;
+            if (p.out_mode == 2)
+                return (uint32_t)(cgi_ * 2) * cstride + ((uint32_t)(2 * orow + (ij >> 1)) * (uint32_t)(2 * p.W) + (uint32_t)(2 * oc + (ij & 1))) * 16u;
+            return (uint32_t)(cgi_ * 2) * cstride + ((uint32_t)orow * (uint32_t)p.W + (uint32_t)oc) * 16u;
+        };
+        const bool res_c8 = p.res_mode != 0 && p.out_mode != 1;
+        uint4 rres[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};     // residual chunks of the CURRENT group (prefetched)
+        auto load_res = [&](int mb_, int cgi_, uint4 (&dst)[2]) {
+            bool ok_;
+            const uint32_t off_ = c8_off(mb_, cgi_, ok_);
+            if (ok_) {
+                dst[0] = __ldg(reinterpret_cast<const uint4*>(p.res + base_off + off_));
+                dst[1] = __ldg(reinterpret_cast<const uint4*>(p.res + base_off + off_ + cstride));
+            }
+        };
         uint32_t r[16];
         if (mb < p.MB) {
+            if (res_c8) load_res(mb, cgi, rres);                  // in flight while the accumulator is awaited / read
             __syncwarp();
             tmem_ld16_nowait(lane_addr + (uint32_t)(mb * p.BN + (cgi << 4)), r);
             tmem_ld_wait();
@@ -667,6 +686,8 @@ __global__ void __launch_bounds__(WIDE ? 576 : kThreads, WIDE ? 1 : 2) conv_tc_k
             const int c0 = cgi << 4;
             const int ocol = w0 + mb * 8 + (m & 7);
             const bool ok = row_ok && ocol < p.W;
+            uint4 rnext[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+            if (res_c8 && more) load_res(nmb, ncgi, rnext);       // next group's residual: a full iteration of latency cover
             float v[16];
 #pragma unroll
             for (int j = 0; j < 16; j += 4) {
@@ -700,17 +721,14 @@ __global__ void __launch_bounds__(WIDE ? 576 : kThreads, WIDE ? 1 : 2) conv_tc_k
             } else {
                 // C8 half output: two 16-byte chunks per pixel.  out_mode 2 = ConvTranspose2d(k=2,s=2) as a
                 // 1x1 conv to 4*Cout_p channels: channel block -> (i,j) sub-pixel, scattered to (2h+i, 2w+j).
-                uint32_t off;
-                if (p.out_mode == 2)
-                    off = (uint32_t)(c0 >> 3) * cstride + ((uint32_t)(2 * orow + (ij >> 1)) * (uint32_t)(2 * p.W) + (uint32_t)(2 * ocol + (ij & 1))) * 16u;
-                else
-                    off = (uint32_t)(c0 >> 3) * cstride + ((uint32_t)orow * (uint32_t)p.W + (uint32_t)ocol) * 16u;
+                bool ok_unused;
+                const uint32_t off = c8_off(mb, cgi, ok_unused);
                 const size_t o = base_off + off;
                 float rv[16];
                 if (p.res_mode != 0) {
 #pragma unroll
                     for (int hh = 0; hh < 2; ++hh) {
-                        const uint4 rr = __ldg(reinterpret_cast<const uint4*>(p.res + o + (size_t)hh * cstride));
+                        const uint4 rr = rres[hh];
                         const float2 r0 = unpack2<BF16>(rr.x), r1 = unpack2<BF16>(rr.y), r2 = unpack2<BF16>(rr.z),
                                      r3 = unpack2<BF16>(rr.w);
                         rv[hh * 8 + 0] = r0.x; rv[hh * 8 + 1] = r0.y; rv[hh * 8 + 2] = r1.x; rv[hh * 8 + 3] = r1.y;
@@ -737,6 +755,8 @@ __global__ void __launch_bounds__(WIDE ? 576 : kThreads, WIDE ? 1 : 2) conv_tc_k
                 }
             }
             if (more) tmem_ld_wait();
+            rres[0] = rnext[0];
+            rres[1] = rnext[1];
             mb = nmb;
             cgi = ncgi;
         }
@@ -889,15 +909,27 @@ static int conv_tc_launch(const void* x_c8, const void* w_packed, const float* b
     p.a_bytes = (uint32_t)p.KCc * p.BH * p.BW * 16;
     p.a_stride = (p.a_bytes + 127u) & ~127u;
     p.b_bytes = (uint32_t)p.KCc * BN * 16;
-    p.a_stages = 2;            // persistent kernel: the next item's halo tile loads while this one is multiplied
-    if (p.num_kb == 1 && 1024 + kHeaderBytes + 2 * p.a_stride + 3 * p.b_bytes > 225 * 1024) p.a_stages = 1;
+    // Shared-memory plan.  Tiles that need <= 256 TMEM columns can co-reside two per SM (one CTA's epilogue and operand
+    // waits hide under the other's MMAs -- small-N MMAs are issue-bound per CTA), so prefer, in this order:
+    // 2 A stages + >= 3 B stages under 113 KB; 1 A stage + >= 3 B stages under 113 KB; else one CTA per SM with
+    // 2 A stages and 3 B stages.
     const int total_b = p.num_kb * KH * KW;
-    // keep a CTA under ~100 KB when possible so two CTAs co-reside (one's epilogue overlaps the other's MMAs)
-    const uint32_t budget_small = 100 * 1024, budget_max = 225 * 1024;
-    const uint32_t fixed = 1024 + kHeaderBytes + p.a_stages * p.a_stride;
+    const uint32_t budget_two = 113 * 1024, budget_max = 225 * 1024, hdr = 1024 + kHeaderBytes;
+    const bool can_pair = out_mode == 3 || MB * BN <= 256;
     int bs = total_b < kMaxBStages ? total_b : kMaxBStages;
-    while (bs > 3 && fixed + bs * p.b_bytes > budget_small) --bs;
-    while (bs > 1 && fixed + bs * p.b_bytes > budget_max) --bs;
+    const int bs_min = bs < 3 ? bs : 3;
+    p.a_stages = 2;
+    if (can_pair && hdr + 2 * p.a_stride + bs_min * p.b_bytes <= budget_two) {
+        while (bs > bs_min && hdr + 2 * p.a_stride + bs * p.b_bytes > budget_two) --bs;
+    } else if (can_pair && hdr + p.a_stride + bs_min * p.b_bytes <= budget_two) {
+        p.a_stages = 1;
+        while (bs > bs_min && hdr + p.a_stride + bs * p.b_bytes > budget_two) --bs;
+    } else {
+        if (hdr + 2 * p.a_stride + p.b_bytes > budget_max) p.a_stages = 1;
+        if (bs > 3) bs = 3;        // measured: a 4th 32 KB weight stage slows the N = 256 convs (L1 carve-out 228 KB instead of 196 KB)
+        while (bs > 1 && hdr + p.a_stages * p.a_stride + bs * p.b_bytes > budget_max) --bs;
+    }
+    const uint32_t fixed = hdr + p.a_stages * p.a_stride;
     if (fixed + bs * p.b_bytes > budget_max) { set_error("conv_tc: tile does not fit shared memory"); return CWFA_EINVAL; }
     p.b_stages = bs;
     p.act = act; p.res_mode = res_mode; p.out_mode = out_mode; p.is_bf16 = is_bf16;
