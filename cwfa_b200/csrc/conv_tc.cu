@@ -266,6 +266,20 @@ __device__ __forceinline__ void act_vec(float (&x)[NV], int act, float slope) {
     }
 }
 
+// One filter tap of one k-block: MB x KS MMAs, fully unrolled (compile-time trip counts: ~4 issue-side instructions
+// per MMA instead of a run-time double loop; small-N MMAs are bound by the single issuing warp, not the tensor pipe).
+template <int MB, int KS>
+__device__ __forceinline__ void issue_tap(uint32_t d_base, uint32_t bn, uint32_t a_lo0, uint32_t a_hi, uint32_t a_kstep,
+                                          uint32_t b_lo0, uint32_t b_hi, uint32_t b_kstep, uint32_t idesc, uint32_t acc_first) {
+#pragma unroll
+    for (int mb = 0; mb < MB; ++mb) {
+#pragma unroll
+        for (int kk = 0; kk < KS; ++kk)
+            tc_mma_f16_split(d_base + mb * bn, a_lo0 + mb * 8 + kk * a_kstep, a_hi, b_lo0 + kk * b_kstep, b_hi, idesc,
+                             kk ? 1u : acc_first);
+    }
+}
+
 // WIDE: 16 epilogue warps (576 threads) for tiles that fill all 512 TMEM columns (one CTA per SM, nothing to
 // overlap the epilogue with): halves the non-overlapped drain time of the N=256 U-Net convolutions.
 // CPL: 0 = plain conv; 1..4 = fused coupling epilogue with (direction, shift source) fixed at compile time
@@ -387,36 +401,43 @@ __global__ void __launch_bounds__(WIDE ? 576 : kThreads, WIDE ? 1 : 2) conv_tc_k
         const uint32_t a_lbo_enc = ((a_lbo >> 4) & 0x3FFFu) << 16, b_lbo_enc = ((b_lbo >> 4) & 0x3FFFu) << 16;
         const uint32_t a_kstep = (2 * a_lbo) >> 4, b_kstep = (2 * b_lbo) >> 4;   // per K=16 step, in 16-byte units
         const int ksteps = p.KCc / 2;
+        const uint32_t b_ring_lo = ((b_base & 0x3FFFFu) >> 4) | b_lbo_enc, b_stage_units = p.b_bytes >> 4;
         const uint32_t leader = elect_one();
         int sa = 0, sb = 0, li = 0;
         uint32_t pa = 0, pb = 0;
+        if (leader) { stamp(p, 2); stamp(p, 3); }                // (the operand waits are no longer stamped: hot loop)
         for (int item = blockIdx.x; item < total; item += gridDim.x, ++li) {
         const int buf = p.acc_bufs == 2 ? (li & 1) : 0;
         const int use = p.acc_bufs == 2 ? (li >> 1) : li;
         mbar_wait(acc_empty(buf), (use & 1) ^ 1);                // epilogue has drained this accumulator buffer
         tc_fence_after();
         const uint32_t d_base = tmem_base + (uint32_t)(buf * acc_cols);
+        uint32_t acc_first = 0u;                                  // first MMA of the item overwrites the accumulator
         for (int kb = 0; kb < p.num_kb; ++kb) {
             mbar_wait(a_full(sa), pa);
-            if (li == 0 && kb == 0 && leader) stamp(p, 2);
-            const uint32_t a_s = a_base + sa * p.a_stride;
-            int it = kb * T;
-            for (int kh = 0; kh < p.KH; ++kh) {
-                for (int kw = 0; kw < p.KW; ++kw, ++it) {
+            // descriptor low words in 16-byte units; taps advance by one pixel (kw) / one tile row (kh)
+            uint32_t a_row = (((a_base + sa * p.a_stride) & 0x3FFFFu) >> 4) | a_lbo_enc;
+            for (int kh = 0; kh < p.KH; ++kh, a_row += (uint32_t)p.BW) {
+                uint32_t a_lo0 = a_row;
+                for (int kw = 0; kw < p.KW; ++kw, ++a_lo0) {
                     mbar_wait(b_full(sb), pb);
-                    if (li == 0 && it == 0 && leader) stamp(p, 3);
                     tc_fence_after();
-                    const uint32_t a_lo0 = (((a_s + (uint32_t)((kh * p.BW + kw) * 16)) & 0x3FFFFu) >> 4) | a_lbo_enc;
-                    const uint32_t b_lo0 = (((b_base + sb * p.b_bytes) & 0x3FFFFu) >> 4) | b_lbo_enc;
                     if (leader) {
-                        for (int mb = 0; mb < p.MB; ++mb) {
-                            const uint32_t d = d_base + mb * p.BN;
-                            uint32_t al = a_lo0 + mb * 8, bl = b_lo0;
-                            for (int kk = 0; kk < ksteps; ++kk, al += a_kstep, bl += b_kstep)
-                                tc_mma_f16_split(d, al, a_hi, bl, b_hi, idesc, (it | kk) ? 1u : 0u);
+                        const uint32_t b_lo0 = b_ring_lo + (uint32_t)sb * b_stage_units;
+                        const int key = (p.MB - 1) * 4 + (ksteps - 1);
+                        switch (key) {
+                            case 0: issue_tap<1, 1>(d_base, p.BN, a_lo0, a_hi, a_kstep, b_lo0, b_hi, b_kstep, idesc, acc_first); break;
+                            case 1: issue_tap<1, 2>(d_base, p.BN, a_lo0, a_hi, a_kstep, b_lo0, b_hi, b_kstep, idesc, acc_first); break;
+                            case 2: issue_tap<1, 3>(d_base, p.BN, a_lo0, a_hi, a_kstep, b_lo0, b_hi, b_kstep, idesc, acc_first); break;
+                            case 3: issue_tap<1, 4>(d_base, p.BN, a_lo0, a_hi, a_kstep, b_lo0, b_hi, b_kstep, idesc, acc_first); break;
+                            case 4: issue_tap<2, 1>(d_base, p.BN, a_lo0, a_hi, a_kstep, b_lo0, b_hi, b_kstep, idesc, acc_first); break;
+                            case 5: issue_tap<2, 2>(d_base, p.BN, a_lo0, a_hi, a_kstep, b_lo0, b_hi, b_kstep, idesc, acc_first); break;
+                            case 6: issue_tap<2, 3>(d_base, p.BN, a_lo0, a_hi, a_kstep, b_lo0, b_hi, b_kstep, idesc, acc_first); break;
+                            default: issue_tap<2, 4>(d_base, p.BN, a_lo0, a_hi, a_kstep, b_lo0, b_hi, b_kstep, idesc, acc_first); break;
                         }
                         tc_commit(b_empty(sb));
                     }
+                    acc_first = 1u;
                     __syncwarp();
                     if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
                 }
