@@ -77,3 +77,68 @@ def test_fused_resblock_vs_unfused_and_cpu(kind, N, H, W):
     print(f"resblock {kind} {N}x{H}x{W}: vs unfused {rel_l2(y, y_ref2):.2e}  vs cpu {rel_l2(y, ref):.2e}")
     assert rel_l2(y, y_ref2) < tol
     assert rel_l2(y, ref) < tol
+
+
+FAST_CASES = [
+    # cin, cout, k, N, H, W, mb, bn  -- lean epilogue (C8 out, no residual); ragged edges, >1 item per CTA, every tile plan
+    (16, 320, 1, 2, 128, 128, 2, 64),     # 640 items on a 296-CTA persistent grid, double-buffered TMEM
+    (6, 192, 3, 1, 37, 53, 1, 192),       # ragged H and W, one M-block, two CTAs per SM
+    (12, 384, 3, 1, 40, 72, 2, 128),      # 256 TMEM columns, single buffer
+    (24, 768, 3, 2, 24, 40, 1, 256),
+    (48, 96, 3, 3, 33, 17, 2, 48),
+    (64, 48, 3, 1, 50, 30, 2, 48),
+    (256, 256, 3, 3, 128, 128, 2, 256),   # WIDE variant, 192 items on 148 CTAs
+    (64, 64, 7, 1, 45, 45, 2, 64),        # one A stage (shared-memory plan for two CTAs per SM)
+]
+
+
+@pytest.mark.parametrize("cin,cout,k,N,H,W,mb,bn", FAST_CASES)
+@pytest.mark.parametrize("act", ["none", "prelu"])
+def test_conv_tc_lean_epilogue_and_persistent_walk(cin, cout, k, N, H, W, mb, bn, act):
+    """C8-output convolutions without residual take the compile-time lean epilogue; the grid is persistent, so these
+    shapes also exercise CTAs walking several (n-block, sample, tile) items, ragged tile edges and each tile plan."""
+    from cwfa_b200 import ops, tc
+    kind = "bf16"
+    x = _round(seeded_randn((N, cin, H, W), 21), kind)
+    w = _round(seeded_randn((cout, cin, k, k), 22, (1.0 / (cin * k * k)) ** 0.5), kind)
+    b = seeded_randn((cout,), 23)
+    ref = F.conv2d(x, w, b, padding=k // 2)
+    slope = torch.full((1,), -0.3 if cin == 6 else 0.2)
+    if act == "prelu":
+        ref = torch.where(ref >= 0, ref, slope * ref)
+    xc = tc.to_c8(x.to(DEV), kind)
+    pc = tc.PackedConv(w.to(DEV), b.to(DEV), kind, bn=bn)
+    y8 = tc.conv_tc(xc, pc, act=ops.ACT_PRELU if act == "prelu" else ops.ACT_NONE,
+                    slope=slope.to(DEV) if act == "prelu" else None, mb=mb)
+    y = tc.from_c8(y8)
+    torch.cuda.synchronize()
+    assert y.shape == ref.shape
+    err = rel_l2(y, ref)
+    print(f"lean conv {cin}->{cout} k{k} {N}x{H}x{W} mb{mb} bn{bn} {act}: rel_l2={err:.2e}")
+    assert err < 6e-3
+    # padded output channels of the C8 tensor must be exactly zero (the next conv reads them as K padding)
+    if y8.Cp != cout:
+        raw = y8.data.float().view(N, y8.Cp // 8, H, W, 8).permute(0, 1, 4, 2, 3).reshape(N, y8.Cp, H, W)
+        assert float(raw[:, cout:].abs().max()) == 0.0
+    # same result from the default tile plan (heuristic BN / MB)
+    y_def = tc.from_c8(tc.conv_tc(xc, tc.PackedConv(w.to(DEV), b.to(DEV), kind), act=ops.ACT_PRELU if act == "prelu" else ops.ACT_NONE,
+                                  slope=slope.to(DEV) if act == "prelu" else None))
+    assert rel_l2(y_def, ref) < 6e-3
+
+
+@pytest.mark.parametrize("N,H,W,cin,cout", [(1, 9, 13, 64, 32), (2, 16, 24, 128, 64), (1, 64, 64, 512, 256)])
+def test_conv_transpose_tc_with_skip(N, H, W, cin, cout):
+    """ConvTranspose2d(k=2, s=2) + skip add (unet.py:166,190): scatter epilogue with the one-group-ahead residual prefetch."""
+    from cwfa_b200 import tc
+    kind = "bf16"
+    x = _round(seeded_randn((N, cin, H, W), 31), kind)
+    w = _round(seeded_randn((cin, cout, 2, 2), 32, (1.0 / cin) ** 0.5), kind)
+    b = seeded_randn((cout,), 33)
+    skip = _round(seeded_randn((N, cout, 2 * H, 2 * W), 34), kind)
+    ref = F.conv_transpose2d(x, w, b, stride=2) + skip
+    pc = tc.PackedConv(w.to(DEV), b.to(DEV), kind, transposed=True)
+    y = tc.from_c8(tc.conv_transpose_tc(tc.to_c8(x.to(DEV), kind), pc, tc.to_c8(skip.to(DEV), kind)))
+    y0 = tc.from_c8(tc.conv_transpose_tc(tc.to_c8(x.to(DEV), kind), pc))
+    torch.cuda.synchronize()
+    assert rel_l2(y, ref) < 6e-3
+    assert rel_l2(y0, ref - skip) < 6e-3
