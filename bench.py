@@ -133,7 +133,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-nll", action="store_true")
     ap.add_argument("--inflight", type=int, default=2, help="graph instances (frames) in flight per GPU")
-    ap.add_argument("--e2e-inflight", type=int, default=3, help="frames in flight in the host-buffer streaming measurement")
+    ap.add_argument("--e2e-inflight", type=int, default=2, help="frames in flight in the host-buffer streaming measurement")
     args = ap.parse_args()
     cfg = dict(side=args.side, depths=args.depths, steps=args.down_steps)
     rank = int(os.environ.get("RANK", "0"))

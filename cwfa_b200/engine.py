@@ -394,30 +394,70 @@ class StreamingReconstructor:
         self.ev_out = [torch.cuda.Event() for _ in range(depth)]
         torch.cuda.synchronize(dev)
 
+    def _staging(self, like_in: torch.Tensor, like_out: torch.Tensor):
+        """Device staging buffers for host-resident frames: the H2D copy of frame i+1 and the D2H copy of frame i-1 use
+        them, so a graph slot's static input/output tensors are tied up only for a device-to-device copy."""
+        if getattr(self, "_stage", None) is None:
+            n = self.depth + 1
+            dev = like_out.device
+            self._stage = ([torch.empty_like(like_in, device=dev) for _ in range(n)],
+                           [torch.empty_like(like_out, device=dev) for _ in range(n)],
+                           [torch.cuda.Event() for _ in range(n)], [torch.cuda.Event() for _ in range(n)],
+                           [torch.cuda.Event() for _ in range(n)], [torch.cuda.Event() for _ in range(n)])
+        return self._stage
+
     def run(self, views: Sequence[torch.Tensor], outs: Sequence[torch.Tensor]) -> None:
         """Reconstructs ``views[i]`` into ``outs[i]``; returns when every output has been written."""
         n = len(views)
         cur = torch.cuda.current_stream()
         for st in self.s_in + self.s_run + self.s_out:
             st.wait_stream(cur)
-        for i in range(n):
-            k = i % self.depth
-            graph, sv, sm, out = self.slots[k]
-            with torch.cuda.stream(self.s_in[k]):
-                if i >= self.depth:
-                    self.s_in[k].wait_event(self.ev_run[k])      # previous replay of this slot has consumed its input
-                sv.copy_(views[i], non_blocking=True)
-                self.ev_in[k].record(self.s_in[k])
-            with torch.cuda.stream(self.s_run[k]):
-                self.s_run[k].wait_event(self.ev_in[k])
-                if i >= self.depth:
-                    self.s_run[k].wait_event(self.ev_out[k])     # previous output of this slot has been copied out
-                graph.replay()
-                self.ev_run[k].record(self.s_run[k])
-            with torch.cuda.stream(self.s_out[k]):
-                self.s_out[k].wait_event(self.ev_run[k])
-                outs[i].copy_(out, non_blocking=True)
-                self.ev_out[k].record(self.s_out[k])
+        host_io = n > 0 and (not views[0].is_cuda or not outs[0].is_cuda)
+        if host_io:
+            _, sv0, _, out0 = self.slots[0]
+            st_in, st_out, ev_h2d, ev_in_free, ev_staged, ev_out_free = self._staging(sv0, out0)
+            ns = len(st_in)
+            s_in, s_out = self.s_in[0], self.s_out[0]
+            for i in range(n):
+                k, j = i % self.depth, i % ns
+                graph, sv, sm, out = self.slots[k]
+                with torch.cuda.stream(s_in):
+                    if i >= ns:
+                        s_in.wait_event(ev_in_free[j])           # the slot that used this staging buffer has copied it in
+                    st_in[j].copy_(views[i], non_blocking=True)
+                    ev_h2d[j].record(s_in)
+                with torch.cuda.stream(self.s_run[k]):           # stream order serialises the replays of one slot
+                    self.s_run[k].wait_event(ev_h2d[j])
+                    sv.copy_(st_in[j], non_blocking=True)
+                    ev_in_free[j].record(self.s_run[k])
+                    graph.replay()
+                    if i >= ns:
+                        self.s_run[k].wait_event(ev_out_free[j]) # the D2H copy that used this staging buffer has finished
+                    st_out[j].copy_(out, non_blocking=True)
+                    ev_staged[j].record(self.s_run[k])
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(ev_staged[j])
+                    outs[i].copy_(st_out[j], non_blocking=True)
+                    ev_out_free[j].record(s_out)
+        else:
+            for i in range(n):
+                k = i % self.depth
+                graph, sv, sm, out = self.slots[k]
+                with torch.cuda.stream(self.s_in[k]):
+                    if i >= self.depth:
+                        self.s_in[k].wait_event(self.ev_run[k])      # previous replay of this slot has consumed its input
+                    sv.copy_(views[i], non_blocking=True)
+                    self.ev_in[k].record(self.s_in[k])
+                with torch.cuda.stream(self.s_run[k]):
+                    self.s_run[k].wait_event(self.ev_in[k])
+                    if i >= self.depth:
+                        self.s_run[k].wait_event(self.ev_out[k])     # previous output of this slot has been copied out
+                    graph.replay()
+                    self.ev_run[k].record(self.s_run[k])
+                with torch.cuda.stream(self.s_out[k]):
+                    self.s_out[k].wait_event(self.ev_run[k])
+                    outs[i].copy_(out, non_blocking=True)
+                    self.ev_out[k].record(self.s_out[k])
         for st in self.s_out + self.s_run:
             cur.wait_stream(st)
         cur.synchronize()
