@@ -186,6 +186,7 @@ struct TcParams {
     int act, res_mode, out_mode;   // out_mode 0: C8 half   1: NCHW fp32   2: C8 half, 2x2 transposed-conv scatter
     int is_bf16;
     const uint8_t* w_packed;
+    const uint32_t* kmask;        // [n-block][k-block]: bit ks set = K-step ks of that weight block has a nonzero (zero K-steps are skipped)
     const float* bias;
     const float* slope;
     const uint8_t* res;
@@ -268,15 +269,19 @@ __device__ __forceinline__ void act_vec(float (&x)[NV], int act, float slope) {
 
 // One filter tap of one k-block: MB x KS MMAs, fully unrolled (compile-time trip counts: ~4 issue-side instructions
 // per MMA instead of a run-time double loop; small-N MMAs are bound by the single issuing warp, not the tensor pipe).
+// `mask` bit kk = K-step kk carries nonzero weights (banded / padded weight tensors skip the rest).
 template <int MB, int KS>
 __device__ __forceinline__ void issue_tap(uint32_t d_base, uint32_t bn, uint32_t a_lo0, uint32_t a_hi, uint32_t a_kstep,
-                                          uint32_t b_lo0, uint32_t b_hi, uint32_t b_kstep, uint32_t idesc, uint32_t acc_first) {
+                                          uint32_t b_lo0, uint32_t b_hi, uint32_t b_kstep, uint32_t idesc, uint32_t acc_first,
+                                          uint32_t mask) {
 #pragma unroll
     for (int mb = 0; mb < MB; ++mb) {
 #pragma unroll
-        for (int kk = 0; kk < KS; ++kk)
-            tc_mma_f16_split(d_base + mb * bn, a_lo0 + mb * 8 + kk * a_kstep, a_hi, b_lo0 + kk * b_kstep, b_hi, idesc,
-                             kk ? 1u : acc_first);
+        for (int kk = 0; kk < KS; ++kk) {
+            if (mask & (1u << kk))
+                tc_mma_f16_split(d_base + mb * bn, a_lo0 + mb * 8 + kk * a_kstep, a_hi, b_lo0 + kk * b_kstep, b_hi, idesc,
+                                 (mask & ((1u << kk) - 1u)) ? 1u : acc_first);
+        }
     }
 }
 
@@ -406,7 +411,8 @@ __global__ void __launch_bounds__(WIDE ? 576 : kThreads, WIDE ? 1 : 2) conv_tc_k
         int sa = 0, sb = 0, li = 0;
         uint32_t pa = 0, pb = 0;
         if (leader) { stamp(p, 2); stamp(p, 3); }                // (the operand waits are no longer stamped: hot loop)
-        for (int item = blockIdx.x; item < total; item += gridDim.x, ++li) {
+        ItemPos pos = split_digits((int)blockIdx.x);
+        for (int item = blockIdx.x; item < total; item += gridDim.x, ++li, advance(pos)) {
         const int buf = p.acc_bufs == 2 ? (li & 1) : 0;
         const int use = p.acc_bufs == 2 ? (li >> 1) : li;
         mbar_wait(acc_empty(buf), (use & 1) ^ 1);                // epilogue has drained this accumulator buffer
@@ -414,6 +420,8 @@ __global__ void __launch_bounds__(WIDE ? 576 : kThreads, WIDE ? 1 : 2) conv_tc_k
         const uint32_t d_base = tmem_base + (uint32_t)(buf * acc_cols);
         uint32_t acc_first = 0u;                                  // first MMA of the item overwrites the accumulator
         for (int kb = 0; kb < p.num_kb; ++kb) {
+            uint32_t kmask = __ldg(p.kmask + pos.nblk * p.num_kb + kb);
+            if (kb == 0 && kmask == 0) kmask = 1u;               // the accumulator must be written at least once per item
             mbar_wait(a_full(sa), pa);
             // descriptor low words in 16-byte units; taps advance by one pixel (kw) / one tile row (kh)
             uint32_t a_row = (((a_base + sa * p.a_stride) & 0x3FFFFu) >> 4) | a_lbo_enc;
@@ -426,18 +434,18 @@ __global__ void __launch_bounds__(WIDE ? 576 : kThreads, WIDE ? 1 : 2) conv_tc_k
                         const uint32_t b_lo0 = b_ring_lo + (uint32_t)sb * b_stage_units;
                         const int key = (p.MB - 1) * 4 + (ksteps - 1);
                         switch (key) {
-                            case 0: issue_tap<1, 1>(d_base, p.BN, a_lo0, a_hi, a_kstep, b_lo0, b_hi, b_kstep, idesc, acc_first); break;
-                            case 1: issue_tap<1, 2>(d_base, p.BN, a_lo0, a_hi, a_kstep, b_lo0, b_hi, b_kstep, idesc, acc_first); break;
-                            case 2: issue_tap<1, 3>(d_base, p.BN, a_lo0, a_hi, a_kstep, b_lo0, b_hi, b_kstep, idesc, acc_first); break;
-                            case 3: issue_tap<1, 4>(d_base, p.BN, a_lo0, a_hi, a_kstep, b_lo0, b_hi, b_kstep, idesc, acc_first); break;
-                            case 4: issue_tap<2, 1>(d_base, p.BN, a_lo0, a_hi, a_kstep, b_lo0, b_hi, b_kstep, idesc, acc_first); break;
-                            case 5: issue_tap<2, 2>(d_base, p.BN, a_lo0, a_hi, a_kstep, b_lo0, b_hi, b_kstep, idesc, acc_first); break;
-                            case 6: issue_tap<2, 3>(d_base, p.BN, a_lo0, a_hi, a_kstep, b_lo0, b_hi, b_kstep, idesc, acc_first); break;
-                            default: issue_tap<2, 4>(d_base, p.BN, a_lo0, a_hi, a_kstep, b_lo0, b_hi, b_kstep, idesc, acc_first); break;
+                            case 0: issue_tap<1, 1>(d_base, p.BN, a_lo0, a_hi, a_kstep, b_lo0, b_hi, b_kstep, idesc, acc_first, kmask); break;
+                            case 1: issue_tap<1, 2>(d_base, p.BN, a_lo0, a_hi, a_kstep, b_lo0, b_hi, b_kstep, idesc, acc_first, kmask); break;
+                            case 2: issue_tap<1, 3>(d_base, p.BN, a_lo0, a_hi, a_kstep, b_lo0, b_hi, b_kstep, idesc, acc_first, kmask); break;
+                            case 3: issue_tap<1, 4>(d_base, p.BN, a_lo0, a_hi, a_kstep, b_lo0, b_hi, b_kstep, idesc, acc_first, kmask); break;
+                            case 4: issue_tap<2, 1>(d_base, p.BN, a_lo0, a_hi, a_kstep, b_lo0, b_hi, b_kstep, idesc, acc_first, kmask); break;
+                            case 5: issue_tap<2, 2>(d_base, p.BN, a_lo0, a_hi, a_kstep, b_lo0, b_hi, b_kstep, idesc, acc_first, kmask); break;
+                            case 6: issue_tap<2, 3>(d_base, p.BN, a_lo0, a_hi, a_kstep, b_lo0, b_hi, b_kstep, idesc, acc_first, kmask); break;
+                            default: issue_tap<2, 4>(d_base, p.BN, a_lo0, a_hi, a_kstep, b_lo0, b_hi, b_kstep, idesc, acc_first, kmask); break;
                         }
                         tc_commit(b_empty(sb));
                     }
-                    acc_first = 1u;
+                    if (kmask) acc_first = 1u;
                     __syncwarp();
                     if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
                 }
@@ -830,7 +838,8 @@ extern "C" int cwfa_tc_kc(int cin_p) { return pick_kc(cin_p); }
 // 4*Cout_p output channels ordered (i*2+j)*Cout_p + co.
 template <bool BF16>
 __global__ void pack_weights_kernel(const float* __restrict__ w, uint16_t* __restrict__ out, int Cout, int Cin, int T,
-                                    int KC, int num_kb, int BN, int nblks, int transposed, int Cout_p) {
+                                    int KC, int num_kb, int BN, int nblks, int transposed, int Cout_p,
+                                    uint32_t* __restrict__ kmask) {
     const int KCc = KC / 8;
     const size_t total = (size_t)nblks * num_kb * T * KCc * BN * 8;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -858,13 +867,19 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, uint16_t* __res
             bits = *reinterpret_cast<uint16_t*>(&h);
         }
         out[i] = bits;
+        if (bits & 0x7FFFu) {                                 // nonzero: mark K-step (chunk pair) of this (n-block, k-block)
+            const uint32_t bit = 1u << (chunk >> 1);
+            uint32_t* m = kmask + nb * num_kb + kb;
+            if (!(*reinterpret_cast<volatile uint32_t*>(m) & bit)) atomicOr(m, bit);
+        }
     }
 }
 
 extern "C" int64_t cwfa_tc_packed_weight_elems(int Cin_p, int Cout_tot_p, int KH, int KW, int BN) {
     const int KC = pick_kc(Cin_p);
     if (!KC || Cout_tot_p % BN) return -1;
-    return (int64_t)(Cout_tot_p / BN) * (Cin_p / KC) * KH * KW * (KC / 8) * BN * 8;
+    // packed half elements + one uint32 K-step mask per (n-block, k-block) appended behind them
+    return (int64_t)(Cout_tot_p / BN) * (Cin_p / KC) * KH * KW * (KC / 8) * BN * 8 + 2 * (int64_t)(Cout_tot_p / BN) * (Cin_p / KC);
 }
 
 extern "C" int cwfa_tc_pack_weights(const float* w, void* packed, int Cout, int Cin, int KH, int KW, int Cin_p,
@@ -879,10 +894,12 @@ extern "C" int cwfa_tc_pack_weights(const float* w, void* packed, int Cout, int 
     const size_t total = (size_t)nblks * num_kb * T * (KC / 8) * BN * 8;
     int blocks = (int)((total + 255) / 256);
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+    uint32_t* kmask = reinterpret_cast<uint32_t*>((uint16_t*)packed + total);        // total * 2 bytes is a multiple of 16
+    if (cudaMemsetAsync(kmask, 0, sizeof(uint32_t) * nblks * num_kb, (cudaStream_t)stream) != cudaSuccess) return check_launch("tc_pack_weights memset");
     if (is_bf16)
-        pack_weights_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(w, (uint16_t*)packed, Cout, Cin, T, KC, num_kb, BN, nblks, transposed, Cout_p);
+        pack_weights_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(w, (uint16_t*)packed, Cout, Cin, T, KC, num_kb, BN, nblks, transposed, Cout_p, kmask);
     else
-        pack_weights_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(w, (uint16_t*)packed, Cout, Cin, T, KC, num_kb, BN, nblks, transposed, Cout_p);
+        pack_weights_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(w, (uint16_t*)packed, Cout, Cin, T, KC, num_kb, BN, nblks, transposed, Cout_p, kmask);
     return check_launch("tc_pack_weights");
 }
 
@@ -954,7 +971,11 @@ static int conv_tc_launch(const void* x_c8, const void* w_packed, const float* b
     if (fixed + bs * p.b_bytes > budget_max) { set_error("conv_tc: tile does not fit shared memory"); return CWFA_EINVAL; }
     p.b_stages = bs;
     p.act = act; p.res_mode = res_mode; p.out_mode = out_mode; p.is_bf16 = is_bf16;
-    p.w_packed = (const uint8_t*)w_packed; p.bias = bias; p.slope = slope; p.res = (const uint8_t*)res; p.out = out;
+    p.w_packed = (const uint8_t*)w_packed; p.bias = bias;
+    {
+        const int nblks_all = (out_mode == 2 ? 4 : 1) * Cout_p / BN;
+        p.kmask = reinterpret_cast<const uint32_t*>((const uint8_t*)w_packed + (size_t)nblks_all * p.num_kb * KH * KW * p.b_bytes);
+    } p.slope = slope; p.res = (const uint8_t*)res; p.out = out;
     p.dbg = g_tc_dbg;
     if (cpl) {
         p.cpl_x = cpl->x; p.cpl_y = cpl->y; p.cpl_t = cpl->t; p.cpl_perm = cpl->perm; p.cpl_ws = cpl->ws;

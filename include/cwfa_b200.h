@@ -143,7 +143,10 @@ int cwfa_gate_add_f32(float* x, const float* m, const float* g, int64_t n, void*
  * channels (res is NCHW fp32), out_mode 2: ConvTranspose2d(k=2,s=2) (unet.py:166) run as a 1x1 conv to
  * 4*Cout_p channels (weights packed with transposed=1) and scattered to a C8 (2H,2W) tensor, res = the
  * skip tensor added at the output location (unet.py:190).  BN = output channels per CTA (multiple of 16, <= 256, divides Cout_p),
- * MB = number of 16x8-pixel M=128 blocks per CTA (1 or 2), MB*BN <= 512 TMEM columns. */
+ * MB = number of 16x8-pixel M=128 blocks per CTA (1 or 2), MB*BN <= 512 TMEM columns.
+ * cwfa_tc_packed_weight_elems = half elements to allocate for w_packed: the packed tiles followed by one uint32 per
+ * (n-block, k-block) whose bit ks says "K-step ks has a nonzero weight" (written by cwfa_tc_pack_weights; cwfa_conv_tc
+ * skips the zero K-steps -- the depth-banded stencil weights of the conditioning net, networks.py:221-225, are 2/3 zero). */
 int cwfa_tc_kc(int cin_p);
 int64_t cwfa_tc_packed_weight_elems(int Cin_p, int Cout_tot_p, int KH, int KW, int BN);
 int cwfa_tc_pack_weights(const float* w, void* packed, int Cout, int Cin, int KH, int KW, int Cin_p,

@@ -1,0 +1,38 @@
+"""Times the two depth-stencil convolutions of the conditioning net (banded weights) at each level's depth count."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from cwfa_b200 import tc, ops
+DEV = "cuda:0"
+for D in (48, 24, 12, 6):
+    Cm = 32
+    w1 = torch.randn(Cm, 3, 3, 3, device=DEV) * 0.2
+    w2 = torch.randn(Cm, 3, 3, 3, device=DEV) * 0.05
+    W1 = torch.zeros(D, Cm, D, 3, 3, device=DEV)
+    W2 = torch.zeros(D, D, Cm, 3, 3, device=DEV)
+    for kd in range(3):
+        for d in range(D):
+            dp = d + kd - 1
+            if 0 <= dp < D:
+                W1[d, :, dp] = w1[:, :, :, kd]
+                W2[d, dp] = w2[:, :, :, kd]
+    s1 = tc.PackedConv(W1.reshape(D * Cm, D, 3, 3), torch.zeros(D * Cm, device=DEV))
+    s2 = tc.PackedConv(W2.reshape(D, D * Cm, 3, 3), torch.zeros(D, device=DEV))
+    slope = torch.full((1,), 0.25, device=DEV)
+    xs = [tc.to_c8(torch.randn(1, D, 512, 512, device=DEV)) for _ in range(4)]
+    hs = [tc.conv_tc(x, s1, act=ops.ACT_PRELU, slope=slope) for x in xs]
+    ys = [tc.conv_tc(h, s2) for h in hs]
+    torch.cuda.synchronize()
+    for name, fn in (("s1", lambda i: tc.conv_tc(xs[i], s1, act=ops.ACT_PRELU, slope=slope)), ("s2", lambda i: tc.conv_tc(hs[i], s2))):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            keep = [fn(i) for i in range(4)]
+        g.replay(); torch.cuda.synchronize()
+        best = 1e9
+        for _ in range(4):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1) / 4)
+        pc = s1 if name == "s1" else s2
+        print(f"D={D} {name} BN={pc.BN} {best*1e3:.1f} us", flush=True)
+        del keep, g
