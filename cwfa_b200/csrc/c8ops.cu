@@ -143,7 +143,68 @@ __global__ void __launch_bounds__(256) c8_bn_apply_kernel(const uint4* __restric
         }
     }
 }
+// out[n, d, y, x] = bias[d] + sum_{ky,kx} g[n, (d/8)*72 + (ky*3+kx)*8 + d%8, y+ky-1, x+kx-1]   (zero outside the image).
+// A 3x3 convolution whose per-tap partial products were produced by ONE 1x1 tensor-core convolution (9x fewer
+// shared-memory operand reads than the tap-by-tap form when Cout is tiny and Cin huge): this kernel is the col2im.
+// blockIdx.y = (sample, depth chunk); blockIdx.x strides over rows; threads over columns; 9 x 16-byte loads per output.
+template <bool BF16>
+__global__ void __launch_bounds__(256) c8_col2im3x3_kernel(const uint4* __restrict__ g, const float* __restrict__ bias,
+                                                           uint4* __restrict__ out, int dchunks, int gchunks, int gvalid, int H, int W) {
+    const int dc = blockIdx.y % dchunks, n = blockIdx.y / dchunks;
+    if (dc >= gvalid) {                              // channel-padding chunk of the output: zeros
+        uint4* oz = out + (int64_t)blockIdx.y * H * W;
+        for (int h = blockIdx.x; h < H; h += gridDim.x)
+            for (int w = threadIdx.x; w < W; w += blockDim.x) oz[(int64_t)h * W + w] = make_uint4(0, 0, 0, 0);
+        return;
+    }
+    float b[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) b[j] = bias ? __ldg(bias + dc * 8 + j) : 0.f;
+    const int64_t plane = (int64_t)H * W;
+    const uint4* gp = g + ((int64_t)n * gchunks + (int64_t)dc * 9) * plane;
+    uint4* op = out + (int64_t)blockIdx.y * plane;
+    for (int h = blockIdx.x; h < H; h += gridDim.x) {
+        for (int w = threadIdx.x; w < W; w += blockDim.x) {
+            float acc[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = b[j];
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+                const int hh = h + ky - 1;
+                if (hh < 0 || hh >= H) continue;
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const int ww = w + kx - 1;
+                    if (ww < 0 || ww >= W) continue;
+                    float v[8];
+                    unpack8<BF16>(__ldg(gp + (int64_t)(ky * 3 + kx) * plane + (int64_t)hh * W + ww), v);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[j] += v[j];
+                }
+            }
+            op[(int64_t)h * W + w] = pack8<BF16>(acc);
+        }
+    }
+}
 }  // namespace
+
+extern "C" int cwfa_c8_col2im3x3(const void* g, const float* bias, void* out, int N, int Dp, int Gp, int H, int W,
+                                 int is_bf16, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N <= 0 || Dp <= 0 || (Dp % 8) || (Gp % 8) || Gp < 72 || H <= 0 || W <= 0 || (int64_t)N * (Dp / 8) > 65535) {
+        set_error("c8_col2im3x3: bad shape (needs Gp >= 72, Dp %% 8 == 0)");
+        return CWFA_EINVAL;
+    }
+    const int gvalid = Gp / 72 < Dp / 8 ? Gp / 72 : Dp / 8;      // depth chunks that have partial products; the rest is channel padding
+    const int planes = N * (Dp / 8);
+    int gx = ceil_div(kNumSMs * 8, planes);
+    if (gx > H) gx = H;
+    const int threads = W >= 256 ? 256 : (W >= 128 ? 128 : 64);
+    dim3 grid(gx, planes);
+    if (is_bf16) c8_col2im3x3_kernel<true><<<grid, threads, 0, st>>>((const uint4*)g, bias, (uint4*)out, Dp / 8, Gp / 8, gvalid, H, W);
+    else c8_col2im3x3_kernel<false><<<grid, threads, 0, st>>>((const uint4*)g, bias, (uint4*)out, Dp / 8, Gp / 8, gvalid, H, W);
+    return check_launch("c8_col2im3x3");
+}
 
 extern "C" int cwfa_c8_stats_workspace_floats(int Cp) { return (Cp / 8) * kC8StatBlocks * 16; }
 

@@ -380,7 +380,13 @@ __global__ void __launch_bounds__(WIDE ? 576 : kThreads, WIDE ? 1 : 2) conv_tc_k
             for (int item = blockIdx.x; item < total; item += gridDim.x, advance(pos)) {   // so the next item's operands load during this epilogue
                 const int nblk = pos.nblk, n = pos.n, h0 = pos.ty * 16, w0 = pos.tx * 8 * p.MB;
                 const uint8_t* src = p.w_packed + (size_t)nblk * p.num_kb * T * p.b_bytes;
+                const uint32_t* km = p.kmask + nblk * p.num_kb;
+                uint32_t km_next = __ldg(km);
                 for (int kb = 0; kb < p.num_kb; ++kb) {
+                    uint32_t kmask = km_next;
+                    if (kb + 1 < p.num_kb) km_next = __ldg(km + kb + 1);          // prefetched: off the per-k-block critical path
+                    if (kb == 0 && kmask == 0) kmask = 1u;                        // same rule as the MMA issuer
+                    if (kmask == 0) { src += (size_t)T * p.b_bytes; continue; }   // all-zero weight block: neither operand is loaded
                     mbar_wait(a_empty(sa), pa ^ 1);
                     mbar_expect_tx(a_full(sa), p.a_bytes);
                     tma_load_4d(a_base + sa * p.a_stride, &tmap, a_full(sa), (w0 - pw) * 8, h0 - ph, kb * p.KCc, n);
@@ -419,9 +425,13 @@ __global__ void __launch_bounds__(WIDE ? 576 : kThreads, WIDE ? 1 : 2) conv_tc_k
         tc_fence_after();
         const uint32_t d_base = tmem_base + (uint32_t)(buf * acc_cols);
         uint32_t acc_first = 0u;                                  // first MMA of the item overwrites the accumulator
+        const uint32_t* km = p.kmask + pos.nblk * p.num_kb;
+        uint32_t km_next = __ldg(km);
         for (int kb = 0; kb < p.num_kb; ++kb) {
-            uint32_t kmask = __ldg(p.kmask + pos.nblk * p.num_kb + kb);
+            uint32_t kmask = km_next;
+            if (kb + 1 < p.num_kb) km_next = __ldg(km + kb + 1);
             if (kb == 0 && kmask == 0) kmask = 1u;               // the accumulator must be written at least once per item
+            if (kmask == 0) continue;                            // all-zero weight block: skipped by the producer as well
             mbar_wait(a_full(sa), pa);
             // descriptor low words in 16-byte units; taps advance by one pixel (kw) / one tile row (kh)
             uint32_t a_row = (((a_base + sa * p.a_stride) & 0x3FFFFu) >> 4) | a_lbo_enc;
@@ -445,7 +455,7 @@ __global__ void __launch_bounds__(WIDE ? 576 : kThreads, WIDE ? 1 : 2) conv_tc_k
                         }
                         tc_commit(b_empty(sb));
                     }
-                    if (kmask) acc_first = 1u;
+                    acc_first = 1u;
                     __syncwarp();
                     if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
                 }

@@ -86,7 +86,14 @@ class _CondNet:
                     W1[d, :, dp] = w1[:, 0, :, :, kd]
                     W2[d, dp] = w2[0, :, :, :, kd]
         self.s1 = tc.PackedConv(W1.reshape(D * Cm, D, 3, 3), b1.repeat(D), kind)
-        self.s2 = tc.PackedConv(W2.reshape(D, D * Cm, 3, 3), b2.repeat(D), kind)
+        # second stencil conv (Cin = 32 D, Cout = D): evaluated as ONE 1x1 conv to 9 tap partials per depth + a col2im
+        # sum -- the tap-by-tap form re-reads the 32 D-channel operand tile from shared memory nine times for a tiny N.
+        # n-blocks of 144 channels = 16 output depths: the packer's zero K-block masks skip the hidden depths out of reach.
+        Wg = tc.col2im3x3_weights(W2.reshape(D, D * Cm, 3, 3))
+        gp = tc.pad16(Wg.shape[0])
+        self.s2g = tc.PackedConv(Wg, None, kind, bn=144 if gp % 144 == 0 else gp)
+        self.s2_bias = b2.repeat(D)
+        self.D = D
 
     def __call__(self, v8: tc.C8) -> tc.C8:
         """views (C8) -> LF condition (C8)."""
@@ -95,7 +102,7 @@ class _CondNet:
         res = tc.conv_tc(v8, self.ds)
         out = tc.conv_tc(out, self.c2, act=ops.ACT_PRELU, slope=rb.relu.weight, res=res, res_mode=1)
         hid = tc.conv_tc(out, self.s1, act=ops.ACT_PRELU, slope=rb.conv3d[1].weight)
-        return tc.conv_tc(hid, self.s2)
+        return tc.col2im3x3_c8(tc.conv_tc(hid, self.s2g), self.s2_bias, self.D)
 
 
 class _UNet:

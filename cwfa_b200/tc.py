@@ -184,6 +184,34 @@ def batchnorm_c8(x: C8, gamma, beta, running_mean, running_var, *, batch_stats: 
     return (y, yp) if pool else y
 
 
+def col2im3x3_weights(w: torch.Tensor) -> torch.Tensor:
+    """(Cout, Cin, 3, 3) conv weights -> (9 * ceil8(Cout), Cin, 1, 1) weights of the 1x1 convolution whose output
+    channel ``(co // 8) * 72 + (ky * 3 + kx) * 8 + co % 8`` is the tap-(ky,kx) partial product of output channel co
+    (``col2im3x3_c8`` sums the nine shifted partials)."""
+    Cout, Cin = w.shape[0], w.shape[1]
+    C8n = (Cout + 7) // 8
+    wp = torch.zeros(C8n * 8, Cin, 3, 3, device=w.device, dtype=torch.float32)
+    wp[:Cout] = w.detach().float()
+    # [chunk, j, Cin, tap] -> [chunk, tap, j, Cin]
+    g = wp.view(C8n, 8, Cin, 9).permute(0, 3, 1, 2).reshape(C8n * 72, Cin, 1, 1)
+    return g.contiguous()
+
+
+def col2im3x3_c8(g: C8, bias: Optional[torch.Tensor], C: int) -> C8:
+    """Sums the nine shifted tap partials of ``conv_tc(x, PackedConv(col2im3x3_weights(w)))`` into the 3x3 convolution
+    output (C channels, zero padding) + bias."""
+    Dp = pad16(C)
+    if g.Cp < 9 * ((C + 7) // 8) * 8:
+        raise ValueError("col2im3x3_c8: partial-product tensor too narrow")
+    out = C8.empty(g.N, C, g.H, g.W, g.data.device, g.kind, Dp)
+    b = None
+    if bias is not None:
+        b = torch.zeros(Dp, device=g.data.device, dtype=torch.float32)
+        b[:C] = bias.detach().float()
+    _lib.call("cwfa_c8_col2im3x3", g.data.data_ptr(), _p(b), out.data.data_ptr(), g.N, Dp, g.Cp, g.H, g.W, g.is_bf16, _stream())
+    return out
+
+
 def resblock_tc(x: C8, p3: PackedConv, p1: PackedConv, in_chunk_off: int = 0) -> C8:
     """Fused trunk residual block y = ELU(conv1x1(ELU(conv3x3(x))) + x) for 64 channels (one persistent kernel).
     ``x`` may be a wider C8 tensor; ``in_chunk_off`` selects the 64-channel slice (8 chunks) to read."""

@@ -171,6 +171,13 @@ int cwfa_c8_channel_stats(const void* x, float* stats, float* workspace, int N, 
                           int is_bf16, void* stream);
 int cwfa_c8_bn_apply(const void* x, const float* scale, const float* shift, void* y, void* ypool,
                      int N, int Cp, int H, int W, int is_bf16, void* stream);
+/* col2im of a 3x3 convolution evaluated as ONE 1x1 tensor-core convolution to 9 partial products per output channel
+ * (second depth-stencil conv of the conditioning net, networks.py:221-225,239: Cin = 32*D, Cout = D):
+ * out[n,d,y,x] = bias[d] + sum_{ky,kx} g[n, (d/8)*72 + (ky*3+kx)*8 + d%8, y+ky-1, x+kx-1].  g: C8 with Gp >= 9*Dp channels,
+ * out: C8 with Dp channels (Dp % 8 == 0; 8-channel chunks beyond Gp/72 are channel padding and are written as zeros),
+ * bias: Dp floats or NULL. */
+int cwfa_c8_col2im3x3(const void* g, const float* bias, void* out, int N, int Dp, int Gp, int H, int W,
+                      int is_bf16, void* stream);
 /* Profiling aid: when set (device buffer of 8 uint64 per CTA), conv_tc records globaltimer stamps. */
 int cwfa_tc_set_debug_buffer(void* buf);
 int cwfa_resblock_set_debug_buffer(void* buf);   /* [cta][8 tiles][8 stamps] uint64 */

@@ -142,3 +142,46 @@ def test_conv_transpose_tc_with_skip(N, H, W, cin, cout):
     torch.cuda.synchronize()
     assert rel_l2(y, ref) < 6e-3
     assert rel_l2(y0, ref - skip) < 6e-3
+
+
+@pytest.mark.parametrize("cin,cout,N,H,W,bn", [(96, 12, 2, 20, 24, None), (256, 6, 1, 33, 17, None), (512, 48, 1, 32, 48, 144)])
+def test_conv3x3_as_1x1_plus_col2im(cin, cout, N, H, W, bn):
+    """3x3 conv with huge Cin / tiny Cout evaluated as one 1x1 tensor-core conv to 9 tap partials + col2im
+    (second depth-stencil conv of the conditioning net): equals the direct 3x3 conv; channel padding stays zero."""
+    from cwfa_b200 import tc
+    kind = "bf16"
+    x = _round(seeded_randn((N, cin, H, W), 41), kind)
+    w = _round(seeded_randn((cout, cin, 3, 3), 42, (1.0 / (cin * 9)) ** 0.5), kind)
+    b = seeded_randn((cout,), 43)
+    ref = F.conv2d(x, w, b, padding=1)
+    wg = tc.col2im3x3_weights(w.to(DEV))
+    pc = tc.PackedConv(wg, None, kind, bn=bn)
+    g = tc.conv_tc(tc.to_c8(x.to(DEV), kind), pc)
+    y8 = tc.col2im3x3_c8(g, b.to(DEV), cout)
+    y = tc.from_c8(y8)
+    torch.cuda.synchronize()
+    assert y.shape == ref.shape
+    assert rel_l2(y, ref) < 8e-3
+    if y8.Cp != cout:
+        raw = y8.data.float().view(N, y8.Cp // 8, H, W, 8).permute(0, 1, 4, 2, 3).reshape(N, y8.Cp, H, W)
+        assert float(raw[:, cout:].abs().max()) == 0.0
+
+
+def test_conv_tc_skips_zero_weight_blocks():
+    """Block-banded weights (each 64-channel output block reads only two 64-channel input blocks): the packer marks the
+    all-zero K-blocks and the kernel skips them -- same result as the dense evaluation, incl. an all-zero output block."""
+    from cwfa_b200 import tc
+    kind = "bf16"
+    cin, cout, H, W = 256, 256, 24, 40
+    w = _round(seeded_randn((cout, cin, 3, 3), 51, (1.0 / (128 * 9)) ** 0.5), kind)
+    mask = torch.zeros(cout, cin)
+    for g in range(3):
+        mask[64 * g:64 * g + 64, 64 * g:64 * g + 128] = 1.0       # output block 3 stays entirely zero
+    w = w * mask[:, :, None, None]
+    x = _round(seeded_randn((2, cin, H, W), 52), kind)
+    b = seeded_randn((cout,), 53)
+    ref = F.conv2d(x, w, b, padding=1)
+    y = tc.from_c8(tc.conv_tc(tc.to_c8(x.to(DEV), kind), tc.PackedConv(w.to(DEV), b.to(DEV), kind, bn=64), mb=2))
+    torch.cuda.synchronize()
+    assert rel_l2(y, ref) < 6e-3
+    assert rel_l2(y[:, 192:], ref[:, 192:]) < 6e-3              # bias only
