@@ -93,6 +93,7 @@ class _CondNet:
         gp = tc.pad16(Wg.shape[0])
         self.s2g = tc.PackedConv(Wg, None, kind, bn=144 if gp % 144 == 0 else gp)
         self.s2_bias = b2.repeat(D)
+        self.s2_mb = 1 if self.s2g.BN == 144 else 2       # measured (scripts/bench_stencil.py)
         self.D = D
 
     def __call__(self, v8: tc.C8) -> tc.C8:
@@ -102,7 +103,7 @@ class _CondNet:
         res = tc.conv_tc(v8, self.ds)
         out = tc.conv_tc(out, self.c2, act=ops.ACT_PRELU, slope=rb.relu.weight, res=res, res_mode=1)
         hid = tc.conv_tc(out, self.s1, act=ops.ACT_PRELU, slope=rb.conv3d[1].weight)
-        return tc.col2im3x3_c8(tc.conv_tc(hid, self.s2g), self.s2_bias, self.D)
+        return tc.col2im3x3_c8(tc.conv_tc(hid, self.s2g, mb=self.s2_mb), self.s2_bias, self.D)
 
 
 class _UNet:
