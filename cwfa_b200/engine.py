@@ -92,7 +92,8 @@ class _CondNet:
         Wg = tc.col2im3x3_weights(W2.reshape(D, D * Cm, 3, 3))
         gp = tc.pad16(Wg.shape[0])
         self.s2g = tc.PackedConv(Wg, None, kind, bn=144 if gp % 144 == 0 else gp)
-        self.s2_bias = b2.repeat(D)
+        self.s2_bias = torch.zeros(tc.pad16(D), device=dev, dtype=torch.float32)
+        self.s2_bias[:D] = b2
         self.s2_mb = 1 if self.s2g.BN == 144 else 2       # measured (scripts/bench_stencil.py)
         self.D = D
 

@@ -206,8 +206,11 @@ def col2im3x3_c8(g: C8, bias: Optional[torch.Tensor], C: int) -> C8:
     out = C8.empty(g.N, C, g.H, g.W, g.data.device, g.kind, Dp)
     b = None
     if bias is not None:
-        b = torch.zeros(Dp, device=g.data.device, dtype=torch.float32)
-        b[:C] = bias.detach().float()
+        if bias.numel() == Dp and bias.dtype == torch.float32:
+            b = _ck(bias.detach(), "bias")          # already padded (hot path: no per-call fill kernels)
+        else:
+            b = torch.zeros(Dp, device=g.data.device, dtype=torch.float32)
+            b[:C] = bias.detach().float()
     _lib.call("cwfa_c8_col2im3x3", g.data.data_ptr(), _p(b), out.data.data_ptr(), g.N, Dp, g.Cp, g.H, g.W, g.is_bf16, _stream())
     return out
 
