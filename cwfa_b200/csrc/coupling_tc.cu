@@ -140,7 +140,6 @@ __global__ void __launch_bounds__(kThreads, 1) coupling_tc_kernel(const __grid_c
         const int m = q * 32 + lane;
         const int gpc = (ch + 7) >> 3;
         const int ngroups = 2 * gpc;
-        float* red = reinterpret_cast<float*>(smem + 256);
         for (int i = 0; i < my_tiles; ++i) {
             const int b = i & 1, ph = (i >> 1) & 1;
             const int t = blockIdx.x + i * gridDim.x;
@@ -226,16 +225,14 @@ __global__ void __launch_bounds__(kThreads, 1) coupling_tc_kernel(const __grid_c
             }
             tc_fence_before();
             mbar_arrive(acc_empty(b));
-            // per-tile partial sums (fixed order => reproducible): warp shuffle -> smem -> one thread
+            // one partial per (tile, epilogue warp), summed in a fixed order by cwfa_coupling_finalize (reproducible);
+            // no CTA-wide barrier: the 16 epilogue warps stay decoupled
             sum_s = warp_sum(sum_s);
             sum_q = warp_sum(sum_q);
-            if (lane == 0) { red[(b * 16 + warp - 2) * 2] = sum_s; red[(b * 16 + warp - 2) * 2 + 1] = sum_q; }
-            asm volatile("bar.sync 1, 512;" ::: "memory");
-            if (threadIdx.x == 64) {
-                float a = 0.f, c = 0.f;
-                for (int k = 0; k < 16; ++k) { a += red[(b * 16 + k) * 2]; c += red[(b * 16 + k) * 2 + 1]; }
-                p.ws[(size_t)t * 2] = INV ? -a : a;
-                p.ws[(size_t)t * 2 + 1] = c;
+            if (lane == 0) {
+                float* w = p.ws + ((size_t)t * 16 + (warp - 2)) * 2;
+                w[0] = INV ? -sum_s : sum_s;
+                w[1] = sum_q;
             }
         }
     }
@@ -248,7 +245,8 @@ __global__ void __launch_bounds__(kThreads, 1) coupling_tc_kernel(const __grid_c
 }
 }  // namespace
 
-extern "C" int cwfa_coupling_tc_tiles(int H, int W) { return ceil_div(W, kTW) * ceil_div(H, kTH); }
+// Partial sums per sample that cwfa_coupling_tc writes: one per (16x16-pixel tile, epilogue warp).
+extern "C" int cwfa_coupling_tc_tiles(int H, int W) { return ceil_div(W, kTW) * ceil_div(H, kTH) * 16; }
 
 // Same contract as cwfa_conv_tc_coupling, for the CWFA sub-network shape: 3x3 conv from 64 hidden channels to
 // Cout_p <= 96 (= one N block), ch <= 48.  workspace: 2 * N * cwfa_coupling_tc_tiles(H, W) floats, to be reduced with

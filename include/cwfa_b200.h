@@ -197,7 +197,8 @@ int cwfa_coupling_finalize(const float* workspace, float* logdet, float* sumsq, 
                            int accumulate, void* stream);
 /* Persistent variant of cwfa_conv_tc_coupling for the CWFA sub-network shape (3x3 conv from 64 hidden channels to
  * Cout_p <= 96 in one N block, ch <= 48): weights resident in shared memory, accumulators double buffered in TMEM,
- * 16 epilogue warps.  workspace: 2 * N * cwfa_coupling_tc_tiles(H, W) floats (reduce with cwfa_coupling_finalize). */
+ * 16 epilogue warps.  workspace: 2 * N * cwfa_coupling_tc_tiles(H, W) floats (one (sum s, sum y^2) partial per tile and
+ * epilogue warp; reduce with cwfa_coupling_finalize(..., tiles = cwfa_coupling_tc_tiles(H, W), ...)). */
 int cwfa_coupling_tc_tiles(int H, int W);
 int cwfa_coupling_tc(const void* b_c8, const void* w_packed, const float* bias, int N, int H, int W, int Cout,
                      int Cout_p, const float* cx, float* cy, const float* ct, float t_scale, const int32_t* perm,

@@ -185,3 +185,58 @@ def test_conv_tc_skips_zero_weight_blocks():
     torch.cuda.synchronize()
     assert rel_l2(y, ref) < 6e-3
     assert rel_l2(y[:, 192:], ref[:, 192:]) < 6e-3              # bias only
+
+
+def _coupling_reference(a, x, t_ext, t_scale, ch, inverse, clamp=2.0, k=0.636):
+    s = clamp * k * torch.atan(a[:, :ch])                 # coupling_layers.py:490-500 (a is already divided by nothing: CWFA clamps via atan)
+    t = t_scale * t_ext if t_ext is not None else a[:, ch:2 * ch]
+    if inverse:
+        y = (x - t) * torch.exp(-s)
+        j = -s.sum(dim=(1, 2, 3))
+    else:
+        y = torch.exp(s) * x + t
+        j = s.sum(dim=(1, 2, 3))
+    return y, j
+
+
+@pytest.mark.parametrize("ch,axis,inverse,ext,zero_x", [
+    (48, 1, True, False, False), (48, 3, True, False, False), (24, 2, False, False, False), (12, 1, False, True, False),
+    (6, 0, True, True, True), (6, 3, False, False, False), (48, 0, True, False, True), (24, 1, True, True, False)])
+@pytest.mark.parametrize("persistent", [True, False])
+def test_fused_coupling_conv_vs_reference(ch, axis, inverse, ext, zero_x, persistent):
+    """Last sub-network conv (64 -> 2 ch, 3x3) + affine coupling + log-det / sum y^2 + preceding permutation (gather on x)
+    in ONE kernel (persistent coupling_tc and the general conv_tc<COUPLING>) vs conv2d + coupling_layers.py:490-500 in torch."""
+    from cwfa_b200 import tc
+    kind, N, H, W = "bf16", 2, 40, 56
+    cout = ch if ext else 2 * ch
+    b = _round(seeded_randn((N, 64, H, W), 61), kind)
+    w = _round(seeded_randn((cout, 64, 3, 3), 62, 0.04), kind)
+    bias = seeded_randn((cout,), 63, 0.1)
+    a = F.conv2d(b, w, bias, padding=1)
+    x = None if zero_x else seeded_randn((N, ch, H, W), 64)
+    t_ext = seeded_randn((N, ch, H, W), 65, 0.3) if ext else None
+    perm = None
+    xin = torch.zeros(N, ch, H, W) if x is None else x
+    if axis and x is not None:
+        n_ax = {1: ch, 2: H, 3: W}[axis]
+        perm = torch.from_numpy(__import__("numpy").random.RandomState(7).permutation(n_ax)).long()
+        xin = xin.index_select(axis, perm)                 # the permutation preceding the coupling (fixed_transforms.py:37-41)
+    y_ref, j_ref = _coupling_reference(a, xin, t_ext, -0.5 ** 0.5 if ext else 1.0, ch, inverse)
+    pc = tc.PackedConv(w.to(DEV), bias.to(DEV), kind, bn=tc.pad16(cout))
+    logdet = torch.full((N,), 3.0, device=DEV)
+    sumsq = torch.zeros(N, device=DEV)
+    y = tc.conv_tc_coupling(tc.to_c8(b.to(DEV), kind), pc, None if x is None else x.to(DEV), ch=ch, inverse=inverse,
+                            t_ext=None if t_ext is None else t_ext.to(DEV), t_scale=-0.5 ** 0.5 if ext else 1.0,
+                            perm=None if perm is None else perm.to(DEV).to(torch.int32), perm_axis=axis if perm is not None else 0,
+                            logdet=logdet, sumsq=sumsq, accumulate=True, persistent=persistent)
+    torch.cuda.synchronize()
+    assert rel_l2(y, y_ref) < 2e-5 * 50                     # fp32 accumulation-order + fast atan/exp differences only
+    assert torch.allclose(logdet.cpu() - 3.0, j_ref, rtol=2e-4, atol=2e-2)
+    assert torch.allclose(sumsq.cpu(), (y_ref.double() ** 2).sum(dim=(1, 2, 3)).float(), rtol=2e-3)
+    # bit-reproducible reductions
+    logdet2 = torch.full((N,), 3.0, device=DEV)
+    tc.conv_tc_coupling(tc.to_c8(b.to(DEV), kind), pc, None if x is None else x.to(DEV), ch=ch, inverse=inverse,
+                        t_ext=None if t_ext is None else t_ext.to(DEV), t_scale=-0.5 ** 0.5 if ext else 1.0,
+                        perm=None if perm is None else perm.to(DEV).to(torch.int32), perm_axis=axis if perm is not None else 0,
+                        logdet=logdet2, persistent=persistent)
+    assert torch.equal(logdet, logdet2)
