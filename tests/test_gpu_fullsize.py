@@ -21,20 +21,32 @@ def full():
     return model.to(DEV), om, views, mvs
 
 
-def test_full_inverse_engine_vs_cpu_oracle(full):
+_REF = {}
+
+
+def _oracle_inverse(om, views, mvs):
+    """The fp32 CPU oracle of the full frame (tens of seconds): computed once per session."""
+    if "inv" not in _REF:
+        _REF["inv"] = O.reconstruct(om, views, mvs, bn_mode="batch", return_all=True)
+    return _REF["inv"]
+
+
+# tolerances on the per-level rel-L2 vs the fp32 oracle: half-precision operand rounding accumulated through ~40 convs
+@pytest.mark.parametrize("kind,tol", [("bf16", 2e-2), ("fp16", 4e-3)])
+def test_full_inverse_engine_vs_cpu_oracle(full, kind, tol):
     from cwfa_b200.engine import CWFAEngine
     model, om, views, mvs = full
     torch.set_num_threads(max(1, torch.get_num_threads()))
-    ref, ref_j = O.reconstruct(om, views, mvs, bn_mode="batch", return_all=True)
-    eng = CWFAEngine(model, "bf16")
+    ref, ref_j = _oracle_inverse(om, views, mvs)
+    eng = CWFAEngine(model, kind)
     outs, jacs = eng.reconstruct(views.to(DEV), [m.to(DEV) for m in mvs], return_all=True)
     rep = {n: (rel_l2(outs[n], ref[n]), max_abs(outs[n], ref[n])) for n in sorted(ref)}
-    print("full 512x512x96 inverse, bf16 engine vs fp32 CPU oracle (rel-L2, max-abs) per level:",
+    print(f"full 512x512x96 inverse, {kind} engine vs fp32 CPU oracle (rel-L2, max-abs) per level:",
           {k: (f"{a:.2e}", f"{b:.2e}") for k, (a, b) in rep.items()})
-    assert all(a < 2e-2 for a, _ in rep.values()), rep
+    assert all(a < tol for a, _ in rep.values()), rep
     for n in ref_j:
         r = float(ref_j[n][0])
-        assert abs(float(jacs[n][0]) - r) < 2e-2 * max(1.0, abs(r)), (n, float(jacs[n][0]), r)
+        assert abs(float(jacs[n][0]) - r) < tol * max(1.0, abs(r)), (n, float(jacs[n][0]), r)
     assert tuple(outs[0].shape) == (1, 96, 512, 512)
     g = eng.reconstruct_graphed(views.to(DEV), [m.to(DEV) for m in mvs])
     assert torch.equal(g, outs[0]), "CUDA-graph replay (parallel branches) must equal the eager engine bit for bit"
