@@ -125,44 +125,42 @@ extern "C" int cwfa_haar1d_inv(const float* lo, const float* hi, float* x, int B
 // K1b: FrEIA 2-D Haar.  One thread per 2x2 input block (one output pixel of 4 wavelets).
 // ------------------------------------------------------------------------------------------
 template <bool UP>
-__global__ void __launch_bounds__(256) haar2d_kernel(const float* __restrict__ src, float* __restrict__ dst, int B,
-                                                     int C, int H2, int W2, int by_wavelet, float fac) {
-    // Fine grid is (B,C,2*H2,2*W2); coarse grid is (B,4C,H2,W2).
-    const int64_t total = (int64_t)B * C * H2 * W2;
-    const int64_t plane = (int64_t)H2 * W2;
+__global__ void __launch_bounds__(256) haar2d_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int H2,
+                                                     int W2, int by_wavelet, float fac) {
+    // Fine grid is (B,C,2*H2,2*W2); coarse grid is (B,4C,H2,W2).  blockIdx.y = (sample, channel) plane of the fine
+    // tensor, blockIdx.x strides over coarse rows, threads over coarse columns: no index divisions.
+    const int c = blockIdx.y % C;
+    const int64_t b4c = (int64_t)(blockIdx.y - c) * 4;            // b * 4C
+    const int64_t cplane = (int64_t)H2 * W2;
     const int W = 2 * W2;
-#pragma unroll 4
-    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
-         idx += (int64_t)gridDim.x * blockDim.x) {
-        const int w2 = (int)(idx % W2);
-        const int h2 = (int)((idx / W2) % H2);
-        const int c = (int)((idx / plane) % C);
-        const int b = (int)(idx / (plane * C));
-        const int64_t fine = (((int64_t)b * C + c) * (2 * H2) + 2 * h2) * W + 2 * w2;
-        int64_t co[4];
+    const float* fsrc = src + (int64_t)blockIdx.y * 4 * cplane;   // fine plane (UP: unused)
+    float* fdst = dst + (int64_t)blockIdx.y * 4 * cplane;
+    int64_t cbase[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int ch = by_wavelet ? k * C + c : 4 * c + k;
-            co[k] = (((int64_t)b * 4 * C + ch) * H2 + h2) * W2 + w2;
-        }
-        if constexpr (!UP) {
-            const float2 r0 = __ldg(reinterpret_cast<const float2*>(src + fine));
-            const float2 r1 = __ldg(reinterpret_cast<const float2*>(src + fine + W));
-            const float a = r0.x, bb = r0.y, cc = r1.x, d = r1.y;
-            dst[co[0]] = fac * (a + bb + cc + d);
-            dst[co[1]] = fac * (a - bb + cc - d);
-            dst[co[2]] = fac * (a + bb - cc - d);
-            dst[co[3]] = fac * (a - bb - cc + d);
-        } else {
-            const float y0 = fac * __ldg(src + co[0]), y1 = fac * __ldg(src + co[1]);
-            const float y2 = fac * __ldg(src + co[2]), y3 = fac * __ldg(src + co[3]);
-            float2 r0, r1;
-            r0.x = y0 + y1 + y2 + y3;
-            r0.y = y0 - y1 + y2 - y3;
-            r1.x = y0 + y1 - y2 - y3;
-            r1.y = y0 - y1 - y2 + y3;
-            *reinterpret_cast<float2*>(dst + fine) = r0;
-            *reinterpret_cast<float2*>(dst + fine + W) = r1;
+    for (int k = 0; k < 4; ++k) cbase[k] = (b4c + (by_wavelet ? k * C + c : 4 * c + k)) * cplane;
+    for (int h2 = blockIdx.x; h2 < H2; h2 += gridDim.x) {
+        const int64_t frow = (int64_t)(2 * h2) * W;
+        const int64_t crow = (int64_t)h2 * W2;
+        for (int w2 = threadIdx.x; w2 < W2; w2 += blockDim.x) {
+            if constexpr (!UP) {
+                const float2 r0 = __ldg(reinterpret_cast<const float2*>(fsrc + frow + 2 * w2));
+                const float2 r1 = __ldg(reinterpret_cast<const float2*>(fsrc + frow + W + 2 * w2));
+                const float a = r0.x, bb = r0.y, cc = r1.x, d = r1.y;
+                dst[cbase[0] + crow + w2] = fac * (a + bb + cc + d);
+                dst[cbase[1] + crow + w2] = fac * (a - bb + cc - d);
+                dst[cbase[2] + crow + w2] = fac * (a + bb - cc - d);
+                dst[cbase[3] + crow + w2] = fac * (a - bb - cc + d);
+            } else {
+                const float y0 = fac * __ldg(src + cbase[0] + crow + w2), y1 = fac * __ldg(src + cbase[1] + crow + w2);
+                const float y2 = fac * __ldg(src + cbase[2] + crow + w2), y3 = fac * __ldg(src + cbase[3] + crow + w2);
+                float2 r0, r1;
+                r0.x = y0 + y1 + y2 + y3;
+                r0.y = y0 - y1 + y2 - y3;
+                r1.x = y0 + y1 - y2 - y3;
+                r1.y = y0 - y1 - y2 + y3;
+                *reinterpret_cast<float2*>(fdst + frow + 2 * w2) = r0;
+                *reinterpret_cast<float2*>(fdst + frow + W + 2 * w2) = r1;
+            }
         }
     }
 }
@@ -170,15 +168,18 @@ __global__ void __launch_bounds__(256) haar2d_kernel(const float* __restrict__ s
 static int haar2d_launch(bool up, const float* src, float* dst, int B, int C, int H, int W, int obw, float fac,
                          cudaStream_t st) {
     // (C,H,W) always describe the FINE tensor.
-    if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || (H & 1) || (W & 1)) {
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || (H & 1) || (W & 1) || (int64_t)B * C > 65535) {
         set_error("haar2d: H and W must be even (got %dx%d)", H, W);
         return CWFA_EINVAL;
     }
-    const int64_t total = (int64_t)B * C * (H / 2) * (W / 2);
-    int blocks = (int)((total + 255) / 256);
-    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
-    if (up) haar2d_kernel<true><<<blocks, 256, 0, st>>>(src, dst, B, C, H / 2, W / 2, obw, fac);
-    else haar2d_kernel<false><<<blocks, 256, 0, st>>>(src, dst, B, C, H / 2, W / 2, obw, fac);
+    const int planes = B * C, H2 = H / 2, W2 = W / 2;
+    int gx = ceil_div(kNumSMs * 8, planes);
+    if (gx > H2) gx = H2;
+    if (gx < 1) gx = 1;
+    const int threads = W2 >= 256 ? 256 : (W2 >= 128 ? 128 : 64);
+    dim3 grid(gx, planes);
+    if (up) haar2d_kernel<true><<<grid, threads, 0, st>>>(src, dst, C, H2, W2, obw, fac);
+    else haar2d_kernel<false><<<grid, threads, 0, st>>>(src, dst, C, H2, W2, obw, fac);
     return check_launch("haar2d");
 }
 extern "C" int cwfa_haar2d_down(const float* x, float* y, int B, int C, int H, int W, int obw, float fac,
@@ -193,28 +194,41 @@ extern "C" int cwfa_haar2d_up(const float* y, float* x, int B, int C, int H, int
 // ------------------------------------------------------------------------------------------
 // K4: permutations (gather along one axis)
 // ------------------------------------------------------------------------------------------
+// blockIdx.y = (sample, channel) plane, blockIdx.x strides over rows, threads over (vectors of) columns: no index
+// divisions.  AXIS 1 / 2 copy whole rows from the permuted plane / row with 16-byte accesses; AXIS 3 stages the source
+// row in shared memory (coalesced read) and gathers from there (coalesced write).
 template <int AXIS, int VEC>
 __global__ void __launch_bounds__(256) permute_kernel(const float* __restrict__ x, float* __restrict__ y,
-                                                      const int32_t* __restrict__ perm, int B, int C, int H, int W) {
-    const int Wv = W / VEC;
-    const int64_t total = (int64_t)B * C * H * Wv;
-#pragma unroll 4
-    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
-         idx += (int64_t)gridDim.x * blockDim.x) {
-        const int w = (int)(idx % Wv) * VEC;
-        const int h = (int)((idx / Wv) % H);
-        const int c = (int)((idx / ((int64_t)Wv * H)) % C);
-        const int b = (int)(idx / ((int64_t)Wv * H * C));
-        int sc = c, sh = h, sw = w;
-        if (AXIS == 1) sc = __ldg(perm + c);
-        if (AXIS == 2) sh = __ldg(perm + h);
-        if (AXIS == 3) sw = __ldg(perm + w);
-        const int64_t so = (((int64_t)b * C + sc) * H + sh) * W + sw;
-        const int64_t dofs = (((int64_t)b * C + c) * H + h) * W + w;
-        if constexpr (VEC == 4) {
-            *reinterpret_cast<float4*>(y + dofs) = __ldg(reinterpret_cast<const float4*>(x + so));
-        } else {
-            y[dofs] = __ldg(x + so);
+                                                      const int32_t* __restrict__ perm, int C, int H, int W) {
+    extern __shared__ float s_row[];               // AXIS 3: W floats (source row) + W ints (perm)
+    const int c = blockIdx.y % C;
+    const int64_t plane = (int64_t)H * W;
+    const int64_t splane = (AXIS == 1) ? ((int64_t)(blockIdx.y - c) + __ldg(perm + c)) * plane : (int64_t)blockIdx.y * plane;
+    const float* xp = x + splane;
+    float* yp = y + (int64_t)blockIdx.y * plane;
+    if constexpr (AXIS == 3) {
+        // one row per warp (private shared-memory slice, warp-level syncs only); perm table shared by the block
+        const int nw = blockDim.x >> 5, wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        int* s_perm = reinterpret_cast<int*>(s_row + (size_t)nw * W);
+        for (int w = threadIdx.x; w < W; w += blockDim.x) s_perm[w] = __ldg(perm + w);
+        __syncthreads();
+        float* row = s_row + (size_t)wid * W;
+        for (int h = blockIdx.x * nw + wid; h < H; h += gridDim.x * nw) {
+            for (int w = lane; w < W; w += 32) row[w] = __ldg(xp + (int64_t)h * W + w);
+            __syncwarp();
+            for (int w = lane; w < W; w += 32) yp[(int64_t)h * W + w] = row[s_perm[w]];
+            __syncwarp();
+        }
+    } else {
+        const int Wv = W / VEC;
+        for (int h = blockIdx.x; h < H; h += gridDim.x) {
+            const int sh = (AXIS == 2) ? __ldg(perm + h) : h;
+            const float* xr = xp + (int64_t)sh * W;
+            float* yr = yp + (int64_t)h * W;
+            for (int w = threadIdx.x; w < Wv; w += blockDim.x) {
+                if constexpr (VEC == 4) reinterpret_cast<float4*>(yr)[w] = __ldg(reinterpret_cast<const float4*>(xr) + w);
+                else yr[w] = __ldg(xr + w);
+            }
         }
     }
 }
@@ -222,19 +236,27 @@ __global__ void __launch_bounds__(256) permute_kernel(const float* __restrict__ 
 extern "C" int cwfa_permute(const float* x, float* y, const int32_t* perm, int axis, int B, int C, int H, int W,
                             void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
-    if (axis < 1 || axis > 3 || B <= 0 || C <= 0 || H <= 0 || W <= 0) { set_error("permute: bad args"); return CWFA_EINVAL; }
+    if (axis < 1 || axis > 3 || B <= 0 || C <= 0 || H <= 0 || W <= 0 || (int64_t)B * C > 65535 || W > 8192) {
+        set_error("permute: bad args");
+        return CWFA_EINVAL;
+    }
     const bool vec = axis != 3 && (W % 4 == 0) && aligned16(x) && aligned16(y);
-    const int64_t total = (int64_t)B * C * H * (vec ? W / 4 : W);
-    int blocks = (int)((total + 255) / 256);
-    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    const int planes = B * C;
+    int gx = ceil_div(kNumSMs * 8, planes);
+    if (gx > H) gx = H;
+    if (gx < 1) gx = 1;
+    const int cols = vec ? W / 4 : W;
+    const int threads = cols >= 256 ? 256 : (cols >= 128 ? 128 : 64);
+    dim3 grid(gx, planes);
     if (axis == 1) {
-        if (vec) permute_kernel<1, 4><<<blocks, 256, 0, st>>>(x, y, perm, B, C, H, W);
-        else permute_kernel<1, 1><<<blocks, 256, 0, st>>>(x, y, perm, B, C, H, W);
+        if (vec) permute_kernel<1, 4><<<grid, threads, 0, st>>>(x, y, perm, C, H, W);
+        else permute_kernel<1, 1><<<grid, threads, 0, st>>>(x, y, perm, C, H, W);
     } else if (axis == 2) {
-        if (vec) permute_kernel<2, 4><<<blocks, 256, 0, st>>>(x, y, perm, B, C, H, W);
-        else permute_kernel<2, 1><<<blocks, 256, 0, st>>>(x, y, perm, B, C, H, W);
+        if (vec) permute_kernel<2, 4><<<grid, threads, 0, st>>>(x, y, perm, C, H, W);
+        else permute_kernel<2, 1><<<grid, threads, 0, st>>>(x, y, perm, C, H, W);
     } else {
-        permute_kernel<3, 1><<<blocks, 256, 0, st>>>(x, y, perm, B, C, H, W);
+        dim3 grid3(ceil_div(gx, 8) > 0 ? ceil_div(gx, 8) : 1, planes);
+        permute_kernel<3, 1><<<grid3, 256, (size_t)W * 4 * 9, st>>>(x, y, perm, C, H, W);
     }
     return check_launch("permute");
 }
@@ -594,39 +616,49 @@ extern "C" int cwfa_attention_gate_f32(float* x, const float* m, const float* v,
 // For lenslet n with centre (cy,cx): lower = max(c - S/2, 0), upper = min(c + S/2, image size); the patch is written
 // bottom/right aligned into the S x S view (reference quirk), the rest of the view is zero (then normalised too).
 // ------------------------------------------------------------------------------------------
+// blockIdx.y = (sample, lenslet): the window geometry is computed once per block; blockIdx.x strides over view rows,
+// threads over view columns (coalesced 4-byte reads of the window row, coalesced writes) -- no index divisions.
 template <typename TIn>
 __global__ void __launch_bounds__(256) extract_views_kernel(const TIn* __restrict__ img, const int32_t* __restrict__ coords,
-                                                            float* __restrict__ out, int B, int Hi, int Wi, int L, int SH, int SW,
+                                                            float* __restrict__ out, int Hi, int Wi, int L, int SH, int SW,
                                                             float mean, float stdv, int normalise) {
-    const int64_t total = (int64_t)B * L * SH * SW;
-#pragma unroll 4
-    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-        const int j = (int)(idx % SW);
-        const int i = (int)((idx / SW) % SH);
-        const int n = (int)((idx / ((int64_t)SW * SH)) % L);
-        const int b = (int)(idx / ((int64_t)SW * SH * L));
-        const int cy = __ldg(coords + 2 * n), cx = __ldg(coords + 2 * n + 1);
-        const int ly = max(cy - SH / 2, 0), lx = max(cx - SW / 2, 0);
-        const int uy = min(cy + SH / 2, Hi), ux = min(cx + SW / 2, Wi);
-        const int ph = max(uy - ly, 0), pw = max(ux - lx, 0);
-        float v = 0.f;
-        const int ii = i - (SH - ph), jj = j - (SW - pw);
-        if (ii >= 0 && jj >= 0 && ph > 0 && pw > 0) v = (float)img[((int64_t)b * Hi + ly + ii) * Wi + lx + jj];
-        out[idx] = normalise ? (v - mean) / stdv : v;
+    const int n = blockIdx.y % L, b = blockIdx.y / L;
+    const int cy = __ldg(coords + 2 * n), cx = __ldg(coords + 2 * n + 1);
+    const int ly = max(cy - SH / 2, 0), lx = max(cx - SW / 2, 0);
+    const int uy = min(cy + SH / 2, Hi), ux = min(cx + SW / 2, Wi);
+    const int ph = max(uy - ly, 0), pw = max(ux - lx, 0);
+    const bool any = ph > 0 && pw > 0;
+    const float zero_v = normalise ? (0.f - mean) / stdv : 0.f;
+    const TIn* ib = img + (int64_t)b * Hi * Wi;
+    float* ob = out + (int64_t)blockIdx.y * SH * SW;
+    for (int i = blockIdx.x; i < SH; i += gridDim.x) {
+        const int ii = i - (SH - ph);
+        const TIn* irow = ib + (int64_t)(ly + ii) * Wi + lx - (SW - pw);
+        float* orow = ob + (int64_t)i * SW;
+        for (int j = threadIdx.x; j < SW; j += blockDim.x) {
+            float v = zero_v;
+            if (any && ii >= 0 && j >= SW - pw) {
+                const float r = (float)irow[j];
+                v = normalise ? (r - mean) / stdv : r;
+            }
+            orow[j] = v;
+        }
     }
 }
 extern "C" int cwfa_extract_views(const void* image, int image_is_half, const int32_t* coords, float* out, int B, int Hi,
                                   int Wi, int L, int SH, int SW, float mean, float stdv, int normalise, void* stream) {
-    if (B <= 0 || Hi <= 0 || Wi <= 0 || L <= 0 || SH <= 0 || SW <= 0 || (normalise && stdv == 0.f)) {
+    if (B <= 0 || Hi <= 0 || Wi <= 0 || L <= 0 || SH <= 0 || SW <= 0 || (normalise && stdv == 0.f) || (int64_t)B * L > 65535) {
         set_error("extract_views: bad arguments");
         return CWFA_EINVAL;
     }
-    const int64_t total = (int64_t)B * L * SH * SW;
-    int blocks = (int)((total + 255) / 256);
-    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    int gx = ceil_div(kNumSMs * 8, B * L);
+    if (gx > SH) gx = SH;
+    if (gx < 1) gx = 1;
+    const int threads = SW >= 256 ? 256 : (SW >= 128 ? 128 : 64);
+    dim3 grid(gx, B * L);
     if (image_is_half)
-        extract_views_kernel<__half><<<blocks, 256, 0, (cudaStream_t)stream>>>((const __half*)image, coords, out, B, Hi, Wi, L, SH, SW, mean, stdv, normalise);
+        extract_views_kernel<__half><<<grid, threads, 0, (cudaStream_t)stream>>>((const __half*)image, coords, out, Hi, Wi, L, SH, SW, mean, stdv, normalise);
     else
-        extract_views_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>((const float*)image, coords, out, B, Hi, Wi, L, SH, SW, mean, stdv, normalise);
+        extract_views_kernel<float><<<grid, threads, 0, (cudaStream_t)stream>>>((const float*)image, coords, out, Hi, Wi, L, SH, SW, mean, stdv, normalise);
     return check_launch("extract_views");
 }
