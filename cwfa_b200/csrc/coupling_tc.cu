@@ -12,11 +12,10 @@ using namespace cwfa;
 using namespace cwfa::tcx;
 
 namespace {
-constexpr int kChunks = 8, kCin = 64;
+constexpr int kChunks = 8;                                   // 64 hidden channels = 8 chunks
 constexpr int kTH = 16, kTW = 16, kBH = 18, kBW = 18;
 constexpr uint32_t kA1Bytes = kChunks * kBH * kBW * 16;      // 41472
 constexpr int kMaxBN = 96;
-constexpr uint32_t kWMax = 9 * kChunks * kMaxBN * 16;         // 110592
 constexpr uint32_t kHeader = 2048;
 constexpr uint32_t kOffW = kHeader;       // weights (9*8*BN*16 bytes), then the A ring (2..4 stages, sized by the launcher)
 constexpr int kMaxAStages = 4;   // barrier slots; the launcher uses at most 3 stages (measured: 2..4 are within noise)
