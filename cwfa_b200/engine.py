@@ -249,11 +249,12 @@ class CWFAEngine:
                                    t_ext=mean_vol if first else None, t_scale=(-1.0 / math.sqrt(2)) if first else 1.0,
                                    perm=perm, perm_axis=axis, logdet=logdet, sumsq=sumsq)
 
-    def _level_detail_inverse(self, n, v8, mean_vol):
-        """Detail half ``hi`` of level n in the inverse direction at z = 0 (INN_z_temperature = 0,
-        CWFA.py:906-907: z is never materialised) and its log-det.  Independent of the other levels."""
+    def _level_detail_inverse(self, n, v8, mean_vol, z=None):
+        """Detail half ``hi`` of level n in the inverse direction and its log-det.  Independent of the other levels.
+        ``z`` None = zeros (INN_z_temperature = 0, CWFA.py:906-907: z is never materialised); otherwise the latent
+        sample (B, ch, H, W) of this level (``sample_z_truncated``, CWFA.py:47-64)."""
         items = self._trunks(n, v8)
-        hi, pending = None, None
+        hi, pending = z, None
         jac = torch.zeros(v8.N, device=v8.data.device, dtype=torch.float32)
         for item in reversed(items):
             if item[0] == "cat":
@@ -267,8 +268,8 @@ class CWFAEngine:
 
     @torch.no_grad()
     def reconstruct(self, views: torch.Tensor, mean_vols: Sequence[Optional[torch.Tensor]], return_all: bool = False,
-                    _side_streams=None):
-        """Inverse reconstruction (CWFA.py:865-924) at z = 0.
+                    _side_streams=None, zs: Optional[Sequence[Optional[torch.Tensor]]] = None):
+        """Inverse reconstruction (CWFA.py:865-924); z = 0 unless ``zs[n]`` gives level n's latent sample.
 
         The LRNN and the coupling coefficients of every level depend only on the views / mean volumes, not on
         each other, so under CUDA-graph capture they are issued on side streams (``_side_streams``) and become
@@ -276,7 +277,7 @@ class CWFAEngine:
         L1 = self.model.n_levels
         v8 = tc.to_c8(views, self.kind)
         mv_last = mean_vols[L1] if len(mean_vols) > L1 else None
-        jobs = [lambda: self.lrnn(v8, mv_last)] + [(lambda n=n: self._level_detail_inverse(n, v8, mean_vols[n])) for n in range(L1 - 1, -1, -1)]
+        jobs = [lambda: self.lrnn(v8, mv_last)] + [(lambda n=n: self._level_detail_inverse(n, v8, mean_vols[n], None if zs is None else zs[n])) for n in range(L1 - 1, -1, -1)]
         if _side_streams:
             main = torch.cuda.current_stream()
             fork = torch.cuda.Event()

@@ -112,3 +112,21 @@ def test_streaming_host_api_matches_engine(golden_tiny, model):
         assert torch.equal(o, ref.cpu()), "streamed frames must equal the one-by-one result bit for bit"
     one = eng.reconstruct_host(frames[2], mv)
     assert torch.equal(one, outs[2])
+
+
+def test_engine_inverse_with_latent_samples(golden_tiny, model):
+    """Temperature > 0: the engine's inverse with explicit latent samples z (CWFA.py:906-912) against the fp32 module
+    path of the same model; z enters through the final PermuteRandom^-1 and the gather of the last coupling."""
+    from cwfa_b200.engine import CWFAEngine
+    views, mvs = tiny_inputs(golden_tiny)
+    views, mvs = views.to(DEV), [m.to(DEV) for m in mvs]
+    zs = [0.7 * seeded_randn((1,) + tuple(model.conv_inn[n].global_out_shapes[0]), 70 + n).to(DEV) for n in range(model.n_levels)]
+    ref, ref_j = model.reconstruct(views, mvs, zs=zs, return_all=True)
+    out0 = model.reconstruct(views, mvs)
+    eng = CWFAEngine(model, "fp16")
+    outs, jacs = eng.reconstruct(views, mvs, return_all=True, zs=zs)
+    for n in ref:
+        assert rel_l2(outs[n], ref[n]) < 5e-3, (n, rel_l2(outs[n], ref[n]))
+    for n in ref_j:
+        assert abs(float(jacs[n][0]) - float(ref_j[n][0])) < 5e-3 * max(1.0, abs(float(ref_j[n][0])))
+    assert rel_l2(ref[0], out0) > 1e-2          # the samples matter
