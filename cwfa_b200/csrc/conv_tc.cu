@@ -668,8 +668,10 @@ __global__ void __launch_bounds__(WIDE ? 576 : kThreads, WIDE ? 1 : 2) conv_tc_k
             base_off = ((size_t)n * p.Cout + cg0) * plane;
             cstride = 0;
         } else if (p.out_mode == 2) {
-            ij = cg0 / p.Cout_p;                     // BN divides Cout_p: one sub-pixel (i,j) per n-block
-            const int co0 = cg0 - ij * p.Cout_p;
+            // n-block = (row sub-pixel i, channel block of BN/2); columns [0,BN/2) -> j = 0, [BN/2,BN) -> j = 1
+            const int nbi = 2 * p.Cout_p / p.BN;
+            ij = nblk / nbi;                         // i
+            const int co0 = (nblk - ij * nbi) * (p.BN >> 1);
             base_off = (((size_t)n * (p.Cout_p >> 3) + (co0 >> 3)) * plane * 4) * 16;
             cstride = plane32 * 64;
         } else {
@@ -683,8 +685,12 @@ __global__ void __launch_bounds__(WIDE ? 576 : kThreads, WIDE ? 1 : 2) conv_tc_k
         auto c8_off = [&](int mb_, int cgi_, bool& ok_) -> uint32_t {
             const int oc = w0 + mb_ * 8 + (m & 7);
             ok_ = row_ok && oc < p.W;
-            if (p.out_mode == 2)
-                return (uint32_t)(cgi_ * 2) * cstride + ((uint32_t)(2 * orow + (ij >> 1)) * (uint32_t)(2 * p.W) + (uint32_t)(2 * oc + (ij & 1))) * 16u;
+            if (p.out_mode == 2) {
+                const int hg = gpm >> 1;             // 16-column groups per sub-pixel half
+                const int jj = cgi_ >= hg ? 1 : 0;
+                return (uint32_t)((cgi_ - jj * hg) * 2) * cstride +
+                       ((uint32_t)(2 * orow + ij) * (uint32_t)(2 * p.W) + (uint32_t)(2 * oc + jj)) * 16u;
+            }
             return (uint32_t)(cgi_ * 2) * cstride + ((uint32_t)orow * (uint32_t)p.W + (uint32_t)oc) * 16u;
         };
         const bool res_c8 = p.res_mode != 0 && p.out_mode != 1;
@@ -851,8 +857,14 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, uint16_t* __res
         if (!transposed) {
             if (co < Cout && ci < Cin) v = w[((size_t)co * Cin + ci) * T + tap];
         } else {
-            const int ij = co / Cout_p, c = co % Cout_p;
-            if (ij < 4 && c < Cout && ci < Cin) v = w[((size_t)ci * Cout + c) * 4 + ij];
+            // n-block nb = (row sub-pixel i, channel block cb); its columns are [j = 0 | j = 1] halves of BN/2 channels,
+            // so one CTA writes both horizontally adjacent output pixels (full 32-byte sectors, see the epilogue)
+            const int hb = BN >> 1, nbi = 2 * Cout_p / BN;
+            const int isub = nb / nbi, cb = nb - isub * nbi;
+            const int j = nn >= hb ? 1 : 0;
+            const int c = cb * hb + (nn - j * hb);
+            const int ij = isub * 2 + j;
+            if (isub < 2 && c < Cout && ci < Cin) v = w[((size_t)ci * Cout + c) * 4 + ij];
         }
         uint16_t bits;
         if constexpr (BF16) {
@@ -912,9 +924,9 @@ static int conv_tc_launch(const void* x_c8, const void* w_packed, const float* b
                           int KW, int BN, int MB, int act, int res_mode, int out_mode, int is_bf16, void* stream,
                           const CouplingArgs* cpl) {
     const int KC = pick_kc(Cin_p);
-    if (N <= 0 || H <= 0 || W <= 0 || !KC || (Cin_p % 16) || (Cout_p % BN) || (BN % 16) || BN < 16 || BN > 256 ||
+    if (N <= 0 || H <= 0 || W <= 0 || !KC || (Cin_p % 16) || (out_mode != 2 && (Cout_p % BN)) || (BN % 16) || BN < 16 || BN > 256 ||
         (MB != 1 && MB != 2) || MB * BN > 512 || !(KH & 1) || !(KW & 1) || KH > 7 || KW > 7 || out_mode < 0 ||
-        out_mode > 3 || (out_mode == 2 && (KH != 1 || KW != 1)) || (out_mode == 3 && (!cpl || BN != Cout_p))) {
+        out_mode > 3 || (out_mode == 2 && (KH != 1 || KW != 1 || (BN % 32) || (2 * Cout_p) % BN)) || (out_mode == 3 && (!cpl || BN != Cout_p))) {
         set_error("conv_tc: unsupported configuration (Cin_p=%d Cout_p=%d BN=%d MB=%d K=%dx%d)", Cin_p, Cout_p, BN, MB, KH, KW);
         return CWFA_EINVAL;
     }

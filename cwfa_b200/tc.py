@@ -81,8 +81,11 @@ class PackedConv:
         self.Cin_p = pad16(Cin) if cin_p is None else cin_p
         self.Cout_p = pad16(Cout)
         tot_p = 4 * self.Cout_p if transposed else self.Cout_p
+        if bn is None and transposed:
+            # transposed convs: an n-block holds both horizontal sub-pixels (BN/2 channels each): BN % 32 == 0, BN | 2*Cout_p
+            bn = next(c for c in (256, 192, 128, 96, 64, 32) if (2 * self.Cout_p) % c == 0)
         if bn is None:
-            bn = pick_bn(tot_p if not transposed else self.Cout_p)
+            bn = pick_bn(tot_p)
             if self.Cin_p <= 64 and not transposed:
                 # small-K convs are epilogue/bandwidth-bound; tile widths measured best on B200 (scripts/sweep_conv_tc.py)
                 for cand in (256, 128, 192, 64, 160, 96, 48, 32, 16):
@@ -102,7 +105,12 @@ class PackedConv:
         if bias is not None:
             b = torch.zeros(tot_p, device=w.device, dtype=torch.float32)
             if transposed:
-                b.view(4, self.Cout_p)[:, :Cout] = bias.detach().float()
+                # column order of the packed transposed weights: n-block = (row sub-pixel i, channel block of BN/2),
+                # columns [j = 0 half | j = 1 half] (see pack_weights_kernel)
+                hb = self.BN // 2
+                bp = torch.zeros(self.Cout_p, device=w.device, dtype=torch.float32)
+                bp[:Cout] = bias.detach().float()
+                b.view(2, self.Cout_p // hb, 2, hb)[:] = bp.view(1, self.Cout_p // hb, 1, hb)
             else:
                 b[:Cout] = bias.detach().float()
             self.bias = b

@@ -142,7 +142,8 @@ int cwfa_gate_add_f32(float* x, const float* m, const float* g, int64_t n, void*
  * res_mode 2: v += res.  out_mode 0: C8 (Cout_p channels; res is C8), out_mode 1: NCHW fp32 with Cout
  * channels (res is NCHW fp32), out_mode 2: ConvTranspose2d(k=2,s=2) (unet.py:166) run as a 1x1 conv to
  * 4*Cout_p channels (weights packed with transposed=1) and scattered to a C8 (2H,2W) tensor, res = the
- * skip tensor added at the output location (unet.py:190).  BN = output channels per CTA (multiple of 16, <= 256, divides Cout_p),
+ * skip tensor added at the output location (unet.py:190; for out_mode 2 an n-block holds BN/2 channels of both horizontal
+ * sub-pixels so that 32-byte sectors are written whole: BN % 32 == 0 and BN divides 2*Cout_p).  BN = output channels per CTA (multiple of 16, <= 256, divides Cout_p),
  * MB = number of 16x8-pixel M=128 blocks per CTA (1 or 2), MB*BN <= 512 TMEM columns.
  * cwfa_tc_packed_weight_elems = half elements to allocate for w_packed: the packed tiles followed by one uint32 per
  * (n-block, k-block) whose bit ks says "K-step ks has a nonzero weight" (written by cwfa_tc_pack_weights; cwfa_conv_tc

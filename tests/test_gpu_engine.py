@@ -82,7 +82,7 @@ def test_unet_pieces_c8(golden_tiny):
     b = seeded_randn((48,), 3)
     skip = seeded_randn((2, 48, 16, 32), 4).bfloat16().float()
     ref = F.conv_transpose2d(x, w, b, stride=2) + skip
-    pc = tc.PackedConv(w.to(DEV), b.to(DEV), "bf16", transposed=True, bn=48)
+    pc = tc.PackedConv(w.to(DEV), b.to(DEV), "bf16", transposed=True)
     y = tc.from_c8(tc.conv_transpose_tc(tc.to_c8(x.to(DEV)), pc, tc.to_c8(skip.to(DEV))))
     assert rel_l2(y, ref) < 4e-3
     xb = seeded_randn((2, 256, 8, 12), 5).bfloat16().float()
