@@ -1068,11 +1068,11 @@ extern "C" int cwfa_conv_tc_coupling(const void* x_c8, const void* w_packed, con
 
 // Sums the per-CTA partials of cwfa_conv_tc_coupling per sample in a fixed order (bit-reproducible):
 // logdet[n] (+)= sum, sumsq[n] = sum y^2 (if not NULL).
-__global__ void __launch_bounds__(256) coupling_finalize_kernel(const float* __restrict__ ws, float* __restrict__ logdet,
-                                                                float* __restrict__ sumsq, int tiles, int accumulate) {
+__global__ void __launch_bounds__(1024) coupling_finalize_kernel(const float* __restrict__ ws, float* __restrict__ logdet,
+                                                                 float* __restrict__ sumsq, int tiles, int accumulate) {
     const int n = blockIdx.x;
     double s = 0.0, q = 0.0;
-    for (int i = threadIdx.x; i < tiles; i += 256) {           // fixed thread <-> partial assignment
+    for (int i = threadIdx.x; i < tiles; i += 1024) {          // fixed thread <-> partial assignment
         const float2 v = __ldg(reinterpret_cast<const float2*>(ws) + (size_t)n * tiles + i);
         s += (double)v.x;
         q += (double)v.y;
@@ -1082,19 +1082,19 @@ __global__ void __launch_bounds__(256) coupling_finalize_kernel(const float* __r
         s += __shfl_xor_sync(0xffffffffu, s, o);
         q += __shfl_xor_sync(0xffffffffu, q, o);
     }
-    __shared__ double red[8][2];
+    __shared__ double red[32][2];
     if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5][0] = s; red[threadIdx.x >> 5][1] = q; }
     __syncthreads();
     if (threadIdx.x == 0) {
         double a = 0.0, b = 0.0;
-        for (int k = 0; k < 8; ++k) { a += red[k][0]; b += red[k][1]; }    // fixed order
+        for (int k = 0; k < 32; ++k) { a += red[k][0]; b += red[k][1]; }   // fixed order
         logdet[n] = (accumulate ? logdet[n] : 0.f) + (float)a;
         if (sumsq) sumsq[n] = (float)b;
     }
 }
 extern "C" int cwfa_coupling_finalize(const float* workspace, float* logdet, float* sumsq, int N, int tiles, int accumulate,
                                       void* stream) {
-    coupling_finalize_kernel<<<N, 256, 0, (cudaStream_t)stream>>>(workspace, logdet, sumsq, tiles, accumulate);
+    coupling_finalize_kernel<<<N, 1024, 0, (cudaStream_t)stream>>>(workspace, logdet, sumsq, tiles, accumulate);
     return check_launch("coupling_finalize");
 }
 
