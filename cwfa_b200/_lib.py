@@ -47,6 +47,8 @@ _SIGS = {
     "cwfa_c8_channel_stats": [vp, vp, vp, i32, i32, i64, i32, vp],
     "cwfa_c8_bn_apply": [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],
     "cwfa_c8_col2im3x3": [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp],
+    "cwfa_c8_layernorm_workspace_floats": [i32],
+    "cwfa_c8_layernorm": [vp, vp, vp, vp, vp, i32, i32, i32, i64, f32, i32, vp],
     "cwfa_conv_tc_coupling_tiles": [i32, i32, i32],
     "cwfa_conv_tc_coupling": [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, f32, vp, i32, i32, f32, f32,
                               i32, vp, i32, vp],
@@ -108,7 +110,7 @@ class CwfaError(RuntimeError):
 
 
 # kernel launches issued per C-ABI call (for bench.py's "gpu_launches" claim)
-_LAUNCHES = {"cwfa_affine": 2, "cwfa_channel_stats_f32": 2, "cwfa_layernorm_chw_f32": 2, "cwfa_c8_channel_stats": 2,
+_LAUNCHES = {"cwfa_affine": 2, "cwfa_channel_stats_f32": 2, "cwfa_layernorm_chw_f32": 2, "cwfa_c8_channel_stats": 2, "cwfa_c8_layernorm": 2,
              "cwfa_tc_set_debug_buffer": 0, "cwfa_resblock_set_debug_buffer": 0, "cwfa_device_check": 0, "cwfa_conv_tc_coupling_tiles": 0, "cwfa_coupling_tc_tiles": 0}
 launch_count = 0
 launch_hist = {}

@@ -186,7 +186,85 @@ __global__ void __launch_bounds__(256) c8_col2im3x3_kernel(const uint4* __restri
         }
     }
 }
+// LayerNorm([C,H,W]) on a C8 tensor (ConvNeXt of the LRNN, networks.py:486-503): statistics over all C*H*W elements of a
+// sample (channel padding is zero and is not counted), then y = (x - mean) * rstd * w + b with the element-wise affine
+// parameters pre-converted to the same C8 half layout (half the parameter traffic of the fp32 NCHW form).
+constexpr int kC8LnBlocks = 296;
+template <bool BF16>
+__global__ void __launch_bounds__(256) c8_ln_stats_kernel(const uint4* __restrict__ x, float* __restrict__ ws, int64_t n16) {
+    const uint4* xs = x + (int64_t)blockIdx.y * n16;
+    float s = 0.f, q = 0.f;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n16; i += (int64_t)gridDim.x * blockDim.x) {
+        float v[8];
+        unpack8<BF16>(__ldg(xs + i), v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s += v[j]; q = fmaf(v[j], v[j], q); }
+    }
+    s = warp_sum(s);
+    q = warp_sum(q);
+    __shared__ float red[8][2];
+    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5][0] = s; red[threadIdx.x >> 5][1] = q; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float a = 0.f, b = 0.f;
+        for (int k = 0; k < 8; ++k) { a += red[k][0]; b += red[k][1]; }
+        ws[((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * 2] = a;
+        ws[((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * 2 + 1] = b;
+    }
+}
+template <bool BF16>
+__global__ void __launch_bounds__(256) c8_ln_apply_kernel(const uint4* __restrict__ x, const uint4* __restrict__ gamma,
+                                                          const uint4* __restrict__ beta, uint4* __restrict__ y,
+                                                          const float* __restrict__ ws, int64_t n16, double count, float eps) {
+    __shared__ float s_mean, s_rstd;
+    if (threadIdx.x == 0) {
+        double s = 0.0, q = 0.0;
+        for (int i = 0; i < kC8LnBlocks; ++i) {                  // fixed order
+            s += (double)ws[((int64_t)blockIdx.y * kC8LnBlocks + i) * 2];
+            q += (double)ws[((int64_t)blockIdx.y * kC8LnBlocks + i) * 2 + 1];
+        }
+        const double mean = s / count;
+        double var = q / count - mean * mean;
+        if (var < 0.0) var = 0.0;
+        s_mean = (float)mean;
+        s_rstd = (float)(1.0 / sqrt(var + (double)eps));
+    }
+    __syncthreads();
+    const float mean = s_mean, rstd = s_rstd;
+    const uint4* xs = x + (int64_t)blockIdx.y * n16;
+    uint4* ys = y + (int64_t)blockIdx.y * n16;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n16; i += (int64_t)gridDim.x * blockDim.x) {
+        float v[8], g[8], b[8];
+        unpack8<BF16>(__ldg(xs + i), v);
+        unpack8<BF16>(__ldg(gamma + i), g);
+        unpack8<BF16>(__ldg(beta + i), b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fmaf((v[j] - mean) * rstd, g[j], b[j]);     // padded channels: g = b = 0 -> 0
+        ys[i] = pack8<BF16>(v);
+    }
+}
 }  // namespace
+
+extern "C" int cwfa_c8_layernorm_workspace_floats(int N) { return 2 * N * kC8LnBlocks; }
+
+// x, y: C8 (N, Cp, H, W); gamma, beta: C8 (1, Cp, H, W) element-wise affine parameters (zero in the channel padding);
+// C = true channel count (statistics are over C*H*W elements).  workspace >= cwfa_c8_layernorm_workspace_floats(N).
+extern "C" int cwfa_c8_layernorm(const void* x, const void* gamma, const void* beta, void* y, float* workspace, int N, int C,
+                                 int Cp, int64_t P, float eps, int is_bf16, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N <= 0 || C <= 0 || Cp < C || (Cp % 8) || P <= 0 || !workspace) { set_error("c8_layernorm: bad shape"); return CWFA_EINVAL; }
+    const int64_t n16 = (int64_t)(Cp / 8) * P;
+    dim3 grid(kC8LnBlocks, N);
+    const double count = (double)C * (double)P;
+    if (is_bf16) {
+        c8_ln_stats_kernel<true><<<grid, 256, 0, st>>>((const uint4*)x, workspace, n16);
+        c8_ln_apply_kernel<true><<<grid, 256, 0, st>>>((const uint4*)x, (const uint4*)gamma, (const uint4*)beta, (uint4*)y, workspace, n16, count, eps);
+    } else {
+        c8_ln_stats_kernel<false><<<grid, 256, 0, st>>>((const uint4*)x, workspace, n16);
+        c8_ln_apply_kernel<false><<<grid, 256, 0, st>>>((const uint4*)x, (const uint4*)gamma, (const uint4*)beta, (uint4*)y, workspace, n16, count, eps);
+    }
+    return check_launch("c8_layernorm");
+}
 
 extern "C" int cwfa_c8_col2im3x3(const void* g, const float* bias, void* out, int N, int Dp, int Gp, int H, int W,
                                  int is_bf16, void* stream) {

@@ -159,16 +159,19 @@ class _LRNN:
         self.cn0_1x1 = tc.PackedConv(cn0.m[2].weight, cn0.m[2].bias, kind)           # 1x1 64 -> 64
         self.cn1_in = tc.PackedConv(cn1.input.weight, cn1.input.bias, kind)          # 1x1 64 -> 6
         self.cn1_7x7 = tc.PackedConv(cn1.m[0].weight, cn1.m[0].bias, kind)           # 7x7  6 -> 6
+        # element-wise LayerNorm parameters of the wide ConvNeXt block in the activation layout (half the traffic)
+        self.cn0_ln_w = tc.to_c8(cn0.m[1].weight.detach().float()[None].contiguous(), kind)
+        self.cn0_ln_b = tc.to_c8(cn0.m[1].bias.detach().float()[None].contiguous(), kind)
 
     def _mean_branch(self, mean_vol: torch.Tensor) -> torch.Tensor:
         """conv3d = ConvNeXt(6,64) -> ConvNeXt(64,6) on the mean volume (networks.py:486-503,527-530): every conv on
-        the tensor cores (channels padded to 16); LayerNorm([C,H,W]) and the final 6-channel 1x1 stay fp32."""
+        the tensor cores (channels padded to 16); the 64-channel LayerNorm([C,H,W]) runs on the C8 tensor, the 6-channel
+        one and the final 6-channel 1x1 stay fp32."""
         cn0, cn1 = self.net.conv3d[0], self.net.conv3d[1]
         k = self.kind
         up8 = tc.conv_tc(tc.to_c8(mean_vol, k), self.cn0_in)                                        # C8, 64 ch
-        m = tc.conv_tc(up8, self.cn0_7x7, out_nchw=True)
-        m = ops.layernorm_chw(m, cn0.m[1].weight, cn0.m[1].bias, cn0.m[1].eps)
-        y8 = tc.conv_tc(tc.to_c8(m, k), self.cn0_1x1, act=ops.ACT_GELU, res=up8, res_mode=2)        # GELU(.) + up
+        m8 = tc.layernorm_c8(tc.conv_tc(up8, self.cn0_7x7), self.cn0_ln_w, self.cn0_ln_b, cn0.m[1].eps)
+        y8 = tc.conv_tc(m8, self.cn0_1x1, act=ops.ACT_GELU, res=up8, res_mode=2)                    # GELU(.) + up
         up1_8 = tc.conv_tc(y8, self.cn1_in)                                                         # C8, 6 (16) ch
         m1 = tc.conv_tc(up1_8, self.cn1_7x7, out_nchw=True)
         m1 = ops.layernorm_chw(m1, cn1.m[1].weight, cn1.m[1].bias, cn1.m[1].eps)

@@ -192,6 +192,18 @@ def batchnorm_c8(x: C8, gamma, beta, running_mean, running_var, *, batch_stats: 
     return (y, yp) if pool else y
 
 
+def layernorm_c8(x: C8, gamma8: C8, beta8: C8, eps: float = 1e-5) -> C8:
+    """LayerNorm([C,H,W]) with element-wise affine parameters (networks.py:486-503) on a C8 tensor; ``gamma8`` / ``beta8`` are
+    the parameters converted once with ``to_c8(param[None], kind)``."""
+    if gamma8.Cp != x.Cp or beta8.Cp != x.Cp or gamma8.H != x.H or gamma8.W != x.W or gamma8.kind != x.kind or beta8.kind != x.kind:
+        raise ValueError("layernorm_c8: parameter layout mismatch")
+    y = C8.empty(x.N, x.C, x.H, x.W, x.data.device, x.kind, x.Cp)
+    ws = torch.empty(_lib.load().cwfa_c8_layernorm_workspace_floats(x.N), device=x.data.device, dtype=torch.float32)
+    _lib.call("cwfa_c8_layernorm", x.data.data_ptr(), gamma8.data.data_ptr(), beta8.data.data_ptr(), y.data.data_ptr(),
+              ws.data_ptr(), x.N, x.C, x.Cp, x.H * x.W, float(eps), x.is_bf16, _stream())
+    return y
+
+
 def col2im3x3_weights(w: torch.Tensor) -> torch.Tensor:
     """(Cout, Cin, 3, 3) conv weights -> (9 * ceil8(Cout), Cin, 1, 1) weights of the 1x1 convolution whose output
     channel ``(co // 8) * 72 + (ky * 3 + kx) * 8 + co % 8`` is the tap-(ky,kx) partial product of output channel co

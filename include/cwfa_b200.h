@@ -179,6 +179,13 @@ int cwfa_c8_bn_apply(const void* x, const float* scale, const float* shift, void
  * bias: Dp floats or NULL. */
 int cwfa_c8_col2im3x3(const void* g, const float* bias, void* out, int N, int Dp, int Gp, int H, int W,
                       int is_bf16, void* stream);
+
+/* LayerNorm([C,H,W]) of the LRNN's ConvNeXt blocks (networks.py:486-503) on C8 tensors: per-sample statistics over the
+ * C*H*W true elements (channel padding must be zero), y = (x - mean) * rstd * gamma + beta with the element-wise affine
+ * parameters given as C8 tensors of shape (1, Cp, H, W) (zero in the padding).  workspace: cwfa_c8_layernorm_workspace_floats(N). */
+int cwfa_c8_layernorm_workspace_floats(int N);
+int cwfa_c8_layernorm(const void* x, const void* gamma, const void* beta, void* y, float* workspace, int N, int C, int Cp,
+                      int64_t P, float eps, int is_bf16, void* stream);
 /* Profiling aid: when set (device buffer of 8 uint64 per CTA), conv_tc records globaltimer stamps. */
 int cwfa_tc_set_debug_buffer(void* buf);
 int cwfa_resblock_set_debug_buffer(void* buf);   /* [cta][8 tiles][8 stamps] uint64 */

@@ -240,3 +240,20 @@ def test_fused_coupling_conv_vs_reference(ch, axis, inverse, ext, zero_x, persis
                         perm=None if perm is None else perm.to(DEV).to(torch.int32), perm_axis=axis if perm is not None else 0,
                         logdet=logdet2, persistent=persistent)
     assert torch.equal(logdet, logdet2)
+
+
+@pytest.mark.parametrize("N,C,H,W,kind", [(1, 64, 32, 32, "bf16"), (2, 6, 17, 23, "bf16"), (1, 64, 24, 40, "fp16")])
+def test_layernorm_c8(N, C, H, W, kind):
+    """LayerNorm([C,H,W]) with element-wise affine (ConvNeXt, networks.py:486-503) on the C8 layout vs F.layer_norm."""
+    from cwfa_b200 import tc
+    x = _round(seeded_randn((N, C, H, W), 81) * 1.7 + 0.3, kind)
+    g = _round(seeded_randn((C, H, W), 82, 0.3) + 1.0, kind)
+    b = _round(seeded_randn((C, H, W), 83, 0.2), kind)
+    ref = F.layer_norm(x, [C, H, W], g, b, 1e-6)
+    y8 = tc.layernorm_c8(tc.to_c8(x.to(DEV), kind), tc.to_c8(g[None].to(DEV), kind), tc.to_c8(b[None].to(DEV), kind), 1e-6)
+    y = tc.from_c8(y8)
+    torch.cuda.synchronize()
+    assert rel_l2(y, ref) < (5e-3 if kind == "bf16" else 7e-4)
+    if y8.Cp != C:
+        raw = y8.data.float().view(N, y8.Cp // 8, H, W, 8).permute(0, 1, 4, 2, 3).reshape(N, y8.Cp, H, W)
+        assert float(raw[:, C:].abs().max()) == 0.0
