@@ -559,10 +559,14 @@ extern "C" int cwfa_layernorm_workspace_blocks(void) { return kLNBlocks; }
 // One thread per sequence position; C <= 16 channels live in registers.
 // ------------------------------------------------------------------------------------------
 constexpr int kAttMaxC = 16;
+// CT = compile-time channel count (exact loops, no predication: the LRNN uses 6); CT = 0 is the run-time fallback (C <= 16).
+template <int CT>
 __global__ void __launch_bounds__(256) attention_gate_kernel(float* __restrict__ x, const float* __restrict__ m,
                                                              const float* __restrict__ v, const float* __restrict__ w1,
                                                              const float* __restrict__ b1, const float* __restrict__ w2,
                                                              const float* __restrict__ b2, int C, int64_t L) {
+    constexpr int NC = CT ? CT : kAttMaxC;
+    const int Cc = CT ? CT : C;                      // compile-time stride of the weight tables when CT is set
     __shared__ float sw1[kAttMaxC * kAttMaxC * 3], sw2[kAttMaxC * kAttMaxC], sb1[kAttMaxC], sb2[kAttMaxC];
     for (int i = threadIdx.x; i < C * C * 3; i += blockDim.x) sw1[i] = __ldg(w1 + i);
     for (int i = threadIdx.x; i < C * C; i += blockDim.x) sw2[i] = __ldg(w2 + i);
@@ -571,29 +575,29 @@ __global__ void __launch_bounds__(256) attention_gate_kernel(float* __restrict__
     const int b = blockIdx.y;
     const float* vb = v + (int64_t)b * C * L;
     for (int64_t l = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; l < L; l += (int64_t)gridDim.x * blockDim.x) {
-        float h[kAttMaxC];
+        float h[NC];
 #pragma unroll
-        for (int o = 0; o < kAttMaxC; ++o) h[o] = o < C ? sb1[o] : 0.f;
+        for (int o = 0; o < NC; ++o) h[o] = (CT || o < C) ? sb1[o] : 0.f;
 #pragma unroll
-        for (int c = 0; c < kAttMaxC; ++c) {
-            if (c < C) {
+        for (int c = 0; c < NC; ++c) {
+            if (CT || c < C) {
                 const float vm = l > 0 ? __ldg(vb + (int64_t)c * L + l - 1) : 0.f;
                 const float v0 = __ldg(vb + (int64_t)c * L + l);
                 const float vp = l + 1 < L ? __ldg(vb + (int64_t)c * L + l + 1) : 0.f;
 #pragma unroll
-                for (int o = 0; o < kAttMaxC; ++o)
-                    if (o < C) h[o] = fmaf(sw1[(o * C + c) * 3 + 2], vp, fmaf(sw1[(o * C + c) * 3 + 1], v0, fmaf(sw1[(o * C + c) * 3], vm, h[o])));
+                for (int o = 0; o < NC; ++o)
+                    if (CT || o < C) h[o] = fmaf(sw1[(o * Cc + c) * 3 + 2], vp, fmaf(sw1[(o * Cc + c) * 3 + 1], v0, fmaf(sw1[(o * Cc + c) * 3], vm, h[o])));
             }
         }
 #pragma unroll
-        for (int o = 0; o < kAttMaxC; ++o) h[o] = fmaxf(h[o], 0.f);
+        for (int o = 0; o < NC; ++o) h[o] = fmaxf(h[o], 0.f);
 #pragma unroll
-        for (int o = 0; o < kAttMaxC; ++o) {
-            if (o < C) {
+        for (int o = 0; o < NC; ++o) {
+            if (CT || o < C) {
                 float a = sb2[o];
 #pragma unroll
-                for (int c = 0; c < kAttMaxC; ++c)
-                    if (c < C) a = fmaf(sw2[o * C + c], h[c], a);
+                for (int c = 0; c < NC; ++c)
+                    if (CT || c < C) a = fmaf(sw2[o * Cc + c], h[c], a);
                 const float g = 1.f / (1.f + expf(-a));
                 const int64_t idx = ((int64_t)b * C + o) * L + l;
                 x[idx] += m[idx] * 2.f * (g - 0.5f);
@@ -606,7 +610,14 @@ extern "C" int cwfa_attention_gate_f32(float* x, const float* m, const float* v,
     if (B <= 0 || C <= 0 || C > kAttMaxC || L <= 0 || B > 65535) { set_error("attention_gate: unsupported shape (C <= 16)"); return CWFA_EINVAL; }
     int blocks = (int)((L + 255) / 256);
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-    attention_gate_kernel<<<dim3(blocks, B), 256, 0, (cudaStream_t)stream>>>(x, m, v, w1, b1, w2, b2, C, L);
+    dim3 grid(blocks, B);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (C) {        // (with CT = C the shared-memory weight indices are compile-time immediates)
+        case 6: attention_gate_kernel<6><<<grid, 256, 0, st>>>(x, m, v, w1, b1, w2, b2, C, L); break;
+        case 4: attention_gate_kernel<4><<<grid, 256, 0, st>>>(x, m, v, w1, b1, w2, b2, C, L); break;
+        case 12: attention_gate_kernel<12><<<grid, 256, 0, st>>>(x, m, v, w1, b1, w2, b2, C, L); break;
+        default: attention_gate_kernel<0><<<grid, 256, 0, st>>>(x, m, v, w1, b1, w2, b2, C, L); break;
+    }
     return check_launch("attention_gate");
 }
 
