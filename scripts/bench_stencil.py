@@ -32,6 +32,13 @@ for D in (48, 24, 12, 6):
     ys = [tc.conv_tc(h, s2) for h in hs]
     torch.cuda.synchronize()
     cases = [("s1", lambda i: tc.conv_tc(xs[i], s1, act=ops.ACT_PRELU, slope=slope)), ("s2 tap-by-tap", lambda i: tc.conv_tc(hs[i], s2))]
+    if os.environ.get("S1_SWEEP"):
+        for bn in (256, 192, 128, 64):
+            if (D * Cm) % bn:
+                continue
+            pcv = tc.PackedConv(W1.reshape(D * Cm, D, 3, 3), torch.zeros(D * Cm, device=DEV), bn=bn)
+            for mb in (1, 2):
+                cases.append((f"s1 bn{bn} mb{mb}", lambda i, pcv=pcv, mb=mb: tc.conv_tc(xs[i], pcv, act=ops.ACT_PRELU, slope=slope, mb=mb)))
     for (bn, mb), pcg in variants.items():
         cases.append((f"s2 1x1 bn{bn} mb{mb}", lambda i, pcg=pcg, mb=mb: tc.conv_tc(hs[i], pcg, mb=mb)))
     g0 = tc.conv_tc(hs[0], next(iter(variants.values())))
