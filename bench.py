@@ -322,15 +322,18 @@ def main():
         vol = torch.randn((B, args.depths, args.side, args.side), generator=g).to(dev)
         vB = torch.randn((B, 29, args.side, args.side), generator=g).to(dev)
         mvB = [m.repeat(B, 1, 1, 1) for m in mvs_dev[:model.n_levels]]
-        eng.forward_nll(vol, vB, mvB)
+        for _ in range(2):                          # warm-up: allocator pools for the batch-8 activations, kernel loading
+            eng.forward_nll(vol, vB, mvB)
         torch.cuda.synchronize()
-        n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        n0.record()
-        for _ in range(3):
+        times = []
+        for _ in range(3):                          # median of 3 individually timed passes (an allocator retry in one
+            n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)   # pass must not set the figure)
+            n0.record()
             res = eng.forward_nll(vol, vB, mvB)
-        n1.record()
-        torch.cuda.synchronize()
-        nll_fps = 3 * B / (n0.elapsed_time(n1) * 1e-3)
+            n1.record()
+            torch.cuda.synchronize()
+            times.append(n0.elapsed_time(n1))
+        nll_fps = B / (sorted(times)[1] * 1e-3)
         del vol, vB, mvB, res
 
     if rank != 0:
