@@ -117,7 +117,10 @@ class _UNet:
             return [(tc.PackedConv(b.block[i].weight, b.block[i].bias, kind), b.block[i + 1], b.block[i + 2]) for i in (0, 3)]
 
         self.down = [block(d) for d in unet.down_path]
-        self.up = [(tc.PackedConv(u.up.weight, u.up.bias, kind, transposed=True), block(u.conv_block)) for u in unet.up_path]
+        # transposed convs: the deepest one (few tiles: 1.7 waves of 256-column items) runs better as 128-column,
+        # double-buffered items (measured: 131 -> 112 us, scripts/bench_convT.py)
+        self.up = [(tc.PackedConv(u.up.weight, u.up.bias, kind, transposed=True, bn=128 if u.up.weight.shape[0] >= 1024 else None),
+                    block(u.conv_block)) for u in unet.up_path]
         self.last = tc.PackedConv(unet.last[0].weight, unet.last[0].bias, kind)
 
     def _block(self, x, blk, training, pool):
@@ -139,7 +142,7 @@ class _UNet:
             else:
                 x8 = self._block(x8, blk, training, False)
         for i, (up, blk) in enumerate(self.up):
-            x8 = tc.conv_transpose_tc(x8, up, skips[-i - 1])
+            x8 = tc.conv_transpose_tc(x8, up, skips[-i - 1], mb=1 if up.BN == 128 else None)
             x8 = self._block(x8, blk, training, False)
         return tc.conv_tc(x8, self.last, act=ops.ACT_PRELU, slope=self.unet.last[1].weight, out_nchw=True)
 
