@@ -10,8 +10,13 @@
 // Weights are pre-packed per (n-block, k-block, tap) as [chunk][BN][8] and streamed with 1-D bulk
 // copies.  Accumulators live in TMEM (128 lanes x BN fp32 columns per M-block).
 //
-// Warp roles (192 threads): warp0 = TMA producer, warp1 = TMEM alloc + MMA issuer (one elected
-// lane), warps2-5 = epilogue (tcgen05.ld -> bias/activation/residual -> global).
+// The grid is persistent: every CTA walks (n-block, sample, tile) work items with stride gridDim.x; the
+// operand rings run straight through item boundaries and tiles of <= 128 TMEM columns are double buffered.
+//
+// Warp roles (320 threads; 576 in the WIDE variant): warp0 = TMA producer, warp1 = TMEM alloc + MMA issuer
+// (one elected lane), warps 2-9 (2-17) = epilogue (tcgen05.ld -> bias/activation/residual -> global).
+// The weight packer appends per-(n-block, k-block) masks of the K = 16 steps that hold a nonzero weight;
+// producer and issuer skip the rest (banded weights of the conditioning net's depth stencil).
 #include <cuda.h>
 #include "common.cuh"
 using namespace cwfa;
