@@ -1,0 +1,391 @@
+"""Differentiable versions of the fp32 module-path ops: ``torch.autograd.Function`` is used only as the
+tape (which op ran, what it saved); every forward AND every adjoint below is one of this repo's CUDA
+kernels called through the C ABI (csrc/backward.cu, elementwise.cu, conv_f32.cu).
+
+The reference trains a flow level with stock autograd (CWFA.py:928-1015): an inverse pass with gradients for
+the MSE term, a forward pass for the NLL term, ``backward()`` and a Lion step.  ``cwfa_b200.ops`` routes here
+whenever gradients are enabled and an input requires them, so the FrEIA-style modules
+(``cwfa_b200.modules`` / ``networks``) train unchanged.  There is no CPU fallback.
+
+Covered (everything a flow level and its conditioning net execute): conv2d 1x1/3x3 (+bias, ELU, residual-add,
+PReLU), the affine coupling with log-det, channel / row / column permutations, the depth-wise Haar transform
+(split / merge forms included), per-sample sum of squares, MSE, the conditioning net's depth stencil.
+The LRNN (BatchNorm, max-pool, transposed conv, LayerNorm, GELU, attention gate) has no adjoints yet: those
+ops stay non-differentiable and ``ops`` says so once.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+
+from . import _lib, ops
+
+_F = torch.autograd.Function
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32(t: torch.Tensor) -> torch.Tensor:
+    return ops._ck(t.detach())
+
+
+def _zeros_like_if_none(g, ref):
+    return torch.zeros_like(ref) if g is None else ops._ck(g)
+
+
+# ---------------------------------------------------------------------------------------------
+# raw adjoint launches
+# ---------------------------------------------------------------------------------------------
+def conv2d_wgrad(x: torch.Tensor, dy: torch.Tensor, KH: int, KW: int) -> torch.Tensor:
+    """dW (Cout,Cin,KH,KW) of a stride-1 'same' convolution from its input and output cotangent."""
+    N, Cin, H, W = x.shape
+    Cout = dy.shape[1]
+    lib = _lib.load()
+    nws = lib.cwfa_conv2d_wgrad_workspace_floats(N, Cin, H, W, Cout, KH, KW)
+    ws = torch.empty(nws, device=x.device, dtype=torch.float32)
+    dw = torch.empty((Cout, Cin, KH, KW), device=x.device, dtype=torch.float32)
+    _lib.call("cwfa_conv2d_wgrad_f32", x.data_ptr(), dy.data_ptr(), dw.data_ptr(), ws.data_ptr(), N, Cin, H, W, Cout, KH, KW, 0, _stream())
+    return dw
+
+
+def conv2d_dgrad(dy: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """dx = conv_same(dy, flip(w)^T): the forward direct-convolution kernel on re-laid weights."""
+    Cout, Cin, KH, KW = w.shape
+    wt = torch.empty((Cin, Cout, KH, KW), device=w.device, dtype=torch.float32)
+    _lib.call("cwfa_conv2d_dgrad_weights_f32", w.data_ptr(), wt.data_ptr(), Cout, Cin, KH, KW, _stream())
+    return ops.conv2d(dy, wt, None)
+
+
+def channel_sum(x: torch.Tensor) -> torch.Tensor:
+    """Per-channel sum over (N,H,W) of a (N,C,...) tensor (bias gradients)."""
+    return ops.channel_stats(x)[0]
+
+
+def axpby(a: torch.Tensor, b: Optional[torch.Tensor], alpha: float, beta: float) -> torch.Tensor:
+    out = torch.empty_like(a)
+    _lib.call("cwfa_axpby_f32", a.data_ptr(), ops._p(b), out.data_ptr(), float(alpha), float(beta), a.numel(), _stream())
+    return out
+
+
+def scale_per_sample(x: torch.Tensor, s: torch.Tensor) -> torch.Tensor:
+    """y[b] = s[b] * x[b] with s a (B,) device tensor (no host sync)."""
+    B = x.shape[0]
+    n = x[0].numel()
+    y = torch.empty_like(x)
+    s = ops._ck(s).reshape(B)
+    _lib.call("cwfa_scale_shift_f32", x.data_ptr(), s.data_ptr(), torch.zeros_like(s).data_ptr(), y.data_ptr(), 1, B, n, _stream())
+    return y
+
+
+# ---------------------------------------------------------------------------------------------
+# conv2d (+bias, +residual before the activation, ELU fused; PReLU as its own op)
+# ---------------------------------------------------------------------------------------------
+class _Conv2d(_F):
+    @staticmethod
+    def forward(ctx, x, w, bias, res, act, res_mode):
+        xx, ww = _f32(x), _f32(w)
+        bb = None if bias is None else _f32(bias)
+        rr = None if res is None else _f32(res)
+        y = ops.conv2d(xx, ww, bb, act=act, res=rr, res_mode=res_mode)
+        ctx.act = act
+        ctx.has_res = rr is not None and res_mode == 1
+        ctx.save_for_backward(xx, ww, y if act == ops.ACT_ELU else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, y = ctx.saved_tensors
+        dv = ops._ck(dy)
+        if ctx.act == ops.ACT_ELU:
+            g = torch.empty_like(dv)
+            _lib.call("cwfa_elu_bwd_f32", dv.data_ptr(), y.data_ptr(), g.data_ptr(), dv.numel(), _stream())
+            dv = g
+        need_x, need_w, need_b, need_r = ctx.needs_input_grad[:4]
+        dx = conv2d_dgrad(dv, w) if need_x else None
+        dw = conv2d_wgrad(x, dv, w.shape[2], w.shape[3]) if need_w else None
+        db = channel_sum(dv) if need_b else None
+        dr = dv if (need_r and ctx.has_res) else None
+        return dx, dw, db, dr, None, None
+
+
+class _PReLU(_F):
+    @staticmethod
+    def forward(ctx, v, slope):
+        vv, ss = _f32(v), _f32(slope)
+        if ss.numel() != 1:
+            raise NotImplementedError("cwfa_b200: PReLU adjoint implements the single shared slope CWFA uses (networks.py:209)")
+        y = torch.empty_like(vv)
+        _lib.call("cwfa_prelu_f32", vv.data_ptr(), ss.data_ptr(), y.data_ptr(), vv.numel(), _stream())
+        ctx.save_for_backward(vv, ss)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        v, slope = ctx.saved_tensors
+        dy = ops._ck(dy)
+        dv = torch.empty_like(v)
+        ds = torch.empty(1, device=v.device, dtype=torch.float32)
+        ws = torch.empty(_lib.load().cwfa_reduce_workspace_blocks(), device=v.device, dtype=torch.float32)
+        _lib.call("cwfa_prelu_bwd_f32", dy.data_ptr(), v.data_ptr(), slope.data_ptr(), dv.data_ptr(), ds.data_ptr(), ws.data_ptr(),
+                  v.numel(), _stream())
+        return dv, ds.reshape(slope.shape)
+
+
+def prelu(v, slope):
+    return _PReLU.apply(v, slope)
+
+
+def conv2d_supported(w, act, res, res_mode) -> bool:
+    KH, KW = w.shape[2], w.shape[3]
+    return (KH == KW and KH in (1, 3) and act in (ops.ACT_NONE, ops.ACT_ELU, ops.ACT_PRELU)
+            and (res is None or res_mode == 1))
+
+
+def conv2d(x, w, bias=None, *, act=ops.ACT_NONE, slope=None, res=None, res_mode=0):
+    if act == ops.ACT_PRELU:
+        return prelu(_Conv2d.apply(x, w, bias, res, ops.ACT_NONE, res_mode if res is not None else 0), slope)
+    return _Conv2d.apply(x, w, bias, res, act, res_mode if res is not None else 0)
+
+
+# ---------------------------------------------------------------------------------------------
+# affine coupling + log-det
+# ---------------------------------------------------------------------------------------------
+class _Affine(_F):
+    """inputs: x (B,ch,..) or None; a = packed [s_raw | t] (B,2ch,..) when t_src is None, else s_raw (B,ch,..) with the
+    shift read from t_src (B,ch,..).  outputs: y, logdet (B,)."""
+
+    @staticmethod
+    def forward(ctx, x, a, t_src, inverse, clamp, t_scale, k_atan, raw):
+        aa = _f32(a)
+        xx = None if x is None else _f32(x)
+        packed = t_src is None
+        if packed:
+            ch = aa.shape[1] // 2
+            a_s, a_t = aa[:, :ch], aa[:, ch:]
+        else:
+            a_s, a_t = aa, ops._prep_inner(t_src.detach())[0]
+            ch = aa.shape[1]
+        y, logdet = ops.affine(xx, a_s, a_t, inverse=inverse, clamp=clamp, t_scale=t_scale, k_atan=k_atan, s_is_final=raw)
+        ctx.cfg = (bool(inverse), float(clamp), float(t_scale), float(k_atan), bool(raw), packed, ch)
+        ctx.save_for_backward(xx, aa, None if packed else a_t)
+        return y, logdet
+
+    @staticmethod
+    def backward(ctx, dy, g_logdet):
+        inverse, clamp, t_scale, k_atan, raw, packed, ch = ctx.cfg
+        x, a, t_keep = ctx.saved_tensors
+        B = a.shape[0]
+        P = a[0, 0].numel()
+        n = ch * P
+        dev = a.device
+        if packed:
+            a_s_ptr, a_t_ptr, ld_s, ld_t = a.data_ptr(), a.data_ptr() + 4 * n, 2 * n, 2 * n
+        else:
+            a_s_ptr, a_t_ptr, ld_s = a.data_ptr(), t_keep.data_ptr(), n
+            ld_t = t_keep.stride(0) if B > 1 else n
+        dy = torch.zeros((B, ch) + tuple(a.shape[2:]), device=dev, dtype=torch.float32) if dy is None else ops._ck(dy)
+        gj = None if g_logdet is None else ops._ck(g_logdet)
+        need_x, need_a, need_t = ctx.needs_input_grad[:3]
+        dx = torch.empty_like(dy) if (need_x and x is not None) else None
+        da = torch.empty_like(a) if need_a else None
+        dt = None
+        if packed:
+            da_s_ptr = None if da is None else da.data_ptr()
+            da_t_ptr = None if da is None else da.data_ptr() + 4 * n
+            ld_ds = ld_dt = 2 * n
+        else:
+            da_s_ptr, ld_ds = (None if da is None else da.data_ptr()), n
+            dt = torch.empty_like(dy) if need_t else None
+            da_t_ptr, ld_dt = (None if dt is None else dt.data_ptr()), n
+        _lib.call("cwfa_affine_bwd", ops._p(x), a_s_ptr, a_t_ptr, dy.data_ptr(), ops._p(gj), ops._p(dx), da_s_ptr, da_t_ptr,
+                  B, ch, P, ld_s, ld_t, ld_ds, ld_dt, clamp, k_atan, t_scale, int(inverse) | (2 if raw else 0), _stream())
+        return dx, da, dt, None, None, None, None, None
+
+
+def affine(x, a_s, a_t, *, inverse, clamp, t_scale, k_atan, s_is_final):
+    """Differentiable ``ops.affine``: returns (y, logdet).  Detects the packed [s|t] sub-network output so that its
+    gradient is written in place instead of being assembled from two slice gradients."""
+    ch = a_s.shape[1]
+    base = a_s._base if a_s._base is not None else None
+    if (base is not None and a_t._base is base and base.dim() == a_s.dim() and base.is_contiguous() and base.shape[1] == 2 * ch
+            and base.dtype == torch.float32 and a_s.data_ptr() == base.data_ptr()
+            and a_t.data_ptr() == base.data_ptr() + 4 * ch * a_s[0, 0].numel()):
+        return _Affine.apply(x, base, None, inverse, clamp, t_scale, k_atan, s_is_final)
+    return _Affine.apply(x, a_s.contiguous(), a_t, inverse, clamp, t_scale, k_atan, s_is_final)
+
+
+# ---------------------------------------------------------------------------------------------
+# permutations, Haar, reductions
+# ---------------------------------------------------------------------------------------------
+def _inverse_perm(perm: torch.Tensor) -> torch.Tensor:
+    cache = getattr(perm, "_cwfa_inv", None)
+    key = perm._version
+    if cache is None or cache[0] != key:
+        inv = torch.empty_like(perm)
+        inv[perm.detach()] = torch.arange(perm.numel(), device=perm.device, dtype=perm.dtype)
+        cache = (key, inv)
+        try:
+            perm._cwfa_inv = cache
+        except AttributeError:
+            pass
+    return cache[1]
+
+
+class _Permute(_F):
+    @staticmethod
+    def forward(ctx, x, perm, axis):
+        ctx.perm, ctx.axis = perm, axis
+        return ops.permute(_f32(x), perm, axis)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return ops.permute(ops._ck(dy), _inverse_perm(ctx.perm), ctx.axis), None, None
+
+
+def permute(x, perm, axis):
+    return _Permute.apply(x, perm, axis)
+
+
+class _Haar1d(_F):
+    """The orthonormal depth-wise Haar transform: the adjoint of each direction is the other direction."""
+
+    @staticmethod
+    def forward(ctx, x, inverse):
+        ctx.inverse = inverse
+        xx = _f32(x)
+        return ops.haar1d_inverse(xx) if inverse else ops.haar1d_forward(xx)
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = ops._ck(dy)
+        return (ops.haar1d_forward(dy) if ctx.inverse else ops.haar1d_inverse(dy)), None
+
+
+def haar1d(x, inverse: bool):
+    return _Haar1d.apply(x, inverse)
+
+
+class _HaarSplit(_F):
+    @staticmethod
+    def forward(ctx, x):
+        return ops.haar1d_split(_f32(x))
+
+    @staticmethod
+    def backward(ctx, dlo, dhi):
+        ref = dlo if dlo is not None else dhi
+        return ops.haar1d_merge(_zeros_like_if_none(dlo, ref), _zeros_like_if_none(dhi, ref))
+
+
+class _HaarMerge(_F):
+    @staticmethod
+    def forward(ctx, lo, hi):
+        return ops.haar1d_merge(_f32(lo), _f32(hi))
+
+    @staticmethod
+    def backward(ctx, dy):
+        return ops.haar1d_split(ops._ck(dy))
+
+
+def haar1d_split(x):
+    return _HaarSplit.apply(x)
+
+
+def haar1d_merge(lo, hi):
+    return _HaarMerge.apply(lo, hi)
+
+
+class _SumSquares(_F):
+    @staticmethod
+    def forward(ctx, x):
+        xx = _f32(x)
+        ctx.save_for_backward(xx)
+        return ops.sum_squares(xx).clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        return scale_per_sample(x, 2.0 * g)
+
+
+def sum_squares(x):
+    return _SumSquares.apply(x)
+
+
+class _Mse(_F):
+    """F.mse_loss(a, b) (mean over all elements; the regulariser of CWFA.py:951-955)."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        aa, bb = _f32(a), _f32(b)
+        d = axpby(aa, bb, 1.0, -1.0)
+        ctx.save_for_backward(d)
+        return ops.sum_squares(d.reshape(1, -1)).reshape(()) / d.numel()
+
+    @staticmethod
+    def backward(ctx, g):
+        (d,) = ctx.saved_tensors
+        s = (2.0 / d.numel()) * g.reshape(1)
+        da = scale_per_sample(d.reshape(1, -1), s).reshape(d.shape) if (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]) else None
+        ga = da if ctx.needs_input_grad[0] else None
+        gb = axpby(da, None, -1.0, 0.0) if ctx.needs_input_grad[1] else None
+        return ga, gb
+
+
+def mse_loss(a, b):
+    return _Mse.apply(a, b)
+
+
+# ---------------------------------------------------------------------------------------------
+# conditioning net's depth stencil (networks.py:221-225,239), unfused so the hidden tensors are on the tape
+# ---------------------------------------------------------------------------------------------
+class _DepthStencil(_F):
+    @staticmethod
+    def forward(ctx, x, w1, b1, slope, w2, b2):
+        xx, ww1, bb1, ss, ww2, bb2 = (_f32(t) for t in (x, w1, b1, slope, w2, b2))
+        B, D, H, W = xx.shape
+        Cm = ww1.shape[0]
+        st = _stream()
+        v1 = torch.empty((B, Cm, D, H, W), device=xx.device, dtype=torch.float32)
+        _lib.call("cwfa_stencil3d_1toC_f32", xx.data_ptr(), ww1.data_ptr(), bb1.data_ptr(), v1.data_ptr(), B, D, H, W, Cm, 0, st)
+        h = torch.empty_like(v1)
+        _lib.call("cwfa_prelu_f32", v1.data_ptr(), ss.data_ptr(), h.data_ptr(), v1.numel(), st)
+        y = torch.empty_like(xx)
+        _lib.call("cwfa_stencil3d_Cto1_f32", h.data_ptr(), ww2.data_ptr(), bb2.data_ptr(), y.data_ptr(), B, D, H, W, Cm, 0, st)
+        ctx.save_for_backward(xx, ww1, ss, ww2, v1, h)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w1, slope, w2, v1, h = ctx.saved_tensors
+        dy = ops._ck(dy)
+        B, D, H, W = x.shape
+        Cm = w1.shape[0]
+        st = _stream()
+        lib = _lib.load()
+        dev = x.device
+        ws = torch.empty(max(lib.cwfa_stencil3d_wgrad_workspace_floats(Cm), lib.cwfa_reduce_workspace_blocks()), device=dev, dtype=torch.float32)
+        dh = torch.empty_like(h)
+        _lib.call("cwfa_stencil3d_1toC_f32", dy.data_ptr(), w2.data_ptr(), None, dh.data_ptr(), B, D, H, W, Cm, 1, st)
+        dw2 = torch.empty_like(w2)
+        _lib.call("cwfa_stencil3d_wgrad_f32", dy.data_ptr(), h.data_ptr(), dw2.data_ptr(), ws.data_ptr(), B, D, H, W, Cm, 1, st)
+        db2 = channel_sum(dy.reshape(1, 1, -1)).reshape(1)
+        dv1 = dh                                     # in place: dh is not needed afterwards
+        dslope = torch.empty(1, device=dev, dtype=torch.float32)
+        _lib.call("cwfa_prelu_bwd_f32", dh.data_ptr(), v1.data_ptr(), slope.data_ptr(), dv1.data_ptr(), dslope.data_ptr(), ws.data_ptr(),
+                  v1.numel(), st)
+        dw1 = torch.empty_like(w1)
+        _lib.call("cwfa_stencil3d_wgrad_f32", x.data_ptr(), dv1.data_ptr(), dw1.data_ptr(), ws.data_ptr(), B, D, H, W, Cm, 0, st)
+        db1 = channel_sum(dv1.reshape(B, Cm, -1))
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            _lib.call("cwfa_stencil3d_Cto1_f32", dv1.data_ptr(), w1.data_ptr(), None, dx.data_ptr(), B, D, H, W, Cm, 1, st)
+        return dx, dw1, db1, dslope.reshape(slope.shape), dw2, db2
+
+
+def depth_stencil3d(x, w1, b1, slope, w2, b2):
+    return _DepthStencil.apply(x, w1, b1, slope, w2, b2)

@@ -1,0 +1,490 @@
+// Training-time (backward) kernels of the fp32 module path, sm_100a.
+//
+// The reference trains one flow level at a time with autograd (CWFA.py:928-1015: inverse pass with
+// gradients for the MSE term, forward pass for the NLL term, Lion update).  These kernels are the
+// hand-written adjoints of the forward kernels in elementwise.cu / conv_f32.cu:
+//   * conv2d weight gradient (register-tiled, split over pixel tiles, deterministic two-stage sum);
+//     the data gradient is the forward direct convolution with flipped/transposed weights;
+//   * affine coupling adjoint (dx, d a_s through the atan clamp, d a_t, log-det cotangent folded in);
+//   * ELU / PReLU adjoints, the 3-D depth-stencil convolutions of the conditioning net and their
+//     weight gradients, the Lion update on a flat parameter buffer.
+// All reductions are two-stage with a fixed summation order (bit-reproducible run to run).
+#include "common.cuh"
+
+using namespace cwfa;
+
+// ------------------------------------------------------------------------------------------
+// conv2d weight gradient: dW[co,ci,kh,kw] = sum_{n,h,w} dy[n,co,h,w] * x[n,ci,h+kh-p,w+kw-p]
+// CTA = 32 output channels x 32 input channels; a thread owns a 2x2 channel block x KS*KS taps and
+// walks the 256 pixels of a tile with a sliding register window over x.
+// ------------------------------------------------------------------------------------------
+constexpr int WG_C = 32;            // channel block (both Cout and Cin)
+constexpr int WG_TH = 8, WG_TW = 32;
+constexpr int WG_DPLANE = WG_TH * WG_TW + 1;
+
+template <int KS>
+struct WgradGeom {
+    static constexpr int XH = WG_TH + KS - 1, XW = WG_TW + KS - 1;
+    static constexpr int XPLANE = (XH * XW) | 1;     // odd plane stride: 16 channels hit 16 banks
+    static constexpr size_t smem = sizeof(float) * (WG_C * XPLANE + WG_C * WG_DPLANE);
+};
+
+template <int KS>
+__global__ void __launch_bounds__(256) conv2d_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                           float* __restrict__ part, int N, int Cin, int H, int W,
+                                                           int Cout, int tiles_x, int tiles_y, int n_ci_blk) {
+    using G = WgradGeom<KS>;
+    constexpr int PAD = KS / 2, KK = KS * KS;
+    extern __shared__ float smem[];
+    float* xs = smem;                       // [WG_C][XPLANE]
+    float* ds = smem + WG_C * G::XPLANE;    // [WG_C][WG_DPLANE]
+    const int tid = threadIdx.x;
+    const int tco = tid >> 4, tci = tid & 15;          // channels tco, tco+16 / tci, tci+16
+    const int co0 = (blockIdx.y / n_ci_blk) * WG_C, ci0 = (blockIdx.y % n_ci_blk) * WG_C;
+    const int tiles = tiles_x * tiles_y;
+    const int64_t P = (int64_t)H * W;
+
+    float acc[2][2][KK];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int t = 0; t < KK; ++t) acc[i][j][t] = 0.f;
+
+    for (int item = blockIdx.x; item < N * tiles; item += gridDim.x) {
+        const int n = item / tiles, t = item % tiles;
+        const int h0 = (t / tiles_x) * WG_TH, w0 = (t % tiles_x) * WG_TW;
+        __syncthreads();
+        for (int i = tid; i < WG_C * G::XH * G::XW; i += 256) {
+            const int cl = i / (G::XH * G::XW), rem = i % (G::XH * G::XW);
+            const int r = rem / G::XW, c = rem % G::XW;
+            const int gh = h0 + r - PAD, gw = w0 + c - PAD, ci = ci0 + cl;
+            float v = 0.f;
+            if (ci < Cin && gh >= 0 && gh < H && gw >= 0 && gw < W) v = __ldg(x + ((int64_t)n * Cin + ci) * P + (int64_t)gh * W + gw);
+            xs[cl * G::XPLANE + rem] = v;
+        }
+        for (int i = tid; i < WG_C * WG_TH * WG_TW; i += 256) {
+            const int cl = i / (WG_TH * WG_TW), pix = i % (WG_TH * WG_TW);
+            const int gh = h0 + pix / WG_TW, gw = w0 + pix % WG_TW, co = co0 + cl;
+            float v = 0.f;
+            if (co < Cout && gh < H && gw < W) v = __ldg(dy + ((int64_t)n * Cout + co) * P + (int64_t)gh * W + gw);
+            ds[cl * WG_DPLANE + pix] = v;
+        }
+        __syncthreads();
+        const float* x0 = xs + tci * G::XPLANE;
+        const float* x1 = xs + (tci + 16) * G::XPLANE;
+        const float* d0 = ds + tco * WG_DPLANE;
+        const float* d1 = ds + (tco + 16) * WG_DPLANE;
+        for (int r = 0; r < WG_TH; ++r) {
+            float win[2][KS][KS];
+#pragma unroll
+            for (int kh = 0; kh < KS; ++kh)
+#pragma unroll
+                for (int kw = 0; kw < KS - 1; ++kw) {
+                    win[0][kh][kw + 1] = x0[(r + kh) * G::XW + kw];
+                    win[1][kh][kw + 1] = x1[(r + kh) * G::XW + kw];
+                }
+#pragma unroll
+            for (int c = 0; c < WG_TW; ++c) {
+#pragma unroll
+                for (int kh = 0; kh < KS; ++kh) {
+#pragma unroll
+                    for (int kw = 0; kw < KS - 1; ++kw) {
+                        win[0][kh][kw] = win[0][kh][kw + 1];
+                        win[1][kh][kw] = win[1][kh][kw + 1];
+                    }
+                    win[0][kh][KS - 1] = x0[(r + kh) * G::XW + c + KS - 1];
+                    win[1][kh][KS - 1] = x1[(r + kh) * G::XW + c + KS - 1];
+                }
+                const float g0 = d0[r * WG_TW + c], g1 = d1[r * WG_TW + c];
+#pragma unroll
+                for (int kh = 0; kh < KS; ++kh)
+#pragma unroll
+                    for (int kw = 0; kw < KS; ++kw) {
+                        acc[0][0][kh * KS + kw] = fmaf(g0, win[0][kh][kw], acc[0][0][kh * KS + kw]);
+                        acc[0][1][kh * KS + kw] = fmaf(g0, win[1][kh][kw], acc[0][1][kh * KS + kw]);
+                        acc[1][0][kh * KS + kw] = fmaf(g1, win[0][kh][kw], acc[1][0][kh * KS + kw]);
+                        acc[1][1][kh * KS + kw] = fmaf(g1, win[1][kh][kw], acc[1][1][kh * KS + kw]);
+                    }
+            }
+        }
+    }
+    float* dst = part + (int64_t)blockIdx.x * Cout * Cin * KK;
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int co = co0 + tco + 16 * i, ci = ci0 + tci + 16 * j;
+            if (co < Cout && ci < Cin) {
+#pragma unroll
+                for (int t = 0; t < KK; ++t) dst[((int64_t)co * Cin + ci) * KK + t] = acc[i][j][t];
+            }
+        }
+}
+
+// out[i] = sum_k part[k*n + i] (fixed order, double accumulation), optionally accumulated into out.
+__global__ void __launch_bounds__(256) partial_sum_kernel(const float* __restrict__ part, float* __restrict__ out, int64_t n,
+                                                          int nparts, int accumulate) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s = 0.0;
+    for (int k = 0; k < nparts; ++k) s += (double)part[(int64_t)k * n + i];
+    out[i] = accumulate ? out[i] + (float)s : (float)s;
+}
+
+static int wgrad_chunks(int N, int H, int W, int Cout, int Cin) {
+    const int tiles = ceil_div(W, WG_TW) * ceil_div(H, WG_TH);
+    const int combos = ceil_div(Cout, WG_C) * ceil_div(Cin, WG_C);
+    int chunks = (kNumSMs * 4) / combos;
+    if (chunks < 1) chunks = 1;
+    const int64_t items = (int64_t)N * tiles;
+    if (chunks > items) chunks = (int)items;
+    return chunks;
+}
+
+extern "C" int64_t cwfa_conv2d_wgrad_workspace_floats(int N, int Cin, int H, int W, int Cout, int KH, int KW) {
+    return (int64_t)wgrad_chunks(N, H, W, Cout, Cin) * Cout * Cin * KH * KW;
+}
+
+extern "C" int cwfa_conv2d_wgrad_f32(const float* x, const float* dy, float* dw, float* workspace, int N, int Cin, int H,
+                                     int W, int Cout, int KH, int KW, int accumulate, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N <= 0 || Cin <= 0 || Cout <= 0 || H <= 0 || W <= 0 || KH != KW || (KH != 1 && KH != 3)) {
+        set_error("conv2d_wgrad: unsupported shape (square kernels of size 1 or 3, got %dx%d)", KH, KW);
+        return CWFA_EINVAL;
+    }
+    const int tiles_x = ceil_div(W, WG_TW), tiles_y = ceil_div(H, WG_TH);
+    const int n_ci = ceil_div(Cin, WG_C), n_co = ceil_div(Cout, WG_C);
+    const int chunks = wgrad_chunks(N, H, W, Cout, Cin);
+    dim3 grid(chunks, n_co * n_ci);
+    if (KH == 3) {
+        static bool attr = false;
+        if (!attr) { cudaFuncSetAttribute(conv2d_wgrad_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WgradGeom<3>::smem); attr = true; }
+        conv2d_wgrad_kernel<3><<<grid, 256, WgradGeom<3>::smem, st>>>(x, dy, workspace, N, Cin, H, W, Cout, tiles_x, tiles_y, n_ci);
+    } else {
+        static bool attr = false;
+        if (!attr) { cudaFuncSetAttribute(conv2d_wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WgradGeom<1>::smem); attr = true; }
+        conv2d_wgrad_kernel<1><<<grid, 256, WgradGeom<1>::smem, st>>>(x, dy, workspace, N, Cin, H, W, Cout, tiles_x, tiles_y, n_ci);
+    }
+    int rc = check_launch("conv2d_wgrad");
+    if (rc) return rc;
+    const int64_t n = (int64_t)Cout * Cin * KH * KW;
+    partial_sum_kernel<<<ceil_div(n, 256), 256, 0, st>>>(workspace, dw, n, chunks, accumulate);
+    return check_launch("conv2d_wgrad_finalize");
+}
+
+// Weights of the data-gradient convolution: wt[ci,co,kh,kw] = w[co,ci,KH-1-kh,KW-1-kw]
+// (dx = conv_same(dy, wt) for stride 1, odd kernels).
+__global__ void dgrad_weights_kernel(const float* __restrict__ w, float* __restrict__ wt, int Cout, int Cin, int KH, int KW) {
+    const int64_t n = (int64_t)Cout * Cin * KH * KW;
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int kw = (int)(i % KW), kh = (int)((i / KW) % KH);
+    const int co = (int)((i / ((int64_t)KW * KH)) % Cout), ci = (int)(i / ((int64_t)KW * KH * Cout));
+    wt[i] = __ldg(w + (((int64_t)co * Cin + ci) * KH + (KH - 1 - kh)) * KW + (KW - 1 - kw));
+}
+extern "C" int cwfa_conv2d_dgrad_weights_f32(const float* w, float* wt, int Cout, int Cin, int KH, int KW, void* stream) {
+    const int64_t n = (int64_t)Cout * Cin * KH * KW;
+    if (n <= 0) { set_error("dgrad_weights: bad shape"); return CWFA_EINVAL; }
+    dgrad_weights_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(w, wt, Cout, Cin, KH, KW);
+    return check_launch("dgrad_weights");
+}
+
+// ------------------------------------------------------------------------------------------
+// activation adjoints / small element-wise helpers
+// ------------------------------------------------------------------------------------------
+static inline int ew_blocks(int64_t n) {
+    int64_t b = (n + 255) / 256;
+    if (b > kNumSMs * 16) b = kNumSMs * 16;
+    return b < 1 ? 1 : (int)b;
+}
+
+// ELU(alpha=1) adjoint from the OUTPUT y: dv = dy * (y > 0 ? 1 : y + 1)
+__global__ void __launch_bounds__(256) elu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y,
+                                                      float* __restrict__ dv, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float yy = __ldg(y + i);
+        dv[i] = __ldg(dy + i) * (yy > 0.f ? 1.f : yy + 1.f);
+    }
+}
+extern "C" int cwfa_elu_bwd_f32(const float* dy, const float* y, float* dv, int64_t n, void* stream) {
+    if (n <= 0) { set_error("elu_bwd: bad size"); return CWFA_EINVAL; }
+    elu_bwd_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(dy, y, dv, n);
+    return check_launch("elu_bwd");
+}
+
+// out = alpha * a + beta * b   (b may be NULL)
+__global__ void __launch_bounds__(256) axpby_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                    float* __restrict__ out, float alpha, float beta, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = alpha * a[i] + (b ? beta * b[i] : 0.f);
+}
+extern "C" int cwfa_axpby_f32(const float* a, const float* b, float* out, float alpha, float beta, int64_t n, void* stream) {
+    if (n <= 0 || !a || !out) { set_error("axpby: bad args"); return CWFA_EINVAL; }
+    axpby_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(a, b, out, alpha, beta, n);
+    return check_launch("axpby");
+}
+
+// PReLU with one shared slope (nn.PReLU(), networks.py:209): y = v > 0 ? v : a*v
+__global__ void __launch_bounds__(256) prelu_fwd_kernel(const float* __restrict__ v, const float* __restrict__ slope,
+                                                        float* __restrict__ y, int64_t n) {
+    const float a = __ldg(slope);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float x = v[i];
+        y[i] = x > 0.f ? x : a * x;
+    }
+}
+extern "C" int cwfa_prelu_f32(const float* v, const float* slope, float* y, int64_t n, void* stream) {
+    if (n <= 0) { set_error("prelu: bad size"); return CWFA_EINVAL; }
+    prelu_fwd_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(v, slope, y, n);
+    return check_launch("prelu");
+}
+
+constexpr int kReduceBlocks = kNumSMs * 2;
+// dv = v > 0 ? dy : a*dy ; dslope = sum_{v<=0} v*dy  (torch's PReLU adjoint convention at v = 0)
+__global__ void __launch_bounds__(256) prelu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ v,
+                                                        const float* __restrict__ slope, float* __restrict__ dv,
+                                                        float* __restrict__ ws, int64_t n) {
+    const float a = __ldg(slope);
+    float s = 0.f, dummy = 0.f;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float x = v[i], g = dy[i];
+        if (x > 0.f) {
+            dv[i] = g;
+        } else {
+            dv[i] = a * g;
+            s = fmaf(x, g, s);
+        }
+    }
+    block_sum2(s, dummy);
+    if (threadIdx.x == 0) ws[blockIdx.x] = s;
+}
+extern "C" int cwfa_reduce_workspace_blocks(void) { return kReduceBlocks; }
+extern "C" int cwfa_prelu_bwd_f32(const float* dy, const float* v, const float* slope, float* dv, float* dslope,
+                                  float* workspace, int64_t n, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n <= 0) { set_error("prelu_bwd: bad size"); return CWFA_EINVAL; }
+    prelu_bwd_kernel<<<kReduceBlocks, 256, 0, st>>>(dy, v, slope, dv, workspace, n);
+    int rc = check_launch("prelu_bwd");
+    if (rc) return rc;
+    partial_sum_kernel<<<1, 32, 0, st>>>(workspace, dslope, 1, kReduceBlocks, 0);
+    return check_launch("prelu_bwd_finalize");
+}
+
+// ------------------------------------------------------------------------------------------
+// affine coupling adjoint (forward: elementwise.cu affine_kernel; coupling_layers.py:490-500)
+//   fwd  y = e^s x + t        : dx = dy e^s ; dt = dy ; ds = dy x e^s + gJ
+//   inv  y = (x - t) e^{-s}   : dx = dy e^{-s} ; dt = -dx ; ds = -dy y - gJ
+//   s = kk atan(a_s) -> d a_s = ds kk / (1 + a_s^2)  (raw: d a_s = ds);  t = t_scale a_t
+// ------------------------------------------------------------------------------------------
+template <bool INV>
+__global__ void __launch_bounds__(256) affine_bwd_kernel(const float* __restrict__ x, const float* __restrict__ a_s,
+                                                         const float* __restrict__ a_t, const float* __restrict__ dy,
+                                                         const float* __restrict__ g_logdet, float* __restrict__ dx,
+                                                         float* __restrict__ da_s, float* __restrict__ da_t, int64_t n,
+                                                         int64_t ld_s, int64_t ld_t, int64_t ld_ds, int64_t ld_dt,
+                                                         float kk, float t_scale, int raw) {
+    const int b = blockIdx.y;
+    const float* xs = x ? x + (int64_t)b * n : nullptr;
+    const float* ss = a_s + (int64_t)b * ld_s;
+    const float* ts = a_t + (int64_t)b * ld_t;
+    const float* gs = dy + (int64_t)b * n;
+    const float gj = g_logdet ? __ldg(g_logdet + b) : 0.f;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float as = ss[i];
+        const float s = raw ? as : kk * atanf(as);
+        const float g = gs[i];
+        const float xv = xs ? xs[i] : 0.f;
+        float gx, gt, gsv;
+        if (INV) {
+            const float e = expf(-s);
+            const float y = (xv - t_scale * ts[i]) * e;
+            gx = g * e;
+            gt = -gx;
+            gsv = -g * y - gj;
+        } else {
+            const float e = expf(s);
+            gx = g * e;
+            gt = g;
+            gsv = gx * xv + gj;
+        }
+        if (dx) dx[(int64_t)b * n + i] = gx;
+        if (da_t) da_t[(int64_t)b * ld_dt + i] = gt * t_scale;
+        if (da_s) da_s[(int64_t)b * ld_ds + i] = raw ? gsv : gsv * kk / fmaf(as, as, 1.f);
+    }
+}
+extern "C" int cwfa_affine_bwd(const float* x, const float* a_s, const float* a_t, const float* dy, const float* g_logdet,
+                               float* dx, float* da_s, float* da_t, int B, int ch, int64_t P, int64_t ld_s, int64_t ld_t,
+                               int64_t ld_ds, int64_t ld_dt, float clamp, float k_atan, float t_scale, int flags,
+                               void* stream) {
+    const int inverse = flags & 1, raw = (flags >> 1) & 1;
+    if (B <= 0 || ch <= 0 || P <= 0 || !a_s || !a_t || !dy) { set_error("affine_bwd: bad args"); return CWFA_EINVAL; }
+    if (!x && !inverse) { set_error("affine_bwd: x may be NULL only in inverse mode"); return CWFA_EINVAL; }
+    const int64_t n = (int64_t)ch * P;
+    dim3 grid(ew_blocks(n) < kNumSMs * 4 ? ew_blocks(n) : kNumSMs * 4, B);
+    const float kk = clamp * k_atan;
+    if (inverse) affine_bwd_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, a_s, a_t, dy, g_logdet, dx, da_s, da_t, n, ld_s, ld_t, ld_ds, ld_dt, kk, t_scale, raw);
+    else affine_bwd_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(x, a_s, a_t, dy, g_logdet, dx, da_s, da_t, n, ld_s, ld_t, ld_ds, ld_dt, kk, t_scale, raw);
+    return check_launch("affine_bwd");
+}
+
+// ------------------------------------------------------------------------------------------
+// Conditioning-net depth stencil, unfused (training): Conv3d(1,Cm,3,p1) and Conv3d(Cm,1,3,p1) over
+// the (H,W,depth) volume of a (B,D,H,W) tensor (networks.py:221-225,239), plus weight gradients.
+// Hidden tensors are (B,Cm,D,H,W).  Tap index = (kh*3+kw)*3+kd, as in the Conv3d weight (Cm,1,3,3,3)
+// whose spatial axes are (H,W,depth).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_taps27(const float* __restrict__ vol, int D, int H, int W, int d, int h, int w, float* v) {
+    const int64_t P = (int64_t)H * W;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+            for (int kd = 0; kd < 3; ++kd) {
+                const int gd = d + kd - 1, gh = h + kh - 1, gw = w + kw - 1;
+                v[(kh * 3 + kw) * 3 + kd] = (gd >= 0 && gd < D && gh >= 0 && gh < H && gw >= 0 && gw < W)
+                                                ? __ldg(vol + (int64_t)gd * P + (int64_t)gh * W + gw) : 0.f;
+            }
+}
+
+// out[b,c,pos] = bias[c] + sum_t w[c,t] * x[b,pos+t]   (flip: use w[c,26-t], the adjoint of Cm->1)
+__global__ void __launch_bounds__(256) stencil_1toC_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                           const float* __restrict__ bias, float* __restrict__ out, int D,
+                                                           int H, int W, int Cm, int flip) {
+    extern __shared__ float wsm[];      // [Cm][27] + [Cm]
+    for (int i = threadIdx.x; i < Cm * 27; i += blockDim.x) {
+        const int c = i / 27, t = i % 27;
+        wsm[i] = __ldg(w + c * 27 + (flip ? 26 - t : t));
+    }
+    for (int i = threadIdx.x; i < Cm; i += blockDim.x) wsm[Cm * 27 + i] = bias ? __ldg(bias + i) : 0.f;
+    __syncthreads();
+    const int b = blockIdx.y;
+    const int64_t V = (int64_t)D * H * W, P = (int64_t)H * W;
+    for (int64_t pos = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; pos < V; pos += (int64_t)gridDim.x * blockDim.x) {
+        const int d = (int)(pos / P), h = (int)((pos % P) / W), ww = (int)(pos % W);
+        float v[27];
+        load_taps27(x + (int64_t)b * V, D, H, W, d, h, ww, v);
+        for (int c = 0; c < Cm; ++c) {
+            float a = wsm[Cm * 27 + c];
+#pragma unroll
+            for (int t = 0; t < 27; ++t) a = fmaf(wsm[c * 27 + t], v[t], a);
+            out[((int64_t)b * Cm + c) * V + pos] = a;
+        }
+    }
+}
+
+// out[b,pos] = bias + sum_c sum_t w[c,t] * hid[b,c,pos+t]   (flip: w[c,26-t], the adjoint of 1->Cm)
+__global__ void __launch_bounds__(256) stencil_Cto1_kernel(const float* __restrict__ hid, const float* __restrict__ w,
+                                                           const float* __restrict__ bias, float* __restrict__ out, int D,
+                                                           int H, int W, int Cm, int flip) {
+    extern __shared__ float wsm[];
+    for (int i = threadIdx.x; i < Cm * 27; i += blockDim.x) {
+        const int c = i / 27, t = i % 27;
+        wsm[i] = __ldg(w + c * 27 + (flip ? 26 - t : t));
+    }
+    __syncthreads();
+    const int b = blockIdx.y;
+    const int64_t V = (int64_t)D * H * W, P = (int64_t)H * W;
+    const float b0 = bias ? __ldg(bias) : 0.f;
+    for (int64_t pos = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; pos < V; pos += (int64_t)gridDim.x * blockDim.x) {
+        const int d = (int)(pos / P), h = (int)((pos % P) / W), ww = (int)(pos % W);
+        float a = b0;
+        for (int c = 0; c < Cm; ++c) {
+            float v[27];
+            load_taps27(hid + ((int64_t)b * Cm + c) * V, D, H, W, d, h, ww, v);
+#pragma unroll
+            for (int t = 0; t < 27; ++t) a = fmaf(wsm[c * 27 + t], v[t], a);
+        }
+        out[(int64_t)b * V + pos] = a;
+    }
+}
+
+// part[blk][c][t] = sum_{b,pos in blk} multi[b,c,pos] * single[b,pos+t]  (flip: stored at 26-t)
+//   1->Cm weights: single = x, multi = d(hidden pre-activation), flip = 0
+//   Cm->1 weights: single = dy, multi = hidden,                 flip = 1
+constexpr int kStencilWgBlocks = kNumSMs;
+__global__ void __launch_bounds__(256) stencil_wgrad_kernel(const float* __restrict__ single, const float* __restrict__ multi,
+                                                            float* __restrict__ part, int B, int D, int H, int W, int Cm,
+                                                            int flip) {
+    __shared__ float red[8][27];
+    const int c = blockIdx.y;
+    const int64_t V = (int64_t)D * H * W, P = (int64_t)H * W;
+    float acc[27];
+#pragma unroll
+    for (int t = 0; t < 27; ++t) acc[t] = 0.f;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < (int64_t)B * V; i += (int64_t)gridDim.x * blockDim.x) {
+        const int b = (int)(i / V);
+        const int64_t pos = i % V;
+        const int d = (int)(pos / P), h = (int)((pos % P) / W), ww = (int)(pos % W);
+        const float g = __ldg(multi + ((int64_t)b * Cm + c) * V + pos);
+        float v[27];
+        load_taps27(single + (int64_t)b * V, D, H, W, d, h, ww, v);
+#pragma unroll
+        for (int t = 0; t < 27; ++t) acc[t] = fmaf(g, v[t], acc[t]);
+    }
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+#pragma unroll
+    for (int t = 0; t < 27; ++t) {
+        const float s = warp_sum(acc[t]);
+        if (lane == 0) red[wp][t] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < 27) {
+        float s = 0.f;
+        for (int k = 0; k < 8; ++k) s += red[k][threadIdx.x];
+        const int t = flip ? 26 - threadIdx.x : threadIdx.x;
+        part[((int64_t)blockIdx.x * Cm + c) * 27 + t] = s;
+    }
+}
+
+extern "C" int cwfa_stencil3d_1toC_f32(const float* x, const float* w, const float* bias, float* out, int B, int D, int H,
+                                       int W, int Cm, int flip, void* stream) {
+    if (B <= 0 || D <= 0 || H <= 0 || W <= 0 || Cm <= 0 || Cm > 256 || B > 65535) { set_error("stencil3d_1toC: bad shape"); return CWFA_EINVAL; }
+    const int64_t V = (int64_t)D * H * W;
+    dim3 grid(ew_blocks(V), B);
+    stencil_1toC_kernel<<<grid, 256, sizeof(float) * Cm * 28, (cudaStream_t)stream>>>(x, w, bias, out, D, H, W, Cm, flip);
+    return check_launch("stencil3d_1toC");
+}
+extern "C" int cwfa_stencil3d_Cto1_f32(const float* hid, const float* w, const float* bias, float* out, int B, int D, int H,
+                                       int W, int Cm, int flip, void* stream) {
+    if (B <= 0 || D <= 0 || H <= 0 || W <= 0 || Cm <= 0 || Cm > 256 || B > 65535) { set_error("stencil3d_Cto1: bad shape"); return CWFA_EINVAL; }
+    const int64_t V = (int64_t)D * H * W;
+    dim3 grid(ew_blocks(V), B);
+    stencil_Cto1_kernel<<<grid, 256, sizeof(float) * Cm * 27, (cudaStream_t)stream>>>(hid, w, bias, out, D, H, W, Cm, flip);
+    return check_launch("stencil3d_Cto1");
+}
+extern "C" int cwfa_stencil3d_wgrad_workspace_floats(int Cm) { return kStencilWgBlocks * Cm * 27; }
+extern "C" int cwfa_stencil3d_wgrad_f32(const float* single, const float* multi, float* dw, float* workspace, int B, int D,
+                                        int H, int W, int Cm, int flip, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (B <= 0 || D <= 0 || H <= 0 || W <= 0 || Cm <= 0 || Cm > 65535) { set_error("stencil3d_wgrad: bad shape"); return CWFA_EINVAL; }
+    stencil_wgrad_kernel<<<dim3(kStencilWgBlocks, Cm), 256, 0, st>>>(single, multi, workspace, B, D, H, W, Cm, flip);
+    int rc = check_launch("stencil3d_wgrad");
+    if (rc) return rc;
+    const int64_t n = (int64_t)Cm * 27;
+    partial_sum_kernel<<<ceil_div(n, 256), 256, 0, st>>>(workspace, dw, n, kStencilWgBlocks, 0);
+    return check_launch("stencil3d_wgrad_finalize");
+}
+
+// ------------------------------------------------------------------------------------------
+// Lion update on a flat buffer (lion_pytorch 0.0.7 `update_fn`, the optimiser of CWFA.py:381,608-610):
+//   p *= 1 - lr*wd ; p -= lr * sign(b1*m + (1-b1)*g) ; m = b2*m + (1-b2)*g      (g pre-scaled by gscale)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) lion_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                   int64_t n, float lr, float b1, float b2, float wd, float gscale) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float gg = g[i] * gscale, mm = m[i];
+        const float u = b1 * mm + (1.f - b1) * gg;
+        const float sg = (u > 0.f) ? 1.f : (u < 0.f ? -1.f : 0.f);
+        p[i] = p[i] * (1.f - lr * wd) - lr * sg;
+        m[i] = b2 * mm + (1.f - b2) * gg;
+    }
+}
+extern "C" int cwfa_lion_step_f32(float* p, const float* g, float* m, int64_t n, float lr, float beta1, float beta2,
+                                  float weight_decay, float grad_scale, void* stream) {
+    if (n <= 0 || !p || !g || !m) { set_error("lion_step: bad args"); return CWFA_EINVAL; }
+    lion_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(p, g, m, n, lr, beta1, beta2, weight_decay, grad_scale);
+    return check_launch("lion_step");
+}

@@ -38,6 +38,22 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+def _grad_on(*tensors) -> bool:
+    """True when the call must go on the autograd tape (cwfa_b200/autograd.py: forward and adjoint both run this repo's
+    kernels).  Inside an autograd Function's forward/backward gradients are disabled, so the raw launches below run."""
+    return torch.is_grad_enabled() and any(torch.is_tensor(t) and t.requires_grad for t in tensors)
+
+
+_warned = set()
+
+
+def _no_adjoint(what: str) -> None:
+    if what not in _warned:
+        _warned.add(what)
+        import warnings
+        warnings.warn(f"cwfa_b200: {what} has no adjoint kernel yet; its output is detached from the autograd graph")
+
+
 def perm_i32(perm: torch.Tensor, device) -> torch.Tensor:
     """int32 device copy of a LongTensor permutation, cached ON the source tensor object (keyed by
     device and in-place version) so that the cache can never outlive or alias the permutation."""
@@ -55,6 +71,9 @@ def perm_i32(perm: torch.Tensor, device) -> torch.Tensor:
 # ---------------------------------------------------------------------------------------------
 def haar1d_forward(x: torch.Tensor) -> torch.Tensor:
     """(B,C,H,W) -> (B,C,H,W) with [:, :C/2] = lo, [:, C/2:] = hi.  INN_utils.py:153-156."""
+    if _grad_on(x):
+        from . import autograd as ag
+        return ag.haar1d(x, False)
     x = _ck(x, "x")
     B, C = x.shape[0], x.shape[1]
     P = x[0, 0].numel()
@@ -67,6 +86,9 @@ def haar1d_forward(x: torch.Tensor) -> torch.Tensor:
 
 def haar1d_inverse(x: torch.Tensor) -> torch.Tensor:
     """Inverse of haar1d_forward on one (B,C,H,W) tensor.  INN_utils.py:157-160."""
+    if _grad_on(x):
+        from . import autograd as ag
+        return ag.haar1d(x, True)
     x = _ck(x, "x")
     B, C = x.shape[0], x.shape[1]
     P = x[0, 0].numel()
@@ -79,6 +101,9 @@ def haar1d_inverse(x: torch.Tensor) -> torch.Tensor:
 
 def haar1d_merge(lo: torch.Tensor, hi: torch.Tensor) -> torch.Tensor:
     """Fused Split^-1 + IDWT: two (B,C/2,H,W) tensors -> (B,C,H,W) without the concat copy."""
+    if _grad_on(lo, hi):
+        from . import autograd as ag
+        return ag.haar1d_merge(lo, hi)
     lo, hi = _ck(lo, "lo"), _ck(hi, "hi")
     B, h = lo.shape[0], lo.shape[1]
     P = lo[0, 0].numel()
@@ -89,6 +114,9 @@ def haar1d_merge(lo: torch.Tensor, hi: torch.Tensor) -> torch.Tensor:
 
 def haar1d_split(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     """Fused DWT + Split: (B,C,H,W) -> separate contiguous (lo, hi)."""
+    if _grad_on(x):
+        from . import autograd as ag
+        return ag.haar1d_split(x)
     x = _ck(x, "x")
     B, C = x.shape[0], x.shape[1]
     P = x[0, 0].numel()
@@ -118,6 +146,9 @@ def haar2d_up(y: torch.Tensor, order_by_wavelet: bool, fac: float) -> torch.Tens
 
 def permute(x: torch.Tensor, perm: torch.Tensor, axis: int) -> torch.Tensor:
     """y = x.index_select(axis, perm) for axis in {1,2,3} of a (B,C,H,W) tensor."""
+    if _grad_on(x):
+        from . import autograd as ag
+        return ag.permute(x, perm, axis)
     x = _ck(x, "x")
     if x.dim() != 4:
         x4 = x.reshape(x.shape[0], x.shape[1], 1, -1)
@@ -132,6 +163,18 @@ def permute(x: torch.Tensor, perm: torch.Tensor, axis: int) -> torch.Tensor:
     return y.view(x.shape)
 
 
+def _prep_inner(t: torch.Tensor):
+    """fp32 tensor whose per-sample (ch,H,W) block is contiguous, plus its batch stride in elements."""
+    B, ch = t.shape[0], t.shape[1]
+    P = t[0, 0].numel()
+    if t.dtype != torch.float32:
+        t = t.float()
+    inner_ok = t[0].is_contiguous() if B > 0 else True
+    if not inner_ok or (B > 1 and t.stride(0) < ch * P):
+        t = t.contiguous()
+    return t, (t.stride(0) if B > 1 else ch * P)
+
+
 def affine(x: Optional[torch.Tensor], a_s: torch.Tensor, a_t: torch.Tensor, *, inverse: bool,
            clamp: float = CLAMP_DEFAULT, t_scale: float = 1.0, want_sumsq: bool = False,
            k_atan: float = K_ATAN, s_is_final: bool = False):
@@ -139,19 +182,14 @@ def affine(x: Optional[torch.Tensor], a_s: torch.Tensor, a_t: torch.Tensor, *, i
     block is contiguous (e.g. the two channel halves of one subnet output)."""
     if not a_s.is_cuda:
         raise RuntimeError("cwfa_b200: affine needs CUDA tensors (no CPU fallback)")
+    if _grad_on(x, a_s, a_t):
+        from . import autograd as ag
+        y, logdet = ag.affine(x, a_s, a_t, inverse=inverse, clamp=clamp, t_scale=t_scale, k_atan=k_atan, s_is_final=s_is_final)
+        return (y, logdet, ag.sum_squares(y)) if want_sumsq else (y, logdet)
     B, ch = a_s.shape[0], a_s.shape[1]
     P = a_s[0, 0].numel()
-
-    def prep(t, name):
-        if t.dtype != torch.float32:
-            t = t.float()
-        inner_ok = t[0].is_contiguous() if B > 0 else True
-        if not inner_ok or (B > 1 and t.stride(0) < ch * P):
-            t = t.contiguous()
-        return t, (t.stride(0) if B > 1 else ch * P)
-
-    a_s, ld_s = prep(a_s, "a_s")
-    a_t, ld_t = prep(a_t, "a_t")
+    a_s, ld_s = _prep_inner(a_s)
+    a_t, ld_t = _prep_inner(a_t)
     xx = None if x is None else _ck(x, "x")
     y = torch.empty((B, ch) + tuple(a_s.shape[2:]), device=a_s.device, dtype=torch.float32)
     logdet = torch.empty(B, device=a_s.device, dtype=torch.float32)
@@ -166,6 +204,11 @@ def affine(x: Optional[torch.Tensor], a_s: torch.Tensor, a_t: torch.Tensor, *, i
 def conv2d(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, act: int = ACT_NONE,
            slope: Optional[torch.Tensor] = None, res: Optional[torch.Tensor] = None, res_mode: int = 0) -> torch.Tensor:
     """fp32 'same' convolution, stride 1.  v = conv+bias; (res_mode 1: +res); act; (res_mode 2: +res)."""
+    if _grad_on(x, w, bias, slope, res):
+        from . import autograd as ag
+        if ag.conv2d_supported(w, act, res, res_mode):
+            return ag.conv2d(x, w, bias, act=act, slope=slope, res=res, res_mode=res_mode)
+        _no_adjoint(f"conv2d {tuple(w.shape[2:])} act={act} res_mode={res_mode}")
     x, w = _ck(x, "x"), _ck(w, "w")
     N, Cin, H, W = x.shape
     Cout, Cin_w, KH, KW = w.shape
@@ -202,6 +245,9 @@ def conv_transpose2x2(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Ten
 
 def depth_stencil3d(x: torch.Tensor, w1, b1, slope, w2, b2) -> torch.Tensor:
     """Conv3d(1->Cm,3,p1) + PReLU + Conv3d(Cm->1,3,p1) over (H,W,depth) of a (B,ch,H,W) tensor."""
+    if _grad_on(x, w1, b1, slope, w2, b2):
+        from . import autograd as ag
+        return ag.depth_stencil3d(x, w1, b1, slope, w2, b2)
     x = _ck(x, "x")
     B, ch, H, W = x.shape
     w1, b1, w2, b2, slope = (_ck(t) for t in (w1, b1, w2, b2, slope))
@@ -276,6 +322,9 @@ def gate_add_(x: torch.Tensor, m: torch.Tensor, g: torch.Tensor) -> torch.Tensor
 
 def sum_squares(x: torch.Tensor) -> torch.Tensor:
     """Per-sample sum of squares over all non-batch axes -> (B,) (the ||z||^2 of CWFA.py:183)."""
+    if _grad_on(x):
+        from . import autograd as ag
+        return ag.sum_squares(x)
     x = _ck(x, "x")
     B = x.shape[0]
     n = x[0].numel()

@@ -1,0 +1,204 @@
+"""Training step of one flow level (BASELINE.json configs[3]).
+
+Reference: the fine-tune branch of ``run_CWFA`` (CWFA.py:586-613 optimiser setup, :928-1015 loss / backward / step):
+for flow level ``n`` the loss is ``w * MSE(gt_n, inn([z, vol_{n+1}], c, rev=True)) + (1 - w) * NLL`` with
+``NLL = (0.5 * ||Z||^2 - logdet.mean()) / numel`` from the forward pass ``inn(gt_n, c)``, ``w = INN_cond_weight = 0.40984``
+(main.py:107); the flow parameters and the level's conditioning net each get a Lion optimiser (lion_pytorch 0.0.7).
+
+Every arithmetic step is one of this repo's CUDA kernels: forward and adjoint kernels through ``cwfa_b200.autograd``
+(torch's autograd engine only orders them), the Lion update as ONE launch per parameter group on a flat buffer.
+Data parallelism: frames are sharded over ranks, gradients are summed with ONE all-reduce of the
+flat gradient buffer per optimiser (<= 4.6 MB for a flow level: a single bucket, sized for launch latency) over
+``torch.distributed`` (NCCL on NVLink; gloo in the CPU tests) and the 1/world factor is folded into the Lion kernel.
+"""
+from __future__ import annotations
+
+from typing import Dict, Iterable, List, Optional, Sequence
+
+import torch
+
+from . import _lib, ops
+
+INN_COND_WEIGHT = 0.40984      # main.py:107
+_ALIGN = 4                     # floats: every parameter starts on a 16-byte boundary of the flat buffer
+
+
+class FlatGroup:
+    """Parameters of one optimiser group re-homed into ONE flat fp32 buffer (``p.data`` and ``p.grad`` become views), so
+    that the optimiser update is one kernel launch and the data-parallel gradient reduction is one collective."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter]):
+        seen, mine, loose = set(), [], []
+        for p in params:
+            if id(p) in seen or not p.requires_grad:
+                continue
+            seen.add(id(p))
+            if not p.dtype.is_floating_point:
+                continue
+            (loose if getattr(p, "_cwfa_flat", False) else mine).append(p)
+        self.params, self.loose = mine, loose          # loose: already owned by another group (e.g. the shared PReLU, networks.py:209)
+        if not mine:
+            raise ValueError("FlatGroup: no trainable floating-point parameters")
+        dev = mine[0].device
+        offs, n = [], 0
+        for p in mine:
+            offs.append(n)
+            n += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+        self.flat = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.grad = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.offsets = offs
+        for p, o in zip(mine, offs):
+            v = self.flat[o:o + p.numel()].view(p.shape)
+            v.copy_(p.data)
+            p.data = v
+            p.grad = self.grad[o:o + p.numel()].view(p.shape)
+            p._cwfa_flat = True
+        self.loose_grads_ready = False
+
+    def zero_grad(self):
+        self.grad.zero_()
+        for p in self.loose:
+            p.grad = None
+
+    def grads_alias_flat(self) -> bool:
+        """Autograd accumulates in place into a pre-existing ``.grad``; if anything replaced one, copy it back."""
+        ok = True
+        for p, o in zip(self.params, self.offsets):
+            g = p.grad
+            view = self.grad[o:o + p.numel()]
+            if g is None:
+                view.zero_()
+            elif g.data_ptr() != view.data_ptr():
+                view.copy_(g.reshape(-1))
+                p.grad = view.view(p.shape)
+                ok = False
+        return ok
+
+
+class Lion:
+    """``lion_pytorch.Lion(params, lr=1e-4, betas=(0.9, 0.99), weight_decay=0.0)`` (v0.0.7; CWFA.py:381,608-610) with the
+    update in ``cwfa_lion_step_f32``: p *= 1 - lr*wd; p -= lr*sign(b1*m + (1-b1)*g); m = b2*m + (1-b2)*g.
+    ``params`` is an iterable of parameters or of group dicts ``{'params': ..., 'lr': ..., 'weight_decay': ...}``."""
+
+    def __init__(self, params, lr: float = 1e-4, betas=(0.9, 0.99), weight_decay: float = 0.0):
+        if lr <= 0.0:
+            raise ValueError("lr must be positive")
+        if not all(0.0 <= b <= 1.0 for b in betas):
+            raise ValueError("betas must lie in [0, 1]")
+        params = list(params)
+        groups = params if params and isinstance(params[0], dict) else [{"params": params}]
+        self.param_groups: List[Dict] = []
+        for g in groups:
+            fg = FlatGroup(list(g["params"]))
+            self.param_groups.append(dict(params=fg.params, flat=fg, lr=float(g.get("lr", lr)), betas=tuple(g.get("betas", betas)),
+                                          weight_decay=float(g.get("weight_decay", weight_decay)),
+                                          exp_avg=torch.zeros_like(fg.flat), loose_state={}))
+        self.grad_scale = 1.0
+
+    def zero_grad(self, set_to_none: bool = False):
+        for g in self.param_groups:
+            g["flat"].zero_grad()
+
+    def flat_grads(self) -> List[torch.Tensor]:
+        for g in self.param_groups:
+            g["flat"].grads_alias_flat()
+        return [g["flat"].grad for g in self.param_groups]
+
+    @torch.no_grad()
+    def step(self):
+        st = torch.cuda.current_stream().cuda_stream
+        for g in self.param_groups:
+            fg: FlatGroup = g["flat"]
+            if not fg.flat.is_cuda:
+                raise RuntimeError("cwfa_b200.Lion: parameters must live on a CUDA device (no CPU fallback)")
+            fg.grads_alias_flat()
+            b1, b2 = g["betas"]
+            _lib.call("cwfa_lion_step_f32", fg.flat.data_ptr(), fg.grad.data_ptr(), g["exp_avg"].data_ptr(), fg.flat.numel(),
+                      g["lr"], b1, b2, g["weight_decay"], float(self.grad_scale), st)
+            for p in fg.loose:
+                if p.grad is None:
+                    continue
+                m = g["loose_state"].setdefault(id(p), torch.zeros_like(p.data))
+                gr = ops._ck(p.grad)
+                _lib.call("cwfa_lion_step_f32", p.data.data_ptr(), gr.data_ptr(), m.data_ptr(), p.numel(), g["lr"], b1, b2,
+                          g["weight_decay"], float(self.grad_scale), st)
+
+
+def allreduce_gradients(optimizers: Sequence[Lion], group=None) -> int:
+    """Data-parallel gradient reduction: ONE sum all-reduce per flat gradient buffer; the mean's 1/world is applied inside
+    the Lion kernel (``grad_scale``) instead of in a separate pass.  Returns the number of collectives issued."""
+    import torch.distributed as dist
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        for o in optimizers:
+            o.grad_scale = 1.0
+        return 0
+    world = dist.get_world_size(group)
+    n = 0
+    for o in optimizers:
+        for g in o.flat_grads():
+            dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group)
+            n += 1
+        for pg in o.param_groups:
+            for p in pg["flat"].loose:
+                if p.grad is not None:
+                    dist.all_reduce(p.grad, op=dist.ReduceOp.SUM, group=group)
+                    n += 1
+        o.grad_scale = 1.0 / world
+    return n
+
+
+def allreduce_nll_terms(sumsq: torch.Tensor, logdet: torch.Tensor, group=None):
+    """Global NLL bookkeeping of a sharded batch: all-reduce of (sum ||z||^2, sum logdet, frame count) -> the three totals."""
+    import torch.distributed as dist
+    t = torch.stack([sumsq.sum().float(), logdet.sum().float(), torch.tensor(float(logdet.numel()), device=logdet.device)])
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, group=group)
+    return t[0], t[1], t[2]
+
+
+def flow_level_loss(model, n: int, gt: torch.Tensor, views: torch.Tensor, mean_vol: torch.Tensor, vol_in: torch.Tensor,
+                    z: Optional[torch.Tensor] = None, cond_weight: float = INN_COND_WEIGHT):
+    """Loss of flow level ``n`` exactly as CWFA.py:891-978 composes it (L2 regulariser, ``loss_func_reg='L2'``).
+
+    gt      (B, C_n, S, S)    ground-truth volume at level n (``gt_cache[n]``)
+    views   (B, 29, S, S)     normalised lenslet views
+    mean_vol(B, C_n/2, S, S)  mean-volume delta condition of the level
+    vol_in  (B, C_n/2, S, S)  the (detached) reconstruction of level n+1 that the inverse pass up-samples
+    Returns ``(loss, parts)``; parts = dict(mse, nll, sumsq (B,), logdet (B,)).
+    """
+    from . import autograd as ag
+    inn = model.conv_inn[n]
+    cond = model.cond_nets[n](views)[-1]                                  # CWFA.py:895
+    c = [cond, mean_vol]
+    if z is None:
+        z = torch.zeros((vol_in.shape[0],) + tuple(inn.global_out_shapes[0]), device=vol_in.device, dtype=torch.float32)
+    vol_rec, _ = inn([z, vol_in.detach()], c=c, rev=True)                 # CWFA.py:912 (with gradients)
+    mse = ag.mse_loss(gt, vol_rec)                                        # CWFA.py:953
+    (Z, _lo), logdet = inn(gt, c=c)                                       # CWFA.py:966
+    sumsq = ops.sum_squares(Z)
+    nll = (0.5 * sumsq.sum() - logdet.mean()) / vol_rec.numel()           # CWFA.py:970,978
+    loss = cond_weight * mse + (1.0 - cond_weight) * nll                  # CWFA.py:957,986
+    return loss, dict(mse=mse.detach(), nll=nll.detach(), sumsq=sumsq.detach(), logdet=logdet.detach())
+
+
+class FlowLevelTrainer:
+    """One flow level's fine-tune step: Lion on the flow parameters (lr, weight decay) and Lion on the level's conditioning
+    net (lr_cond), CWFA.py:596-610.  Defaults are the reference's (main.py:40-45 after the 1e-7 scaling of :238-243)."""
+
+    def __init__(self, model, n: int, lr: float = 221e-7, lr_cond: float = 845e-7, weight_decay: float = 1e-2,
+                 cond_weight: float = INN_COND_WEIGHT, group=None):
+        self.model, self.n, self.cond_weight, self.group = model, n, cond_weight, group
+        self.optimizer = Lion([{"params": list(model.conv_inn[n].parameters()), "lr": lr, "weight_decay": weight_decay}], lr=lr)
+        self.optimizer_cond = Lion(list(model.cond_nets[n].parameters()), lr=lr_cond)
+        self.collectives = 0
+
+    def step(self, gt, views, mean_vol, vol_in, z=None):
+        self.optimizer.zero_grad()
+        self.optimizer_cond.zero_grad()
+        loss, parts = flow_level_loss(self.model, self.n, gt, views, mean_vol, vol_in, z, self.cond_weight)
+        loss.backward()
+        self.collectives = allreduce_gradients([self.optimizer, self.optimizer_cond], self.group)
+        self.optimizer_cond.step()                                        # CWFA.py:1002-1005
+        self.optimizer.step()
+        parts["loss"] = loss.detach()
+        return parts

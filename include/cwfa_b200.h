@@ -216,6 +216,53 @@ int cwfa_coupling_tc(const void* b_c8, const void* w_packed, const float* bias, 
 int cwfa_nchw_to_c8(const float* x, void* y, int N, int C, int Cp, int64_t P, int is_bf16, void* stream);
 int cwfa_c8_to_nchw(const void* x, float* y, int N, int C, int Cp, int64_t P, int is_bf16, void* stream);
 
+/* ==== training-time adjoints of the fp32 module path (csrc/backward.cu) =========================================
+ * The reference trains one flow level at a time with torch autograd (CWFA.py:928-1015: inverse pass WITH gradients for
+ * the MSE term, forward pass for the NLL term, backward, Lion step).  These are the hand-written adjoints of the forward
+ * kernels above; cwfa_b200/autograd.py is the only caller. */
+/* conv2d weight gradient dW[co,ci,kh,kw] = sum_{n,h,w} dy[n,co,h,w] * x[n,ci,h+kh-p,w+kw-p] of the stride-1 'same' convs
+ * (square kernels 1x1 / 3x3: every conv of the coupling sub-networks networks.py:611-638 and of the conditioning net's
+ * 2-D part :211-219).  Deterministic two-stage sum; workspace >= cwfa_conv2d_wgrad_workspace_floats(...) floats.
+ * accumulate != 0: dw += result.  The DATA gradient is cwfa_conv2d_f32(dy, wt) with wt from cwfa_conv2d_dgrad_weights_f32
+ * (wt[ci,co,kh,kw] = w[co,ci,KH-1-kh,KW-1-kw]); the bias gradient is cwfa_channel_stats_f32(dy). */
+int64_t cwfa_conv2d_wgrad_workspace_floats(int N, int Cin, int H, int W, int Cout, int KH, int KW);
+int cwfa_conv2d_wgrad_f32(const float* x, const float* dy, float* dw, float* workspace, int N, int Cin, int H, int W,
+                          int Cout, int KH, int KW, int accumulate, void* stream);
+int cwfa_conv2d_dgrad_weights_f32(const float* w, float* wt, int Cout, int Cin, int KH, int KW, void* stream);
+/* ELU(alpha=1) adjoint from the layer OUTPUT y: dv = dy * (y > 0 ? 1 : y + 1)  (dv may alias dy). */
+int cwfa_elu_bwd_f32(const float* dy, const float* y, float* dv, int64_t n, void* stream);
+/* out = alpha*a + beta*b (b may be NULL). */
+int cwfa_axpby_f32(const float* a, const float* b, float* out, float alpha, float beta, int64_t n, void* stream);
+/* nn.PReLU() with one shared slope (networks.py:209) as a stand-alone op and its adjoint: dv = v > 0 ? dy : a*dy,
+ * dslope[0] = sum_{v<=0} v*dy (torch's convention at 0).  workspace >= cwfa_reduce_workspace_blocks() floats. */
+int cwfa_prelu_f32(const float* v, const float* slope, float* y, int64_t n, void* stream);
+int cwfa_reduce_workspace_blocks(void);
+int cwfa_prelu_bwd_f32(const float* dy, const float* v, const float* slope, float* dv, float* dslope, float* workspace,
+                       int64_t n, void* stream);
+/* Adjoint of cwfa_affine (same argument meaning; coupling_layers.py:490-500).  dy = cotangent of y, g_logdet (B, may be NULL)
+ * = cotangent of logdet.  Outputs (each may be NULL): dx (B,ch,P); da_s / da_t with batch strides ld_ds / ld_dt so that both
+ * halves of one (B,2ch,P) sub-network output gradient are written in place. */
+int cwfa_affine_bwd(const float* x, const float* a_s, const float* a_t, const float* dy, const float* g_logdet, float* dx,
+                    float* da_s, float* da_t, int B, int ch, int64_t P, int64_t ld_s, int64_t ld_t, int64_t ld_ds,
+                    int64_t ld_dt, float clamp, float k_atan, float t_scale, int flags, void* stream);
+/* The conditioning net's depth stencil (networks.py:221-225,239) UNFUSED, for training: Conv3d(1,Cm,3,p1) and
+ * Conv3d(Cm,1,3,p1) over the (H,W,depth) volume of a (B,D,H,W) tensor; hidden tensors are (B,Cm,D,H,W); weights (Cm,27)
+ * with tap = (kh*3+kw)*3+kd.  flip != 0 applies the point-reflected kernel = the adjoint of the OTHER conv
+ * (d hidden = 1toC(dy, w2, flip); dx = Cto1(d pre-activation, w1, flip)).  bias may be NULL.
+ * wgrad: dw[c,t] = sum multi[b,c,pos] * single[b,pos+t] (1->Cm weights: single = x, multi = d pre-activation, flip 0;
+ * Cm->1 weights: single = dy, multi = hidden, flip 1).  workspace >= cwfa_stencil3d_wgrad_workspace_floats(Cm) floats. */
+int cwfa_stencil3d_1toC_f32(const float* x, const float* w, const float* bias, float* out, int B, int D, int H, int W,
+                            int Cm, int flip, void* stream);
+int cwfa_stencil3d_Cto1_f32(const float* hid, const float* w, const float* bias, float* out, int B, int D, int H, int W,
+                            int Cm, int flip, void* stream);
+int cwfa_stencil3d_wgrad_workspace_floats(int Cm);
+int cwfa_stencil3d_wgrad_f32(const float* single, const float* multi, float* dw, float* workspace, int B, int D, int H,
+                             int W, int Cm, int flip, void* stream);
+/* Lion update on a flat fp32 buffer (lion_pytorch 0.0.7, requirements.txt:1; call sites CWFA.py:381,608-610):
+ * p *= 1 - lr*wd; p -= lr*sign(beta1*m + (1-beta1)*g); m = beta2*m + (1-beta2)*g, with g read as g*grad_scale. */
+int cwfa_lion_step_f32(float* p, const float* g, float* m, int64_t n, float lr, float beta1, float beta2,
+                       float weight_decay, float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

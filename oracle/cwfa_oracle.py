@@ -429,3 +429,49 @@ def evaluate_inn_forward(model: dict, gt_volume: Tensor, extra_cond_in=None):
         x = lo
         cache.append(lo)
     return losses, cache, prior, ljs
+
+
+# ----------------------------------------------------------------------------------------
+# Training step of one flow level (CWFA.py:928-1015) -- differentiable through torch CPU autograd
+# ----------------------------------------------------------------------------------------
+def level_train_loss(inn_sd: SD, cond_sd: SD, spec: dict, gt: Tensor, views: Tensor, mean_vol: Tensor,
+                     vol_in: Tensor, cond_weight: float = 0.40984):
+    """Loss the reference back-propagates for a flow level (``loss_func_reg='L2'``, z = 0):
+    cond = cond_net(views) (CWFA.py:895); vol = inn([0, vol_in], c, rev=True) (:912);
+    loss_cond = mse(gt, vol) (:953); Z, J = inn(gt, c) (:966);
+    nll = (0.5 * ||Z||^2 - J.mean()) / vol.numel() (:970,978);
+    loss = w * loss_cond + (1 - w) * nll (:957,986).  Returns (loss, mse, nll)."""
+    c_lf = cond_network(cond_sd, views)
+    z0 = torch.zeros_like(vol_in)
+    vol, _ = level_inverse(inn_sd, spec, z0, vol_in, c_lf, mean_vol)
+    mse = F.mse_loss(gt, vol)
+    z, _lo, jac = level_forward(inn_sd, spec, gt, c_lf, mean_vol)
+    nll = (0.5 * torch.norm(z) ** 2 - jac.mean()) / vol.numel()
+    return cond_weight * mse + (1.0 - cond_weight) * nll, mse, nll
+
+
+def level_train_grads(inn_sd: SD, cond_sd: SD, spec: dict, gt, views, mean_vol, vol_in, cond_weight: float = 0.40984):
+    """Gradients of ``level_train_loss`` w.r.t. every floating-point entry of both state_dicts.
+    The shared PReLU of the conditioning net (three keys, one tensor: networks.py:209) is tied before differentiating,
+    so its gradient is the sum over its three uses, as in the reference."""
+    inn = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point else v) for k, v in inn_sd.items()}
+    cond = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point else v) for k, v in cond_sd.items()}
+    p = "subnetworks.0."
+    cond[p + "relu.weight"] = cond[p + "conv1.1.weight"]
+    cond[p + "conv3d.1.weight"] = cond[p + "conv1.1.weight"]
+    loss, mse, nll = level_train_loss(inn, cond, spec, gt, views, mean_vol, vol_in, cond_weight)
+    loss.backward()
+    zero = lambda v: torch.zeros_like(v)
+    g_inn = {k: (v.grad if v.grad is not None else zero(v)) for k, v in inn.items() if v.dtype.is_floating_point}
+    g_cond = {k: (v.grad if v.grad is not None else zero(v)) for k, v in cond.items() if v.dtype.is_floating_point}
+    return dict(loss=loss.detach(), mse=mse.detach(), nll=nll.detach(), inn=g_inn, cond=g_cond)
+
+
+def lion_step(p: Tensor, g: Tensor, m: Tensor, lr: float, beta1: float = 0.9, beta2: float = 0.99, wd: float = 0.0):
+    """lion_pytorch 0.0.7 ``update_fn`` (requirements.txt:1; not vendored in the reference tree, restated from the published
+    algorithm -- parity unpinned): p *= 1 - lr*wd; p -= lr*sign(b1*m + (1-b1)*g); m = b2*m + (1-b2)*g.  Returns (p, m)."""
+    p = p * (1.0 - lr * wd)
+    upd = torch.sign(m * beta1 + g * (1.0 - beta1))
+    p = p - lr * upd
+    m = m * beta2 + g * (1.0 - beta2)
+    return p, m
