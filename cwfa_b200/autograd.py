@@ -145,10 +145,69 @@ def conv2d_supported(w, act, res, res_mode) -> bool:
             and (res is None or res_mode == 1))
 
 
+# ---- tensor-core variant: forward and data gradient on the tcgen05 implicit-GEMM kernel (bf16/fp16 operands, fp32
+# accumulation and fp32 NCHW results), weight gradient in fp32.  BASELINE.json configs[3] names bf16 for the training step;
+# the reference's own GPU path trains under fp16 autocast (CWFA.py:845,996).
+_PRECISION = "fp32"
+
+
+def set_training_precision(kind: str) -> str:
+    """'fp32' (reference precision, direct CUDA-core convolutions) or 'bf16' / 'fp16' (tensor-core convolutions in the
+    differentiable path).  Returns the previous setting."""
+    global _PRECISION
+    if kind not in ("fp32", "bf16", "fp16"):
+        raise ValueError(f"unknown training precision {kind!r}")
+    prev, _PRECISION = _PRECISION, kind
+    return prev
+
+
+def training_precision() -> str:
+    return _PRECISION
+
+
+class _Conv2dTC(_F):
+    @staticmethod
+    def forward(ctx, x, w, bias, res, act, res_mode, kind):
+        from . import tc
+        xx, ww = _f32(x), _f32(w)
+        rr = None if res is None else _f32(res)
+        pc = tc.PackedConv(ww, None if bias is None else bias.detach(), kind)
+        y = tc.conv_tc(tc.to_c8(xx, kind), pc, act=act, res=rr, res_mode=res_mode, out_nchw=True)
+        ctx.act, ctx.kind = act, kind
+        ctx.has_res = rr is not None and res_mode == 1
+        ctx.save_for_backward(xx, ww, y if act == ops.ACT_ELU else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        from . import tc
+        x, w, y = ctx.saved_tensors
+        dv = ops._ck(dy)
+        if ctx.act == ops.ACT_ELU:
+            g = torch.empty_like(dv)
+            _lib.call("cwfa_elu_bwd_f32", dv.data_ptr(), y.data_ptr(), g.data_ptr(), dv.numel(), _stream())
+            dv = g
+        need_x, need_w, need_b, need_r = ctx.needs_input_grad[:4]
+        dx = None
+        if need_x:
+            Cout, Cin, KH, KW = w.shape
+            wt = torch.empty((Cin, Cout, KH, KW), device=w.device, dtype=torch.float32)
+            _lib.call("cwfa_conv2d_dgrad_weights_f32", w.data_ptr(), wt.data_ptr(), Cout, Cin, KH, KW, _stream())
+            dx = tc.conv_tc(tc.to_c8(dv, ctx.kind), tc.PackedConv(wt, None, ctx.kind), out_nchw=True)
+        dw = conv2d_wgrad(x, dv, w.shape[2], w.shape[3]) if need_w else None
+        db = channel_sum(dv) if need_b else None
+        dr = dv if (need_r and ctx.has_res) else None
+        return dx, dw, db, dr, None, None, None
+
+
 def conv2d(x, w, bias=None, *, act=ops.ACT_NONE, slope=None, res=None, res_mode=0):
-    if act == ops.ACT_PRELU:
-        return prelu(_Conv2d.apply(x, w, bias, res, ops.ACT_NONE, res_mode if res is not None else 0), slope)
-    return _Conv2d.apply(x, w, bias, res, act, res_mode if res is not None else 0)
+    rm = res_mode if res is not None else 0
+    a = ops.ACT_NONE if act == ops.ACT_PRELU else act
+    if _PRECISION == "fp32":
+        y = _Conv2d.apply(x, w, bias, res, a, rm)
+    else:
+        y = _Conv2dTC.apply(x, w, bias, res, a, rm, _PRECISION)
+    return prelu(y, slope) if act == ops.ACT_PRELU else y
 
 
 # ---------------------------------------------------------------------------------------------

@@ -376,6 +376,7 @@ __global__ void __launch_bounds__(256) stencil_1toC_kernel(const float* __restri
 }
 
 // out[b,pos] = bias + sum_c sum_t w[c,t] * hid[b,c,pos+t]   (flip: w[c,26-t], the adjoint of 1->Cm)
+// A thread owns 4 consecutive w positions: every (kd,kh) row segment of 6 values is loaded once for 12 FMAs.
 __global__ void __launch_bounds__(256) stencil_Cto1_kernel(const float* __restrict__ hid, const float* __restrict__ w,
                                                            const float* __restrict__ bias, float* __restrict__ out, int D,
                                                            int H, int W, int Cm, int flip) {
@@ -386,18 +387,42 @@ __global__ void __launch_bounds__(256) stencil_Cto1_kernel(const float* __restri
     }
     __syncthreads();
     const int b = blockIdx.y;
-    const int64_t V = (int64_t)D * H * W, P = (int64_t)H * W;
+    const int W4 = (W + 3) / 4;
+    const int64_t V = (int64_t)D * H * W, P = (int64_t)H * W, V4 = (int64_t)D * H * W4;
     const float b0 = bias ? __ldg(bias) : 0.f;
-    for (int64_t pos = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; pos < V; pos += (int64_t)gridDim.x * blockDim.x) {
-        const int d = (int)(pos / P), h = (int)((pos % P) / W), ww = (int)(pos % W);
-        float a = b0;
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < V4; q += (int64_t)gridDim.x * blockDim.x) {
+        const int w0 = (int)(q % W4) * 4, h = (int)((q / W4) % H), d = (int)(q / ((int64_t)W4 * H));
+        float a[4] = {b0, b0, b0, b0};
         for (int c = 0; c < Cm; ++c) {
-            float v[27];
-            load_taps27(hid + ((int64_t)b * Cm + c) * V, D, H, W, d, h, ww, v);
+            const float* vol = hid + ((int64_t)b * Cm + c) * V;
+            const float* wc = wsm + c * 27;
 #pragma unroll
-            for (int t = 0; t < 27; ++t) a = fmaf(wsm[c * 27 + t], v[t], a);
+            for (int kd = 0; kd < 3; ++kd) {
+                const int gd = d + kd - 1;
+                if (gd < 0 || gd >= D) continue;
+#pragma unroll
+                for (int kh = 0; kh < 3; ++kh) {
+                    const int gh = h + kh - 1;
+                    if (gh < 0 || gh >= H) continue;
+                    const float* row = vol + (int64_t)gd * P + (int64_t)gh * W;
+                    float v[6];
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) {
+                        const int gw = w0 + j - 1;
+                        v[j] = (gw >= 0 && gw < W) ? __ldg(row + gw) : 0.f;
+                    }
+#pragma unroll
+                    for (int kw = 0; kw < 3; ++kw) {
+                        const float ww = wc[(kh * 3 + kw) * 3 + kd];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) a[j] = fmaf(ww, v[j + kw], a[j]);
+                    }
+                }
+            }
         }
-        out[(int64_t)b * V + pos] = a;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (w0 + j < W) out[(int64_t)b * V + (int64_t)d * P + (int64_t)h * W + w0 + j] = a[j];
     }
 }
 
@@ -405,37 +430,48 @@ __global__ void __launch_bounds__(256) stencil_Cto1_kernel(const float* __restri
 //   1->Cm weights: single = x, multi = d(hidden pre-activation), flip = 0
 //   Cm->1 weights: single = dy, multi = hidden,                 flip = 1
 constexpr int kStencilWgBlocks = kNumSMs;
+constexpr int SW_CG = 4;            // hidden channels per thread: the 27 taps of `single` are loaded once for 4*27 FMAs
 __global__ void __launch_bounds__(256) stencil_wgrad_kernel(const float* __restrict__ single, const float* __restrict__ multi,
                                                             float* __restrict__ part, int B, int D, int H, int W, int Cm,
                                                             int flip) {
-    __shared__ float red[8][27];
-    const int c = blockIdx.y;
+    __shared__ float red[8][SW_CG * 27];
+    const int c0 = blockIdx.y * SW_CG;
     const int64_t V = (int64_t)D * H * W, P = (int64_t)H * W;
-    float acc[27];
+    float acc[SW_CG][27];
 #pragma unroll
-    for (int t = 0; t < 27; ++t) acc[t] = 0.f;
+    for (int j = 0; j < SW_CG; ++j)
+#pragma unroll
+        for (int t = 0; t < 27; ++t) acc[j][t] = 0.f;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < (int64_t)B * V; i += (int64_t)gridDim.x * blockDim.x) {
         const int b = (int)(i / V);
         const int64_t pos = i % V;
         const int d = (int)(pos / P), h = (int)((pos % P) / W), ww = (int)(pos % W);
-        const float g = __ldg(multi + ((int64_t)b * Cm + c) * V + pos);
         float v[27];
         load_taps27(single + (int64_t)b * V, D, H, W, d, h, ww, v);
 #pragma unroll
-        for (int t = 0; t < 27; ++t) acc[t] = fmaf(g, v[t], acc[t]);
+        for (int j = 0; j < SW_CG; ++j) {
+            const float g = (c0 + j < Cm) ? __ldg(multi + ((int64_t)b * Cm + c0 + j) * V + pos) : 0.f;
+#pragma unroll
+            for (int t = 0; t < 27; ++t) acc[j][t] = fmaf(g, v[t], acc[j][t]);
+        }
     }
     const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
 #pragma unroll
-    for (int t = 0; t < 27; ++t) {
-        const float s = warp_sum(acc[t]);
-        if (lane == 0) red[wp][t] = s;
-    }
+    for (int j = 0; j < SW_CG; ++j)
+#pragma unroll
+        for (int t = 0; t < 27; ++t) {
+            const float s = warp_sum(acc[j][t]);
+            if (lane == 0) red[wp][j * 27 + t] = s;
+        }
     __syncthreads();
-    if (threadIdx.x < 27) {
-        float s = 0.f;
-        for (int k = 0; k < 8; ++k) s += red[k][threadIdx.x];
-        const int t = flip ? 26 - threadIdx.x : threadIdx.x;
-        part[((int64_t)blockIdx.x * Cm + c) * 27 + t] = s;
+    if (threadIdx.x < SW_CG * 27) {
+        const int j = threadIdx.x / 27, t0 = threadIdx.x % 27;
+        if (c0 + j < Cm) {
+            float s = 0.f;
+            for (int k = 0; k < 8; ++k) s += red[k][threadIdx.x];
+            const int t = flip ? 26 - t0 : t0;
+            part[((int64_t)blockIdx.x * Cm + c0 + j) * 27 + t] = s;
+        }
     }
 }
 
@@ -450,7 +486,7 @@ extern "C" int cwfa_stencil3d_1toC_f32(const float* x, const float* w, const flo
 extern "C" int cwfa_stencil3d_Cto1_f32(const float* hid, const float* w, const float* bias, float* out, int B, int D, int H,
                                        int W, int Cm, int flip, void* stream) {
     if (B <= 0 || D <= 0 || H <= 0 || W <= 0 || Cm <= 0 || Cm > 256 || B > 65535) { set_error("stencil3d_Cto1: bad shape"); return CWFA_EINVAL; }
-    const int64_t V = (int64_t)D * H * W;
+    const int64_t V = (int64_t)D * H * ((W + 3) / 4);
     dim3 grid(ew_blocks(V), B);
     stencil_Cto1_kernel<<<grid, 256, sizeof(float) * Cm * 27, (cudaStream_t)stream>>>(hid, w, bias, out, D, H, W, Cm, flip);
     return check_launch("stencil3d_Cto1");
@@ -460,7 +496,7 @@ extern "C" int cwfa_stencil3d_wgrad_f32(const float* single, const float* multi,
                                         int H, int W, int Cm, int flip, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (B <= 0 || D <= 0 || H <= 0 || W <= 0 || Cm <= 0 || Cm > 65535) { set_error("stencil3d_wgrad: bad shape"); return CWFA_EINVAL; }
-    stencil_wgrad_kernel<<<dim3(kStencilWgBlocks, Cm), 256, 0, st>>>(single, multi, workspace, B, D, H, W, Cm, flip);
+    stencil_wgrad_kernel<<<dim3(kStencilWgBlocks, ceil_div(Cm, SW_CG)), 256, 0, st>>>(single, multi, workspace, B, D, H, W, Cm, flip);
     int rc = check_launch("stencil3d_wgrad");
     if (rc) return rc;
     const int64_t n = (int64_t)Cm * 27;

@@ -421,13 +421,41 @@ class ConditionalAffineTransform(_BaseCouplingBlock):
             raise ValueError("ConditionalAffineTransform must have a condition")
         self.subnet = subnet_constructor(self.condition_length, 2 * self.channels)
 
-    def forward(self, x, c=[], rev=False, jac=True):
+    def _st(self, c):
         cond = torch.cat(list(c), 1) if len(c) > 1 else c[0]
         split_fn = getattr(self.subnet, "forward_split", None)
         if split_fn is not None:
-            a_s, a_t, t_scale = split_fn(cond)
+            return split_fn(cond)
+        a = self.subnet(cond)
+        return a[:, :self.channels], a[:, self.channels:], 1.0
+
+    def forward(self, x, c=[], rev=False, jac=True):
+        memo = _SUBNET_MEMO[-1] if _SUBNET_MEMO else None
+        if memo is None:
+            a_s, a_t, t_scale = self._st(c)
         else:
-            a = self.subnet(cond)
-            a_s, a_t, t_scale = a[:, :self.channels], a[:, self.channels:], 1.0
+            # (s, t) depend on the conditions only: a training step that runs the level in both directions on the SAME
+            # condition tensors (CWFA.py:912 and :966) evaluates each sub-network once; autograd sums both uses.
+            key = (id(self),) + tuple((id(t), t._version) for t in c)
+            hit = memo.get(key)
+            if hit is None:
+                hit = memo[key] = (self._st(c), list(c))          # keeps the condition tensors alive: ids stay unique
+            a_s, a_t, t_scale = hit[0]
         y, j = ops.affine(x[0], a_s, a_t, inverse=rev, clamp=self.clamp, t_scale=t_scale)
         return (y,), j
+
+
+_SUBNET_MEMO: list = []
+
+
+class share_subnet_outputs:
+    """Context manager: inside it a ``ConditionalAffineTransform`` called again with the same condition tensor objects
+    reuses its sub-network output instead of recomputing it (used by ``cwfa_b200.training.flow_level_loss``)."""
+
+    def __enter__(self):
+        _SUBNET_MEMO.append({})
+        return self
+
+    def __exit__(self, *exc):
+        _SUBNET_MEMO.pop()
+        return False

@@ -37,9 +37,9 @@ class FlatGroup:
                 continue
             (loose if getattr(p, "_cwfa_flat", False) else mine).append(p)
         self.params, self.loose = mine, loose          # loose: already owned by another group (e.g. the shared PReLU, networks.py:209)
-        if not mine:
+        if not mine and not loose:
             raise ValueError("FlatGroup: no trainable floating-point parameters")
-        dev = mine[0].device
+        dev = (mine or loose)[0].device
         offs, n = [], 0
         for p in mine:
             offs.append(n)
@@ -53,7 +53,11 @@ class FlatGroup:
             p.data = v
             p.grad = self.grad[o:o + p.numel()].view(p.shape)
             p._cwfa_flat = True
-        self.loose_grads_ready = False
+
+    def release(self):
+        """Give the parameters up (they keep their values and stay views of this buffer) so another group may re-home them."""
+        for p in self.params:
+            p._cwfa_flat = False
 
     def zero_grad(self):
         self.grad.zero_()
@@ -99,6 +103,10 @@ class Lion:
         for g in self.param_groups:
             g["flat"].zero_grad()
 
+    def release(self):
+        for g in self.param_groups:
+            g["flat"].release()
+
     def flat_grads(self) -> List[torch.Tensor]:
         for g in self.param_groups:
             g["flat"].grads_alias_flat()
@@ -113,8 +121,9 @@ class Lion:
                 raise RuntimeError("cwfa_b200.Lion: parameters must live on a CUDA device (no CPU fallback)")
             fg.grads_alias_flat()
             b1, b2 = g["betas"]
-            _lib.call("cwfa_lion_step_f32", fg.flat.data_ptr(), fg.grad.data_ptr(), g["exp_avg"].data_ptr(), fg.flat.numel(),
-                      g["lr"], b1, b2, g["weight_decay"], float(self.grad_scale), st)
+            if fg.flat.numel():
+                _lib.call("cwfa_lion_step_f32", fg.flat.data_ptr(), fg.grad.data_ptr(), g["exp_avg"].data_ptr(), fg.flat.numel(),
+                          g["lr"], b1, b2, g["weight_decay"], float(self.grad_scale), st)
             for p in fg.loose:
                 if p.grad is None:
                     continue
@@ -136,8 +145,9 @@ def allreduce_gradients(optimizers: Sequence[Lion], group=None) -> int:
     n = 0
     for o in optimizers:
         for g in o.flat_grads():
-            dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group)
-            n += 1
+            if g.numel():
+                dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group)
+                n += 1
         for pg in o.param_groups:
             for p in pg["flat"].loose:
                 if p.grad is not None:
@@ -172,9 +182,11 @@ def flow_level_loss(model, n: int, gt: torch.Tensor, views: torch.Tensor, mean_v
     c = [cond, mean_vol]
     if z is None:
         z = torch.zeros((vol_in.shape[0],) + tuple(inn.global_out_shapes[0]), device=vol_in.device, dtype=torch.float32)
-    vol_rec, _ = inn([z, vol_in.detach()], c=c, rev=True)                 # CWFA.py:912 (with gradients)
-    mse = ag.mse_loss(gt, vol_rec)                                        # CWFA.py:953
-    (Z, _lo), logdet = inn(gt, c=c)                                       # CWFA.py:966
+    from .modules import share_subnet_outputs
+    with share_subnet_outputs():                                          # s, t of every block: computed once, used twice
+        vol_rec, _ = inn([z, vol_in.detach()], c=c, rev=True)             # CWFA.py:912 (with gradients)
+        mse = ag.mse_loss(gt, vol_rec)                                    # CWFA.py:953
+        (Z, _lo), logdet = inn(gt, c=c)                                   # CWFA.py:966
     sumsq = ops.sum_squares(Z)
     nll = (0.5 * sumsq.sum() - logdet.mean()) / vol_rec.numel()           # CWFA.py:970,978
     loss = cond_weight * mse + (1.0 - cond_weight) * nll                  # CWFA.py:957,986
@@ -186,17 +198,26 @@ class FlowLevelTrainer:
     net (lr_cond), CWFA.py:596-610.  Defaults are the reference's (main.py:40-45 after the 1e-7 scaling of :238-243)."""
 
     def __init__(self, model, n: int, lr: float = 221e-7, lr_cond: float = 845e-7, weight_decay: float = 1e-2,
-                 cond_weight: float = INN_COND_WEIGHT, group=None):
-        self.model, self.n, self.cond_weight, self.group = model, n, cond_weight, group
+                 cond_weight: float = INN_COND_WEIGHT, group=None, precision: str = "fp32"):
+        self.model, self.n, self.cond_weight, self.group, self.precision = model, n, cond_weight, group, precision
         self.optimizer = Lion([{"params": list(model.conv_inn[n].parameters()), "lr": lr, "weight_decay": weight_decay}], lr=lr)
         self.optimizer_cond = Lion(list(model.cond_nets[n].parameters()), lr=lr_cond)
         self.collectives = 0
 
+    def release(self):
+        self.optimizer.release()
+        self.optimizer_cond.release()
+
     def step(self, gt, views, mean_vol, vol_in, z=None):
         self.optimizer.zero_grad()
         self.optimizer_cond.zero_grad()
-        loss, parts = flow_level_loss(self.model, self.n, gt, views, mean_vol, vol_in, z, self.cond_weight)
-        loss.backward()
+        from . import autograd as ag
+        prev = ag.set_training_precision(self.precision)      # 'bf16'/'fp16': convolutions (forward + data gradient) on tcgen05
+        try:
+            loss, parts = flow_level_loss(self.model, self.n, gt, views, mean_vol, vol_in, z, self.cond_weight)
+            loss.backward()
+        finally:
+            ag.set_training_precision(prev)
         self.collectives = allreduce_gradients([self.optimizer, self.optimizer_cond], self.group)
         self.optimizer_cond.step()                                        # CWFA.py:1002-1005
         self.optimizer.step()

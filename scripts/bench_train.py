@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16", "fp16"])
     ap.add_argument("--json", default=None)
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -38,7 +39,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device(dev))
     n, S, D = a.level, a.side, a.depths
     model = cwfa_b200.CWFAModel(n_depths=D, volume_side_size=S, INN_max_down_steps=n + 2, seed=0).to(dev)
-    tr = FlowLevelTrainer(model, n)
+    tr = FlowLevelTrainer(model, n, precision=a.precision)
     C = D // 2 ** n
     g = torch.Generator(device="cpu").manual_seed(1000 + rank)             # every rank its own frame
     mk = lambda *s, sc=1.0: (torch.randn(*s, generator=g) * sc).to(dev)
@@ -64,7 +65,7 @@ def main():
         ms = float(t)
     losses.append(float(parts["loss"]))
     if rank == 0:
-        out = {"metric": "flow-level training steps/s (fp32 module path: fwd NLL + inverse MSE + backward + Lion)", "level": n,
+        out = {"metric": "flow-level training steps/s (fwd NLL + inverse MSE + backward + Lion)", "precision": a.precision, "level": n,
                "value": world * a.batch * 1000.0 / ms, "unit": "frames/s", "ms_per_step": ms, "n_gpus": world, "batch_per_gpu": a.batch,
                "side": S, "depths": D, "launches_per_step": (_lib.launch_count - l0) / a.steps, "collectives_per_step": tr.collectives,
                "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30, "losses": losses}

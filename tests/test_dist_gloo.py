@@ -49,3 +49,59 @@ def test_two_rank_gather_matches_single_process(n_frames):
     assert all(p.exitcode == 0 for p in procs)
     ref = torch.stack([torch.tensor([float(f), float(f) ** 2]) for f in range(n_frames)])
     assert torch.equal(full, ref) and total == n_frames
+
+
+# ---- training: gradient all-reduce of the flat buffers (cwfa_b200/training.py) -----------------------
+def _toy_net():
+    torch.manual_seed(7)
+    return torch.nn.Sequential(torch.nn.Conv2d(3, 6, 3, padding=1), torch.nn.PReLU(), torch.nn.Conv2d(6, 2, 1))
+
+
+def _toy_grads(net, frame_id):
+    g = torch.Generator().manual_seed(100 + frame_id)
+    x = torch.randn(1, 3, 8, 8, generator=g)
+    for p in net.parameters():
+        if p.grad is not None:
+            p.grad.zero_()
+    net(x).square().mean().backward()
+
+
+def _train_worker(rank, world, port, q):
+    from cwfa_b200.training import Lion, allreduce_gradients, allreduce_nll_terms
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    net = _toy_net()
+    opt = Lion([{"params": [net[0].weight, net[0].bias]}, {"params": list(net[1].parameters()) + list(net[2].parameters())}], lr=1e-3)
+    opt.zero_grad()
+    _toy_grads(net, rank)                                   # every rank its own frame
+    n = allreduce_gradients([opt])
+    tot = allreduce_nll_terms(torch.tensor([1.0 + rank, 2.0]), torch.tensor([10.0 * (rank + 1), 1.0]))
+    if rank == 0:
+        q.put((n, opt.grad_scale, [g.clone() for g in opt.flat_grads()], [float(t) for t in tot]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gradient_allreduce_matches_single_process():
+    from cwfa_b200.training import Lion
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    procs = [ctx.Process(target=_train_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    n, scale, flats, tot = q.get()
+    [p.join(60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    assert n == 2 and scale == 0.5                          # one collective per flat buffer; the mean is folded into Lion
+    # single process: sum of the two frames' gradients in the same flat layout
+    net = _toy_net()
+    opt = Lion([{"params": [net[0].weight, net[0].bias]}, {"params": list(net[1].parameters()) + list(net[2].parameters())}], lr=1e-3)
+    acc = [torch.zeros_like(g) for g in opt.flat_grads()]
+    for f in range(2):
+        opt.zero_grad()
+        _toy_grads(net, f)
+        for a, g in zip(acc, opt.flat_grads()):
+            a += g
+    for a, g in zip(acc, flats):
+        assert torch.allclose(a, g, rtol=1e-6, atol=1e-8) and float(g.abs().sum()) > 0
+    assert tot == [3.0 + 4.0, 30.0 + 2.0, 4.0]

@@ -277,6 +277,40 @@ def test_flow_level_gradients_mid_size_vs_oracle():
     assert errs[k] < 1e-3, (k, errs[k])
 
 
+@pytest.mark.parametrize("kind,tol_all,tol_each", [("bf16", 3e-2, 1.5e-1), ("fp16", 4e-3, 2e-2)])
+def test_flow_level_gradients_tensor_core_path(golden_tiny, golden_train, kind, tol_all, tol_each):
+    """Training precision 'bf16' / 'fp16': every convolution of the step (forward and data gradient) runs on the tcgen05
+    kernel with half-precision operands and fp32 accumulation; weight gradients, couplings, log-dets stay fp32.
+    Tolerance vs the fp32 oracle: rel-L2 over ALL gradients <= tol_all, every tensor <= tol_each (stated; printed)."""
+    from cwfa_b200 import _lib, autograd as ag
+    n = 1
+    lv = build_tiny_model(golden_tiny).export_for_oracle()["levels"][n]
+    model = build_tiny_model(golden_tiny, DEV)
+    w = golden_train["config"]["cond_weight"]
+    inputs = train_inputs(golden_train, n)
+    prev = ag.set_training_precision(kind)
+    before = dict(_lib.launch_hist)
+    try:
+        loss, parts, gi, gc = _our_level_grads(model, n, inputs, w)
+    finally:
+        ag.set_training_precision(prev)
+    assert _lib.launch_hist.get("cwfa_conv_tc", 0) - before.get("cwfa_conv_tc", 0) >= 80       # fwd + dgrad convs on tensor cores
+    r = O.level_train_grads(lv["inn"], lv["cond"], lv["spec"], *inputs, w)
+    num = den = 0.0
+    worst = ("", 0.0)
+    for ours, ref in ((gi, r["inn"]), (gc, r["cond"])):
+        for k, v in ours.items():
+            d = (v.double().cpu() - ref[k].double()).norm().item()
+            b = ref[k].double().norm().item()
+            num, den = num + d * d, den + b * b
+            if b > 0 and d / b > worst[1]:
+                worst = (k, d / b)
+    total = (num / den) ** 0.5
+    print(f"{kind}: loss {float(loss):.5f} (fp32 oracle {float(r['loss']):.5f}); gradients rel-L2 all {total:.2e}, worst {worst[1]:.2e} at {worst[0]}")
+    assert abs(float(loss) - float(r["loss"])) < 2e-2 * abs(float(r["loss"]))
+    assert total < tol_all and worst[1] < tol_each, (total, worst)
+
+
 # ---------------------------------------------------------------------------------------------
 # (d) optimiser steps
 # ---------------------------------------------------------------------------------------------
