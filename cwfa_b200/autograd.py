@@ -165,6 +165,18 @@ def training_precision() -> str:
     return _PRECISION
 
 
+def conv2d_wgrad_tc(x8, dy8, Cin: int, Cout: int, K: int) -> torch.Tensor:
+    """dW (Cout,Cin,K,K) fp32 from C8 half-precision x and dy on the tensor cores (csrc/wgrad_tc.cu)."""
+    lib = _lib.load()
+    N, H, W = x8.N, x8.H, x8.W
+    nws = lib.cwfa_wgrad_tc_workspace_floats(N, H, W, Cin, x8.Cp, Cout, K)
+    ws = torch.empty(nws, device=x8.data.device, dtype=torch.float32)
+    dw = torch.empty((Cout, Cin, K, K), device=x8.data.device, dtype=torch.float32)
+    _lib.call("cwfa_wgrad_tc", x8.data.data_ptr(), dy8.data.data_ptr(), dw.data_ptr(), ws.data_ptr(), N, H, W, Cin, x8.Cp, Cout, dy8.Cp,
+              K, K, x8.is_bf16, _stream())
+    return dw
+
+
 class _Conv2dTC(_F):
     @staticmethod
     def forward(ctx, x, w, bias, res, act, res_mode, kind):
@@ -172,29 +184,35 @@ class _Conv2dTC(_F):
         xx, ww = _f32(x), _f32(w)
         rr = None if res is None else _f32(res)
         pc = tc.PackedConv(ww, None if bias is None else bias.detach(), kind)
-        y = tc.conv_tc(tc.to_c8(xx, kind), pc, act=act, res=rr, res_mode=res_mode, out_nchw=True)
+        x8 = tc.to_c8(xx, kind)
+        y = tc.conv_tc(x8, pc, act=act, res=rr, res_mode=res_mode, out_nchw=True)
         ctx.act, ctx.kind = act, kind
         ctx.has_res = rr is not None and res_mode == 1
-        ctx.save_for_backward(xx, ww, y if act == ops.ACT_ELU else None)
+        ctx.wgrad_tc = tc.pad16(ww.shape[0]) <= 128                   # else: fp32 CUDA-core weight gradient
+        ctx.Cin = xx.shape[1]
+        ctx.save_for_backward(None if ctx.wgrad_tc else xx, ww, y if act == ops.ACT_ELU else None, x8.data if ctx.wgrad_tc else None)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         from . import tc
-        x, w, y = ctx.saved_tensors
+        x, w, y, x8d = ctx.saved_tensors
         dv = ops._ck(dy)
         if ctx.act == ops.ACT_ELU:
             g = torch.empty_like(dv)
             _lib.call("cwfa_elu_bwd_f32", dv.data_ptr(), y.data_ptr(), g.data_ptr(), dv.numel(), _stream())
             dv = g
         need_x, need_w, need_b, need_r = ctx.needs_input_grad[:4]
+        Cout, Cin, KH, KW = w.shape
+        dv8 = tc.to_c8(dv, ctx.kind) if (need_x or (need_w and ctx.wgrad_tc)) else None
         dx = None
         if need_x:
-            Cout, Cin, KH, KW = w.shape
             wt = torch.empty((Cin, Cout, KH, KW), device=w.device, dtype=torch.float32)
             _lib.call("cwfa_conv2d_dgrad_weights_f32", w.data_ptr(), wt.data_ptr(), Cout, Cin, KH, KW, _stream())
-            dx = tc.conv_tc(tc.to_c8(dv, ctx.kind), tc.PackedConv(wt, None, ctx.kind), out_nchw=True)
-        dw = conv2d_wgrad(x, dv, w.shape[2], w.shape[3]) if need_w else None
+            dx = tc.conv_tc(dv8, tc.PackedConv(wt, None, ctx.kind), out_nchw=True)
+        dw = None
+        if need_w:
+            dw = conv2d_wgrad_tc(tc.C8(x8d, Cin, ctx.kind), dv8, Cin, Cout, KH) if ctx.wgrad_tc else conv2d_wgrad(x, dv, KH, KW)
         db = channel_sum(dv) if need_b else None
         dr = dv if (need_r and ctx.has_res) else None
         return dx, dw, db, dr, None, None, None

@@ -349,9 +349,22 @@ __device__ __forceinline__ void load_taps27(const float* __restrict__ vol, int D
             }
 }
 
+// Row walker shared by the stencil kernels: a block covers `rpb` rows (b,d,h) per iteration, a thread a fixed column
+// slot -- index arithmetic is a few 32-bit divisions per ROW, none per element.
+struct RowWalk {
+    int tpr, rpb, trow, tcol, rows;
+    __device__ RowWalk(int B, int D, int H, int slots) {
+        tpr = slots < 256 ? slots : 256;
+        rpb = 256 / tpr;
+        trow = threadIdx.x / tpr;
+        tcol = threadIdx.x % tpr;
+        rows = B * D * H;
+    }
+};
+
 // out[b,c,pos] = bias[c] + sum_t w[c,t] * x[b,pos+t]   (flip: use w[c,26-t], the adjoint of Cm->1)
 __global__ void __launch_bounds__(256) stencil_1toC_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                                           const float* __restrict__ bias, float* __restrict__ out, int D,
+                                                           const float* __restrict__ bias, float* __restrict__ out, int B, int D,
                                                            int H, int W, int Cm, int flip) {
     extern __shared__ float wsm[];      // [Cm][27] + [Cm]
     for (int i = threadIdx.x; i < Cm * 27; i += blockDim.x) {
@@ -360,17 +373,22 @@ __global__ void __launch_bounds__(256) stencil_1toC_kernel(const float* __restri
     }
     for (int i = threadIdx.x; i < Cm; i += blockDim.x) wsm[Cm * 27 + i] = bias ? __ldg(bias + i) : 0.f;
     __syncthreads();
-    const int b = blockIdx.y;
-    const int64_t V = (int64_t)D * H * W, P = (int64_t)H * W;
-    for (int64_t pos = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; pos < V; pos += (int64_t)gridDim.x * blockDim.x) {
-        const int d = (int)(pos / P), h = (int)((pos % P) / W), ww = (int)(pos % W);
-        float v[27];
-        load_taps27(x + (int64_t)b * V, D, H, W, d, h, ww, v);
-        for (int c = 0; c < Cm; ++c) {
-            float a = wsm[Cm * 27 + c];
+    const int64_t V = (int64_t)D * H * W;
+    const RowWalk rw(B, D, H, W);
+    if (rw.trow >= rw.rpb) return;
+    for (int row = blockIdx.x * rw.rpb + rw.trow; row < rw.rows; row += gridDim.x * rw.rpb) {
+        const int h = row % H, d = (row / H) % D, b = row / (H * D);
+        const int64_t rowoff = ((int64_t)d * H + h) * W;
+        for (int ww = rw.tcol; ww < W; ww += rw.tpr) {
+            float v[27];
+            load_taps27(x + (int64_t)b * V, D, H, W, d, h, ww, v);
+            float* o = out + (int64_t)b * Cm * V + rowoff + ww;
+            for (int c = 0; c < Cm; ++c) {
+                float a = wsm[Cm * 27 + c];
 #pragma unroll
-            for (int t = 0; t < 27; ++t) a = fmaf(wsm[c * 27 + t], v[t], a);
-            out[((int64_t)b * Cm + c) * V + pos] = a;
+                for (int t = 0; t < 27; ++t) a = fmaf(wsm[c * 27 + t], v[t], a);
+                o[(int64_t)c * V] = a;
+            }
         }
     }
 }
@@ -378,7 +396,7 @@ __global__ void __launch_bounds__(256) stencil_1toC_kernel(const float* __restri
 // out[b,pos] = bias + sum_c sum_t w[c,t] * hid[b,c,pos+t]   (flip: w[c,26-t], the adjoint of 1->Cm)
 // A thread owns 4 consecutive w positions: every (kd,kh) row segment of 6 values is loaded once for 12 FMAs.
 __global__ void __launch_bounds__(256) stencil_Cto1_kernel(const float* __restrict__ hid, const float* __restrict__ w,
-                                                           const float* __restrict__ bias, float* __restrict__ out, int D,
+                                                           const float* __restrict__ bias, float* __restrict__ out, int B, int D,
                                                            int H, int W, int Cm, int flip) {
     extern __shared__ float wsm[];
     for (int i = threadIdx.x; i < Cm * 27; i += blockDim.x) {
@@ -386,43 +404,47 @@ __global__ void __launch_bounds__(256) stencil_Cto1_kernel(const float* __restri
         wsm[i] = __ldg(w + c * 27 + (flip ? 26 - t : t));
     }
     __syncthreads();
-    const int b = blockIdx.y;
     const int W4 = (W + 3) / 4;
-    const int64_t V = (int64_t)D * H * W, P = (int64_t)H * W, V4 = (int64_t)D * H * W4;
+    const int64_t V = (int64_t)D * H * W, P = (int64_t)H * W;
     const float b0 = bias ? __ldg(bias) : 0.f;
-    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < V4; q += (int64_t)gridDim.x * blockDim.x) {
-        const int w0 = (int)(q % W4) * 4, h = (int)((q / W4) % H), d = (int)(q / ((int64_t)W4 * H));
-        float a[4] = {b0, b0, b0, b0};
-        for (int c = 0; c < Cm; ++c) {
-            const float* vol = hid + ((int64_t)b * Cm + c) * V;
-            const float* wc = wsm + c * 27;
+    const RowWalk rw(B, D, H, W4);
+    if (rw.trow >= rw.rpb) return;
+    for (int row = blockIdx.x * rw.rpb + rw.trow; row < rw.rows; row += gridDim.x * rw.rpb) {
+        const int h = row % H, d = (row / H) % D, b = row / (H * D);
+        for (int wc = rw.tcol; wc < W4; wc += rw.tpr) {
+            const int w0 = wc * 4;
+            float a[4] = {b0, b0, b0, b0};
+            for (int c = 0; c < Cm; ++c) {
+                const float* vol = hid + ((int64_t)b * Cm + c) * V;
+                const float* wc_ = wsm + c * 27;
 #pragma unroll
-            for (int kd = 0; kd < 3; ++kd) {
-                const int gd = d + kd - 1;
-                if (gd < 0 || gd >= D) continue;
+                for (int kd = 0; kd < 3; ++kd) {
+                    const int gd = d + kd - 1;
+                    if (gd < 0 || gd >= D) continue;
 #pragma unroll
-                for (int kh = 0; kh < 3; ++kh) {
-                    const int gh = h + kh - 1;
-                    if (gh < 0 || gh >= H) continue;
-                    const float* row = vol + (int64_t)gd * P + (int64_t)gh * W;
-                    float v[6];
+                    for (int kh = 0; kh < 3; ++kh) {
+                        const int gh = h + kh - 1;
+                        if (gh < 0 || gh >= H) continue;
+                        const float* rowp = vol + (int64_t)gd * P + (int64_t)gh * W;
+                        float v[6];
 #pragma unroll
-                    for (int j = 0; j < 6; ++j) {
-                        const int gw = w0 + j - 1;
-                        v[j] = (gw >= 0 && gw < W) ? __ldg(row + gw) : 0.f;
-                    }
+                        for (int j = 0; j < 6; ++j) {
+                            const int gw = w0 + j - 1;
+                            v[j] = (gw >= 0 && gw < W) ? __ldg(rowp + gw) : 0.f;
+                        }
 #pragma unroll
-                    for (int kw = 0; kw < 3; ++kw) {
-                        const float ww = wc[(kh * 3 + kw) * 3 + kd];
+                        for (int kw = 0; kw < 3; ++kw) {
+                            const float ww = wc_[(kh * 3 + kw) * 3 + kd];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) a[j] = fmaf(ww, v[j + kw], a[j]);
+                            for (int j = 0; j < 4; ++j) a[j] = fmaf(ww, v[j + kw], a[j]);
+                        }
                     }
                 }
             }
-        }
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (w0 + j < W) out[(int64_t)b * V + (int64_t)d * P + (int64_t)h * W + w0 + j] = a[j];
+            for (int j = 0; j < 4; ++j)
+                if (w0 + j < W) out[(int64_t)b * V + (int64_t)d * P + (int64_t)h * W + w0 + j] = a[j];
+        }
     }
 }
 
@@ -436,23 +458,28 @@ __global__ void __launch_bounds__(256) stencil_wgrad_kernel(const float* __restr
                                                             int flip) {
     __shared__ float red[8][SW_CG * 27];
     const int c0 = blockIdx.y * SW_CG;
-    const int64_t V = (int64_t)D * H * W, P = (int64_t)H * W;
+    const int64_t V = (int64_t)D * H * W;
     float acc[SW_CG][27];
 #pragma unroll
     for (int j = 0; j < SW_CG; ++j)
 #pragma unroll
         for (int t = 0; t < 27; ++t) acc[j][t] = 0.f;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < (int64_t)B * V; i += (int64_t)gridDim.x * blockDim.x) {
-        const int b = (int)(i / V);
-        const int64_t pos = i % V;
-        const int d = (int)(pos / P), h = (int)((pos % P) / W), ww = (int)(pos % W);
-        float v[27];
-        load_taps27(single + (int64_t)b * V, D, H, W, d, h, ww, v);
+    const RowWalk rw(B, D, H, W);
+    if (rw.trow < rw.rpb) {
+        for (int row = blockIdx.x * rw.rpb + rw.trow; row < rw.rows; row += gridDim.x * rw.rpb) {
+            const int h = row % H, d = (row / H) % D, b = row / (H * D);
+            const int64_t rowoff = ((int64_t)d * H + h) * W;
+            for (int ww = rw.tcol; ww < W; ww += rw.tpr) {
+                float v[27];
+                load_taps27(single + (int64_t)b * V, D, H, W, d, h, ww, v);
+                const float* mp = multi + ((int64_t)b * Cm + c0) * V + rowoff + ww;
 #pragma unroll
-        for (int j = 0; j < SW_CG; ++j) {
-            const float g = (c0 + j < Cm) ? __ldg(multi + ((int64_t)b * Cm + c0 + j) * V + pos) : 0.f;
+                for (int j = 0; j < SW_CG; ++j) {
+                    const float g = (c0 + j < Cm) ? __ldg(mp + (int64_t)j * V) : 0.f;
 #pragma unroll
-            for (int t = 0; t < 27; ++t) acc[j][t] = fmaf(g, v[t], acc[j][t]);
+                    for (int t = 0; t < 27; ++t) acc[j][t] = fmaf(g, v[t], acc[j][t]);
+                }
+            }
         }
     }
     const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
@@ -477,18 +504,18 @@ __global__ void __launch_bounds__(256) stencil_wgrad_kernel(const float* __restr
 
 extern "C" int cwfa_stencil3d_1toC_f32(const float* x, const float* w, const float* bias, float* out, int B, int D, int H,
                                        int W, int Cm, int flip, void* stream) {
-    if (B <= 0 || D <= 0 || H <= 0 || W <= 0 || Cm <= 0 || Cm > 256 || B > 65535) { set_error("stencil3d_1toC: bad shape"); return CWFA_EINVAL; }
-    const int64_t V = (int64_t)D * H * W;
-    dim3 grid(ew_blocks(V), B);
-    stencil_1toC_kernel<<<grid, 256, sizeof(float) * Cm * 28, (cudaStream_t)stream>>>(x, w, bias, out, D, H, W, Cm, flip);
+    if (B <= 0 || D <= 0 || H <= 0 || W <= 0 || Cm <= 0 || Cm > 256 || (int64_t)B * D * H > 0x7fffffff) { set_error("stencil3d_1toC: bad shape"); return CWFA_EINVAL; }
+    const int rows = B * D * H;
+    const int grid = rows < kNumSMs * 8 ? rows : kNumSMs * 8;
+    stencil_1toC_kernel<<<grid, 256, sizeof(float) * Cm * 28, (cudaStream_t)stream>>>(x, w, bias, out, B, D, H, W, Cm, flip);
     return check_launch("stencil3d_1toC");
 }
 extern "C" int cwfa_stencil3d_Cto1_f32(const float* hid, const float* w, const float* bias, float* out, int B, int D, int H,
                                        int W, int Cm, int flip, void* stream) {
-    if (B <= 0 || D <= 0 || H <= 0 || W <= 0 || Cm <= 0 || Cm > 256 || B > 65535) { set_error("stencil3d_Cto1: bad shape"); return CWFA_EINVAL; }
-    const int64_t V = (int64_t)D * H * ((W + 3) / 4);
-    dim3 grid(ew_blocks(V), B);
-    stencil_Cto1_kernel<<<grid, 256, sizeof(float) * Cm * 27, (cudaStream_t)stream>>>(hid, w, bias, out, D, H, W, Cm, flip);
+    if (B <= 0 || D <= 0 || H <= 0 || W <= 0 || Cm <= 0 || Cm > 256 || (int64_t)B * D * H > 0x7fffffff) { set_error("stencil3d_Cto1: bad shape"); return CWFA_EINVAL; }
+    const int rows = B * D * H;
+    const int grid = rows < kNumSMs * 8 ? rows : kNumSMs * 8;
+    stencil_Cto1_kernel<<<grid, 256, sizeof(float) * Cm * 27, (cudaStream_t)stream>>>(hid, w, bias, out, B, D, H, W, Cm, flip);
     return check_launch("stencil3d_Cto1");
 }
 extern "C" int cwfa_stencil3d_wgrad_workspace_floats(int Cm) { return kStencilWgBlocks * Cm * 27; }

@@ -375,13 +375,13 @@ __global__ void __launch_bounds__(256) channel_stats_kernel(const float* __restr
                                                             int C, int64_t P) {
     const int c = blockIdx.y;
     float s = 0.f, q = 0.f;
-    const int64_t per = (int64_t)N * P;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < per; i += (int64_t)gridDim.x * blockDim.x) {
-        const int n = (int)(i / P);
-        const int64_t p = i % P;
-        const float v = __ldg(x + ((int64_t)n * C + c) * P + p);
-        s += v;
-        q += v * v;
+    for (int n = 0; n < N; ++n) {
+        const float* xp = x + ((int64_t)n * C + c) * P;
+        for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < P; p += (int64_t)gridDim.x * blockDim.x) {
+            const float v = __ldg(xp + p);
+            s += v;
+            q += v * v;
+        }
     }
     block_sum2(s, q);
     if (threadIdx.x == 0) {

@@ -83,6 +83,22 @@ def test_conv2d_adjoints(N, Cin, Cout, H, W, K, act, use_res):
         assert rel_l2(ag_.grad, ac.grad) < TOL
 
 
+@pytest.mark.parametrize("kind", ["bf16", "fp16"])
+@pytest.mark.parametrize("N,Cin,Cout,H,W,K", [(1, 64, 64, 32, 32, 3), (2, 29, 48, 13, 37, 3), (1, 64, 96, 40, 24, 3), (1, 6, 64, 64, 64, 1),
+                                              (1, 64, 64, 17, 33, 1), (1, 48, 48, 24, 40, 3), (2, 64, 12, 64, 48, 3), (1, 96, 64, 8, 16, 1)])
+def test_wgrad_tensor_core_kernel(kind, N, Cin, Cout, H, W, K):
+    """csrc/wgrad_tc.cu (MN-major tcgen05 operands straight from the C8 tiles) vs torch's fp32 weight gradient of the SAME
+    half-rounded inputs: only the fp32 summation order differs -> rel-L2 <= 2e-5."""
+    from cwfa_b200 import autograd as ag, tc
+    dt = torch.bfloat16 if kind == "bf16" else torch.float16
+    x = seeded_randn((N, Cin, H, W), 1).to(dt).float()
+    dy = seeded_randn((N, Cout, H, W), 2).to(dt).float()
+    ref = torch.nn.grad.conv2d_weight(x, (Cout, Cin, K, K), dy, padding=K // 2)
+    got = ag.conv2d_wgrad_tc(tc.to_c8(x.to(DEV), kind), tc.to_c8(dy.to(DEV), kind), Cin, Cout, K)
+    err = rel_l2(got, ref)
+    assert err < 2e-5, err
+
+
 @pytest.mark.parametrize("inverse", [False, True])
 @pytest.mark.parametrize("mode", ["packed", "split_tscale", "x_none"])
 def test_affine_adjoint(inverse, mode):
