@@ -75,7 +75,7 @@ _SIGS = {
 }
 _I64_FUNCS = {"cwfa_tc_packed_weight_elems": [i32, i32, i32, i32, i32],
               "cwfa_conv2d_wgrad_workspace_floats": [i32] * 7,
-              "cwfa_wgrad_tc_workspace_floats": [i32] * 7}
+              "cwfa_wgrad_tc_workspace_floats": [i32] * 8}
 _RESTYPES = {"cwfa_version": C.c_char_p, "cwfa_last_error": C.c_char_p}
 _OPTIONAL = {}
 

@@ -169,7 +169,7 @@ def conv2d_wgrad_tc(x8, dy8, Cin: int, Cout: int, K: int) -> torch.Tensor:
     """dW (Cout,Cin,K,K) fp32 from C8 half-precision x and dy on the tensor cores (csrc/wgrad_tc.cu)."""
     lib = _lib.load()
     N, H, W = x8.N, x8.H, x8.W
-    nws = lib.cwfa_wgrad_tc_workspace_floats(N, H, W, Cin, x8.Cp, Cout, K)
+    nws = lib.cwfa_wgrad_tc_workspace_floats(N, H, W, Cin, x8.Cp, Cout, dy8.Cp, K)
     ws = torch.empty(nws, device=x8.data.device, dtype=torch.float32)
     dw = torch.empty((Cout, Cin, K, K), device=x8.data.device, dtype=torch.float32)
     _lib.call("cwfa_wgrad_tc", x8.data.data_ptr(), dy8.data.data_ptr(), dw.data_ptr(), ws.data_ptr(), N, H, W, Cin, x8.Cp, Cout, dy8.Cp,
@@ -188,7 +188,7 @@ class _Conv2dTC(_F):
         y = tc.conv_tc(x8, pc, act=act, res=rr, res_mode=res_mode, out_nchw=True)
         ctx.act, ctx.kind = act, kind
         ctx.has_res = rr is not None and res_mode == 1
-        ctx.wgrad_tc = tc.pad16(ww.shape[0]) <= 128                   # else: fp32 CUDA-core weight gradient
+        ctx.wgrad_tc = True
         ctx.Cin = xx.shape[1]
         ctx.save_for_backward(None if ctx.wgrad_tc else xx, ww, y if act == ops.ACT_ELU else None, x8.data if ctx.wgrad_tc else None)
         return y
@@ -464,5 +464,36 @@ class _DepthStencil(_F):
         return dx, dw1, db1, dslope.reshape(slope.shape), dw2, db2
 
 
+_BAND = {}
+
+
+def _band_index(D: int, device):
+    """kd[d, d'] = d' - d + 1 clipped to [0, 2] and mask[d, d'] = (|d' - d| <= 1): zero padding in depth falls out of the band."""
+    key = (D, str(device))
+    if key not in _BAND:
+        d = torch.arange(D, device=device)
+        off = d[None, :] - d[:, None] + 1
+        _BAND[key] = (off.clamp(0, 2).reshape(-1), ((off >= 0) & (off <= 2)).float())
+    return _BAND[key]
+
+
+def depth_stencil3d_banded(x, w1, b1, slope, w2, b2):
+    """The depth stencil as two ordinary 3x3 2-D convolutions on the tensor cores (the formulation of the inference engine,
+    cwfa_b200/engine.py:_CondNet): channels carry (depth, hidden channel), weights are the depth-banded expansion
+    W1[(d,c), d'] = w1[c,:,:,d'-d+1], W2[d, (d',c)] = w2[c,:,:,d'-d+1].  The expansion is a gather of the
+    (Cm,27) parameters, so autograd folds the banded weight gradients (wgrad_tc) back onto them."""
+    D, Cm = x.shape[1], w1.shape[0]
+    kd, mask = _band_index(D, x.device)
+    # gather along kd (a pure re-indexing of the (Cm,27) parameters; its adjoint is torch's index_add)
+    g1 = w1[:, 0].index_select(3, kd).reshape(Cm, 3, 3, D, D) * mask            # [c, h, w, d, d']
+    g2 = w2[0].index_select(3, kd).reshape(Cm, 3, 3, D, D) * mask
+    W1 = g1.permute(3, 0, 4, 1, 2).reshape(D * Cm, D, 3, 3)                      # [(d,c), d', h, w]
+    W2 = g2.permute(3, 4, 0, 1, 2).reshape(D, D * Cm, 3, 3)                      # [d, (d',c), h, w]
+    hid = conv2d(x, W1, b1.repeat(D), act=ops.ACT_PRELU, slope=slope)
+    return conv2d(hid, W2, b2.expand(D))
+
+
 def depth_stencil3d(x, w1, b1, slope, w2, b2):
+    if _PRECISION != "fp32":
+        return depth_stencil3d_banded(x, w1, b1, slope, w2, b2)
     return _DepthStencil.apply(x, w1, b1, slope, w2, b2)

@@ -30,7 +30,7 @@ constexpr int WT_A_CHUNK = WT_BH * WT_BW * 16;       // bytes of one 8-channel c
 constexpr int WT_A_BYTES = 16 * WT_A_CHUNK;          // M = 128 rows = 16 chunks (chunks >= Cout/8 stay zero)
 
 struct WtParams {
-    int N, H, W, Cout, Cin, co_chunks, nb_chunks, tiles_x, tiles_y, num_tiles;
+    int N, H, W, Cout, Cin, co_chunks /* per M block: min(16, Cout_p/8) */, nb_chunks, tiles_x, tiles_y, num_tiles;
     float* part;                                      // [gridDim.x][KS*KS][Cin][Cout]: lanes (= co) write consecutive floats
 };
 
@@ -85,6 +85,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const __grid_co
     const int my_tiles = (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int tiles_per_img = p.tiles_x * p.tiles_y;
     const int ci_chunk0 = blockIdx.y * p.nb_chunks;
+    const int co_chunk0 = blockIdx.z * 16;               // M block of 128 output channels (TMA zero-fills chunks past the tensor)
 
     if (warp == 0) {
         // ============================ TMA producer ============================
@@ -98,7 +99,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const __grid_co
                 mbar_wait(empty(s), ((i / WT_STAGES) & 1) ^ 1);
                 mbar_expect_tx(full(s), tx);
                 const uint32_t base = ring + (uint32_t)(s * stage_bytes);
-                tma_load_4d(base, &tm_dy, full(s), w0 * 8, h0, 0, n);
+                tma_load_4d(base, &tm_dy, full(s), w0 * 8, h0, co_chunk0, n);
                 tma_load_4d(base + WT_A_BYTES, &tm_x, full(s), (w0 - PAD) * 8, h0 - PAD, ci_chunk0, n);
             }
         }
@@ -133,10 +134,10 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const __grid_co
     } else {
         // ============================ epilogue: TMEM -> per-CTA partial dW ============================
         const int q = warp & 3;                          // TMEM lane quarter this warp may read
-        const int co = q * 32 + lane;
+        const int co = co_chunk0 * 8 + q * 32 + lane;
         mbar_wait(acc_done, 0);
         tc_fence_after();
-        float* dst = p.part + (size_t)blockIdx.x * p.Cout * p.Cin * KK;
+        float* dst = p.part + (size_t)blockIdx.x * p.Cout * p.Cin * KK;   // [t][ci][co]
         for (int t = 0; t < KK; ++t)
             for (int c0 = 0; c0 < NB; c0 += 16) {
                 uint32_t v[16];
@@ -170,16 +171,17 @@ __global__ void __launch_bounds__(256) wgrad_tc_finalize_kernel(const float* __r
     out[((int64_t)co * Cin + ci) * KK + t] = (float)s;
 }
 
-struct WtPlan { int nb_chunks, n_ci_blk, chunks; };
-static WtPlan wt_plan(int N, int H, int W, int Cin_p, int KS) {
+struct WtPlan { int nb_chunks, n_ci_blk, n_m_blk, chunks; };
+static WtPlan wt_plan(int N, int H, int W, int Cin_p, int Cout_p, int KS) {
     WtPlan pl;
-    const int max_nb = (KS == 3) ? 32 : 64;                 // KS*KS*NB <= 512 TMEM columns
+    const int max_nb = (KS == 3) ? 48 : 64;                 // KS*KS*NB <= 512 TMEM columns
     int nb = Cin_p < max_nb ? Cin_p : max_nb;
     while (Cin_p % nb) nb -= 16;
     pl.nb_chunks = nb / 8;
     pl.n_ci_blk = Cin_p / nb;
+    pl.n_m_blk = ceil_div(Cout_p, 128);
     const int64_t tiles = (int64_t)N * ceil_div(H, WT_BH) * ceil_div(W, WT_BW);
-    int chunks = kNumSMs / pl.n_ci_blk;
+    int chunks = kNumSMs / (pl.n_ci_blk * pl.n_m_blk);
     if (chunks < 1) chunks = 1;
     if (chunks > tiles) chunks = (int)tiles;
     pl.chunks = chunks;
@@ -188,38 +190,38 @@ static WtPlan wt_plan(int N, int H, int W, int Cin_p, int KS) {
 
 }  // namespace
 
-extern "C" int64_t cwfa_wgrad_tc_workspace_floats(int N, int H, int W, int Cin, int Cin_p, int Cout, int KH) {
+extern "C" int64_t cwfa_wgrad_tc_workspace_floats(int N, int H, int W, int Cin, int Cin_p, int Cout, int Cout_p, int KH) {
     if (KH != 1 && KH != 3) return -1;
-    return (int64_t)wt_plan(N, H, W, Cin_p, KH).chunks * Cout * Cin * KH * KH;
+    return (int64_t)wt_plan(N, H, W, Cin_p, Cout_p, KH).chunks * Cout * Cin * KH * KH;
 }
 
 extern "C" int cwfa_wgrad_tc(const void* x_c8, const void* dy_c8, float* dw, float* workspace, int N, int H, int W, int Cin,
                              int Cin_p, int Cout, int Cout_p, int KH, int KW, int is_bf16, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (N <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || KH != KW || (KH != 1 && KH != 3) || (Cin_p % 16) || (Cout_p % 16) ||
-        Cin_p < Cin || Cout_p < Cout || Cout_p > 128 || !x_c8 || !dy_c8 || !dw || !workspace) {
-        set_error("wgrad_tc: unsupported configuration (Cin_p=%d Cout_p=%d K=%dx%d; needs Cout_p <= 128, 1x1 or 3x3)", Cin_p, Cout_p, KH, KW);
+        Cin_p < Cin || Cout_p < Cout || !x_c8 || !dy_c8 || !dw || !workspace) {
+        set_error("wgrad_tc: unsupported configuration (Cin_p=%d Cout_p=%d K=%dx%d; needs 1x1 or 3x3)", Cin_p, Cout_p, KH, KW);
         return CWFA_EINVAL;
     }
     if ((reinterpret_cast<uintptr_t>(x_c8) & 15) || (reinterpret_cast<uintptr_t>(dy_c8) & 15)) {
         set_error("wgrad_tc: pointers must be 16-byte aligned");
         return CWFA_EINVAL;
     }
-    const WtPlan pl = wt_plan(N, H, W, Cin_p, KH);
+    const WtPlan pl = wt_plan(N, H, W, Cin_p, Cout_p, KH);
     WtParams p{};
     p.N = N; p.H = H; p.W = W; p.Cout = Cout; p.Cin = Cin;
-    p.co_chunks = Cout_p / 8; p.nb_chunks = pl.nb_chunks;
+    p.co_chunks = Cout_p / 8 < 16 ? Cout_p / 8 : 16; p.nb_chunks = pl.nb_chunks;
     p.tiles_x = ceil_div(W, WT_BW); p.tiles_y = ceil_div(H, WT_BH);
     const int64_t nt = (int64_t)p.tiles_x * p.tiles_y * N;
     if (nt > 0x7fffffff) { set_error("wgrad_tc: too many tiles"); return CWFA_EINVAL; }
     p.num_tiles = (int)nt;
     p.part = workspace;
     CUtensorMap tm_dy, tm_x;
-    int rc = make_c8_tensor_map(&tm_dy, dy_c8, N, Cout_p / 8, H, W, WT_BW, WT_BH, Cout_p / 8, is_bf16);
+    int rc = make_c8_tensor_map(&tm_dy, dy_c8, N, Cout_p / 8, H, W, WT_BW, WT_BH, p.co_chunks, is_bf16);
     if (rc) return rc;
     rc = make_c8_tensor_map(&tm_x, x_c8, N, Cin_p / 8, H, W, WT_BW + KH - 1, WT_BH + KH - 1, pl.nb_chunks, is_bf16);
     if (rc) return rc;
-    dim3 grid(pl.chunks, pl.n_ci_blk);
+    dim3 grid(pl.chunks, pl.n_ci_blk, pl.n_m_blk);
     if (KH == 3) {
         const size_t smem = 2048 + (size_t)WT_STAGES * WtGeom<3>::stage_bytes(pl.nb_chunks);
         static bool attr = false;

@@ -230,10 +230,10 @@ int cwfa_conv2d_wgrad_f32(const float* x, const float* dy, float* dw, float* wor
                           int Cout, int KH, int KW, int accumulate, void* stream);
 int cwfa_conv2d_dgrad_weights_f32(const float* w, float* wt, int Cout, int Cin, int KH, int KW, void* stream);
 /* Convolution weight gradient on the tcgen05 tensor cores (csrc/wgrad_tc.cu): x and dy are C8 half tensors (Cin_p / Cout_p
- * channels, Cout_p <= 128), dW is (Cout,Cin,KH,KW) fp32, square kernels 1x1 / 3x3, stride 1, 'same'.  The contraction over
+ * channels; output channels in M blocks of 128), dW is (Cout,Cin,KH,KW) fp32, square kernels 1x1 / 3x3, stride 1, 'same'.  The contraction over
  * pixels runs as M=128 x N<=64 x K=16 MMAs on MN-major operands (the C8 tile is the operand as TMA lands it; a tap is a
  * descriptor offset); one fp32 partial per CTA, fixed-order final sum.  workspace >= cwfa_wgrad_tc_workspace_floats(...). */
-int64_t cwfa_wgrad_tc_workspace_floats(int N, int H, int W, int Cin, int Cin_p, int Cout, int KH);
+int64_t cwfa_wgrad_tc_workspace_floats(int N, int H, int W, int Cin, int Cin_p, int Cout, int Cout_p, int KH);
 int cwfa_wgrad_tc(const void* x_c8, const void* dy_c8, float* dw, float* workspace, int N, int H, int W, int Cin, int Cin_p,
                   int Cout, int Cout_p, int KH, int KW, int is_bf16, void* stream);
 /* ELU(alpha=1) adjoint from the layer OUTPUT y: dv = dy * (y > 0 ? 1 : y + 1)  (dv may alias dy). */

@@ -85,7 +85,8 @@ def test_conv2d_adjoints(N, Cin, Cout, H, W, K, act, use_res):
 
 @pytest.mark.parametrize("kind", ["bf16", "fp16"])
 @pytest.mark.parametrize("N,Cin,Cout,H,W,K", [(1, 64, 64, 32, 32, 3), (2, 29, 48, 13, 37, 3), (1, 64, 96, 40, 24, 3), (1, 6, 64, 64, 64, 1),
-                                              (1, 64, 64, 17, 33, 1), (1, 48, 48, 24, 40, 3), (2, 64, 12, 64, 48, 3), (1, 96, 64, 8, 16, 1)])
+                                              (1, 64, 64, 17, 33, 1), (1, 48, 48, 24, 40, 3), (2, 64, 12, 64, 48, 3), (1, 96, 64, 8, 16, 1),
+                                              (1, 48, 200, 16, 32, 3), (1, 160, 48, 16, 32, 3), (1, 16, 1536, 8, 16, 3), (1, 256, 300, 9, 17, 1)])
 def test_wgrad_tensor_core_kernel(kind, N, Cin, Cout, H, W, K):
     """csrc/wgrad_tc.cu (MN-major tcgen05 operands straight from the C8 tiles) vs torch's fp32 weight gradient of the SAME
     half-rounded inputs: only the fp32 summation order differs -> rel-L2 <= 2e-5."""
