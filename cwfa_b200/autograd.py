@@ -247,7 +247,7 @@ class _Affine(_F):
             a_s, a_t = aa, ops._prep_inner(t_src.detach())[0]
             ch = aa.shape[1]
         y, logdet = ops.affine(xx, a_s, a_t, inverse=inverse, clamp=clamp, t_scale=t_scale, k_atan=k_atan, s_is_final=raw)
-        ctx.cfg = (bool(inverse), float(clamp), float(t_scale), float(k_atan), bool(raw), packed, ch)
+        ctx.cfg = (bool(inverse), float(clamp), float(t_scale), float(k_atan), int(raw), packed, ch)     # raw: 0 ATAN, 1 final s, 2 TANH
         ctx.save_for_backward(xx, aa, None if packed else a_t)
         return y, logdet
 
@@ -279,7 +279,7 @@ class _Affine(_F):
             dt = torch.empty_like(dy) if need_t else None
             da_t_ptr, ld_dt = (None if dt is None else dt.data_ptr()), n
         _lib.call("cwfa_affine_bwd", ops._p(x), a_s_ptr, a_t_ptr, dy.data_ptr(), ops._p(gj), ops._p(dx), da_s_ptr, da_t_ptr,
-                  B, ch, P, ld_s, ld_t, ld_ds, ld_dt, clamp, k_atan, t_scale, int(inverse) | (2 if raw else 0), _stream())
+                  B, ch, P, ld_s, ld_t, ld_ds, ld_dt, clamp, k_atan, t_scale, int(inverse) | (4 if raw == 2 else (2 if raw else 0)), _stream())
         return dx, da, dt, None, None, None, None, None
 
 

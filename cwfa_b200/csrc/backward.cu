@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(256) affine_bwd_kernel(const float* __restrict
                                                          const float* __restrict__ g_logdet, float* __restrict__ dx,
                                                          float* __restrict__ da_s, float* __restrict__ da_t, int64_t n,
                                                          int64_t ld_s, int64_t ld_t, int64_t ld_ds, int64_t ld_dt,
-                                                         float kk, float t_scale, int raw) {
+                                                         float kk, float t_scale, int raw, float k_in) {
     const int b = blockIdx.y;
     const float* xs = x ? x + (int64_t)b * n : nullptr;
     const float* ss = a_s + (int64_t)b * ld_s;
@@ -293,7 +293,8 @@ __global__ void __launch_bounds__(256) affine_bwd_kernel(const float* __restrict
     const float gj = g_logdet ? __ldg(g_logdet + b) : 0.f;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const float as = ss[i];
-        const float s = raw ? as : kk * atanf(as);
+        const float th = raw == 2 ? tanhf(k_in * as) : 0.f;
+        const float s = raw == 1 ? as : (raw == 2 ? kk * th : kk * atanf(as));
         const float g = gs[i];
         const float xv = xs ? xs[i] : 0.f;
         float gx, gt, gsv;
@@ -311,21 +312,21 @@ __global__ void __launch_bounds__(256) affine_bwd_kernel(const float* __restrict
         }
         if (dx) dx[(int64_t)b * n + i] = gx;
         if (da_t) da_t[(int64_t)b * ld_dt + i] = gt * t_scale;
-        if (da_s) da_s[(int64_t)b * ld_ds + i] = raw ? gsv : gsv * kk / fmaf(as, as, 1.f);
+        if (da_s) da_s[(int64_t)b * ld_ds + i] = raw == 1 ? gsv : (raw == 2 ? gsv * kk * k_in * (1.f - th * th) : gsv * kk / fmaf(as, as, 1.f));
     }
 }
 extern "C" int cwfa_affine_bwd(const float* x, const float* a_s, const float* a_t, const float* dy, const float* g_logdet,
                                float* dx, float* da_s, float* da_t, int B, int ch, int64_t P, int64_t ld_s, int64_t ld_t,
                                int64_t ld_ds, int64_t ld_dt, float clamp, float k_atan, float t_scale, int flags,
                                void* stream) {
-    const int inverse = flags & 1, raw = (flags >> 1) & 1;
+    const int inverse = flags & 1, raw = (flags & 4) ? 2 : ((flags >> 1) & 1);
     if (B <= 0 || ch <= 0 || P <= 0 || !a_s || !a_t || !dy) { set_error("affine_bwd: bad args"); return CWFA_EINVAL; }
     if (!x && !inverse) { set_error("affine_bwd: x may be NULL only in inverse mode"); return CWFA_EINVAL; }
     const int64_t n = (int64_t)ch * P;
     dim3 grid(ew_blocks(n) < kNumSMs * 4 ? ew_blocks(n) : kNumSMs * 4, B);
-    const float kk = clamp * k_atan;
-    if (inverse) affine_bwd_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, a_s, a_t, dy, g_logdet, dx, da_s, da_t, n, ld_s, ld_t, ld_ds, ld_dt, kk, t_scale, raw);
-    else affine_bwd_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(x, a_s, a_t, dy, g_logdet, dx, da_s, da_t, n, ld_s, ld_t, ld_ds, ld_dt, kk, t_scale, raw);
+    const float kk = raw == 2 ? clamp : clamp * k_atan;
+    if (inverse) affine_bwd_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, a_s, a_t, dy, g_logdet, dx, da_s, da_t, n, ld_s, ld_t, ld_ds, ld_dt, kk, t_scale, raw, k_atan);
+    else affine_bwd_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(x, a_s, a_t, dy, g_logdet, dx, da_s, da_t, n, ld_s, ld_t, ld_ds, ld_dt, kk, t_scale, raw, k_atan);
     return check_launch("affine_bwd");
 }
 

@@ -270,7 +270,7 @@ template <int VEC, bool INV>
 __global__ void __launch_bounds__(256) affine_kernel(const float* __restrict__ x, const float* __restrict__ a_s,
                                                      const float* __restrict__ a_t, float* __restrict__ y,
                                                      float* __restrict__ ws, int ch, int64_t P, int64_t ld_s,
-                                                     int64_t ld_t, float kk, float t_scale, int raw) {
+                                                     int64_t ld_t, float kk, float t_scale, int raw, float k_in) {
     const int b = blockIdx.y;
     const int64_t n = (int64_t)ch * P;           // elements of this sample
     const float* xs = x ? x + (int64_t)b * n : nullptr;
@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(256) affine_kernel(const float* __restrict__ x
         }
 #pragma unroll
         for (int k = 0; k < VEC; ++k) {
-            const float s = raw ? sv[k] : kk * atanf(sv[k]);
+            const float s = raw == 1 ? sv[k] : (raw == 2 ? kk * tanhf(k_in * sv[k]) : kk * atanf(sv[k]));
             const float t = t_scale * tv[k];
             sum_s += s;
             yv[k] = INV ? (xv[k] - t) * expf(-s) : expf(s) * xv[k] + t;
@@ -341,7 +341,7 @@ extern "C" int cwfa_affine_workspace_blocks(void) { return kAffineBlocks; }
 extern "C" int cwfa_affine(const float* x, const float* a_s, const float* a_t, float* y, float* logdet, float* sumsq,
                            float* workspace, int B, int ch, int64_t P, int64_t ld_s, int64_t ld_t, float clamp,
                            float k_atan, float t_scale, int flags, void* stream) {
-    const int inverse = flags & 1, raw = (flags >> 1) & 1;
+    const int inverse = flags & 1, raw = (flags & 4) ? 2 : ((flags >> 1) & 1);
     cudaStream_t st = (cudaStream_t)stream;
     if (B <= 0 || ch <= 0 || P <= 0 || !a_s || !a_t || !y || !logdet || !workspace) {
         set_error("affine: bad args");
@@ -352,13 +352,13 @@ extern "C" int cwfa_affine(const float* x, const float* a_s, const float* a_t, f
     const bool vec = (n % 4 == 0) && (ld_s % 4 == 0) && (ld_t % 4 == 0) && aligned16(a_s) && aligned16(a_t) &&
                      aligned16(y) && (!x || aligned16(x));
     dim3 grid(kAffineBlocks, B);
-    const float kk = clamp * k_atan;
+    const float kk = raw == 2 ? clamp : clamp * k_atan;      // TANH mode: s = clamp * tanh(k_atan * a)
     if (vec) {
-        if (inverse) affine_kernel<4, true><<<grid, 256, 0, st>>>(x, a_s, a_t, y, workspace, ch, P, ld_s, ld_t, kk, t_scale, raw);
-        else affine_kernel<4, false><<<grid, 256, 0, st>>>(x, a_s, a_t, y, workspace, ch, P, ld_s, ld_t, kk, t_scale, raw);
+        if (inverse) affine_kernel<4, true><<<grid, 256, 0, st>>>(x, a_s, a_t, y, workspace, ch, P, ld_s, ld_t, kk, t_scale, raw, k_atan);
+        else affine_kernel<4, false><<<grid, 256, 0, st>>>(x, a_s, a_t, y, workspace, ch, P, ld_s, ld_t, kk, t_scale, raw, k_atan);
     } else {
-        if (inverse) affine_kernel<1, true><<<grid, 256, 0, st>>>(x, a_s, a_t, y, workspace, ch, P, ld_s, ld_t, kk, t_scale, raw);
-        else affine_kernel<1, false><<<grid, 256, 0, st>>>(x, a_s, a_t, y, workspace, ch, P, ld_s, ld_t, kk, t_scale, raw);
+        if (inverse) affine_kernel<1, true><<<grid, 256, 0, st>>>(x, a_s, a_t, y, workspace, ch, P, ld_s, ld_t, kk, t_scale, raw, k_atan);
+        else affine_kernel<1, false><<<grid, 256, 0, st>>>(x, a_s, a_t, y, workspace, ch, P, ld_s, ld_t, kk, t_scale, raw, k_atan);
     }
     int rc = check_launch("affine");
     if (rc) return rc;

@@ -459,3 +459,173 @@ class share_subnet_outputs:
     def __exit__(self, *exc):
         _SUBNET_MEMO.pop()
         return False
+
+
+# ---------------------------------------------------------------------------------------------
+# ActNorm and AllInOneBlock (the remaining selectable module-API surface)
+# ---------------------------------------------------------------------------------------------
+class ActNorm(InvertibleModule):
+    """Per-channel affine y = x * exp(scale) + bias, initialised from the first batch to zero mean / unit std
+    (FrEIA/modules/invertible_resnet.py:11-85).  One ``scale_shift`` kernel per call; the data-dependent initialisation
+    reads the per-channel (sum, sum of squares) from the ``channel_stats`` kernel."""
+
+    def __init__(self, dims_in, dims_c=None, init_data: Union[torch.Tensor, None] = None):
+        super().__init__(dims_in, dims_c)
+        self.dims_in = dims_in[0]
+        param_dims = [1, self.dims_in[0]] + [1 for _ in range(len(self.dims_in) - 1)]
+        self.scale = nn.Parameter(torch.zeros(*param_dims))
+        self.bias = nn.Parameter(torch.zeros(*param_dims))
+        self.init_on_next_batch = init_data is None
+        if init_data is not None:
+            self._initialize_with_data(init_data)
+        self._register_load_state_dict_pre_hook(lambda *a: setattr(self, "init_on_next_batch", False))
+
+    @torch.no_grad()
+    def _initialize_with_data(self, data):
+        assert all(data.shape[i + 1] == self.dims_in[i] for i in range(len(self.dims_in))), \
+            "Can't initialize ActNorm layer, provided data don't match input dimensions."
+        C = self.dims_in[0]
+        x = data.reshape(data.shape[0], C, -1)
+        n = x.shape[0] * x.shape[2]
+        s, q = ops.channel_stats(x.reshape(x.shape[0], C, 1, -1)).double()
+        var = (q - s * s / n) / (n - 1)                                   # torch.std: unbiased
+        scale = torch.log(1.0 / var.sqrt())
+        self.scale.data = scale.float().view_as(self.scale).to(self.scale.device)
+        self.bias.data = (-(s / n) * scale.exp()).float().view_as(self.bias).to(self.bias.device)
+        self.init_on_next_batch = False
+
+    def forward(self, x, rev=False, jac=True):
+        if self.init_on_next_batch:
+            self._initialize_with_data(x[0])
+        j = (self.scale.sum() * np.prod(self.dims_in[1:])).repeat(x[0].shape[0])
+        e = self.scale.detach().reshape(-1).exp()
+        b = self.bias.detach().reshape(-1)
+        if not rev:
+            return [ops.scale_shift(x[0], e, b)], j
+        return [ops.scale_shift(x[0], 1.0 / e, -b / e)], -j
+
+    def output_dims(self, input_dims):
+        assert len(input_dims) == 1, "Can only use 1 input"
+        return input_dims
+
+
+class AllInOneBlock(InvertibleModule):
+    """Coupling + (soft / hard / Householder) permutation + global affine in one block
+    (FrEIA/modules/all_in_one_block.py:13-271), for image-shaped inputs (rank 2).
+    ``y = W (Psi(s_global) * Coupling(x) + t_global)``; the coupling is ``x2 * exp(clamp * tanh(0.1 a_s)) + 0.1 a_t`` with
+    ``a = subnet(cat(x1, c))``.  The coupling runs in the fused affine kernel (TANH clamp mode), the channel mixing as a
+    1x1 convolution, the global affine as one scale/shift pass."""
+
+    def __init__(self, dims_in, dims_c=[], subnet_constructor: Callable = None, affine_clamping: float = 2.0,
+                 gin_block: bool = False, global_affine_init: float = 1.0, global_affine_type: str = "SOFTPLUS",
+                 permute_soft: bool = False, learned_householder_permutation: int = 0, reverse_permutation: bool = False):
+        super().__init__(dims_in, dims_c)
+        channels = dims_in[0][0]
+        self.input_rank = len(dims_in[0]) - 1
+        if self.input_rank != 2:
+            raise ValueError("cwfa_b200.AllInOneBlock implements image-shaped inputs (C,H,W) only")
+        self.sum_dims = tuple(range(1, 2 + self.input_rank))
+        if len(dims_c) == 0:
+            self.conditional, self.condition_channels = False, 0
+        else:
+            assert tuple(dims_c[0][1:]) == tuple(dims_in[0][1:]), \
+                f"Dimensions of input and condition don't agree: {dims_c} vs {dims_in}."
+            self.conditional, self.condition_channels = True, sum(dc[0] for dc in dims_c)
+        self.splits = [channels - channels // 2, channels // 2]
+        self.in_channels, self.clamp, self.GIN = channels, affine_clamping, gin_block
+        self.reverse_pre_permute, self.householder = reverse_permutation, learned_householder_permutation
+        if permute_soft and channels > 512:
+            warnings.warn(f"Soft permutation will take a very long time to initialize with {channels} feature channels. "
+                          "Consider using hard permutation instead.")
+        if global_affine_type == "SIGMOID":
+            global_scale = 2.0 - np.log(10.0 / global_affine_init - 1.0)
+            self.global_scale_activation = lambda a: 10 * torch.sigmoid(a - 2.0)
+        elif global_affine_type == "SOFTPLUS":
+            global_scale = 2.0 * np.log(np.exp(0.5 * 10.0 * global_affine_init) - 1)
+            self.softplus = nn.Softplus(beta=0.5)
+            self.global_scale_activation = lambda a: 0.1 * self.softplus(a)
+        elif global_affine_type == "EXP":
+            global_scale = np.log(global_affine_init)
+            self.global_scale_activation = lambda a: torch.exp(a)
+        else:
+            raise ValueError('Global affine activation must be "SIGMOID", "SOFTPLUS" or "EXP"')
+        self.global_scale = nn.Parameter(torch.ones(1, channels, 1, 1) * float(global_scale))
+        self.global_offset = nn.Parameter(torch.zeros(1, channels, 1, 1))
+        if permute_soft:
+            from scipy.stats import special_ortho_group
+            w = special_ortho_group.rvs(channels)
+        else:
+            w = np.zeros((channels, channels))
+            for i, j in enumerate(np.random.permutation(channels)):
+                w[i, j] = 1.0
+        if self.householder:
+            self.vk_householder = nn.Parameter(0.2 * torch.randn(self.householder, channels), requires_grad=True)
+            self.w_perm = self.w_perm_inv = None
+            self.w_0 = nn.Parameter(torch.FloatTensor(w), requires_grad=False)
+        else:
+            self.w_perm = nn.Parameter(torch.FloatTensor(w).view(channels, channels, 1, 1), requires_grad=False)
+            self.w_perm_inv = nn.Parameter(torch.FloatTensor(w.T).view(channels, channels, 1, 1), requires_grad=False)
+        if subnet_constructor is None:
+            raise ValueError("Please supply a callable subnet_constructor function or object (see docstring)")
+        self.subnet = subnet_constructor(self.splits[0] + self.condition_channels, 2 * self.splits[1])
+        self.last_jac = None
+
+    def _construct_householder_permutation(self):
+        w = self.w_0
+        for vk in self.vk_householder:                      # C x C host-side algebra on the reflection vectors
+            w = torch.mm(w, torch.eye(self.in_channels, device=w.device) - 2 * torch.ger(vk, vk) / torch.dot(vk, vk))
+        return w.reshape(self.in_channels, self.in_channels, 1, 1)
+
+    def _permute(self, x, rev=False):
+        if self.GIN:
+            scale, perm_log_jac = None, 0.0
+        else:
+            scale = self.global_scale_activation(self.global_scale).detach().reshape(-1)
+            perm_log_jac = torch.sum(torch.log(scale))
+        off = self.global_offset.detach().reshape(-1)
+        if rev:
+            y = ops.conv2d(x, self.w_perm_inv.detach(), None)
+            return (ops.scale_shift(y, torch.ones_like(off) if scale is None else 1.0 / scale, -off if scale is None else -off / scale),
+                    perm_log_jac)
+        y = ops.scale_shift(x, torch.ones_like(off) if scale is None else scale, off)
+        return ops.conv2d(y, self.w_perm.detach(), None), perm_log_jac
+
+    def _pre_permute(self, x, rev=False):
+        return ops.conv2d(x, (self.w_perm if rev else self.w_perm_inv).detach(), None)
+
+    def _affine(self, x, a, rev=False):
+        ch = x.shape[1]
+        if self.GIN:
+            s = self.clamp * torch.tanh(0.1 * a[:, :ch])
+            s = s - torch.mean(s, dim=self.sum_dims, keepdim=True)
+            y, _ = ops.affine(x, s.contiguous(), a[:, ch:], inverse=rev, t_scale=0.1, s_is_final=True)
+            j = torch.sum(s, dim=self.sum_dims)
+            return y, (-j if rev else j)
+        return ops.affine(x, a[:, :ch], a[:, ch:], inverse=rev, clamp=self.clamp, k_atan=0.1, t_scale=0.1, tanh_clamp=True)
+
+    def forward(self, x, c=[], rev=False, jac=True):
+        if self.householder:
+            self.w_perm = self._construct_householder_permutation()
+            if rev or self.reverse_pre_permute:
+                self.w_perm_inv = self.w_perm.transpose(0, 1).contiguous()
+        global_scaling_jac = 0.0
+        if rev:
+            x0, global_scaling_jac = self._permute(x[0], rev=True)
+        elif self.reverse_pre_permute:
+            x0 = self._pre_permute(x[0], rev=False)
+        else:
+            x0 = x[0]
+        x1, x2 = torch.split(x0, self.splits, dim=1)
+        x1c = torch.cat([x1, *c], 1) if self.conditional else x1.contiguous()
+        a1 = self.subnet(x1c)
+        x2, j2 = self._affine(x2.contiguous(), a1, rev=rev)
+        x_out = torch.cat((x1, x2), 1)
+        if not rev:
+            x_out, global_scaling_jac = self._permute(x_out, rev=False)
+        elif self.reverse_pre_permute:
+            x_out = self._pre_permute(x_out, rev=True)
+        n_pixels = x_out[0, :1].numel()
+        return (x_out,), j2 + (-1) ** rev * n_pixels * global_scaling_jac
+
+    def output_dims(self, input_dims):
+        return input_dims

@@ -328,7 +328,7 @@ def conditional_wavelet_flow(input_volume_shape, condition_shape, st_subnet, con
         cond_channels = [cond_net.subnetworks[0].out_channels] + list(condition_shape[2:])
 
     blocks = {"RNVP": Fm.RNVPCouplingBlock, "GLOW": Fm.GLOWCouplingBlock, "GIN": Fm.GINCouplingBlock,
-              "CAT": Fm.ConditionalAffineTransform}
+              "CAT": Fm.ConditionalAffineTransform, "AI1": Fm.AllInOneBlock}
     if block_type not in blocks:
         raise ValueError(f"block_type {block_type!r} is not implemented (have {sorted(blocks)})")
     INN_block = blocks[block_type]
@@ -385,6 +385,8 @@ def level_spec(inn: "Ff.GraphINN") -> dict:
             nodes.append({"idx": i, "type": "GLOW"})
         elif isinstance(m, Fm.RNVPCouplingBlock):
             nodes.append({"idx": i, "type": "RNVP"})
+        elif isinstance(m, Fm.AllInOneBlock):
+            nodes.append({"idx": i, "type": "AI1"})
         else:
             raise ValueError(f"unsupported module in flow level: {type(m).__name__}")
     return {"nodes": nodes}

@@ -177,14 +177,16 @@ def _prep_inner(t: torch.Tensor):
 
 def affine(x: Optional[torch.Tensor], a_s: torch.Tensor, a_t: torch.Tensor, *, inverse: bool,
            clamp: float = CLAMP_DEFAULT, t_scale: float = 1.0, want_sumsq: bool = False,
-           k_atan: float = K_ATAN, s_is_final: bool = False):
+           k_atan: float = K_ATAN, s_is_final: bool = False, tanh_clamp: bool = False):
     """Affine coupling with fused log-det.  a_s / a_t: (B,ch,H,W) views whose inner (ch,H,W)
-    block is contiguous (e.g. the two channel halves of one subnet output)."""
+    block is contiguous (e.g. the two channel halves of one subnet output).
+    ``tanh_clamp``: s = clamp * tanh(k_atan * a_s) (AllInOneBlock, all_in_one_block.py:206-211) instead of the ATAN clamp."""
     if not a_s.is_cuda:
         raise RuntimeError("cwfa_b200: affine needs CUDA tensors (no CPU fallback)")
     if _grad_on(x, a_s, a_t):
         from . import autograd as ag
-        y, logdet = ag.affine(x, a_s, a_t, inverse=inverse, clamp=clamp, t_scale=t_scale, k_atan=k_atan, s_is_final=s_is_final)
+        y, logdet = ag.affine(x, a_s, a_t, inverse=inverse, clamp=clamp, t_scale=t_scale, k_atan=k_atan,
+                              s_is_final=2 if tanh_clamp else int(bool(s_is_final)))
         return (y, logdet, ag.sum_squares(y)) if want_sumsq else (y, logdet)
     B, ch = a_s.shape[0], a_s.shape[1]
     P = a_s[0, 0].numel()
@@ -197,7 +199,7 @@ def affine(x: Optional[torch.Tensor], a_s: torch.Tensor, a_t: torch.Tensor, *, i
     nblk = _lib.load().cwfa_affine_workspace_blocks()
     ws = torch.empty(2 * B * nblk, device=a_s.device, dtype=torch.float32)
     _lib.call("cwfa_affine", _p(xx), a_s.data_ptr(), a_t.data_ptr(), y.data_ptr(), logdet.data_ptr(), _p(sumsq),
-              ws.data_ptr(), B, ch, P, ld_s, ld_t, float(clamp), float(k_atan), float(t_scale), int(inverse) | (2 if s_is_final else 0), _stream())
+              ws.data_ptr(), B, ch, P, ld_s, ld_t, float(clamp), float(k_atan), float(t_scale), int(inverse) | (4 if (tanh_clamp or s_is_final == 2) else (2 if s_is_final else 0)), _stream())
     return (y, logdet, sumsq) if want_sumsq else (y, logdet)
 
 
@@ -289,6 +291,18 @@ def batchnorm(x: torch.Tensor, gamma, beta, running_mean=None, running_var=None,
               shift.data_ptr(), C, count, float(eps), _stream())
     y = torch.empty_like(x)
     _lib.call("cwfa_scale_shift_f32", x.data_ptr(), scale.data_ptr(), shift.data_ptr(), y.data_ptr(), N, C, P, _stream())
+    return y
+
+
+def scale_shift(x: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor) -> torch.Tensor:
+    """y[b,c,...] = x[b,c,...] * scale[c] + shift[c]  (ActNorm / global affine of AllInOneBlock)."""
+    if _grad_on(x, scale, shift):
+        _no_adjoint("scale_shift")
+    x = _ck(x, "x")
+    N, C = x.shape[0], x.shape[1]
+    P = x[0, 0].numel()
+    y = torch.empty_like(x)
+    _lib.call("cwfa_scale_shift_f32", x.data_ptr(), _ck(scale, "scale").data_ptr(), _ck(shift, "shift").data_ptr(), y.data_ptr(), N, C, P, _stream())
     return y
 
 

@@ -223,3 +223,52 @@ class FlowLevelTrainer:
         self.optimizer.step()
         parts["loss"] = loss.detach()
         return parts
+
+
+# ---------------------------------------------------------------------------------------------
+# OOD decision and the coarse-to-fine fine-tune schedule
+# ---------------------------------------------------------------------------------------------
+def ood_decision(nll_per_level: Sequence[torch.Tensor], step_LL_to_use: int = 0, step_LL_ths_to_use: float = -1.33) -> torch.Tensor:
+    """Out-of-distribution flag per frame from the forward-NLL scores (``CWFAModel.forward_nll`` -> ``nll_per_sample``).
+    The reference declares the knobs (main.py:79-80: ``--step_LL_to_use`` = which flow level's likelihood, ``--step_LL_ths_to_use``
+    = -1.33) but its ``evaluate_OOD_prediction`` is not in the tree (main.py:16,401 are commented out), so the rule is the
+    paper's: a frame is OUT of distribution when the log-likelihood of the chosen level, LL = -NLL, falls below the threshold."""
+    ll = -nll_per_level[step_LL_to_use]
+    return ll < step_LL_ths_to_use
+
+
+def fine_tune_flow_levels(model, frames: Sequence[dict], levels: Optional[Sequence[int]] = None, epochs_per_step: int = 1,
+                          precision: str = "fp32", lr: float = 221e-7, lr_cond: float = 845e-7, weight_decay: float = 1e-2,
+                          cond_weight: float = INN_COND_WEIGHT, group=None):
+    """Coarse-to-fine schedule of the reference's fine-tune loop (CWFA.py:746-771) for the flow levels: the level being
+    optimised moves from the coarsest flow (L-2) to the finest (0); while a level trains, its input volume per frame comes from
+    the cache filled by the level below it (``upsampled_cache``, CWFA.py:748-750,919-920), which starts from the LRNN output.
+
+    frames: dicts with ``views`` (1,29,S,S), ``gt`` (1,D,S,S) and ``mean_vols`` (list, level n -> (1,C_n/2,S,S); optional last
+    entry = the LRNN's mean volume).  Returns {level: [loss per step]}.  (The LRNN's own training step -- U-Net adjoints -- is
+    not implemented; its weights are used as they are.)"""
+    L1 = model.n_levels
+    levels = list(range(L1 - 1, -1, -1)) if levels is None else list(levels)
+    with torch.no_grad():
+        gt_caches, cache = [], []
+        for f in frames:
+            _, gtc, _, _ = model.evaluate_INN_forward(f["gt"], extra_cond_in=f["mean_vols"], fix_empty_depths=False)   # GT pyramid
+            gt_caches.append(gtc)
+            mv_last = f["mean_vols"][L1] if len(f["mean_vols"]) > L1 else None
+            cache.append(model.cond_nets[L1](f["views"], mv_last)[-1])                                                  # CWFA.py:882
+    history = {}
+    for n in range(L1 - 1, -1, -1):
+        if n in levels:
+            tr = FlowLevelTrainer(model, n, lr=lr, lr_cond=lr_cond, weight_decay=weight_decay, cond_weight=cond_weight,
+                                  group=group, precision=precision)
+            history[n] = []
+            for _ in range(epochs_per_step):
+                for i, f in enumerate(frames):
+                    history[n].append(float(tr.step(gt_caches[i][n], f["views"], f["mean_vols"][n], cache[i])["loss"]))
+            tr.release()
+        with torch.no_grad():                                  # last pass of the step: refill the cache for the next finer level
+            for i, f in enumerate(frames):
+                c0 = model.cond_nets[n](f["views"])[-1]
+                z = torch.zeros((cache[i].shape[0],) + tuple(model.conv_inn[n].global_out_shapes[0]), device=cache[i].device)
+                cache[i], _ = model.conv_inn[n]([z, cache[i]], c=[c0, f["mean_vols"][n]], rev=True)
+    return history, cache

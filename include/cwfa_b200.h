@@ -73,7 +73,8 @@ int cwfa_permute(const float* x, float* y, const int32_t* perm, int axis,
  * subnet output, or a_t may be the mean-volume condition with t_scale = -1/sqrt2
  * (networks.py:671).  x may be NULL in inv mode (z = 0, CWFA.py:906-907).
  * flags: bit0 = inverse; bit1 = a_s already holds the final s (no clamp applied; GIN blocks,
- * coupling_layers.py:360-361).
+ * coupling_layers.py:360-361); bit2 = TANH clamp of AllInOneBlock: s = clamp * tanh(k_atan * a_s)
+ * (all_in_one_block.py:206-211, k_atan = t_scale = 0.1).
  * logdet (B) and sumsq (B, may be NULL: sum over c,p of y^2, CWFA.py:183) are OVERWRITTEN;
  * workspace must hold 2*B*cwfa_affine_workspace_blocks() floats (deterministic 2-stage sum). */
 int cwfa_affine_workspace_blocks(void);

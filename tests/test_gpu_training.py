@@ -344,3 +344,32 @@ def test_training_steps_reduce_loss_and_are_reproducible(golden_tiny, golden_tra
     print("losses", runs[0][0])
     assert runs[0][0][-1] < runs[0][0][0]
     assert runs[0][0] == runs[1][0] and torch.equal(runs[0][1], runs[1][1])      # deterministic reductions everywhere
+
+
+def test_coarse_to_fine_schedule_and_ood_rule(golden_tiny):
+    """The reference's fine-tune schedule over the flow levels (coarsest first, per-frame cache handed down) on two tiny
+    frames, then the OOD rule on forward-NLL scores."""
+    from cwfa_b200.training import fine_tune_flow_levels, ood_decision
+    model = build_tiny_model(golden_tiny, DEV)
+    cfg = golden_tiny["config"]
+    D, S, L = cfg["D"], cfg["S"], cfg["MAX"]
+    frames = []
+    for i in range(2):
+        mv = [seeded_randn((1, D // 2 ** (n + 1), S, S), 70 + 10 * i + n, 0.1).to(DEV) for n in range(L - 1)]
+        frames.append(dict(views=seeded_randn((1, 29, S, S), 60 + i).to(DEV), gt=seeded_randn((1, D, S, S), 50 + i).to(DEV), mean_vols=mv))
+    before = model.reconstruct(frames[0]["views"], frames[0]["mean_vols"]).clone()
+    hist, cache = fine_tune_flow_levels(model, frames, epochs_per_step=2, lr=1e-4, lr_cond=1e-4)
+    assert sorted(hist) == [0, 1] and all(len(v) == 4 for v in hist.values())
+    assert all(math.isfinite(x) for v in hist.values() for x in v)
+    assert hist[1][-2] < hist[1][0] and hist[0][-2] < hist[0][0]              # same frame, one epoch later
+    assert cache[0].shape == (1, D, S, S)
+    after = model.reconstruct(frames[0]["views"], frames[0]["mean_vols"])
+    # the cache is the fine-tuned reconstruction; not bit-equal to a fresh one because the conditioning nets of ALL levels share
+    # ONE PReLU instance (networks.py:209), which kept training while level 0 was optimised
+    assert rel_l2(cache[0], after) < 2e-2 and max_abs(after, before) > 1e-4
+    res = model.forward_nll(torch.cat([f["gt"] for f in frames]), torch.cat([f["views"] for f in frames]),
+                            [torch.cat([f["mean_vols"][n] for f in frames]) for n in range(L - 1)])
+    nll = [r["nll_per_sample"] for r in res]
+    flags = ood_decision(nll, 0, -1.33)
+    assert flags.shape == (2,) and flags.dtype == torch.bool
+    assert torch.equal(flags.cpu(), (-nll[0] < -1.33).cpu())
