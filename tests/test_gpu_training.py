@@ -373,3 +373,56 @@ def test_coarse_to_fine_schedule_and_ood_rule(golden_tiny):
     flags = ood_decision(nll, 0, -1.33)
     assert flags.shape == (2,) and flags.dtype == torch.bool
     assert torch.equal(flags.cpu(), (-nll[0] < -1.33).cpu())
+
+
+def test_full_size_training_step_properties():
+    """BASELINE.json configs[3] at FULL size (level 0: 96 -> 48+48 channels, 512x512, batch 1), size-independent properties:
+    (1) directional derivative: (loss(theta + eps d) - loss(theta - eps d)) / (2 eps) = <grad, d> with d = grad / |grad|, the
+        two losses evaluated under no_grad, i.e. through the FUSED inference kernels (tolerance 3 %);
+    (2) the tensor-core (bf16) step -- conv_tc forward / data gradient, wgrad_tc incl. the 1536-channel banded stencil shapes --
+        against the fp32 step on the same weights: all-gradient rel-L2 <= 3e-2, cosine >= 0.999."""
+    import cwfa_b200
+    from cwfa_b200 import autograd as ag
+    from cwfa_b200.training import flow_level_loss
+    model = cwfa_b200.CWFAModel(n_depths=96, volume_side_size=512, INN_max_down_steps=2, seed=0).to(DEV)
+    S = 512
+    gt, views = seeded_randn((1, 96, S, S), 1).to(DEV), seeded_randn((1, 29, S, S), 2).to(DEV)
+    mv, vin = seeded_randn((1, 48, S, S), 3, 0.1).to(DEV), seeded_randn((1, 48, S, S), 4).to(DEV)
+    params = [p for p in list(model.conv_inn[0].parameters()) + list(model.cond_nets[0].parameters()) if p.requires_grad]
+
+    def grads(kind):
+        for p in params:
+            p.grad = None
+        prev = ag.set_training_precision(kind)
+        try:
+            loss, _ = flow_level_loss(model, 0, gt, views, mv, vin)
+            loss.backward()
+        finally:
+            ag.set_training_precision(prev)
+        return float(loss), [None if p.grad is None else p.grad.detach().clone() for p in params]
+
+    loss0, g32 = grads("fp32")
+    used = [i for i, g in enumerate(g32) if g is not None]
+    gnorm = math.sqrt(sum(float(g32[i].double().pow(2).sum()) for i in used))
+    assert gnorm > 0 and math.isfinite(loss0)
+    ratios = []
+    for target in (2e-3, 5e-4):                               # intended loss change across the symmetric difference
+        eps = 0.5 * target / gnorm
+        vals = []
+        with torch.no_grad():
+            for sign in (+1.0, -1.0):
+                for i in used:
+                    params[i].add_(g32[i], alpha=sign * eps / gnorm)
+                vals.append(float(flow_level_loss(model, 0, gt, views, mv, vin)[0]))
+                for i in used:
+                    params[i].sub_(g32[i], alpha=sign * eps / gnorm)
+        ratios.append((vals[0] - vals[1]) / (2 * eps) / gnorm)
+    print(f"full-size level 0: loss {loss0:.6f}, |grad| {gnorm:.4e}, finite difference / <grad, d> = {ratios}")
+    assert min(abs(r - 1.0) for r in ratios) < 3e-2, ratios
+    loss16, g16 = grads("bf16")
+    num = sum(float((g16[i].double() - g32[i].double()).pow(2).sum()) for i in used)
+    dot = sum(float((g16[i].double() * g32[i].double()).sum()) for i in used)
+    n16 = math.sqrt(sum(float(g16[i].double().pow(2).sum()) for i in used))
+    print(f"bf16 vs fp32 at full size: loss {loss16:.6f} vs {loss0:.6f}; gradient rel-L2 {math.sqrt(num) / gnorm:.2e}, cosine {dot / (gnorm * n16):.5f}")
+    assert abs(loss16 - loss0) < 2e-2 * abs(loss0)
+    assert math.sqrt(num) / gnorm < 3e-2 and dot / (gnorm * n16) > 0.999
