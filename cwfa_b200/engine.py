@@ -422,9 +422,12 @@ class StreamingReconstructor:
                            [torch.cuda.Event() for _ in range(n)], [torch.cuda.Event() for _ in range(n)])
         return self._stage
 
-    def run(self, views: Sequence[torch.Tensor], outs: Sequence[torch.Tensor]) -> None:
-        """Reconstructs ``views[i]`` into ``outs[i]``; returns when every output has been written."""
+    def run(self, views: Sequence[torch.Tensor], outs: Sequence[torch.Tensor], latency_events: Optional[list] = None) -> None:
+        """Reconstructs ``views[i]`` into ``outs[i]``; returns when every output has been written.
+        ``latency_events``: a list that receives one (start, end) pair of timing events per frame -- start when the frame's
+        input copy is issued to the device queue position it can run at, end when its output has been written."""
         n = len(views)
+        lat = latency_events
         cur = torch.cuda.current_stream()
         for st in self.s_in + self.s_run + self.s_out:
             st.wait_stream(cur)
@@ -440,6 +443,9 @@ class StreamingReconstructor:
                 with torch.cuda.stream(s_in):
                     if i >= ns:
                         s_in.wait_event(ev_in_free[j])           # the slot that used this staging buffer has copied it in
+                    if lat is not None:
+                        e0 = torch.cuda.Event(enable_timing=True)
+                        e0.record(s_in)
                     st_in[j].copy_(views[i], non_blocking=True)
                     ev_h2d[j].record(s_in)
                 with torch.cuda.stream(self.s_run[k]):           # stream order serialises the replays of one slot
@@ -455,6 +461,10 @@ class StreamingReconstructor:
                     s_out.wait_event(ev_staged[j])
                     outs[i].copy_(st_out[j], non_blocking=True)
                     ev_out_free[j].record(s_out)
+                    if lat is not None:
+                        e1 = torch.cuda.Event(enable_timing=True)
+                        e1.record(s_out)
+                        lat.append((e0, e1))
         else:
             for i in range(n):
                 k = i % self.depth
@@ -462,6 +472,9 @@ class StreamingReconstructor:
                 with torch.cuda.stream(self.s_in[k]):
                     if i >= self.depth:
                         self.s_in[k].wait_event(self.ev_run[k])      # previous replay of this slot has consumed its input
+                    if lat is not None:
+                        e0 = torch.cuda.Event(enable_timing=True)
+                        e0.record(self.s_in[k])
                     sv.copy_(views[i], non_blocking=True)
                     self.ev_in[k].record(self.s_in[k])
                 with torch.cuda.stream(self.s_run[k]):
@@ -474,6 +487,10 @@ class StreamingReconstructor:
                     self.s_out[k].wait_event(self.ev_run[k])
                     outs[i].copy_(out, non_blocking=True)
                     self.ev_out[k].record(self.s_out[k])
+                    if lat is not None:
+                        e1 = torch.cuda.Event(enable_timing=True)
+                        e1.record(self.s_out[k])
+                        lat.append((e0, e1))
         for st in self.s_out + self.s_run:
             cur.wait_stream(st)
         cur.synchronize()
