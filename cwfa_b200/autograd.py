@@ -497,3 +497,117 @@ def depth_stencil3d(x, w1, b1, slope, w2, b2):
     if _PRECISION != "fp32":
         return depth_stencil3d_banded(x, w1, b1, slope, w2, b2)
     return _DepthStencil.apply(x, w1, b1, slope, w2, b2)
+
+
+# ---------------------------------------------------------------------------------------------
+# LRNN U-Net ops (unet.py:72-113,161-195): BatchNorm2d, 2x2 max-pool, ConvTranspose2d(k=2,s=2) + skip
+# ---------------------------------------------------------------------------------------------
+class _BatchNorm(_F):
+    """y = gamma * (x - mean) * rstd + beta with batch statistics (the reference's LRNN runs in .train() mode, CWFA.py:531-532) or
+    running statistics.  Adjoint (batch): dx = a dy + b x + c0 with a = gamma rstd, b = -gamma rstd^2 <dy, xhat>/n,
+    c0 = -a <dy>/n - b mean; d gamma = <dy, xhat>, d beta = <dy> -- two per-channel sums + one element-wise pass."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, batch_stats, eps):
+        xx = _f32(x)
+        N, C = xx.shape[0], xx.shape[1]
+        P = xx[0, 0].numel()
+        n = float(N * P)
+        if batch_stats:
+            s, q = ops.channel_stats(xx).double()
+            mean = s / n
+            var = (q / n - mean * mean).clamp_min(0.0)
+        else:
+            mean, var = running_mean.detach().double(), running_var.detach().double()
+        rstd = 1.0 / torch.sqrt(var + eps)
+        g = gamma.detach().double()
+        scale = (g * rstd).float()
+        shift = (beta.detach().double() - mean * g * rstd).float()
+        ctx.save_for_backward(xx, g, mean, rstd)
+        ctx.batch_stats, ctx.n = bool(batch_stats), n
+        return ops.scale_shift(xx, scale, shift)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, g, mean, rstd = ctx.saved_tensors
+        dy = ops._ck(dy)
+        N, C = x.shape[0], x.shape[1]
+        P = x[0, 0].numel()
+        lib = _lib.load()
+        out = torch.empty(2 * C, device=x.device, dtype=torch.float32)
+        ws = torch.empty(2 * C * lib.cwfa_channel_dot_workspace_blocks(), device=x.device, dtype=torch.float32)
+        _lib.call("cwfa_channel_dot_stats_f32", x.data_ptr(), dy.data_ptr(), out.data_ptr(), ws.data_ptr(), N, C, P, _stream())
+        sdy, sdyx = out[:C].double(), out[C:].double()
+        dgamma = rstd * (sdyx - mean * sdy)
+        a = g * rstd
+        if ctx.batch_stats:
+            b = -g * rstd * rstd * dgamma / ctx.n
+            c0 = -a * sdy / ctx.n - b * mean
+        else:
+            b = torch.zeros_like(a)
+            c0 = torch.zeros_like(a)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            af, bf, cf = a.float().contiguous(), b.float().contiguous(), c0.float().contiguous()
+            _lib.call("cwfa_bn_bwd_apply_f32", dy.data_ptr(), x.data_ptr(), af.data_ptr(), bf.data_ptr(), cf.data_ptr(), dx.data_ptr(),
+                      N, C, P, _stream())
+        return dx, dgamma.float(), sdy.float(), None, None, None, None
+
+
+def batchnorm(x, gamma, beta, running_mean, running_var, *, batch_stats, eps):
+    return _BatchNorm.apply(x, gamma, beta, running_mean, running_var, batch_stats, eps)
+
+
+class _MaxPool2(_F):
+    @staticmethod
+    def forward(ctx, x):
+        xx = _f32(x)
+        ctx.save_for_backward(xx)
+        return ops.maxpool2(xx)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        dy = ops._ck(dy)
+        N, C, H, W = x.shape
+        dx = torch.empty_like(x)
+        _lib.call("cwfa_maxpool2_bwd_f32", x.data_ptr(), dy.data_ptr(), dx.data_ptr(), N, C, H, W, _stream())
+        return dx
+
+
+def maxpool2(x):
+    return _MaxPool2.apply(x)
+
+
+class _PixelShuffle2(_F):
+    """y[n,c,2h+i,2w+j] = z[n,4c+2i+j,h,w] + skip: the scatter half of ConvTranspose2d(k=2,s=2) (unet.py:166) and the skip ADD
+    (unet.py:190); the channel-mixing half is an ordinary 1x1 convolution to 4*Cout channels."""
+
+    @staticmethod
+    def forward(ctx, z, skip):
+        zz = _f32(z)
+        sk = None if skip is None else _f32(skip)
+        N, C4, H, W = zz.shape
+        y = torch.empty((N, C4 // 4, 2 * H, 2 * W), device=zz.device, dtype=torch.float32)
+        _lib.call("cwfa_pixel_shuffle2_f32", zz.data_ptr(), ops._p(sk), y.data_ptr(), N, C4 // 4, H, W, 0, _stream())
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = ops._ck(dy)
+        N, C, H2, W2 = dy.shape
+        dz = None
+        if ctx.needs_input_grad[0]:
+            dz = torch.empty((N, 4 * C, H2 // 2, W2 // 2), device=dy.device, dtype=torch.float32)
+            _lib.call("cwfa_pixel_shuffle2_f32", dy.data_ptr(), None, dz.data_ptr(), N, C, H2 // 2, W2 // 2, 1, _stream())
+        return dz, (dy if ctx.needs_input_grad[1] else None)
+
+
+def conv_transpose2x2(x, w, bias=None, skip=None):
+    """ConvTranspose2d(k=2,s=2)(x) + skip, differentiable: 1x1 convolution with W'[(co,i,j), ci] = w[ci,co,i,j] (a re-indexing of
+    the parameter; forward / data gradient / weight gradient on the convolution kernels) followed by the pixel shuffle."""
+    Cin, Cout = w.shape[0], w.shape[1]
+    wp = w.permute(1, 2, 3, 0).reshape(4 * Cout, Cin, 1, 1)
+    bp = None if bias is None else bias.repeat_interleave(4)
+    return _PixelShuffle2.apply(conv2d(x, wp, bp), skip)

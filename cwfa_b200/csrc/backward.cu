@@ -552,3 +552,140 @@ extern "C" int cwfa_lion_step_f32(float* p, const float* g, float* m, int64_t n,
     lion_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(p, g, m, n, lr, beta1, beta2, weight_decay, grad_scale);
     return check_launch("lion_step");
 }
+
+// ------------------------------------------------------------------------------------------
+// LRNN U-Net adjoints (unet.py:72-113,161-195): BatchNorm2d, 2x2 max-pool, ConvTranspose2d(k=2,s=2) as a 1x1 convolution
+// followed by a pixel shuffle (+ skip add)
+// ------------------------------------------------------------------------------------------
+// per channel: (sum dy, sum dy*x) over (N,H,W); same two-stage scheme / workspace as channel_stats (32 blocks per channel)
+constexpr int kDotBlocks = 32;
+__global__ void __launch_bounds__(256) channel_dot_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                          float* __restrict__ ws, int N, int C, int64_t P) {
+    const int c = blockIdx.y;
+    float s = 0.f, q = 0.f;
+    for (int n = 0; n < N; ++n) {
+        const float* xp = x + ((int64_t)n * C + c) * P;
+        const float* gp = dy + ((int64_t)n * C + c) * P;
+        for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < P; p += (int64_t)gridDim.x * blockDim.x) {
+            const float g = __ldg(gp + p);
+            s += g;
+            q = fmaf(g, __ldg(xp + p), q);
+        }
+    }
+    block_sum2(s, q);
+    if (threadIdx.x == 0) {
+        ws[((int64_t)c * gridDim.x + blockIdx.x) * 2 + 0] = s;
+        ws[((int64_t)c * gridDim.x + blockIdx.x) * 2 + 1] = q;
+    }
+}
+__global__ void channel_dot_finalize_kernel(const float* __restrict__ ws, float* __restrict__ out, int C, int nblocks) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s = 0.0, q = 0.0;
+    for (int i = 0; i < nblocks; ++i) {
+        s += (double)ws[((int64_t)c * nblocks + i) * 2 + 0];
+        q += (double)ws[((int64_t)c * nblocks + i) * 2 + 1];
+    }
+    out[c] = (float)s;
+    out[C + c] = (float)q;
+}
+extern "C" int cwfa_channel_dot_workspace_blocks(void) { return kDotBlocks; }
+extern "C" int cwfa_channel_dot_stats_f32(const float* x, const float* dy, float* out, float* workspace, int N, int C, int64_t P,
+                                          void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N <= 0 || C <= 0 || C > 65535 || P <= 0) { set_error("channel_dot_stats: bad shape"); return CWFA_EINVAL; }
+    channel_dot_kernel<<<dim3(kDotBlocks, C), 256, 0, st>>>(x, dy, workspace, N, C, P);
+    int rc = check_launch("channel_dot_stats");
+    if (rc) return rc;
+    channel_dot_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(workspace, out, C, kDotBlocks);
+    return check_launch("channel_dot_finalize");
+}
+
+// dx = a[c]*dy + b[c]*x + c0[c]   (BatchNorm adjoint with the per-channel coefficients computed from the two sums)
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                           const float* __restrict__ a, const float* __restrict__ b,
+                                                           const float* __restrict__ c0, float* __restrict__ dx, int64_t NC,
+                                                           int C, int64_t P) {
+    for (int64_t row = blockIdx.y; row < NC; row += gridDim.y) {
+        const int c = (int)(row % C);
+        const float aa = __ldg(a + c), bb = __ldg(b + c), cc = __ldg(c0 + c);
+        const float* gp = dy + row * P;
+        const float* xp = x + row * P;
+        float* op = dx + row * P;
+        for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < P; p += (int64_t)gridDim.x * blockDim.x)
+            op[p] = fmaf(aa, gp[p], fmaf(bb, xp[p], cc));
+    }
+}
+extern "C" int cwfa_bn_bwd_apply_f32(const float* dy, const float* x, const float* a, const float* b, const float* c0, float* dx,
+                                     int N, int C, int64_t P, void* stream) {
+    if (N <= 0 || C <= 0 || P <= 0) { set_error("bn_bwd_apply: bad shape"); return CWFA_EINVAL; }
+    const int64_t NC = (int64_t)N * C;
+    int gx = (int)((P + 255) / 256);
+    if (gx > 64) gx = 64;
+    dim3 grid(gx, NC < 4096 ? (int)NC : 4096);
+    bn_bwd_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dy, x, a, b, c0, dx, NC, C, P);
+    return check_launch("bn_bwd_apply");
+}
+
+// 2x2 max-pool adjoint: the gradient goes to the FIRST maximum of the window in row-major scan order (torch's rule)
+__global__ void __launch_bounds__(256) maxpool2_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                           float* __restrict__ dx, int64_t NC, int H2, int W2) {
+    const int W = 2 * W2;
+    for (int64_t row = blockIdx.y; row < NC * H2; row += gridDim.y) {
+        const int64_t nc = row / H2;
+        const int h2 = (int)(row % H2);
+        const float* xp = x + (nc * 2 * H2 + 2 * h2) * W;
+        float* op = dx + (nc * 2 * H2 + 2 * h2) * W;
+        const float* gp = dy + row * W2;
+        for (int w2 = blockIdx.x * blockDim.x + threadIdx.x; w2 < W2; w2 += gridDim.x * blockDim.x) {
+            const float v00 = xp[2 * w2], v01 = xp[2 * w2 + 1], v10 = xp[W + 2 * w2], v11 = xp[W + 2 * w2 + 1];
+            int k = 0;
+            float m = v00;
+            if (v01 > m) { m = v01; k = 1; }
+            if (v10 > m) { m = v10; k = 2; }
+            if (v11 > m) { m = v11; k = 3; }
+            const float g = gp[w2];
+            op[2 * w2] = k == 0 ? g : 0.f;
+            op[2 * w2 + 1] = k == 1 ? g : 0.f;
+            op[W + 2 * w2] = k == 2 ? g : 0.f;
+            op[W + 2 * w2 + 1] = k == 3 ? g : 0.f;
+        }
+    }
+}
+extern "C" int cwfa_maxpool2_bwd_f32(const float* x, const float* dy, float* dx, int N, int C, int H, int W, void* stream) {
+    if (N <= 0 || C <= 0 || H <= 0 || W <= 0 || (H & 1) || (W & 1)) { set_error("maxpool2_bwd: bad shape"); return CWFA_EINVAL; }
+    const int64_t rows = (int64_t)N * C * (H / 2);
+    dim3 grid(ceil_div(W / 2, 256), rows < 65535 ? (int)rows : 65535);
+    maxpool2_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, dy, dx, (int64_t)N * C, H / 2, W / 2);
+    return check_launch("maxpool2_bwd");
+}
+
+// pixel shuffle r = 2: y[n,c,2h+i,2w+j] = z[n,4c+2i+j,h,w] (+ skip);  inverse: z = unshuffle(y)
+__global__ void __launch_bounds__(256) pixel_shuffle2_kernel(const float* __restrict__ src, const float* __restrict__ skip,
+                                                             float* __restrict__ dst, int64_t NC, int H, int W, int inverse) {
+    // one thread per LOW-resolution pixel (h,w) of one (n,c): moves the 2x2 block
+    const int64_t P = (int64_t)H * W;
+    for (int64_t row = blockIdx.y; row < NC * H; row += gridDim.y) {
+        const int64_t nc = row / H;
+        const int h = (int)(row % H);
+        for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < W; w += gridDim.x * blockDim.x) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int64_t lo = (nc * 4 + 2 * i + j) * P + (int64_t)h * W + w;
+                    const int64_t hi = (nc * 2 * H + 2 * h + i) * (2 * (int64_t)W) + 2 * w + j;
+                    if (inverse) dst[lo] = src[hi];
+                    else dst[hi] = src[lo] + (skip ? skip[hi] : 0.f);
+                }
+        }
+    }
+}
+extern "C" int cwfa_pixel_shuffle2_f32(const float* src, const float* skip, float* dst, int N, int C, int H, int W, int inverse,
+                                       void* stream) {
+    if (N <= 0 || C <= 0 || H <= 0 || W <= 0) { set_error("pixel_shuffle2: bad shape"); return CWFA_EINVAL; }
+    const int64_t rows = (int64_t)N * C * H;
+    dim3 grid(ceil_div(W, 256), rows < 65535 ? (int)rows : 65535);
+    pixel_shuffle2_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, skip, dst, (int64_t)N * C, H, W, inverse);
+    return check_launch("pixel_shuffle2");
+}

@@ -235,6 +235,9 @@ def conv1d_flat(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], 
 
 def conv_transpose2x2(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
                       skip: Optional[torch.Tensor] = None) -> torch.Tensor:
+    if _grad_on(x, w, bias, skip):
+        from . import autograd as ag
+        return ag.conv_transpose2x2(x, w, bias, skip)
     x, w = _ck(x, "x"), _ck(w, "w")
     N, Cin, H, W = x.shape
     Cout = w.shape[1]
@@ -275,6 +278,9 @@ def batchnorm(x: torch.Tensor, gamma, beta, running_mean=None, running_var=None,
               eps: float = 1e-5) -> torch.Tensor:
     """nn.BatchNorm2d forward: batch statistics (training-mode normalisation, what the reference's
     LRNN runs at inference, CWFA.py:531-532) or running statistics (eval mode)."""
+    if _grad_on(x, gamma, beta):
+        from . import autograd as ag
+        return ag.batchnorm(x, gamma, beta, running_mean, running_var, batch_stats=batch_stats, eps=eps)
     x = _ck(x, "x")
     N, C = x.shape[0], x.shape[1]
     P = x[0, 0].numel()
@@ -307,6 +313,9 @@ def scale_shift(x: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor) -> to
 
 
 def maxpool2(x: torch.Tensor) -> torch.Tensor:
+    if _grad_on(x):
+        from . import autograd as ag
+        return ag.maxpool2(x)
     x = _ck(x, "x")
     N, C, H, W = x.shape
     y = torch.empty((N, C, H // 2, W // 2), device=x.device, dtype=torch.float32)

@@ -272,3 +272,41 @@ def fine_tune_flow_levels(model, frames: Sequence[dict], levels: Optional[Sequen
                 z = torch.zeros((cache[i].shape[0],) + tuple(model.conv_inn[n].global_out_shapes[0]), device=cache[i].device)
                 cache[i], _ = model.conv_inn[n]([z, cache[i]], c=[c0, f["mean_vols"][n]], rev=True)
     return history, cache
+
+
+# ---------------------------------------------------------------------------------------------
+# The LRNN ("last step") training step (CWFA.py:596-602, 882, 936-941)
+# ---------------------------------------------------------------------------------------------
+def lrnn_loss(model, gt: torch.Tensor, views: torch.Tensor, mean_vol: Optional[torch.Tensor] = None):
+    """``F.mse_loss(curr_gt, cond_nets[-1](views, mean_vol)[-1])`` (``loss_func_first_step='L2'``).  gt: (B, D/2^(L-1), S, S).
+    Differentiable through the U-Net (conv / PReLU / BatchNorm / max-pool / transposed conv adjoint kernels); the mean-volume
+    branch (ConvNeXt 7x7 + LayerNorm + GELU, attention gate) has no adjoints yet and is treated as a constant."""
+    from . import autograd as ag
+    vol = model.cond_nets[-1](views, mean_vol)[-1]
+    return ag.mse_loss(gt, vol), vol
+
+
+class LRNNTrainer:
+    """Lion on ``cond_nets[-1].parameters()`` with ``learning_rate_first_step`` (80e-7 after main.py:240-241) and weight decay
+    1e-2 (CWFA.py:600-602); one flat buffer (<= 255 MB fp32 at the full config), one all-reduce per step under data parallelism."""
+
+    def __init__(self, model, lr: float = 80e-7, weight_decay: float = 1e-2, group=None, precision: str = "fp32"):
+        self.model, self.group, self.precision = model, group, precision
+        self.optimizer = Lion([{"params": list(model.cond_nets[-1].parameters()), "lr": lr, "weight_decay": weight_decay}], lr=lr)
+        self.collectives = 0
+
+    def release(self):
+        self.optimizer.release()
+
+    def step(self, gt, views, mean_vol=None):
+        from . import autograd as ag
+        self.optimizer.zero_grad()
+        prev = ag.set_training_precision(self.precision)
+        try:
+            loss, _ = lrnn_loss(self.model, gt, views, mean_vol)
+            loss.backward()
+        finally:
+            ag.set_training_precision(prev)
+        self.collectives = allreduce_gradients([self.optimizer], self.group)
+        self.optimizer.step()
+        return dict(loss=loss.detach())

@@ -266,6 +266,18 @@ int cwfa_stencil3d_Cto1_f32(const float* hid, const float* w, const float* bias,
 int cwfa_stencil3d_wgrad_workspace_floats(int Cm);
 int cwfa_stencil3d_wgrad_f32(const float* single, const float* multi, float* dw, float* workspace, int B, int D, int H,
                              int W, int Cm, int flip, void* stream);
+/* LRNN U-Net adjoints (unet.py:72-113,161-195).  channel_dot_stats: out[c] = sum dy, out[C+c] = sum dy*x over (N,H,W)
+ * (workspace >= 2*C*cwfa_channel_dot_workspace_blocks() floats); bn_bwd_apply: dx = a[c]*dy + b[c]*x + c0[c] (the BatchNorm
+ * adjoint once the per-channel coefficients are known); maxpool2_bwd: gradient to the first maximum of each 2x2 window
+ * (x is the pooling INPUT (N,C,H,W), dy (N,C,H/2,W/2)); pixel_shuffle2: y[n,c,2h+i,2w+j] = z[n,4c+2i+j,h,w] (+ skip), C = channels
+ * of y, (H,W) = size of z -- with a 1x1 convolution in front this is ConvTranspose2d(k=2,s=2) + skip add (unet.py:166,190);
+ * inverse != 0 is its adjoint (un-shuffle of src = y into dst = z). */
+int cwfa_channel_dot_workspace_blocks(void);
+int cwfa_channel_dot_stats_f32(const float* x, const float* dy, float* out, float* workspace, int N, int C, int64_t P, void* stream);
+int cwfa_bn_bwd_apply_f32(const float* dy, const float* x, const float* a, const float* b, const float* c0, float* dx,
+                          int N, int C, int64_t P, void* stream);
+int cwfa_maxpool2_bwd_f32(const float* x, const float* dy, float* dx, int N, int C, int H, int W, void* stream);
+int cwfa_pixel_shuffle2_f32(const float* src, const float* skip, float* dst, int N, int C, int H, int W, int inverse, void* stream);
 /* Lion update on a flat fp32 buffer (lion_pytorch 0.0.7, requirements.txt:1; call sites CWFA.py:381,608-610):
  * p *= 1 - lr*wd; p -= lr*sign(beta1*m + (1-beta1)*g); m = beta2*m + (1-beta2)*g, with g read as g*grad_scale. */
 int cwfa_lion_step_f32(float* p, const float* g, float* m, int64_t n, float lr, float beta1, float beta2,

@@ -475,3 +475,13 @@ def lion_step(p: Tensor, g: Tensor, m: Tensor, lr: float, beta1: float = 0.9, be
     p = p - lr * upd
     m = m * beta2 + g * (1.0 - beta2)
     return p, m
+
+
+def lrnn_train_grads(sd: SD, views: Tensor, gt: Tensor, mean_vol: Optional[Tensor] = None, bn_mode: str = "batch"):
+    """The LRNN ("last step") training loss of the reference, ``loss_func_first_step='L2'``: F.mse_loss(curr_gt, LRNN(views))
+    (CWFA.py:882,936-941), differentiated w.r.t. every floating-point entry of the Encoder state_dict (torch CPU autograd)."""
+    p = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and "running" not in k else v) for k, v in sd.items()}
+    loss = F.mse_loss(gt, lrnn(p, views, mean_vol, bn_mode))
+    loss.backward()
+    grads = {k: v.grad for k, v in p.items() if torch.is_tensor(v) and v.requires_grad and v.grad is not None}
+    return dict(loss=loss.detach(), grads=grads)

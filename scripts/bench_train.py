@@ -21,6 +21,7 @@ from cwfa_b200.training import FlowLevelTrainer             # noqa: E402
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--level", type=int, default=0)
+    ap.add_argument("--lrnn", action="store_true", help="time the LRNN ('last step') training step instead of a flow level")
     ap.add_argument("--side", type=int, default=512)
     ap.add_argument("--depths", type=int, default=96)
     ap.add_argument("--batch", type=int, default=1)
@@ -38,13 +39,28 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device(dev))
     n, S, D = a.level, a.side, a.depths
-    model = cwfa_b200.CWFAModel(n_depths=D, volume_side_size=S, INN_max_down_steps=n + 2, seed=0).to(dev)
-    tr = FlowLevelTrainer(model, n, precision=a.precision)
+    steps_total = 5 if a.lrnn else n + 2
+    model = cwfa_b200.CWFAModel(n_depths=D, volume_side_size=S, INN_max_down_steps=steps_total, seed=0).to(dev)
+    if a.lrnn:
+        from cwfa_b200.training import LRNNTrainer
+        lt = LRNNTrainer(model, precision=a.precision)
+    else:
+        tr = FlowLevelTrainer(model, n, precision=a.precision)
     C = D // 2 ** n
     g = torch.Generator(device="cpu").manual_seed(1000 + rank)             # every rank its own frame
     mk = lambda *s, sc=1.0: (torch.randn(*s, generator=g) * sc).to(dev)
     gt, views = mk(a.batch, C, S, S), mk(a.batch, 29, S, S)
     mean_vol, vol_in = mk(a.batch, C // 2, S, S, sc=0.1), mk(a.batch, C // 2, S, S)
+    if a.lrnn:
+        gt_l = mk(a.batch, D // 16, S, S)
+
+        class _T:                                              # same call shape as FlowLevelTrainer for the loops below
+            collectives = 0
+            def step(self, *_):
+                r = lt.step(gt_l, views)
+                self.collectives = lt.collectives
+                return r
+        tr = _T()
     losses = []
     for _ in range(a.warmup):
         losses.append(float(tr.step(gt, views, mean_vol, vol_in)["loss"]))
@@ -65,7 +81,7 @@ def main():
         ms = float(t)
     losses.append(float(parts["loss"]))
     if rank == 0:
-        out = {"metric": "flow-level training steps/s (fwd NLL + inverse MSE + backward + Lion)", "precision": a.precision, "level": n,
+        out = {"metric": "flow-level training steps/s (fwd NLL + inverse MSE + backward + Lion)", "precision": a.precision, "level": "lrnn" if a.lrnn else n,
                "value": world * a.batch * 1000.0 / ms, "unit": "frames/s", "ms_per_step": ms, "n_gpus": world, "batch_per_gpu": a.batch,
                "side": S, "depths": D, "launches_per_step": (_lib.launch_count - l0) / a.steps, "collectives_per_step": tr.collectives,
                "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30, "losses": losses}

@@ -67,6 +67,19 @@ def test_oracle_train_grads_match_reference_autograd(golden_tiny, golden_train, 
         assert t is not None and float(t.abs().max()) == 0.0, k
 
 
+def test_oracle_lrnn_grads_match_reference_autograd(golden_tiny, golden_train):
+    """LRNN step: F.mse_loss(gt, Encoder(views)) through the U-Net (BatchNorm batch statistics, max-pool, transposed conv)."""
+    model = build_tiny_model(golden_tiny).export_for_oracle()
+    cfg, g = golden_train["config"], golden_train["lrnn"]
+    D, S, B, MAX = cfg["D"], cfg["S"], cfg["B"], cfg["MAX"]
+    views = seeded_randn((B, 29, S, S), g["seeds"]["views"])
+    gt = seeded_randn((B, D // 2 ** (MAX - 1), S, S), g["seeds"]["gt"])
+    r = O.lrnn_train_grads(model["lrnn"], views, gt)
+    assert abs(float(r["loss"]) - float(g["loss"])) <= 2e-5 * abs(float(g["loss"]))
+    check_against_golden(r["grads"], g["grads"], 3e-4)
+    assert all(k not in r["grads"] for k in g["no_grad_keys"])          # mean-volume branch: unused without a mean volume
+
+
 def test_flat_group_rehomes_parameters():
     from cwfa_b200.training import FlatGroup
     torch.manual_seed(0)
