@@ -339,7 +339,7 @@ def main():
 
     # ---- BASELINE.json configs[3]: training step of flow level 0 (forward NLL + inverse MSE + backward + Lion), bf16 convs
     train_ms = train_err = None
-    if rank == 0 and not args.no_train:
+    if rank == 0 and world == 1 and not args.no_train:      # single process only: the trainer's gradient all-reduce spans the default group
         try:
             from cwfa_b200.training import FlowLevelTrainer
             g = torch.Generator(device="cpu").manual_seed(11)

@@ -239,24 +239,32 @@ def ood_decision(nll_per_level: Sequence[torch.Tensor], step_LL_to_use: int = 0,
 
 def fine_tune_flow_levels(model, frames: Sequence[dict], levels: Optional[Sequence[int]] = None, epochs_per_step: int = 1,
                           precision: str = "fp32", lr: float = 221e-7, lr_cond: float = 845e-7, weight_decay: float = 1e-2,
-                          cond_weight: float = INN_COND_WEIGHT, group=None):
-    """Coarse-to-fine schedule of the reference's fine-tune loop (CWFA.py:746-771) for the flow levels: the level being
-    optimised moves from the coarsest flow (L-2) to the finest (0); while a level trains, its input volume per frame comes from
-    the cache filled by the level below it (``upsampled_cache``, CWFA.py:748-750,919-920), which starts from the LRNN output.
+                          cond_weight: float = INN_COND_WEIGHT, group=None, lr_first_step: float = 80e-7):
+    """Coarse-to-fine schedule of the reference's fine-tune loop (CWFA.py:746-771): the step being optimised moves from the LRNN
+    (index L-1, when listed in ``levels``) through the coarsest flow (L-2) to the finest (0); while a flow level trains, its input
+    volume per frame comes from the cache filled by the step below it (``upsampled_cache``, CWFA.py:748-750,919-920).
 
     frames: dicts with ``views`` (1,29,S,S), ``gt`` (1,D,S,S) and ``mean_vols`` (list, level n -> (1,C_n/2,S,S); optional last
-    entry = the LRNN's mean volume).  Returns {level: [loss per step]}.  (The LRNN's own training step -- U-Net adjoints -- is
-    not implemented; its weights are used as they are.)"""
+    entry = the LRNN's mean volume).  ``levels`` defaults to the flow levels; add ``L-1`` to also run the LRNN step first.
+    Returns ({step: [loss per optimiser step]}, per-frame cache of the finest reconstruction)."""
     L1 = model.n_levels
     levels = list(range(L1 - 1, -1, -1)) if levels is None else list(levels)
     with torch.no_grad():
-        gt_caches, cache = [], []
+        gt_caches = []
         for f in frames:
             _, gtc, _, _ = model.evaluate_INN_forward(f["gt"], extra_cond_in=f["mean_vols"], fix_empty_depths=False)   # GT pyramid
             gt_caches.append(gtc)
-            mv_last = f["mean_vols"][L1] if len(f["mean_vols"]) > L1 else None
-            cache.append(model.cond_nets[L1](f["views"], mv_last)[-1])                                                  # CWFA.py:882
     history = {}
+    mv_last = lambda f: f["mean_vols"][L1] if len(f["mean_vols"]) > L1 else None
+    if L1 in levels:                                           # the "last step": LRNN on the coarsest ground truth
+        lt = LRNNTrainer(model, lr=lr_first_step, weight_decay=weight_decay, group=group, precision=precision)
+        history[L1] = []
+        for _ in range(epochs_per_step):
+            for i, f in enumerate(frames):
+                history[L1].append(float(lt.step(gt_caches[i][L1], f["views"], mv_last(f))["loss"]))
+        lt.release()
+    with torch.no_grad():
+        cache = [model.cond_nets[L1](f["views"], mv_last(f))[-1] for f in frames]                                        # CWFA.py:882
     for n in range(L1 - 1, -1, -1):
         if n in levels:
             tr = FlowLevelTrainer(model, n, lr=lr, lr_cond=lr_cond, weight_decay=weight_decay, cond_weight=cond_weight,

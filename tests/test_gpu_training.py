@@ -358,8 +358,9 @@ def test_coarse_to_fine_schedule_and_ood_rule(golden_tiny):
         mv = [seeded_randn((1, D // 2 ** (n + 1), S, S), 70 + 10 * i + n, 0.1).to(DEV) for n in range(L - 1)]
         frames.append(dict(views=seeded_randn((1, 29, S, S), 60 + i).to(DEV), gt=seeded_randn((1, D, S, S), 50 + i).to(DEV), mean_vols=mv))
     before = model.reconstruct(frames[0]["views"], frames[0]["mean_vols"]).clone()
-    hist, cache = fine_tune_flow_levels(model, frames, epochs_per_step=2, lr=1e-4, lr_cond=1e-4)
-    assert sorted(hist) == [0, 1] and all(len(v) == 4 for v in hist.values())
+    hist, cache = fine_tune_flow_levels(model, frames, levels=[2, 1, 0], epochs_per_step=2, lr=1e-4, lr_cond=1e-4, lr_first_step=1e-4)
+    assert sorted(hist) == [0, 1, 2] and all(len(v) == 4 for v in hist.values())          # LRNN step first, then the flow levels
+    assert hist[2][-2] < hist[2][0]
     assert all(math.isfinite(x) for v in hist.values() for x in v)
     assert hist[1][-2] < hist[1][0] and hist[0][-2] < hist[0][0]              # same frame, one epoch later
     assert cache[0].shape == (1, D, S, S)
