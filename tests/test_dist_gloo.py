@@ -32,7 +32,7 @@ def _worker(rank, world, port, n_frames, q):
     t = torch.tensor([float(b - a)])
     dist.all_reduce(t)                                    # same reduction bench.py uses for frames processed
     if rank == 0:
-        q.put((full, float(t)))
+        q.put((full.tolist(), float(t)))          # by value: a tensor would travel as a shared-memory fd that dies with this process
     dist.barrier()
     dist.destroy_process_group()
 
@@ -48,7 +48,7 @@ def test_two_rank_gather_matches_single_process(n_frames):
     [p.join(60) for p in procs]
     assert all(p.exitcode == 0 for p in procs)
     ref = torch.stack([torch.tensor([float(f), float(f) ** 2]) for f in range(n_frames)])
-    assert torch.equal(full, ref) and total == n_frames
+    assert torch.equal(torch.tensor(full).reshape(ref.shape), ref) and total == n_frames
 
 
 # ---- training: gradient all-reduce of the flat buffers (cwfa_b200/training.py) -----------------------
@@ -77,7 +77,7 @@ def _train_worker(rank, world, port, q):
     n = allreduce_gradients([opt])
     tot = allreduce_nll_terms(torch.tensor([1.0 + rank, 2.0]), torch.tensor([10.0 * (rank + 1), 1.0]))
     if rank == 0:
-        q.put((n, opt.grad_scale, [g.clone() for g in opt.flat_grads()], [float(t) for t in tot]))
+        q.put((n, opt.grad_scale, [g.tolist() for g in opt.flat_grads()], [float(t) for t in tot]))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -103,5 +103,6 @@ def test_two_rank_gradient_allreduce_matches_single_process():
         for a, g in zip(acc, opt.flat_grads()):
             a += g
     for a, g in zip(acc, flats):
+        g = torch.tensor(g)
         assert torch.allclose(a, g, rtol=1e-6, atol=1e-8) and float(g.abs().sum()) > 0
     assert tot == [3.0 + 4.0, 30.0 + 2.0, 4.0]
