@@ -10,12 +10,13 @@ whenever gradients are enabled and an input requires them, so the FrEIA-style mo
 Covered (everything a flow level and its conditioning net execute): conv2d 1x1/3x3 (+bias, ELU, residual-add,
 PReLU), the affine coupling with log-det, channel / row / column permutations, the depth-wise Haar transform
 (split / merge forms included), per-sample sum of squares, MSE, the conditioning net's depth stencil.
-The LRNN (BatchNorm, max-pool, transposed conv, LayerNorm, GELU, attention gate) has no adjoints yet: those
-ops stay non-differentiable and ``ops`` says so once.
+The LRNN's U-Net is covered too (BatchNorm2d, 2x2 max-pool, ConvTranspose2d(k=2,s=2) + skip add as a 1x1 convolution followed by
+a pixel shuffle).  Its mean-volume branch (7x7 conv, LayerNorm, GELU, attention gate) has no adjoints yet: those ops stay
+non-differentiable and ``ops`` says so once.  ``set_training_precision('bf16'|'fp16')`` moves every convolution of the tape
+(forward, data gradient, weight gradient) onto the tcgen05 kernels.
 """
 from __future__ import annotations
 
-import math
 from typing import Optional
 
 import torch
