@@ -72,6 +72,11 @@ _SIGS = {
     "cwfa_stencil3d_wgrad_workspace_floats": [i32],
     "cwfa_stencil3d_wgrad_f32": [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp],
     "cwfa_lion_step_f32": [vp, vp, vp, i64, f32, f32, f32, f32, f32, vp],
+    "cwfa_act_bwd_f32": [vp, vp, vp, i64, i32, vp],
+    "cwfa_gelu_add_f32": [vp, vp, vp, vp, i64, vp],
+    "cwfa_ln_bwd_stats_f32": [vp, vp, vp, vp, vp, i32, i64, vp],
+    "cwfa_ln_bwd_apply_f32": [vp, vp, vp, vp, vp, vp, vp, i32, i64, vp],
+    "cwfa_gate_f32": [vp, vp, vp, vp, vp, vp, i64, vp],
     "cwfa_channel_dot_workspace_blocks": [],
     "cwfa_channel_dot_stats_f32": [vp, vp, vp, vp, i32, i32, i64, vp],
     "cwfa_bn_bwd_apply_f32": [vp, vp, vp, vp, vp, vp, i32, i32, i64, vp],
@@ -133,7 +138,7 @@ class CwfaError(RuntimeError):
 
 # kernel launches issued per C-ABI call (for bench.py's "gpu_launches" claim)
 _LAUNCHES = {"cwfa_affine": 2, "cwfa_channel_stats_f32": 2, "cwfa_layernorm_chw_f32": 2, "cwfa_c8_channel_stats": 2, "cwfa_c8_layernorm": 2, "cwfa_conv2d_wgrad_f32": 2, "cwfa_wgrad_tc": 2, "cwfa_prelu_bwd_f32": 2, "cwfa_stencil3d_wgrad_f32": 2,
-             "cwfa_reduce_workspace_blocks": 0, "cwfa_channel_dot_workspace_blocks": 0, "cwfa_channel_dot_stats_f32": 2, "cwfa_stencil3d_wgrad_workspace_floats": 0,
+             "cwfa_reduce_workspace_blocks": 0, "cwfa_channel_dot_workspace_blocks": 0, "cwfa_channel_dot_stats_f32": 2, "cwfa_ln_bwd_stats_f32": 2, "cwfa_stencil3d_wgrad_workspace_floats": 0,
              "cwfa_tc_set_debug_buffer": 0, "cwfa_resblock_set_debug_buffer": 0, "cwfa_device_check": 0, "cwfa_conv_tc_coupling_tiles": 0, "cwfa_coupling_tc_tiles": 0}
 launch_count = 0
 launch_hist = {}

@@ -11,8 +11,8 @@ Covered (everything a flow level and its conditioning net execute): conv2d 1x1/3
 PReLU), the affine coupling with log-det, channel / row / column permutations, the depth-wise Haar transform
 (split / merge forms included), per-sample sum of squares, MSE, the conditioning net's depth stencil.
 The LRNN's U-Net is covered too (BatchNorm2d, 2x2 max-pool, ConvTranspose2d(k=2,s=2) + skip add as a 1x1 convolution followed by
-a pixel shuffle).  Its mean-volume branch (7x7 conv, LayerNorm, GELU, attention gate) has no adjoints yet: those ops stay
-non-differentiable and ``ops`` says so once.  ``set_training_precision('bf16'|'fp16')`` moves every convolution of the tape
+a pixel shuffle) and so is its mean-volume branch (7x7 conv, LayerNorm([C,H,W]), GELU + skip, attention gate).  Ops without an
+adjoint (e.g. the fused depth-wise attention kernel, 2-D Haar) stay non-differentiable and ``ops`` says so once.  ``set_training_precision('bf16'|'fp16')`` moves every convolution of the tape
 (forward, data gradient, weight gradient) onto the tcgen05 kernels.
 """
 from __future__ import annotations
@@ -94,16 +94,16 @@ class _Conv2d(_F):
         y = ops.conv2d(xx, ww, bb, act=act, res=rr, res_mode=res_mode)
         ctx.act = act
         ctx.has_res = rr is not None and res_mode == 1
-        ctx.save_for_backward(xx, ww, y if act == ops.ACT_ELU else None)
+        ctx.save_for_backward(xx, ww, y if act != ops.ACT_NONE else None)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, w, y = ctx.saved_tensors
         dv = ops._ck(dy)
-        if ctx.act == ops.ACT_ELU:
+        if ctx.act != ops.ACT_NONE:                     # ELU / ReLU / sigmoid: adjoint from the layer output
             g = torch.empty_like(dv)
-            _lib.call("cwfa_elu_bwd_f32", dv.data_ptr(), y.data_ptr(), g.data_ptr(), dv.numel(), _stream())
+            _lib.call("cwfa_act_bwd_f32", dv.data_ptr(), y.data_ptr(), g.data_ptr(), dv.numel(), int(ctx.act), _stream())
             dv = g
         need_x, need_w, need_b, need_r = ctx.needs_input_grad[:4]
         dx = conv2d_dgrad(dv, w) if need_x else None
@@ -140,10 +140,16 @@ def prelu(v, slope):
     return _PReLU.apply(v, slope)
 
 
+_FROM_OUTPUT = (ops.ACT_NONE, ops.ACT_ELU, ops.ACT_RELU, ops.ACT_SIGMOID)
+
+
 def conv2d_supported(w, act, res, res_mode) -> bool:
     KH, KW = w.shape[2], w.shape[3]
-    return (KH == KW and KH in (1, 3) and act in (ops.ACT_NONE, ops.ACT_ELU, ops.ACT_PRELU)
-            and (res is None or res_mode == 1))
+    if KH != KW or KH not in (1, 3, 7):
+        return False
+    if act == ops.ACT_GELU:                             # ConvNeXt tail: gelu(conv) + skip (networks.py:491-503)
+        return res is None or res_mode == 2
+    return act in _FROM_OUTPUT + (ops.ACT_PRELU,) and (res is None or res_mode == 1)
 
 
 # ---- tensor-core variant: forward and data gradient on the tcgen05 implicit-GEMM kernel (bf16/fp16 operands, fp32
@@ -189,7 +195,7 @@ class _Conv2dTC(_F):
         y = tc.conv_tc(x8, pc, act=act, res=rr, res_mode=res_mode, out_nchw=True)
         ctx.act, ctx.kind = act, kind
         ctx.has_res = rr is not None and res_mode == 1
-        ctx.wgrad_tc = True
+        ctx.wgrad_tc = ww.shape[2] in (1, 3)                             # 7x7: fp32 weight gradient (csrc/backward.cu)
         ctx.Cin = xx.shape[1]
         ctx.save_for_backward(None if ctx.wgrad_tc else xx, ww, y if act == ops.ACT_ELU else None, x8.data if ctx.wgrad_tc else None)
         return y
@@ -219,14 +225,118 @@ class _Conv2dTC(_F):
         return dx, dw, db, dr, None, None, None
 
 
+class _GeluAdd(_F):
+    """y = gelu(v) + r (exact erf GELU + the ConvNeXt skip, networks.py:492,503)."""
+
+    @staticmethod
+    def forward(ctx, v, r):
+        vv = _f32(v)
+        rr = None if r is None else _f32(r)
+        ctx.save_for_backward(vv)
+        y = torch.empty_like(vv)
+        _lib.call("cwfa_gelu_add_f32", vv.data_ptr(), ops._p(rr), None, y.data_ptr(), vv.numel(), _stream())
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (v,) = ctx.saved_tensors
+        dy = ops._ck(dy)
+        dv = torch.empty_like(v)
+        _lib.call("cwfa_gelu_add_f32", v.data_ptr(), None, dy.data_ptr(), dv.data_ptr(), v.numel(), _stream())
+        return dv, (dy if ctx.needs_input_grad[1] else None)
+
+
 def conv2d(x, w, bias=None, *, act=ops.ACT_NONE, slope=None, res=None, res_mode=0):
     rm = res_mode if res is not None else 0
+    if act == ops.ACT_GELU:
+        lin = _Conv2d.apply(x, w, bias, None, ops.ACT_NONE, 0) if _PRECISION == "fp32" else \
+            _Conv2dTC.apply(x, w, bias, None, ops.ACT_NONE, 0, _PRECISION)
+        return _GeluAdd.apply(lin, res)
     a = ops.ACT_NONE if act == ops.ACT_PRELU else act
-    if _PRECISION == "fp32":
+    if _PRECISION == "fp32" or a in (ops.ACT_RELU, ops.ACT_SIGMOID):     # the tiny attention convs stay on the fp32 kernels
         y = _Conv2d.apply(x, w, bias, res, a, rm)
     else:
         y = _Conv2dTC.apply(x, w, bias, res, a, rm, _PRECISION)
     return prelu(y, slope) if act == ops.ACT_PRELU else y
+
+
+def conv1d_flat(x, w, bias, act):
+    """Conv1d over the flattened H*W axis (GlobalAttention, networks.py:250-262) as a convolution on a one-row image; a k = 3
+    kernel is embedded in the middle row of a 3x3 kernel (rows above / below the image are zero padding)."""
+    B, C, L = x.shape
+    k = w.shape[-1]
+    w4 = w.reshape(w.shape[0], w.shape[1], 1, k)
+    if k == 3:
+        w4 = torch.nn.functional.pad(w4, (0, 0, 1, 1))
+    elif k != 1:
+        raise NotImplementedError("conv1d_flat adjoint: kernel sizes 1 and 3")
+    return conv2d(x.reshape(B, C, 1, L), w4, bias, act=act).reshape(B, w.shape[0], L)
+
+
+class _LayerNormCHW(_F):
+    """LayerNorm([C,H,W]) with element-wise affine (networks.py:490)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        xx, gg = _f32(x), _f32(gamma)
+        ctx.eps = float(eps)
+        ctx.save_for_backward(xx, gg)
+        return ops.layernorm_chw(xx, gg, _f32(beta), eps)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma = ctx.saved_tensors
+        dy = ops._ck(dy)
+        B = x.shape[0]
+        n = x[0].numel()
+        dev = x.device
+        s, q = ops.channel_stats(x.reshape(1, B, n)).double()             # per-sample sum, sum of squares
+        mean = s / n
+        rstd = 1.0 / torch.sqrt((q / n - mean * mean).clamp_min(0.0) + ctx.eps)
+        lib = _lib.load()
+        out = torch.empty(2 * B, device=dev, dtype=torch.float32)
+        ws = torch.empty(2 * B * lib.cwfa_channel_dot_workspace_blocks(), device=dev, dtype=torch.float32)
+        _lib.call("cwfa_ln_bwd_stats_f32", x.data_ptr(), dy.data_ptr(), gamma.data_ptr(), out.data_ptr(), ws.data_ptr(), B, n, _stream())
+        sg, sgx = out[:B].double(), out[B:].double()
+        coef = torch.stack([mean, rstd, sg / n, rstd * (sgx - mean * sg) / n], 1).float().contiguous()
+        need_x, need_g, need_b = ctx.needs_input_grad[:3]
+        dx = torch.empty_like(x) if need_x else None
+        dg = torch.empty_like(gamma) if need_g else None
+        db = torch.empty_like(gamma) if need_b else None
+        _lib.call("cwfa_ln_bwd_apply_f32", x.data_ptr(), dy.data_ptr(), gamma.data_ptr(), coef.data_ptr(), ops._p(dx), ops._p(dg), ops._p(db),
+                  B, n, _stream())
+        return dx, dg, db, None
+
+
+def layernorm_chw(x, gamma, beta, eps):
+    return _LayerNormCHW.apply(x, gamma, beta, eps)
+
+
+class _GateAdd(_F):
+    """y = x + m * 2 * (g - 0.5)  (networks.py:554)."""
+
+    @staticmethod
+    def forward(ctx, x, m, g):
+        xx, mm, gg = _f32(x), _f32(m), _f32(g)
+        ctx.save_for_backward(mm, gg)
+        y = torch.empty_like(xx)
+        _lib.call("cwfa_gate_f32", xx.data_ptr(), mm.data_ptr(), gg.data_ptr(), None, y.data_ptr(), None, xx.numel(), _stream())
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        m, g = ctx.saved_tensors
+        dy = ops._ck(dy)
+        need_x, need_m, need_g = ctx.needs_input_grad
+        dm = torch.empty_like(m) if need_m else None
+        dg = torch.empty_like(g) if need_g else None
+        if need_m or need_g:
+            _lib.call("cwfa_gate_f32", None, m.data_ptr(), g.data_ptr(), dy.data_ptr(), ops._p(dm), ops._p(dg), m.numel(), _stream())
+        return (dy if need_x else None), dm, dg
+
+
+def gate_add(x, m, g):
+    return _GateAdd.apply(x, m, g)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -18,37 +18,38 @@ using namespace cwfa;
 // CTA = 32 output channels x 32 input channels; a thread owns a 2x2 channel block x KS*KS taps and
 // walks the 256 pixels of a tile with a sliding register window over x.
 // ------------------------------------------------------------------------------------------
-constexpr int WG_C = 32;            // channel block (both Cout and Cin)
 constexpr int WG_TH = 8, WG_TW = 32;
 constexpr int WG_DPLANE = WG_TH * WG_TW + 1;
 
-template <int KS>
+// CB = channels per thread in each of the two channel axes: 2 (1x1 / 3x3: 2x2xKS^2 accumulators) or 1 (7x7: 49 accumulators)
+template <int KS, int CB>
 struct WgradGeom {
+    static constexpr int C = 16 * CB;                // channel block of the CTA (both Cout and Cin)
     static constexpr int XH = WG_TH + KS - 1, XW = WG_TW + KS - 1;
     static constexpr int XPLANE = (XH * XW) | 1;     // odd plane stride: 16 channels hit 16 banks
-    static constexpr size_t smem = sizeof(float) * (WG_C * XPLANE + WG_C * WG_DPLANE);
+    static constexpr size_t smem = sizeof(float) * (C * XPLANE + C * WG_DPLANE);
 };
 
-template <int KS>
+template <int KS, int CB>
 __global__ void __launch_bounds__(256) conv2d_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                            float* __restrict__ part, int N, int Cin, int H, int W,
                                                            int Cout, int tiles_x, int tiles_y, int n_ci_blk) {
-    using G = WgradGeom<KS>;
-    constexpr int PAD = KS / 2, KK = KS * KS;
+    using G = WgradGeom<KS, CB>;
+    constexpr int PAD = KS / 2, KK = KS * KS, WG_C = G::C;
     extern __shared__ float smem[];
     float* xs = smem;                       // [WG_C][XPLANE]
     float* ds = smem + WG_C * G::XPLANE;    // [WG_C][WG_DPLANE]
     const int tid = threadIdx.x;
-    const int tco = tid >> 4, tci = tid & 15;          // channels tco, tco+16 / tci, tci+16
+    const int tco = tid >> 4, tci = tid & 15;          // channels tco (+16) / tci (+16)
     const int co0 = (blockIdx.y / n_ci_blk) * WG_C, ci0 = (blockIdx.y % n_ci_blk) * WG_C;
     const int tiles = tiles_x * tiles_y;
     const int64_t P = (int64_t)H * W;
 
-    float acc[2][2][KK];
+    float acc[CB][CB][KK];
 #pragma unroll
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < CB; ++i)
 #pragma unroll
-        for (int j = 0; j < 2; ++j)
+        for (int j = 0; j < CB; ++j)
 #pragma unroll
             for (int t = 0; t < KK; ++t) acc[i][j][t] = 0.f;
 
@@ -72,49 +73,51 @@ __global__ void __launch_bounds__(256) conv2d_wgrad_kernel(const float* __restri
             ds[cl * WG_DPLANE + pix] = v;
         }
         __syncthreads();
-        const float* x0 = xs + tci * G::XPLANE;
-        const float* x1 = xs + (tci + 16) * G::XPLANE;
-        const float* d0 = ds + tco * WG_DPLANE;
-        const float* d1 = ds + (tco + 16) * WG_DPLANE;
+        const float* xq[CB];
+        const float* dq[CB];
+#pragma unroll
+        for (int j = 0; j < CB; ++j) {
+            xq[j] = xs + (tci + 16 * j) * G::XPLANE;
+            dq[j] = ds + (tco + 16 * j) * WG_DPLANE;
+        }
         for (int r = 0; r < WG_TH; ++r) {
-            float win[2][KS][KS];
+            float win[CB][KS][KS];
 #pragma unroll
-            for (int kh = 0; kh < KS; ++kh)
-#pragma unroll
-                for (int kw = 0; kw < KS - 1; ++kw) {
-                    win[0][kh][kw + 1] = x0[(r + kh) * G::XW + kw];
-                    win[1][kh][kw + 1] = x1[(r + kh) * G::XW + kw];
-                }
-#pragma unroll
-            for (int c = 0; c < WG_TW; ++c) {
-#pragma unroll
-                for (int kh = 0; kh < KS; ++kh) {
-#pragma unroll
-                    for (int kw = 0; kw < KS - 1; ++kw) {
-                        win[0][kh][kw] = win[0][kh][kw + 1];
-                        win[1][kh][kw] = win[1][kh][kw + 1];
-                    }
-                    win[0][kh][KS - 1] = x0[(r + kh) * G::XW + c + KS - 1];
-                    win[1][kh][KS - 1] = x1[(r + kh) * G::XW + c + KS - 1];
-                }
-                const float g0 = d0[r * WG_TW + c], g1 = d1[r * WG_TW + c];
+            for (int j = 0; j < CB; ++j)
 #pragma unroll
                 for (int kh = 0; kh < KS; ++kh)
 #pragma unroll
-                    for (int kw = 0; kw < KS; ++kw) {
-                        acc[0][0][kh * KS + kw] = fmaf(g0, win[0][kh][kw], acc[0][0][kh * KS + kw]);
-                        acc[0][1][kh * KS + kw] = fmaf(g0, win[1][kh][kw], acc[0][1][kh * KS + kw]);
-                        acc[1][0][kh * KS + kw] = fmaf(g1, win[0][kh][kw], acc[1][0][kh * KS + kw]);
-                        acc[1][1][kh * KS + kw] = fmaf(g1, win[1][kh][kw], acc[1][1][kh * KS + kw]);
+                    for (int kw = 0; kw < KS - 1; ++kw) win[j][kh][kw + 1] = xq[j][(r + kh) * G::XW + kw];
+#pragma unroll
+            for (int c = 0; c < WG_TW; ++c) {
+#pragma unroll
+                for (int j = 0; j < CB; ++j)
+#pragma unroll
+                    for (int kh = 0; kh < KS; ++kh) {
+#pragma unroll
+                        for (int kw = 0; kw < KS - 1; ++kw) win[j][kh][kw] = win[j][kh][kw + 1];
+                        win[j][kh][KS - 1] = xq[j][(r + kh) * G::XW + c + KS - 1];
                     }
+                float g[CB];
+#pragma unroll
+                for (int i = 0; i < CB; ++i) g[i] = dq[i][r * WG_TW + c];
+#pragma unroll
+                for (int kh = 0; kh < KS; ++kh)
+#pragma unroll
+                    for (int kw = 0; kw < KS; ++kw)
+#pragma unroll
+                        for (int i = 0; i < CB; ++i)
+#pragma unroll
+                            for (int j = 0; j < CB; ++j)
+                                acc[i][j][kh * KS + kw] = fmaf(g[i], win[j][kh][kw], acc[i][j][kh * KS + kw]);
             }
         }
     }
     float* dst = part + (int64_t)blockIdx.x * Cout * Cin * KK;
 #pragma unroll
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < CB; ++i)
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
+        for (int j = 0; j < CB; ++j) {
             const int co = co0 + tco + 16 * i, ci = ci0 + tci + 16 * j;
             if (co < Cout && ci < Cin) {
 #pragma unroll
@@ -133,9 +136,10 @@ __global__ void __launch_bounds__(256) partial_sum_kernel(const float* __restric
     out[i] = accumulate ? out[i] + (float)s : (float)s;
 }
 
-static int wgrad_chunks(int N, int H, int W, int Cout, int Cin) {
+static int wgrad_chunks(int N, int H, int W, int Cout, int Cin, int KS) {
+    const int cblk = KS == 7 ? 16 : 32;
     const int tiles = ceil_div(W, WG_TW) * ceil_div(H, WG_TH);
-    const int combos = ceil_div(Cout, WG_C) * ceil_div(Cin, WG_C);
+    const int combos = ceil_div(Cout, cblk) * ceil_div(Cin, cblk);
     int chunks = (kNumSMs * 4) / combos;
     if (chunks < 1) chunks = 1;
     const int64_t items = (int64_t)N * tiles;
@@ -144,29 +148,32 @@ static int wgrad_chunks(int N, int H, int W, int Cout, int Cin) {
 }
 
 extern "C" int64_t cwfa_conv2d_wgrad_workspace_floats(int N, int Cin, int H, int W, int Cout, int KH, int KW) {
-    return (int64_t)wgrad_chunks(N, H, W, Cout, Cin) * Cout * Cin * KH * KW;
+    return (int64_t)wgrad_chunks(N, H, W, Cout, Cin, KH) * Cout * Cin * KH * KW;
+}
+
+template <int KS, int CB>
+static void wgrad_launch(dim3 grid, cudaStream_t st, const float* x, const float* dy, float* ws, int N, int Cin, int H, int W, int Cout,
+                         int tiles_x, int tiles_y, int n_ci) {
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(conv2d_wgrad_kernel<KS, CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WgradGeom<KS, CB>::smem); attr = true; }
+    conv2d_wgrad_kernel<KS, CB><<<grid, 256, WgradGeom<KS, CB>::smem, st>>>(x, dy, ws, N, Cin, H, W, Cout, tiles_x, tiles_y, n_ci);
 }
 
 extern "C" int cwfa_conv2d_wgrad_f32(const float* x, const float* dy, float* dw, float* workspace, int N, int Cin, int H,
                                      int W, int Cout, int KH, int KW, int accumulate, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
-    if (N <= 0 || Cin <= 0 || Cout <= 0 || H <= 0 || W <= 0 || KH != KW || (KH != 1 && KH != 3)) {
-        set_error("conv2d_wgrad: unsupported shape (square kernels of size 1 or 3, got %dx%d)", KH, KW);
+    if (N <= 0 || Cin <= 0 || Cout <= 0 || H <= 0 || W <= 0 || KH != KW || (KH != 1 && KH != 3 && KH != 7)) {
+        set_error("conv2d_wgrad: unsupported shape (square kernels of size 1, 3 or 7, got %dx%d)", KH, KW);
         return CWFA_EINVAL;
     }
+    const int cblk = KH == 7 ? 16 : 32;
     const int tiles_x = ceil_div(W, WG_TW), tiles_y = ceil_div(H, WG_TH);
-    const int n_ci = ceil_div(Cin, WG_C), n_co = ceil_div(Cout, WG_C);
-    const int chunks = wgrad_chunks(N, H, W, Cout, Cin);
+    const int n_ci = ceil_div(Cin, cblk), n_co = ceil_div(Cout, cblk);
+    const int chunks = wgrad_chunks(N, H, W, Cout, Cin, KH);
     dim3 grid(chunks, n_co * n_ci);
-    if (KH == 3) {
-        static bool attr = false;
-        if (!attr) { cudaFuncSetAttribute(conv2d_wgrad_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WgradGeom<3>::smem); attr = true; }
-        conv2d_wgrad_kernel<3><<<grid, 256, WgradGeom<3>::smem, st>>>(x, dy, workspace, N, Cin, H, W, Cout, tiles_x, tiles_y, n_ci);
-    } else {
-        static bool attr = false;
-        if (!attr) { cudaFuncSetAttribute(conv2d_wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WgradGeom<1>::smem); attr = true; }
-        conv2d_wgrad_kernel<1><<<grid, 256, WgradGeom<1>::smem, st>>>(x, dy, workspace, N, Cin, H, W, Cout, tiles_x, tiles_y, n_ci);
-    }
+    if (KH == 3) wgrad_launch<3, 2>(grid, st, x, dy, workspace, N, Cin, H, W, Cout, tiles_x, tiles_y, n_ci);
+    else if (KH == 1) wgrad_launch<1, 2>(grid, st, x, dy, workspace, N, Cin, H, W, Cout, tiles_x, tiles_y, n_ci);
+    else wgrad_launch<7, 1>(grid, st, x, dy, workspace, N, Cin, H, W, Cout, tiles_x, tiles_y, n_ci);
     int rc = check_launch("conv2d_wgrad");
     if (rc) return rc;
     const int64_t n = (int64_t)Cout * Cin * KH * KW;
@@ -688,4 +695,121 @@ extern "C" int cwfa_pixel_shuffle2_f32(const float* src, const float* skip, floa
     dim3 grid(ceil_div(W, 256), rows < 65535 ? (int)rows : 65535);
     pixel_shuffle2_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, skip, dst, (int64_t)N * C, H, W, inverse);
     return check_launch("pixel_shuffle2");
+}
+
+// ------------------------------------------------------------------------------------------
+// LRNN mean-volume branch adjoints (networks.py:244-262, 486-503, 554): activation adjoints from the layer OUTPUT,
+// GELU + skip, LayerNorm([C,H,W]) with element-wise affine, attention gate
+// ------------------------------------------------------------------------------------------
+// kind: CWFA_ACT_ELU dv = dy*(y>0 ? 1 : y+1); CWFA_ACT_RELU dv = y>0 ? dy : 0; CWFA_ACT_SIGMOID dv = dy*y*(1-y)
+__global__ void __launch_bounds__(256) act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y,
+                                                      float* __restrict__ dv, int64_t n, int kind) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float yy = __ldg(y + i), g = __ldg(dy + i);
+        float d;
+        if (kind == CWFA_ACT_ELU) d = yy > 0.f ? 1.f : yy + 1.f;
+        else if (kind == CWFA_ACT_RELU) d = yy > 0.f ? 1.f : 0.f;
+        else d = yy * (1.f - yy);
+        dv[i] = g * d;
+    }
+}
+extern "C" int cwfa_act_bwd_f32(const float* dy, const float* y, float* dv, int64_t n, int kind, void* stream) {
+    if (n <= 0 || (kind != CWFA_ACT_ELU && kind != CWFA_ACT_RELU && kind != CWFA_ACT_SIGMOID)) { set_error("act_bwd: bad args"); return CWFA_EINVAL; }
+    act_bwd_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(dy, y, dv, n, kind);
+    return check_launch("act_bwd");
+}
+
+// forward: y = gelu(v) + r (exact erf GELU, networks.py:492,503); backward (dy != NULL): dv = dy * (Phi(v) + v phi(v))
+__global__ void __launch_bounds__(256) gelu_add_kernel(const float* __restrict__ v, const float* __restrict__ r,
+                                                       const float* __restrict__ dy, float* __restrict__ out, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float x = v[i];
+        const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752440f));
+        if (dy) out[i] = dy[i] * (cdf + x * 0.39894228040143267794f * expf(-0.5f * x * x));
+        else out[i] = x * cdf + (r ? r[i] : 0.f);
+    }
+}
+extern "C" int cwfa_gelu_add_f32(const float* v, const float* r, const float* dy, float* out, int64_t n, void* stream) {
+    if (n <= 0 || !v || !out) { set_error("gelu_add: bad args"); return CWFA_EINVAL; }
+    gelu_add_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(v, r, dy, out, n);
+    return check_launch("gelu_add");
+}
+
+// LayerNorm adjoint, stage 1: per sample (sum g, sum g*x) with g = dy*gamma (two-stage, kDotBlocks blocks per sample)
+__global__ void __launch_bounds__(256) ln_bwd_stats_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                           const float* __restrict__ gamma, float* __restrict__ ws, int64_t n) {
+    const int b = blockIdx.y;
+    const float* xp = x + (int64_t)b * n;
+    const float* gp = dy + (int64_t)b * n;
+    float s = 0.f, q = 0.f;
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+        const float g = gp[p] * __ldg(gamma + p);
+        s += g;
+        q = fmaf(g, xp[p], q);
+    }
+    block_sum2(s, q);
+    if (threadIdx.x == 0) {
+        ws[((int64_t)b * gridDim.x + blockIdx.x) * 2 + 0] = s;
+        ws[((int64_t)b * gridDim.x + blockIdx.x) * 2 + 1] = q;
+    }
+}
+extern "C" int cwfa_ln_bwd_stats_f32(const float* x, const float* dy, const float* gamma, float* out, float* workspace, int B,
+                                     int64_t n, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (B <= 0 || B > 65535 || n <= 0) { set_error("ln_bwd_stats: bad shape"); return CWFA_EINVAL; }
+    ln_bwd_stats_kernel<<<dim3(kDotBlocks, B), 256, 0, st>>>(x, dy, gamma, workspace, n);
+    int rc = check_launch("ln_bwd_stats");
+    if (rc) return rc;
+    channel_dot_finalize_kernel<<<ceil_div(B, 128), 128, 0, st>>>(workspace, out, B, kDotBlocks);     // out[b] = sum g, out[B+b] = sum g*x
+    return check_launch("ln_bwd_stats_finalize");
+}
+// stage 2: coef[b] = (mean, rstd, mean(g), mean(g*xhat));  dx = rstd*(gamma*dy - mean(g) - xhat*mean(g*xhat));
+// dgamma[p] = sum_b dy*xhat, dbeta[p] = sum_b dy  (a thread owns one element position p and walks the batch)
+__global__ void __launch_bounds__(256) ln_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                           const float* __restrict__ gamma, const float* __restrict__ coef,
+                                                           float* __restrict__ dx, float* __restrict__ dgamma,
+                                                           float* __restrict__ dbeta, int B, int64_t n) {
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+        const float gm = __ldg(gamma + p);
+        float dg = 0.f, db = 0.f;
+        for (int b = 0; b < B; ++b) {
+            const float mean = __ldg(coef + 4 * b), rstd = __ldg(coef + 4 * b + 1), mg = __ldg(coef + 4 * b + 2), mgx = __ldg(coef + 4 * b + 3);
+            const float g = dy[(int64_t)b * n + p];
+            const float xh = (x[(int64_t)b * n + p] - mean) * rstd;
+            if (dx) dx[(int64_t)b * n + p] = rstd * (gm * g - mg - xh * mgx);
+            dg = fmaf(g, xh, dg);
+            db += g;
+        }
+        if (dgamma) dgamma[p] = dg;
+        if (dbeta) dbeta[p] = db;
+    }
+}
+extern "C" int cwfa_ln_bwd_apply_f32(const float* x, const float* dy, const float* gamma, const float* coef, float* dx,
+                                     float* dgamma, float* dbeta, int B, int64_t n, void* stream) {
+    if (B <= 0 || n <= 0) { set_error("ln_bwd_apply: bad shape"); return CWFA_EINVAL; }
+    ln_bwd_apply_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(x, dy, gamma, coef, dx, dgamma, dbeta, B, n);
+    return check_launch("ln_bwd_apply");
+}
+
+// attention gate y = x + m*2*(g-0.5) (networks.py:554): forward when dy == NULL (out0 = y), else the adjoint
+// out0 = dm = dy*2*(g-0.5), out1 = dg = dy*2*m   (dx = dy needs no kernel)
+__global__ void __launch_bounds__(256) gate_kernel(const float* __restrict__ x, const float* __restrict__ m,
+                                                   const float* __restrict__ g, const float* __restrict__ dy,
+                                                   float* __restrict__ out0, float* __restrict__ out1, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float gg = 2.f * (g[i] - 0.5f);
+        if (dy) {
+            const float d = dy[i];
+            if (out0) out0[i] = d * gg;
+            if (out1) out1[i] = d * 2.f * m[i];
+        } else {
+            out0[i] = fmaf(m[i], gg, x[i]);
+        }
+    }
+}
+extern "C" int cwfa_gate_f32(const float* x, const float* m, const float* g, const float* dy, float* out0, float* out1, int64_t n,
+                             void* stream) {
+    if (n <= 0 || !m || !g || (!dy && (!x || !out0))) { set_error("gate: bad args"); return CWFA_EINVAL; }
+    gate_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(x, m, g, dy, out0, out1, n);
+    return check_launch("gate");
 }

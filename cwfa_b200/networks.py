@@ -285,7 +285,10 @@ class LRNN(nn.Module):
         x = self.deconv[1](_conv(self.deconv[0], x_in))
         if mean_vol is not None:
             mean_processed = self.conv3d[1](self.conv3d[0](mean_vol))
-            if mean_vol.shape[1] <= 16:
+            if torch.is_grad_enabled() and (mean_processed.requires_grad or self.attention_3d.m[0].weight.requires_grad):
+                from . import autograd as ag          # training: differentiable gate, attention through the conv kernels
+                x = ag.gate_add(x, mean_processed, self.attention_3d(mean_vol))
+            elif mean_vol.shape[1] <= 16:
                 x = ops.attention_gate_(x, mean_processed, mean_vol, self.attention_3d)   # x += m*2*(attn-0.5), :554
             else:
                 x = ops.gate_add_(x, mean_processed, self.attention_3d(mean_vol))

@@ -227,6 +227,9 @@ def conv2d(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
 
 def conv1d_flat(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], act: int) -> torch.Tensor:
     """Conv1d over the flattened H*W axis (GlobalAttention, networks.py:250-262): (B,C,L)."""
+    if _grad_on(x, w, bias):
+        from . import autograd as ag
+        return ag.conv1d_flat(x, w, bias, act)
     B, C, L = x.shape
     k = w.shape[-1]
     y = conv2d(x.reshape(B, C, 1, L), w.reshape(w.shape[0], w.shape[1], 1, k), bias, act=act)
@@ -324,6 +327,9 @@ def maxpool2(x: torch.Tensor) -> torch.Tensor:
 
 
 def layernorm_chw(x: torch.Tensor, gamma, beta, eps: float = 1e-5) -> torch.Tensor:
+    if _grad_on(x, gamma, beta):
+        from . import autograd as ag
+        return ag.layernorm_chw(x, gamma, beta, eps)
     x = _ck(x, "x")
     N = x.shape[0]
     n = x[0].numel()

@@ -287,8 +287,8 @@ def fine_tune_flow_levels(model, frames: Sequence[dict], levels: Optional[Sequen
 # ---------------------------------------------------------------------------------------------
 def lrnn_loss(model, gt: torch.Tensor, views: torch.Tensor, mean_vol: Optional[torch.Tensor] = None):
     """``F.mse_loss(curr_gt, cond_nets[-1](views, mean_vol)[-1])`` (``loss_func_first_step='L2'``).  gt: (B, D/2^(L-1), S, S).
-    Differentiable through the U-Net (conv / PReLU / BatchNorm / max-pool / transposed conv adjoint kernels); the mean-volume
-    branch (ConvNeXt 7x7 + LayerNorm + GELU, attention gate) has no adjoints yet and is treated as a constant."""
+    Differentiable through the U-Net (conv / PReLU / BatchNorm / max-pool / transposed conv adjoint kernels) and, when a mean
+    volume is given, through the ConvNeXt branch and the attention gate (networks.py:548-555)."""
     from . import autograd as ag
     vol = model.cond_nets[-1](views, mean_vol)[-1]
     return ag.mse_loss(gt, vol), vol

@@ -222,8 +222,8 @@ int cwfa_c8_to_nchw(const void* x, float* y, int N, int C, int Cp, int64_t P, in
  * the MSE term, forward pass for the NLL term, backward, Lion step).  These are the hand-written adjoints of the forward
  * kernels above; cwfa_b200/autograd.py is the only caller. */
 /* conv2d weight gradient dW[co,ci,kh,kw] = sum_{n,h,w} dy[n,co,h,w] * x[n,ci,h+kh-p,w+kw-p] of the stride-1 'same' convs
- * (square kernels 1x1 / 3x3: every conv of the coupling sub-networks networks.py:611-638 and of the conditioning net's
- * 2-D part :211-219).  Deterministic two-stage sum; workspace >= cwfa_conv2d_wgrad_workspace_floats(...) floats.
+ * (square kernels 1x1 / 3x3 / 7x7: every conv of the coupling sub-networks networks.py:611-638, of the conditioning net's
+ * 2-D part :211-219 and the ConvNeXt 7x7 of the LRNN :489).  Deterministic two-stage sum; workspace >= cwfa_conv2d_wgrad_workspace_floats(...) floats.
  * accumulate != 0: dw += result.  The DATA gradient is cwfa_conv2d_f32(dy, wt) with wt from cwfa_conv2d_dgrad_weights_f32
  * (wt[ci,co,kh,kw] = w[co,ci,KH-1-kh,KW-1-kw]); the bias gradient is cwfa_channel_stats_f32(dy). */
 int64_t cwfa_conv2d_wgrad_workspace_floats(int N, int Cin, int H, int W, int Cout, int KH, int KW);
@@ -278,6 +278,18 @@ int cwfa_bn_bwd_apply_f32(const float* dy, const float* x, const float* a, const
                           int N, int C, int64_t P, void* stream);
 int cwfa_maxpool2_bwd_f32(const float* x, const float* dy, float* dx, int N, int C, int H, int W, void* stream);
 int cwfa_pixel_shuffle2_f32(const float* src, const float* skip, float* dst, int N, int C, int H, int W, int inverse, void* stream);
+/* LRNN mean-volume branch adjoints (networks.py:244-262, 486-503, 554).  act_bwd: adjoint of ELU / ReLU / sigmoid from the layer
+ * OUTPUT (kind = CWFA_ACT_*).  gelu_add: dy == NULL: out = gelu(v) + r (r may be NULL); else out = dy * gelu'(v).
+ * ln_bwd_stats: out[b] = sum dy*gamma, out[B+b] = sum dy*gamma*x over the n = C*H*W elements of sample b
+ * (workspace >= 2*B*cwfa_channel_dot_workspace_blocks() floats); ln_bwd_apply: coef = B x (mean, rstd, mean g, mean g*xhat):
+ * dx = rstd*(gamma*dy - mean g - xhat*mean(g xhat)), dgamma[p] = sum_b dy*xhat, dbeta[p] = sum_b dy (each output may be NULL).
+ * gate: dy == NULL: out0 = x + m*2*(g-0.5); else out0 = dy*2*(g-0.5) (= dm), out1 = dy*2*m (= dg). */
+int cwfa_act_bwd_f32(const float* dy, const float* y, float* dv, int64_t n, int kind, void* stream);
+int cwfa_gelu_add_f32(const float* v, const float* r, const float* dy, float* out, int64_t n, void* stream);
+int cwfa_ln_bwd_stats_f32(const float* x, const float* dy, const float* gamma, float* out, float* workspace, int B, int64_t n, void* stream);
+int cwfa_ln_bwd_apply_f32(const float* x, const float* dy, const float* gamma, const float* coef, float* dx, float* dgamma,
+                          float* dbeta, int B, int64_t n, void* stream);
+int cwfa_gate_f32(const float* x, const float* m, const float* g, const float* dy, float* out0, float* out1, int64_t n, void* stream);
 /* Lion update on a flat fp32 buffer (lion_pytorch 0.0.7, requirements.txt:1; call sites CWFA.py:381,608-610):
  * p *= 1 - lr*wd; p -= lr*sign(beta1*m + (1-beta1)*g); m = beta2*m + (1-beta2)*g, with g read as g*grad_scale. */
 int cwfa_lion_step_f32(float* p, const float* g, float* m, int64_t n, float lr, float beta1, float beta2,

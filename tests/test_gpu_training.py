@@ -526,3 +526,85 @@ def test_lrnn_trainer_reduces_loss(golden_tiny, golden_train):
     losses = [float(tr.step(gt, views)["loss"]) for _ in range(4)]
     print("LRNN losses", losses)
     assert losses[-1] < losses[0]
+
+
+# ---------------------------------------------------------------------------------------------
+# LRNN mean-volume branch: ConvNeXt (7x7 conv, LayerNorm([C,H,W]), GELU + skip) and the attention gate
+# ---------------------------------------------------------------------------------------------
+def test_mean_volume_branch_ops_adjoints():
+    from cwfa_b200 import ops, autograd as ag
+    # 7x7 convolution (fp32 weight gradient kernel, 16x16 channel blocks), ragged channels / tiles
+    for (N, Cin, Cout, H, W) in ((1, 20, 18, 13, 37), (2, 6, 64, 16, 32)):
+        x, w, b = seeded_randn((N, Cin, H, W), 1), seeded_randn((Cout, Cin, 7, 7), 2, 0.05), seeded_randn((Cout,), 3)
+        gy = seeded_randn((N, Cout, H, W), 4)
+        cl = [leaf(t) for t in (x, w, b)]
+        F.conv2d(cl[0], cl[1], cl[2], padding=3).backward(gy)
+        gl = [leaf(t, DEV) for t in (x, w, b)]
+        ops.conv2d(*gl).backward(gy.to(DEV))
+        for a_, c_ in zip(gl, cl):
+            assert rel_l2(a_.grad, c_.grad) < TOL
+    # gelu(conv1x1) + skip
+    N, C, H, W = 2, 7, 9, 20
+    x, w, b, r = seeded_randn((N, C, H, W), 5), seeded_randn((C, C, 1, 1), 6, 0.5), seeded_randn((C,), 7), seeded_randn((N, C, H, W), 8)
+    gy = seeded_randn((N, C, H, W), 9)
+    cl = [leaf(t) for t in (x, w, b, r)]
+    yc = F.gelu(F.conv2d(cl[0], cl[1], cl[2])) + cl[3]
+    yc.backward(gy)
+    gl = [leaf(t, DEV) for t in (x, w, b, r)]
+    yg = ops.conv2d(gl[0], gl[1], gl[2], act=ops.ACT_GELU, res=gl[3], res_mode=2)
+    assert rel_l2(yg, yc) < 1e-5
+    yg.backward(gy.to(DEV))
+    for a_, c_ in zip(gl, cl):
+        assert rel_l2(a_.grad, c_.grad) < TOL
+    # LayerNorm([C,H,W]) with element-wise affine
+    gam, bet = seeded_randn((C, H, W), 10) * 0.3 + 1.0, seeded_randn((C, H, W), 11)
+    cl = [leaf(t) for t in (x * 1.5 + 0.3, gam, bet)]
+    F.layer_norm(cl[0], (C, H, W), cl[1], cl[2], 1e-5).backward(gy)
+    gl = [leaf(t, DEV) for t in (x * 1.5 + 0.3, gam, bet)]
+    ops.layernorm_chw(gl[0], gl[1], gl[2], 1e-5).backward(gy.to(DEV))
+    for a_, c_ in zip(gl, cl):
+        assert rel_l2(a_.grad, c_.grad) < TOL
+    # Conv1d over the flattened H*W axis with ReLU / sigmoid, then the gate
+    L = H * W
+    f = seeded_randn((N, C, L), 12)
+    w3, b3, w1, b1 = seeded_randn((C, C, 3), 13, 0.4), seeded_randn((C,), 14), seeded_randn((C, C, 1), 15, 0.4), seeded_randn((C,), 16)
+    xx, mm = seeded_randn((N, C, L), 17), seeded_randn((N, C, L), 18)
+    gz = seeded_randn((N, C, L), 19)
+    cl = [leaf(t) for t in (w3, b3, w1, b1, xx, mm)]
+    gc = torch.sigmoid(F.conv1d(F.relu(F.conv1d(f, cl[0], cl[1], padding=1)), cl[2], cl[3]))
+    (cl[4] + cl[5] * 2 * (gc - 0.5)).backward(gz)
+    gl = [leaf(t, DEV) for t in (w3, b3, w1, b1, xx, mm)]
+    gg = ops.conv1d_flat(ops.conv1d_flat(f.to(DEV), gl[0], gl[1], ops.ACT_RELU), gl[2], gl[3], ops.ACT_SIGMOID)
+    assert rel_l2(gg, gc) < 1e-5
+    ag.gate_add(gl[4], gl[5], gg).backward(gz.to(DEV))
+    for a_, c_ in zip(gl, cl):
+        assert rel_l2(a_.grad, c_.grad) < TOL
+
+
+def test_lrnn_step_with_mean_volume_vs_oracle_and_reference(golden_tiny, golden_train):
+    """fp32 LRNN step incl. the mean-volume branch: every one of the 79 parameters gets its gradient; reference = the float64
+    oracle (conditioning of the U-Net part: see the test above) and the reference's own autograd (golden)."""
+    from cwfa_b200.training import lrnn_loss
+    cfg, g = golden_train["config"], golden_train["lrnn_mv"]
+    D, S, B, MAX = cfg["D"], cfg["S"], cfg["B"], cfg["MAX"]
+    nd = D // 2 ** (MAX - 1)
+    views, gt = seeded_randn((B, 29, S, S), g["seeds"]["views"]), seeded_randn((B, nd, S, S), g["seeds"]["gt"])
+    mv = seeded_randn((B, nd, S, S), g["seeds"]["mean_vol"], 0.1)
+    om = build_tiny_model(golden_tiny).export_for_oracle()
+    model = build_tiny_model(golden_tiny, DEV)
+    for p in model.parameters():
+        p.grad = None
+    loss, _ = lrnn_loss(model, gt.to(DEV), views.to(DEV), mv.to(DEV))
+    loss.backward()
+    ours = {k: p.grad for k, p in model.cond_nets[-1].named_parameters() if p.grad is not None}
+    sd64 = {k: (v.double() if v.dtype.is_floating_point else v) for k, v in om["lrnn"].items()}
+    r = O.lrnn_train_grads(sd64, views.double(), gt.double(), mv.double())
+    assert set(ours) == set(r["grads"]) == set(g["grads"])
+    branch = {k: rel_l2(v, r["grads"][k]) for k, v in ours.items() if "conv3d" in k or "attention" in k}
+    kb = max(branch, key=branch.get)
+    unet = {k: rel_l2(v, r["grads"][k]) for k, v in ours.items() if k not in branch}
+    ku = max(unet, key=unet.get)
+    print(f"LRNN + mean volume: loss {float(loss):.6f} (reference {float(g['loss']):.6f}); mean-volume branch worst {branch[kb]:.2e} at {kb}; U-Net worst {unet[ku]:.2e} at {ku}")
+    assert abs(float(loss) - float(g["loss"])) < 1e-4 * abs(float(g["loss"]))
+    assert branch[kb] < 2e-3 and unet[ku] < 5e-2
+    check_against_golden({k: v.cpu() for k, v in ours.items()}, g["grads"], 5e-2)

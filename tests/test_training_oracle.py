@@ -80,6 +80,20 @@ def test_oracle_lrnn_grads_match_reference_autograd(golden_tiny, golden_train):
     assert all(k not in r["grads"] for k in g["no_grad_keys"])          # mean-volume branch: unused without a mean volume
 
 
+def test_oracle_lrnn_grads_with_mean_volume_branch(golden_tiny, golden_train):
+    """LRNN step incl. the mean-volume branch (ConvNeXt 7x7 + LayerNorm + GELU, attention gate): all 79 parameters get gradients."""
+    model = build_tiny_model(golden_tiny).export_for_oracle()
+    cfg, g = golden_train["config"], golden_train["lrnn_mv"]
+    D, S, B, MAX = cfg["D"], cfg["S"], cfg["B"], cfg["MAX"]
+    nd = D // 2 ** (MAX - 1)
+    views, gt = seeded_randn((B, 29, S, S), g["seeds"]["views"]), seeded_randn((B, nd, S, S), g["seeds"]["gt"])
+    mv = seeded_randn((B, nd, S, S), g["seeds"]["mean_vol"], 0.1)
+    r = O.lrnn_train_grads(model["lrnn"], views, gt, mv)
+    assert abs(float(r["loss"]) - float(g["loss"])) <= 2e-5 * abs(float(g["loss"]))
+    assert set(r["grads"]) == set(g["grads"]) and not g["no_grad_keys"]
+    check_against_golden(r["grads"], g["grads"], 3e-4)
+
+
 def test_flat_group_rehomes_parameters():
     from cwfa_b200.training import FlatGroup
     torch.manual_seed(0)
