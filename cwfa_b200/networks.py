@@ -369,6 +369,19 @@ def conditional_wavelet_flow(input_volume_shape, condition_shape, st_subnet, con
     return cond_net, subnetworks
 
 
+def reset_ActNorm(network, n_to_reset=50):
+    """Re-arms the data-dependent initialisation of the first ``n_to_reset`` ActNorm layers of an INN (networks.py:137-151; call site
+    CWFA.py:537).  Returns (network, number of layers reset)."""
+    n = 0
+    for m in next(network.named_children())[1]:
+        if isinstance(m, Fm.ActNorm):
+            m.init_on_next_batch = True
+            n += 1
+            if n_to_reset and n >= n_to_reset:
+                break
+    return network, n
+
+
 def level_spec(inn: "Ff.GraphINN") -> dict:
     """Node sequence of the flow branch of a level (what ``state_dict`` does not carry):
     used by the fused engine and by the parity tests to drive the oracle."""
