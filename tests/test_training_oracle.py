@@ -121,3 +121,32 @@ def test_oracle_lion_matches_published_update():
     u = torch.sign(0.9 * m + 0.1 * g)                     # [-1, +1, 0, +1]
     assert torch.equal(u, torch.tensor([-1.0, 1.0, 0.0, 1.0]))
     assert torch.allclose(p2, p * (1 - 0.1 * 0.01) - 0.1 * u) and torch.allclose(m2, 0.99 * m + 0.01 * g)
+
+
+def test_banded_depth_stencil_weights_equal_the_conv3d():
+    """The depth-banded 2-D form of the conditioning net's Conv3d pair (cwfa_b200/autograd.py:depth_stencil3d_banded, also the
+    inference engine's formulation) reproduces conv3d -> prelu -> conv3d of the reference (networks.py:221-225,236-241) on CPU."""
+    import torch.nn.functional as F
+    from cwfa_b200 import autograd as ag
+    D, Cm, H, W = 6, 5, 7, 9
+    x = seeded_randn((2, D, H, W), 1)
+    w1, b1 = seeded_randn((Cm, 1, 3, 3, 3), 2, 0.3), seeded_randn((Cm,), 3)
+    w2, b2 = seeded_randn((1, Cm, 3, 3, 3), 4, 0.3), seeded_randn((1,), 5)
+    a = torch.tensor([0.2])
+    v = x.permute(0, 2, 3, 1).unsqueeze(1)
+    ref = F.conv3d(F.prelu(F.conv3d(v, w1, b1, padding=1), a), w2, b2, padding=1)[:, 0].permute(0, 3, 1, 2)
+    kd, mask = ag._band_index(D, "cpu")
+    g1 = w1[:, 0].index_select(3, kd).reshape(Cm, 3, 3, D, D) * mask
+    g2 = w2[0].index_select(3, kd).reshape(Cm, 3, 3, D, D) * mask
+    W1 = g1.permute(3, 0, 4, 1, 2).reshape(D * Cm, D, 3, 3)
+    W2 = g2.permute(3, 4, 0, 1, 2).reshape(D, D * Cm, 3, 3)
+    hid = F.prelu(F.conv2d(x, W1, b1.repeat(D), padding=1), a)
+    out = F.conv2d(hid, W2, b2.expand(D), padding=1)
+    assert float((out - ref).abs().max()) < 1e-5
+
+
+def test_ood_rule():
+    from cwfa_b200.training import ood_decision
+    nll = [torch.tensor([1.0, 1.5, -2.0]), torch.tensor([0.0, 9.0, 9.0])]
+    assert ood_decision(nll, 0, -1.33).tolist() == [False, True, False]       # LL = -NLL below the threshold -> out of distribution
+    assert ood_decision(nll, 1, -1.33).tolist() == [False, True, True]
