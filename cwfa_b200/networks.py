@@ -4,8 +4,9 @@
 The ``nn.Conv2d`` / ``nn.BatchNorm2d`` / ... children below are PARAMETER HOLDERS only (same
 key names, shapes and default initialisation as the reference); their own ``forward`` is
 never called.  Every ``forward`` here launches this repo's CUDA kernels through ``ops``
-(reference precision fp32) or, for the wide convolutions when ``cwfa_b200.set_precision`` is
-'bf16'/'fp16', the tcgen05 implicit-GEMM path in ``tc``.
+(reference precision fp32).  With gradients enabled the same calls go on torch's autograd tape
+(``cwfa_b200.autograd``: forward and adjoint kernels, optionally on the tcgen05 convolution kernels via
+``autograd.set_training_precision('bf16'|'fp16')``); the throughput path for inference is ``cwfa_b200.engine``.
 
 Inference semantics: stochastic regularisers are identity (Dropout3d of the conditioning net
 in eval mode, networks.py:224; the U-Net's always-on ``F.dropout2d(p=0.005)``, unet.py:80,86;
