@@ -72,6 +72,7 @@ _SIGS = {
     "cwfa_stencil3d_wgrad_workspace_floats": [i32],
     "cwfa_stencil3d_wgrad_f32": [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp],
     "cwfa_lion_step_f32": [vp, vp, vp, i64, f32, f32, f32, f32, f32, vp],
+    "cwfa_lion_step_masked_f32": [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, vp],
     "cwfa_act_bwd_f32": [vp, vp, vp, i64, i32, vp],
     "cwfa_gelu_add_f32": [vp, vp, vp, vp, i64, vp],
     "cwfa_ln_bwd_stats_f32": [vp, vp, vp, vp, vp, i32, i64, vp],

@@ -544,8 +544,10 @@ extern "C" int cwfa_stencil3d_wgrad_f32(const float* single, const float* multi,
 //   p *= 1 - lr*wd ; p -= lr * sign(b1*m + (1-b1)*g) ; m = b2*m + (1-b2)*g      (g pre-scaled by gscale)
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) lion_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                                                   int64_t n, float lr, float b1, float b2, float wd, float gscale) {
+                                                   const uint8_t* __restrict__ mask, int64_t n, float lr, float b1, float b2,
+                                                   float wd, float gscale) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        if (mask && !mask[i]) continue;                 // parameter received no gradient this step: lion_pytorch skips it entirely
         const float gg = g[i] * gscale, mm = m[i];
         const float u = b1 * mm + (1.f - b1) * gg;
         const float sg = (u > 0.f) ? 1.f : (u < 0.f ? -1.f : 0.f);
@@ -553,11 +555,15 @@ __global__ void __launch_bounds__(256) lion_kernel(float* __restrict__ p, const 
         m[i] = b2 * mm + (1.f - b2) * gg;
     }
 }
+extern "C" int cwfa_lion_step_masked_f32(float* p, const float* g, float* m, const uint8_t* mask, int64_t n, float lr, float beta1,
+                                         float beta2, float weight_decay, float grad_scale, void* stream) {
+    if (n <= 0 || !p || !g || !m) { set_error("lion_step: bad args"); return CWFA_EINVAL; }
+    lion_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(p, g, m, mask, n, lr, beta1, beta2, weight_decay, grad_scale);
+    return check_launch("lion_step");
+}
 extern "C" int cwfa_lion_step_f32(float* p, const float* g, float* m, int64_t n, float lr, float beta1, float beta2,
                                   float weight_decay, float grad_scale, void* stream) {
-    if (n <= 0 || !p || !g || !m) { set_error("lion_step: bad args"); return CWFA_EINVAL; }
-    lion_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(p, g, m, n, lr, beta1, beta2, weight_decay, grad_scale);
-    return check_launch("lion_step");
+    return cwfa_lion_step_masked_f32(p, g, m, nullptr, n, lr, beta1, beta2, weight_decay, grad_scale, stream);
 }
 
 // ------------------------------------------------------------------------------------------

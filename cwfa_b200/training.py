@@ -47,20 +47,47 @@ class FlatGroup:
         self.flat = torch.zeros(n, device=dev, dtype=torch.float32)
         self.grad = torch.zeros(n, device=dev, dtype=torch.float32)
         self.offsets = offs
-        for p, o in zip(mine, offs):
+        self.used = [False] * len(mine)                 # "received a gradient since zero_grad": lion_pytorch skips the others
+        self._mask, self._mask_key, self._hooks = None, None, []
+        for i, (p, o) in enumerate(zip(mine, offs)):
             v = self.flat[o:o + p.numel()].view(p.shape)
             v.copy_(p.data)
             p.data = v
             p.grad = self.grad[o:o + p.numel()].view(p.shape)
             p._cwfa_flat = True
+            self._hooks.append(p.register_hook(lambda g, i=i: self._mark(i)))
+
+    def _mark(self, i):
+        self.used[i] = True
+
+    def mark_all_used(self):
+        """For gradients written by hand INTO the flat views (no autograd hook fires): treat every parameter as having a gradient."""
+        self.used = [True] * len(self.params)
+
+    def mask(self):
+        """Byte mask over the flat buffer (1 = parameter received a gradient this step), or None when all did."""
+        if all(self.used):
+            return None
+        key = tuple(self.used)
+        if key != self._mask_key:
+            m = torch.zeros(self.flat.numel(), dtype=torch.uint8, device=self.flat.device)
+            for p, o, u in zip(self.params, self.offsets, self.used):
+                if u:
+                    m[o:o + p.numel()] = 1
+            self._mask, self._mask_key = m, key
+        return self._mask
 
     def release(self):
         """Give the parameters up (they keep their values and stay views of this buffer) so another group may re-home them."""
         for p in self.params:
             p._cwfa_flat = False
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
 
     def zero_grad(self):
         self.grad.zero_()
+        self.used = [False] * len(self.params)
         for p in self.loose:
             p.grad = None
 
@@ -75,6 +102,7 @@ class FlatGroup:
             elif g.data_ptr() != view.data_ptr():
                 view.copy_(g.reshape(-1))
                 p.grad = view.view(p.shape)
+                self.used[self.params.index(p)] = True        # a gradient tensor was assigned by hand
                 ok = False
         return ok
 
@@ -107,6 +135,10 @@ class Lion:
         for g in self.param_groups:
             g["flat"].release()
 
+    def mark_all_used(self):
+        for g in self.param_groups:
+            g["flat"].mark_all_used()
+
     def flat_grads(self) -> List[torch.Tensor]:
         for g in self.param_groups:
             g["flat"].grads_alias_flat()
@@ -121,9 +153,11 @@ class Lion:
                 raise RuntimeError("cwfa_b200.Lion: parameters must live on a CUDA device (no CPU fallback)")
             fg.grads_alias_flat()
             b1, b2 = g["betas"]
-            if fg.flat.numel():
-                _lib.call("cwfa_lion_step_f32", fg.flat.data_ptr(), fg.grad.data_ptr(), g["exp_avg"].data_ptr(), fg.flat.numel(),
-                          g["lr"], b1, b2, g["weight_decay"], float(self.grad_scale), st)
+            if fg.flat.numel() and any(fg.used):
+                mk = fg.mask()
+                _lib.call("cwfa_lion_step_masked_f32", fg.flat.data_ptr(), fg.grad.data_ptr(), g["exp_avg"].data_ptr(),
+                          None if mk is None else mk.data_ptr(), fg.flat.numel(), g["lr"], b1, b2, g["weight_decay"],
+                          float(self.grad_scale), st)
             for p in fg.loose:
                 if p.grad is None:
                     continue

@@ -294,6 +294,10 @@ int cwfa_gate_f32(const float* x, const float* m, const float* g, const float* d
  * p *= 1 - lr*wd; p -= lr*sign(beta1*m + (1-beta1)*g); m = beta2*m + (1-beta2)*g, with g read as g*grad_scale. */
 int cwfa_lion_step_f32(float* p, const float* g, float* m, int64_t n, float lr, float beta1, float beta2,
                        float weight_decay, float grad_scale, void* stream);
+/* The same with a per-element byte mask (may be NULL): elements with mask 0 are left untouched -- lion_pytorch skips parameters whose
+ * .grad is None (e.g. the unused block_grad_up / block1|block12 / block7|block72 weights of the sub-networks). */
+int cwfa_lion_step_masked_f32(float* p, const float* g, float* m, const uint8_t* mask, int64_t n, float lr, float beta1,
+                              float beta2, float weight_decay, float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -218,6 +218,7 @@ def test_lion_kernel_vs_oracle():
         gs[3][0, :8] = 0.0                                        # sign(0) = 0 on the first step
         for p, g in zip(ps, gs):
             p.grad.copy_(g.to(DEV))
+        opt.mark_all_used()                                   # gradients written by hand into the flat views
         opt.step()
         for i in range(4):
             ref_p[i], ref_m[i] = O.lion_step(ref_p[i], gs[i], ref_m[i], hyp[i][0], 0.9, 0.99, hyp[i][1])
@@ -338,7 +339,10 @@ def test_training_steps_reduce_loss_and_are_reproducible(golden_tiny, golden_tra
     for _ in range(2):
         model = build_tiny_model(golden_tiny, DEV)
         tr = FlowLevelTrainer(model, 1, lr=2e-4, lr_cond=2e-4)
+        unused0 = model.conv_inn[1].module_list[2].subnet.block_grad_up.weight.detach().clone()
         losses = [float(tr.step(*inputs)["loss"]) for _ in range(5)]
+        # parameters that never receive a gradient (kept for checkpoint compatibility) are skipped, as lion_pytorch does (no decay)
+        assert torch.equal(unused0, model.conv_inn[1].module_list[2].subnet.block_grad_up.weight.detach())
         runs.append((losses, torch.cat([p.detach().reshape(-1) for p in model.conv_inn[1].parameters() if p.requires_grad]).clone()))
         assert tr.collectives == 0
     print("losses", runs[0][0])

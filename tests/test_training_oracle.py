@@ -111,8 +111,13 @@ def test_flat_group_rehomes_parameters():
     # a parameter claimed by a second group stays "loose" there (the conditioning nets share ONE PReLU, networks.py:209)
     fg2 = FlatGroup([net[1].weight, torch.nn.Parameter(torch.zeros(3))])
     assert len(fg2.loose) == 1 and len(fg2.params) == 1
+    assert all(fg.used) and fg.mask() is None             # every parameter received a gradient (autograd hooks)
     fg.zero_grad()
-    assert float(fg.grad.abs().sum()) == 0.0
+    assert float(fg.grad.abs().sum()) == 0.0 and not any(fg.used)
+    net[0](x).sum().backward()                            # only the first conv is used now
+    assert fg.used == [True, True, False, False, False]
+    m = fg.mask()
+    assert int(m.sum()) == net[0].weight.numel() + net[0].bias.numel() and int(m[: net[0].weight.numel()].min()) == 1
 
 
 def test_oracle_lion_matches_published_update():
