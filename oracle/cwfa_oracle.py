@@ -485,3 +485,70 @@ def lrnn_train_grads(sd: SD, views: Tensor, gt: Tensor, mean_vol: Optional[Tenso
     loss.backward()
     grads = {k: v.grad for k, v in p.items() if torch.is_tensor(v) and v.requires_grad and v.grad is not None}
     return dict(loss=loss.detach(), grads=grads)
+
+
+# ----------------------------------------------------------------------------------------
+# ActNorm and AllInOneBlock
+# ----------------------------------------------------------------------------------------
+def actnorm_init(data: Tensor) -> Tuple[Tensor, Tensor]:
+    """ActNorm._initialize_with_data, invertible_resnet.py:53-64: scale = log(1/std_c) (unbiased std over batch and space),
+    bias = -mean_c(data * exp(scale)).  Returns (scale, bias) shaped (1,C,1,1)."""
+    C = data.shape[1]
+    flat = data.transpose(0, 1).contiguous().view(C, -1)
+    scale = torch.log(1.0 / flat.std(dim=-1))
+    bias = -(flat * scale.exp()[:, None]).mean(dim=-1)
+    shape = [1, C] + [1] * (data.dim() - 2)
+    return scale.view(shape), bias.view(shape)
+
+
+def actnorm(x: Tensor, scale: Tensor, bias: Tensor, rev: bool = False) -> Tuple[Tensor, Tensor]:
+    """ActNorm.forward, invertible_resnet.py:66-81: y = x * exp(scale) + bias, J = sum(scale) * prod(spatial dims) per sample."""
+    jac = (scale.sum() * x[0, 0].numel()).repeat(x.shape[0])
+    if rev:
+        return (x - bias) / scale.exp(), -jac
+    return x * scale.exp() + bias, jac
+
+
+def all_in_one_block(sd: SD, pre: str, x: Tensor, conds: Sequence[Tensor], rev: bool, clamp: float = 2.0, gin: bool = False,
+                     global_affine_type: str = "SOFTPLUS", reverse_permutation: bool = False, householder: int = 0):
+    """AllInOneBlock.forward, all_in_one_block.py:216-262 (``_permute`` :171-187, ``_pre_permute`` :189-195, ``_affine`` :197-214,
+    Householder product :160-169) for image-shaped inputs, with the CWFA sub-network under ``pre + 'subnet.'``."""
+    C = x.shape[1]
+    if householder:
+        w = sd[pre + "w_0"]
+        for vk in sd[pre + "vk_householder"]:
+            w = torch.mm(w, torch.eye(C, dtype=w.dtype) - 2 * torch.ger(vk, vk) / torch.dot(vk, vk))
+        w_perm = w.reshape(C, C, 1, 1)
+        w_perm_inv = w_perm.transpose(0, 1).contiguous()
+    else:
+        w_perm, w_perm_inv = sd[pre + "w_perm"], sd[pre + "w_perm_inv"]
+    gs, go = sd[pre + "global_scale"], sd[pre + "global_offset"]
+    act = {"SIGMOID": lambda a: 10 * torch.sigmoid(a - 2.0), "SOFTPLUS": lambda a: 0.1 * F.softplus(a, beta=0.5),
+           "EXP": torch.exp}[global_affine_type]
+    scale = None if gin else act(gs)
+    perm_jac = 0.0 if gin else torch.sum(torch.log(scale))
+    n_pix = x[0, :1].numel()
+    if rev:
+        x = F.conv2d(x, w_perm_inv) - go
+        if scale is not None:
+            x = x / scale
+    elif reverse_permutation:
+        x = F.conv2d(x, w_perm_inv)
+    l1 = C - C // 2
+    x1, x2 = x[:, :l1], x[:, l1:]
+    a = subnet(sd, pre + "subnet.", torch.cat([x1, *conds], 1) if len(conds) else x1, True) * 0.1
+    ch = x2.shape[1]
+    s = clamp * torch.tanh(a[:, :ch])
+    if gin:
+        s = s - s.mean(dim=(1, 2, 3), keepdim=True)
+    j2 = s.sum(dim=(1, 2, 3))
+    if rev:
+        x2, j2 = (x2 - a[:, ch:]) * torch.exp(-s), -j2
+    else:
+        x2 = x2 * torch.exp(s) + a[:, ch:]
+    out = torch.cat((x1, x2), 1)
+    if not rev:
+        out = F.conv2d((out * scale if scale is not None else out) + go, w_perm)
+    elif reverse_permutation:
+        out = F.conv2d(out, w_perm)
+    return out, j2 + (-1) ** int(rev) * n_pix * perm_jac
