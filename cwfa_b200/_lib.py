@@ -53,7 +53,7 @@ _SIGS = {
     "cwfa_conv_tc_coupling": [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, f32, vp, i32, i32, f32, f32,
                               i32, vp, i32, vp],
     "cwfa_coupling_tc_tiles": [i32, i32],
-    "cwfa_coupling_tc": [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, f32, vp, i32, i32, f32, f32, i32, vp, i32, vp],
+    "cwfa_coupling_tc": [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, f32, vp, i32, i32, f32, f32, i32, vp, vp, vp, i32, vp, i32, vp],
     "cwfa_coupling_finalize": [vp, vp, vp, i32, i32, i32, vp],
     "cwfa_nchw_to_c8": [vp, vp, i32, i32, i32, i64, i32, vp],
     "cwfa_c8_to_nchw": [vp, vp, i32, i32, i32, i64, i32, vp],

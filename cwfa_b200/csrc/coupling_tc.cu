@@ -32,8 +32,12 @@ struct CpParams {
     float* y;
     const float* t_ext;          // external shift or NULL
     const int* perm;
-    float* ws;                   // [num_tiles][2]
+    float* ws;                   // [num_tiles][16][2]
     float kk, tscale;
+    float* logdet;               // in-kernel finalize (ticket != NULL): logdet[n] (+)= sum s, sumsq[n] = sum y^2
+    float* sumsq;
+    int* ticket;                 // zero on entry; the last CTA to finish reduces the partials in a fixed order and resets it
+    int accumulate;
 };
 
 template <bool BF16, bool INV, bool EXT>
@@ -234,6 +238,7 @@ __global__ void __launch_bounds__(kThreads, 1) coupling_tc_kernel(const __grid_c
                 w[1] = sum_q;
             }
         }
+        if (p.ticket) __threadfence();          // this warp's partials are visible device-wide before the CTA takes its ticket
     }
     tc_fence_before();
     __syncthreads();
@@ -241,6 +246,41 @@ __global__ void __launch_bounds__(kThreads, 1) coupling_tc_kernel(const __grid_c
         tc_fence_after();
         tmem_dealloc(tmem, 512);
     }
+    if (p.ticket == nullptr) return;
+    // ---- in-kernel finalize: the LAST CTA to finish sums all (tile, warp) partials of every sample in a FIXED order
+    // (thread <-> partial assignment and tree shape do not depend on which CTA is last => bit-reproducible), so the
+    // separate cwfa_coupling_finalize launch disappears.
+    __shared__ int s_last;
+    __shared__ double s_red[kThreads / 32][2];
+    if (threadIdx.x == 0) s_last = (atomicAdd(p.ticket, 1) == (int)gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const int per_img = tiles_per_img * 16;
+    for (int n = 0; n < p.N; ++n) {
+        double s = 0.0, q = 0.0;
+        const float2* src = reinterpret_cast<const float2*>(p.ws) + (size_t)n * per_img;
+        for (int i = threadIdx.x; i < per_img; i += kThreads) {
+            const float2 v = __ldcg(src + i);
+            s += (double)v.x;
+            q += (double)v.y;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, o);
+            q += __shfl_xor_sync(0xffffffffu, q, o);
+        }
+        if (lane == 0) { s_red[warp][0] = s; s_red[warp][1] = q; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double a = 0.0, b = 0.0;
+            for (int k = 0; k < kThreads / 32; ++k) { a += s_red[k][0]; b += s_red[k][1]; }
+            p.logdet[n] = (p.accumulate ? p.logdet[n] : 0.f) + (float)a;
+            if (p.sumsq) p.sumsq[n] = (float)b;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *p.ticket = 0;        // ready for the next launch / graph replay that reuses this buffer
 }
 }  // namespace
 
@@ -248,14 +288,15 @@ __global__ void __launch_bounds__(kThreads, 1) coupling_tc_kernel(const __grid_c
 extern "C" int cwfa_coupling_tc_tiles(int H, int W) { return ceil_div(W, kTW) * ceil_div(H, kTH) * 16; }
 
 // Same contract as cwfa_conv_tc_coupling, for the CWFA sub-network shape: 3x3 conv from 64 hidden channels to
-// Cout_p <= 96 (= one N block), ch <= 48.  workspace: 2 * N * cwfa_coupling_tc_tiles(H, W) floats, to be reduced with
-// cwfa_coupling_finalize(..., tiles = cwfa_coupling_tc_tiles(H, W), ...).
+// Cout_p <= 96 (= one N block), ch <= 48.  workspace: 2 * N * cwfa_coupling_tc_tiles(H, W) floats.  With ticket != NULL
+// (one int32, zero on entry, left zero on exit) the kernel itself reduces them into logdet / sumsq (last-CTA finalize, fixed
+// order); with ticket == NULL reduce with cwfa_coupling_finalize(..., tiles = cwfa_coupling_tc_tiles(H, W), ...).
 extern "C" int cwfa_coupling_tc(const void* b_c8, const void* w_packed, const float* bias, int N, int H, int W, int Cout,
                                 int Cout_p, const float* cx, float* cy, const float* ct, float t_scale, const int32_t* perm,
-                                int perm_axis, int ch, float clamp, float k_atan, int inverse, float* workspace, int is_bf16,
-                                void* stream) {
+                                int perm_axis, int ch, float clamp, float k_atan, int inverse, float* workspace, float* logdet,
+                                float* sumsq, int accumulate, int32_t* ticket, int is_bf16, void* stream) {
     if (N <= 0 || H <= 0 || W <= 0 || (int64_t)ch * H * W >= (1ll << 31) || !cy || !workspace || ch <= 0 || ch > 48 || Cout_p > kMaxBN || (Cout_p % 16) ||
-        (ct ? Cout < ch : Cout < 2 * ch) || (perm && (perm_axis < 1 || perm_axis > 3)) || (!cx && !inverse)) {
+        (ct ? Cout < ch : Cout < 2 * ch) || (perm && (perm_axis < 1 || perm_axis > 3)) || (!cx && !inverse) || (ticket && !logdet)) {
         set_error("coupling_tc: unsupported arguments (needs 64 -> Cout_p <= 96, ch <= 48)");
         return CWFA_EINVAL;
     }
@@ -272,6 +313,7 @@ extern "C" int cwfa_coupling_tc(const void* b_c8, const void* w_packed, const fl
     p.BN = Cout_p; p.ch = ch; p.axis = perm_axis;
     p.w = (const uint8_t*)w_packed; p.bias = bias; p.x = cx; p.y = cy; p.t_ext = ct; p.perm = perm; p.ws = workspace;
     p.kk = clamp * k_atan; p.tscale = t_scale;
+    p.logdet = logdet; p.sumsq = sumsq; p.ticket = ticket; p.accumulate = accumulate;
     CUtensorMap tmap;
     int rc = make_c8_tensor_map(&tmap, b_c8, N, kChunks, H, W, kBW, kBH, kChunks, is_bf16);
     if (rc) return rc;

@@ -246,14 +246,21 @@ class CWFAEngine:
                 out.append(("perm", mod, extra, None))
         return out
 
-    def _couple(self, item, x, mean_vol, pending, inverse, logdet, sumsq=None):
+    @staticmethod
+    def _jac_and_tickets(n_samples: int, device, n_tickets: int = 8):
+        """One zero-filled allocation (one memset) per level: the (B,) log-det accumulator plus the int32 tickets of the
+        level's coupling kernels (in-kernel last-CTA finalize, cwfa_coupling_tc)."""
+        buf = torch.zeros(n_samples + n_tickets, device=device, dtype=torch.float32)
+        return buf[:n_samples], buf[n_samples:].view(torch.int32)
+
+    def _couple(self, item, x, mean_vol, pending, inverse, logdet, sumsq=None, ticket=None):
         """Final conv of one sub-network with the coupling fused in its epilogue."""
         _, mod, sub, b8 = item
         perm, axis = (None, 0) if pending is None else (ops.perm_i32(pending[0], b8.data.device), pending[1])
         first = not sub.normal
         return tc.conv_tc_coupling(b8, sub.out, x, ch=mod.channels, inverse=inverse, clamp=mod.clamp,
                                    t_ext=mean_vol if first else None, t_scale=(-1.0 / math.sqrt(2)) if first else 1.0,
-                                   perm=perm, perm_axis=axis, logdet=logdet, sumsq=sumsq)
+                                   perm=perm, perm_axis=axis, logdet=logdet, sumsq=sumsq, ticket=ticket)
 
     def _level_detail_inverse(self, n, v8, mean_vol, z=None):
         """Detail half ``hi`` of level n in the inverse direction and its log-det.  Independent of the other levels.
@@ -261,11 +268,12 @@ class CWFAEngine:
         sample (B, ch, H, W) of this level (``sample_z_truncated``, CWFA.py:47-64)."""
         items = self._trunks(n, v8)
         hi, pending = z, None
-        jac = torch.zeros(v8.N, device=v8.data.device, dtype=torch.float32)
+        jac, tickets = self._jac_and_tickets(v8.N, v8.data.device)
+        k = 0
         for item in reversed(items):
             if item[0] == "cat":
-                hi = self._couple(item, hi, mean_vol, pending, True, jac)
-                pending = None
+                hi = self._couple(item, hi, mean_vol, pending, True, jac, ticket=tickets[k:k + 1])
+                pending, k = None, (k + 1) % tickets.numel()
             elif hi is not None:
                 pending = (item[1].perm_inv, item[2])       # gathered by the next coupling's epilogue
         if pending is not None:
@@ -316,13 +324,13 @@ class CWFAEngine:
         x = volume
         for n in range(self.model.n_levels):
             lo, hi = ops.haar1d_split(x)
-            jac = torch.zeros(x.shape[0], device=x.device, dtype=torch.float32)
+            jac, tickets = self._jac_and_tickets(x.shape[0], x.device)
             sumsq = torch.empty_like(jac)
-            pending = None
+            pending, k = None, 0
             for item in self._trunks(n, v8):
                 if item[0] == "cat":
-                    hi = self._couple(item, hi, mean_vols[n], pending, False, jac, sumsq)   # sumsq: last coupling wins
-                    pending = None
+                    hi = self._couple(item, hi, mean_vols[n], pending, False, jac, sumsq, ticket=tickets[k:k + 1])   # sumsq: last coupling wins
+                    pending, k = None, (k + 1) % tickets.numel()
                 else:
                     pending = (item[1].perm, item[2])
             if pending is not None:          # trailing permutation: does not change ||z||^2

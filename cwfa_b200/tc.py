@@ -253,10 +253,12 @@ def conv_tc_coupling(b: C8, pc: PackedConv, x: Optional[torch.Tensor], *, ch: in
                      k_atan: float = 0.636, t_ext: Optional[torch.Tensor] = None, t_scale: float = 1.0,
                      perm: Optional[torch.Tensor] = None, perm_axis: int = 0, logdet: torch.Tensor = None,
                      sumsq: Optional[torch.Tensor] = None, accumulate: bool = True, mb: Optional[int] = None,
-                     persistent: Optional[bool] = None) -> torch.Tensor:
+                     persistent: Optional[bool] = None, ticket: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Last conv of a coupling sub-network with the affine coupling, the log-det partial sums and the preceding
     permutation (as a gather on ``x``) fused into its epilogue.  ``x`` None = zeros (z = 0, inverse only).
-    ``logdet`` (B,) is accumulated in place (fixed-order reduction); ``sumsq`` (B,) receives sum(y^2)."""
+    ``logdet`` (B,) is accumulated in place (fixed-order reduction); ``sumsq`` (B,) receives sum(y^2).
+    ``ticket``: one zero int32 on the device (the kernel leaves it zero); with it the persistent kernel reduces its partial
+    sums itself (last CTA, fixed order) instead of a separate finalize launch."""
     if b.Cp != pc.Cin_p or b.kind != pc.kind:
         raise ValueError("conv_tc_coupling: input layout mismatch")
     need = ch if t_ext is not None else 2 * ch
@@ -277,8 +279,9 @@ def conv_tc_coupling(b: C8, pc: PackedConv, x: Optional[torch.Tensor], *, ch: in
         ws = torch.empty(2 * N * tiles, device=dev, dtype=torch.float32)
         _lib.call("cwfa_coupling_tc", b.data.data_ptr(), pc.packed.data_ptr(), _p(pc.bias), N, H, W, pc.Cout, pc.Cout_p, _p(xx),
                   y.data_ptr(), _p(tt), float(t_scale), _p(perm), int(perm_axis), ch, float(clamp), float(k_atan), int(inverse),
-                  ws.data_ptr(), b.is_bf16, _stream())
-        _lib.call("cwfa_coupling_finalize", ws.data_ptr(), logdet.data_ptr(), _p(sumsq), N, tiles, int(accumulate), _stream())
+                  ws.data_ptr(), logdet.data_ptr(), _p(sumsq), int(accumulate), _p(ticket), b.is_bf16, _stream())
+        if ticket is None:
+            _lib.call("cwfa_coupling_finalize", ws.data_ptr(), logdet.data_ptr(), _p(sumsq), N, tiles, int(accumulate), _stream())
         return y
     tiles = lib.cwfa_conv_tc_coupling_tiles(H, W, mb)
     ws = torch.empty(2 * N * tiles, device=dev, dtype=torch.float32)

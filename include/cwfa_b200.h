@@ -207,12 +207,14 @@ int cwfa_coupling_finalize(const float* workspace, float* logdet, float* sumsq, 
 /* Persistent variant of cwfa_conv_tc_coupling for the CWFA sub-network shape (3x3 conv from 64 hidden channels to
  * Cout_p <= 96 in one N block, ch <= 48): weights resident in shared memory, accumulators double buffered in TMEM,
  * 16 epilogue warps.  workspace: 2 * N * cwfa_coupling_tc_tiles(H, W) floats (one (sum s, sum y^2) partial per tile and
- * epilogue warp; reduce with cwfa_coupling_finalize(..., tiles = cwfa_coupling_tc_tiles(H, W), ...)). */
+ * epilogue warp).  ticket != NULL (one int32 that is zero on entry; left zero on exit): the last CTA to finish reduces the
+ * partials in a fixed order inside the kernel, logdet[n] = (accumulate ? logdet[n] : 0) + sum, sumsq[n] = sum y^2 (may be
+ * NULL) -- no finalize launch.  ticket == NULL: reduce with cwfa_coupling_finalize(..., tiles = cwfa_coupling_tc_tiles(H, W), ...). */
 int cwfa_coupling_tc_tiles(int H, int W);
 int cwfa_coupling_tc(const void* b_c8, const void* w_packed, const float* bias, int N, int H, int W, int Cout,
                      int Cout_p, const float* cx, float* cy, const float* ct, float t_scale, const int32_t* perm,
-                     int perm_axis, int ch, float clamp, float k_atan, int inverse, float* workspace, int is_bf16,
-                     void* stream);
+                     int perm_axis, int ch, float clamp, float k_atan, int inverse, float* workspace, float* logdet,
+                     float* sumsq, int accumulate, int32_t* ticket, int is_bf16, void* stream);
 /* Layout converters NCHW fp32 <-> C8 half (channels padded with zeros up to Cp). */
 int cwfa_nchw_to_c8(const float* x, void* y, int N, int C, int Cp, int64_t P, int is_bf16, void* stream);
 int cwfa_c8_to_nchw(const void* x, float* y, int N, int C, int Cp, int64_t P, int is_bf16, void* stream);

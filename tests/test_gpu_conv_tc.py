@@ -202,7 +202,7 @@ def _coupling_reference(a, x, t_ext, t_scale, ch, inverse, clamp=2.0, k=0.636):
 @pytest.mark.parametrize("ch,axis,inverse,ext,zero_x", [
     (48, 1, True, False, False), (48, 3, True, False, False), (24, 2, False, False, False), (12, 1, False, True, False),
     (6, 0, True, True, True), (6, 3, False, False, False), (48, 0, True, False, True), (24, 1, True, True, False)])
-@pytest.mark.parametrize("persistent", [True, False])
+@pytest.mark.parametrize("persistent", [True, False, "ticket"])
 def test_fused_coupling_conv_vs_reference(ch, axis, inverse, ext, zero_x, persistent):
     """Last sub-network conv (64 -> 2 ch, 3x3) + affine coupling + log-det / sum y^2 + preceding permutation (gather on x)
     in ONE kernel (persistent coupling_tc and the general conv_tc<COUPLING>) vs conv2d + coupling_layers.py:490-500 in torch."""
@@ -223,13 +223,17 @@ def test_fused_coupling_conv_vs_reference(ch, axis, inverse, ext, zero_x, persis
         xin = xin.index_select(axis, perm)                 # the permutation preceding the coupling (fixed_transforms.py:37-41)
     y_ref, j_ref = _coupling_reference(a, xin, t_ext, -0.5 ** 0.5 if ext else 1.0, ch, inverse)
     pc = tc.PackedConv(w.to(DEV), bias.to(DEV), kind, bn=tc.pad16(cout))
+    # "ticket": the persistent kernel reduces its own partial sums (last-CTA finalize); the int32 must come back as zero
+    ticket = torch.zeros(1, device=DEV, dtype=torch.int32) if persistent == "ticket" else None
+    persistent = bool(persistent)
     logdet = torch.full((N,), 3.0, device=DEV)
     sumsq = torch.zeros(N, device=DEV)
     y = tc.conv_tc_coupling(tc.to_c8(b.to(DEV), kind), pc, None if x is None else x.to(DEV), ch=ch, inverse=inverse,
                             t_ext=None if t_ext is None else t_ext.to(DEV), t_scale=-0.5 ** 0.5 if ext else 1.0,
                             perm=None if perm is None else perm.to(DEV).to(torch.int32), perm_axis=axis if perm is not None else 0,
-                            logdet=logdet, sumsq=sumsq, accumulate=True, persistent=persistent)
+                            logdet=logdet, sumsq=sumsq, accumulate=True, persistent=persistent, ticket=ticket)
     torch.cuda.synchronize()
+    assert ticket is None or int(ticket[0]) == 0
     assert rel_l2(y, y_ref) < 2e-5 * 50                     # fp32 accumulation-order + fast atan/exp differences only
     assert torch.allclose(logdet.cpu() - 3.0, j_ref, rtol=2e-4, atol=2e-2)
     assert torch.allclose(sumsq.cpu(), (y_ref.double() ** 2).sum(dim=(1, 2, 3)).float(), rtol=2e-3)
@@ -238,7 +242,7 @@ def test_fused_coupling_conv_vs_reference(ch, axis, inverse, ext, zero_x, persis
     tc.conv_tc_coupling(tc.to_c8(b.to(DEV), kind), pc, None if x is None else x.to(DEV), ch=ch, inverse=inverse,
                         t_ext=None if t_ext is None else t_ext.to(DEV), t_scale=-0.5 ** 0.5 if ext else 1.0,
                         perm=None if perm is None else perm.to(DEV).to(torch.int32), perm_axis=axis if perm is not None else 0,
-                        logdet=logdet2, persistent=persistent)
+                        logdet=logdet2, persistent=persistent, ticket=ticket)
     assert torch.equal(logdet, logdet2)
 
 
