@@ -111,10 +111,14 @@ def load():
         path = _build.LIB_PATH
         try:
             path = _build.build()
-        except Exception as e:  # stale-but-present library is still usable
-            if not os.path.exists(path):
+        except Exception as e:
+            # A library that does not match the sources must never be bound with this file's argtypes (raw device
+            # pointers through a mismatched ABI = silent memory corruption): refuse it.
+            if os.path.exists(path) and _build.built_hash() == _build.source_hash():
+                pass                     # up to date; the failure was incidental (e.g. nvcc absent on a deploy box)
+            else:
                 raise RuntimeError(
-                    "cwfa_b200: CUDA library missing and could not be built "
+                    "cwfa_b200: the CUDA library is missing or older than its sources and could not be (re)built "
                     f"({e}); there is no CPU fallback") from e
         lib = C.CDLL(path)
         for name, args in {**_SIGS, **_OPTIONAL}.items():

@@ -670,6 +670,38 @@ def batchnorm(x, gamma, beta, running_mean, running_var, *, batch_stats, eps):
     return _BatchNorm.apply(x, gamma, beta, running_mean, running_var, batch_stats, eps)
 
 
+class _ScaleShift(_F):
+    """y[b,c] = x[b,c] * scale[c] + shift[c] (ActNorm, invertible_resnet.py:66-81; global affine of AllInOneBlock,
+    all_in_one_block.py:171-187).  Adjoint: dx = dy * scale[c]; d scale[c] = <dy, x>_c; d shift[c] = <dy>_c -- the two
+    per-channel sums come from ONE pass of the BatchNorm-adjoint reduction kernel (``channel_dot_stats``)."""
+
+    @staticmethod
+    def forward(ctx, x, scale, shift):
+        xx, sc, sh = _f32(x), _f32(scale).reshape(-1), _f32(shift).reshape(-1)
+        ctx.save_for_backward(xx, sc)
+        ctx.shapes = (scale.shape, shift.shape)
+        return ops.scale_shift(xx, sc, sh)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, sc = ctx.saved_tensors
+        dy = ops._ck(dy)
+        N, C = x.shape[0], x.shape[1]
+        P = x[0, 0].numel()
+        dx = ops.scale_shift(dy, sc, torch.zeros_like(sc)) if ctx.needs_input_grad[0] else None
+        dsc = dsh = None
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            out = torch.empty(2 * C, device=x.device, dtype=torch.float32)
+            ws = torch.empty(2 * C * _lib.load().cwfa_channel_dot_workspace_blocks(), device=x.device, dtype=torch.float32)
+            _lib.call("cwfa_channel_dot_stats_f32", x.data_ptr(), dy.data_ptr(), out.data_ptr(), ws.data_ptr(), N, C, P, _stream())
+            dsh, dsc = out[:C].reshape(ctx.shapes[1]), out[C:].reshape(ctx.shapes[0])
+        return dx, dsc, dsh
+
+
+def scale_shift(x, scale, shift):
+    return _ScaleShift.apply(x, scale, shift)
+
+
 class _MaxPool2(_F):
     @staticmethod
     def forward(ctx, x):

@@ -250,31 +250,35 @@ __global__ void __launch_bounds__(kThreads, 1) coupling_tc_kernel(const __grid_c
     // ---- in-kernel finalize: the LAST CTA to finish sums all (tile, warp) partials of every sample in a FIXED order
     // (thread <-> partial assignment and tree shape do not depend on which CTA is last => bit-reproducible), so the
     // separate cwfa_coupling_finalize launch disappears.
-    __shared__ int s_last;
-    __shared__ double s_red[kThreads / 32][2];
-    if (threadIdx.x == 0) s_last = (atomicAdd(p.ticket, 1) == (int)gridDim.x - 1) ? 1 : 0;
+    // (scratch lives in the dynamic header: the kernel already uses the full 227 KB carve-out, so no static shared memory)
+    volatile int* s_last = reinterpret_cast<volatile int*>(smem + 132);
+    double* s_red = reinterpret_cast<double*>(smem + 256);          // [16 warps][2]
+    if (threadIdx.x == 0) *s_last = (atomicAdd(p.ticket, 1) == (int)gridDim.x - 1) ? 1 : 0;
     __syncthreads();
-    if (!s_last) return;
+    if (!*s_last) return;
     __threadfence();
     const int per_img = tiles_per_img * 16;
+    constexpr int kRed = 512;                                       // reducing threads (16 warps)
     for (int n = 0; n < p.N; ++n) {
         double s = 0.0, q = 0.0;
         const float2* src = reinterpret_cast<const float2*>(p.ws) + (size_t)n * per_img;
-        for (int i = threadIdx.x; i < per_img; i += kThreads) {
-            const float2 v = __ldcg(src + i);
-            s += (double)v.x;
-            q += (double)v.y;
-        }
+        if (threadIdx.x < kRed) {
+            for (int i = threadIdx.x; i < per_img; i += kRed) {
+                const float2 v = __ldcg(src + i);
+                s += (double)v.x;
+                q += (double)v.y;
+            }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            s += __shfl_xor_sync(0xffffffffu, s, o);
-            q += __shfl_xor_sync(0xffffffffu, q, o);
+            for (int o = 16; o > 0; o >>= 1) {
+                s += __shfl_xor_sync(0xffffffffu, s, o);
+                q += __shfl_xor_sync(0xffffffffu, q, o);
+            }
+            if (lane == 0) { s_red[warp * 2] = s; s_red[warp * 2 + 1] = q; }
         }
-        if (lane == 0) { s_red[warp][0] = s; s_red[warp][1] = q; }
         __syncthreads();
         if (threadIdx.x == 0) {
             double a = 0.0, b = 0.0;
-            for (int k = 0; k < kThreads / 32; ++k) { a += s_red[k][0]; b += s_red[k][1]; }
+            for (int k = 0; k < kRed / 32; ++k) { a += s_red[k * 2]; b += s_red[k * 2 + 1]; }
             p.logdet[n] = (p.accumulate ? p.logdet[n] : 0.f) + (float)a;
             if (p.sumsq) p.sumsq[n] = (float)b;
         }

@@ -6,6 +6,7 @@ Mirrors: ``XLFMDatasetFull.extract_views`` (XLFMDataset.py:212-242), ``serialize
 """
 from __future__ import annotations
 
+import argparse
 import glob
 import os
 import re
@@ -70,11 +71,14 @@ def load_INN_steps(path, prefix="model_step_*__ep_*", epoch=-1) -> Dict[int, lis
     return found
 
 
-def load_checkpoints(model, path: str, epoch: int = -1, strict: bool = True):
+def load_checkpoints(model, path: str, epoch: int = -1, strict: bool = True, permute_dim_axes: Optional[Dict[int, Dict[int, int]]] = None):
     """Loads reference-format step checkpoints into a ``CWFAModel`` (step k -> conv_inn[k-1] / cond_nets[k-1], as in
     CWFA.py:488-522) and returns the stored ``training_statistics`` (or None).  ``PermuteDim`` axes are not part of the
     reference's ``state_dict`` (INN_utils.py:58-61); a file written by ``save_checkpoints`` carries them as
-    ``permute_dim_axes``."""
+    ``permute_dim_axes``; for files written by the reference pass ``permute_dim_axes={step: {module_idx: axis}}``.
+
+    SECURITY: the reference format pickles an argparse.Namespace, so the files are read with ``weights_only=False`` like the
+    reference does (CWFA.py:483) -- unpickling executes code: load checkpoints from TRUSTED sources only."""
     steps = load_INN_steps(path, epoch=epoch)
     stats = None
     for step, (_, fname) in sorted(steps.items()):
@@ -82,7 +86,9 @@ def load_checkpoints(model, path: str, epoch: int = -1, strict: bool = True):
         ix = step - 1
         if ix < model.n_levels and data.get("INN_state_dict") is not None:
             model.conv_inn[ix].load_state_dict(data["INN_state_dict"], strict=strict)
-            for idx, axis in (data.get("permute_dim_axes") or {}).items():
+            axes = dict(data.get("permute_dim_axes") or {})
+            axes.update((permute_dim_axes or {}).get(step, {}))
+            for idx, axis in axes.items():
                 model.conv_inn[ix].module_list[int(idx)].dims_to_permute = [1, int(axis)]
         if data.get("condition_state_dict") is not None and ix < len(model.cond_nets):
             model.cond_nets[ix].load_state_dict(data["condition_state_dict"], strict=strict)
@@ -91,13 +97,28 @@ def load_checkpoints(model, path: str, epoch: int = -1, strict: bool = True):
     return stats
 
 
+def _args_namespace(model, args, step: int) -> argparse.Namespace:
+    """The ``args`` entry of a reference checkpoint is the run's argparse.Namespace; the reference loader reads it by
+    ATTRIBUTE (``args_model.INN_down_steps = ix+1``, ``.INN_internal_chans``, ``.INN_use_perm``, ``.INN_block_type``,
+    ``.INN_n_blocks``, ``.INN_use_bias``, ``.INN_max_down_steps``, ``'force_last_step_NF' in args_model``; CWFA.py:486-508).
+    Accepts a Namespace, a dict or None; the model's shape flags (``CWFAConfig``) fill whatever the caller did not give."""
+    from dataclasses import asdict, is_dataclass
+    base = vars(args) if isinstance(args, argparse.Namespace) else dict(args or {})
+    cfg = asdict(model.cfg) if is_dataclass(getattr(model, "cfg", None)) else {}
+    ns = argparse.Namespace(**{**cfg, **base})
+    ns.INN_down_steps = step
+    return ns
+
+
 def save_checkpoints(model, path: str, epoch: int = 0, training_statistics=None, args=None):
-    """One reference-format file per step (model_step_{k}__ep_{E}); adds the PermuteDim axes as an extra key."""
+    """One reference-format file per step (model_step_{k}__ep_{E}) that the reference's own loader accepts: ``args`` is an
+    argparse.Namespace (see ``_args_namespace``).  Adds the PermuteDim axes as an extra key (``permute_dim_axes``), which the
+    reference ignores and ``load_checkpoints`` uses (the axis is not part of the reference's state_dict, INN_utils.py:58-61)."""
     from .modules import PermuteDim
     os.makedirs(path, exist_ok=True)
     for ix in range(len(model.cond_nets)):
         inn = model.conv_inn[ix] if ix < model.n_levels else None
-        a = dict(args or {}, INN_down_steps=ix + 1)
+        a = _args_namespace(model, args, ix + 1)
         fname = serialize_INN_step(inn, model.cond_nets[ix], None, training_statistics, a, epoch, path)
         if inn is not None:
             data = torch.load(fname, weights_only=False)

@@ -20,7 +20,7 @@ import torch
 
 from . import modules as Fm
 from . import networks, ops, tc
-from .pipeline import CWFAModel
+from .pipeline import CWFAModel, lrnn_mean_volume
 
 
 class _Subnet:
@@ -290,7 +290,7 @@ class CWFAEngine:
         parallel branches of the graph; only the four Haar merges are sequential."""
         L1 = self.model.n_levels
         v8 = tc.to_c8(views, self.kind)
-        mv_last = mean_vols[L1] if len(mean_vols) > L1 else None
+        mv_last = lrnn_mean_volume(mean_vols, L1)            # CWFA.py:882: mean_vols_cache[L-2] unless given explicitly
         jobs = [lambda: self.lrnn(v8, mv_last)] + [(lambda n=n: self._level_detail_inverse(n, v8, mean_vols[n], None if zs is None else zs[n])) for n in range(L1 - 1, -1, -1)]
         if _side_streams:
             main = torch.cuda.current_stream()

@@ -335,13 +335,15 @@ class SequenceINN(InvertibleModule):
     def output_dims(self, input_dims=None):
         if not self.force_tuple_output:
             raise ValueError("You can only call output_dims on a SequenceINN when setting force_tuple_output=True.")
-        return [self.shapes[-1]]
+        return input_dims                      # sequence_inn.py:62-66 returns its argument unchanged
 
     def forward(self, x_or_z, c: Iterable[torch.Tensor] = None, rev: bool = False, jac: bool = True):
+        """sequence_inn.py:68-99: a tensor or a 1-tuple in; the log-det starts as the integer 0 and takes the type of the
+        first module's ``jac`` (python number for fixed transforms, ``(B,)`` tensor for couplings)."""
         order = range(len(self.module_list))
         order = reversed(order) if rev else order
-        log_det = torch.zeros(x_or_z.shape[0], dtype=x_or_z.dtype, device=x_or_z.device)
-        cur = (x_or_z,)
+        log_det = 0
+        cur = (x_or_z,) if torch.is_tensor(x_or_z) else x_or_z
         for i in order:
             if self.conditions[i] is None:
                 cur, j = self.module_list[i](cur, jac=jac, rev=rev)

@@ -275,8 +275,10 @@ class PermuteDim(InvertibleModule):
 class _BaseCouplingBlock(InvertibleModule):
     """Dimension checks, split sizes and the soft clamp (coupling_layers.py:8-121).
 
-    Only ``clamp_activation="ATAN"`` runs in the fused CUDA coupling kernel; other clamp
-    functions are part of upstream FrEIA's API but are not used by CWFA and are rejected."""
+    Clamp activations (coupling_layers.py:50-60): ``"ATAN"`` (s = clamp * 0.636 * atan(a), what CWFA uses), ``"TANH"``
+    (s = clamp * tanh(a)) and ``"SIGMOID"`` (s = clamp * 2 (sigmoid(a) - 0.5) = clamp * tanh(a / 2)) are evaluated inside the
+    fused affine kernel (ATAN / TANH clamp modes).  A callable is applied to the sub-network output with the caller's own
+    torch ops (it is arbitrary Python) and the kernel receives the finished ``s``."""
 
     def __init__(self, dims_in, dims_c=[], clamp: float = 2.0, clamp_activation: Union[str, Callable] = "ATAN"):
         super().__init__(dims_in, dims_c)
@@ -289,10 +291,34 @@ class _BaseCouplingBlock(InvertibleModule):
             "Dimensions of input and one or more conditions don't agree."
         self.conditional = len(dims_c) > 0
         self.condition_length = sum(dims_c[i][0] for i in range(len(dims_c)))
-        if clamp_activation != "ATAN":
-            raise ValueError(f'clamp activation "{clamp_activation}" is not implemented by the CUDA coupling '
-                             'kernel; CWFA uses "ATAN" (coupling_layers.py:52)')
+        self.f_clamp = None
+        if isinstance(clamp_activation, str):
+            if clamp_activation == "ATAN":
+                self._clamp_kw = dict(k_atan=ops.K_ATAN, tanh_clamp=False)
+            elif clamp_activation == "TANH":
+                self._clamp_kw = dict(k_atan=1.0, tanh_clamp=True)
+            elif clamp_activation == "SIGMOID":
+                self._clamp_kw = dict(k_atan=0.5, tanh_clamp=True)          # 2 (sigmoid(u) - 0.5) == tanh(u / 2)
+            else:
+                raise ValueError(f'Unknown clamp activation "{clamp_activation}"')
+        else:
+            self.f_clamp = clamp_activation
+            self._clamp_kw = None
         self.clamp_activation = clamp_activation
+
+    def _affine(self, x, a_s, a_t, rev, t_scale: float = 1.0):
+        """y, log-det of one affine coupling with this block's clamp: the fused affine kernel."""
+        if self._clamp_kw is None:                                     # user-supplied clamp function
+            s = self.clamp * self.f_clamp(a_s)
+            return ops.affine(x, s.contiguous(), a_t, inverse=rev, clamp=self.clamp, t_scale=t_scale, s_is_final=True)
+        return ops.affine(x, a_s, a_t, inverse=rev, clamp=self.clamp, t_scale=t_scale, **self._clamp_kw)
+
+    def _clamped_s(self, a_s):
+        """s = clamp * f_clamp(a_s) as a tensor (only the volume-preserving GIN block needs it outside the kernel)."""
+        if self._clamp_kw is None:
+            return self.clamp * self.f_clamp(a_s)
+        k = self._clamp_kw["k_atan"]
+        return self.clamp * (torch.tanh(k * a_s) if self._clamp_kw["tanh_clamp"] else k * torch.atan(a_s))
 
     def output_dims(self, input_dims):
         if len(input_dims) != 1:
@@ -319,12 +345,11 @@ class _BaseCouplingBlock(InvertibleModule):
         s_raw, t = a[:, :n_out], a[:, n_out:]
         if gin:
             # volume preserving: s -= mean over channels (coupling_layers.py:361)
-            s = self.clamp * ops.K_ATAN * torch.atan(s_raw)
+            s = self._clamped_s(s_raw)
             s = s - s.mean(1, keepdim=True)
             y, _ = ops.affine(x_active, s.contiguous(), t, inverse=rev, clamp=self.clamp, s_is_final=True)
             return y, 0.0
-        y, j = ops.affine(x_active, s_raw, t, inverse=rev, clamp=self.clamp)
-        return y, j
+        return self._affine(x_active, s_raw, t, rev)
 
 
 class NICECouplingBlock(_BaseCouplingBlock):
@@ -358,10 +383,10 @@ class RNVPCouplingBlock(_BaseCouplingBlock):
         self.subnet_t2 = subnet_constructor(self.split_len2 + self.condition_length, self.split_len1)
 
     def _coupling1(self, x1, u2, rev=False):
-        return ops.affine(x1, self.subnet_s2(u2), self.subnet_t2(u2), inverse=rev, clamp=self.clamp)
+        return self._affine(x1, self.subnet_s2(u2), self.subnet_t2(u2), rev)
 
     def _coupling2(self, x2, u1, rev=False):
-        return ops.affine(x2, self.subnet_s1(u1), self.subnet_t1(u1), inverse=rev, clamp=self.clamp)
+        return self._affine(x2, self.subnet_s1(u1), self.subnet_t1(u1), rev)
 
 
 class GLOWCouplingBlock(_BaseCouplingBlock):
@@ -441,7 +466,7 @@ class ConditionalAffineTransform(_BaseCouplingBlock):
             if hit is None:
                 hit = memo[key] = (self._st(c), list(c))          # keeps the condition tensors alive: ids stay unique
             a_s, a_t, t_scale = hit[0]
-        y, j = ops.affine(x[0], a_s, a_t, inverse=rev, clamp=self.clamp, t_scale=t_scale)
+        y, j = self._affine(x[0], a_s, a_t, rev, t_scale=t_scale)
         return (y,), j
 
 
@@ -497,9 +522,11 @@ class ActNorm(InvertibleModule):
     def forward(self, x, rev=False, jac=True):
         if self.init_on_next_batch:
             self._initialize_with_data(x[0])
+        # the C-element parameter algebra (exp, reciprocal) is host-level glue on torch's tape; the per-element pass and its
+        # adjoint (dx, d scale, d bias) are the scale_shift kernels (cwfa_b200.autograd._ScaleShift)
         j = (self.scale.sum() * np.prod(self.dims_in[1:])).repeat(x[0].shape[0])
-        e = self.scale.detach().reshape(-1).exp()
-        b = self.bias.detach().reshape(-1)
+        e = self.scale.reshape(-1).exp()
+        b = self.bias.reshape(-1)
         if not rev:
             return [ops.scale_shift(x[0], e, b)], j
         return [ops.scale_shift(x[0], 1.0 / e, -b / e)], -j
@@ -580,18 +607,20 @@ class AllInOneBlock(InvertibleModule):
         if self.GIN:
             scale, perm_log_jac = None, 0.0
         else:
-            scale = self.global_scale_activation(self.global_scale).detach().reshape(-1)
+            scale = self.global_scale_activation(self.global_scale).reshape(-1)
             perm_log_jac = torch.sum(torch.log(scale))
-        off = self.global_offset.detach().reshape(-1)
+        off = self.global_offset.reshape(-1)
+        # differentiable end to end: scale_shift and the 1x1 channel mixing have adjoint kernels (global_scale, global_offset
+        # and -- through the Householder product -- vk_householder receive gradients, as in the reference)
         if rev:
-            y = ops.conv2d(x, self.w_perm_inv.detach(), None)
+            y = ops.conv2d(x, self.w_perm_inv, None)
             return (ops.scale_shift(y, torch.ones_like(off) if scale is None else 1.0 / scale, -off if scale is None else -off / scale),
                     perm_log_jac)
         y = ops.scale_shift(x, torch.ones_like(off) if scale is None else scale, off)
-        return ops.conv2d(y, self.w_perm.detach(), None), perm_log_jac
+        return ops.conv2d(y, self.w_perm, None), perm_log_jac
 
     def _pre_permute(self, x, rev=False):
-        return ops.conv2d(x, (self.w_perm if rev else self.w_perm_inv).detach(), None)
+        return ops.conv2d(x, self.w_perm if rev else self.w_perm_inv, None)
 
     def _affine(self, x, a, rev=False):
         ch = x.shape[1]

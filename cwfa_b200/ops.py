@@ -44,14 +44,10 @@ def _grad_on(*tensors) -> bool:
     return torch.is_grad_enabled() and any(torch.is_tensor(t) and t.requires_grad for t in tensors)
 
 
-_warned = set()
-
-
 def _no_adjoint(what: str) -> None:
-    if what not in _warned:
-        _warned.add(what)
-        import warnings
-        warnings.warn(f"cwfa_b200: {what} has no adjoint kernel yet; its output is detached from the autograd graph")
+    """An op without an adjoint kernel was reached while an input requires a gradient.  Silently detaching would cut the
+    parameters upstream off from the loss (they would then drift under weight decay / partial gradients): refuse."""
+    raise NotImplementedError(f"cwfa_b200: {what} has no adjoint kernel; run it under torch.no_grad() or detach its inputs explicitly")
 
 
 def perm_i32(perm: torch.Tensor, device) -> torch.Tensor:
@@ -306,7 +302,8 @@ def batchnorm(x: torch.Tensor, gamma, beta, running_mean=None, running_var=None,
 def scale_shift(x: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor) -> torch.Tensor:
     """y[b,c,...] = x[b,c,...] * scale[c] + shift[c]  (ActNorm / global affine of AllInOneBlock)."""
     if _grad_on(x, scale, shift):
-        _no_adjoint("scale_shift")
+        from . import autograd as ag
+        return ag.scale_shift(x, scale, shift)
     x = _ck(x, "x")
     N, C = x.shape[0], x.shape[1]
     P = x[0, 0].numel()
@@ -362,6 +359,19 @@ def sum_squares(x: torch.Tensor) -> torch.Tensor:
     ws = torch.empty(2 * B * _lib.load().cwfa_stats_workspace_blocks(), device=x.device, dtype=torch.float32)
     _lib.call("cwfa_channel_stats_f32", x.data_ptr(), stats.data_ptr(), ws.data_ptr(), 1, B, n, _stream())
     return stats[B:]
+
+
+def batch_mean(x: torch.Tensor) -> torch.Tensor:
+    """Mean over the batch axis, keepdim: (K,...) -> (1,...) (the multi-sample average of CWFA.py:913-914), as K - 1 axpby passes."""
+    x = _ck(x, "x")
+    K = x.shape[0]
+    n = x[0].numel()
+    bufs = [torch.empty((1,) + tuple(x.shape[1:]), device=x.device, dtype=torch.float32) for _ in range(2 if K > 1 else 1)]
+    st = _stream()
+    _lib.call("cwfa_axpby_f32", x.data_ptr(), None, bufs[0].data_ptr(), 1.0 / K, 0.0, n, st)
+    for k in range(1, K):                                     # ping-pong: the kernel's operands are __restrict__
+        _lib.call("cwfa_axpby_f32", x.data_ptr() + 4 * k * n, bufs[(k - 1) & 1].data_ptr(), bufs[k & 1].data_ptr(), 1.0 / K, 1.0, n, st)
+    return bufs[(K - 1) & 1]
 
 
 def attention_gate_(x: torch.Tensor, m: torch.Tensor, v: torch.Tensor, att) -> torch.Tensor:

@@ -34,6 +34,16 @@ class CWFAConfig:
     n_views: int = 29
 
 
+def lrnn_mean_volume(mean_vols: Sequence[Optional[torch.Tensor]], n_levels: int) -> Optional[torch.Tensor]:
+    """The mean volume the LRNN receives.  The reference calls ``cond_nets[L-1](views, mean_vols_cache[n_net-1])`` (CWFA.py:882),
+    i.e. the mean-volume condition of the LAST flow level (index L-2), so a list with one entry per flow level -- the
+    reference's ``mean_vols_cache`` -- gives exactly that.  An explicit extra entry ``mean_vols[L-1]`` overrides it
+    (``None`` = run the LRNN without its mean-volume branch, ``Encoder(im)``, networks.py:581-582)."""
+    if len(mean_vols) > n_levels:
+        return mean_vols[n_levels]
+    return mean_vols[n_levels - 1] if n_levels >= 1 else None
+
+
 class CWFAModel(nn.Module):
     """``conv_inn[n]`` (flow level n, n < L-1), ``cond_nets[n]`` (conditioning nets, last one is the
     LRNN ``Encoder``) exactly as ``run_CWFA`` assembles them (CWFA.py:478-529)."""
@@ -46,8 +56,6 @@ class CWFAModel(nn.Module):
                 raise TypeError(f"unknown config field {k!r}")
             setattr(cfg, k, v)
         self.cfg = cfg
-        if cfg.disable_low_res_input:
-            raise NotImplementedError("disable_low_res_input=1 is not wired in the pipeline driver")
         if seed is not None:
             torch.manual_seed(seed)
             np.random.seed(seed)
@@ -64,7 +72,7 @@ class CWFAModel(nn.Module):
                 st_subnet=networks.wavelet_flow_subnetwork2D, conditional_network=ctor,
                 n_internal_ch=cfg.INN_internal_chans, n_down_steps=ix + 1,
                 use_permutations=cfg.INN_use_perm == 1, block_type=cfg.INN_block_type,
-                n_blocks=cfg.INN_n_blocks, disable_low_res_input=False)
+                n_blocks=cfg.INN_n_blocks, disable_low_res_input=bool(cfg.disable_low_res_input))
             self.conv_inn.append(graphs[ix])
             self.cond_nets.append(cn)
         self.cond_nets.append(networks.Encoder(cfg.n_views, D // 2 ** (L - 1), L, cfg.INN_internal_chans,
@@ -78,37 +86,68 @@ class CWFAModel(nn.Module):
         return len(self.conv_inn)
 
     # ---- inverse reconstruction (CWFA.py:865-924) -------------------------------------------
+    def level_conditions(self, n: int, views: torch.Tensor, mean_vols: Sequence[Optional[torch.Tensor]], low_res: torch.Tensor):
+        """The condition list of flow level n as the reference's driver assembles it (CWFA.py:891-901):
+        ``[cond_net(views), mean_vols_cache[n]]``, or -- with ``disable_low_res_input=1`` -- the single condition
+        ``[low_res]`` (the volume of the level below: the previous up-sampled reconstruction in the inverse loop)."""
+        if self.cfg.disable_low_res_input:
+            return [low_res]
+        return [self.cond_nets[n](views)[-1], mean_vols[n]]
+
     @torch.no_grad()
     def reconstruct(self, views: torch.Tensor, mean_vols: Sequence[Optional[torch.Tensor]],
-                    zs: Optional[Sequence[torch.Tensor]] = None, return_all: bool = False):
+                    zs: Optional[Sequence[torch.Tensor]] = None, return_all: bool = False,
+                    n_samples: int = 1, temperature: Optional[float] = None):
         """views (B,29,S,S) normalised lenslet views; mean_vols[n] the mean-volume delta condition of
-        level n (n < L-1) and optionally mean_vols[L-1] the LRNN's mean volume.  z = 0 unless ``zs``
-        is given (INN_z_temperature = 0, CWFA.py:906-907)."""
+        level n (n < L-1) -- the reference's ``mean_vols_cache``; the LRNN receives ``mean_vols[L-2]`` as in CWFA.py:882
+        unless an extra entry ``mean_vols[L-1]`` (a tensor, or None for no mean-volume branch) is supplied
+        (``lrnn_mean_volume``).  z = 0 unless ``zs`` is given or ``temperature`` (default ``cfg.INN_z_temperature`` = 0,
+        CWFA.py:906-907) is non-zero, in which case z ~ ``sample_z_truncated``.
+
+        ``n_samples`` > 1 at batch 1 is the reference's multi-sample path (``INN_n_samples``, CWFA.py:903-914): every level
+        runs on ``n_samples`` copies of (low-res volume, conditions) with independent z and the level output is the mean over
+        the samples.  ``zs[n]`` then has ``n_samples`` rows."""
         L1 = self.n_levels
-        mv_last = mean_vols[L1] if len(mean_vols) > L1 else None
+        T = self.cfg.INN_z_temperature if temperature is None else temperature
+        if n_samples > 1 and views.shape[0] != 1:
+            raise ValueError("n_samples > 1 needs batch size 1 (CWFA.py:904: n_samples = INN_n_samples if batch_size == 1 else 1)")
+        mv_last = lrnn_mean_volume(mean_vols, L1)
         vol = self.cond_nets[L1](views, mv_last)[-1]
         outs, jacs = {L1: vol}, {}
         for n in range(L1 - 1, -1, -1):
-            c0 = self.cond_nets[n](views)[-1]
             inn = self.conv_inn[n]
-            if zs is None:
-                z = torch.zeros((vol.shape[0],) + tuple(inn.global_out_shapes[0]), device=vol.device, dtype=vol.dtype)
-            else:
+            conds = self.level_conditions(n, views, mean_vols, vol)
+            rows = vol.shape[0] * n_samples
+            if zs is not None and zs[n] is not None:
                 z = zs[n]
-            vol, jac = inn([z, vol], c=[c0, mean_vols[n]], rev=True)
+            else:
+                z = sample_z_truncated((rows,) + tuple(inn.global_out_shapes[0]), device=vol.device, temperature=T)
+            if n_samples > 1:
+                vol = vol.repeat(n_samples, 1, 1, 1)
+                conds = [c.repeat(n_samples, 1, 1, 1) for c in conds]
+            vol, jac = inn([z, vol], c=conds, rev=True)
+            if n_samples > 1:
+                vol = ops.batch_mean(vol)                               # upsampled_vol.mean(0).unsqueeze(0), CWFA.py:913-914
             outs[n], jacs[n] = vol, jac
         return (outs, jacs) if return_all else vol
 
     # ---- forward pyramid + NLL (CWFA.py:156-196, :966-978) -------------------------------------
     @torch.no_grad()
-    def forward_nll(self, volume: torch.Tensor, views: torch.Tensor, mean_vols: Sequence[torch.Tensor]):
+    def forward_nll(self, volume: torch.Tensor, views: torch.Tensor, mean_vols: Sequence[torch.Tensor],
+                    low_res_conditions: Optional[Sequence[torch.Tensor]] = None):
         """Per level: z, lo, logdet[B], sumsq[B], nll_per_sample[B] = (0.5*sumsq - logdet)/(ch*P) and the
-        reference's batch-coupled ``nll_ref`` = (0.5*||Z||^2_batch - logdet)/lo.numel() (CWFA.py:183-189)."""
+        reference's batch-coupled ``nll_ref`` = (0.5*||Z||^2_batch - logdet)/lo.numel() (CWFA.py:183-189).
+        With ``disable_low_res_input=1`` the single condition of level n is ``low_res_conditions[n]`` (what the training step
+        passes: the reconstruction of the level below, CWFA.py:900-901,966); by default the volume's own low-resolution half."""
         res = []
         x = volume
         for n in range(self.n_levels):
-            c0 = self.cond_nets[n](views)[-1]
-            (z, lo), jac = self.conv_inn[n](x, c=[c0, mean_vols[n]])
+            if self.cfg.disable_low_res_input:
+                given = low_res_conditions[n] if low_res_conditions is not None and n < len(low_res_conditions) else None
+                conds = [given if given is not None else ops.haar1d_split(x)[0]]
+            else:
+                conds = self.level_conditions(n, views, mean_vols, None)
+            (z, lo), jac = self.conv_inn[n](x, c=conds)
             sumsq = ops.sum_squares(z)
             per = (0.5 * sumsq - jac) / z[0].numel()
             ref = (0.5 * sumsq.sum() - jac) / lo.numel()

@@ -88,21 +88,28 @@ class FlatGroup:
     def zero_grad(self):
         self.grad.zero_()
         self.used = [False] * len(self.params)
+        for p, o in zip(self.params, self.offsets):           # a foreign ``zero_grad(set_to_none=True)`` may have dropped the views
+            if p.grad is None or p.grad.data_ptr() != self.grad.data_ptr() + 4 * o:
+                p.grad = self.grad[o:o + p.numel()].view(p.shape)
         for p in self.loose:
             p.grad = None
 
     def grads_alias_flat(self) -> bool:
         """Autograd accumulates in place into a pre-existing ``.grad``; if anything replaced one, copy it back."""
         ok = True
-        for p, o in zip(self.params, self.offsets):
+        for i, (p, o) in enumerate(zip(self.params, self.offsets)):
             g = p.grad
             view = self.grad[o:o + p.numel()]
             if g is None:
+                # ``model.zero_grad()`` / ``p.grad = None`` (torch's set_to_none default) detached the parameter from the flat
+                # buffer: no gradient this step; re-home ``.grad`` so the next backward accumulates into the buffer again
                 view.zero_()
+                p.grad = view.view(p.shape)
+                ok = False
             elif g.data_ptr() != view.data_ptr():
                 view.copy_(g.reshape(-1))
                 p.grad = view.view(p.shape)
-                self.used[self.params.index(p)] = True        # a gradient tensor was assigned by hand
+                self.used[i] = True                            # a gradient tensor was assigned by hand (or re-allocated by autograd)
                 ok = False
         return ok
 
@@ -278,8 +285,8 @@ def fine_tune_flow_levels(model, frames: Sequence[dict], levels: Optional[Sequen
     (index L-1, when listed in ``levels``) through the coarsest flow (L-2) to the finest (0); while a flow level trains, its input
     volume per frame comes from the cache filled by the step below it (``upsampled_cache``, CWFA.py:748-750,919-920).
 
-    frames: dicts with ``views`` (1,29,S,S), ``gt`` (1,D,S,S) and ``mean_vols`` (list, level n -> (1,C_n/2,S,S); optional last
-    entry = the LRNN's mean volume).  ``levels`` defaults to the flow levels; add ``L-1`` to also run the LRNN step first.
+    frames: dicts with ``views`` (1,29,S,S), ``gt`` (1,D,S,S) and ``mean_vols`` (list, level n -> (1,C_n/2,S,S) = the reference's
+    ``mean_vols_cache``; the LRNN gets its last entry as in CWFA.py:882 unless an extra entry -- tensor or None -- is appended).  ``levels`` defaults to the flow levels; add ``L-1`` to also run the LRNN step first.
     Returns ({step: [loss per optimiser step]}, per-frame cache of the finest reconstruction)."""
     L1 = model.n_levels
     levels = list(range(L1 - 1, -1, -1)) if levels is None else list(levels)
@@ -289,7 +296,8 @@ def fine_tune_flow_levels(model, frames: Sequence[dict], levels: Optional[Sequen
             _, gtc, _, _ = model.evaluate_INN_forward(f["gt"], extra_cond_in=f["mean_vols"], fix_empty_depths=False)   # GT pyramid
             gt_caches.append(gtc)
     history = {}
-    mv_last = lambda f: f["mean_vols"][L1] if len(f["mean_vols"]) > L1 else None
+    from .pipeline import lrnn_mean_volume
+    mv_last = lambda f: lrnn_mean_volume(f["mean_vols"], L1)          # CWFA.py:882: mean_vols_cache[L-2] unless given explicitly
     if L1 in levels:                                           # the "last step": LRNN on the coarsest ground truth
         lt = LRNNTrainer(model, lr=lr_first_step, weight_decay=weight_decay, group=group, precision=precision)
         history[L1] = []

@@ -144,14 +144,26 @@ def subnet(sd: SD, pre: str, inp: Tensor, normal: bool) -> Tensor:
     return torch.cat((b7, -low / math.sqrt(2)), 1)
 
 
-def affine(x: Tensor, a: Tensor, rev: bool, clamp: float = CLAMP) -> Tuple[Tensor, Tensor]:
-    """s = clamp * 0.636 * atan(a[:, :ch]); t = a[:, ch:]; coupling_layers.py:490-500.
+def f_clamp(u: Tensor, act="ATAN") -> Tensor:
+    """Clamp activations of _BaseCouplingBlock, coupling_layers.py:50-60: ATAN -> 0.636 atan(u), TANH -> tanh(u),
+    SIGMOID -> 2 (sigmoid(u) - 0.5); anything else is the user's callable."""
+    if act == "ATAN":
+        return K_ATAN * torch.atan(u)
+    if act == "TANH":
+        return torch.tanh(u)
+    if act == "SIGMOID":
+        return 2.0 * (torch.sigmoid(u) - 0.5)
+    return act(u)
+
+
+def affine(x: Tensor, a: Tensor, rev: bool, clamp: float = CLAMP, act="ATAN") -> Tuple[Tensor, Tensor]:
+    """s = clamp * f_clamp(a[:, :ch]) (0.636 atan by default); t = a[:, ch:]; coupling_layers.py:490-500.
 
     fwd: y = exp(s) * x + t, J = +sum(s);  rev: y = (x - t) * exp(-s), J = -sum(s).
     """
     ch = x.shape[1]
     s, t = a[:, :ch], a[:, ch:]
-    s = clamp * (K_ATAN * torch.atan(s))
+    s = clamp * f_clamp(s, act)
     j = torch.sum(s, dim=tuple(range(1, x.dim())))
     if rev:
         return (x - t) * torch.exp(-s), -j
@@ -159,15 +171,15 @@ def affine(x: Tensor, a: Tensor, rev: bool, clamp: float = CLAMP) -> Tuple[Tenso
 
 
 def cat_block(sd: SD, pre: str, x: Tensor, conds: Sequence[Tensor], rev: bool,
-              first: bool) -> Tuple[Tensor, Tensor]:
+              first: bool, clamp: float = CLAMP, act="ATAN") -> Tuple[Tensor, Tensor]:
     """ConditionalAffineTransform.forward, coupling_layers.py:475-500."""
     cond = torch.cat(list(conds), 1) if len(conds) > 1 else conds[0]
     a = subnet(sd, pre + "subnet.", cond, normal=not first)
-    return affine(x, a, rev)
+    return affine(x, a, rev, clamp, act)
 
 
 def glow_block(sd: SD, pre: str, x: Tensor, conds: Sequence[Tensor], rev: bool,
-               kind: str = "GLOW") -> Tuple[Tensor, Tensor]:
+               kind: str = "GLOW", clamp: float = CLAMP, act="ATAN") -> Tuple[Tensor, Tensor]:
     """_BaseCouplingBlock.forward + GLOW/GIN/RNVP couplings.  coupling_layers.py:62-87,
     :160-229 (RNVP), :232-302 (GLOW), :305-381 (GIN)."""
     l1 = x.shape[1] // 2
@@ -182,7 +194,7 @@ def glow_block(sd: SD, pre: str, x: Tensor, conds: Sequence[Tensor], rev: bool,
         else:
             a = subnet(sd, f"{pre}subnet{which}.", u, True)
             s, t = a[:, :n_out], a[:, n_out:]
-        s = CLAMP * (K_ATAN * torch.atan(s))
+        s = clamp * f_clamp(s, act)
         if kind == "GIN":
             s = s - s.mean(1, keepdim=True)
             return s, t, 0.0
@@ -350,30 +362,43 @@ def lrnn(sd: SD, views: Tensor, mean_vol: Optional[Tensor] = None, bn_mode: str 
 # ----------------------------------------------------------------------------------------
 def reconstruct(model: dict, views: Tensor, mean_vols: Sequence[Optional[Tensor]],
                 zs: Optional[Sequence[Tensor]] = None, bn_mode: str = "batch",
-                return_all: bool = False):
+                return_all: bool = False, disable_low_res_input: bool = False, n_samples: int = 1):
     """Inverse reconstruction, CWFA.py:865-924: LRNN low-res volume, then each flow level
     n = L-1 .. 0 with z = 0 (INN_z_temperature = 0, CWFA.py:906-907).
 
     model = {"levels": [{"inn": sd, "cond": sd, "spec": spec}, ...], "lrnn": sd}
-    mean_vols[n] is the mean-volume delta condition of level n (n < L) and mean_vols[L]
-    (may be None) the LRNN's mean volume (CWFA.py:882 passes mean_vols_cache[n_net-1]).
+    mean_vols[n] is the mean-volume delta condition of level n (n < L).  The LRNN receives
+    mean_vols[L-1] -- CWFA.py:882 passes mean_vols_cache[n_net-1], the last flow level's condition --
+    unless an explicit extra entry mean_vols[L] (tensor, or None = no mean-volume branch) is given.
+    disable_low_res_input: the level's single condition is the previous up-sampled volume (CWFA.py:899-901).
+    n_samples > 1 (batch 1): n_samples copies of (z, low-res volume, conditions), mean over the samples (CWFA.py:903-914).
     """
     levels = model["levels"]
     L = len(levels)
-    vol = lrnn(model["lrnn"], views, mean_vols[L] if len(mean_vols) > L else None, bn_mode)
+    mv_last = mean_vols[L] if len(mean_vols) > L else mean_vols[L - 1]
+    vol = lrnn(model["lrnn"], views, mv_last, bn_mode)
     outs = {L: vol}
     jacs = {}
     for n in range(L - 1, -1, -1):
         lv = levels[n]
-        c_lf = cond_network(lv["cond"], views)
-        z = torch.zeros_like(vol) if zs is None else zs[n]
-        vol, jac = level_inverse(lv["inn"], lv["spec"], z, vol, c_lf, mean_vols[n])
+        if disable_low_res_input:
+            c_lf, c_mean = vol, None                          # cond_processed = [upsampled_vol]
+        else:
+            c_lf, c_mean = cond_network(lv["cond"], views), mean_vols[n]
+        if n_samples > 1:
+            rep = lambda t: None if t is None else t.repeat(n_samples, 1, 1, 1)
+            vol, c_lf, c_mean = rep(vol), rep(c_lf), rep(c_mean)
+        z = torch.zeros_like(vol) if zs is None or zs[n] is None else zs[n]
+        vol, jac = level_inverse(lv["inn"], lv["spec"], z, vol, c_lf, c_mean)
+        if n_samples > 1:
+            vol = vol.mean(0).unsqueeze(0)
         outs[n] = vol
         jacs[n] = jac
     return (outs, jacs) if return_all else vol
 
 
-def forward_nll(model: dict, volume: Tensor, views: Tensor, mean_vols: Sequence[Tensor]):
+def forward_nll(model: dict, volume: Tensor, views: Tensor, mean_vols: Sequence[Tensor],
+                disable_low_res_input: bool = False, low_res_conditions: Optional[Sequence[Tensor]] = None):
     """Forward pyramid with REAL conditions + per-level NLL (CWFA.py:966-978; pyramid
     structure of evaluate_INN_forward, CWFA.py:156-196).
 
@@ -381,18 +406,51 @@ def forward_nll(model: dict, volume: Tensor, views: Tensor, mean_vols: Sequence[
     nll_per_sample[B] = (0.5*sumsq_b - logdet_b) / (ch*P),
     nll_ref = the reference's batch-coupled formula (0.5*||Z||^2 - logdet) / Z[-1].numel()
     (CWFA.py:183-189: ||Z||^2 over the WHOLE batch, numel of the lo tensor incl. batch).
+    disable_low_res_input: single condition = low_res_conditions[n], default the volume's own low-resolution half.
     """
     res = []
     x = volume
-    for lv, mv in zip(model["levels"], mean_vols):
-        c_lf = cond_network(lv["cond"], views)
-        z, lo, jac = level_forward(lv["inn"], lv["spec"], x, c_lf, mv)
+    for n, lv in enumerate(model["levels"]):
+        if disable_low_res_input:
+            given = low_res_conditions[n] if low_res_conditions is not None and n < len(low_res_conditions) else None
+            c_lf = given if given is not None else haar1d(x)[0][:, :x.shape[1] // 2]
+            c_mean = None
+        else:
+            c_lf, c_mean = cond_network(lv["cond"], views), mean_vols[n]
+        z, lo, jac = level_forward(lv["inn"], lv["spec"], x, c_lf, c_mean)
         sumsq = (z.double() ** 2).flatten(1).sum(1).to(z.dtype)
         per = (0.5 * sumsq - jac) / z[0].numel()
         ref = (0.5 * torch.norm(z) ** 2 - jac) / lo.numel()
         res.append(dict(z=z, lo=lo, logdet=jac, sumsq=sumsq, nll_per_sample=per, nll_ref=ref))
         x = lo
     return res
+
+
+def sequence_inn(sd: SD, steps: Sequence[dict], x: Tensor, conds: Sequence[Tensor], rev: bool = False):
+    """SequenceINN.forward, FrEIA/framework/sequence_inn.py:68-99: modules applied in order (reversed for rev), log-dets summed.
+    ``steps[i]`` = {"type": perm_chan | GLOW | GIN | RNVP | cat | haar1d | haar2d, "cond": index or None, ...}; the
+    parameters of module i live under ``module_list.{i}.`` as in the reference's state_dict."""
+    jac = 0
+    order = range(len(steps))
+    for i in (reversed(order) if rev else order):
+        st = steps[i]
+        pre = f"module_list.{i}."
+        c = [] if st.get("cond") is None else [conds[st["cond"]]]
+        t = st["type"]
+        if t == "perm_chan":
+            x, j = permute_random(x, sd[pre + "perm"], sd[pre + "perm_inv"], rev), 0.0
+        elif t in ("GLOW", "GIN", "RNVP"):
+            x, j = glow_block(sd, pre, x, c, rev, t, st.get("clamp", CLAMP), st.get("act", "ATAN"))
+        elif t == "cat":
+            x, j = cat_block(sd, pre, x, c, rev, first=False, clamp=st.get("clamp", CLAMP), act=st.get("act", "ATAN"))
+        elif t == "haar1d":
+            x, j = haar1d(x, rev)
+        elif t == "haar2d":
+            x, j = haar2d(x, rev, st.get("order_by_wavelet", False), st.get("rebalance", 1.0))
+        else:
+            raise ValueError(t)
+        jac = j + jac
+    return x, jac
 
 
 # ----------------------------------------------------------------------------------------

@@ -25,7 +25,7 @@ def test_engine_inverse_vs_reference(golden_tiny, model, kind, bn_mode, use_mv):
     from cwfa_b200.engine import CWFAEngine
     views, mean_vols = tiny_inputs(golden_tiny)
     L = model.n_levels
-    mv = [t.to(DEV) for t in mean_vols[:L]] + ([mean_vols[L].to(DEV)] if use_mv else [])
+    mv = [t.to(DEV) for t in mean_vols[:L]] + ([mean_vols[L].to(DEV)] if use_mv else [None])
     model.cond_nets[-1].train(bn_mode == "batch")
     eng = CWFAEngine(model, kind)
     outs, jacs = eng.reconstruct(views.to(DEV), mv, return_all=True)

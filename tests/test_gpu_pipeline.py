@@ -22,7 +22,7 @@ def model(golden_tiny):
 def test_inverse_reconstruction_vs_reference(golden_tiny, model, bn_mode, use_mv):
     views, mean_vols = tiny_inputs(golden_tiny)
     L = model.n_levels
-    mv = [t.to(DEV) for t in mean_vols[:L]] + ([mean_vols[L].to(DEV)] if use_mv else [])
+    mv = [t.to(DEV) for t in mean_vols[:L]] + ([mean_vols[L].to(DEV)] if use_mv else [None])
     model.cond_nets[-1].train(bn_mode == "batch")
     outs, jacs = model.reconstruct(views.to(DEV), mv, return_all=True)
     model.cond_nets[-1].train()

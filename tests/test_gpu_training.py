@@ -470,15 +470,54 @@ def test_unet_ops_adjoints():
         assert rel_l2(a_.grad, c_.grad) < TOL
 
 
-@pytest.mark.parametrize("kind,tol_all,tol_each", [("fp32", 5e-3, 5e-2), ("fp16", 1e-1, 1.0), ("bf16", 3e-1, 2.0)])
-def test_lrnn_step_gradients_vs_oracle_and_reference(golden_tiny, golden_train, kind, tol_all, tol_each):
-    """Reference for the comparison: the oracle evaluated in float64.  The U-Net gradient is ill-conditioned in fp32 (max-pool
-    arg-max and PReLU kinks flip on 1e-7 perturbations of the activations; BatchNorm over 512 samples at the deepest level): the
+def test_zero_grad_set_to_none_between_steps(golden_tiny, golden_train):
+    """``model.zero_grad()`` (set_to_none=True is torch's default) drops the ``.grad`` views of the flat buffer; the next
+    backward then allocates fresh gradient tensors.  The optimiser must pick those up (and re-home them) instead of crashing or
+    stepping on zeros: the run must equal one that never called ``model.zero_grad()``, bit for bit."""
+    from cwfa_b200.training import FlowLevelTrainer
+    inputs = [t.to(DEV) for t in train_inputs(golden_train, 1)]
+    runs = []
+    for foreign_zero in (False, True):
+        model = build_tiny_model(golden_tiny, DEV)
+        tr = FlowLevelTrainer(model, 1, lr=2e-4, lr_cond=2e-4)
+        losses = []
+        for _ in range(3):
+            if foreign_zero:
+                model.zero_grad()                                   # sets every p.grad to None
+                assert model.conv_inn[1].module_list[2].subnet.block2[0].weight.grad is None
+            losses.append(float(tr.step(*inputs)["loss"]))
+        runs.append((losses, torch.cat([p.detach().reshape(-1) for p in model.conv_inn[1].parameters() if p.requires_grad]).clone()))
+        tr.release()
+    assert runs[0][0] == runs[1][0] and torch.equal(runs[0][1], runs[1][1])
+
+
+def _grad_errors(ours, ref):
+    """(total rel-L2 over all tensors, {key: rel-L2}, |g|-weighted fraction of entries whose SIGN agrees -- the only thing the
+    Lion update consumes at the first step: sign(b1 m + (1 - b1) g) with m = 0)."""
+    num = den = agree = weight = 0.0
+    per = {}
+    for k, r in ref.items():
+        v, r = ours[k].double().cpu(), r.double()
+        d, b_ = (v - r).norm().item(), r.norm().item()
+        num, den = num + d * d, den + b_ * b_
+        per[k] = d / b_ if b_ > 0 else 0.0
+        w = r.abs()
+        agree += float((w * (torch.sign(v) == torch.sign(r))).sum())
+        weight += float(w.sum())
+    return (num / den) ** 0.5, per, agree / weight
+
+
+@pytest.mark.parametrize("kind", ["fp32", "fp16", "bf16"])
+def test_lrnn_step_gradients_vs_oracle_and_reference(golden_tiny, golden_train, kind):
+    """Reference for the comparison: the oracle evaluated in float64.  The U-Net gradient is ill-conditioned (max-pool arg-max
+    and PReLU kinks flip on tiny perturbations of the activations; BatchNorm over 512 samples at the deepest level): the
     oracle's OWN fp32 run differs from its fp64 run by 1.4e-3 rel-L2 over all gradients (worst tensor 8.4e-3), which sets the
-    scale of the stated tolerances (fp32: 5e-3 / 5e-2).  With half-precision operands the same amplification acts on 1e-3 / 4e-3
-    perturbations: the error grows layer by layer from the output (measured fp16 4.7e-3 at the last conv -> 6e-2 at the first,
-    bf16 1.4e-2 -> 1.7e-1; worst tensors are PReLU slopes, scalars with cancellation), so those rows only bound the total
-    (fp16 1e-1, bf16 3e-1) and pin the output layer (3e-2); the deterministic-fill weights of the fixture are a worst case."""
+    fp32 tolerances (5e-3 / 5e-2).  For the half-precision modes the yardstick is computed, not assumed: the float64 oracle is
+    re-run with every convolution operand (input, weight, output cotangent) rounded to fp16 / bf16 (tests/helpers.py:
+    half_operand_emulation) -- the error the ARITHMETIC TYPE causes on this network (fp16 ~5e-2 total, bf16 ~1.3e-1 on the
+    deterministic-fill fixture, a worst case).  The tensor-core kernels must stay within 2x of that in total, within 4x per
+    tensor (floor: the emulation's total), and agree with float64 on the gradient SIGNS -- all Lion consumes -- as often as
+    the emulation does (minus 2 %)."""
     from cwfa_b200 import autograd as ag
     from cwfa_b200.training import lrnn_loss
     cfg, g = golden_train["config"], golden_train["lrnn"]
@@ -499,24 +538,28 @@ def test_lrnn_step_gradients_vs_oracle_and_reference(golden_tiny, golden_train, 
     sd64 = {k: (v.double() if v.dtype.is_floating_point else v) for k, v in om["lrnn"].items()}
     r = O.lrnn_train_grads(sd64, views.double(), gt.double())
     assert set(ours) == set(r["grads"]) == set(g["grads"])
-    num = den = 0.0
-    worst = ("", 0.0)
-    for k, v in ours.items():
-        d = (v.double().cpu() - r["grads"][k].double()).norm().item()
-        b_ = r["grads"][k].double().norm().item()
-        num, den = num + d * d, den + b_ * b_
-        if b_ > 0 and d / b_ > worst[1]:
-            worst = (k, d / b_)
-    total = (num / den) ** 0.5
+    total, per, signs = _grad_errors(ours, r["grads"])
+    worst = max(per.items(), key=lambda kv: kv[1])
     probe_keys = ["net.deconv.1.last.0.weight", "net.deconv.1.up_path.1.conv_block.block.3.weight", "net.deconv.1.up_path.1.up.weight",
                   "net.deconv.1.down_path.2.block.0.weight", "net.deconv.1.down_path.0.block.0.weight", "net.deconv.0.weight"]
-    print({k.replace("net.deconv.", ""): f"{rel_l2(ours[k], r['grads'][k]):.1e}" for k in probe_keys})
-    assert rel_l2(ours["net.deconv.1.last.0.weight"], r["grads"]["net.deconv.1.last.0.weight"]) < (1e-4 if kind == "fp32" else 3e-2)
-    print(f"LRNN step {kind}: loss {float(loss):.6f} (reference {float(g['loss']):.6f}); gradients rel-L2 all {total:.2e}, worst {worst[1]:.2e} at {worst[0]}")
+    print({k.replace("net.deconv.", ""): f"{per[k]:.1e}" for k in probe_keys})
+    print(f"LRNN step {kind}: loss {float(loss):.6f} (reference {float(g['loss']):.6f}); gradients vs float64 oracle: rel-L2 all {total:.2e}, "
+          f"worst {worst[1]:.2e} at {worst[0]}, |g|-weighted sign agreement {signs:.4f}")
+    assert per["net.deconv.1.last.0.weight"] < (1e-4 if kind == "fp32" else 3e-2)
     assert abs(float(loss) - float(g["loss"])) < (1e-4 if kind == "fp32" else 2e-2) * abs(float(g["loss"]))
-    assert total < tol_all and worst[1] < tol_each, (total, worst)
     if kind == "fp32":
+        assert total < 5e-3 and worst[1] < 5e-2 and signs > 0.999, (total, worst, signs)
         check_against_golden({k: v.cpu() for k, v in ours.items()}, g["grads"], 5e-2)
+        return
+    from helpers import half_operand_emulation
+    with half_operand_emulation(kind):
+        emu = O.lrnn_train_grads(sd64, views.double(), gt.double())
+    e_total, e_per, e_signs = _grad_errors(emu["grads"], r["grads"])
+    print(f"  float64 oracle with {kind}-rounded conv operands: rel-L2 all {e_total:.2e}, worst {max(e_per.values()):.2e}, sign agreement {e_signs:.4f}")
+    assert total < 2.0 * e_total, (total, e_total)
+    bad = {k: (v, e_per[k]) for k, v in per.items() if v > 4.0 * max(e_per[k], e_total)}
+    assert not bad, bad
+    assert signs > e_signs - 0.02, (signs, e_signs)
 
 
 def test_lrnn_trainer_reduces_loss(golden_tiny, golden_train):
