@@ -7,7 +7,8 @@ Drop-in surface (same names / signatures / state_dict keys as the reference, pvj
     cwfa_b200.pipeline   ~ the ~40 lines of CWFA.py that drive the flow (reconstruct / forward NLL)
 All arithmetic runs in hand-written CUDA kernels behind the C ABI in include/cwfa_b200.h.
 """
-from . import _lib, data, framework, modules, networks, ops  # noqa: F401
+from . import _lib, data, framework, modules, networks, ops, packed  # noqa: F401
+from .packed import inference_precision, set_inference_precision, weights_changed  # noqa: F401
 from .pipeline import CWFAModel, CWFAConfig  # noqa: F401
 
 __version__ = "0.1.0"

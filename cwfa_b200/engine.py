@@ -23,174 +23,20 @@ from . import networks, ops, tc
 from .pipeline import CWFAModel, lrnn_mean_volume
 
 
-class _Subnet:
-    """Packed weights of one wavelet_flow_subnetwork2D(_first) (networks.py:586-706)."""
-
-    def __init__(self, sub, kind):
-        self.normal = sub.normal
-        first = sub.block12 if sub.normal else sub.block1
-        self.inp = tc.PackedConv(first.weight, first.bias, kind)
-        self.res = []
-        for name in ("block2", "block4", "block6"):
-            blk = getattr(sub, name)
-            self.res.append((tc.PackedConv(blk[0].weight, blk[0].bias, kind), tc.PackedConv(blk[2].weight, blk[2].bias, kind)))
-        last = sub.block72[1] if sub.normal else sub.block7[1]
-        self.out = tc.PackedConv(last.weight, last.bias, kind, bn=tc.pad16(last.weight.shape[0]))   # one N block: s and t in one CTA
-
-    def trunk(self, lf8: tc.C8, b: Optional[tc.C8] = None, chunk_off: int = 0) -> tc.C8:
-        """LF condition (C8) -> ELU(b6) (C8, n hidden channels).  ``b`` (optional): precomputed output of the input
-        1x1 conv, possibly a slice (``chunk_off``) of the tensor produced by one batched conv over all
-        sub-networks of the level."""
-        if b is None:
-            b = tc.conv_tc(lf8, self.inp)
-        fused = self.inp.Cout_p == 64
-        for i, (p3, p1) in enumerate(self.res):
-            if fused:
-                b = tc.resblock_tc(b, p3, p1, chunk_off if i == 0 else 0)
-            else:
-                assert chunk_off == 0
-                t = tc.conv_tc(b, p3, act=ops.ACT_ELU)
-                b = tc.conv_tc(t, p1, act=ops.ACT_ELU, res=b, res_mode=1)
-        return b
-
-    def __call__(self, lf8: tc.C8) -> torch.Tensor:
-        """LF condition -> fp32 NCHW coefficient tensor (unfused path)."""
-        return tc.conv_tc(self.trunk(lf8), self.out, out_nchw=True)
-
-
-class _CondNet:
-    """cond_network / ResidualBlock (networks.py:165-242) entirely on the tensor cores.
-
-    The depth stencil Conv3d(1->Cm) -> PReLU -> Conv3d(Cm->1) over the (H, W, depth) volume
-    (networks.py:221-225,239) is executed as two ordinary 3x3 2-D convolutions whose channel axis
-    carries (depth, hidden-channel) and whose weights are the depth-banded expansion of the 3x3x3
-    kernels: W1[(d,c), d'] = w1[c, :, :, d'-d+1], W2[d, (d',c)] = w2[c, :, :, d'-d+1] for |d'-d| <= 1.
-    Zero padding in depth falls out of the band; zero padding in H, W is the conv's own padding."""
-
-    def __init__(self, net, kind):
-        rb = net.subnetworks[0]
-        self.rb = rb
-        self.c1 = tc.PackedConv(rb.conv1[0].weight, rb.conv1[0].bias, kind)
-        self.ds = tc.PackedConv(rb.downsample[0].weight, rb.downsample[0].bias, kind)
-        self.c2 = tc.PackedConv(rb.conv2[0].weight, rb.conv2[0].bias, kind)
-        w1, b1 = rb.conv3d[0].weight.detach().float(), rb.conv3d[0].bias.detach().float()      # (Cm,1,3,3,3), (Cm)
-        w2, b2 = rb.conv3d[3].weight.detach().float(), rb.conv3d[3].bias.detach().float()      # (1,Cm,3,3,3), (1)
-        Cm, D = w1.shape[0], rb.out_channels
-        dev = w1.device
-        W1 = torch.zeros(D, Cm, D, 3, 3, device=dev)          # [d, c, d', ky, kx]
-        W2 = torch.zeros(D, D, Cm, 3, 3, device=dev)          # [d, d', c, ky, kx]
-        for kd in range(3):
-            for d in range(D):
-                dp = d + kd - 1
-                if 0 <= dp < D:
-                    W1[d, :, dp] = w1[:, 0, :, :, kd]
-                    W2[d, dp] = w2[0, :, :, :, kd]
-        self.s1 = tc.PackedConv(W1.reshape(D * Cm, D, 3, 3), b1.repeat(D), kind)
-        # second stencil conv (Cin = 32 D, Cout = D): evaluated as ONE 1x1 conv to 9 tap partials per depth + a col2im
-        # sum -- the tap-by-tap form re-reads the 32 D-channel operand tile from shared memory nine times for a tiny N.
-        # n-blocks of 144 channels = 16 output depths: the packer's zero K-block masks skip the hidden depths out of reach.
-        Wg = tc.col2im3x3_weights(W2.reshape(D, D * Cm, 3, 3))
-        gp = tc.pad16(Wg.shape[0])
-        self.s2g = tc.PackedConv(Wg, None, kind, bn=144 if gp % 144 == 0 else gp)
-        self.s2_bias = torch.zeros(tc.pad16(D), device=dev, dtype=torch.float32)
-        self.s2_bias[:D] = b2
-        self.s2_mb = 1 if self.s2g.BN == 144 else 2       # measured (scripts/bench_stencil.py)
-        self.D = D
-
-    def __call__(self, v8: tc.C8) -> tc.C8:
-        """views (C8) -> LF condition (C8)."""
-        rb = self.rb
-        out = tc.conv_tc(v8, self.c1, act=ops.ACT_PRELU, slope=rb.conv1[1].weight)
-        res = tc.conv_tc(v8, self.ds)
-        out = tc.conv_tc(out, self.c2, act=ops.ACT_PRELU, slope=rb.relu.weight, res=res, res_mode=1)
-        hid = tc.conv_tc(out, self.s1, act=ops.ACT_PRELU, slope=rb.conv3d[1].weight)
-        return tc.col2im3x3_c8(tc.conv_tc(hid, self.s2g, mb=self.s2_mb), self.s2_bias, self.D)
-
-
-class _UNet:
-    """LRNN U-Net (unet.py:9-195) in C8: conv+PReLU on tensor cores, BatchNorm (+max-pool) fused passes."""
-
-    def __init__(self, unet, kind):
-        self.unet = unet
-
-        def block(b):
-            return [(tc.PackedConv(b.block[i].weight, b.block[i].bias, kind), b.block[i + 1], b.block[i + 2]) for i in (0, 3)]
-
-        self.down = [block(d) for d in unet.down_path]
-        # transposed convs: the deepest one (few tiles: 1.7 waves of 256-column items) runs better as 128-column,
-        # double-buffered items (measured: 131 -> 112 us, scripts/bench_convT.py)
-        self.up = [(tc.PackedConv(u.up.weight, u.up.bias, kind, transposed=True, bn=128 if u.up.weight.shape[0] >= 1024 else None),
-                    block(u.conv_block)) for u in unet.up_path]
-        self.last = tc.PackedConv(unet.last[0].weight, unet.last[0].bias, kind)
-
-    def _block(self, x, blk, training, pool):
-        (p0, a0, n0), (p1, a1, n1) = blk
-        x = tc.conv_tc(x, p0, act=ops.ACT_PRELU, slope=a0.weight)
-        x = tc.batchnorm_c8(x, n0.weight, n0.bias, n0.running_mean, n0.running_var, batch_stats=training, eps=n0.eps)
-        x = tc.conv_tc(x, p1, act=ops.ACT_PRELU, slope=a1.weight)
-        return tc.batchnorm_c8(x, n1.weight, n1.bias, n1.running_mean, n1.running_var, batch_stats=training, eps=n1.eps,
-                               pool=pool)
-
-    def __call__(self, x8: tc.C8) -> torch.Tensor:
-        training = self.unet.training
-        skips = []
-        nd = len(self.down)
-        for i, blk in enumerate(self.down):
-            if i != nd - 1:
-                full, x8 = self._block(x8, blk, training, True)
-                skips.append(full)
-            else:
-                x8 = self._block(x8, blk, training, False)
-        for i, (up, blk) in enumerate(self.up):
-            x8 = tc.conv_transpose_tc(x8, up, skips[-i - 1], mb=1 if up.BN == 128 else None)
-            x8 = self._block(x8, blk, training, False)
-        return tc.conv_tc(x8, self.last, act=ops.ACT_PRELU, slope=self.unet.last[1].weight, out_nchw=True)
-
-
-class _LRNN:
-    """Encoder/LRNN (networks.py:505-584)."""
-
-    def __init__(self, enc, kind):
-        net = enc.net
-        self.net = net
-        self.kind = kind
-        self.proj = tc.PackedConv(net.deconv[0].weight, net.deconv[0].bias, kind)
-        self.unet = _UNet(net.deconv[1], kind)
-        cn0, cn1 = net.conv3d[0], net.conv3d[1]
-        self.cn0_in = tc.PackedConv(cn0.input.weight, cn0.input.bias, kind)          # 1x1  6 -> 64
-        self.cn0_7x7 = tc.PackedConv(cn0.m[0].weight, cn0.m[0].bias, kind)           # 7x7 64 -> 64
-        self.cn0_1x1 = tc.PackedConv(cn0.m[2].weight, cn0.m[2].bias, kind)           # 1x1 64 -> 64
-        self.cn1_in = tc.PackedConv(cn1.input.weight, cn1.input.bias, kind)          # 1x1 64 -> 6
-        self.cn1_7x7 = tc.PackedConv(cn1.m[0].weight, cn1.m[0].bias, kind)           # 7x7  6 -> 6
-        # element-wise LayerNorm parameters of the wide ConvNeXt block in the activation layout (half the traffic)
-        self.cn0_ln_w = tc.to_c8(cn0.m[1].weight.detach().float()[None].contiguous(), kind)
-        self.cn0_ln_b = tc.to_c8(cn0.m[1].bias.detach().float()[None].contiguous(), kind)
-
-    def _mean_branch(self, mean_vol: torch.Tensor) -> torch.Tensor:
-        """conv3d = ConvNeXt(6,64) -> ConvNeXt(64,6) on the mean volume (networks.py:486-503,527-530): every conv on
-        the tensor cores (channels padded to 16); the 64-channel LayerNorm([C,H,W]) runs on the C8 tensor, the 6-channel
-        one and the final 6-channel 1x1 stay fp32."""
-        cn0, cn1 = self.net.conv3d[0], self.net.conv3d[1]
-        k = self.kind
-        up8 = tc.conv_tc(tc.to_c8(mean_vol, k), self.cn0_in)                                        # C8, 64 ch
-        m8 = tc.layernorm_c8(tc.conv_tc(up8, self.cn0_7x7), self.cn0_ln_w, self.cn0_ln_b, cn0.m[1].eps)
-        y8 = tc.conv_tc(m8, self.cn0_1x1, act=ops.ACT_GELU, res=up8, res_mode=2)                    # GELU(.) + up
-        up1_8 = tc.conv_tc(y8, self.cn1_in)                                                         # C8, 6 (16) ch
-        m1 = tc.conv_tc(up1_8, self.cn1_7x7, out_nchw=True)
-        m1 = ops.layernorm_chw(m1, cn1.m[1].weight, cn1.m[1].bias, cn1.m[1].eps)
-        return ops.conv2d(m1, cn1.m[2].weight, cn1.m[2].bias, act=ops.ACT_GELU, res=tc.from_c8(up1_8), res_mode=2)
-
-    def __call__(self, v8: tc.C8, mean_vol: Optional[torch.Tensor]) -> torch.Tensor:
-        x = self.unet(tc.conv_tc(v8, self.proj))
-        if mean_vol is not None:
-            x = ops.attention_gate_(x, self._mean_branch(mean_vol), mean_vol, self.net.attention_3d)
-        return x
+from .packed import _CondNet, _LRNN, _Subnet, _UNet  # noqa: F401  (executors shared with the module-API fast path)
 
 
 class CWFAEngine:
     """``engine = CWFAEngine(model); vol = engine.reconstruct(views, mean_vols)``.
 
-    The model's parameters are packed at construction; call ``refresh()`` after changing them."""
+    The model's parameters are packed at construction; call ``refresh()`` after changing them.
+
+    Every graph the reference's ``conditional_wavelet_flow`` can build runs here: ``ConditionalAffineTransform`` blocks (the
+    default, networks.py:289-297) use the fused trunk / coupling kernels; any other invertible block (GLOW / RNVP / GIN / AI1 /
+    ...) is executed through its own ``forward`` with the tensor-core inference switch on (``cwfa_b200.packed``: its sub-networks
+    run on tcgen05 and, where the clamp allows, with the coupling fused into the last convolution).
+    ``disable_low_res_input=1`` (networks.py:331-338, CWFA.py:899-901) makes the levels sequential: the condition of level n is
+    the volume reconstructed by level n+1."""
 
     def __init__(self, model: CWFAModel, kind: str = "bf16"):
         if kind not in ("bf16", "fp16"):
@@ -203,12 +49,13 @@ class CWFAEngine:
 
     def refresh(self):
         m, kind = self.model, self.kind
+        self.dlr = bool(m.cfg.disable_low_res_input)
         self.levels = []
         for n in range(m.n_levels):
             inn = m.conv_inn[n]
             nodes = []
             for mod in inn.module_list:
-                if isinstance(mod, Fm.ConditionalAffineTransform):
+                if isinstance(mod, Fm.ConditionalAffineTransform) and mod._clamp_kw is not None and not mod._clamp_kw["tanh_clamp"]:
                     nodes.append(("cat", mod, _Subnet(mod.subnet, kind)))
                 elif isinstance(mod, Fm.PermuteRandom):
                     nodes.append(("perm", mod, 1))
@@ -216,26 +63,26 @@ class CWFAEngine:
                     nodes.append(("perm", mod, mod.axis))
                 elif isinstance(mod, (Fm.HaarTransform1D, Fm.Split)):
                     continue
+                elif isinstance(mod, Fm.InvertibleModule):
+                    nodes.append(("module", mod, None))          # generic block: its own forward, tensor-core inference switch on
                 else:
-                    raise NotImplementedError(f"CWFAEngine supports the default CAT graph; found {type(mod).__name__} "
-                                              "(use CWFAModel.reconstruct for other block types)")
+                    raise NotImplementedError(f"CWFAEngine: {type(mod).__name__} is not an invertible module of this package")
             subs = [x[2] for x in nodes if x[0] == "cat"]
             batched = None
-            if all(sn.inp.Cout_p == 64 and sn.inp.Cin_p == subs[0].inp.Cin_p for sn in subs):
+            if len(subs) > 1 and all(sn.inp.Cout_p == 64 and sn.inp.Cin_p == subs[0].inp.Cin_p and sn.inp.Cin == subs[0].inp.Cin for sn in subs):
                 # one 1x1 conv for the input layers of all sub-networks of the level (they all read the LF condition)
                 ws = [(mod.subnet.block12 if mod.subnet.normal else mod.subnet.block1) for k_, mod, _ in nodes if k_ == "cat"]
                 batched = tc.PackedConv(torch.cat([w.weight.detach() for w in ws], 0), torch.cat([w.bias.detach() for w in ws], 0),
                                         kind, bn=64)
-            self.levels.append(dict(nodes=nodes, cond=_CondNet(m.cond_nets[n], kind), batched_in=batched))
+            self.levels.append(dict(nodes=nodes, cond=None if self.dlr else _CondNet(m.cond_nets[n], kind), batched_in=batched))
         self.lrnn = _LRNN(m.cond_nets[-1], kind)
         self._graphs: Dict = {}
 
     # -------------------------------------------------------------------------------------
-    def _trunks(self, n: int, v8: tc.C8):
-        """Conditioning net + the trunks of all sub-networks of level n.  They depend on the conditions only (CAT
-        blocks, coupling_layers.py:475-500), so forward and inverse share them and levels are independent."""
+    def _trunks(self, n: int, lf8: tc.C8):
+        """The trunks of all fused sub-networks of level n from the level's LF condition (C8).  They depend on the conditions
+        only (CAT blocks, coupling_layers.py:475-500), so forward and inverse share them and levels are independent."""
         lv = self.levels[n]
-        lf8 = lv["cond"](v8)
         b_all = tc.conv_tc(lf8, lv["batched_in"]) if lv["batched_in"] is not None else None
         out, k = [], 0
         for kind, mod, extra in lv["nodes"]:
@@ -243,8 +90,14 @@ class CWFAEngine:
                 out.append(("cat", mod, extra, extra.trunk(lf8, b_all, 8 * k) if b_all is not None else extra.trunk(lf8)))
                 k += 1
             else:
-                out.append(("perm", mod, extra, None))
+                out.append((kind, mod, extra, None))
         return out
+
+    def _lf(self, n: int, v8: Optional[tc.C8], low_res: Optional[torch.Tensor]) -> tc.C8:
+        """LF condition of level n: conditioning net of the views, or (disable_low_res_input) the volume of the level below."""
+        if self.dlr:
+            return tc.to_c8(low_res, self.kind)
+        return self.levels[n]["cond"](v8)
 
     @staticmethod
     def _jac_and_tickets(n_samples: int, device, n_tickets: int = 8):
@@ -254,44 +107,113 @@ class CWFAEngine:
         return buf[:n_samples], buf[n_samples:].view(torch.int32)
 
     def _couple(self, item, x, mean_vol, pending, inverse, logdet, sumsq=None, ticket=None):
-        """Final conv of one sub-network with the coupling fused in its epilogue."""
+        """Final conv of one sub-network with the coupling fused in its epilogue.  When ``x`` carries more samples than the
+        conditions (multi-sample reconstruction, CWFA.py:903-914) the coefficients are computed ONCE and broadcast over the
+        samples by the affine kernel."""
         _, mod, sub, b8 = item
-        perm, axis = (None, 0) if pending is None else (ops.perm_i32(pending[0], b8.data.device), pending[1])
         first = not sub.normal
+        t_scale = (-1.0 / math.sqrt(2)) if first else 1.0
+        if x is not None and x.shape[0] != b8.N:
+            K = x.shape[0]
+            if pending is not None:
+                x = ops.permute(x, pending[0], pending[1])
+            a = tc.conv_tc(b8, sub.out, out_nchw=True)                       # (1, 2ch | ch, H, W)
+            ch = mod.channels
+            a_s = a[:, :ch].expand(K, -1, -1, -1)
+            a_t = (mean_vol if first else a[:, ch:]).expand(K, -1, -1, -1)
+            y, j, q = ops.affine(x, a_s, a_t, inverse=inverse, clamp=mod.clamp, t_scale=t_scale, want_sumsq=True)
+            logdet += j
+            if sumsq is not None:
+                sumsq.copy_(q)
+            return y
+        perm, axis = (None, 0) if pending is None else (ops.perm_i32(pending[0], b8.data.device), pending[1])
         return tc.conv_tc_coupling(b8, sub.out, x, ch=mod.channels, inverse=inverse, clamp=mod.clamp,
-                                   t_ext=mean_vol if first else None, t_scale=(-1.0 / math.sqrt(2)) if first else 1.0,
+                                   t_ext=mean_vol if first else None, t_scale=t_scale,
                                    perm=perm, perm_axis=axis, logdet=logdet, sumsq=sumsq, ticket=ticket)
 
-    def _level_detail_inverse(self, n, v8, mean_vol, z=None):
-        """Detail half ``hi`` of level n in the inverse direction and its log-det.  Independent of the other levels.
-        ``z`` None = zeros (INN_z_temperature = 0, CWFA.py:906-907: z is never materialised); otherwise the latent
-        sample (B, ch, H, W) of this level (``sample_z_truncated``, CWFA.py:47-64)."""
-        items = self._trunks(n, v8)
+    def _run_module(self, mod, hi, lf_nchw, rev, logdet):
+        """A generic invertible block through its own forward (module-API fast path: sub-networks on tcgen05)."""
+        from . import packed
+        with packed.inference_precision(self.kind):
+            (hi,), j = mod((hi,), c=[lf_nchw], rev=rev) if mod.dims_c else mod((hi,), rev=rev)
+        if torch.is_tensor(j):
+            logdet += j
+        elif j != 0:
+            logdet += float(j)
+        return hi
+
+    def _level_detail_inverse(self, n, lf8, mean_vol, z=None, rows: int = 1):
+        """Detail half ``hi`` of level n in the inverse direction and its log-det.  Independent of the other levels unless
+        ``disable_low_res_input``.  ``z`` None = zeros (INN_z_temperature = 0, CWFA.py:906-907: z is never materialised);
+        otherwise the latent sample(s) of this level (``sample_z_truncated``, CWFA.py:47-64), ``rows`` of them."""
+        items = self._trunks(n, lf8)
         hi, pending = z, None
-        jac, tickets = self._jac_and_tickets(v8.N, v8.data.device)
-        k = 0
+        jac, tickets = self._jac_and_tickets(rows if z is None else z.shape[0], lf8.data.device)
+        lf_nchw, k = None, 0
         for item in reversed(items):
             if item[0] == "cat":
                 hi = self._couple(item, hi, mean_vol, pending, True, jac, ticket=tickets[k:k + 1])
                 pending, k = None, (k + 1) % tickets.numel()
-            elif hi is not None:
-                pending = (item[1].perm_inv, item[2])       # gathered by the next coupling's epilogue
+            elif item[0] == "perm":
+                if hi is not None:
+                    pending = (item[1].perm_inv, item[2])       # gathered by the next coupling's epilogue
+            else:
+                if hi is None:
+                    hi = torch.zeros((rows,) + tuple(item[1].dims_in[0]), device=lf8.data.device, dtype=torch.float32)
+                if pending is not None:
+                    hi, pending = ops.permute(hi, pending[0], pending[1]), None
+                if lf_nchw is None:
+                    lf_nchw = tc.from_c8(lf8)
+                    if lf_nchw.shape[0] != hi.shape[0]:
+                        lf_nchw = lf_nchw.expand(hi.shape[0], -1, -1, -1).contiguous()
+                hi = self._run_module(item[1], hi, lf_nchw, True, jac)
         if pending is not None:
             hi = ops.permute(hi, pending[0], pending[1])
         return hi, jac
 
     @torch.no_grad()
     def reconstruct(self, views: torch.Tensor, mean_vols: Sequence[Optional[torch.Tensor]], return_all: bool = False,
-                    _side_streams=None, zs: Optional[Sequence[Optional[torch.Tensor]]] = None):
-        """Inverse reconstruction (CWFA.py:865-924); z = 0 unless ``zs[n]`` gives level n's latent sample.
+                    _side_streams=None, zs: Optional[Sequence[Optional[torch.Tensor]]] = None, n_samples: int = 1,
+                    temperature: Optional[float] = None):
+        """Inverse reconstruction (CWFA.py:865-924); z = 0 unless ``zs[n]`` gives level n's latent sample(s) or
+        ``temperature`` (default ``cfg.INN_z_temperature`` = 0) is non-zero (then z ~ ``sample_z_truncated``).
+        ``n_samples`` > 1 (batch 1): the reference's multi-sample path (CWFA.py:903-914) -- the coefficients of a level are
+        computed once, applied to ``n_samples`` latent samples, and the samples are averaged (the Haar merge is linear, so the
+        mean is taken on the detail half before the merge).
 
         The LRNN and the coupling coefficients of every level depend only on the views / mean volumes, not on
         each other, so under CUDA-graph capture they are issued on side streams (``_side_streams``) and become
         parallel branches of the graph; only the four Haar merges are sequential."""
+        from .pipeline import sample_z_truncated
         L1 = self.model.n_levels
+        T = self.model.cfg.INN_z_temperature if temperature is None else temperature
+        B = views.shape[0]
+        if n_samples > 1 and B != 1:
+            raise ValueError("n_samples > 1 needs batch size 1 (CWFA.py:904)")
         v8 = tc.to_c8(views, self.kind)
         mv_last = lrnn_mean_volume(mean_vols, L1)            # CWFA.py:882: mean_vols_cache[L-2] unless given explicitly
-        jobs = [lambda: self.lrnn(v8, mv_last)] + [(lambda n=n: self._level_detail_inverse(n, v8, mean_vols[n], None if zs is None else zs[n])) for n in range(L1 - 1, -1, -1)]
+
+        def z_of(n):
+            if zs is not None and zs[n] is not None:
+                return zs[n]
+            if T != 0:
+                return sample_z_truncated((B * n_samples,) + tuple(self.model.conv_inn[n].global_out_shapes[0]), device=views.device,
+                                          temperature=T)
+            return None
+
+        def finish(hi):
+            return ops.batch_mean(hi) if (n_samples > 1 and hi.shape[0] > 1) else hi
+
+        if self.dlr:                                         # sequential pyramid: the condition is the volume of the level below
+            vol = self.lrnn(v8, mv_last)
+            outs, jacs = {L1: vol}, {}
+            for n in range(L1 - 1, -1, -1):
+                hi, jac = self._level_detail_inverse(n, self._lf(n, None, vol), None, z_of(n), B)
+                vol = ops.haar1d_merge(vol, finish(hi))
+                outs[n], jacs[n] = vol, jac
+            return (outs, jacs) if return_all else vol
+        jobs = [lambda: self.lrnn(v8, mv_last)] + [(lambda n=n: self._level_detail_inverse(n, self._lf(n, v8, None), mean_vols[n], z_of(n), B))
+                                                    for n in range(L1 - 1, -1, -1)]
         if _side_streams:
             main = torch.cuda.current_stream()
             fork = torch.cuda.Event()
@@ -312,65 +234,167 @@ class CWFAEngine:
         outs, jacs = {L1: vol}, {}
         for k, n in enumerate(range(L1 - 1, -1, -1)):
             hi, jac = results[1 + k]
-            vol = ops.haar1d_merge(vol, hi)          # Split^-1 + IDWT: the only sequential part of the pyramid
+            vol = ops.haar1d_merge(vol, finish(hi))  # Split^-1 + IDWT: the only sequential part of the pyramid
             outs[n], jacs[n] = vol, jac
         return (outs, jacs) if return_all else vol
 
+    def _level_forward(self, n, hi, lf8, mean_vol):
+        """Detail half of level n through the flow in the forward direction: (z, logdet[B], sumsq[B])."""
+        jac, tickets = self._jac_and_tickets(hi.shape[0], hi.device)
+        sumsq = None
+        pending, k, lf_nchw = None, 0, None
+        last_was_cat = False
+        for item in self._trunks(n, lf8):
+            if item[0] == "cat":
+                sumsq = torch.empty_like(jac) if sumsq is None else sumsq
+                hi = self._couple(item, hi, mean_vol, pending, False, jac, sumsq, ticket=tickets[k:k + 1])   # sumsq: last coupling wins
+                pending, k, last_was_cat = None, (k + 1) % tickets.numel(), True
+            elif item[0] == "perm":
+                pending = (item[1].perm, item[2])
+            else:
+                if pending is not None:
+                    hi, pending = ops.permute(hi, pending[0], pending[1]), None
+                if lf_nchw is None:
+                    lf_nchw = tc.from_c8(lf8)
+                hi = self._run_module(item[1], hi, lf_nchw, False, jac)
+                last_was_cat = False
+        if pending is not None:          # trailing permutation: does not change ||z||^2
+            hi = ops.permute(hi, pending[0], pending[1])
+        if not last_was_cat or sumsq is None:
+            sumsq = ops.sum_squares(hi)
+        return hi, jac, sumsq
+
     @torch.no_grad()
-    def forward_nll(self, volume: torch.Tensor, views: torch.Tensor, mean_vols: Sequence[torch.Tensor]):
-        """Forward pyramid + per-level NLL (CWFA.py:966-978); same outputs as CWFAModel.forward_nll."""
-        v8 = tc.to_c8(views, self.kind)
-        res = []
+    def forward_nll(self, volume: torch.Tensor, views: torch.Tensor, mean_vols: Sequence[torch.Tensor],
+                    low_res_conditions: Optional[Sequence[torch.Tensor]] = None, _side_streams=None):
+        """Forward pyramid + per-level NLL (CWFA.py:966-978); same outputs as CWFAModel.forward_nll.
+
+        The conditioning nets and trunks of the four levels depend on the views only, so under CUDA-graph capture
+        (``forward_nll_graphed``) they run as parallel branches next to the Haar pyramid of the volume."""
+        L1 = self.model.n_levels
+        v8 = None if self.dlr else tc.to_c8(views, self.kind)
+        # Haar pyramid of the volume first (cheap, sequential): lo_n / hi_n of every level
+        los, his = [], []
         x = volume
-        for n in range(self.model.n_levels):
+        for n in range(L1):
             lo, hi = ops.haar1d_split(x)
-            jac, tickets = self._jac_and_tickets(x.shape[0], x.device)
-            sumsq = torch.empty_like(jac)
-            pending, k = None, 0
-            for item in self._trunks(n, v8):
-                if item[0] == "cat":
-                    hi = self._couple(item, hi, mean_vols[n], pending, False, jac, sumsq, ticket=tickets[k:k + 1])   # sumsq: last coupling wins
-                    pending, k = None, (k + 1) % tickets.numel()
-                else:
-                    pending = (item[1].perm, item[2])
-            if pending is not None:          # trailing permutation: does not change ||z||^2
-                hi = ops.permute(hi, pending[0], pending[1])
-            per = (0.5 * sumsq - jac) / hi[0].numel()
-            ref = (0.5 * sumsq.sum() - jac) / lo.numel()
-            res.append(dict(z=hi, lo=lo, logdet=jac, sumsq=sumsq, nll_per_sample=per, nll_ref=ref))
+            los.append(lo)
+            his.append(hi)
             x = lo
+
+        def job(n):
+            if self.dlr:
+                given = low_res_conditions[n] if low_res_conditions is not None and n < len(low_res_conditions) else None
+                lf8 = tc.to_c8(given if given is not None else los[n], self.kind)
+                return self._level_forward(n, his[n], lf8, None)
+            return self._level_forward(n, his[n], self._lf(n, v8, None), mean_vols[n])
+
+        if _side_streams:
+            main = torch.cuda.current_stream()
+            fork = torch.cuda.Event()
+            fork.record(main)
+            results, joins = [], []
+            for st, n in zip(_side_streams, range(L1)):
+                st.wait_event(fork)
+                with torch.cuda.stream(st):
+                    results.append(job(n))
+                    ev = torch.cuda.Event()
+                    ev.record(st)
+                joins.append(ev)
+            for ev in joins:
+                main.wait_event(ev)
+        else:
+            results = [job(n) for n in range(L1)]
+        res = []
+        for n, (z, jac, sumsq) in enumerate(results):
+            lo = los[n]
+            per = (0.5 * sumsq - jac) / z[0].numel()
+            ref = (0.5 * sumsq.sum() - jac) / lo.numel()
+            res.append(dict(z=z, lo=lo, logdet=jac, sumsq=sumsq, nll_per_sample=per, nll_ref=ref))
         return res
 
-    # ---- CUDA-graph replay of the whole frame -------------------------------------------
-    def _graph_slot(self, views: torch.Tensor, mean_vols, slot: int = 0):
-        """(graph, static_views, static_mean_vols, static_out) for this shape; ``slot`` selects an independent
-        instance (own static buffers) so that several frames can be in flight."""
-        key = (tuple(views.shape), tuple(None if m is None else tuple(m.shape) for m in mean_vols), views.device.index, slot)
+    # ---- CUDA-graph replay of the forward pyramid (BASELINE.json configs[2]) ---------------------------------------------
+    def forward_nll_graphed(self, volume: torch.Tensor, views: torch.Tensor, mean_vols: Sequence[torch.Tensor]):
+        """``forward_nll`` as one CUDA-graph replay (static shapes; inputs are copied into static buffers, the returned tensors
+        are the graph's static outputs, overwritten by the next call): the four levels' conditioning nets / trunks / couplings
+        are parallel branches of the graph."""
+        key = ("nll", tuple(volume.shape), tuple(views.shape), tuple(tuple(m.shape) for m in mean_vols), volume.device.index)
         g = self._graphs.get(key)
         if g is None:
-            sv = views.clone()
-            sm = [None if m is None else m.clone() for m in mean_vols]
+            sx, sv, sm = volume.clone(), views.clone(), [m.clone() for m in mean_vols]
             s = torch.cuda.Stream()
             s.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s):
                 for _ in range(2):
-                    self.reconstruct(sv, sm)
+                    self.forward_nll(sx, sv, sm)
             torch.cuda.current_stream().wait_stream(s)
             graph = torch.cuda.CUDAGraph()
-            side = [torch.cuda.Stream() for _ in range(self.model.n_levels + 1)] if self.parallel_branches else None
+            side = [torch.cuda.Stream() for _ in range(self.model.n_levels)] if self.parallel_branches else None
             with torch.cuda.graph(graph):
-                out = self.reconstruct(sv, sm, _side_streams=side)
-            g = self._graphs[key] = (graph, sv, sm, out)
+                out = self.forward_nll(sx, sv, sm, _side_streams=side)
+            g = self._graphs[key] = (graph, sx, sv, sm, out)
+        graph, sx, sv, sm, out = g
+        sx.copy_(volume, non_blocking=True)
+        sv.copy_(views, non_blocking=True)
+        for d, s_ in zip(sm, mean_vols):
+            d.copy_(s_, non_blocking=True)
+        graph.replay()
+        return out
+
+    # ---- CUDA-graph replay of the whole frame -------------------------------------------
+    def _graph_slot(self, views: torch.Tensor, mean_vols, slot: int = 0, z_rows: int = 0):
+        """(graph, static_views, static_mean_vols, static_out, static_zs) for this shape; ``slot`` selects an independent
+        instance (own static buffers) so that several frames can be in flight.  ``z_rows`` > 0: the graph takes the latent
+        samples of every level as inputs (``z_rows`` rows each; temperature > 0 / multi-sample reconstruction) -- they are
+        sampled outside the graph into the static buffers."""
+        key = (tuple(views.shape), tuple(None if m is None else tuple(m.shape) for m in mean_vols), views.device.index, slot, z_rows)
+        g = self._graphs.get(key)
+        if g is None:
+            sv = views.clone()
+            sm = [None if m is None else m.clone() for m in mean_vols]
+            sz = None
+            if z_rows:
+                sz = [torch.zeros((z_rows,) + tuple(self.model.conv_inn[n].global_out_shapes[0]), device=views.device, dtype=torch.float32)
+                      for n in range(self.model.n_levels)]
+            ns = max(1, z_rows // views.shape[0])
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                for _ in range(2):
+                    self.reconstruct(sv, sm, zs=sz, n_samples=ns)
+            torch.cuda.current_stream().wait_stream(s)
+            graph = torch.cuda.CUDAGraph()
+            side = [torch.cuda.Stream() for _ in range(self.model.n_levels + 1)] if (self.parallel_branches and not self.dlr) else None
+            with torch.cuda.graph(graph):
+                out = self.reconstruct(sv, sm, _side_streams=side, zs=sz, n_samples=ns)
+            g = self._graphs[key] = (graph, sv, sm, out, sz)
         return g
 
-    def reconstruct_graphed(self, views: torch.Tensor, mean_vols: Sequence[Optional[torch.Tensor]]) -> torch.Tensor:
+    def _fill_z(self, sz, zs, temperature):
+        """Latent samples of one frame into a graph slot's static z buffers (current stream): given ``zs`` or fresh draws."""
+        for n, d in enumerate(sz):
+            if zs is not None and zs[n] is not None:
+                d.copy_(zs[n], non_blocking=True)
+            elif temperature:
+                torch.nn.init.trunc_normal_(d, mean=0.0, std=1.0, a=-temperature, b=temperature)     # sample_z_truncated, CWFA.py:47-64
+            else:
+                d.zero_()
+
+    def reconstruct_graphed(self, views: torch.Tensor, mean_vols: Sequence[Optional[torch.Tensor]],
+                            zs: Optional[Sequence[Optional[torch.Tensor]]] = None, n_samples: int = 1,
+                            temperature: Optional[float] = None) -> torch.Tensor:
         """Same as ``reconstruct`` but replays a captured CUDA graph (static shapes; inputs are copied into
-        static buffers, the returned tensor is the graph's static output buffer)."""
-        graph, sv, sm, out = self._graph_slot(views, mean_vols)
+        static buffers, the returned tensor is the graph's static output buffer).  With ``zs`` / a non-zero temperature /
+        ``n_samples`` > 1 the latent samples are graph INPUTS filled before the replay."""
+        T = self.model.cfg.INN_z_temperature if temperature is None else temperature
+        z_rows = views.shape[0] * n_samples if (zs is not None or T != 0 or n_samples > 1) else 0
+        graph, sv, sm, out, sz = self._graph_slot(views, mean_vols, z_rows=z_rows)[:5]
         sv.copy_(views, non_blocking=True)
         for d, s_ in zip(sm, mean_vols):
             if d is not None:
                 d.copy_(s_, non_blocking=True)
+        if sz is not None:
+            self._fill_z(sz, zs, T)
         graph.replay()
         return out
 
@@ -405,7 +429,7 @@ class StreamingReconstructor:
         self.eng, self.depth = engine, depth
         dev = mean_vols[0].device
         probe = torch.zeros(views_shape, device=dev, dtype=torch.float32)
-        self.slots = [engine._graph_slot(probe, mean_vols, slot=k) for k in range(depth)]
+        self.slots = [engine._graph_slot(probe, mean_vols, slot=k)[:4] for k in range(depth)]
         for (graph, sv, sm, out) in self.slots:
             for d, s_ in zip(sm, mean_vols):
                 if d is not None:

@@ -22,7 +22,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from . import ops
+from . import ops, packed
 
 
 class InvertibleModule(nn.Module):
@@ -313,6 +313,28 @@ class _BaseCouplingBlock(InvertibleModule):
             return ops.affine(x, s.contiguous(), a_t, inverse=rev, clamp=self.clamp, t_scale=t_scale, s_is_final=True)
         return ops.affine(x, a_s, a_t, inverse=rev, clamp=self.clamp, t_scale=t_scale, **self._clamp_kw)
 
+    def _fused_executor(self, subnet, n_out: int, ext: bool, *tensors):
+        """The sub-network's tensor-core executor when this coupling can run with the coupling FUSED into the epilogue of the
+        sub-network's last convolution (``tc.conv_tc_coupling``), else None: needs the inference switch on
+        (``cwfa_b200.set_inference_precision``), no gradient, the ATAN clamp (the only one the epilogue evaluates), image-shaped
+        data and [s | t] (or s alone when the shift is external) in one N block of the last conv."""
+        kind = packed.fast_kind(*tensors)
+        ex_fn = getattr(subnet, "packed_executor", None)
+        if kind is None or ex_fn is None or self._clamp_kw is None or self._clamp_kw["tanh_clamp"] or self.ndims != 3 or n_out > 48:
+            return None
+        ex = ex_fn(kind)
+        return ex if ex.out.Cout == (n_out if ext else 2 * n_out) and ex.out.BN == ex.out.Cout_p else None
+
+    def _couple(self, subnet, u, x_active, n_out: int, rev: bool):
+        """(y, log-det) of one affine coupling whose coefficients are ``subnet(u)`` = [s_raw | t]: ONE tensor-core kernel for
+        the last conv + coupling when ``_fused_executor`` allows it (s, t never reach HBM), else sub-network output -> fused
+        affine kernel."""
+        ex = self._fused_executor(subnet, n_out, False, u, x_active)
+        if ex is not None:
+            return ex.couple(u, x_active, ch=n_out, inverse=rev, clamp=self.clamp, k_atan=self._clamp_kw["k_atan"])
+        a = subnet(u)
+        return self._affine(x_active, a[:, :n_out], a[:, n_out:], rev)
+
     def _clamped_s(self, a_s):
         """s = clamp * f_clamp(a_s) as a tensor (only the volume-preserving GIN block needs it outside the kernel)."""
         if self._clamp_kw is None:
@@ -382,11 +404,18 @@ class RNVPCouplingBlock(_BaseCouplingBlock):
         self.subnet_s2 = subnet_constructor(self.split_len2 + self.condition_length, self.split_len1)
         self.subnet_t2 = subnet_constructor(self.split_len2 + self.condition_length, self.split_len1)
 
+    def _st_couple(self, sub_s, sub_t, u, x_active, n_out, rev):
+        t = sub_t(u)
+        ex = self._fused_executor(sub_s, n_out, True, u, x_active)
+        if ex is not None:                       # s from the fused last conv of subnet_s, t (its own sub-network) as external shift
+            return ex.couple(u, x_active, ch=n_out, inverse=rev, clamp=self.clamp, k_atan=self._clamp_kw["k_atan"], t_ext=t, t_scale=1.0)
+        return self._affine(x_active, sub_s(u), t, rev)
+
     def _coupling1(self, x1, u2, rev=False):
-        return self._affine(x1, self.subnet_s2(u2), self.subnet_t2(u2), rev)
+        return self._st_couple(self.subnet_s2, self.subnet_t2, u2, x1, self.split_len1, rev)
 
     def _coupling2(self, x2, u1, rev=False):
-        return self._affine(x2, self.subnet_s1(u1), self.subnet_t1(u1), rev)
+        return self._st_couple(self.subnet_s1, self.subnet_t1, u1, x2, self.split_len2, rev)
 
 
 class GLOWCouplingBlock(_BaseCouplingBlock):
@@ -400,10 +429,14 @@ class GLOWCouplingBlock(_BaseCouplingBlock):
         self._gin = False
 
     def _coupling1(self, x1, u2, rev=False):
-        return self._affine_from(x1, self.subnet2(u2), self.split_len1, rev, self._gin)
+        if self._gin:
+            return self._affine_from(x1, self.subnet2(u2), self.split_len1, rev, True)
+        return self._couple(self.subnet2, u2, x1, self.split_len1, rev)
 
     def _coupling2(self, x2, u1, rev=False):
-        return self._affine_from(x2, self.subnet1(u1), self.split_len2, rev, self._gin)
+        if self._gin:
+            return self._affine_from(x2, self.subnet1(u1), self.split_len2, rev, True)
+        return self._couple(self.subnet1, u1, x2, self.split_len2, rev)
 
 
 class GINCouplingBlock(GLOWCouplingBlock):
@@ -426,7 +459,7 @@ class AffineCouplingOneSided(_BaseCouplingBlock):
     def forward(self, x, c=[], rev=False, jac=True):
         x1, x2 = torch.split(x[0], [self.split_len1, self.split_len2], dim=1)
         x1_c = torch.cat([x1, *c], 1) if self.conditional else x1
-        y2, j = self._affine_from(x2, self.subnet(x1_c), self.split_len2, rev)
+        y2, j = self._couple(self.subnet, x1_c, x2, self.split_len2, rev)
         return (torch.cat((x1, y2), 1),), j
 
 
@@ -456,6 +489,18 @@ class ConditionalAffineTransform(_BaseCouplingBlock):
 
     def forward(self, x, c=[], rev=False, jac=True):
         memo = _SUBNET_MEMO[-1] if _SUBNET_MEMO else None
+        first = not getattr(self.subnet, "normal", True)
+        ex = self._fused_executor(self.subnet, self.channels, first, x[0], *c) if memo is None else None
+        if ex is not None:
+            # tensor-core inference: sub-network trunk + last conv with the coupling in its epilogue
+            cond = torch.cat(list(c), 1) if len(c) > 1 else c[0]
+            if first:                                                    # s = trunk(LF half), t = -meanvol / sqrt2 (networks.py:653-671)
+                n = self.subnet.c_in // 2
+                y, j = ex.couple(cond[:, -n:].contiguous(), x[0], ch=self.channels, inverse=rev, clamp=self.clamp,
+                                 k_atan=self._clamp_kw["k_atan"], t_ext=cond[:, :-n].contiguous(), t_scale=-1.0 / math.sqrt(2))
+            else:
+                y, j = ex.couple(cond, x[0], ch=self.channels, inverse=rev, clamp=self.clamp, k_atan=self._clamp_kw["k_atan"])
+            return (y,), j
         if memo is None:
             a_s, a_t, t_scale = self._st(c)
         else:

@@ -25,7 +25,7 @@ import torch.nn as nn
 
 from . import framework as Ff
 from . import modules as Fm
-from . import ops
+from . import ops, packed
 from .modules import HaarTransform1D, PermuteDim
 
 # hidden width of the coupling sub-networks; set by conditional_wavelet_flow (networks.py:272-274)
@@ -86,7 +86,14 @@ class wavelet_flow_subnetwork2D(nn.Module):
             b = _conv(blk[2], t, res=b, res_mode=1, act=ops.ACT_ELU)
         return b
 
+    def packed_executor(self, kind: str):
+        """Tensor-core executor of this sub-network (weights packed once, cached; ``cwfa_b200.packed``)."""
+        return packed.executor(self, kind, packed._Subnet)
+
     def forward(self, inp):
+        kind = packed.fast_kind(inp)
+        if kind is not None:                     # inference with set_inference_precision('bf16'|'fp16'): tcgen05 kernels
+            return self.packed_executor(kind).from_nchw(inp)
         return _conv(self.block72[1], self.trunk(_conv(self.block12, inp)))
 
 
@@ -104,6 +111,9 @@ class wavelet_flow_subnetwork2D_first(wavelet_flow_subnetwork2D):
         """Returns (a_s, a_t, t_scale) without materialising cat(b7, -low/sqrt2)."""
         n = self.c_in // 2
         low, cond = inp[:, :-n], inp[:, -n:]
+        kind = packed.fast_kind(inp)
+        if kind is not None:
+            return self.packed_executor(kind).from_nchw(cond.contiguous()), low, -1.0 / math.sqrt(2)
         b7 = _conv(self.block7[1], self.trunk(_conv(self.block1, cond.contiguous())))
         return b7, low, -1.0 / math.sqrt(2)
 
@@ -156,6 +166,9 @@ class cond_network(nn.Module):
         self.subnetworks = nn.Sequential(ResidualBlock(c_in, c_out, chans_3D=cond_chans))
 
     def forward(self, lf_img):
+        kind = packed.fast_kind(lf_img)
+        if kind is not None:
+            return [packed.executor(self, kind, packed._CondNet).from_nchw(lf_img)]
         return [self.subnetworks[0](lf_img)]
 
 
@@ -306,7 +319,16 @@ class Encoder(nn.Module):
         self.net = LRNN(c_in, c_out, use_bias, size=size)
 
     def forward(self, im_in, mean_vol=None):
+        kind = packed.fast_kind(im_in, mean_vol)
+        if kind is not None and self._tc_ok(mean_vol):
+            return [packed.executor(self, kind, packed._LRNN).from_nchw(im_in, mean_vol)]
         return [self.net(im_in) if mean_vol is None else self.net(im_in, mean_vol)]
+
+    def _tc_ok(self, mean_vol) -> bool:
+        """The C8 U-Net executor needs unpadded channel counts (multiples of 16: wf = 8 gives 256/512/1024) and the fused
+        attention gate its compile-time channel limit."""
+        widths_ok = all(blk.block[0].weight.shape[0] % 16 == 0 for blk in self.net.deconv[1].down_path)
+        return widths_ok and (mean_vol is None or mean_vol.shape[1] <= 16)
 
 
 # ---------------------------------------------------------------------------------------------

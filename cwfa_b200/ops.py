@@ -166,6 +166,8 @@ def _prep_inner(t: torch.Tensor):
     if t.dtype != torch.float32:
         t = t.float()
     inner_ok = t[0].is_contiguous() if B > 0 else True
+    if B > 1 and inner_ok and t.stride(0) == 0:
+        return t, 0                                   # one (ch,H,W) block broadcast over the batch (``expand``): read in place
     if not inner_ok or (B > 1 and t.stride(0) < ch * P):
         t = t.contiguous()
     return t, (t.stride(0) if B > 1 else ch * P)

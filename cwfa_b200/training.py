@@ -153,6 +153,8 @@ class Lion:
 
     @torch.no_grad()
     def step(self):
+        from . import packed
+        packed.weights_changed()          # the kernel below rewrites the flat buffer in place: cached tensor-core executors are stale
         st = torch.cuda.current_stream().cuda_stream
         for g in self.param_groups:
             fg: FlatGroup = g["flat"]
