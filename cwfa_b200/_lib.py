@@ -35,6 +35,7 @@ _SIGS = {
     "cwfa_layernorm_workspace_blocks": [],
     "cwfa_layernorm_chw_f32": [vp, vp, vp, vp, vp, i32, i64, f32, vp],
     "cwfa_gate_add_f32": [vp, vp, vp, i64, vp],
+    "cwfa_cast_f32_f16": [vp, vp, i64, vp],
     "cwfa_extract_views": [vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, f32, f32, i32, vp],
     "cwfa_attention_gate_f32": [vp, vp, vp, vp, vp, vp, vp, i32, i32, i64, vp],
     "cwfa_tc_kc": [i32],

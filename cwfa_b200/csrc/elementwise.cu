@@ -3,6 +3,7 @@
 // All are single-pass, 128-bit vectorised where alignment allows, grid sized in multiples
 // of the SM count.  Reference arithmetic cited per function in include/cwfa_b200.h.
 #include <stdarg.h>
+#include <algorithm>
 #include "common.cuh"
 
 namespace cwfa {
@@ -544,6 +545,31 @@ __global__ void __launch_bounds__(256) gate_add_kernel(float* __restrict__ x, co
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         x[i] += m[i] * 2.f * (g[i] - 0.5f);
 }
+// fp32 -> fp16 narrowing of a finished volume (optional half-size device->host transfer; the reference's own GPU output is
+// fp16 under autocast, CWFA.py:845): 8 elements per thread, 2 x 16-byte loads, one 16-byte store, grid = multiple of the SM count.
+__global__ void __launch_bounds__(256) cast_f32_f16_kernel(const float4* __restrict__ x, uint4* __restrict__ y, int64_t n8,
+                                                           const float* __restrict__ xt, __half* __restrict__ yt, int64_t tail0, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 a = __ldg(x + 2 * i), b = __ldg(x + 2 * i + 1);
+        __half2 h0 = __floats2half2_rn(a.x, a.y), h1 = __floats2half2_rn(a.z, a.w), h2 = __floats2half2_rn(b.x, b.y), h3 = __floats2half2_rn(b.z, b.w);
+        uint4 o;
+        o.x = *reinterpret_cast<uint32_t*>(&h0); o.y = *reinterpret_cast<uint32_t*>(&h1);
+        o.z = *reinterpret_cast<uint32_t*>(&h2); o.w = *reinterpret_cast<uint32_t*>(&h3);
+        y[i] = o;
+    }
+    if (blockIdx.x == 0)
+        for (int64_t i = tail0 + threadIdx.x; i < n; i += blockDim.x) yt[i] = __float2half_rn(xt[i]);
+}
+extern "C" int cwfa_cast_f32_f16(const float* x, void* y, int64_t n, void* stream) {
+    if (!x || !y || n < 0 || !aligned16(x) || !aligned16(y)) { set_error("cast_f32_f16: bad arguments (16-byte aligned pointers required)"); return CWFA_EINVAL; }
+    if (n == 0) return CWFA_OK;
+    const int64_t n8 = n / 8;
+    const int blocks = (int)std::min<int64_t>((n8 + 255) / 256 + 1, (int64_t)kNumSMs * 8);
+    cast_f32_f16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<uint4*>(y), n8, x,
+                                                                  reinterpret_cast<__half*>(y), n8 * 8, n);
+    return check_launch("cast_f32_f16");
+}
+
 extern "C" int cwfa_gate_add_f32(float* x, const float* m, const float* g, int64_t n, void* stream) {
     int blocks = (int)((n + 255) / 256);
     if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;

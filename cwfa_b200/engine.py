@@ -425,8 +425,14 @@ class StreamingReconstructor:
     to one-by-one reconstruction.  Inputs / outputs may live on the host (pinned) or on the device.
     The mean-volume pyramid is a dataset constant and stays on the device."""
 
-    def __init__(self, engine: CWFAEngine, views_shape, mean_vols: Sequence[Optional[torch.Tensor]], depth: int = 2):
-        self.eng, self.depth = engine, depth
+    def __init__(self, engine: CWFAEngine, views_shape, mean_vols: Sequence[Optional[torch.Tensor]], depth: int = 2,
+                 out_dtype: torch.dtype = torch.float32):
+        """``out_dtype=torch.float16``: host-resident outputs are narrowed on the device (one cast kernel) so the device->host
+        transfer carries half the bytes (the reference's own GPU output is fp16 under autocast, CWFA.py:845); the host buffers
+        passed to ``run`` must then be fp16."""
+        if out_dtype not in (torch.float32, torch.float16):
+            raise ValueError("out_dtype must be torch.float32 or torch.float16")
+        self.eng, self.depth, self.out_dtype = engine, depth, out_dtype
         dev = mean_vols[0].device
         probe = torch.zeros(views_shape, device=dev, dtype=torch.float32)
         self.slots = [engine._graph_slot(probe, mean_vols, slot=k)[:4] for k in range(depth)]
@@ -449,7 +455,7 @@ class StreamingReconstructor:
             n = self.depth + 1
             dev = like_out.device
             self._stage = ([torch.empty_like(like_in, device=dev) for _ in range(n)],
-                           [torch.empty_like(like_out, device=dev) for _ in range(n)],
+                           [torch.empty(like_out.shape, device=dev, dtype=self.out_dtype) for _ in range(n)],
                            [torch.cuda.Event() for _ in range(n)], [torch.cuda.Event() for _ in range(n)],
                            [torch.cuda.Event() for _ in range(n)], [torch.cuda.Event() for _ in range(n)])
         return self._stage
@@ -487,7 +493,10 @@ class StreamingReconstructor:
                     graph.replay()
                     if i >= ns:
                         self.s_run[k].wait_event(ev_out_free[j]) # the D2H copy that used this staging buffer has finished
-                    st_out[j].copy_(out, non_blocking=True)
+                    if self.out_dtype == torch.float16:
+                        ops.cast_f16(out, st_out[j])
+                    else:
+                        st_out[j].copy_(out, non_blocking=True)
                     ev_staged[j].record(self.s_run[k])
                 with torch.cuda.stream(s_out):
                     s_out.wait_event(ev_staged[j])

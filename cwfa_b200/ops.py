@@ -363,6 +363,17 @@ def sum_squares(x: torch.Tensor) -> torch.Tensor:
     return stats[B:]
 
 
+def cast_f16(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 -> fp16 copy of a finished volume into ``out`` (device); used for half-size device->host transfers."""
+    x = _ck(x, "x")
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=torch.float16)
+    if not (out.is_cuda and out.is_contiguous() and out.dtype == torch.float16 and out.numel() == x.numel()):
+        raise ValueError("cast_f16: out must be a contiguous fp16 CUDA tensor of the same size")
+    _lib.call("cwfa_cast_f32_f16", x.data_ptr(), out.data_ptr(), x.numel(), _stream())
+    return out
+
+
 def batch_mean(x: torch.Tensor) -> torch.Tensor:
     """Mean over the batch axis, keepdim: (K,...) -> (1,...) (the multi-sample average of CWFA.py:913-914), as K - 1 axpby passes."""
     x = _ck(x, "x")

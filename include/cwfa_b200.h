@@ -133,6 +133,9 @@ int cwfa_extract_views(const void* image, int image_is_half, const int32_t* coor
                        int Wi, int L, int SH, int SW, float mean, float stdv, int normalise, void* stream);
 /* x += m * 2 * (g - 0.5)   (networks.py:554) */
 int cwfa_gate_add_f32(float* x, const float* m, const float* g, int64_t n, void* stream);
+/* fp32 -> fp16 narrowing of n elements (x, y 16-byte aligned): optional half-size host transfer of a finished volume (the
+ * reference's own GPU output is fp16 under autocast, CWFA.py:845). */
+int cwfa_cast_f32_f16(const float* x, void* y, int64_t n, void* stream);
 
 /* ---- K2: tcgen05 / TMEM / TMA implicit-GEMM convolution (bf16 or fp16 operands, fp32 accumulate) --
  * The throughput path for every wide convolution of the path: coupling sub-network trunk
