@@ -91,8 +91,8 @@ FULL_TOL = {"bf16": (1e-2, 1e-2), "fp16": (2e-3, 2e-3)}
 # On the probe's deterministic-fill weights bf16 OPERAND ROUNDING ALONE exceeds 1e-2: tests/golden/r2_full_emu.pt holds the error
 # of the CPU oracle re-run with every convolution operand rounded to the half type and exact accumulation (generator:
 # tests/golden/make_emulation_yardstick.py): bf16 1.0-1.3e-2 per level, log-det up to 1.1e-2.  The limit per quantity is
-# max(stated tolerance, 2 x that yardstick); every test prints its per-level table.
-EMU_FACTOR = 2.0
+# max(stated tolerance, 2.5 x that yardstick -- the forward yardstick is one frame, the test takes the worst of eight); every test prints its per-level table.
+EMU_FACTOR = 2.5
 
 
 @pytest.fixture(scope="module")

@@ -91,6 +91,8 @@ def test_reference_flow_builder_runs_on_this_packages_modules(golden_tiny):
         inns.append(inn.eval().to(DEV))
         conds.append(cn.eval().to(DEV))
     views, mean_vols = tiny_inputs(golden_tiny)
+    torch.backends.cudnn.allow_tf32 = False                          # the reference's torch convolutions in true fp32 on the GPU
+    torch.backends.cuda.matmul.allow_tf32 = False
     vol = golden_tiny["recon/batch/nomv/lrnn"].to(DEV)              # the LRNN output of the reference; the flow levels are under test here
     with torch.no_grad():
         for n in range(MAX - 2, -1, -1):
