@@ -619,13 +619,17 @@ class _BatchNorm(_F):
     c0 = -a <dy>/n - b mean; d gamma = <dy, xhat>, d beta = <dy> -- two per-channel sums + one element-wise pass."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, running_mean, running_var, batch_stats, eps):
+    def forward(ctx, x, gamma, beta, running_mean, running_var, batch_stats, eps, momentum=None, update_running=False,
+                num_batches_tracked=None):
         xx = _f32(x)
         N, C = xx.shape[0], xx.shape[1]
         P = xx[0, 0].numel()
         n = float(N * P)
         if batch_stats:
-            s, q = ops.channel_stats(xx).double()
+            st = ops.channel_stats(xx)
+            if update_running:
+                ops.update_running_stats(st.reshape(-1), n, running_mean, running_var, momentum, num_batches_tracked)
+            s, q = st.double()
             mean = s / n
             var = (q / n - mean * mean).clamp_min(0.0)
         else:
@@ -663,11 +667,12 @@ class _BatchNorm(_F):
             af, bf, cf = a.float().contiguous(), b.float().contiguous(), c0.float().contiguous()
             _lib.call("cwfa_bn_bwd_apply_f32", dy.data_ptr(), x.data_ptr(), af.data_ptr(), bf.data_ptr(), cf.data_ptr(), dx.data_ptr(),
                       N, C, P, _stream())
-        return dx, dgamma.float(), sdy.float(), None, None, None, None
+        return dx, dgamma.float(), sdy.float(), None, None, None, None, None, None, None
 
 
-def batchnorm(x, gamma, beta, running_mean, running_var, *, batch_stats, eps):
-    return _BatchNorm.apply(x, gamma, beta, running_mean, running_var, batch_stats, eps)
+def batchnorm(x, gamma, beta, running_mean, running_var, *, batch_stats, eps, momentum=None, update_running=False,
+              num_batches_tracked=None):
+    return _BatchNorm.apply(x, gamma, beta, running_mean, running_var, batch_stats, eps, momentum, update_running, num_batches_tracked)
 
 
 class _ScaleShift(_F):

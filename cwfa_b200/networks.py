@@ -228,8 +228,12 @@ class UNetConvBlock(nn.Module):
             x = _conv(self.block[i], x, act=ops.ACT_PRELU, slope=self.block[i + 1].weight)
             if self.batch_norm:
                 bn = self.block[i + 2]
+                # .train() mode = batch statistics AND the running-statistics update, exactly like nn.BatchNorm2d (the reference
+                # keeps its LRNN in .train() mode at inference too, CWFA.py:531-532, so its checkpoints carry these updates)
                 x = ops.batchnorm(x, bn.weight, bn.bias, bn.running_mean, bn.running_var,
-                                  batch_stats=self.training, eps=bn.eps)
+                                  batch_stats=self.training, eps=bn.eps, momentum=bn.momentum,
+                                  update_running=self.training and bn.track_running_stats,
+                                  num_batches_tracked=bn.num_batches_tracked)
         return x
 
 

@@ -275,13 +275,36 @@ def channel_stats(x: torch.Tensor) -> torch.Tensor:
     return stats.view(2, C)
 
 
+def update_running_stats(stats: torch.Tensor, count: float, running_mean, running_var, momentum: Optional[float],
+                         num_batches_tracked=None) -> None:
+    """nn.BatchNorm2d's training-mode side effect (what the reference's LRNN, left in ``.train()`` mode, does on EVERY forward --
+    CWFA.py:531-532, unet.py:100-107 -- and therefore what ends up in its checkpoints):
+    ``running = (1 - m) running + m batch`` with the UNBIASED batch variance; ``momentum=None`` = cumulative average.
+    ``stats`` = per-channel (sum, sum of squares) from the statistics kernel; C-element parameter algebra on the host side."""
+    if running_mean is None or running_var is None:
+        return
+    C = running_mean.numel()
+    s, q = stats[:C].double(), stats[C:].double()
+    mean = s / count
+    var_unbiased = (q - s * mean) / max(count - 1.0, 1.0)
+    with torch.no_grad():
+        if num_batches_tracked is not None:
+            num_batches_tracked += 1
+        m = momentum if momentum is not None else 1.0 / float(num_batches_tracked if num_batches_tracked is not None else 1)
+        running_mean.mul_(1.0 - m).add_(mean.to(running_mean.dtype), alpha=m)
+        running_var.mul_(1.0 - m).add_(var_unbiased.to(running_var.dtype), alpha=m)
+
+
 def batchnorm(x: torch.Tensor, gamma, beta, running_mean=None, running_var=None, *, batch_stats: bool,
-              eps: float = 1e-5) -> torch.Tensor:
+              eps: float = 1e-5, momentum: Optional[float] = None, update_running: bool = False,
+              num_batches_tracked=None) -> torch.Tensor:
     """nn.BatchNorm2d forward: batch statistics (training-mode normalisation, what the reference's
-    LRNN runs at inference, CWFA.py:531-532) or running statistics (eval mode)."""
+    LRNN runs at inference, CWFA.py:531-532) or running statistics (eval mode).  ``update_running``: also apply the
+    training-mode running-statistics update (``update_running_stats``)."""
     if _grad_on(x, gamma, beta):
         from . import autograd as ag
-        return ag.batchnorm(x, gamma, beta, running_mean, running_var, batch_stats=batch_stats, eps=eps)
+        return ag.batchnorm(x, gamma, beta, running_mean, running_var, batch_stats=batch_stats, eps=eps,
+                            momentum=momentum, update_running=update_running, num_batches_tracked=num_batches_tracked)
     x = _ck(x, "x")
     N, C = x.shape[0], x.shape[1]
     P = x[0, 0].numel()
@@ -290,6 +313,8 @@ def batchnorm(x: torch.Tensor, gamma, beta, running_mean=None, running_var=None,
     if batch_stats:
         stats = channel_stats(x).reshape(-1)
         count = float(N * P)
+        if update_running:
+            update_running_stats(stats, count, running_mean, running_var, momentum, num_batches_tracked)
     else:
         rm, rv = _ck(running_mean), _ck(running_var)
         stats = torch.cat([rm, rv + rm * rm]).contiguous()     # as (sum, sumsq) with count 1

@@ -176,6 +176,80 @@ class Lion:
                           g["weight_decay"], float(self.grad_scale), st)
 
 
+class GradScaler:
+    """Dynamic loss scaling with the semantics of ``torch.cuda.amp.GradScaler`` as the reference uses it
+    (``GradScaler(init_scale=2.**2)``, CWFA.py:613; ``scaler.scale(loss).backward(); scaler.step(opt); scaler.update()``,
+    CWFA.py:1005-1015): the loss is multiplied by ``scale`` before ``backward()``; ``step`` un-scales the gradients and SKIPS
+    the optimiser step when any gradient is non-finite; ``update`` halves the scale after a skipped step and doubles it after
+    ``growth_interval`` consecutive good ones.  For this package's ``Lion`` the un-scaling costs nothing (1/scale is folded into
+    the update kernel's gradient factor) and the finiteness check is one sum-of-squares reduction over the flat gradient buffer."""
+
+    def __init__(self, init_scale: float = 2.0 ** 16, growth_factor: float = 2.0, backoff_factor: float = 0.5,
+                 growth_interval: int = 2000, enabled: bool = True):
+        self._scale, self.growth_factor, self.backoff_factor = float(init_scale), float(growth_factor), float(backoff_factor)
+        self.growth_interval, self.enabled = int(growth_interval), bool(enabled)
+        self._growth_tracker, self._found_inf = 0, False
+        self.skipped_steps = 0
+
+    def get_scale(self) -> float:
+        return self._scale if self.enabled else 1.0
+
+    def scale(self, loss: torch.Tensor) -> torch.Tensor:
+        return loss * self._scale if self.enabled else loss
+
+    @staticmethod
+    def _non_finite(opt: "Lion") -> bool:
+        bad = False
+        for g in opt.flat_grads():
+            if g.numel():
+                bad = bad or not bool(torch.isfinite(ops.sum_squares(g.view(1, -1))).all())     # sum g^2 is finite <=> every g is
+        for pg in opt.param_groups:
+            for p in pg["flat"].loose:
+                if p.grad is not None:
+                    bad = bad or not bool(torch.isfinite(ops.sum_squares(p.grad.reshape(1, -1))).all())
+        return bad
+
+    def step(self, optimizer: "Lion"):
+        """Un-scale + step, or skip when a gradient overflowed (returns True when the step was applied)."""
+        if not self.enabled:
+            optimizer.step()
+            return True
+        if self._non_finite(optimizer):
+            self._found_inf = True
+            return False
+        prev = optimizer.grad_scale
+        optimizer.grad_scale = prev / self._scale
+        try:
+            optimizer.step()
+        finally:
+            optimizer.grad_scale = prev
+        return True
+
+    def update(self, new_scale: Optional[float] = None):
+        if not self.enabled:
+            return
+        if new_scale is not None:
+            self._scale = float(new_scale)
+        elif self._found_inf:
+            self._scale *= self.backoff_factor
+            self._growth_tracker = 0
+            self.skipped_steps += 1
+        else:
+            self._growth_tracker += 1
+            if self._growth_tracker == self.growth_interval:
+                self._scale *= self.growth_factor
+                self._growth_tracker = 0
+        self._found_inf = False
+
+    def state_dict(self):
+        return dict(scale=self._scale, growth_factor=self.growth_factor, backoff_factor=self.backoff_factor,
+                    growth_interval=self.growth_interval, _growth_tracker=self._growth_tracker)
+
+    def load_state_dict(self, sd):
+        self._scale, self.growth_factor, self.backoff_factor = float(sd["scale"]), sd["growth_factor"], sd["backoff_factor"]
+        self.growth_interval, self._growth_tracker = sd["growth_interval"], sd["_growth_tracker"]
+
+
 def allreduce_gradients(optimizers: Sequence[Lion], group=None) -> int:
     """Data-parallel gradient reduction: ONE sum all-reduce per flat gradient buffer; the mean's 1/world is applied inside
     the Lion kernel (``grad_scale``) instead of in a separate pass.  Returns the number of collectives issued."""
@@ -241,8 +315,12 @@ class FlowLevelTrainer:
     net (lr_cond), CWFA.py:596-610.  Defaults are the reference's (main.py:40-45 after the 1e-7 scaling of :238-243)."""
 
     def __init__(self, model, n: int, lr: float = 221e-7, lr_cond: float = 845e-7, weight_decay: float = 1e-2,
-                 cond_weight: float = INN_COND_WEIGHT, group=None, precision: str = "fp32"):
+                 cond_weight: float = INN_COND_WEIGHT, group=None, precision: str = "fp32", grad_scaler: "Optional[GradScaler]" = "auto"):
+        """``grad_scaler``: loss scaling as in the reference (``GradScaler(init_scale=4)``, CWFA.py:613,1005-1015).  ``"auto"``
+        = on for ``precision='fp16'`` (the reference's autocast arithmetic: fp16 cotangents underflow without it), off for
+        bf16 / fp32 (same exponent range as fp32)."""
         self.model, self.n, self.cond_weight, self.group, self.precision = model, n, cond_weight, group, precision
+        self.scaler = (GradScaler(init_scale=4.0) if precision == "fp16" else None) if grad_scaler == "auto" else grad_scaler
         self.optimizer = Lion([{"params": list(model.conv_inn[n].parameters()), "lr": lr, "weight_decay": weight_decay}], lr=lr)
         self.optimizer_cond = Lion(list(model.cond_nets[n].parameters()), lr=lr_cond)
         self.collectives = 0
@@ -258,12 +336,18 @@ class FlowLevelTrainer:
         prev = ag.set_training_precision(self.precision)      # 'bf16'/'fp16': convolutions (forward + data gradient) on tcgen05
         try:
             loss, parts = flow_level_loss(self.model, self.n, gt, views, mean_vol, vol_in, z, self.cond_weight)
-            loss.backward()
+            (self.scaler.scale(loss) if self.scaler is not None else loss).backward()              # CWFA.py:1007
         finally:
             ag.set_training_precision(prev)
         self.collectives = allreduce_gradients([self.optimizer, self.optimizer_cond], self.group)
-        self.optimizer_cond.step()                                        # CWFA.py:1002-1005
-        self.optimizer.step()
+        if self.scaler is not None:                                       # CWFA.py:1012-1015
+            self.scaler.step(self.optimizer_cond)
+            self.scaler.step(self.optimizer)
+            self.scaler.update()
+            parts["loss_scale"] = self.scaler.get_scale()
+        else:
+            self.optimizer_cond.step()                                    # CWFA.py:1002-1005
+            self.optimizer.step()
         parts["loss"] = loss.detach()
         return parts
 
@@ -342,8 +426,10 @@ class LRNNTrainer:
     """Lion on ``cond_nets[-1].parameters()`` with ``learning_rate_first_step`` (80e-7 after main.py:240-241) and weight decay
     1e-2 (CWFA.py:600-602); one flat buffer (<= 255 MB fp32 at the full config), one all-reduce per step under data parallelism."""
 
-    def __init__(self, model, lr: float = 80e-7, weight_decay: float = 1e-2, group=None, precision: str = "fp32"):
+    def __init__(self, model, lr: float = 80e-7, weight_decay: float = 1e-2, group=None, precision: str = "fp32",
+                 grad_scaler: "Optional[GradScaler]" = "auto"):
         self.model, self.group, self.precision = model, group, precision
+        self.scaler = (GradScaler(init_scale=4.0) if precision == "fp16" else None) if grad_scaler == "auto" else grad_scaler
         self.optimizer = Lion([{"params": list(model.cond_nets[-1].parameters()), "lr": lr, "weight_decay": weight_decay}], lr=lr)
         self.collectives = 0
 
@@ -356,9 +442,13 @@ class LRNNTrainer:
         prev = ag.set_training_precision(self.precision)
         try:
             loss, _ = lrnn_loss(self.model, gt, views, mean_vol)
-            loss.backward()
+            (self.scaler.scale(loss) if self.scaler is not None else loss).backward()
         finally:
             ag.set_training_precision(prev)
         self.collectives = allreduce_gradients([self.optimizer], self.group)
-        self.optimizer.step()
+        if self.scaler is not None:
+            self.scaler.step(self.optimizer)
+            self.scaler.update()
+        else:
+            self.optimizer.step()
         return dict(loss=loss.detach())

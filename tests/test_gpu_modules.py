@@ -150,3 +150,41 @@ def test_depth_stencil_vs_torch_cpu(ch, H, W):
     ref = F.conv3d(F.prelu(F.conv3d(v, w1, b1, padding=1), a), w2, b2, padding=1)[:, 0].permute(0, 3, 1, 2)
     y = ops.depth_stencil3d(x.to(DEV), w1.to(DEV), b1.to(DEV), a.to(DEV), w2.to(DEV), b2.to(DEV))
     assert rel_l2(y, ref) < 1e-5
+
+
+def test_batchnorm_train_mode_updates_running_statistics_like_torch():
+    """unet.py:100-107 uses nn.BatchNorm2d and the reference leaves its LRNN in .train() mode (CWFA.py:531-532): every forward
+    normalises with batch statistics AND moves running_mean / running_var (unbiased variance, momentum 0.1) and
+    num_batches_tracked -- the values its checkpoints carry.  Same side effect here, checked against torch's own module."""
+    import torch.nn as nn
+    from cwfa_b200 import ops
+    C = 8
+    ref = nn.BatchNorm2d(C)
+    with torch.no_grad():
+        ref.weight.copy_(seeded_randn((C,), 1) * 0.3 + 1.0)
+        ref.bias.copy_(seeded_randn((C,), 2) * 0.2)
+        ref.running_mean.copy_(seeded_randn((C,), 3) * 0.1)
+        ref.running_var.copy_(seeded_randn((C,), 4).abs() + 0.5)
+    ours = nn.BatchNorm2d(C)
+    ours.load_state_dict(ref.state_dict())
+    ours = ours.to(DEV)
+    for step in range(3):
+        x = seeded_randn((2, C, 9, 11), 10 + step) * (1.0 + step) + 0.3 * step
+        ref.train()
+        y_ref = ref(x)
+        y = ops.batchnorm(x.to(DEV), ours.weight, ours.bias, ours.running_mean, ours.running_var, batch_stats=True, eps=ours.eps,
+                          momentum=ours.momentum, update_running=True, num_batches_tracked=ours.num_batches_tracked)
+        assert rel_l2(y, y_ref.detach()) < 1e-5
+        assert max_abs(ours.running_mean, ref.running_mean) < 1e-6 and rel_l2(ours.running_var, ref.running_var) < 1e-6
+        assert int(ours.num_batches_tracked) == int(ref.num_batches_tracked) == step + 1
+    ref.eval()
+    x = seeded_randn((2, C, 9, 11), 20)
+    y = ops.batchnorm(x.to(DEV), ours.weight, ours.bias, ours.running_mean, ours.running_var, batch_stats=False, eps=ours.eps)
+    assert rel_l2(y, ref(x).detach()) < 1e-5
+    # the differentiable path (training step) applies the same update
+    xg = (seeded_randn((2, C, 9, 11), 30)).to(DEV).requires_grad_(True)
+    ref.train()
+    ref(seeded_randn((2, C, 9, 11), 30))
+    ops.batchnorm(xg, ours.weight, ours.bias, ours.running_mean, ours.running_var, batch_stats=True, eps=ours.eps, momentum=ours.momentum,
+                  update_running=True, num_batches_tracked=ours.num_batches_tracked).sum().backward()
+    assert max_abs(ours.running_mean, ref.running_mean) < 1e-6 and int(ours.num_batches_tracked) == 4

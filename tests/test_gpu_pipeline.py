@@ -14,7 +14,9 @@ TOL = 1e-4        # rel-L2, fp32 path (stated tolerance; SURVEY.md section 7 'Pr
 
 @pytest.fixture(scope="module")
 def model(golden_tiny):
-    return build_tiny_model(golden_tiny, DEV)
+    m = build_tiny_model(golden_tiny, DEV)
+    m._lrnn_snapshot = {k: v.detach().clone() for k, v in m.cond_nets[-1].state_dict().items()}
+    return m
 
 
 @pytest.mark.parametrize("bn_mode", ["batch", "running"])
@@ -23,6 +25,9 @@ def test_inverse_reconstruction_vs_reference(golden_tiny, model, bn_mode, use_mv
     views, mean_vols = tiny_inputs(golden_tiny)
     L = model.n_levels
     mv = [t.to(DEV) for t in mean_vols[:L]] + ([mean_vols[L].to(DEV)] if use_mv else [None])
+    # a .train()-mode forward updates the BatchNorm running statistics (as in the reference): start every case from the
+    # fixture's weights, like the golden generator does (tests/golden/make_golden.py: fill(enc, 300) per case)
+    model.cond_nets[-1].load_state_dict(model._lrnn_snapshot)
     model.cond_nets[-1].train(bn_mode == "batch")
     outs, jacs = model.reconstruct(views.to(DEV), mv, return_all=True)
     model.cond_nets[-1].train()

@@ -470,6 +470,50 @@ def test_unet_ops_adjoints():
         assert rel_l2(a_.grad, c_.grad) < TOL
 
 
+def test_grad_scaler_matches_torch_semantics_and_skips_overflowed_steps(golden_tiny, golden_train):
+    """``GradScaler(init_scale=4)`` as the reference drives it (CWFA.py:613,1005-1015): (a) scale trajectory equals
+    torch.amp.GradScaler's for the same good / overflowed step pattern; (b) a power-of-two loss scale is exact in fp32, so a
+    scaled fp32 run is bit-identical to an unscaled one; (c) an overflowed gradient skips the step and halves the scale."""
+    from cwfa_b200.training import FlowLevelTrainer, GradScaler
+    # (a) trajectory vs torch
+    ref = torch.amp.GradScaler("cuda", init_scale=4.0, growth_interval=3)
+    ours = GradScaler(init_scale=4.0, growth_interval=3)
+    w = torch.nn.Parameter(torch.ones(4, device=DEV))
+    opt = torch.optim.SGD([w], lr=0.0)
+    for bad in (False, False, True, False, False, False, True, True, False):
+        w.grad = torch.full((4,), float("inf") if bad else 1.0, device=DEV)
+        ref.step(opt)
+        ref.update()
+        ours._found_inf = bad
+        ours.update()
+        assert ours.get_scale() == ref.get_scale(), (ours.get_scale(), ref.get_scale())
+    # (b) exactness of a power-of-two scale in fp32
+    inputs = [t.to(DEV) for t in train_inputs(golden_train, 1)]
+    runs = []
+    for scaler in (None, GradScaler(init_scale=4.0)):
+        model = build_tiny_model(golden_tiny, DEV)
+        tr = FlowLevelTrainer(model, 1, lr=2e-4, lr_cond=2e-4, grad_scaler=scaler)
+        for _ in range(3):
+            tr.step(*inputs)
+        runs.append(torch.cat([p.detach().reshape(-1) for p in model.conv_inn[1].parameters() if p.requires_grad]).clone())
+        tr.release()
+    assert torch.equal(runs[0], runs[1])
+    # (c) overflow -> skipped step, scale halves, later steps resume
+    model = build_tiny_model(golden_tiny, DEV)
+    tr = FlowLevelTrainer(model, 1, lr=2e-4, lr_cond=2e-4, precision="fp16")
+    assert tr.scaler is not None and tr.scaler.get_scale() == 4.0          # on by default for the reference's fp16 arithmetic
+    before = torch.cat([p.detach().reshape(-1) for p in model.conv_inn[1].parameters() if p.requires_grad]).clone()
+    tr.scaler.update(new_scale=2.0 ** 120)                                  # forces an overflow of the scaled loss / gradients
+    tr.step(*inputs)
+    after = torch.cat([p.detach().reshape(-1) for p in model.conv_inn[1].parameters() if p.requires_grad])
+    assert torch.equal(before, after) and tr.scaler.get_scale() == 2.0 ** 119 and tr.scaler.skipped_steps == 1
+    tr.scaler.update(new_scale=4.0)
+    parts = tr.step(*inputs)
+    after2 = torch.cat([p.detach().reshape(-1) for p in model.conv_inn[1].parameters() if p.requires_grad])
+    assert not torch.equal(before, after2) and parts["loss_scale"] == 4.0 and torch.isfinite(after2).all()
+    tr.release()
+
+
 def test_zero_grad_set_to_none_between_steps(golden_tiny, golden_train):
     """``model.zero_grad()`` (set_to_none=True is torch's default) drops the ``.grad`` views of the flat buffer; the next
     backward then allocates fresh gradient tensors.  The optimiser must pick those up (and re-home them) instead of crashing or
