@@ -481,6 +481,7 @@ def test_grad_scaler_matches_torch_semantics_and_skips_overflowed_steps(golden_t
     w = torch.nn.Parameter(torch.ones(4, device=DEV))
     opt = torch.optim.SGD([w], lr=0.0)
     for bad in (False, False, True, False, False, False, True, True, False):
+        ref.scale(torch.ones((), device=DEV))                      # torch initialises its scale tensor lazily in scale()
         w.grad = torch.full((4,), float("inf") if bad else 1.0, device=DEV)
         ref.step(opt)
         ref.update()
