@@ -74,9 +74,39 @@ class CWFAEngine:
                 ws = [(mod.subnet.block12 if mod.subnet.normal else mod.subnet.block1) for k_, mod, _ in nodes if k_ == "cat"]
                 batched = tc.PackedConv(torch.cat([w.weight.detach() for w in ws], 0), torch.cat([w.bias.detach() for w in ws], 0),
                                         kind, bn=64)
-            self.levels.append(dict(nodes=nodes, cond=None if self.dlr else _CondNet(m.cond_nets[n], kind), batched_in=batched))
+            self.levels.append(dict(nodes=nodes, cond=None if self.dlr else _CondNet(m.cond_nets[n], kind), batched_in=batched,
+                                    f8=self._plan_f8(nodes, kind)))
         self.lrnn = _LRNN(m.cond_nets[-1], kind)
         self._graphs: Dict = {}
+
+    use_f8 = True          # lean coupling path on the F8 layout (csrc/coupling_f8.cu) for levels made of CAT blocks + permutations
+
+    @staticmethod
+    def _plan_f8(nodes, kind):
+        """F8 plan of a level whose flow is CAT blocks + permutations (the default graph, networks.py:305-366): the detail half
+        stays in the channel order it ENTERED the flow; a channel permutation (fixed_transforms.py:37-41) only updates the map
+        ``m`` (logical channel -> storage slot: m <- m[perm]) and every coupling's last conv is packed with its output channels
+        in storage order.  Returns None when the level has other block types (they run on the NCHW path)."""
+        if not nodes or any(k == "module" for k, _, _ in nodes):
+            return None
+        cats = [mod for k, mod, _ in nodes if k == "cat"]
+        if not cats or any(sub.inp.Cout_p != 64 or sub.out.KH != 3 for k, _, sub in nodes if k == "cat") or cats[0].channels > 48:
+            return None
+        ch = cats[0].channels
+        dev = next(cats[0].parameters()).device
+        m = torch.arange(ch)
+        packed = []
+        for k, mod, extra in nodes:
+            if k == "perm" and extra == 1:
+                m = m[mod.perm.detach().cpu().long()]
+            elif k == "cat":
+                minv = torch.empty_like(m)
+                minv[m] = torch.arange(ch)
+                last = mod.subnet.block72[1] if mod.subnet.normal else mod.subnet.block7[1]
+                packed.append(tc.coupling_weights_f8(last.weight, last.bias, ch, minv, not mod.subnet.normal, kind))
+        minv = torch.empty_like(m)
+        minv[m] = torch.arange(ch)
+        return dict(ch=ch, out=packed, z_from_storage=m.to(dev, torch.int32).contiguous(), storage_from_z=minv.to(dev, torch.int32).contiguous())
 
     # -------------------------------------------------------------------------------------
     def _trunks(self, n: int, lf8: tc.C8):
@@ -147,6 +177,9 @@ class CWFAEngine:
         ``disable_low_res_input``.  ``z`` None = zeros (INN_z_temperature = 0, CWFA.py:906-907: z is never materialised);
         otherwise the latent sample(s) of this level (``sample_z_truncated``, CWFA.py:47-64), ``rows`` of them."""
         items = self._trunks(n, lf8)
+        plan = self.levels[n]["f8"] if (self.use_f8 and (lf8.H * lf8.W) % 4 == 0) else None
+        if plan is not None and (z is None or z.shape[0] == lf8.N):
+            return self._level_detail_inverse_f8(n, items, plan, lf8, mean_vol, z)
         hi, pending = z, None
         jac, tickets = self._jac_and_tickets(rows if z is None else z.shape[0], lf8.data.device)
         lf_nchw, k = None, 0
@@ -170,6 +203,39 @@ class CWFAEngine:
         if pending is not None:
             hi = ops.permute(hi, pending[0], pending[1])
         return hi, jac
+
+    def _couple_f8(self, item, pc, x8, mv8, pending, inverse, logdet, sumsq, ticket):
+        _, mod, sub, b8 = item
+        first = not sub.normal
+        perm, axis = (None, 0) if pending is None else (ops.perm_i32(pending[0], b8.data.device), pending[1])
+        return tc.coupling_f8(b8, pc, x8, ch=mod.channels, inverse=inverse, clamp=mod.clamp, t_ext8=mv8 if first else None,
+                              t_scale=(-1.0 / math.sqrt(2)) if first else 1.0, perm=perm, perm_axis=axis, logdet=logdet, sumsq=sumsq,
+                              ticket=ticket)
+
+    @staticmethod
+    def _permute_f8(x8, ch, perm, axis):
+        """Row / column permutation of an F8 tensor that no coupling follows (never the case in CWFA's graphs): via NCHW."""
+        return tc.to_f8(ops.permute(tc.from_f8(x8, ch), perm, axis))
+
+    def _level_detail_inverse_f8(self, n, items, plan, lf8, mean_vol, z):
+        """Inverse of a CAT-only level on the F8 layout: returns (("f8", hi8), logdet)."""
+        ch = plan["ch"]
+        hi = None if z is None else tc.to_f8(z, plan["storage_from_z"])
+        mv8 = None if mean_vol is None else tc.to_f8(mean_vol)
+        jac, tickets = self._jac_and_tickets(lf8.N, lf8.data.device)
+        pending, k = None, 0
+        pcs = plan["out"]
+        ci = len(pcs)
+        for item in reversed(items):
+            if item[0] == "cat":
+                ci -= 1
+                hi = self._couple_f8(item, pcs[ci], hi, mv8, pending, True, jac, None, tickets[k:k + 1])
+                pending, k = None, (k + 1) % tickets.numel()
+            elif item[2] != 1 and hi is not None:               # row / column permutation: gathered by the next coupling
+                pending = (item[1].perm_inv, item[2])
+        if pending is not None:
+            hi = self._permute_f8(hi, ch, pending[0], pending[1])
+        return ("f8", hi), jac
 
     @torch.no_grad()
     def reconstruct(self, views: torch.Tensor, mean_vols: Sequence[Optional[torch.Tensor]], return_all: bool = False,
@@ -201,15 +267,20 @@ class CWFAEngine:
                                           temperature=T)
             return None
 
-        def finish(hi):
-            return ops.batch_mean(hi) if (n_samples > 1 and hi.shape[0] > 1) else hi
+        def merge(vol, hi):
+            """Split^-1 + IDWT of a level; the detail half arrives in NCHW or (CAT-only levels) in the F8 layout."""
+            if isinstance(hi, tuple):
+                return tc.haar1d_merge_f8(vol, hi[1])
+            if n_samples > 1 and hi.shape[0] > 1:
+                hi = ops.batch_mean(hi)
+            return ops.haar1d_merge(vol, hi)
 
         if self.dlr:                                         # sequential pyramid: the condition is the volume of the level below
             vol = self.lrnn(v8, mv_last)
             outs, jacs = {L1: vol}, {}
             for n in range(L1 - 1, -1, -1):
                 hi, jac = self._level_detail_inverse(n, self._lf(n, None, vol), None, z_of(n), B)
-                vol = ops.haar1d_merge(vol, finish(hi))
+                vol = merge(vol, hi)
                 outs[n], jacs[n] = vol, jac
             return (outs, jacs) if return_all else vol
         jobs = [lambda: self.lrnn(v8, mv_last)] + [(lambda n=n: self._level_detail_inverse(n, self._lf(n, v8, None), mean_vols[n], z_of(n), B))
@@ -234,12 +305,31 @@ class CWFAEngine:
         outs, jacs = {L1: vol}, {}
         for k, n in enumerate(range(L1 - 1, -1, -1)):
             hi, jac = results[1 + k]
-            vol = ops.haar1d_merge(vol, finish(hi))  # Split^-1 + IDWT: the only sequential part of the pyramid
+            vol = merge(vol, hi)                     # Split^-1 + IDWT: the only sequential part of the pyramid
             outs[n], jacs[n] = vol, jac
         return (outs, jacs) if return_all else vol
 
+    def _level_forward_f8(self, n, plan, hi8, lf8, mean_vol):
+        ch = plan["ch"]
+        jac, tickets = self._jac_and_tickets(hi8.shape[0], hi8.device)
+        sumsq = torch.empty_like(jac)
+        mv8 = None if mean_vol is None else tc.to_f8(mean_vol)
+        pending, k, ci = None, 0, 0
+        for item in self._trunks(n, lf8):
+            if item[0] == "cat":
+                hi8 = self._couple_f8(item, plan["out"][ci], hi8, mv8, pending, False, jac, sumsq, tickets[k:k + 1])   # sumsq: last coupling wins
+                pending, k, ci = None, (k + 1) % tickets.numel(), ci + 1
+            elif item[2] != 1:
+                pending = (item[1].perm, item[2])
+        if pending is not None:
+            hi8 = self._permute_f8(hi8, ch, pending[0], pending[1])
+        return tc.from_f8(hi8, ch, plan["z_from_storage"]), jac, sumsq
+
     def _level_forward(self, n, hi, lf8, mean_vol):
-        """Detail half of level n through the flow in the forward direction: (z, logdet[B], sumsq[B])."""
+        """Detail half of level n through the flow in the forward direction: (z, logdet[B], sumsq[B]).  ``hi``: NCHW tensor, or
+        ("f8", tensor) from ``haar1d_split_f8`` for CAT-only levels."""
+        if isinstance(hi, tuple):
+            return self._level_forward_f8(n, self.levels[n]["f8"], hi[1], lf8, mean_vol)
         jac, tickets = self._jac_and_tickets(hi.shape[0], hi.device)
         sumsq = None
         pending, k, lf_nchw = None, 0, None
@@ -277,7 +367,11 @@ class CWFAEngine:
         los, his = [], []
         x = volume
         for n in range(L1):
-            lo, hi = ops.haar1d_split(x)
+            if self.use_f8 and self.levels[n]["f8"] is not None and (x.shape[2] * x.shape[3]) % 4 == 0:
+                lo, hi8 = tc.haar1d_split_f8(x)
+                hi = ("f8", hi8)
+            else:
+                lo, hi = ops.haar1d_split(x)
             los.append(lo)
             his.append(hi)
             x = lo

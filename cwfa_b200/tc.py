@@ -290,3 +290,91 @@ def conv_tc_coupling(b: C8, pc: PackedConv, x: Optional[torch.Tensor], *, ch: in
               float(clamp), float(k_atan), int(inverse), ws.data_ptr(), b.is_bf16, _stream())
     _lib.call("cwfa_coupling_finalize", ws.data_ptr(), logdet.data_ptr(), _p(sumsq), N, tiles, int(accumulate), _stream())
     return y
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# F8: the detail half of a flow level as [N][ceil(ch/8)][H][W][8] fp32 (csrc/coupling_f8.cu) -- the engine's coupling state
+# ---------------------------------------------------------------------------------------------------------------------
+def ch8(ch: int) -> int:
+    return (ch + 7) // 8 * 8
+
+
+def _i32(t: Optional[torch.Tensor], device) -> Optional[torch.Tensor]:
+    return None if t is None else t.to(device=device, dtype=torch.int32).contiguous()
+
+
+def to_f8(x: torch.Tensor, chan_map: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(N,C,H,W) fp32 -> F8 (N, ceil(C/8), H, W, 8); slot j holds channel ``chan_map[j]`` (identity when None)."""
+    x = _ck(x, "x")
+    N, C, H, W = x.shape
+    y = torch.empty((N, ch8(C) // 8, H, W, 8), device=x.device, dtype=torch.float32)
+    _lib.call("cwfa_nchw_to_f8", x.data_ptr(), _p(chan_map), y.data_ptr(), N, C, H * W, _stream())
+    return y
+
+
+def from_f8(x8: torch.Tensor, C: int, chan_map: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """F8 -> (N,C,H,W) fp32; channel c reads slot ``chan_map[c]`` (identity when None)."""
+    N, G, H, W, _ = x8.shape
+    y = torch.empty((N, C, H, W), device=x8.device, dtype=torch.float32)
+    _lib.call("cwfa_f8_to_nchw", x8.data_ptr(), _p(chan_map), y.data_ptr(), N, C, H * W, _stream())
+    return y
+
+
+def haar1d_split_f8(x: torch.Tensor):
+    """Fused DWT + Split: (B,C,H,W) -> lo (B,C/2,H,W) NCHW and the detail half in F8."""
+    x = _ck(x, "x")
+    B, C, H, W = x.shape
+    h = C // 2
+    lo = torch.empty((B, h, H, W), device=x.device, dtype=torch.float32)
+    hi = torch.empty((B, ch8(h) // 8, H, W, 8), device=x.device, dtype=torch.float32)
+    _lib.call("cwfa_haar1d_fwd_f8", x.data_ptr(), lo.data_ptr(), hi.data_ptr(), B, C, H * W, _stream())
+    return lo, hi
+
+
+def haar1d_merge_f8(lo: torch.Tensor, hi8: torch.Tensor) -> torch.Tensor:
+    """Fused Split^-1 + IDWT: lo (B,h,H,W) NCHW + detail half in F8 -> (B,2h,H,W)."""
+    lo = _ck(lo, "lo")
+    B, h, H, W = lo.shape
+    if tuple(hi8.shape) != (B, ch8(h) // 8, H, W, 8):
+        raise ValueError(f"haar1d_merge_f8: detail half has shape {tuple(hi8.shape)}, expected {(B, ch8(h) // 8, H, W, 8)}")
+    out = torch.empty((B, 2 * h, H, W), device=lo.device, dtype=torch.float32)
+    _lib.call("cwfa_haar1d_inv_f8", lo.data_ptr(), hi8.data_ptr(), out.data_ptr(), B, 2 * h, H * W, _stream())
+    return out
+
+
+def coupling_weights_f8(weight: torch.Tensor, bias: torch.Tensor, ch: int, slot_to_chan: torch.Tensor, ext: bool, kind: str) -> "PackedConv":
+    """Last conv of a coupling sub-network re-ordered for ``coupling_f8``: output column j (< chp8) = s of storage slot j =
+    conv channel ``slot_to_chan[j]``, column chp8 + j = its t (``ext``: s only); padding slots get zero weights and bias."""
+    c8 = ch8(ch)
+    w, b = weight.detach().float(), bias.detach().float()
+    rows = c8 if ext else 2 * c8
+    wn = torch.zeros((rows,) + tuple(w.shape[1:]), device=w.device, dtype=torch.float32)
+    bn_ = torch.zeros(rows, device=w.device, dtype=torch.float32)
+    idx = slot_to_chan.to(w.device).long()
+    wn[:ch] = w[idx]
+    bn_[:ch] = b[idx]
+    if not ext:
+        wn[c8:c8 + ch] = w[ch + idx]
+        bn_[c8:c8 + ch] = b[ch + idx]
+    return PackedConv(wn, bn_, kind, bn=pad16(rows))
+
+
+def coupling_f8(b: C8, pc: PackedConv, x8: Optional[torch.Tensor], *, ch: int, inverse: bool, clamp: float = 2.0, k_atan: float = 0.636,
+                t_ext8: Optional[torch.Tensor] = None, t_scale: float = 1.0, perm: Optional[torch.Tensor] = None, perm_axis: int = 0,
+                logdet: torch.Tensor = None, sumsq: Optional[torch.Tensor] = None, accumulate: bool = True,
+                ticket: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``conv_tc_coupling`` on the F8 detail half (lean epilogue; channel permutations live in ``pc``'s column order)."""
+    if b.Cp != 64 or pc.Cin_p != 64 or pc.KH != 3 or pc.KW != 3 or b.kind != pc.kind or pc.BN != pc.Cout_p:
+        raise ValueError("coupling_f8: needs a 3x3 conv from 64 hidden channels packed in one n-block")
+    N, H, W = b.N, b.H, b.W
+    c8 = ch8(ch)
+    y = torch.empty((N, c8 // 8, H, W, 8), device=b.data.device, dtype=torch.float32)
+    lib = _lib.load()
+    tiles = lib.cwfa_coupling_tc_tiles(H, W)
+    ws = torch.empty(2 * N * tiles, device=b.data.device, dtype=torch.float32)
+    _lib.call("cwfa_coupling_f8", b.data.data_ptr(), pc.packed.data_ptr(), _p(pc.bias), N, H, W, pc.BN, c8, _p(x8), y.data_ptr(),
+              _p(t_ext8), float(t_scale), _p(perm), int(perm_axis), float(clamp), float(k_atan), int(inverse), ws.data_ptr(),
+              logdet.data_ptr(), _p(sumsq), int(accumulate), _p(ticket), b.is_bf16, _stream())
+    if ticket is None:
+        _lib.call("cwfa_coupling_finalize", ws.data_ptr(), logdet.data_ptr(), _p(sumsq), N, tiles, int(accumulate), _stream())
+    return y

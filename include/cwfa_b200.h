@@ -218,6 +218,25 @@ int cwfa_coupling_tc(const void* b_c8, const void* w_packed, const float* bias, 
                      int Cout_p, const float* cx, float* cy, const float* ct, float t_scale, const int32_t* perm,
                      int perm_axis, int ch, float clamp, float k_atan, int inverse, float* workspace, float* logdet,
                      float* sumsq, int accumulate, int32_t* ticket, int is_bf16, void* stream);
+/* ---- the coupling path on the "F8" layout of a level's detail half: [N][ceil(ch/8)][H][W][8] fp32, channel padding zero
+ * (csrc/coupling_f8.cu).  cwfa_coupling_f8 = cwfa_coupling_tc with a lean epilogue: x / y / external shift as 128-bit
+ * vectors, no channel gather (the caller permutes the OUTPUT CHANNELS of w_packed so that [s | t] arrive in storage order:
+ * columns [0,chp8) = s of slot j, [chp8,2 chp8) = t of slot j; with ct != NULL columns [0,chp8) = s only), bias through an
+ * extra MMA, row (perm_axis 2) / column (perm_axis 3) permutations as a gather on cx.  chp8 = 8 * ceil(ch / 8) <= 48; BN =
+ * number of conv output columns (one n-block, multiple of 16, <= 96).  workspace / logdet / sumsq / accumulate / ticket as in
+ * cwfa_coupling_tc (tiles = cwfa_coupling_tc_tiles(H, W)). */
+int cwfa_coupling_f8(const void* b_c8, const void* w_packed, const float* bias, int N, int H, int W, int BN, int chp8,
+                     const float* cx, float* cy, const float* ct, float t_scale, const int32_t* perm, int perm_axis,
+                     float clamp, float k_atan, int inverse, float* workspace, float* logdet, float* sumsq, int accumulate,
+                     int32_t* ticket, int is_bf16, void* stream);
+/* Depth-wise Haar DWT + Split (INN_utils.py:142-161, graph_topology.py:73-80) with the detail half written / read in F8:
+ * fwd: x (B,C,P) -> lo (B,C/2,P) NCHW, hi F8;  inv: lo, hi F8 -> x.  P % 4 == 0, pointers 16-byte aligned; every access 128-bit. */
+int cwfa_haar1d_fwd_f8(const float* x, float* lo, float* hi_f8, int B, int C, int64_t P, void* stream);
+int cwfa_haar1d_inv_f8(const float* lo, const float* hi_f8, float* x, int B, int C, int64_t P, void* stream);
+/* NCHW fp32 <-> F8 with an optional int32 channel map (NULL = identity): to_f8: slot j = channel map[j]; to_nchw: channel c =
+ * slot map[c] (the flow's accumulated channel permutation, fixed_transforms.py:37-41, applied once at the boundary). */
+int cwfa_nchw_to_f8(const float* x, const int32_t* map, float* y_f8, int B, int C, int64_t P, void* stream);
+int cwfa_f8_to_nchw(const float* x_f8, const int32_t* map, float* y, int B, int C, int64_t P, void* stream);
 /* Layout converters NCHW fp32 <-> C8 half (channels padded with zeros up to Cp). */
 int cwfa_nchw_to_c8(const float* x, void* y, int N, int C, int Cp, int64_t P, int is_bf16, void* stream);
 int cwfa_c8_to_nchw(const void* x, float* y, int N, int C, int Cp, int64_t P, int is_bf16, void* stream);

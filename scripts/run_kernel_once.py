@@ -56,6 +56,20 @@ if what == "coupling":
         us = bench(lambda i: tc.conv_tc_coupling(bs[i], pc, xs[i], ch=ch, inverse=True, perm=perm, perm_axis=1, logdet=ld), n)
         if us:
             print(f"coupling_tc ch={ch} (+ finalize launch): {us:.1f} us", flush=True)
+elif what == "coupling_f8":
+    for ch in ((48, 24, 12, 6) if timed else (48,)):
+        n = 6
+        c8 = tc.ch8(ch)
+        bs = [tc.to_c8(torch.randn(1, 64, 512, 512, device=DEV)) for _ in range(n)]
+        pc = tc.coupling_weights_f8(torch.randn(2 * ch, 64, 3, 3, device=DEV) * 0.04, torch.zeros(2 * ch, device=DEV), ch, torch.randperm(ch), False, "bf16")
+        xs = [tc.to_f8(torch.randn(1, ch, 512, 512, device=DEV)) for _ in range(n)]
+        perm = torch.randperm(512, device=DEV).to(torch.int32)
+        ld = torch.zeros(1, device=DEV)
+        tk = torch.zeros(8, device=DEV, dtype=torch.int32)
+        us = bench(lambda i: tc.coupling_f8(bs[i], pc, xs[i], ch=ch, inverse=True, perm=perm, perm_axis=2, logdet=ld, ticket=tk[:1]), n)
+        if us:
+            fl = 2.0 * P * 64 * 2 * ch * 9
+            print(f"coupling_f8 ch={ch}: {us:.1f} us  {fl / us / 1e6:.0f} TFLOP/s", flush=True)
 elif what == "resblock":
     n = 8
     xin = [tc.to_c8(torch.randn(1, 64, 512, 512, device=DEV)) for _ in range(n)]

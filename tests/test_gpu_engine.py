@@ -130,3 +130,54 @@ def test_engine_inverse_with_latent_samples(golden_tiny, model):
     for n in ref_j:
         assert abs(float(jacs[n][0]) - float(ref_j[n][0])) < 5e-3 * max(1.0, abs(float(ref_j[n][0])))
     assert rel_l2(ref[0], out0) > 1e-2          # the samples matter
+
+
+# ---- the F8 coupling path (csrc/coupling_f8.cu) ------------------------------------------------------------------------
+@pytest.mark.parametrize("B,C,H,W", [(1, 16, 64, 64), (2, 12, 8, 12), (1, 96, 32, 32), (3, 4, 6, 6)])
+def test_f8_haar_and_converters_vs_oracle(B, C, H, W):
+    """Depth-wise Haar + Split with the detail half in the F8 layout, and the NCHW <-> F8 converters with a channel map, against
+    the oracle's Haar (INN_utils.py:142-161) -- bit-level: same arithmetic, other layout."""
+    from cwfa_b200 import tc
+    x = seeded_randn((B, C, H, W), 70)
+    y, _ = O.haar1d(x)
+    h = C // 2
+    lo, hi8 = tc.haar1d_split_f8(x.to(DEV))
+    assert max_abs(lo, y[:, :h]) < 1e-6 and max_abs(tc.from_f8(hi8, h), y[:, h:]) < 1e-6
+    if h % 8:
+        assert float(hi8.reshape(B, -1, H * W, 8)[:, -1, :, h % 8:].abs().max()) == 0.0        # channel padding is zero
+    assert max_abs(tc.haar1d_merge_f8(lo, hi8), x) < 1e-6
+    perm = torch.from_numpy(__import__("numpy").random.RandomState(3).permutation(h)).to(torch.int32).to(DEV)
+    z = seeded_randn((B, h, H, W), 71).to(DEV)
+    z8 = tc.to_f8(z, perm)                                                                   # slot j = channel perm[j]
+    assert torch.equal(tc.from_f8(z8, h), z[:, perm.long()])
+    inv = torch.empty_like(perm)
+    inv[perm.long()] = torch.arange(h, device=DEV, dtype=torch.int32)
+    assert torch.equal(tc.from_f8(z8, h, inv), z)                                            # channel c = slot inv[c]
+
+
+@pytest.mark.parametrize("kind", ["bf16", "fp16"])
+def test_engine_f8_path_equals_nchw_path(golden_tiny, model, kind):
+    """The lean F8 coupling path (channel permutations folded into the packed weights, bias through an MMA, 128-bit I/O) against
+    the NCHW coupling path of the same engine: inverse (z = 0 and given z) and forward NLL; differences are fp32 rounding only."""
+    from cwfa_b200.engine import CWFAEngine
+    views, mean_vols = tiny_inputs(golden_tiny)
+    views, mv = views.to(DEV), [t.to(DEV) for t in mean_vols]
+    eng = CWFAEngine(model, kind)
+    assert all(lv["f8"] is not None for lv in eng.levels)
+    zs = [seeded_randn((1,) + tuple(model.conv_inn[n].global_out_shapes[0]), 130 + n, 0.5).to(DEV) for n in range(model.n_levels)]
+    cfg = golden_tiny["config"]
+    x = seeded_randn((2, cfg["D"], cfg["S"], cfg["S"]), 2).to(DEV)
+    vB = seeded_randn((2, 29, cfg["S"], cfg["S"]), 3).to(DEV)
+    mvB = [t.repeat(2, 1, 1, 1) for t in mv[:model.n_levels]]
+    res = {}
+    for f8 in (True, False):
+        eng.use_f8 = f8
+        res[f8] = (eng.reconstruct(views, mv, return_all=True), eng.reconstruct(views, mv, zs=zs, return_all=True), eng.forward_nll(x, vB, mvB))
+    for a, b in ((res[True][0], res[False][0]), (res[True][1], res[False][1])):
+        for n in a[0]:
+            assert rel_l2(a[0][n], b[0][n]) < 2e-5, (n, rel_l2(a[0][n], b[0][n]))
+        for n in a[1]:
+            assert abs(float(a[1][n][0] - b[1][n][0])) < 1e-4 * max(1.0, abs(float(b[1][n][0])))
+    for ra, rb in zip(res[True][2], res[False][2]):
+        assert rel_l2(ra["z"], rb["z"]) < 2e-5 and rel_l2(ra["logdet"], rb["logdet"]) < 1e-4 and rel_l2(ra["sumsq"], rb["sumsq"]) < 1e-4
+        assert torch.equal(ra["lo"], rb["lo"])
