@@ -6,6 +6,7 @@ import torch
 
 from conftest import max_abs, rel_l2
 from helpers import build_tiny_model, tiny_inputs
+from oracle import cwfa_oracle as O
 from oracle.weights import seeded_randn
 
 pytestmark = pytest.mark.gpu
