@@ -54,9 +54,10 @@ _SIGS = {
     "cwfa_conv_tc_coupling": [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, f32, vp, i32, i32, f32, f32,
                               i32, vp, i32, vp],
     "cwfa_coupling_tc_tiles": [i32, i32],
-    "cwfa_coupling_tc": [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, f32, vp, i32, i32, f32, f32, i32, vp, vp, vp, i32, vp, i32, vp],
+    "cwfa_coupling_tc": [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, f32, vp, i32, i32, f32, f32, i32, vp, vp, vp, i32, vp, i32, i32, i32, vp],
+    "cwfa_resblock_tc_batched": [vp, vp, i32, vp, vp, vp, vp, i32, i32, i32, i32, vp, i32, vp, i32, vp],
     "cwfa_coupling_finalize": [vp, vp, vp, i32, i32, i32, vp],
-    "cwfa_coupling_f8": [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, f32, vp, i32, f32, f32, i32, vp, vp, vp, i32, vp, i32, vp],
+    "cwfa_coupling_f8": [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, f32, vp, i32, f32, f32, i32, vp, vp, vp, i32, vp, i32, i32, i32, vp],
     "cwfa_haar1d_fwd_f8": [vp, vp, vp, i32, i32, i64, vp],
     "cwfa_haar1d_inv_f8": [vp, vp, vp, i32, i32, i64, vp],
     "cwfa_nchw_to_f8": [vp, vp, vp, i32, i32, i64, vp],

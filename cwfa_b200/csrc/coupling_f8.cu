@@ -39,7 +39,7 @@ constexpr int kMaxG = 3;                                     // 8-channel groups
 
 struct F8Params {
     int N, H, W, tiles_x, tiles_y, num_tiles;
-    int BN, chp8, axis, a_stages;
+    int BN, chp8, axis, a_stages, in_chunk_off;
     uint32_t off_a;
     const uint8_t* w;            // packed [9][8][BN][8]
     const float* bias;           // BN floats or NULL
@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(kThreads, 1) coupling_f8_kernel(const __grid_c
                 const int h0 = (r / p.tiles_x) * kTH, w0 = (r % p.tiles_x) * kTW;
                 mbar_wait(a_empty(sa), pa ^ 1);
                 mbar_expect_tx(a_full(sa), kA1Bytes);
-                tma_load_4d(s0 + p.off_a + sa * kA1Bytes, &tmap, a_full(sa), (w0 - 1) * 8, h0 - 1, 0, n);
+                tma_load_4d(s0 + p.off_a + sa * kA1Bytes, &tmap, a_full(sa), (w0 - 1) * 8, h0 - 1, p.in_chunk_off, n);
                 if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
             }
         }
@@ -486,10 +486,10 @@ extern "C" int cwfa_f8_to_nchw(const float* x_f8, const int32_t* map, float* y, 
 extern "C" int cwfa_coupling_f8(const void* b_c8, const void* w_packed, const float* bias, int N, int H, int W, int BN, int chp8,
                                 const float* cx, float* cy, const float* ct, float t_scale, const int32_t* perm, int perm_axis,
                                 float clamp, float k_atan, int inverse, float* workspace, float* logdet, float* sumsq, int accumulate,
-                                int32_t* ticket, int is_bf16, void* stream) {
+                                int32_t* ticket, int in_total_chunks, int in_chunk_off, int is_bf16, void* stream) {
     if (N <= 0 || H <= 0 || W <= 0 || (int64_t)chp8 * H * W >= (1ll << 31) || !cy || !workspace || chp8 <= 0 || chp8 > 48 || (chp8 & 7) ||
         BN > kMaxBN || (BN % 16) || (ct ? BN < chp8 : BN < 2 * chp8) || (perm && perm_axis != 2 && perm_axis != 3) || (!cx && !inverse) ||
-        (ticket && !logdet)) {
+        (ticket && !logdet) || in_chunk_off < 0 || in_chunk_off + kChunks > in_total_chunks) {
         set_error("coupling_f8: unsupported arguments (needs 64 -> BN <= 96 in one n-block, chp8 <= 48 multiple of 8, row / column perms only)");
         return CWFA_EINVAL;
     }
@@ -512,7 +512,8 @@ extern "C" int cwfa_coupling_f8(const void* b_c8, const void* w_packed, const fl
     p.tscale = t_scale;
     p.logdet = logdet; p.sumsq = sumsq; p.ticket = ticket; p.accumulate = accumulate;
     CUtensorMap tmap;
-    int rc = make_c8_tensor_map(&tmap, b_c8, N, kChunks, H, W, kBW, kBH, kChunks, is_bf16);
+    p.in_chunk_off = in_chunk_off;
+    int rc = make_c8_tensor_map(&tmap, b_c8, N, in_total_chunks, H, W, kBW, kBH, kChunks, is_bf16);
     if (rc) return rc;
     typedef void (*KernT)(const CUtensorMap, const F8Params);
     static const KernT table[2][4] = {

@@ -24,7 +24,7 @@ constexpr int kMaxG = 3;                                      // 8-channel group
 
 struct CpParams {
     int N, H, W, tiles_x, tiles_y, num_tiles;
-    int BN, ch, axis, a_stages;
+    int BN, ch, axis, a_stages, in_chunk_off;
     uint32_t off_a;
     const uint8_t* w;            // packed [9][8][BN][8]
     const float* bias;           // BN floats or NULL
@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(kThreads, 1) coupling_tc_kernel(const __grid_c
                 const int h0 = (r / p.tiles_x) * kTH, w0 = (r % p.tiles_x) * kTW;
                 mbar_wait(a_empty(sa), pa ^ 1);
                 mbar_expect_tx(a_full(sa), kA1Bytes);
-                tma_load_4d(s0 + p.off_a + sa * kA1Bytes, &tmap, a_full(sa), (w0 - 1) * 8, h0 - 1, 0, n);
+                tma_load_4d(s0 + p.off_a + sa * kA1Bytes, &tmap, a_full(sa), (w0 - 1) * 8, h0 - 1, p.in_chunk_off, n);
                 if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
             }
         }
@@ -298,9 +298,11 @@ extern "C" int cwfa_coupling_tc_tiles(int H, int W) { return ceil_div(W, kTW) * 
 extern "C" int cwfa_coupling_tc(const void* b_c8, const void* w_packed, const float* bias, int N, int H, int W, int Cout,
                                 int Cout_p, const float* cx, float* cy, const float* ct, float t_scale, const int32_t* perm,
                                 int perm_axis, int ch, float clamp, float k_atan, int inverse, float* workspace, float* logdet,
-                                float* sumsq, int accumulate, int32_t* ticket, int is_bf16, void* stream) {
+                                float* sumsq, int accumulate, int32_t* ticket, int in_total_chunks, int in_chunk_off, int is_bf16,
+                                void* stream) {
     if (N <= 0 || H <= 0 || W <= 0 || (int64_t)ch * H * W >= (1ll << 31) || !cy || !workspace || ch <= 0 || ch > 48 || Cout_p > kMaxBN || (Cout_p % 16) ||
-        (ct ? Cout < ch : Cout < 2 * ch) || (perm && (perm_axis < 1 || perm_axis > 3)) || (!cx && !inverse) || (ticket && !logdet)) {
+        (ct ? Cout < ch : Cout < 2 * ch) || (perm && (perm_axis < 1 || perm_axis > 3)) || (!cx && !inverse) || (ticket && !logdet) ||
+        in_chunk_off < 0 || in_chunk_off + kChunks > in_total_chunks) {
         set_error("coupling_tc: unsupported arguments (needs 64 -> Cout_p <= 96, ch <= 48)");
         return CWFA_EINVAL;
     }
@@ -319,7 +321,8 @@ extern "C" int cwfa_coupling_tc(const void* b_c8, const void* w_packed, const fl
     p.kk = clamp * k_atan; p.tscale = t_scale;
     p.logdet = logdet; p.sumsq = sumsq; p.ticket = ticket; p.accumulate = accumulate;
     CUtensorMap tmap;
-    int rc = make_c8_tensor_map(&tmap, b_c8, N, kChunks, H, W, kBW, kBH, kChunks, is_bf16);
+    p.in_chunk_off = in_chunk_off;
+    int rc = make_c8_tensor_map(&tmap, b_c8, N, in_total_chunks, H, W, kBW, kBH, kChunks, is_bf16);
     if (rc) return rc;
     typedef void (*KernT)(const CUtensorMap, const CpParams);
     static const KernT table[2][4] = {

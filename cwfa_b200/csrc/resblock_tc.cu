@@ -23,21 +23,26 @@ constexpr uint32_t kW1Bytes = kTapBytes;                      // 8192
 constexpr uint32_t kA2MbBytes = kChunks * 128 * 16;           // 16384 per M-block
 constexpr uint32_t kHeader = 2048;
 constexpr uint32_t kOnesBytes = 2 * 128 * 16;                // A tile of the bias MMA: [2 chunks][128 rows][8], e0 = e1 = 1
-constexpr uint32_t kBiasBytes = 2 * kC * 16;                 // B tile of the bias MMA: [2 chunks][64 n][8], e0 = hi, e1 = lo
+constexpr int kMaxSets = 5;                                  // weight sets (sub-networks) one launch can walk
+constexpr uint32_t kBiasRow = kC * 16;                       // chunk 0 of one bias B tile: [64 n][8], e0 = hi, e1 = lo (1 KB)
+// bias tiles: [set][conv 0 = 3x3 | 1 = 1x1] chunk-0 rows, then ONE shared all-zero chunk (chunk 1 of every tile: LBO points at it)
+constexpr uint32_t kBiasBytes = (2 * kMaxSets + 1) * kBiasRow;
 constexpr uint32_t kOffW3 = kHeader, kOffW1 = kOffW3 + kW3Bytes, kOffA1 = kOffW1 + kW1Bytes,
-                   kOffA2 = kOffA1 + 2 * kA1Bytes, kOffOnes = kOffA2 + 2 * kA2MbBytes, kOffB3 = kOffOnes + kOnesBytes,
-                   kOffB1 = kOffB3 + kBiasBytes, kSmemTotal = kOffB1 + kBiasBytes;
+                   kOffA2 = kOffA1 + 2 * kA1Bytes, kOffOnes = kOffA2 + 2 * kA2MbBytes, kOffBias = kOffOnes + kOnesBytes,
+                   kOffZero = kOffBias + 2 * kMaxSets * kBiasRow, kSmemTotal = kOffBias + kBiasBytes;
 constexpr int kThreads = 448;        // warp0 TMA, warp1 MMA, warps2-5 EPI1, warps6-13 EPI2 (one M-block per warp set)
 
 struct RbParams {
-    int N, H, W, tiles_x, tiles_y, num_tiles;
-    int in_total_chunks, in_chunk_off, out_total_chunks, out_chunk_off;
+    int N, H, W, tiles_x, tiles_y, num_tiles;        // num_tiles = n_sets * tiles_per_set
+    int n_sets, tiles_per_set;                       // weight sets (independent sub-network blocks) walked by ONE launch
+    int in_total_chunks, out_total_chunks;
+    int in_chunk_off[kMaxSets], out_chunk_off[kMaxSets];
     const uint8_t* x;        // input C8 tensor base (also the residual)
     uint8_t* y;              // output C8 tensor base
-    const uint8_t* w3;       // packed [9][8][64][8]
-    const uint8_t* w1;       // packed [8][64][8]
-    const float* b3;         // 64
-    const float* b1;         // 64
+    const uint8_t* w3[kMaxSets];       // packed [9][8][64][8]
+    const uint8_t* w1[kMaxSets];       // packed [8][64][8]
+    const float* b3[kMaxSets];         // 64
+    const float* b1[kMaxSets];         // 64
     unsigned long long* dbg;  // optional profiling stamps: [cta][tile<8][8]
 };
 __device__ __forceinline__ void rb_stamp(const RbParams& p, int tile, int slot) {
@@ -61,7 +66,7 @@ __global__ void __launch_bounds__(kThreads, 1) resblock_tc_kernel(const __grid_c
     auto acc1_empty = [&](int b) { return s0 + 8u * (7 + b); };
     auto acc2_full = [&](int b) { return s0 + 8u * (9 + b); };
     auto acc2_empty = [&](int b) { return s0 + 8u * (11 + b); };
-    const uint32_t a2_full = s0 + 8u * 13, a2_empty = s0 + 8u * 14;
+    const uint32_t a2_full = s0 + 8u * 13, a2_empty = s0 + 8u * 14, w_empty = s0 + 8u * 15;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 128);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -77,20 +82,21 @@ __global__ void __launch_bounds__(kThreads, 1) resblock_tc_kernel(const __grid_c
         }
         mbar_init(a2_full, 128);
         mbar_init(a2_empty, 1);
+        mbar_init(w_empty, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // Biases enter the accumulators through one extra K=16 MMA per GEMM: A = "ones" tile (columns k=0,1 are 1),
     // B rows k=0 / k=1 = bf16 hi / lo parts of the fp32 bias (hi + lo reproduces it to ~2^-17 relative).
-    for (int i = threadIdx.x; i < (int)(kOnesBytes + 2 * kBiasBytes) / 16; i += kThreads) {
+    for (int i = threadIdx.x; i < (int)(kOnesBytes + kBiasBytes) / 16; i += kThreads) {
         uint4 v = make_uint4(0, 0, 0, 0);
         const int ones_units = kOnesBytes / 16;
         if (i < 128) {
             v.x = pack2<BF16>(1.f, 1.f);                                  // chunk 0 of the ones tile: e0 = e1 = 1
         } else if (i >= ones_units) {
-            const int j = i - ones_units;                                 // bias tiles: [b3 chunk0 | b3 chunk1 | b1 chunk0 | b1 chunk1]
-            const int which = j / (2 * kC), r = j % (2 * kC);
-            if (r < kC) {
-                const float bv = __ldg((which ? p.b1 : p.b3) + r);
+            const int j = i - ones_units;                                 // [set][conv][64 rows], then the zero chunk
+            const int tile = j / kC, r = j % kC;
+            if (tile < 2 * p.n_sets) {
+                const float bv = __ldg(((tile & 1) ? p.b1[tile >> 1] : p.b3[tile >> 1]) + r);
                 float hi;
                 if constexpr (BF16) hi = __bfloat162float(__float2bfloat16_rn(bv));
                 else hi = __half2float(__float2half_rn(bv));
@@ -105,24 +111,37 @@ __global__ void __launch_bounds__(kThreads, 1) resblock_tc_kernel(const __grid_c
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const int my_tiles = (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    // several weight sets: each CTA walks a CONTIGUOUS range of the (set, sample, tile) space (at most one or two weight switches
+    // per CTA and launch); one set: tiles strided over the CTAs (the CTAs sweep the image together: best DRAM / L2 locality)
+    const bool strided = p.n_sets == 1;
+    const int t_begin = strided ? (int)blockIdx.x : (int)((int64_t)blockIdx.x * p.num_tiles / gridDim.x);
+    const int t_step = strided ? (int)gridDim.x : 1;
+    const int my_tiles = strided ? (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x
+                                 : (int)((int64_t)(blockIdx.x + 1) * p.num_tiles / gridDim.x) - t_begin;
     const int tiles_per_img = p.tiles_x * p.tiles_y;
     const size_t plane = (size_t)p.H * p.W;
 
     if (warp == 0) {
         // ============================ TMA producer ============================
         if (lane == 0) {
-            mbar_expect_tx(w_full, kW3Bytes + kW1Bytes);
-            bulk_load(s0 + kOffW3, p.w3, kW3Bytes, w_full);
-            bulk_load(s0 + kOffW1, p.w1, kW1Bytes, w_full);
+            int cur = -1;
+            uint32_t wsw = 0;                                   // weight switches so far
             for (int i = 0; i < my_tiles; ++i) {
-                const int t = blockIdx.x + i * gridDim.x;
-                const int n = t / tiles_per_img, r = t % tiles_per_img;
+                const int t = t_begin + i * t_step;
+                const int k = t / p.tiles_per_set, ts = t - k * p.tiles_per_set;
+                if (k != cur) {                                 // (re)load the resident weights of set k
+                    if (cur >= 0) { mbar_wait(w_empty, wsw & 1); ++wsw; }      // every MMA reading the old set has completed
+                    mbar_expect_tx(w_full, kW3Bytes + kW1Bytes);
+                    bulk_load(s0 + kOffW3, p.w3[k], kW3Bytes, w_full);
+                    bulk_load(s0 + kOffW1, p.w1[k], kW1Bytes, w_full);
+                    cur = k;
+                }
+                const int n = ts / tiles_per_img, r = ts % tiles_per_img;
                 const int h0 = (r / p.tiles_x) * kTH, w0 = (r % p.tiles_x) * kTW;
                 const int b = i & 1;
                 mbar_wait(a1_empty(b), ((i >> 1) & 1) ^ 1);
                 mbar_expect_tx(a1_full(b), kA1Bytes);
-                tma_load_4d(s0 + kOffA1 + b * kA1Bytes, &tmap, a1_full(b), (w0 - 1) * 8, h0 - 1, p.in_chunk_off, n);
+                tma_load_4d(s0 + kOffA1 + b * kA1Bytes, &tmap, a1_full(b), (w0 - 1) * 8, h0 - 1, p.in_chunk_off[k], n);
             }
         }
     } else if (warp == 1) {
@@ -134,12 +153,18 @@ __global__ void __launch_bounds__(kThreads, 1) resblock_tc_kernel(const __grid_c
         const uint32_t a1_hi = desc_hi(a1_sbo), w_hi = desc_hi(w_sbo), a2_hi = desc_hi(a2_sbo);
         const uint32_t w3_lo0 = desc_lo(s0 + kOffW3, w_lbo), w1_lo0 = desc_lo(s0 + kOffW1, w_lbo);
         const uint32_t ones_lo = desc_lo(s0 + kOffOnes, 128 * 16);         // same geometry as an A2 M-block (LBO 2048, SBO 128)
-        const uint32_t b3_lo = desc_lo(s0 + kOffB3, w_lbo), b1_lo = desc_lo(s0 + kOffB1, w_lbo);
+        // bias B tile of (set k, conv c): chunk 0 at kOffBias + (2k + c) KB, chunk 1 = the shared zero chunk (LBO = distance to it)
+        auto bias_lo = [&](int k, int c) {
+            const uint32_t base = kOffBias + (uint32_t)(2 * k + c) * kBiasRow;
+            return desc_lo(s0 + base, kOffZero - base);
+        };
         const uint32_t leader = elect_one();
-        mbar_wait(w_full, 0);
+        int cur_set = -1;
+        uint32_t wph = 0;
 
-        auto gemm2 = [&](int j) {
+        auto gemm2 = [&](int j, int kset) {
             const int bj = j & 1;
+            const uint32_t b1_lo = bias_lo(kset, 1);
             mbar_wait(a2_full, j & 1);
             mbar_wait(acc2_empty(bj), ((j >> 1) & 1) ^ 1);
             tc_fence_after();
@@ -160,8 +185,24 @@ __global__ void __launch_bounds__(kThreads, 1) resblock_tc_kernel(const __grid_c
             __syncwarp();
         };
 
+        bool g2_done = true;                                    // GEMM2 of tile i-1 already issued?
+        int prev_set = -1;
         for (int i = 0; i < my_tiles; ++i) {
             const int b = i & 1, ph = (i >> 1) & 1;
+            const int kset = (t_begin + i * t_step) / p.tiles_per_set;
+            if (kset != cur_set) {
+                if (cur_set >= 0) {
+                    // weight switch: GEMM2 of the last tile of the old set still needs W1 -- issue it now (drains the
+                    // pipeline once), then tell the producer that the resident weights may be overwritten
+                    if (!g2_done) { gemm2(i - 1, prev_set); g2_done = true; }
+                    if (leader) tc_commit(w_empty);
+                    __syncwarp();
+                }
+                mbar_wait(w_full, wph);
+                wph ^= 1;
+                cur_set = kset;
+            }
+            const uint32_t b3_lo = bias_lo(kset, 0);
             mbar_wait(a1_full(b), ph);
             mbar_wait(acc1_empty(b), ph ^ 1);
             tc_fence_after();
@@ -190,9 +231,11 @@ __global__ void __launch_bounds__(kThreads, 1) resblock_tc_kernel(const __grid_c
                 rb_stamp(p, i, 1);
             }
             __syncwarp();
-            if (i >= 1) gemm2(i - 1);
+            if (i >= 1 && !g2_done) gemm2(i - 1, prev_set);
+            g2_done = false;                                    // GEMM2 of THIS tile is outstanding
+            prev_set = kset;
         }
-        if (my_tiles > 0) gemm2(my_tiles - 1);
+        if (my_tiles > 0) gemm2(my_tiles - 1, prev_set);
     } else if (warp < 6) {
         // ============================ EPI1: acc1 -> ELU -> shared (A of GEMM2) ============================
         const int q = warp & 3;
@@ -235,8 +278,9 @@ __global__ void __launch_bounds__(kThreads, 1) resblock_tc_kernel(const __grid_c
         const int m = q * 32 + lane;
         for (int i = 0; i < my_tiles; ++i) {
             const int b = i & 1, ph = (i >> 1) & 1;
-            const int t = blockIdx.x + i * gridDim.x;
-            const int n = t / tiles_per_img, rr = t % tiles_per_img;
+            const int t = t_begin + i * t_step;
+            const int kset = t / p.tiles_per_set, ts = t - kset * p.tiles_per_set;
+            const int n = ts / tiles_per_img, rr = ts % tiles_per_img;
             const int h0 = (rr / p.tiles_x) * kTH, w0 = (rr % p.tiles_x) * kTW;
             const int orow = h0 + (m >> 3);
             const int mb = (warp - 6) >> 2;               // warps 6-9 -> M-block 0, warps 10-13 -> M-block 1
@@ -247,7 +291,7 @@ __global__ void __launch_bounds__(kThreads, 1) resblock_tc_kernel(const __grid_c
             // was just fetched by TMA); 8 x 16-byte loads in flight per thread
             uint4 rx[8];
             {
-                const uint8_t* xin = p.x + (((size_t)n * p.in_total_chunks + p.in_chunk_off) * plane + pix) * 16;
+                const uint8_t* xin = p.x + (((size_t)n * p.in_total_chunks + p.in_chunk_off[kset]) * plane + pix) * 16;
 #pragma unroll
                 for (int ch = 0; ch < 8; ++ch)
                     rx[ch] = ok ? __ldg(reinterpret_cast<const uint4*>(xin + (size_t)ch * plane * 16)) : make_uint4(0, 0, 0, 0);
@@ -256,7 +300,7 @@ __global__ void __launch_bounds__(kThreads, 1) resblock_tc_kernel(const __grid_c
             tc_fence_after();
             if (threadIdx.x == 192) rb_stamp(p, i, 5);
             {
-                uint8_t* yout = p.y + (((size_t)n * p.out_total_chunks + p.out_chunk_off) * plane + pix) * 16;
+                uint8_t* yout = p.y + (((size_t)n * p.out_total_chunks + p.out_chunk_off[kset]) * plane + pix) * 16;
                 uint32_t r[64];
                 __syncwarp();
                 const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(256 + (b * 2 + mb) * kC);
@@ -293,29 +337,35 @@ __global__ void __launch_bounds__(kThreads, 1) resblock_tc_kernel(const __grid_c
 static unsigned long long* g_rb_dbg = nullptr;
 extern "C" int cwfa_resblock_set_debug_buffer(void* buf) { g_rb_dbg = (unsigned long long*)buf; return CWFA_OK; }
 
-extern "C" int cwfa_resblock_tc(const void* x_c8, void* y_c8, const void* w3_packed, const void* w1_packed, const float* b3,
-                                const float* b1, int N, int H, int W, int in_total_chunks, int in_chunk_off,
-                                int out_total_chunks, int out_chunk_off, int is_bf16, void* stream) {
-    if (N <= 0 || H <= 0 || W <= 0 || in_chunk_off < 0 || out_chunk_off < 0 || in_chunk_off + kChunks > in_total_chunks ||
-        out_chunk_off + kChunks > out_total_chunks || !b3 || !b1) {
-        set_error("resblock_tc: bad arguments");
+static int resblock_launch(const void* x_c8, void* y_c8, int n_sets, const void* const* w3, const void* const* w1, const float* const* b3,
+                           const float* const* b1, int N, int H, int W, int in_total_chunks, const int* in_chunk_off, int out_total_chunks,
+                           const int* out_chunk_off, int is_bf16, void* stream) {
+    if (N <= 0 || H <= 0 || W <= 0 || n_sets < 1 || n_sets > kMaxSets) {
+        set_error("resblock_tc: bad arguments (1..%d weight sets)", kMaxSets);
         return CWFA_EINVAL;
     }
-    if ((reinterpret_cast<uintptr_t>(x_c8) & 15) || (reinterpret_cast<uintptr_t>(y_c8) & 15) ||
-        (reinterpret_cast<uintptr_t>(w3_packed) & 15) || (reinterpret_cast<uintptr_t>(w1_packed) & 15)) {
+    if ((reinterpret_cast<uintptr_t>(x_c8) & 15) || (reinterpret_cast<uintptr_t>(y_c8) & 15)) {
         set_error("resblock_tc: pointers must be 16-byte aligned");
         return CWFA_EINVAL;
     }
     RbParams p{};
     p.N = N; p.H = H; p.W = W;
     p.tiles_x = ceil_div(W, kTW); p.tiles_y = ceil_div(H, kTH);
-    const int64_t nt = (int64_t)p.tiles_x * p.tiles_y * N;
-    if (nt > 0x7fffffff) { set_error("resblock_tc: too many tiles"); return CWFA_EINVAL; }
-    p.num_tiles = (int)nt;
-    p.in_total_chunks = in_total_chunks; p.in_chunk_off = in_chunk_off;
-    p.out_total_chunks = out_total_chunks; p.out_chunk_off = out_chunk_off;
-    p.x = (const uint8_t*)x_c8; p.y = (uint8_t*)y_c8; p.w3 = (const uint8_t*)w3_packed; p.w1 = (const uint8_t*)w1_packed;
-    p.b3 = b3; p.b1 = b1;
+    const int64_t per_set = (int64_t)p.tiles_x * p.tiles_y * N;
+    if (per_set * n_sets > 0x7fffffff) { set_error("resblock_tc: too many tiles"); return CWFA_EINVAL; }
+    p.n_sets = n_sets; p.tiles_per_set = (int)per_set; p.num_tiles = (int)(per_set * n_sets);
+    p.in_total_chunks = in_total_chunks; p.out_total_chunks = out_total_chunks;
+    for (int k = 0; k < n_sets; ++k) {
+        if (in_chunk_off[k] < 0 || out_chunk_off[k] < 0 || in_chunk_off[k] + kChunks > in_total_chunks ||
+            out_chunk_off[k] + kChunks > out_total_chunks || !b3[k] || !b1[k] || (reinterpret_cast<uintptr_t>(w3[k]) & 15) ||
+            (reinterpret_cast<uintptr_t>(w1[k]) & 15)) {
+            set_error("resblock_tc: bad chunk offsets / missing bias / unaligned weights in set %d", k);
+            return CWFA_EINVAL;
+        }
+        p.in_chunk_off[k] = in_chunk_off[k]; p.out_chunk_off[k] = out_chunk_off[k];
+        p.w3[k] = (const uint8_t*)w3[k]; p.w1[k] = (const uint8_t*)w1[k]; p.b3[k] = b3[k]; p.b1[k] = b1[k];
+    }
+    p.x = (const uint8_t*)x_c8; p.y = (uint8_t*)y_c8;
     p.dbg = g_rb_dbg;
     CUtensorMap tmap;
     int rc = make_c8_tensor_map(&tmap, x_c8, N, in_total_chunks, H, W, kBW, kBH, kChunks, is_bf16);
@@ -329,4 +379,22 @@ extern "C" int cwfa_resblock_tc(const void* x_c8, void* y_c8, const void* w3_pac
     const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
     kern<<<grid, kThreads, kSmemTotal + 1024, (cudaStream_t)stream>>>(tmap, p);
     return check_launch("resblock_tc");
+}
+
+extern "C" int cwfa_resblock_tc(const void* x_c8, void* y_c8, const void* w3_packed, const void* w1_packed, const float* b3,
+                                const float* b1, int N, int H, int W, int in_total_chunks, int in_chunk_off,
+                                int out_total_chunks, int out_chunk_off, int is_bf16, void* stream) {
+    return resblock_launch(x_c8, y_c8, 1, &w3_packed, &w1_packed, &b3, &b1, N, H, W, in_total_chunks, &in_chunk_off, out_total_chunks,
+                           &out_chunk_off, is_bf16, stream);
+}
+
+// The same block for n_sets (<= 5) INDEPENDENT sub-networks in ONE launch: set k reads the 64-channel slice at in_chunk_off[k] of
+// x and writes the slice at out_chunk_off[k] of y with its own weights / biases.  Every CTA walks a contiguous range of the
+// (set, sample, tile) space and re-loads its resident weights at most once, so prologue, tail and wave quantisation are paid once
+// per block row of a level (5 sub-networks, networks.py:305-366) instead of once per sub-network.
+extern "C" int cwfa_resblock_tc_batched(const void* x_c8, void* y_c8, int n_sets, const void* const* w3_packed, const void* const* w1_packed,
+                                        const float* const* b3, const float* const* b1, int N, int H, int W, int in_total_chunks,
+                                        const int* in_chunk_off, int out_total_chunks, const int* out_chunk_off, int is_bf16, void* stream) {
+    return resblock_launch(x_c8, y_c8, n_sets, w3_packed, w1_packed, b3, b1, N, H, W, in_total_chunks, in_chunk_off, out_total_chunks,
+                           out_chunk_off, is_bf16, stream);
 }

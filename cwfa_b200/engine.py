@@ -109,18 +109,33 @@ class CWFAEngine:
         return dict(ch=ch, out=packed, z_from_storage=m.to(dev, torch.int32).contiguous(), storage_from_z=minv.to(dev, torch.int32).contiguous())
 
     # -------------------------------------------------------------------------------------
-    def _trunks(self, n: int, lf8: tc.C8):
+    batch_trunks = True    # the block rows of a level's sub-network trunks as ONE launch each (cwfa_resblock_tc_batched)
+
+    def _trunks(self, n: int, lf8: tc.C8, allow_batched: bool = True):
         """The trunks of all fused sub-networks of level n from the level's LF condition (C8).  They depend on the conditions
-        only (CAT blocks, coupling_layers.py:475-500), so forward and inverse share them and levels are independent."""
+        only (CAT blocks, coupling_layers.py:475-500), so forward and inverse share them and levels are independent.
+        Items: (kind, module, executor, trunk output C8, chunk offset of this sub-network's 64-channel slice in it).
+        With a batched input conv the three block rows of the (<= 5) trunks run as three launches over all sub-networks."""
         lv = self.levels[n]
         b_all = tc.conv_tc(lf8, lv["batched_in"]) if lv["batched_in"] is not None else None
+        subs = [extra for kind, _, extra in lv["nodes"] if kind == "cat"]
         out, k = [], 0
+        if b_all is not None and allow_batched and self.batch_trunks and 2 <= len(subs) <= 5:
+            for r in range(3):
+                b_all = tc.resblock_tc_batched(b_all, [sn.res[r] for sn in subs])
+            for kind, mod, extra in lv["nodes"]:
+                if kind == "cat":
+                    out.append(("cat", mod, extra, b_all, 8 * k))
+                    k += 1
+                else:
+                    out.append((kind, mod, extra, None, 0))
+            return out
         for kind, mod, extra in lv["nodes"]:
             if kind == "cat":
-                out.append(("cat", mod, extra, extra.trunk(lf8, b_all, 8 * k) if b_all is not None else extra.trunk(lf8)))
+                out.append(("cat", mod, extra, extra.trunk(lf8, b_all, 8 * k) if b_all is not None else extra.trunk(lf8), 0))
                 k += 1
             else:
-                out.append((kind, mod, extra, None))
+                out.append((kind, mod, extra, None, 0))
         return out
 
     def _lf(self, n: int, v8: Optional[tc.C8], low_res: Optional[torch.Tensor]) -> tc.C8:
@@ -140,7 +155,7 @@ class CWFAEngine:
         """Final conv of one sub-network with the coupling fused in its epilogue.  When ``x`` carries more samples than the
         conditions (multi-sample reconstruction, CWFA.py:903-914) the coefficients are computed ONCE and broadcast over the
         samples by the affine kernel."""
-        _, mod, sub, b8 = item
+        _, mod, sub, b8, off = item
         first = not sub.normal
         t_scale = (-1.0 / math.sqrt(2)) if first else 1.0
         if x is not None and x.shape[0] != b8.N:
@@ -159,7 +174,7 @@ class CWFAEngine:
         perm, axis = (None, 0) if pending is None else (ops.perm_i32(pending[0], b8.data.device), pending[1])
         return tc.conv_tc_coupling(b8, sub.out, x, ch=mod.channels, inverse=inverse, clamp=mod.clamp,
                                    t_ext=mean_vol if first else None, t_scale=t_scale,
-                                   perm=perm, perm_axis=axis, logdet=logdet, sumsq=sumsq, ticket=ticket)
+                                   perm=perm, perm_axis=axis, logdet=logdet, sumsq=sumsq, ticket=ticket, chunk_off=off)
 
     def _run_module(self, mod, hi, lf_nchw, rev, logdet):
         """A generic invertible block through its own forward (module-API fast path: sub-networks on tcgen05)."""
@@ -176,7 +191,7 @@ class CWFAEngine:
         """Detail half ``hi`` of level n in the inverse direction and its log-det.  Independent of the other levels unless
         ``disable_low_res_input``.  ``z`` None = zeros (INN_z_temperature = 0, CWFA.py:906-907: z is never materialised);
         otherwise the latent sample(s) of this level (``sample_z_truncated``, CWFA.py:47-64), ``rows`` of them."""
-        items = self._trunks(n, lf8)
+        items = self._trunks(n, lf8, allow_batched=(z is None or z.shape[0] == lf8.N))
         plan = self.levels[n]["f8"] if (self.use_f8 and (lf8.H * lf8.W) % 4 == 0) else None
         if plan is not None and (z is None or z.shape[0] == lf8.N):
             return self._level_detail_inverse_f8(n, items, plan, lf8, mean_vol, z)
@@ -205,12 +220,12 @@ class CWFAEngine:
         return hi, jac
 
     def _couple_f8(self, item, pc, x8, mv8, pending, inverse, logdet, sumsq, ticket):
-        _, mod, sub, b8 = item
+        _, mod, sub, b8, off = item
         first = not sub.normal
         perm, axis = (None, 0) if pending is None else (ops.perm_i32(pending[0], b8.data.device), pending[1])
         return tc.coupling_f8(b8, pc, x8, ch=mod.channels, inverse=inverse, clamp=mod.clamp, t_ext8=mv8 if first else None,
                               t_scale=(-1.0 / math.sqrt(2)) if first else 1.0, perm=perm, perm_axis=axis, logdet=logdet, sumsq=sumsq,
-                              ticket=ticket)
+                              ticket=ticket, chunk_off=off)
 
     @staticmethod
     def _permute_f8(x8, ch, perm, axis):

@@ -253,13 +253,13 @@ def conv_tc_coupling(b: C8, pc: PackedConv, x: Optional[torch.Tensor], *, ch: in
                      k_atan: float = 0.636, t_ext: Optional[torch.Tensor] = None, t_scale: float = 1.0,
                      perm: Optional[torch.Tensor] = None, perm_axis: int = 0, logdet: torch.Tensor = None,
                      sumsq: Optional[torch.Tensor] = None, accumulate: bool = True, mb: Optional[int] = None,
-                     persistent: Optional[bool] = None, ticket: Optional[torch.Tensor] = None) -> torch.Tensor:
+                     persistent: Optional[bool] = None, ticket: Optional[torch.Tensor] = None, chunk_off: int = 0) -> torch.Tensor:
     """Last conv of a coupling sub-network with the affine coupling, the log-det partial sums and the preceding
     permutation (as a gather on ``x``) fused into its epilogue.  ``x`` None = zeros (z = 0, inverse only).
     ``logdet`` (B,) is accumulated in place (fixed-order reduction); ``sumsq`` (B,) receives sum(y^2).
     ``ticket``: one zero int32 on the device (the kernel leaves it zero); with it the persistent kernel reduces its partial
     sums itself (last CTA, fixed order) instead of a separate finalize launch."""
-    if b.Cp != pc.Cin_p or b.kind != pc.kind:
+    if (b.Cp != pc.Cin_p and not (pc.Cin_p == 64 and chunk_off * 8 + 64 <= b.Cp)) or b.kind != pc.kind:
         raise ValueError("conv_tc_coupling: input layout mismatch")
     need = ch if t_ext is not None else 2 * ch
     if pc.Cout != need or pc.BN != pc.Cout_p:
@@ -274,12 +274,14 @@ def conv_tc_coupling(b: C8, pc: PackedConv, x: Optional[torch.Tensor], *, ch: in
     lib = _lib.load()
     if persistent is None:
         persistent = pc.Cin_p == 64 and pc.KH == 3 and pc.KW == 3 and pc.Cout_p <= 96 and ch <= 48
+    if (b.Cp != 64 or chunk_off) and not persistent:
+        raise ValueError("conv_tc_coupling: a channel slice of a wider tensor needs the persistent kernel")
     if persistent:
         tiles = lib.cwfa_coupling_tc_tiles(H, W)
         ws = torch.empty(2 * N * tiles, device=dev, dtype=torch.float32)
         _lib.call("cwfa_coupling_tc", b.data.data_ptr(), pc.packed.data_ptr(), _p(pc.bias), N, H, W, pc.Cout, pc.Cout_p, _p(xx),
                   y.data_ptr(), _p(tt), float(t_scale), _p(perm), int(perm_axis), ch, float(clamp), float(k_atan), int(inverse),
-                  ws.data_ptr(), logdet.data_ptr(), _p(sumsq), int(accumulate), _p(ticket), b.is_bf16, _stream())
+                  ws.data_ptr(), logdet.data_ptr(), _p(sumsq), int(accumulate), _p(ticket), b.Cp // 8, int(chunk_off), b.is_bf16, _stream())
         if ticket is None:
             _lib.call("cwfa_coupling_finalize", ws.data_ptr(), logdet.data_ptr(), _p(sumsq), N, tiles, int(accumulate), _stream())
         return y
@@ -362,9 +364,10 @@ def coupling_weights_f8(weight: torch.Tensor, bias: torch.Tensor, ch: int, slot_
 def coupling_f8(b: C8, pc: PackedConv, x8: Optional[torch.Tensor], *, ch: int, inverse: bool, clamp: float = 2.0, k_atan: float = 0.636,
                 t_ext8: Optional[torch.Tensor] = None, t_scale: float = 1.0, perm: Optional[torch.Tensor] = None, perm_axis: int = 0,
                 logdet: torch.Tensor = None, sumsq: Optional[torch.Tensor] = None, accumulate: bool = True,
-                ticket: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """``conv_tc_coupling`` on the F8 detail half (lean epilogue; channel permutations live in ``pc``'s column order)."""
-    if b.Cp != 64 or pc.Cin_p != 64 or pc.KH != 3 or pc.KW != 3 or b.kind != pc.kind or pc.BN != pc.Cout_p:
+                ticket: Optional[torch.Tensor] = None, chunk_off: int = 0) -> torch.Tensor:
+    """``conv_tc_coupling`` on the F8 detail half (lean epilogue; channel permutations live in ``pc``'s column order).
+    ``b`` may be a wider C8 tensor; ``chunk_off`` selects its 64-channel slice (8 chunks)."""
+    if chunk_off * 8 + 64 > b.Cp or pc.Cin_p != 64 or pc.KH != 3 or pc.KW != 3 or b.kind != pc.kind or pc.BN != pc.Cout_p:
         raise ValueError("coupling_f8: needs a 3x3 conv from 64 hidden channels packed in one n-block")
     N, H, W = b.N, b.H, b.W
     c8 = ch8(ch)
@@ -374,7 +377,32 @@ def coupling_f8(b: C8, pc: PackedConv, x8: Optional[torch.Tensor], *, ch: int, i
     ws = torch.empty(2 * N * tiles, device=b.data.device, dtype=torch.float32)
     _lib.call("cwfa_coupling_f8", b.data.data_ptr(), pc.packed.data_ptr(), _p(pc.bias), N, H, W, pc.BN, c8, _p(x8), y.data_ptr(),
               _p(t_ext8), float(t_scale), _p(perm), int(perm_axis), float(clamp), float(k_atan), int(inverse), ws.data_ptr(),
-              logdet.data_ptr(), _p(sumsq), int(accumulate), _p(ticket), b.is_bf16, _stream())
+              logdet.data_ptr(), _p(sumsq), int(accumulate), _p(ticket), b.Cp // 8, int(chunk_off), b.is_bf16, _stream())
     if ticket is None:
         _lib.call("cwfa_coupling_finalize", ws.data_ptr(), logdet.data_ptr(), _p(sumsq), N, tiles, int(accumulate), _stream())
+    return y
+
+
+def resblock_tc_batched(x: C8, sets, in_chunk_offs=None) -> C8:
+    """The fused trunk block (``resblock_tc``) for several INDEPENDENT sub-networks in one launch: ``sets`` = [(p3, p1), ...]
+    (<= 5); set k reads the 64-channel slice at chunk ``in_chunk_offs[k]`` (default 8 k) of ``x`` and writes slice k of the
+    returned tensor (64 * len(sets) channels)."""
+    import ctypes as C
+    n = len(sets)
+    if not 1 <= n <= 5:
+        raise ValueError("resblock_tc_batched: 1..5 weight sets")
+    for p3, p1 in sets:
+        for pc, k in ((p3, 3), (p1, 1)):
+            if pc.Cin_p != 64 or pc.Cout_p != 64 or pc.BN != 64 or pc.KH != k or pc.bias is None or pc.kind != x.kind:
+                raise ValueError("resblock_tc_batched: needs 64->64 convs (3x3 then 1x1) packed with BN=64 and biases")
+    offs = [8 * k for k in range(n)] if in_chunk_offs is None else list(in_chunk_offs)
+    if any(o * 8 + 64 > x.Cp for o in offs):
+        raise ValueError("resblock_tc_batched: input slice out of range")
+    y = C8.empty(x.N, 64 * n, x.H, x.W, x.data.device, x.kind, 64 * n)
+    vps = lambda vals: (C.c_void_p * n)(*vals)
+    w3, w1 = vps([s_[0].packed.data_ptr() for s_ in sets]), vps([s_[1].packed.data_ptr() for s_ in sets])
+    b3, b1 = vps([s_[0].bias.data_ptr() for s_ in sets]), vps([s_[1].bias.data_ptr() for s_ in sets])
+    io, oo = (C.c_int * n)(*offs), (C.c_int * n)(*[8 * k for k in range(n)])
+    _lib.call("cwfa_resblock_tc_batched", x.data.data_ptr(), y.data.data_ptr(), n, w3, w1, b3, b1, x.N, x.H, x.W, x.Cp // 8, io,
+              n * 8, oo, x.is_bf16, _stream())
     return y

@@ -167,6 +167,13 @@ int cwfa_conv_tc(const void* x_c8, const void* w_packed, const float* bias, cons
 int cwfa_resblock_tc(const void* x_c8, void* y_c8, const void* w3_packed, const void* w1_packed,
                      const float* b3, const float* b1, int N, int H, int W, int in_total_chunks,
                      int in_chunk_off, int out_total_chunks, int out_chunk_off, int is_bf16, void* stream);
+/* The same block for n_sets (<= 5) independent sub-networks in ONE launch (the block row of a level's five coupling
+ * sub-networks, networks.py:305-366): set k reads the slice at in_chunk_off[k] of x, writes the slice at out_chunk_off[k] of y,
+ * with its own packed weights / biases (host arrays of n_sets pointers / offsets). */
+int cwfa_resblock_tc_batched(const void* x_c8, void* y_c8, int n_sets, const void* const* w3_packed,
+                             const void* const* w1_packed, const float* const* b3, const float* const* b1, int N, int H, int W,
+                             int in_total_chunks, const int* in_chunk_off, int out_total_chunks, const int* out_chunk_off,
+                             int is_bf16, void* stream);
 /* ---- C8 helpers of the LRNN U-Net: per-channel (sum, sumsq) over (N,H,W) -> stats[2*Cp]
  * (workspace >= cwfa_c8_stats_workspace_floats(Cp) floats; feed to cwfa_bn_finalize_f32), and BatchNorm
  * apply y = x*scale+shift, optionally also writing the 2x2 max-pooled tensor (unet.py:79).
@@ -217,18 +224,20 @@ int cwfa_coupling_tc_tiles(int H, int W);
 int cwfa_coupling_tc(const void* b_c8, const void* w_packed, const float* bias, int N, int H, int W, int Cout,
                      int Cout_p, const float* cx, float* cy, const float* ct, float t_scale, const int32_t* perm,
                      int perm_axis, int ch, float clamp, float k_atan, int inverse, float* workspace, float* logdet,
-                     float* sumsq, int accumulate, int32_t* ticket, int is_bf16, void* stream);
+                     float* sumsq, int accumulate, int32_t* ticket, int in_total_chunks, int in_chunk_off, int is_bf16,
+                     void* stream);
 /* ---- the coupling path on the "F8" layout of a level's detail half: [N][ceil(ch/8)][H][W][8] fp32, channel padding zero
  * (csrc/coupling_f8.cu).  cwfa_coupling_f8 = cwfa_coupling_tc with a lean epilogue: x / y / external shift as 128-bit
  * vectors, no channel gather (the caller permutes the OUTPUT CHANNELS of w_packed so that [s | t] arrive in storage order:
  * columns [0,chp8) = s of slot j, [chp8,2 chp8) = t of slot j; with ct != NULL columns [0,chp8) = s only), bias through an
  * extra MMA, row (perm_axis 2) / column (perm_axis 3) permutations as a gather on cx.  chp8 = 8 * ceil(ch / 8) <= 48; BN =
- * number of conv output columns (one n-block, multiple of 16, <= 96).  workspace / logdet / sumsq / accumulate / ticket as in
+ * number of conv output columns (one n-block, multiple of 16, <= 96).  b_c8 is the 64-channel slice (8 chunks from in_chunk_off)
+ * of a C8 tensor with in_total_chunks chunks (cwfa_coupling_tc likewise).  workspace / logdet / sumsq / accumulate / ticket as in
  * cwfa_coupling_tc (tiles = cwfa_coupling_tc_tiles(H, W)). */
 int cwfa_coupling_f8(const void* b_c8, const void* w_packed, const float* bias, int N, int H, int W, int BN, int chp8,
                      const float* cx, float* cy, const float* ct, float t_scale, const int32_t* perm, int perm_axis,
                      float clamp, float k_atan, int inverse, float* workspace, float* logdet, float* sumsq, int accumulate,
-                     int32_t* ticket, int is_bf16, void* stream);
+                     int32_t* ticket, int in_total_chunks, int in_chunk_off, int is_bf16, void* stream);
 /* Depth-wise Haar DWT + Split (INN_utils.py:142-161, graph_topology.py:73-80) with the detail half written / read in F8:
  * fwd: x (B,C,P) -> lo (B,C/2,P) NCHW, hi F8;  inv: lo, hi F8 -> x.  P % 4 == 0, pointers 16-byte aligned; every access 128-bit. */
 int cwfa_haar1d_fwd_f8(const float* x, float* lo, float* hi_f8, int B, int C, int64_t P, void* stream);

@@ -78,6 +78,14 @@ elif what == "resblock":
     us = bench(lambda i: tc.resblock_tc(xin[i], p3, p1), n)
     if us:
         print(f"resblock_tc: {us:.1f} us  {2.0 * P * 64 * 64 * 10 / us / 1e6:.0f} TFLOP/s", flush=True)
+elif what == "resblock5":
+    n = 4
+    xin = [tc.to_c8(torch.randn(1, 320, 512, 512, device=DEV)) for _ in range(n)]
+    sets = [(tc.PackedConv(torch.randn(64, 64, 3, 3, device=DEV) * 0.04, torch.zeros(64, device=DEV), bn=64),
+             tc.PackedConv(torch.randn(64, 64, 1, 1, device=DEV) * 0.1, torch.zeros(64, device=DEV), bn=64)) for _ in range(5)]
+    us = bench(lambda i: tc.resblock_tc_batched(xin[i], sets), n)
+    if us:
+        print(f"resblock_tc_batched (5 sub-networks): {us:.1f} us = {us / 5:.1f} us per block  {5 * 2.0 * P * 64 * 64 * 10 / us / 1e6:.0f} TFLOP/s", flush=True)
 elif what == "bn":
     n = 4
     c8s = [tc.to_c8(torch.randn(1, 256, 512, 512, device=DEV)) for _ in range(n)]

@@ -261,3 +261,24 @@ def test_layernorm_c8(N, C, H, W, kind):
     if y8.Cp != C:
         raw = y8.data.float().view(N, y8.Cp // 8, H, W, 8).permute(0, 1, 4, 2, 3).reshape(N, y8.Cp, H, W)
         assert float(raw[:, C:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("kind,N,H,W,nsets", [("bf16", 1, 48, 80, 5), ("fp16", 2, 33, 19, 3), ("bf16", 1, 16, 16, 2), ("bf16", 3, 64, 64, 5)])
+def test_batched_trunk_block_equals_per_subnetwork_launches(kind, N, H, W, nsets):
+    """One launch over the block row of several independent sub-networks (cwfa_resblock_tc_batched: contiguous tile ranges, one
+    weight switch per CTA) must equal the per-sub-network launches BIT FOR BIT (same MMAs, same epilogues), ragged shapes and
+    set boundaries that fall inside a CTA's range included."""
+    from cwfa_b200 import tc
+    x = _round(seeded_randn((N, 64 * nsets, H, W), 91), kind)
+    x8 = tc.to_c8(x.to(DEV), kind)
+    sets = []
+    for k in range(nsets):
+        w3 = _round(seeded_randn((64, 64, 3, 3), 100 + k, 0.05), kind)
+        w1 = _round(seeded_randn((64, 64, 1, 1), 200 + k, 0.12), kind)
+        sets.append((tc.PackedConv(w3.to(DEV), seeded_randn((64,), 300 + k, 0.1).to(DEV), kind, bn=64),
+                     tc.PackedConv(w1.to(DEV), seeded_randn((64,), 400 + k, 0.1).to(DEV), kind, bn=64)))
+    y = tc.from_c8(tc.resblock_tc_batched(x8, sets))
+    for k, (p3, p1) in enumerate(sets):
+        yk = tc.from_c8(tc.resblock_tc(x8, p3, p1, 8 * k))
+        assert torch.equal(y[:, 64 * k:64 * (k + 1)], yk), k
+    torch.cuda.synchronize()
