@@ -159,34 +159,48 @@ def run_cpu_oracle(cfg, threads, steps, warmup, om, seed, return_levels=False):
 
 
 def bind_to_gpu_numa_node(index: int):
-    """Pins this process to the CPUs of the NUMA node the GPU hangs off (sysfs), so the pinned host buffers of the
-    end-to-end measurement are first-touched on that socket.  Returns (node or None, reason string)."""
+    """Pins this process to the CPUs next to GPU ``index`` so that the pinned host buffers of the end-to-end measurement are
+    first-touched on the GPU's own socket (with 8 ranks streaming 130 MB per frame each, buffers that all land on one NUMA node
+    make half of the GPUs copy across the socket interconnect).  Sources, in order: NVML's ideal CPU affinity of the device
+    (what `nvidia-smi topo -m` prints), then sysfs' numa_node of the PCI function.  Returns (description or None, reason)."""
+    allowed = os.sched_getaffinity(0)
     try:
         import pynvml
         pynvml.nvmlInit()
         h = pynvml.nvmlDeviceGetHandleByIndex(index)
+    except Exception as ex:
+        return None, f"nvml unavailable ({type(ex).__name__}: {ex})"
+    try:
+        ncpu = os.cpu_count() or 1
+        words = (max(allowed | {ncpu - 1}) + 64) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        use = cpus & allowed
+        if use and use != allowed:
+            os.sched_setaffinity(0, use)
+            return f"nvml cpu affinity ({len(use)} cpus)", f"pinned to {len(use)} of {len(allowed)} allowed CPUs (NVML ideal affinity of GPU {index})"
+        why = "NVML affinity covers every allowed CPU (single NUMA domain or cpuset already local)" if use else "NVML affinity disjoint from this process' cpuset"
+    except Exception as ex:
+        why = f"nvmlDeviceGetCpuAffinity failed ({type(ex).__name__})"
+    try:
         bdf = pynvml.nvmlDeviceGetPciInfo(h).busId
         bdf = (bdf.decode() if isinstance(bdf, bytes) else bdf).lower()
         if len(bdf.split(":")[0]) == 8:                  # NVML prints an 8-digit domain; sysfs uses 4
             bdf = bdf[4:]
-    except Exception as ex:
-        return None, f"nvml unavailable ({type(ex).__name__})"
-    try:
-        path = f"/sys/bus/pci/devices/{bdf}/numa_node"
-        node = int(open(path).read().strip())
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
         if node < 0:
-            return None, f"{path} reports {node} (no NUMA affinity exposed in this container)"
+            return None, why + f"; sysfs numa_node of {bdf} is {node}"
         cpus = set()
         for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
             lo, _, hi = part.partition("-")
             cpus.update(range(int(lo), int(hi or lo) + 1))
-        allowed = cpus & os.sched_getaffinity(0)
-        if not allowed:
-            return None, f"node {node} has no CPU in this process' cpuset"
-        os.sched_setaffinity(0, allowed)
-        return node, f"pinned to {len(allowed)} CPUs of node {node}"
+        use = cpus & allowed
+        if not use:
+            return None, why + f"; node {node} has no CPU in this process' cpuset"
+        os.sched_setaffinity(0, use)
+        return f"numa node {node}", f"pinned to {len(use)} CPUs of NUMA node {node} (sysfs)"
     except Exception as ex:
-        return None, f"sysfs lookup failed for {bdf} ({type(ex).__name__}: {ex})"
+        return None, why + f"; sysfs lookup failed ({type(ex).__name__})"
 
 
 def pctl(vals, q):
@@ -340,6 +354,24 @@ def main():
     barrier()
     e2e_ms = e2.elapsed_time(e3)
     e2e_host_ms = (time.perf_counter() - t_host0) * 1e3      # host wall clock around the same region (sanity)
+    # the same with the volume narrowed to fp16 on the device before the D2H copy (half the bytes; the reference's own GPU
+    # output is fp16 under its default autocast, CWFA.py:845) -- reported in extra, the headline e2e keeps --out-dtype
+    e2e16_ms = None
+    if args.out_dtype == "fp32":
+        try:
+            st16 = StreamingReconstructor(eng, tuple(views_host[0].shape), mvs_dev, depth=args.e2e_inflight, out_dtype=torch.float16)
+            outs16 = [torch.empty((1, args.depths, args.side, args.side), dtype=torch.float16, pin_memory=True) for _ in range(4)]
+            st16.run([views_host[i % n_rot] for i in range(3)], [outs16[i % 4] for i in range(3)])
+            barrier()
+            h0_, h1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            h0_.record()
+            st16.run([views_host[i % n_rot] for i in range(args.steps)], [outs16[i % 4] for i in range(args.steps)])
+            h1_.record()
+            barrier()
+            e2e16_ms = h0_.elapsed_time(h1_)
+            del st16, outs16
+        except Exception as ex:
+            print(f"bench: fp16-volume e2e leg failed: {ex!r}", file=sys.stderr)
     # copy-only ceiling of the same host traffic (no compute): what the platform allows for these bytes per frame
     cp0, cp1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     st_in, st_out = torch.empty_like(views_dev[0]), torch.empty((1, args.depths, args.side, args.side), device=dev, dtype=out_dt)
@@ -366,9 +398,10 @@ def main():
     del streamer_h
 
     if world > 1:
-        t = torch.tensor([elapsed_ms, e2e_ms, copy_only_ms], device=dev, dtype=torch.float64)
+        t = torch.tensor([elapsed_ms, e2e_ms, copy_only_ms, e2e16_ms or 0.0], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed_ms, e2e_ms, copy_only_ms = float(t[0]), float(t[1]), float(t[2])
+        e2e16_ms = float(t[3]) if e2e16_ms else None
 
     # ---- dominant-kernel roofline: sum of tcgen05 conv launch durations over one step (CUDA events on the launch stream)
     conv_ms, n_conv, per_kernel = 0.0, 0, {}
@@ -377,7 +410,7 @@ def main():
         orig = _lib.call
 
         def timed_call(name, *a):
-            if name in ("cwfa_conv_tc", "cwfa_resblock_tc", "cwfa_conv_tc_coupling", "cwfa_coupling_tc"):
+            if name in ("cwfa_conv_tc", "cwfa_resblock_tc", "cwfa_resblock_tc_batched", "cwfa_conv_tc_coupling", "cwfa_coupling_tc", "cwfa_coupling_f8"):
                 s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 s.record()
                 orig(name, *a)
@@ -618,7 +651,9 @@ def main():
                    "l2_policy": "per-step working set (activations ~3 GB) exceeds the 126 MB L2; inputs rotate over 4 buffers",
                    "baseline_note": "README.md:29 publishes ~0.16 s/frame on unstated hardware"},
         "clocks": clocks,
-        "extra": {"module_api_frames_per_s": module_fps,
+        "extra": {"e2e_fp16_volume_frames_per_s": (world * args.steps / (e2e16_ms * 1e-3)) if e2e16_ms else None,
+                  "e2e_fp16_volume_note": "end to end as in e2e, the reconstructed volume narrowed to fp16 on the device before the D2H copy (30.4 MB H2D + 50.3 MB D2H per frame)",
+                  "module_api_frames_per_s": module_fps,
                   "module_api_note": "the reference's own entry points (cond_nets[n](views), conv_inn[n]([z, vol], c=..., rev=True)) on this package's drop-in modules with "
                                      f"set_inference_precision('{args.kind}'): eager, device-resident inputs, 10 frames, 1 GPU",
                   "forward_nll_frames_per_s_batch8": nll_fps, "forward_nll_graph_frames_per_s_batch8": nll_graph_fps,
@@ -635,7 +670,7 @@ def main():
                 "copy_only_frames_per_s": world * args.steps / (copy_only_ms * 1e-3),
                 "copy_only_note": "the same H2D + D2H bytes per frame with NO compute (both directions concurrently): the platform ceiling for this host traffic"},
         "gpu_launches": launches_per_step * args.steps,
-        "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel + resblock_tc_kernel + coupling_tc_kernel (all tcgen05 implicit-GEMM convolution launches of a frame)", "achieved": achieved, "peak": peak_tf,
+        "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel + resblock_tc_kernel + coupling_f8_kernel (all tcgen05 implicit-GEMM convolution launches of a frame)", "achieved": achieved, "peak": peak_tf,
                      "unit": "TFLOP/s", "frac": (achieved / peak_tf) if achieved else None, "traffic": traffic,
                      "launches_per_step": n_conv, "avg_launch_us": (conv_ms * 1e3 / n_conv) if n_conv else None,
                      "algorithmic_flop_per_step": conv_flop, "conv_ms_per_step": conv_ms, "peak_source": peak_src,
