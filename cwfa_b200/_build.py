@@ -32,7 +32,7 @@ def sources():
 
 
 def _deps():
-    return sources() + sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + \
+    return sources() + sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + sorted(glob.glob(os.path.join(CSRC, "*.h"))) + \
         sorted(glob.glob(os.path.join(os.path.dirname(HERE), "include", "*.h")))
 
 

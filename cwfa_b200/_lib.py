@@ -41,8 +41,8 @@ _SIGS = {
     "cwfa_tc_kc": [i32],
     "cwfa_tc_pack_weights": [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp],
     "cwfa_conv_tc": [vp, vp, vp, vp, vp, vp] + [i32] * 14 + [vp],
-    "cwfa_tc_set_debug_buffer": [vp],
-    "cwfa_resblock_set_debug_buffer": [vp],
+    "cwfa_conv_tc_bn": [vp, vp, vp, vp, vp] + [i32] * 12 + [vp, vp],
+    "cwfa_bn_partial_finalize": [vp, i32, i32, vp, vp, f64, f32, vp, vp, vp, vp],
     "cwfa_resblock_tc": [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp],
     "cwfa_c8_stats_workspace_floats": [i32],
     "cwfa_c8_channel_stats": [vp, vp, vp, i32, i32, i64, i32, vp],
@@ -92,15 +92,17 @@ _SIGS = {
     "cwfa_pixel_shuffle2_f32": [vp, vp, vp, i32, i32, i32, i32, i32, vp],
 }
 _I64_FUNCS = {"cwfa_tc_packed_weight_elems": [i32, i32, i32, i32, i32],
+              "cwfa_conv_tc_stats_floats": [i32, i32],
               "cwfa_conv2d_wgrad_workspace_floats": [i32] * 7,
               "cwfa_wgrad_tc_workspace_floats": [i32] * 8}
 _RESTYPES = {"cwfa_version": C.c_char_p, "cwfa_last_error": C.c_char_p}
-_OPTIONAL = {}
+# private profiling hooks (csrc/cwfa_b200_debug.h): bound for scripts/trace_*.py, not part of the public header
+_OPTIONAL = {"cwfa_tc_set_debug_buffer": [vp], "cwfa_resblock_set_debug_buffer": [vp]}
 
 
 def exported_symbols():
     """Every symbol include/cwfa_b200.h declares (used by the CPU-side ABI test)."""
-    return sorted(list(_SIGS) + list(_RESTYPES) + list(_OPTIONAL) + list(_I64_FUNCS))
+    return sorted(list(_SIGS) + list(_RESTYPES) + list(_I64_FUNCS))
 
 
 def lib_path() -> str:

@@ -184,13 +184,44 @@ def conv2d_wgrad_tc(x8, dy8, Cin: int, Cout: int, K: int) -> torch.Tensor:
     return dw
 
 
+def _packed_for(w, bias, kind: str, transposed_for_dgrad: bool = False):
+    """Packed tensor-core weights of a parameter, cached ON the parameter object: re-packed only when the parameter changed
+    (in-place version / storage) or after an optimiser step (``packed.weights_changed``, called by ``Lion.step``) -- a training
+    step otherwise spends ~6 % of its time re-packing the same weights for the forward conv and for the data gradient."""
+    from . import packed, tc
+    b_key = None if bias is None else (bias._version, bias.data_ptr())
+    key = (kind, packed._EPOCH, w._version, w.data_ptr(), b_key, transposed_for_dgrad)
+    cache = getattr(w, "_cwfa_pack", None)
+    if cache is None:
+        cache = {}
+        try:
+            w._cwfa_pack = cache
+        except AttributeError:
+            pass
+    slot = "dgrad" if transposed_for_dgrad else "fwd"
+    hit = cache.get(slot)
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    ww = _f32(w)
+    if transposed_for_dgrad:
+        Cout, Cin, KH, KW = ww.shape
+        wt = torch.empty((Cin, Cout, KH, KW), device=ww.device, dtype=torch.float32)
+        _lib.call("cwfa_conv2d_dgrad_weights_f32", ww.data_ptr(), wt.data_ptr(), Cout, Cin, KH, KW, _stream())
+        pc = tc.PackedConv(wt, None, kind)
+    else:
+        pc = tc.PackedConv(ww, None if bias is None else bias.detach(), kind)
+    cache[slot] = (key, pc)
+    return pc
+
+
 class _Conv2dTC(_F):
     @staticmethod
     def forward(ctx, x, w, bias, res, act, res_mode, kind):
         from . import tc
         xx, ww = _f32(x), _f32(w)
         rr = None if res is None else _f32(res)
-        pc = tc.PackedConv(ww, None if bias is None else bias.detach(), kind)
+        pc = _packed_for(w, bias, kind)
+        ctx.w_ref = w
         x8 = tc.to_c8(xx, kind)
         y = tc.conv_tc(x8, pc, act=act, res=rr, res_mode=res_mode, out_nchw=True)
         ctx.act, ctx.kind = act, kind
@@ -214,9 +245,7 @@ class _Conv2dTC(_F):
         dv8 = tc.to_c8(dv, ctx.kind) if (need_x or (need_w and ctx.wgrad_tc)) else None
         dx = None
         if need_x:
-            wt = torch.empty((Cin, Cout, KH, KW), device=w.device, dtype=torch.float32)
-            _lib.call("cwfa_conv2d_dgrad_weights_f32", w.data_ptr(), wt.data_ptr(), Cout, Cin, KH, KW, _stream())
-            dx = tc.conv_tc(dv8, tc.PackedConv(wt, None, ctx.kind), out_nchw=True)
+            dx = tc.conv_tc(dv8, _packed_for(ctx.w_ref, None, ctx.kind, transposed_for_dgrad=True), out_nchw=True)
         dw = None
         if need_w:
             dw = conv2d_wgrad_tc(tc.C8(x8d, Cin, ctx.kind), dv8, Cin, Cout, KH) if ctx.wgrad_tc else conv2d_wgrad(x, dv, KH, KW)

@@ -183,6 +183,10 @@ struct TcParams {
     const uint8_t* res;
     void* out;
     unsigned long long* dbg;      // optional: 8 globaltimer stamps per CTA (profiling aid, NULL = off)
+    // Optional per-channel (sum, sum of squares) of the activated output for a following BatchNorm (lean epilogue only):
+    // [gridDim.x][4 lane quadrants][MB][2][Cout_p] floats, zero on entry; every address has ONE writing thread per launch,
+    // so the fire-and-forget reductions land in program order (bit-reproducible).  NULL = off.
+    float* stats;
     // out_mode 3: fused affine coupling (coupling_layers.py:490-500).  Columns [0,ch) = s_raw, [ch,2ch) = t unless
     // cpl_t (external shift, scaled by cpl_tscale).  x is read through the preceding permutation (gather).
     const float* cpl_x;           // (N,ch,H,W) fp32 or NULL (= zeros, z = 0)
@@ -641,6 +645,30 @@ __global__ void __launch_bounds__(WIDE ? 576 : kThreads, WIDE ? 1 : 2) conv_tc_k
                 *reinterpret_cast<uint4*>(ptr) = o0;
                 *reinterpret_cast<uint4*>(ptr + cstride) = o1;
             }
+            if constexpr (WIDE) if (p.stats) {
+                // BatchNorm statistics of this group's 16 channels over the warp's 32 pixels, without a separate pass over the
+                // tensor: transpose-reduce butterfly (16 + 8 + 4 + 2 + 1 shuffles).  After it lane L holds channel L & 15:
+                // lanes 0-15 the sum, lanes 16-31 the sum of squares (of the fp32 activations, before the half rounding).
+                const float okf = ok ? 1.f : 0.f;
+                const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2, h1 = lane & 1;
+                float a16[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float x1 = v[j] * okf, x2 = x1 * x1;
+                    const float recv = __shfl_xor_sync(0xffffffffu, h16 ? x1 : x2, 16);
+                    a16[j] = (h16 ? x2 : x1) + recv;
+                }
+                float a8[8], a4[4], a2[2];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) a8[j] = (h8 ? a16[j + 8] : a16[j]) + __shfl_xor_sync(0xffffffffu, h8 ? a16[j] : a16[j + 8], 8);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) a4[j] = (h4 ? a8[j + 4] : a8[j]) + __shfl_xor_sync(0xffffffffu, h4 ? a8[j] : a8[j + 4], 4);
+#pragma unroll
+                for (int j = 0; j < 2; ++j) a2[j] = (h2 ? a4[j + 2] : a4[j]) + __shfl_xor_sync(0xffffffffu, h2 ? a4[j] : a4[j + 2], 2);
+                const float tot = (h1 ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, h1 ? a2[0] : a2[1], 1);
+                float* dst = p.stats + ((((size_t)blockIdx.x * 4 + q) * p.MB + mb) * 2 + (lane >> 4)) * p.Cout_p + nblk * p.BN + (cgi << 4) + (lane & 15);
+                atomicAdd(dst, tot);                 // result unused: compiles to RED (fire and forget)
+            }
             if (nmb != mb) {                         // next M-block: new pixel column
                 ocol = w0 + nmb * 8 + (m & 7);
                 ok = row_ok && ocol < p.W;
@@ -927,7 +955,7 @@ struct CouplingArgs {
 static int conv_tc_launch(const void* x_c8, const void* w_packed, const float* bias, const float* slope,
                           const void* res, void* out, int N, int H, int W, int Cin_p, int Cout, int Cout_p, int KH,
                           int KW, int BN, int MB, int act, int res_mode, int out_mode, int is_bf16, void* stream,
-                          const CouplingArgs* cpl) {
+                          const CouplingArgs* cpl, float* stats = nullptr) {
     const int KC = pick_kc(Cin_p);
     if (N <= 0 || H <= 0 || W <= 0 || !KC || (Cin_p % 16) || (out_mode != 2 && (Cout_p % BN)) || (BN % 16) || BN < 16 || BN > 256 ||
         (MB != 1 && MB != 2) || MB * BN > 512 || !(KH & 1) || !(KW & 1) || KH > 7 || KW > 7 || out_mode < 0 ||
@@ -990,6 +1018,7 @@ static int conv_tc_launch(const void* x_c8, const void* w_packed, const float* b
         p.kmask = reinterpret_cast<const uint32_t*>((const uint8_t*)w_packed + (size_t)nblks_all * p.num_kb * KH * KW * p.b_bytes);
     } p.slope = slope; p.res = (const uint8_t*)res; p.out = out;
     p.dbg = g_tc_dbg;
+    p.stats = stats;
     if (cpl) {
         p.cpl_x = cpl->x; p.cpl_y = cpl->y; p.cpl_t = cpl->t; p.cpl_perm = cpl->perm; p.cpl_ws = cpl->ws;
         p.cpl_ch = cpl->ch; p.cpl_axis = cpl->axis; p.cpl_inverse = cpl->inverse; p.cpl_kk = cpl->kk; p.cpl_tscale = cpl->tscale;
@@ -1012,6 +1041,10 @@ static int conv_tc_launch(const void* x_c8, const void* w_packed, const float* b
     int ki;
     // lean epilogue variants: C8 output, no residual, activation none / PReLU
     const int fast = (out_mode == 0 && res_mode == 0) ? (act == CWFA_ACT_NONE ? 1 : (act == CWFA_ACT_PRELU && slope) ? 2 : 0) : 0;
+    if (stats && (fast == 0 || !wide)) {
+        set_error("conv_tc: fused BatchNorm statistics need the lean epilogue of the wide kernel (C8 output, no residual, act none / PReLU, MB * BN > 256)");
+        return CWFA_EINVAL;
+    }
     if (out_mode == 3) {
         const int cplmode = (cpl->t ? 2 : 0) + (cpl->inverse ? 1 : 0);       // 0 fwd, 1 inv, 2 fwd+ext, 3 inv+ext
         static const KernT table[2][4] = {
@@ -1055,6 +1088,48 @@ extern "C" int cwfa_conv_tc(const void* x_c8, const void* w_packed, const float*
 }
 
 // Last conv of a coupling sub-network with the affine coupling fused into its epilogue.
+// cwfa_conv_tc with the per-channel (sum, sum of squares) of the activated output accumulated in its epilogue (for a following
+// BatchNorm in batch-statistics mode, unet.py:100-107): stats_partial = cwfa_conv_tc_stats_floats(Cout_p, MB) floats, ZERO on
+// entry; reduce with cwfa_bn_partial_finalize.  C8 output, no residual, activation none / PReLU only.
+extern "C" int64_t cwfa_conv_tc_stats_floats(int Cout_p, int MB) { return (int64_t)2 * kNumSMs * 4 * MB * 2 * Cout_p; }
+extern "C" int cwfa_conv_tc_bn(const void* x_c8, const void* w_packed, const float* bias, const float* slope, void* out, int N, int H,
+                               int W, int Cin_p, int Cout, int Cout_p, int KH, int KW, int BN, int MB, int act, int is_bf16,
+                               float* stats_partial, void* stream) {
+    if (!stats_partial) { set_error("conv_tc_bn: stats_partial is NULL"); return CWFA_EINVAL; }
+    return conv_tc_launch(x_c8, w_packed, bias, slope, nullptr, out, N, H, W, Cin_p, Cout, Cout_p, KH, KW, BN, MB, act, 0, 0, is_bf16,
+                          stream, nullptr, stats_partial);
+}
+// Fixed-order sum of the partial statistics over their (CTA, quadrant, M-block) slices -> BatchNorm scale / shift:
+// scale = gamma * rstd, shift = beta - mean * scale (biased variance, as nn.BatchNorm2d normalises in training mode); also
+// writes stats_out[2 * Cp] = (sum, sum of squares) when not NULL (running-statistics update on the host side).
+__global__ void __launch_bounds__(128) bn_partial_finalize_kernel(const float* __restrict__ part, int slices, int Cp, const float* __restrict__ gamma,
+                                                                   const float* __restrict__ beta, double count, float eps,
+                                                                   float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ stats_out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= Cp) return;
+    double s = 0.0, q = 0.0;
+    for (int k = 0; k < slices; ++k) {               // slice k: [2][Cp]; consecutive threads read consecutive channels
+        s += (double)__ldg(part + ((size_t)k * 2) * Cp + c);
+        q += (double)__ldg(part + ((size_t)k * 2 + 1) * Cp + c);
+    }
+    const double mean = s / count;
+    double var = q / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const double rstd = 1.0 / sqrt(var + (double)eps);
+    const double g = (double)__ldg(gamma + c);
+    scale[c] = (float)(g * rstd);
+    shift[c] = (float)((double)__ldg(beta + c) - mean * g * rstd);
+    if (stats_out) { stats_out[c] = (float)s; stats_out[Cp + c] = (float)q; }
+}
+extern "C" int cwfa_bn_partial_finalize(const float* stats_partial, int Cout_p, int MB, const float* gamma, const float* beta, double count,
+                                        float eps, float* scale, float* shift, float* stats_out, void* stream) {
+    if (!stats_partial || !gamma || !beta || !scale || !shift || Cout_p <= 0 || count <= 0) { set_error("bn_partial_finalize: bad arguments"); return CWFA_EINVAL; }
+    const int slices = 2 * kNumSMs * 4 * MB;
+    bn_partial_finalize_kernel<<<ceil_div(Cout_p, 128), 128, 0, (cudaStream_t)stream>>>(stats_partial, slices, Cout_p, gamma, beta, count, eps,
+                                                                                        scale, shift, stats_out);
+    return check_launch("bn_partial_finalize");
+}
+
 extern "C" int cwfa_conv_tc_coupling_tiles(int H, int W, int MB) { return ceil_div(W, 8 * MB) * ceil_div(H, 16); }
 
 extern "C" int cwfa_conv_tc_coupling(const void* x_c8, const void* w_packed, const float* bias, int N, int H, int W, int Cin_p,

@@ -9,6 +9,7 @@
 // acc1/acc2 are double buffered in TMEM (512 columns) so GEMM1 of tile i+1 overlaps the epilogues of tile i.
 // Warp roles (448 threads): warp0 TMA producer, warp1 MMA issuer, warps2-5 EPI1, warps6-13 EPI2 (4 warps per M-block).
 #include "tc_common.cuh"
+#include "cwfa_b200_debug.h"
 using namespace cwfa;
 using namespace cwfa::tcx;
 

@@ -195,13 +195,22 @@ class _UNet:
                     block(u.conv_block)) for u in unet.up_path]
         self.last = tc.PackedConv(unet.last[0].weight, unet.last[0].bias, kind)
 
+    fuse_bn_stats = True       # BatchNorm batch statistics accumulated in the producing conv's epilogue (cwfa_conv_tc_bn)
+
+    def _conv_bn(self, x, pconv, prelu, bn, training, pool=False):
+        """conv -> PReLU -> BatchNorm (unet.py:99-107).  In batch-statistics mode the per-channel sums come out of the conv's own
+        epilogue (no pass over the tensor for them); the normalisation (+ the 2x2 max-pool) is one apply pass."""
+        if training and self.fuse_bn_stats:
+            y, part, mb = tc.conv_tc_bn_stats(x, pconv, act=ops.ACT_PRELU, slope=prelu.weight)
+            return tc.batchnorm_c8(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, batch_stats=True, eps=bn.eps, pool=pool,
+                                   partial=(part, mb))
+        y = tc.conv_tc(x, pconv, act=ops.ACT_PRELU, slope=prelu.weight)
+        return tc.batchnorm_c8(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, batch_stats=training, eps=bn.eps, pool=pool)
+
     def _block(self, x, blk, training, pool):
         (p0, a0, n0), (p1, a1, n1) = blk
-        x = tc.conv_tc(x, p0, act=ops.ACT_PRELU, slope=a0.weight)
-        x = tc.batchnorm_c8(x, n0.weight, n0.bias, n0.running_mean, n0.running_var, batch_stats=training, eps=n0.eps)
-        x = tc.conv_tc(x, p1, act=ops.ACT_PRELU, slope=a1.weight)
-        return tc.batchnorm_c8(x, n1.weight, n1.bias, n1.running_mean, n1.running_var, batch_stats=training, eps=n1.eps,
-                               pool=pool)
+        x = self._conv_bn(x, p0, a0, n0, training)
+        return self._conv_bn(x, p1, a1, n1, training, pool=pool)
 
     def __call__(self, x8: tc.C8) -> torch.Tensor:
         training = self.unet.training

@@ -144,6 +144,28 @@ def conv_tc(x: C8, pc: PackedConv, *, act: int = 0, slope: Optional[torch.Tensor
     return out
 
 
+def conv_tc_bn_stats(x: C8, pc: PackedConv, *, act: int = 0, slope: Optional[torch.Tensor] = None, mb: Optional[int] = None):
+    """``conv_tc`` (C8 out, no residual, act none / PReLU) that also accumulates the BatchNorm statistics of its activated
+    output in the epilogue.  Returns (out, partial, MB) -- feed ``partial`` to ``batchnorm_c8(..., partial=...)`` -- or
+    (out, None, MB) when the shape does not use the wide kernel (the caller then runs the separate statistics pass)."""
+    if x.Cp != pc.Cin_p or x.kind != pc.kind or pc.transposed:
+        raise ValueError("conv_tc_bn_stats: input / weight layout mismatch")
+    N, H, W = x.N, x.H, x.W
+    if mb is None:
+        mb = 2 if (pc.BN * 2 <= 512 and W > 8) else 1
+        if pc.BN >= 192 and pc.Cin_p <= 64:
+            mb = 1
+    if mb * pc.BN <= 256 or pc.Cout_p != pc.Cout:
+        return conv_tc(x, pc, act=act, slope=slope, mb=mb), None, mb
+    dev = x.data.device
+    out = C8.empty(N, pc.Cout, H, W, dev, x.kind, pc.Cout_p)
+    part = torch.zeros(_lib.load().cwfa_conv_tc_stats_floats(pc.Cout_p, mb), device=dev, dtype=torch.float32)
+    slope_t = None if slope is None else _ck(slope.detach(), "slope")
+    _lib.call("cwfa_conv_tc_bn", x.data.data_ptr(), pc.packed.data_ptr(), _p(pc.bias), _p(slope_t), out.data.data_ptr(), N, H, W,
+              pc.Cin_p, pc.Cout, pc.Cout_p, pc.KH, pc.KW, pc.BN, mb, act, x.is_bf16, part.data_ptr(), _stream())
+    return out, part, mb
+
+
 def conv_transpose_tc(x: C8, pc: PackedConv, skip: Optional[C8] = None, mb: Optional[int] = None) -> C8:
     """ConvTranspose2d(k=2,s=2) (+ skip add) on the tensor cores: 1x1 conv to 4*Cout_p channels whose epilogue
     scatters each channel block to its (i,j) sub-pixel of the (2H,2W) output (unet.py:166,190)."""
@@ -164,14 +186,25 @@ def conv_transpose_tc(x: C8, pc: PackedConv, skip: Optional[C8] = None, mb: Opti
 
 
 def batchnorm_c8(x: C8, gamma, beta, running_mean, running_var, *, batch_stats: bool, eps: float = 1e-5,
-                 pool: bool = False):
+                 pool: bool = False, partial=None):
     """BatchNorm2d on a C8 tensor (batch or running statistics); optionally also returns the 2x2 max-pooled
-    tensor (fused).  Channels must not be padded (Cp == C), true for the U-Net widths 256/512/1024."""
+    tensor (fused).  Channels must not be padded (Cp == C), true for the U-Net widths 256/512/1024.
+    ``partial`` = (partial statistics, MB) from ``conv_tc_bn_stats``: the statistics pass over the tensor is skipped."""
     if x.Cp != x.C:
         raise ValueError("batchnorm_c8: padded channel layouts are not supported")
     dev = x.data.device
     Cp, N, H, W = x.Cp, x.N, x.H, x.W
     lib = _lib.load()
+    if batch_stats and partial is not None and partial[0] is not None:
+        scale = torch.empty(Cp, device=dev, dtype=torch.float32)
+        shift = torch.empty(Cp, device=dev, dtype=torch.float32)
+        _lib.call("cwfa_bn_partial_finalize", partial[0].data_ptr(), Cp, int(partial[1]), _ck(gamma.detach()).data_ptr(),
+                  _ck(beta.detach()).data_ptr(), float(N * H * W), float(eps), scale.data_ptr(), shift.data_ptr(), None, _stream())
+        y = C8.empty(N, x.C, H, W, dev, x.kind, Cp)
+        yp = C8.empty(N, x.C, H // 2, W // 2, dev, x.kind, Cp) if pool else None
+        _lib.call("cwfa_c8_bn_apply", x.data.data_ptr(), scale.data_ptr(), shift.data_ptr(), y.data.data_ptr(),
+                  None if yp is None else yp.data.data_ptr(), N, Cp, H, W, x.is_bf16, _stream())
+        return (y, yp) if pool else y
     if batch_stats:
         stats = torch.empty(2 * Cp, device=dev, dtype=torch.float32)
         ws = torch.empty(lib.cwfa_c8_stats_workspace_floats(Cp), device=dev, dtype=torch.float32)

@@ -160,6 +160,16 @@ int cwfa_conv_tc(const void* x_c8, const void* w_packed, const float* bias, cons
                  const void* res, void* out, int N, int H, int W, int Cin_p, int Cout, int Cout_p,
                  int KH, int KW, int BN, int MB, int act, int res_mode, int out_mode, int is_bf16,
                  void* stream);
+/* cwfa_conv_tc with the BatchNorm statistics of its (activated) output accumulated in the epilogue -- no separate pass over
+ * the tensor (unet.py:100-107: conv -> PReLU -> BatchNorm in batch-statistics mode).  stats_partial:
+ * cwfa_conv_tc_stats_floats(Cout_p, MB) floats, ZERO on entry; cwfa_bn_partial_finalize sums it in a fixed order into the
+ * BatchNorm scale / shift (and the raw (sum, sumsq) when stats_out != NULL).  C8 output, no residual, act none / PReLU. */
+int64_t cwfa_conv_tc_stats_floats(int Cout_p, int MB);
+int cwfa_conv_tc_bn(const void* x_c8, const void* w_packed, const float* bias, const float* slope, void* out, int N, int H,
+                    int W, int Cin_p, int Cout, int Cout_p, int KH, int KW, int BN, int MB, int act, int is_bf16,
+                    float* stats_partial, void* stream);
+int cwfa_bn_partial_finalize(const float* stats_partial, int Cout_p, int MB, const float* gamma, const float* beta, double count,
+                             float eps, float* scale, float* shift, float* stats_out, void* stream);
 /* ---- fused persistent residual block of the coupling sub-network trunk (networks.py:624-634,659-663):
  * y = ELU( W1x1 * ELU( W3x3 (*) x + b3 ) + b1 + x ), 64 -> 64 -> 64 channels.  x / y are 64-channel slices
  * (8 chunks starting at *_chunk_off) of C8 tensors with *_total_chunks chunks; y must not alias x.
@@ -197,9 +207,6 @@ int cwfa_c8_col2im3x3(const void* g, const float* bias, void* out, int N, int Dp
 int cwfa_c8_layernorm_workspace_floats(int N);
 int cwfa_c8_layernorm(const void* x, const void* gamma, const void* beta, void* y, float* workspace, int N, int C, int Cp,
                       int64_t P, float eps, int is_bf16, void* stream);
-/* Profiling aid: when set (device buffer of 8 uint64 per CTA), conv_tc records globaltimer stamps. */
-int cwfa_tc_set_debug_buffer(void* buf);
-int cwfa_resblock_set_debug_buffer(void* buf);   /* [cta][8 tiles][8 stamps] uint64 */
 /* ---- K2+K3+K4 fused: the LAST conv of a coupling sub-network (networks.py:635-638) with the affine coupling
  * (coupling_layers.py:490-500), the per-sample log-det partial sums and the preceding permutation's gather
  * (fixed_transforms.py:37-41, INN_utils.py:73-81) in its epilogue.  Conv columns [0,ch) = s_raw, [ch,2ch) = t,

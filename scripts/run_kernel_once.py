@@ -86,6 +86,22 @@ elif what == "resblock5":
     us = bench(lambda i: tc.resblock_tc_batched(xin[i], sets), n)
     if us:
         print(f"resblock_tc_batched (5 sub-networks): {us:.1f} us = {us / 5:.1f} us per block  {5 * 2.0 * P * 64 * 64 * 10 / us / 1e6:.0f} TFLOP/s", flush=True)
+elif what == "convbn":
+    n = 4
+    xin = [tc.to_c8(torch.randn(1, 256, 512, 512, device=DEV)) for _ in range(n)]
+    pc = tc.PackedConv(torch.randn(256, 256, 3, 3, device=DEV) * 0.03, torch.zeros(256, device=DEV))
+    sl = torch.tensor([0.2], device=DEV)
+    g, b = torch.ones(256, device=DEV), torch.zeros(256, device=DEV)
+    us0 = bench(lambda i: tc.conv_tc(xin[i], pc, act=ops.ACT_PRELU, slope=sl), n)
+    def sep(i):
+        y = tc.conv_tc(xin[i], pc, act=ops.ACT_PRELU, slope=sl)
+        return tc.batchnorm_c8(y, g, b, None, None, batch_stats=True, pool=True)
+    def fused(i):
+        y, part, mb = tc.conv_tc_bn_stats(xin[i], pc, act=ops.ACT_PRELU, slope=sl)
+        return tc.batchnorm_c8(y, g, b, None, None, batch_stats=True, pool=True, partial=(part, mb))
+    us1, us2 = bench(sep, n), bench(fused, n)
+    if us0:
+        print(f"conv 256->256 3x3 @512 + PReLU: {us0:.1f} us;  + BatchNorm (+pool) separate stats pass: {us1:.1f} us;  fused stats: {us2:.1f} us", flush=True)
 elif what == "bn":
     n = 4
     c8s = [tc.to_c8(torch.randn(1, 256, 512, 512, device=DEV)) for _ in range(n)]

@@ -113,6 +113,15 @@ def test_streaming_host_api_matches_engine(golden_tiny, model):
         assert torch.equal(o, ref.cpu()), "streamed frames must equal the one-by-one result bit for bit"
     one = eng.reconstruct_host(frames[2], mv)
     assert torch.equal(one, outs[2])
+    # fp16 host volumes (half the D2H bytes; the reference's own GPU output dtype under autocast, CWFA.py:845): exactly the
+    # round-to-nearest fp16 of the fp32 result (one cast kernel on the device, cwfa_cast_f32_f16)
+    outs16 = [torch.empty((1, golden_tiny["config"]["D"], views.shape[2], views.shape[3]), dtype=torch.float16, pin_memory=True) for _ in range(5)]
+    StreamingReconstructor(eng, tuple(views.shape), mv, depth=2, out_dtype=torch.float16).run(frames, outs16)
+    for o16, o in zip(outs16, outs):
+        assert torch.equal(o16, o.half())
+    from cwfa_b200 import ops
+    x = seeded_randn((3, 5, 7, 11), 9).to(DEV) * 100.0                  # odd element count: vector body + scalar tail
+    assert torch.equal(ops.cast_f16(x), x.half())
 
 
 def test_engine_inverse_with_latent_samples(golden_tiny, model):
@@ -182,3 +191,31 @@ def test_engine_f8_path_equals_nchw_path(golden_tiny, model, kind):
     for ra, rb in zip(res[True][2], res[False][2]):
         assert rel_l2(ra["z"], rb["z"]) < 2e-5 and rel_l2(ra["logdet"], rb["logdet"]) < 1e-4 and rel_l2(ra["sumsq"], rb["sumsq"]) < 1e-4
         assert torch.equal(ra["lo"], rb["lo"])
+
+
+@pytest.mark.parametrize("N,Cin,Cout,H,W", [(1, 256, 256, 40, 24), (2, 64, 512, 16, 16), (1, 512, 1024, 19, 13)])
+def test_conv_with_fused_batchnorm_statistics(N, Cin, Cout, H, W):
+    """conv -> PReLU -> BatchNorm (unet.py:99-107) with the batch statistics accumulated in the conv's epilogue
+    (cwfa_conv_tc_bn + cwfa_bn_partial_finalize) against torch CPU ops, ragged tiles included; the statistics are
+    bit-reproducible (every partial address has a single writer) and the conv output itself is unchanged."""
+    import torch.nn.functional as F
+    from cwfa_b200 import ops, tc
+    x = seeded_randn((N, Cin, H, W), 1).bfloat16().float()
+    w = (seeded_randn((Cout, Cin, 3, 3), 2) * (2.0 / (9 * Cin)) ** 0.5).bfloat16().float()
+    b = seeded_randn((Cout,), 3) * 0.1
+    slope = torch.tensor([0.23])
+    g, be = seeded_randn((Cout,), 6) * 0.2 + 1.0, seeded_randn((Cout,), 7)
+    act = F.prelu(F.conv2d(x, w, b, padding=1), slope)
+    ref = F.batch_norm(act, None, None, g, be, training=True)
+    pc = tc.PackedConv(w.to(DEV), b.to(DEV), "bf16")
+    x8 = tc.to_c8(x.to(DEV))
+    y8, part, mb = tc.conv_tc_bn_stats(x8, pc, act=ops.ACT_PRELU, slope=slope.to(DEV))
+    assert part is not None, "these shapes must take the wide kernel (fused statistics)"
+    assert torch.equal(y8.data, tc.conv_tc(x8, pc, act=ops.ACT_PRELU, slope=slope.to(DEV), mb=mb).data)
+    out = tc.batchnorm_c8(y8, g.to(DEV), be.to(DEV), None, None, batch_stats=True, partial=(part, mb))
+    assert rel_l2(tc.from_c8(out), ref) < 5e-3
+    # against the separate statistics pass over the (half-rounded) stored tensor: same normalisation up to that rounding
+    sep = tc.batchnorm_c8(y8, g.to(DEV), be.to(DEV), None, None, batch_stats=True)
+    assert rel_l2(tc.from_c8(out), tc.from_c8(sep)) < 3e-3
+    y8b, part2, _ = tc.conv_tc_bn_stats(x8, pc, act=ops.ACT_PRELU, slope=slope.to(DEV))
+    assert torch.equal(part, part2)
