@@ -430,7 +430,7 @@ def main():
         orig = _lib.call
 
         def timed_call(name, *a):
-            if name in ("cwfa_conv_tc", "cwfa_resblock_tc", "cwfa_resblock_tc_batched", "cwfa_conv_tc_coupling", "cwfa_coupling_tc", "cwfa_coupling_f8"):
+            if name in ("cwfa_conv_tc", "cwfa_conv_tc_bn", "cwfa_resblock_tc", "cwfa_resblock_tc_batched", "cwfa_conv_tc_coupling", "cwfa_coupling_tc", "cwfa_coupling_f8"):
                 s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 s.record()
                 orig(name, *a)

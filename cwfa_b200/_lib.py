@@ -42,7 +42,7 @@ _SIGS = {
     "cwfa_tc_pack_weights": [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp],
     "cwfa_conv_tc": [vp, vp, vp, vp, vp, vp] + [i32] * 14 + [vp],
     "cwfa_conv_tc_bn": [vp, vp, vp, vp, vp] + [i32] * 12 + [vp, vp],
-    "cwfa_bn_partial_finalize": [vp, i32, i32, vp, vp, f64, f32, vp, vp, vp, vp],
+    "cwfa_bn_partial_finalize": [vp, i32, i32, i32, i32, i32, vp, vp, f32, vp, vp, vp, vp],
     "cwfa_resblock_tc": [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp],
     "cwfa_c8_stats_workspace_floats": [i32],
     "cwfa_c8_channel_stats": [vp, vp, vp, i32, i32, i64, i32, vp],
@@ -92,7 +92,7 @@ _SIGS = {
     "cwfa_pixel_shuffle2_f32": [vp, vp, vp, i32, i32, i32, i32, i32, vp],
 }
 _I64_FUNCS = {"cwfa_tc_packed_weight_elems": [i32, i32, i32, i32, i32],
-              "cwfa_conv_tc_stats_floats": [i32, i32],
+              "cwfa_conv_tc_stats_floats": [i32, i32, i32, i32, i32],
               "cwfa_conv2d_wgrad_workspace_floats": [i32] * 7,
               "cwfa_wgrad_tc_workspace_floats": [i32] * 8}
 _RESTYPES = {"cwfa_version": C.c_char_p, "cwfa_last_error": C.c_char_p}
@@ -151,7 +151,7 @@ class CwfaError(RuntimeError):
 
 
 # kernel launches issued per C-ABI call (for bench.py's "gpu_launches" claim)
-_LAUNCHES = {"cwfa_affine": 2, "cwfa_channel_stats_f32": 2, "cwfa_layernorm_chw_f32": 2, "cwfa_c8_channel_stats": 2, "cwfa_c8_layernorm": 2, "cwfa_conv2d_wgrad_f32": 2, "cwfa_wgrad_tc": 2, "cwfa_prelu_bwd_f32": 2, "cwfa_stencil3d_wgrad_f32": 2,
+_LAUNCHES = {"cwfa_bn_partial_finalize": 2, "cwfa_affine": 2, "cwfa_channel_stats_f32": 2, "cwfa_layernorm_chw_f32": 2, "cwfa_c8_channel_stats": 2, "cwfa_c8_layernorm": 2, "cwfa_conv2d_wgrad_f32": 2, "cwfa_wgrad_tc": 2, "cwfa_prelu_bwd_f32": 2, "cwfa_stencil3d_wgrad_f32": 2,
              "cwfa_reduce_workspace_blocks": 0, "cwfa_channel_dot_workspace_blocks": 0, "cwfa_channel_dot_stats_f32": 2, "cwfa_ln_bwd_stats_f32": 2, "cwfa_stencil3d_wgrad_workspace_floats": 0,
              "cwfa_tc_set_debug_buffer": 0, "cwfa_resblock_set_debug_buffer": 0, "cwfa_device_check": 0, "cwfa_conv_tc_coupling_tiles": 0, "cwfa_coupling_tc_tiles": 0}
 launch_count = 0

@@ -183,9 +183,9 @@ struct TcParams {
     const uint8_t* res;
     void* out;
     unsigned long long* dbg;      // optional: 8 globaltimer stamps per CTA (profiling aid, NULL = off)
-    // Optional per-channel (sum, sum of squares) of the activated output for a following BatchNorm (lean epilogue only):
-    // [gridDim.x][4 lane quadrants][MB][2][Cout_p] floats, zero on entry; every address has ONE writing thread per launch,
-    // so the fire-and-forget reductions land in program order (bit-reproducible).  NULL = off.
+    // Optional per-channel (sum, sum of squares) of the activated output for a following BatchNorm (lean epilogue of the wide
+    // kernel only): one partial per (32-pixel warp row, channel), [N * tiles * 4 quadrants * MB][2][Cout_p] floats, each written
+    // exactly once with plain 64-byte-contiguous stores (no atomics, no zero-fill; summed in a fixed order afterwards).  NULL = off.
     float* stats;
     // out_mode 3: fused affine coupling (coupling_layers.py:490-500).  Columns [0,ch) = s_raw, [ch,2ch) = t unless
     // cpl_t (external shift, scaled by cpl_tscale).  x is read through the preceding permutation (gather).
@@ -207,6 +207,7 @@ __device__ __forceinline__ void stamp(const TcParams& p, int slot) {
 }
 
 constexpr int kMaxBStages = 8;
+constexpr int kStatSplits = 74;      // second-stage partials of the fused BatchNorm statistics (stage-1 grid = channel blocks x 74)
 constexpr int kThreads = 320;        // warp0 TMA, warp1 MMA, warps 2..9 epilogue (8 epilogue warps; the WIDE variant has 16)
 constexpr int kHeaderBytes = 2048;   // barriers, tmem slot, bias stage
 
@@ -666,8 +667,8 @@ __global__ void __launch_bounds__(WIDE ? 576 : kThreads, WIDE ? 1 : 2) conv_tc_k
 #pragma unroll
                 for (int j = 0; j < 2; ++j) a2[j] = (h2 ? a4[j + 2] : a4[j]) + __shfl_xor_sync(0xffffffffu, h2 ? a4[j] : a4[j + 2], 2);
                 const float tot = (h1 ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, h1 ? a2[0] : a2[1], 1);
-                float* dst = p.stats + ((((size_t)blockIdx.x * 4 + q) * p.MB + mb) * 2 + (lane >> 4)) * p.Cout_p + nblk * p.BN + (cgi << 4) + (lane & 15);
-                atomicAdd(dst, tot);                 // result unused: compiles to RED (fire and forget)
+                const size_t slice = (((size_t)n * tiles + (size_t)(pos.ty * p.tiles_x + pos.tx)) * 4 + q) * p.MB + mb;
+                p.stats[(slice * 2 + (lane >> 4)) * p.Cout_p + nblk * p.BN + (cgi << 4) + (lane & 15)] = tot;
             }
             if (nmb != mb) {                         // next M-block: new pixel column
                 ocol = w0 + nmb * 8 + (m & 7);
@@ -1088,10 +1089,14 @@ extern "C" int cwfa_conv_tc(const void* x_c8, const void* w_packed, const float*
 }
 
 // Last conv of a coupling sub-network with the affine coupling fused into its epilogue.
-// cwfa_conv_tc with the per-channel (sum, sum of squares) of the activated output accumulated in its epilogue (for a following
-// BatchNorm in batch-statistics mode, unet.py:100-107): stats_partial = cwfa_conv_tc_stats_floats(Cout_p, MB) floats, ZERO on
-// entry; reduce with cwfa_bn_partial_finalize.  C8 output, no residual, activation none / PReLU only.
-extern "C" int64_t cwfa_conv_tc_stats_floats(int Cout_p, int MB) { return (int64_t)2 * kNumSMs * 4 * MB * 2 * Cout_p; }
+// cwfa_conv_tc with the per-channel (sum, sum of squares) of the activated output produced by its epilogue (for a following
+// BatchNorm in batch-statistics mode, unet.py:100-107): stats_partial = cwfa_conv_tc_stats_floats(N, H, W, Cout_p, MB) floats
+// (no initialisation needed: every slot is written once); reduce with cwfa_bn_partial_finalize.  C8 output, no residual,
+// activation none / PReLU, MB * BN > 256 only.
+static int64_t stats_slices(int N, int H, int W, int MB) { return (int64_t)N * ceil_div(W, 8 * MB) * ceil_div(H, 16) * 4 * MB; }
+extern "C" int64_t cwfa_conv_tc_stats_floats(int N, int H, int W, int Cout_p, int MB) {
+    return stats_slices(N, H, W, MB) * 2 * Cout_p + (int64_t)kStatSplits * 2 * Cout_p;      // + the second-stage buffer
+}
 extern "C" int cwfa_conv_tc_bn(const void* x_c8, const void* w_packed, const float* bias, const float* slope, void* out, int N, int H,
                                int W, int Cin_p, int Cout, int Cout_p, int KH, int KW, int BN, int MB, int act, int is_bf16,
                                float* stats_partial, void* stream) {
@@ -1099,9 +1104,25 @@ extern "C" int cwfa_conv_tc_bn(const void* x_c8, const void* w_packed, const flo
     return conv_tc_launch(x_c8, w_packed, bias, slope, nullptr, out, N, H, W, Cin_p, Cout, Cout_p, KH, KW, BN, MB, act, 0, 0, is_bf16,
                           stream, nullptr, stats_partial);
 }
-// Fixed-order sum of the partial statistics over their (CTA, quadrant, M-block) slices -> BatchNorm scale / shift:
-// scale = gamma * rstd, shift = beta - mean * scale (biased variance, as nn.BatchNorm2d normalises in training mode); also
-// writes stats_out[2 * Cp] = (sum, sum of squares) when not NULL (running-statistics update on the host side).
+// Stage 1: block (channel block, split s) sums its contiguous range of slices; stage 2: fixed-order sum over the splits ->
+// BatchNorm scale = gamma * rstd, shift = beta - mean * scale (biased variance, as nn.BatchNorm2d normalises in training mode);
+// also stats_out[2 * Cp] = (sum, sum of squares) when not NULL.
+__global__ void __launch_bounds__(128) bn_partial_stage1_kernel(const float* __restrict__ part, int64_t slices, int Cp, float* __restrict__ part2) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= Cp) return;
+    const int64_t k0 = slices * blockIdx.y / gridDim.y, k1 = slices * (blockIdx.y + 1) / gridDim.y;
+    float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;       // two independent chains per value (latency), fixed association order
+    int64_t k = k0;
+    for (; k + 1 < k1; k += 2) {
+        s0 += __ldg(part + (k * 2) * Cp + c);
+        q0 += __ldg(part + (k * 2 + 1) * Cp + c);
+        s1 += __ldg(part + ((k + 1) * 2) * Cp + c);
+        q1 += __ldg(part + ((k + 1) * 2 + 1) * Cp + c);
+    }
+    if (k < k1) { s0 += __ldg(part + (k * 2) * Cp + c); q0 += __ldg(part + (k * 2 + 1) * Cp + c); }
+    part2[((size_t)blockIdx.y * 2) * Cp + c] = s0 + s1;
+    part2[((size_t)blockIdx.y * 2 + 1) * Cp + c] = q0 + q1;
+}
 __global__ void __launch_bounds__(128) bn_partial_finalize_kernel(const float* __restrict__ part, int slices, int Cp, const float* __restrict__ gamma,
                                                                    const float* __restrict__ beta, double count, float eps,
                                                                    float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ stats_out) {
@@ -1121,11 +1142,16 @@ __global__ void __launch_bounds__(128) bn_partial_finalize_kernel(const float* _
     shift[c] = (float)((double)__ldg(beta + c) - mean * g * rstd);
     if (stats_out) { stats_out[c] = (float)s; stats_out[Cp + c] = (float)q; }
 }
-extern "C" int cwfa_bn_partial_finalize(const float* stats_partial, int Cout_p, int MB, const float* gamma, const float* beta, double count,
+extern "C" int cwfa_bn_partial_finalize(float* stats_partial, int N, int H, int W, int Cout_p, int MB, const float* gamma, const float* beta,
                                         float eps, float* scale, float* shift, float* stats_out, void* stream) {
-    if (!stats_partial || !gamma || !beta || !scale || !shift || Cout_p <= 0 || count <= 0) { set_error("bn_partial_finalize: bad arguments"); return CWFA_EINVAL; }
-    const int slices = 2 * kNumSMs * 4 * MB;
-    bn_partial_finalize_kernel<<<ceil_div(Cout_p, 128), 128, 0, (cudaStream_t)stream>>>(stats_partial, slices, Cout_p, gamma, beta, count, eps,
+    if (!stats_partial || !gamma || !beta || !scale || !shift || Cout_p <= 0 || N <= 0) { set_error("bn_partial_finalize: bad arguments"); return CWFA_EINVAL; }
+    const int64_t slices = stats_slices(N, H, W, MB);
+    float* part2 = stats_partial + slices * 2 * Cout_p;
+    const int splits = slices < kStatSplits ? (int)slices : kStatSplits;
+    bn_partial_stage1_kernel<<<dim3(ceil_div(Cout_p, 128), splits), 128, 0, (cudaStream_t)stream>>>(stats_partial, slices, Cout_p, part2);
+    int rc = check_launch("bn_partial_stage1");
+    if (rc) return rc;
+    bn_partial_finalize_kernel<<<ceil_div(Cout_p, 128), 128, 0, (cudaStream_t)stream>>>(part2, splits, Cout_p, gamma, beta, (double)N * H * W, eps,
                                                                                         scale, shift, stats_out);
     return check_launch("bn_partial_finalize");
 }

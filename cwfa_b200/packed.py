@@ -195,7 +195,11 @@ class _UNet:
                     block(u.conv_block)) for u in unet.up_path]
         self.last = tc.PackedConv(unet.last[0].weight, unet.last[0].bias, kind)
 
-    fuse_bn_stats = True       # BatchNorm batch statistics accumulated in the producing conv's epilogue (cwfa_conv_tc_bn)
+    # BatchNorm batch statistics produced by the conv's epilogue (cwfa_conv_tc_bn) instead of a separate pass over the tensor.
+    # Measured NEUTRAL at frame level on B200 (A/B in one run: 153.4 / 154.7 frames/s fused vs 155.6 / 153.5 separate): the
+    # butterfly + partial stores cost the 256-channel convs what the saved 0.9 GB read pass gains, so the default keeps the
+    # convolution kernels lean; CWFA_FUSE_BN=1 (or the class attribute) switches it on.
+    fuse_bn_stats = __import__("os").environ.get("CWFA_FUSE_BN", "0") == "1"
 
     def _conv_bn(self, x, pconv, prelu, bn, training, pool=False):
         """conv -> PReLU -> BatchNorm (unet.py:99-107).  In batch-statistics mode the per-channel sums come out of the conv's own

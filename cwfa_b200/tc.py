@@ -159,7 +159,7 @@ def conv_tc_bn_stats(x: C8, pc: PackedConv, *, act: int = 0, slope: Optional[tor
         return conv_tc(x, pc, act=act, slope=slope, mb=mb), None, mb
     dev = x.data.device
     out = C8.empty(N, pc.Cout, H, W, dev, x.kind, pc.Cout_p)
-    part = torch.zeros(_lib.load().cwfa_conv_tc_stats_floats(pc.Cout_p, mb), device=dev, dtype=torch.float32)
+    part = torch.empty(_lib.load().cwfa_conv_tc_stats_floats(N, H, W, pc.Cout_p, mb), device=dev, dtype=torch.float32)
     slope_t = None if slope is None else _ck(slope.detach(), "slope")
     _lib.call("cwfa_conv_tc_bn", x.data.data_ptr(), pc.packed.data_ptr(), _p(pc.bias), _p(slope_t), out.data.data_ptr(), N, H, W,
               pc.Cin_p, pc.Cout, pc.Cout_p, pc.KH, pc.KW, pc.BN, mb, act, x.is_bf16, part.data_ptr(), _stream())
@@ -198,8 +198,8 @@ def batchnorm_c8(x: C8, gamma, beta, running_mean, running_var, *, batch_stats: 
     if batch_stats and partial is not None and partial[0] is not None:
         scale = torch.empty(Cp, device=dev, dtype=torch.float32)
         shift = torch.empty(Cp, device=dev, dtype=torch.float32)
-        _lib.call("cwfa_bn_partial_finalize", partial[0].data_ptr(), Cp, int(partial[1]), _ck(gamma.detach()).data_ptr(),
-                  _ck(beta.detach()).data_ptr(), float(N * H * W), float(eps), scale.data_ptr(), shift.data_ptr(), None, _stream())
+        _lib.call("cwfa_bn_partial_finalize", partial[0].data_ptr(), N, H, W, Cp, int(partial[1]), _ck(gamma.detach()).data_ptr(),
+                  _ck(beta.detach()).data_ptr(), float(eps), scale.data_ptr(), shift.data_ptr(), None, _stream())
         y = C8.empty(N, x.C, H, W, dev, x.kind, Cp)
         yp = C8.empty(N, x.C, H // 2, W // 2, dev, x.kind, Cp) if pool else None
         _lib.call("cwfa_c8_bn_apply", x.data.data_ptr(), scale.data_ptr(), shift.data_ptr(), y.data.data_ptr(),

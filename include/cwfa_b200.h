@@ -160,15 +160,16 @@ int cwfa_conv_tc(const void* x_c8, const void* w_packed, const float* bias, cons
                  const void* res, void* out, int N, int H, int W, int Cin_p, int Cout, int Cout_p,
                  int KH, int KW, int BN, int MB, int act, int res_mode, int out_mode, int is_bf16,
                  void* stream);
-/* cwfa_conv_tc with the BatchNorm statistics of its (activated) output accumulated in the epilogue -- no separate pass over
- * the tensor (unet.py:100-107: conv -> PReLU -> BatchNorm in batch-statistics mode).  stats_partial:
- * cwfa_conv_tc_stats_floats(Cout_p, MB) floats, ZERO on entry; cwfa_bn_partial_finalize sums it in a fixed order into the
- * BatchNorm scale / shift (and the raw (sum, sumsq) when stats_out != NULL).  C8 output, no residual, act none / PReLU. */
-int64_t cwfa_conv_tc_stats_floats(int Cout_p, int MB);
+/* cwfa_conv_tc with the BatchNorm statistics of its (activated) output produced by the epilogue -- no separate pass over the
+ * tensor (unet.py:100-107: conv -> PReLU -> BatchNorm in batch-statistics mode): one (sum, sum of squares) partial per 32-pixel
+ * warp row and channel, plain stores, then a fixed-order two-stage sum (bit-reproducible).  stats_partial:
+ * cwfa_conv_tc_stats_floats(N, H, W, Cout_p, MB) floats, no initialisation; cwfa_bn_partial_finalize turns it into the BatchNorm
+ * scale / shift (and the raw (sum, sumsq) when stats_out != NULL).  C8 output, no residual, act none / PReLU, MB * BN > 256. */
+int64_t cwfa_conv_tc_stats_floats(int N, int H, int W, int Cout_p, int MB);
 int cwfa_conv_tc_bn(const void* x_c8, const void* w_packed, const float* bias, const float* slope, void* out, int N, int H,
                     int W, int Cin_p, int Cout, int Cout_p, int KH, int KW, int BN, int MB, int act, int is_bf16,
                     float* stats_partial, void* stream);
-int cwfa_bn_partial_finalize(const float* stats_partial, int Cout_p, int MB, const float* gamma, const float* beta, double count,
+int cwfa_bn_partial_finalize(float* stats_partial, int N, int H, int W, int Cout_p, int MB, const float* gamma, const float* beta,
                              float eps, float* scale, float* shift, float* stats_out, void* stream);
 /* ---- fused persistent residual block of the coupling sub-network trunk (networks.py:624-634,659-663):
  * y = ELU( W1x1 * ELU( W3x3 (*) x + b3 ) + b1 + x ), 64 -> 64 -> 64 channels.  x / y are 64-channel slices

@@ -1,5 +1,5 @@
 """Per-kernel roofline table at the full-config shapes (CUDA events around a CUDA-graph replay of the calls, best of 5, tensors rotated through > L2).
-Writes profiles/r01_kernel_rooflines.md.  HBM peak / tensor peak from MEASURED_PEAKS.json."""
+Writes profiles/r02_kernel_rooflines.md.  HBM peak / tensor peak from MEASURED_PEAKS.json."""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -87,7 +87,26 @@ pco = tc.PackedConv(torch.randn(96, 64, 3, 3, device=DEV) * 0.04, torch.zeros(96
 xs48 = [torch.randn(1, 48, 512, 512, device=DEV) for _ in range(n)]
 ld = torch.zeros(1, device=DEV)
 pi = torch.randperm(48).to(torch.int32).to(DEV)
-tensor("conv_tc + fused coupling (64->96, ch=48, channel perm)", 2.0 * P * 64 * 96 * 9, lambda i: tc.conv_tc_coupling(xin[i], pco, xs48[i], ch=48, inverse=True, perm=pi, perm_axis=1, logdet=ld), n)
+tensor("coupling_tc: last conv + coupling, NCHW state (64->96, ch=48, channel perm; module-API path)", 2.0 * P * 64 * 96 * 9, lambda i: tc.conv_tc_coupling(xin[i], pco, xs48[i], ch=48, inverse=True, perm=pi, perm_axis=1, logdet=ld), n)
+tk = torch.zeros(8, device=DEV, dtype=torch.int32)
+for ch_ in (48, 24, 12, 6):
+    pcf = tc.coupling_weights_f8(torch.randn(2 * ch_, 64, 3, 3, device=DEV) * 0.04, torch.zeros(2 * ch_, device=DEV), ch_, torch.randperm(ch_), False, "bf16")
+    xf = [tc.to_f8(torch.randn(1, ch_, 512, 512, device=DEV)) for _ in range(n)]
+    rp = torch.randperm(512, device=DEV).to(torch.int32)
+    tensor(f"coupling_f8: last conv + coupling, F8 state (64->{2 * tc.ch8(ch_)}, ch={ch_}, row perm; engine path)", 2.0 * P * 64 * 2 * ch_ * 9,
+           lambda i: tc.coupling_f8(xin[i], pcf, xf[i], ch=ch_, inverse=True, perm=rp, perm_axis=2, logdet=ld, ticket=tk[:1]), n)
+    del xf
+x5 = [tc.to_c8(torch.randn(1, 320, 512, 512, device=DEV)) for _ in range(4)]
+sets5 = [(tc.PackedConv(torch.randn(64, 64, 3, 3, device=DEV) * 0.04, torch.zeros(64, device=DEV), bn=64),
+          tc.PackedConv(torch.randn(64, 64, 1, 1, device=DEV) * 0.1, torch.zeros(64, device=DEV), bn=64)) for _ in range(5)]
+tensor("resblock_tc_batched: the block row of 5 sub-network trunks in one launch (5 x 64 ch) @512x512", 5 * 2.0 * P * 64 * 64 * 10, lambda i: tc.resblock_tc_batched(x5[i], sets5), 4)
+del x5
+hx = [torch.randn(1, 96, 512, 512, device=DEV) for _ in range(4)]
+hbm("haar1d split, detail half in F8 (C=96)", 2 * 96 * P * 4, lambda i: tc.haar1d_split_f8(hx[i]), 4)
+lo4 = [torch.randn(1, 48, 512, 512, device=DEV) for _ in range(4)]
+hi4 = [tc.to_f8(torch.randn(1, 48, 512, 512, device=DEV)) for _ in range(4)]
+hbm("haar1d merge, detail half in F8 (C=96)", 2 * 96 * P * 4, lambda i: tc.haar1d_merge_f8(lo4[i], hi4[i]), 4)
+del hx, lo4, hi4
 
 # conditioning-net depth stencil (48 depths): banded 3x3 conv s1 (hidden tensor write), s2 as 1x1 conv to tap partials, col2im
 del xin, xs48
@@ -113,14 +132,15 @@ hbm("depth stencil s1: banded 3x3 conv 48 -> 1536 ch + PReLU (tcgen05, zero K-st
 hbm("depth stencil s2: 1x1 conv 1536 -> 432 tap partials (tcgen05, zero K-blocks skipped)", (D * Cm + 432) * P * 2, lambda i: tc.conv_tc(hd[i], s2g, mb=1), 4)
 hbm("depth stencil s2: col2im of the 9 tap partials -> 48 ch", (432 + 48) * P * 2, lambda i: tc.col2im3x3_c8(gd[i % 2], bias2, 48), 4)
 
-md = ["# Per-kernel roofline (round 1, one B200; CUDA events around a CUDA-graph replay, best of 5, tensors rotated through > L2)", "",
+md = ["# Per-kernel roofline (round 2, one B200; CUDA events around a CUDA-graph replay, best of 5, tensors rotated through > L2)", "",
       f"Peaks: HBM {HBM} GB/s, bf16 {TF} TFLOP/s burst (MEASURED_PEAKS.json; kernels timed in isolation).", "",
       "| kernel | bound | algorithmic work | us | achieved | frac of measured peak |", "|---|---|---|---|---|---|"]
 md += ["| " + " | ".join(r) + " |" for r in rows]
-md += ["", "Notes: `resblock_tc` and the fused coupling conv issue N = 64 / N = 96 MMAs, whose rate is set by the shared-memory operand reads",
-       "(A 4 KB + B 2-3 KB per 128x N x16 MMA at 128 B/clk/SM = 48-55 cycles against 32-48 cycles of tensor math): the trunk block runs at 59",
-       "cycles/MMA (`scripts/trace_resblock.py`), i.e. 0.8 of that operand-bandwidth bound; the coupling conv is bound by its",
-       "~40-instruction-per-value epilogue (atan, exp, gather, log-det sums).  The depth-stencil rows are HBM rows: their tensor work is",
-       "small once the zero blocks of the banded weights are skipped, the traffic is the 1536-channel hidden tensor."]
-open(os.path.join(ROOT, "profiles", "r01_kernel_rooflines.md"), "w").write("\n".join(md) + "\n")
+md += ["", "Notes: the trunk block and the coupling convs issue N <= 96 MMAs.  An SS-mode (both operands from shared memory) M = 128, K = 16",
+       "MMA costs ~59 cycles on this chip INDEPENDENT of N <= 64 (measured: `profiles/r02_resblock_experiments.md` -- N sweep 64/32/16,",
+       "operand alignment, accumulator-chain experiments all flat), so these kernels have a ceiling of 32/59 = 0.54 of the tensor peak;",
+       "batching the five sub-networks of a level into one launch removes most of the per-launch prologue / tail (24 us per block instead",
+       "of 28-31).  The depth-stencil rows are HBM rows: their tensor work is small once the zero blocks of the banded weights are",
+       "skipped, the traffic is the 1536-channel hidden tensor."]
+open(os.path.join(ROOT, "profiles", "r02_kernel_rooflines.md"), "w").write("\n".join(md) + "\n")
 print("\n".join(md))
