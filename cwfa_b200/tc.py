@@ -307,7 +307,7 @@ def conv_tc_coupling(b: C8, pc: PackedConv, x: Optional[torch.Tensor], *, ch: in
     lib = _lib.load()
     if persistent is None:
         persistent = pc.Cin_p == 64 and pc.KH == 3 and pc.KW == 3 and pc.Cout_p <= 96 and ch <= 48
-    if (b.Cp != 64 or chunk_off) and not persistent:
+    if (b.Cp != pc.Cin_p or chunk_off) and not persistent:
         raise ValueError("conv_tc_coupling: a channel slice of a wider tensor needs the persistent kernel")
     if persistent:
         tiles = lib.cwfa_coupling_tc_tiles(H, W)
