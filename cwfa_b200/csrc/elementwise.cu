@@ -668,17 +668,38 @@ __global__ void __launch_bounds__(256) extract_views_kernel(const TIn* __restric
     const float zero_v = normalise ? (0.f - mean) / stdv : 0.f;
     const TIn* ib = img + (int64_t)b * Hi * Wi;
     float* ob = out + (int64_t)blockIdx.y * SH * SW;
-    for (int i = blockIdx.x; i < SH; i += gridDim.x) {
+    // 4 output columns per thread (one 16-byte store; the window start is arbitrary, so the reads stay 4-byte but cover the
+    // same 16 contiguous bytes) and two view rows in flight per thread: ~8x the bytes in flight of the one-element form, which
+    // is what this latency-bound gather was missing (0.30 -> of the HBM peak).
+    const bool vec = (SW & 3) == 0;
+    const int jw = vec ? SW >> 2 : SW;
+    auto load_row = [&](int i, int j, float (&v)[4]) {
         const int ii = i - (SH - ph);
         const TIn* irow = ib + (int64_t)(ly + ii) * Wi + lx - (SW - pw);
-        float* orow = ob + (int64_t)i * SW;
-        for (int j = threadIdx.x; j < SW; j += blockDim.x) {
-            float v = zero_v;
-            if (any && ii >= 0 && j >= SW - pw) {
-                const float r = (float)irow[j];
-                v = normalise ? (r - mean) / stdv : r;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int jj = vec ? 4 * j + k : j;
+            v[k] = zero_v;
+            if ((vec || k == 0) && any && ii >= 0 && jj >= SW - pw) {
+                const float r = (float)irow[jj];
+                v[k] = normalise ? (r - mean) / stdv : r;
             }
-            orow[j] = v;
+        }
+    };
+    auto store_row = [&](int i, int j, const float (&v)[4]) {
+        float* orow = ob + (int64_t)i * SW;
+        if (vec) *reinterpret_cast<float4*>(orow + 4 * j) = make_float4(v[0], v[1], v[2], v[3]);
+        else orow[j] = v[0];
+    };
+    const int gstep = gridDim.x;
+    for (int i = blockIdx.x; i < SH; i += 2 * gstep) {
+        const bool two = i + gstep < SH;
+        for (int j = threadIdx.x; j < jw; j += blockDim.x) {
+            float a[4], b2[4];
+            load_row(i, j, a);
+            if (two) load_row(i + gstep, j, b2);
+            store_row(i, j, a);
+            if (two) store_row(i + gstep, j, b2);
         }
     }
 }
@@ -691,7 +712,9 @@ extern "C" int cwfa_extract_views(const void* image, int image_is_half, const in
     int gx = ceil_div(kNumSMs * 8, B * L);
     if (gx > SH) gx = SH;
     if (gx < 1) gx = 1;
-    const int threads = SW >= 256 ? 256 : (SW >= 128 ? 128 : 64);
+    const int work = (SW & 3) == 0 ? SW / 4 : SW;              // items per view row (4 columns each when SW % 4 == 0)
+    const int threads = work >= 256 ? 256 : (work >= 128 ? 128 : 64);
+    if ((SW & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15)) { set_error("extract_views: out must be 16-byte aligned"); return CWFA_EINVAL; }
     dim3 grid(gx, B * L);
     if (image_is_half)
         extract_views_kernel<__half><<<grid, threads, 0, (cudaStream_t)stream>>>((const __half*)image, coords, out, Hi, Wi, L, SH, SW, mean, stdv, normalise);
