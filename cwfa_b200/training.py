@@ -49,6 +49,7 @@ class FlatGroup:
         self.offsets = offs
         self.used = [False] * len(mine)                 # "received a gradient since zero_grad": lion_pytorch skips the others
         self._mask, self._mask_key, self._hooks = None, None, []
+        self._buckets, self._ov_hooks = None, []
         for i, (p, o) in enumerate(zip(mine, offs)):
             v = self.flat[o:o + p.numel()].view(p.shape)
             v.copy_(p.data)
@@ -59,6 +60,62 @@ class FlatGroup:
 
     def _mark(self, i):
         self.used[i] = True
+
+    # ---- gradient all-reduce overlapped with backward ("bucketed, overlapped with backward") ----------
+    def enable_overlap(self, group=None, bucket_bytes: int = 32 << 20):
+        """Splits the flat gradient buffer into contiguous buckets (built from the END of the buffer: backward produces the
+        gradients of the last layers first) and all-reduces each bucket asynchronously the moment the last of its parameters
+        has accumulated its gradient, so the collective of the early buckets runs under the rest of the backward pass
+        (the LRNN step reduces 255 MB; a flow level's 4.8 MB is a single bucket).  ``finish_overlap`` waits for the buckets in
+        flight and reduces whatever did not complete (parameters that received no gradient)."""
+        self._ov_group = group
+        self._buckets = []                     # [lo, hi, [param indices]]
+        lo_hi, members, size = None, [], 0
+        for i in range(len(self.params) - 1, -1, -1):
+            p, o = self.params[i], self.offsets[i]
+            end = o + (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+            lo_hi = (o, end) if lo_hi is None else (o, lo_hi[1])
+            members.append(i)
+            size += (end - o) * 4
+            if size >= bucket_bytes or i == 0:
+                self._buckets.append([lo_hi[0], lo_hi[1], members])
+                lo_hi, members, size = None, [], 0
+        self._bucket_of = {}
+        for b, (_, _, mem) in enumerate(self._buckets):
+            for i in mem:
+                self._bucket_of[i] = b
+        self._ov_hooks = [p.register_post_accumulate_grad_hook(lambda _p, i=i: self._param_ready(i)) for i, p in enumerate(self.params)]
+        self._reset_overlap()
+
+    def _reset_overlap(self):
+        if getattr(self, "_buckets", None) is None:
+            return
+        self._pending = [len(mem) for _, _, mem in self._buckets]
+        self._works = [None] * len(self._buckets)
+
+    def _param_ready(self, i):
+        import torch.distributed as dist
+        b = self._bucket_of[i]
+        self._pending[b] -= 1
+        if self._pending[b] == 0 and dist.is_available() and dist.is_initialized() and dist.get_world_size(self._ov_group) > 1:
+            p, o = self.params[i], self.offsets[i]
+            if p.grad is not None and p.grad.data_ptr() == self.grad.data_ptr() + 4 * o:      # gradients live in the flat buffer
+                lo, hi, _ = self._buckets[b]
+                self._works[b] = dist.all_reduce(self.grad[lo:hi], op=dist.ReduceOp.SUM, group=self._ov_group, async_op=True)
+
+    def finish_overlap(self) -> int:
+        """Waits for the bucket collectives in flight, reduces the buckets that never became ready; returns the number of
+        collectives of this step.  Every rank sees the same ready-set (same graph), so the sequence of collectives matches."""
+        import torch.distributed as dist
+        n = 0
+        for b, (lo, hi, _) in enumerate(self._buckets):
+            if self._works[b] is not None:
+                self._works[b].wait()
+            else:
+                dist.all_reduce(self.grad[lo:hi], op=dist.ReduceOp.SUM, group=self._ov_group)
+            n += 1
+        self._reset_overlap()
+        return n
 
     def mark_all_used(self):
         """For gradients written by hand INTO the flat views (no autograd hook fires): treat every parameter as having a gradient."""
@@ -81,13 +138,14 @@ class FlatGroup:
         """Give the parameters up (they keep their values and stay views of this buffer) so another group may re-home them."""
         for p in self.params:
             p._cwfa_flat = False
-        for h in self._hooks:
+        for h in self._hooks + getattr(self, "_ov_hooks", []):
             h.remove()
-        self._hooks = []
+        self._hooks, self._ov_hooks, self._buckets = [], [], None
 
     def zero_grad(self):
         self.grad.zero_()
         self.used = [False] * len(self.params)
+        self._reset_overlap()
         for p, o in zip(self.params, self.offsets):           # a foreign ``zero_grad(set_to_none=True)`` may have dropped the views
             if p.grad is None or p.grad.data_ptr() != self.grad.data_ptr() + 4 * o:
                 p.grad = self.grad[o:o + p.numel()].view(p.shape)
@@ -145,6 +203,11 @@ class Lion:
     def mark_all_used(self):
         for g in self.param_groups:
             g["flat"].mark_all_used()
+
+    def enable_overlap(self, group=None, bucket_bytes: int = 32 << 20):
+        """Bucketed gradient all-reduce overlapped with backward for every flat buffer of this optimiser (``FlatGroup.enable_overlap``)."""
+        for g in self.param_groups:
+            g["flat"].enable_overlap(group, bucket_bytes)
 
     def flat_grads(self) -> List[torch.Tensor]:
         for g in self.param_groups:
@@ -261,9 +324,14 @@ def allreduce_gradients(optimizers: Sequence[Lion], group=None) -> int:
     world = dist.get_world_size(group)
     n = 0
     for o in optimizers:
-        for g in o.flat_grads():
-            if g.numel():
-                dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group)
+        for pg in o.param_groups:
+            fg = pg["flat"]
+            if getattr(fg, "_buckets", None) is not None:
+                fg.grads_alias_flat()
+                n += fg.finish_overlap()                    # buckets were reduced under the backward pass
+            elif fg.grad.numel():
+                fg.grads_alias_flat()
+                dist.all_reduce(fg.grad, op=dist.ReduceOp.SUM, group=group)
                 n += 1
         for pg in o.param_groups:
             for p in pg["flat"].loose:
@@ -272,6 +340,14 @@ def allreduce_gradients(optimizers: Sequence[Lion], group=None) -> int:
                     n += 1
         o.grad_scale = 1.0 / world
     return n
+
+
+def _maybe_overlap(optimizers, group, bucket_bytes: int = 32 << 20):
+    """Data-parallel runs: reduce the gradient buckets under the backward pass."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        for o in optimizers:
+            o.enable_overlap(group, bucket_bytes)
 
 
 def allreduce_nll_terms(sumsq: torch.Tensor, logdet: torch.Tensor, group=None):
@@ -324,6 +400,7 @@ class FlowLevelTrainer:
         self.optimizer = Lion([{"params": list(model.conv_inn[n].parameters()), "lr": lr, "weight_decay": weight_decay}], lr=lr)
         self.optimizer_cond = Lion(list(model.cond_nets[n].parameters()), lr=lr_cond)
         self.collectives = 0
+        _maybe_overlap([self.optimizer, self.optimizer_cond], group)
 
     def release(self):
         self.optimizer.release()
@@ -432,6 +509,7 @@ class LRNNTrainer:
         self.scaler = (GradScaler(init_scale=4.0) if precision == "fp16" else None) if grad_scaler == "auto" else grad_scaler
         self.optimizer = Lion([{"params": list(model.cond_nets[-1].parameters()), "lr": lr, "weight_decay": weight_decay}], lr=lr)
         self.collectives = 0
+        _maybe_overlap([self.optimizer], group)
 
     def release(self):
         self.optimizer.release()
