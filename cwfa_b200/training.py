@@ -92,9 +92,20 @@ class FlatGroup:
             return
         self._pending = [len(mem) for _, _, mem in self._buckets]
         self._works = [None] * len(self._buckets)
+        self._armed = False
+
+    def arm_overlap(self):
+        """The hooks launch collectives only for the backward pass that follows this call (a trainer's ``step``): a backward run
+        outside a data-parallel step (gradient accumulation on one rank, a single-process comparison leg) must not issue a
+        collective the other ranks never join."""
+        if getattr(self, "_buckets", None) is not None:
+            self._reset_overlap()
+            self._armed = True
 
     def _param_ready(self, i):
         import torch.distributed as dist
+        if not self._armed:
+            return
         b = self._bucket_of[i]
         self._pending[b] -= 1
         if self._pending[b] == 0 and dist.is_available() and dist.is_initialized() and dist.get_world_size(self._ov_group) > 1:
@@ -208,6 +219,10 @@ class Lion:
         """Bucketed gradient all-reduce overlapped with backward for every flat buffer of this optimiser (``FlatGroup.enable_overlap``)."""
         for g in self.param_groups:
             g["flat"].enable_overlap(group, bucket_bytes)
+
+    def arm_overlap(self):
+        for g in self.param_groups:
+            g["flat"].arm_overlap()
 
     def flat_grads(self) -> List[torch.Tensor]:
         for g in self.param_groups:
@@ -326,7 +341,7 @@ def allreduce_gradients(optimizers: Sequence[Lion], group=None) -> int:
     for o in optimizers:
         for pg in o.param_groups:
             fg = pg["flat"]
-            if getattr(fg, "_buckets", None) is not None:
+            if getattr(fg, "_buckets", None) is not None and fg._armed:
                 fg.grads_alias_flat()
                 n += fg.finish_overlap()                    # buckets were reduced under the backward pass
             elif fg.grad.numel():
@@ -409,6 +424,8 @@ class FlowLevelTrainer:
     def step(self, gt, views, mean_vol, vol_in, z=None):
         self.optimizer.zero_grad()
         self.optimizer_cond.zero_grad()
+        self.optimizer.arm_overlap()
+        self.optimizer_cond.arm_overlap()
         from . import autograd as ag
         prev = ag.set_training_precision(self.precision)      # 'bf16'/'fp16': convolutions (forward + data gradient) on tcgen05
         try:
@@ -517,6 +534,7 @@ class LRNNTrainer:
     def step(self, gt, views, mean_vol=None):
         from . import autograd as ag
         self.optimizer.zero_grad()
+        self.optimizer.arm_overlap()
         prev = ag.set_training_precision(self.precision)
         try:
             loss, _ = lrnn_loss(self.model, gt, views, mean_vol)

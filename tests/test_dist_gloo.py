@@ -74,7 +74,12 @@ def _train_worker(rank, world, port, q, overlap=False):
     opt = Lion([{"params": [net[0].weight, net[0].bias]}, {"params": list(net[1].parameters()) + list(net[2].parameters())}], lr=1e-3)
     if overlap:
         opt.enable_overlap(bucket_bytes=64)                 # tiny buckets: several collectives per flat buffer, launched from the hooks
+    if overlap and rank == 0:                               # a backward outside an armed step (one rank only) issues no collective
+        opt.zero_grad()
+        _toy_grads(net, 5)
     opt.zero_grad()
+    if overlap:
+        opt.arm_overlap()                                   # what a trainer's step() does before its backward
     _toy_grads(net, rank)                                   # every rank its own frame
     n = allreduce_gradients([opt])
     tot = allreduce_nll_terms(torch.tensor([1.0 + rank, 2.0]), torch.tensor([10.0 * (rank + 1), 1.0]))
