@@ -48,6 +48,7 @@ _SIGS = {
     "cwfa_c8_channel_stats": [vp, vp, vp, i32, i32, i64, i32, vp],
     "cwfa_c8_bn_apply": [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],
     "cwfa_c8_col2im3x3": [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp],
+    "cwfa_stencil3d_tc": [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp],
     "cwfa_c8_layernorm_workspace_floats": [i32],
     "cwfa_c8_layernorm": [vp, vp, vp, vp, vp, i32, i32, i32, i64, f32, i32, vp],
     "cwfa_conv_tc_coupling_tiles": [i32, i32, i32],

@@ -268,6 +268,42 @@ def col2im3x3_c8(g: C8, bias: Optional[torch.Tensor], C: int) -> C8:
     return out
 
 
+class StencilWeights:
+    """Operands of ``stencil3d_tc``: the two Conv3d kernels of the conditioning net's depth stencil (networks.py:221-225) packed
+    for the fused true-3-D kernel (csrc/stencil_tc.cu; layout in include/cwfa_b200.h)."""
+
+    def __init__(self, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor, kind: str = "bf16"):
+        w1, b1 = w1.detach().float(), b1.detach().float()           # (Cm, 1, 3, 3, 3) [kh, kw, kd], (Cm)
+        w2, b2 = w2.detach().float(), b2.detach().float()           # (1, Cm, 3, 3, 3), (1)
+        Cm = w1.shape[0]
+        if Cm != 32 or tuple(w1.shape[1:]) != (1, 3, 3, 3) or tuple(w2.shape) != (1, Cm, 3, 3, 3):
+            raise ValueError("StencilWeights: needs Conv3d(1, 32, 3) -> Conv3d(32, 1, 3)")
+        dt = _DTYPES[kind][0]
+        dev = w1.device
+        A = torch.zeros(Cm, 32, device=dev)                          # [hidden n][k]
+        A[:, :27] = w1.reshape(Cm, 27)                               # k = (kh*3+kw)*3+kd
+        hi = b1.to(dt).float()
+        A[:, 27], A[:, 28] = hi, b1 - hi                             # fp32-accurate bias: [hi | lo] against two 1.0 columns
+        W1 = A.view(Cm, 4, 8).permute(1, 0, 2)                       # [chunk][n][8]
+        B = torch.zeros(3, 16, Cm, device=dev)                       # [kd][n = kh*3+kw][k = c]
+        B[:, :9] = w2[0].permute(3, 1, 2, 0).reshape(3, 9, Cm)       # w2[c, kh, kw, kd] -> [kd][kh*3+kw][c]
+        W2 = B.view(3, 16, 4, 8).permute(0, 2, 1, 3)                 # [kd][chunk][n][8]
+        self.packed = torch.cat([W1.reshape(-1), W2.reshape(-1)]).to(dt).contiguous()
+        self.b2 = b2.reshape(1).contiguous()
+        self.kind = kind
+
+
+def stencil3d_tc(x: C8, sw: StencilWeights, slope: torch.Tensor, D: int, rows_max: int = 0) -> C8:
+    """Depth stencil of the conditioning net, fused: ``Conv3d(1,32,3) -> PReLU(slope) -> Conv3d(32,1,3)`` over (H, W, depth) of the
+    first ``D`` channels of ``x`` (networks.py:239).  ``slope`` is the (1,) PReLU parameter, read on the device."""
+    if x.kind != sw.kind or D > x.Cp or slope.numel() != 1:
+        raise ValueError("stencil3d_tc: kind / depth mismatch or a per-channel PReLU")
+    out = C8.empty(x.N, D, x.H, x.W, x.data.device, x.kind, pad16(D))
+    _lib.call("cwfa_stencil3d_tc", x.data.data_ptr(), out.data.data_ptr(), sw.packed.data_ptr(), sw.b2.data_ptr(),
+              _ck(slope.detach(), "slope").data_ptr(), x.N, x.H, x.W, D, x.Cp // 8, out.Cp // 8, rows_max, x.is_bf16, _stream())
+    return out
+
+
 def resblock_tc(x: C8, p3: PackedConv, p1: PackedConv, in_chunk_off: int = 0) -> C8:
     """Fused trunk residual block y = ELU(conv1x1(ELU(conv3x3(x))) + x) for 64 channels (one persistent kernel).
     ``x`` may be a wider C8 tensor; ``in_chunk_off`` selects the 64-channel slice (8 chunks) to read."""

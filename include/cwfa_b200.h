@@ -202,6 +202,18 @@ int cwfa_c8_bn_apply(const void* x, const float* scale, const float* shift, void
 int cwfa_c8_col2im3x3(const void* g, const float* bias, void* out, int N, int Dp, int Gp, int H, int W,
                       int is_bf16, void* stream);
 
+/* The conditioning net's depth stencil Conv3d(1 -> 32, 3) -> PReLU -> Conv3d(32 -> 1, 3) over the (H, W, depth) volume
+ * (networks.py:221-225 applied at :239) as ONE fused tcgen05 kernel in its true 3-D form (csrc/stencil_tc.cu): GEMM rows are
+ * voxels, the 32-channel hidden volume stays in shared / tensor memory.
+ * x: C8 tensor [N][cin_chunks][H][W][8] whose first D channels are the depths; y: C8 [N][cout_chunks][H][W][8] (channels >= D
+ * are written as zeros).  wpack (half precision of the tensor's kind, 5120 bytes):
+ *   W1 [4 chunks][32 hidden][8]: k = (kh*3+kw)*3+kd < 27 the first conv's taps, k = 27 / 28 the [hi | lo] split of its bias;
+ *   W2[kd] [4 chunks][16][8], kd = 0..2: row n = kh*3+kw (< 9), k = hidden channel: the second conv's taps.
+ * b2: the second conv's bias (1 float), slope: the PReLU slope (1 float); both read on the device.
+ * rows_max: GEMM rows per pixel-row of a strip (multiple of 128, <= 768; 0 = default). 1 <= D <= 64. */
+int cwfa_stencil3d_tc(const void* x, void* y, const void* wpack, const float* b2, const float* slope, int N, int H, int W,
+                      int D, int cin_chunks, int cout_chunks, int rows_max, int is_bf16, void* stream);
+
 /* LayerNorm([C,H,W]) of the LRNN's ConvNeXt blocks (networks.py:486-503) on C8 tensors: per-sample statistics over the
  * C*H*W true elements (channel padding must be zero), y = (x - mean) * rstd * gamma + beta with the element-wise affine
  * parameters given as C8 tensors of shape (1, Cp, H, W) (zero in the padding).  workspace: cwfa_c8_layernorm_workspace_floats(N). */

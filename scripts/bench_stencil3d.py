@@ -1,0 +1,47 @@
+"""Timing of the fused depth-stencil kernel at the full-config shapes (512 x 512, D = 48 / 24 / 12 / 6), CUDA events around a CUDA-graph
+replay on rotated inputs, against the banded two-convolution form.   python scripts/bench_stencil3d.py [rows_max ...]"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from cwfa_b200 import tc
+
+DEV = "cuda:0"
+rows_list = [int(a) for a in sys.argv[1:]] or [0]
+
+
+def timed(fn, n):
+    for i in range(n):
+        fn(i)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        keep = [fn(i) for i in range(n)]
+    g.replay()
+    torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1) / n)
+    del keep, g
+    return best * 1e3
+
+
+for D in (48, 24, 12, 6):
+    n = 6
+    w1, b1 = torch.randn(32, 1, 3, 3, 3, device=DEV) * 0.3, torch.randn(32, device=DEV) * 0.1
+    w2, b2 = torch.randn(1, 32, 3, 3, 3, device=DEV) * 0.1, torch.randn(1, device=DEV)
+    sl = torch.tensor([0.25], device=DEV)
+    sw = tc.StencilWeights(w1, b1, w2, b2, "bf16")
+    xs = [tc.to_c8(torch.randn(1, D, 512, 512, device=DEV)) for _ in range(n)]
+    for rm in rows_list:
+        us = timed(lambda i: tc.stencil3d_tc(xs[i], sw, sl, D, rows_max=rm), n)
+        vox = 512 * 512 * D
+        print(f"stencil3d_tc D={D} rows_max={rm or 768}: {us:.1f} us  ({vox / us / 1e3:.1f} Gvoxel/s, {vox * 3456 / us / 1e6:.1f} TFLOP/s true 3-D flops)", flush=True)
+print("ok")
