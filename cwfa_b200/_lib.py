@@ -98,7 +98,7 @@ _I64_FUNCS = {"cwfa_tc_packed_weight_elems": [i32, i32, i32, i32, i32],
               "cwfa_wgrad_tc_workspace_floats": [i32] * 8}
 _RESTYPES = {"cwfa_version": C.c_char_p, "cwfa_last_error": C.c_char_p}
 # private profiling hooks (csrc/cwfa_b200_debug.h): bound for scripts/trace_*.py, not part of the public header
-_OPTIONAL = {"cwfa_tc_set_debug_buffer": [vp], "cwfa_resblock_set_debug_buffer": [vp]}
+_OPTIONAL = {"cwfa_tc_set_debug_buffer": [vp], "cwfa_resblock_set_debug_buffer": [vp], "cwfa_stencil_set_debug_buffer": [vp]}
 
 
 def exported_symbols():

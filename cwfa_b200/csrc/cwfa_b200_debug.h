@@ -8,6 +8,8 @@ extern "C" {
 int cwfa_tc_set_debug_buffer(void* buf);
 /* [cta][8 tiles][8 stamps] uint64 (NULL = off): resblock_tc_kernel per-tile timeline */
 int cwfa_resblock_set_debug_buffer(void* buf);
+/* 8 uint64 (NULL = off): stencil3d_tc_kernel CTA (0,0): cycles in [x load, im2col, GEMM1, epilogue 1, GEMM2, epilogue 2, gather], pixel-rows */
+int cwfa_stencil_set_debug_buffer(void* buf);
 #ifdef __cplusplus
 }
 #endif

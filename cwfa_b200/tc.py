@@ -280,11 +280,11 @@ class StencilWeights:
             raise ValueError("StencilWeights: needs Conv3d(1, 32, 3) -> Conv3d(32, 1, 3)")
         dt = _DTYPES[kind][0]
         dev = w1.device
-        A = torch.zeros(Cm, 32, device=dev)                          # [hidden n][k]
-        A[:, :27] = w1.reshape(Cm, 27)                               # k = (kh*3+kw)*3+kd
+        A = torch.zeros(3, Cm, 16, device=dev)                       # [kd][hidden n][k]: k = kh*3+kw < 9
+        A[:, :, :9] = w1[:, 0].permute(3, 0, 1, 2).reshape(3, Cm, 9)
         hi = b1.to(dt).float()
-        A[:, 27], A[:, 28] = hi, b1 - hi                             # fp32-accurate bias: [hi | lo] against two 1.0 columns
-        W1 = A.view(Cm, 4, 8).permute(1, 0, 2)                       # [chunk][n][8]
+        A[1, :, 9], A[1, :, 10] = hi, b1 - hi                        # fp32-accurate bias: [hi | lo] against two 1.0 columns (centre tap)
+        W1 = A.view(3, Cm, 2, 8).permute(0, 2, 1, 3)                 # [kd][chunk][n][8]
         B = torch.zeros(3, 16, Cm, device=dev)                       # [kd][n = kh*3+kw][k = c]
         B[:, :9] = w2[0].permute(3, 1, 2, 0).reshape(3, 9, Cm)       # w2[c, kh, kw, kd] -> [kd][kh*3+kw][c]
         W2 = B.view(3, 16, 4, 8).permute(0, 2, 1, 3)                 # [kd][chunk][n][8]

@@ -206,8 +206,9 @@ int cwfa_c8_col2im3x3(const void* g, const float* bias, void* out, int N, int Dp
  * (networks.py:221-225 applied at :239) as ONE fused tcgen05 kernel in its true 3-D form (csrc/stencil_tc.cu): GEMM rows are
  * voxels, the 32-channel hidden volume stays in shared / tensor memory.
  * x: C8 tensor [N][cin_chunks][H][W][8] whose first D channels are the depths; y: C8 [N][cout_chunks][H][W][8] (channels >= D
- * are written as zeros).  wpack (half precision of the tensor's kind, 5120 bytes):
- *   W1 [4 chunks][32 hidden][8]: k = (kh*3+kw)*3+kd < 27 the first conv's taps, k = 27 / 28 the [hi | lo] split of its bias;
+ * are written as zeros; cout_chunks even).  wpack (half precision of the tensor's kind, 6144 bytes):
+ *   W1[kd] [2 chunks][32 hidden][8], kd = 0..2: k = kh*3+kw < 9 the first conv's spatial taps at depth tap kd; for kd = 1,
+ *   k = 9 / 10 hold the [hi | lo] split of its bias;
  *   W2[kd] [4 chunks][16][8], kd = 0..2: row n = kh*3+kw (< 9), k = hidden channel: the second conv's taps.
  * b2: the second conv's bias (1 float), slope: the PReLU slope (1 float); both read on the device.
  * rows_max: GEMM rows per pixel-row of a strip (multiple of 128, <= 768; 0 = default). 1 <= D <= 64. */

@@ -45,3 +45,13 @@ for D in (48, 24, 12, 6):
         vox = 512 * 512 * D
         print(f"stencil3d_tc D={D} rows_max={rm or 768}: {us:.1f} us  ({vox / us / 1e3:.1f} Gvoxel/s, {vox * 3456 / us / 1e6:.1f} TFLOP/s true 3-D flops)", flush=True)
 print("ok")
+# phase breakdown of CTA (0, 0) (cycles per pixel-row), level 0
+from cwfa_b200 import _lib
+buf = torch.zeros(8, device=DEV, dtype=torch.int64)
+_lib.call("cwfa_stencil_set_debug_buffer", buf.data_ptr())
+tc.stencil3d_tc(xs[0] if D == 48 else tc.to_c8(torch.randn(1, 48, 512, 512, device=DEV)), tc.StencilWeights(w1, b1, w2, b2, "bf16"), sl, 48)
+torch.cuda.synchronize()
+_lib.call("cwfa_stencil_set_debug_buffer", None)
+b = buf.tolist()
+names = ["x load", "im2col", "GEMM1", "epilogue 1", "GEMM2", "epilogue 2", "gather"]
+print("phase cycles per pixel-row (CTA 0, D=48):", {n: round(v / max(b[7], 1)) for n, v in zip(names, b[:7])}, "pixel-rows", b[7], "total/row", round(sum(b[:7]) / max(b[7], 1)))
