@@ -43,6 +43,7 @@ def conv_flops_per_frame(cfg):
         ch = D // 2 ** (n + 1)
         total += 2.0 * P * (614400 + 5504 * ch)                    # 5 sub-networks
         total += 2.0 * P * (9 * 29 * ch * 2 + 9 * ch * ch)         # conditioning net 2-D convs
+        total += 2.0 * P * ch * (27 * 32 * 2)                      # depth stencil Conv3d(1,32,3) + Conv3d(32,1,3), true 3-D MACs
     nd = D // 2 ** (L - 1)
     unet = (9 * nd * 256 + 9 * 256 * 256) * P + (9 * 256 * 512 + 9 * 512 * 512) * P / 4 + \
            (9 * 512 * 1024 + 9 * 1024 * 1024) * P / 16 + (4 * 1024 * 512) * P / 16 + (2 * 9 * 512 * 512) * P / 4 + \
@@ -430,7 +431,7 @@ def main():
         orig = _lib.call
 
         def timed_call(name, *a):
-            if name in ("cwfa_conv_tc", "cwfa_conv_tc_bn", "cwfa_resblock_tc", "cwfa_resblock_tc_batched", "cwfa_conv_tc_coupling", "cwfa_coupling_tc", "cwfa_coupling_f8"):
+            if name in ("cwfa_conv_tc", "cwfa_conv_tc_bn", "cwfa_resblock_tc", "cwfa_resblock_tc_batched", "cwfa_conv_tc_coupling", "cwfa_coupling_tc", "cwfa_coupling_f8", "cwfa_stencil3d_tc"):
                 s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 s.record()
                 orig(name, *a)
@@ -693,7 +694,7 @@ def main():
                 "copy_only_frames_per_s": world * args.steps / (copy_only_ms * 1e-3),
                 "copy_only_note": "the same H2D + D2H bytes per frame with NO compute (both directions concurrently): the platform ceiling for this host traffic"},
         "gpu_launches": launches_per_step * args.steps,
-        "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel + resblock_tc_kernel + coupling_f8_kernel (all tcgen05 implicit-GEMM convolution launches of a frame)", "achieved": achieved, "peak": peak_tf,
+        "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel + resblock_tc_kernel + coupling_f8_kernel + stencil3d_tc_kernel (all tcgen05 implicit-GEMM convolution launches of a frame)", "achieved": achieved, "peak": peak_tf,
                      "unit": "TFLOP/s", "frac": (achieved / peak_tf) if achieved else None, "traffic": traffic,
                      "launches_per_step": n_conv, "avg_launch_us": (conv_ms * 1e3 / n_conv) if n_conv else None,
                      "algorithmic_flop_per_step": conv_flop, "conv_ms_per_step": conv_ms, "peak_source": peak_src,

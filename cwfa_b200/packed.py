@@ -130,7 +130,8 @@ class _CondNet:
     """cond_network / ResidualBlock (networks.py:165-242) entirely on the tensor cores.
 
     The depth stencil Conv3d(1->Cm) -> PReLU -> Conv3d(Cm->1) over the (H, W, depth) volume
-    (networks.py:221-225,239) is executed as two ordinary 3x3 2-D convolutions whose channel axis
+    (networks.py:221-225,239) runs as the fused voxel-row kernel ``tc.stencil3d_tc`` for the reference's Cm = 32; for any other
+    width it is executed as two ordinary 3x3 2-D convolutions whose channel axis
     carries (depth, hidden-channel) and whose weights are the depth-banded expansion of the 3x3x3
     kernels: W1[(d,c), d'] = w1[c, :, :, d'-d+1], W2[d, (d',c)] = w2[c, :, :, d'-d+1] for |d'-d| <= 1.
     Zero padding in depth falls out of the band; zero padding in H, W is the conv's own padding."""
@@ -145,6 +146,13 @@ class _CondNet:
         w2, b2 = rb.conv3d[3].weight.detach().float(), rb.conv3d[3].bias.detach().float()      # (1,Cm,3,3,3), (1)
         Cm, D = w1.shape[0], rb.out_channels
         dev = w1.device
+        self.D = D
+        # The fused true-3-D kernel (csrc/stencil_tc.cu: voxel rows, hidden volume kept in the SM) covers the reference's
+        # default 32 hidden channels; other widths take the banded two-convolution form below.
+        self.fused = Cm == 32 and 1 <= D <= 64 and rb.conv3d[1].weight.numel() == 1 and self.fuse_stencil
+        if self.fused:
+            self.sw = tc.StencilWeights(w1, b1, w2, b2, kind)
+            return
         W1 = torch.zeros(D, Cm, D, 3, 3, device=dev)          # [d, c, d', ky, kx]
         W2 = torch.zeros(D, D, Cm, 3, 3, device=dev)          # [d, d', c, ky, kx]
         for kd in range(3):
@@ -163,7 +171,9 @@ class _CondNet:
         self.s2_bias = torch.zeros(tc.pad16(D), device=dev, dtype=torch.float32)
         self.s2_bias[:D] = b2
         self.s2_mb = 1 if self.s2g.BN == 144 else 2       # measured (scripts/bench_stencil.py)
-        self.D = D
+
+    # CWFA_FUSED_STENCIL=0 keeps the banded form (A/B measurements)
+    fuse_stencil = __import__("os").environ.get("CWFA_FUSED_STENCIL", "1") == "1"
 
     def __call__(self, v8: tc.C8) -> tc.C8:
         """views (C8) -> LF condition (C8)."""
@@ -171,6 +181,8 @@ class _CondNet:
         out = tc.conv_tc(v8, self.c1, act=ops.ACT_PRELU, slope=rb.conv1[1].weight)
         res = tc.conv_tc(v8, self.ds)
         out = tc.conv_tc(out, self.c2, act=ops.ACT_PRELU, slope=rb.relu.weight, res=res, res_mode=1)
+        if self.fused:
+            return tc.stencil3d_tc(out, self.sw, rb.conv3d[1].weight, self.D)
         hid = tc.conv_tc(out, self.s1, act=ops.ACT_PRELU, slope=rb.conv3d[1].weight)
         return tc.col2im3x3_c8(tc.conv_tc(hid, self.s2g, mb=self.s2_mb), self.s2_bias, self.D)
 
