@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(kThreads, MINB) stencil3d_tc_kernel(const StPa
             const int gy = y0 + py;
             const bool row_in = gy >= 0 && gy < p.H;
             const int qd = warp & 3;
-            for (int m = warp >> 2; m < n_mt; m += 2) {
+            for (int m = warp >> 2; m < n_mt; m += kThreads / 128) {
                 if (128 * m + 32 * qd >= rows) continue;
                 const int r = 128 * m + 32 * qd + lane;
                 const int px = (int)(((uint32_t)r * div_magic) >> 16), dq = r - px * Dq, gx = x0 - 1 + px;
@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(kThreads, MINB) stencil3d_tc_kernel(const StPa
         {
             __half* qs = q + ((py + 1) % 3) * 9 * QP;
             const int qd = warp & 3;
-            for (int m = warp >> 2; m < n_mt; m += 2) {
+            for (int m = warp >> 2; m < n_mt; m += kThreads / 128) {
                 if (128 * m + 32 * qd >= rows) continue;
                 const int r = 128 * m + 32 * qd + lane;
                 uint32_t a[16];
@@ -294,7 +294,7 @@ extern "C" int cwfa_stencil3d_tc(const void* x, void* y, const void* wpack, cons
     const uint32_t smem_bytes = p.off_stage + stage_bytes;
     const int n_mt = rows_cap / 128;
     p.tmem_cols = n_mt * 32 <= 32 ? 32 : n_mt * 32 <= 64 ? 64 : n_mt * 32 <= 128 ? 128 : 256;
-    const int minb = (3 * (smem_bytes + 1024) <= 227 * 1024 && 3 * p.tmem_cols <= 512) ? 3 : 2;
+    const int minb = 2;
     int ys = (minb * kNumSMs) / p.strips;          // one unit per resident CTA
     if (ys < 1) ys = 1;
     if (ys > H) ys = H;
@@ -303,10 +303,9 @@ extern "C" int cwfa_stencil3d_tc(const void* x, void* y, const void* wpack, cons
     p.x = (const uint4*)x; p.y = (uint4*)y; p.w = (const uint4*)wpack; p.b2 = b2; p.slope = slope;
     p.prof = g_st_prof;
     p.N = N; p.H = H; p.W = W; p.D = D; p.cin_chunks = cin_chunks; p.cout_chunks = cout_chunks;
-    void (*kern)(const StParams) = is_bf16 ? (minb == 3 ? stencil3d_tc_kernel<true, 3> : stencil3d_tc_kernel<true, 2>)
-                                           : (minb == 3 ? stencil3d_tc_kernel<false, 3> : stencil3d_tc_kernel<false, 2>);
-    static bool attr_done[4] = {false, false, false, false};
-    const int ki = (is_bf16 ? 2 : 0) + (minb == 3 ? 1 : 0);
+    void (*kern)(const StParams) = is_bf16 ? stencil3d_tc_kernel<true, 2> : stencil3d_tc_kernel<false, 2>;
+    static bool attr_done[2] = {false, false};
+    const int ki = is_bf16 ? 1 : 0;
     if (!attr_done[ki]) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024) != cudaSuccess ||
             cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100) != cudaSuccess)

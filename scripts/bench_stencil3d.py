@@ -53,5 +53,5 @@ tc.stencil3d_tc(xs[0] if D == 48 else tc.to_c8(torch.randn(1, 48, 512, 512, devi
 torch.cuda.synchronize()
 _lib.call("cwfa_stencil_set_debug_buffer", None)
 b = buf.tolist()
-names = ["-", "im2col", "wait GEMM2", "epilogue 2+sync", "gather", "wait GEMM1", "epilogue 1"]
+names = ["-", "im2col", "GEMM1", "epilogue 1", "GEMM2", "epilogue 2", "gather"]
 print("phase cycles per pixel-row (CTA 0, D=48):", {n: round(v / max(b[7], 1)) for n, v in zip(names, b[:7])}, "pixel-rows", b[7], "total/row", round(sum(b[:7]) / max(b[7], 1)))
