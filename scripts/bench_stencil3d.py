@@ -44,6 +44,26 @@ for D in (48, 24, 12, 6):
         us = timed(lambda i: tc.stencil3d_tc(xs[i], sw, sl, D, rows_max=rm), n)
         vox = 512 * 512 * D
         print(f"stencil3d_tc D={D} rows_max={rm or 768}: {us:.1f} us  ({vox / us / 1e3:.1f} Gvoxel/s, {vox * 3456 / us / 1e6:.1f} TFLOP/s true 3-D flops)", flush=True)
+    # the banded two-convolution form it replaces (packed._CondNet with fuse_stencil off)
+    from cwfa_b200 import ops
+    Cm = 32
+    W1 = torch.zeros(D, Cm, D, 3, 3, device=DEV)
+    W2 = torch.zeros(D, D, Cm, 3, 3, device=DEV)
+    for kd in range(3):
+        for d in range(D):
+            dp = d + kd - 1
+            if 0 <= dp < D:
+                W1[d, :, dp] = w1[:, 0, :, :, kd]
+                W2[d, dp] = w2[0, :, :, :, kd]
+    s1 = tc.PackedConv(W1.reshape(D * Cm, D, 3, 3), b1.repeat(D), "bf16")
+    Wg = tc.col2im3x3_weights(W2.reshape(D, D * Cm, 3, 3))
+    gp = tc.pad16(Wg.shape[0])
+    s2g = tc.PackedConv(Wg, None, "bf16", bn=144 if gp % 144 == 0 else gp)
+    bias = torch.zeros(tc.pad16(D), device=DEV)
+    mb = 1 if s2g.BN == 144 else 2
+    us = timed(lambda i: tc.col2im3x3_c8(tc.conv_tc(tc.conv_tc(xs[i], s1, act=ops.ACT_PRELU, slope=sl), s2g, mb=mb), bias, D), n)
+    print(f"banded form   D={D}: {us:.1f} us (s1 conv + s2 1x1 conv + col2im)", flush=True)
+    del s1, s2g, W1, W2, Wg
 print("ok")
 # phase breakdown of CTA (0, 0) (cycles per pixel-row), level 0
 from cwfa_b200 import _lib

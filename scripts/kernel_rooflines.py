@@ -131,6 +131,15 @@ bias2 = torch.zeros(48, device=DEV)
 hbm("depth stencil s1: banded 3x3 conv 48 -> 1536 ch + PReLU (tcgen05, zero K-steps skipped)", (D + D * Cm) * P * 2, lambda i: tc.conv_tc(xd[i], s1, act=ops.ACT_PRELU, slope=slope), 4)
 hbm("depth stencil s2: 1x1 conv 1536 -> 432 tap partials (tcgen05, zero K-blocks skipped)", (D * Cm + 432) * P * 2, lambda i: tc.conv_tc(hd[i], s2g, mb=1), 4)
 hbm("depth stencil s2: col2im of the 9 tap partials -> 48 ch", (432 + 48) * P * 2, lambda i: tc.col2im3x3_c8(gd[i % 2], bias2, 48), 4)
+# the fused voxel-row kernel that replaces the three rows above in the engine (csrc/stencil_tc.cu)
+del hd, gd, s1, s2g, W1, W2
+sw = tc.StencilWeights(w1.unsqueeze(1), torch.zeros(Cm, device=DEV), w2.unsqueeze(0), torch.zeros(1, device=DEV), "bf16")
+tensor("stencil3d_tc: fused Conv3d(1,32,3) + PReLU + Conv3d(32,1,3), 48 depths (MMA-instruction-bound: 9 x M128 MMAs of N <= 32 per 128 voxels; true 3-D flops)",
+       2.0 * 27 * 32 * 2 * D * P, lambda i: tc.stencil3d_tc(xd[i], sw, slope, D), 4)
+for Dl in (24, 12, 6):
+    xl = [tc.to_c8(torch.randn(1, Dl, 512, 512, device=DEV)) for _ in range(4)]
+    tensor(f"stencil3d_tc: {Dl} depths", 2.0 * 27 * 32 * 2 * Dl * P, lambda i: tc.stencil3d_tc(xl[i], sw, slope, Dl), 4)
+    del xl
 
 md = ["# Per-kernel roofline (round 2, one B200; CUDA events around a CUDA-graph replay, best of 5, tensors rotated through > L2)", "",
       f"Peaks: HBM {HBM} GB/s, bf16 {TF} TFLOP/s burst (MEASURED_PEAKS.json; kernels timed in isolation).", "",
@@ -140,7 +149,12 @@ md += ["", "Notes: the trunk block and the coupling convs issue N <= 96 MMAs.  A
        "MMA costs ~59 cycles on this chip INDEPENDENT of N <= 64 (measured: `profiles/r02_resblock_experiments.md` -- N sweep 64/32/16,",
        "operand alignment, accumulator-chain experiments all flat), so these kernels have a ceiling of 32/59 = 0.54 of the tensor peak;",
        "batching the five sub-networks of a level into one launch removes most of the per-launch prologue / tail (24 us per block instead",
-       "of 28-31).  The depth-stencil rows are HBM rows: their tensor work is small once the zero blocks of the banded weights are",
-       "skipped, the traffic is the 1536-channel hidden tensor."]
+       "of 28-31).  The banded depth-stencil rows are HBM rows: their tensor work is small once the zero blocks of the banded weights are",
+       "skipped, the traffic is the 1536-channel hidden tensor.  The engine now runs the stencil as ONE fused voxel-row kernel",
+       "(`stencil3d_tc`: 406 us instead of 571 us at 48 depths); its tensor-roofline fraction is small by construction -- the true 3-D",
+       "work is 3456 flop per voxel with K = 9 / 32 and N = 32 / 9, so it is bound by the 44-cycle minimum of an M = 128 MMA and by its",
+       "epilogues, not by tensor math or HBM (`profiles/r02_stencil3d_notes.md`).  A clean SS-mode instruction stream measures 48 cycles",
+       "per N = 64 MMA (`experiments/ts_mma_probe.cu`); the 55-59 cycles inside the trunk block include its epilogue traffic on the",
+       "shared-memory port."]
 open(os.path.join(ROOT, "profiles", "r02_kernel_rooflines.md"), "w").write("\n".join(md) + "\n")
 print("\n".join(md))
