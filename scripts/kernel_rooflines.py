@@ -134,7 +134,7 @@ hbm("depth stencil s2: col2im of the 9 tap partials -> 48 ch", (432 + 48) * P * 
 # the fused voxel-row kernel that replaces the three rows above in the engine (csrc/stencil_tc.cu)
 del hd, gd, s1, s2g, W1, W2
 sw = tc.StencilWeights(w1.unsqueeze(1), torch.zeros(Cm, device=DEV), w2.unsqueeze(0), torch.zeros(1, device=DEV), "bf16")
-tensor("stencil3d_tc: fused Conv3d(1,32,3) + PReLU + Conv3d(32,1,3), 48 depths (MMA-instruction-bound: 9 x M128 MMAs of N <= 32 per 128 voxels; true 3-D flops)",
+tensor("stencil3d_tc: fused Conv3d(1,32,3) + PReLU + Conv3d(32,1,3), 48 depths (true 3-D flops; MMA-ISSUE-bound, not math-bound: 1.15 M M128 MMAs of N <= 32 at >= 44 cycles each = a ~180 us floor, 0.44 of it)",
        2.0 * 27 * 32 * 2 * D * P, lambda i: tc.stencil3d_tc(xd[i], sw, slope, D), 4)
 for Dl in (24, 12, 6):
     xl = [tc.to_c8(torch.randn(1, Dl, 512, 512, device=DEV)) for _ in range(4)]
