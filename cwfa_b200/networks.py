@@ -167,7 +167,7 @@ class cond_network(nn.Module):
 
     def forward(self, lf_img):
         if self.global_attention is not None:                # networks.py:196 (None in the reference's constructor)
-            lf_img = lf_img * self.global_attention(lf_img)
+            return [self.subnetworks[0](lf_img * self.global_attention(lf_img))]
         kind = packed.fast_kind(lf_img)
         if kind is not None:
             return [packed.executor(self, kind, packed._CondNet).from_nchw(lf_img)]

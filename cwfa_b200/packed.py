@@ -137,6 +137,9 @@ class _CondNet:
     Zero padding in depth falls out of the band; zero padding in H, W is the conv's own padding."""
 
     def __init__(self, net, kind):
+        if getattr(net, "global_attention", None) is not None:
+            raise NotImplementedError("the tensor-core conditioning-net executor takes the views as they are: apply "
+                                      "cond_network.global_attention (None in the reference, networks.py:189) in the module path")
         rb = net.subnetworks[0]
         self.rb = rb
         self.c1 = tc.PackedConv(rb.conv1[0].weight, rb.conv1[0].bias, kind)
