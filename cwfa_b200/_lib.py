@@ -46,6 +46,7 @@ _SIGS = {
     "cwfa_resblock_tc": [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp],
     "cwfa_c8_stats_workspace_floats": [i32],
     "cwfa_c8_channel_stats": [vp, vp, vp, i32, i32, i64, i32, vp],
+    "cwfa_c8_bn_batch_scale_shift": [vp, vp, vp, f32, vp, vp, vp, i32, i32, i64, i32, vp],
     "cwfa_c8_bn_apply": [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],
     "cwfa_c8_col2im3x3": [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp],
     "cwfa_stencil3d_tc": [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp],

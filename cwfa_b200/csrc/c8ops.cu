@@ -299,6 +299,47 @@ extern "C" int cwfa_c8_channel_stats(const void* x, float* stats, float* workspa
     return check_launch("c8_stats_finalize");
 }
 
+// Batch statistics straight to the BatchNorm scale / shift: the fixed-order sum of the block partials and
+// scale = gamma / sqrt(var + eps), shift = beta - mean * scale in ONE finalize launch (unet.py:100-107 in batch-statistics mode).
+__global__ void c8_stats_bn_finalize_kernel(const float* __restrict__ ws, const float* __restrict__ gamma,
+                                            const float* __restrict__ beta, float* __restrict__ scale,
+                                            float* __restrict__ shift, int Cp, int nblocks, double count, float eps) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= Cp) return;
+    const int ch = c >> 3, j = c & 7;
+    double s = 0.0, q = 0.0;
+    for (int i = 0; i < nblocks; ++i) {
+        s += (double)ws[((int64_t)ch * nblocks + i) * 16 + j];
+        q += (double)ws[((int64_t)ch * nblocks + i) * 16 + 8 + j];
+    }
+    s = (double)(float)s;                       // the same roundings as c8_stats_finalize_kernel + bn_finalize_kernel
+    q = (double)(float)q;
+    const double mean = s / count;
+    double var = q / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const double sc = (double)gamma[c] / sqrt(var + (double)eps);
+    scale[c] = (float)sc;
+    shift[c] = (float)((double)beta[c] - mean * sc);
+}
+
+extern "C" int cwfa_c8_bn_batch_scale_shift(const void* x, const float* gamma, const float* beta, float eps, float* scale,
+                                            float* shift, float* workspace, int N, int Cp, int64_t P, int is_bf16,
+                                            void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N <= 0 || Cp <= 0 || (Cp % 8) || P <= 0 || !gamma || !beta || !scale || !shift || !workspace) {
+        set_error("c8_bn_batch_scale_shift: bad arguments");
+        return CWFA_EINVAL;
+    }
+    dim3 grid(kC8StatBlocks, Cp / 8);
+    if (is_bf16) c8_stats_kernel<true><<<grid, 256, 0, st>>>((const uint4*)x, workspace, N, Cp / 8, P);
+    else c8_stats_kernel<false><<<grid, 256, 0, st>>>((const uint4*)x, workspace, N, Cp / 8, P);
+    int rc = check_launch("c8_stats");
+    if (rc) return rc;
+    c8_stats_bn_finalize_kernel<<<ceil_div(Cp, 128), 128, 0, st>>>(workspace, gamma, beta, scale, shift, Cp, kC8StatBlocks,
+                                                                 (double)N * (double)P, eps);
+    return check_launch("c8_stats_bn_finalize");
+}
+
 extern "C" int cwfa_c8_bn_apply(const void* x, const float* scale, const float* shift, void* y, void* ypool, int N,
                                 int Cp, int H, int W, int is_bf16, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;

@@ -201,7 +201,7 @@ extern "C" int cwfa_haar2d_up(const float* y, float* x, int B, int C, int H, int
 template <int AXIS, int VEC>
 __global__ void __launch_bounds__(256) permute_kernel(const float* __restrict__ x, float* __restrict__ y,
                                                       const int32_t* __restrict__ perm, int C, int H, int W) {
-    extern __shared__ float s_row[];               // AXIS 3: W floats (source row) + W ints (perm)
+    extern __shared__ __align__(16) float s_row[];   // AXIS 3: W floats (source row) per warp + W ints (perm)
     const int c = blockIdx.y % C;
     const int64_t plane = (int64_t)H * W;
     const int64_t splane = (AXIS == 1) ? ((int64_t)(blockIdx.y - c) + __ldg(perm + c)) * plane : (int64_t)blockIdx.y * plane;
@@ -214,11 +214,28 @@ __global__ void __launch_bounds__(256) permute_kernel(const float* __restrict__ 
         for (int w = threadIdx.x; w < W; w += blockDim.x) s_perm[w] = __ldg(perm + w);
         __syncthreads();
         float* row = s_row + (size_t)wid * W;
-        for (int h = blockIdx.x * nw + wid; h < H; h += gridDim.x * nw) {
-            for (int w = lane; w < W; w += 32) row[w] = __ldg(xp + (int64_t)h * W + w);
-            __syncwarp();
-            for (int w = lane; w < W; w += 32) yp[(int64_t)h * W + w] = row[s_perm[w]];
-            __syncwarp();
+        if constexpr (VEC == 4) {
+            // 16-byte global accesses on both sides: the row lands in shared memory as float4, four gathered columns leave as one float4
+            const int W4 = W >> 2;
+            const int4* s_perm4 = reinterpret_cast<const int4*>(s_perm);
+            for (int h = blockIdx.x * nw + wid; h < H; h += gridDim.x * nw) {
+                const float4* xr = reinterpret_cast<const float4*>(xp + (int64_t)h * W);
+                for (int w = lane; w < W4; w += 32) reinterpret_cast<float4*>(row)[w] = __ldg(xr + w);
+                __syncwarp();
+                float4* yr = reinterpret_cast<float4*>(yp + (int64_t)h * W);
+                for (int w = lane; w < W4; w += 32) {
+                    const int4 pp = s_perm4[w];
+                    yr[w] = make_float4(row[pp.x], row[pp.y], row[pp.z], row[pp.w]);
+                }
+                __syncwarp();
+            }
+        } else {
+            for (int h = blockIdx.x * nw + wid; h < H; h += gridDim.x * nw) {
+                for (int w = lane; w < W; w += 32) row[w] = __ldg(xp + (int64_t)h * W + w);
+                __syncwarp();
+                for (int w = lane; w < W; w += 32) yp[(int64_t)h * W + w] = row[s_perm[w]];
+                __syncwarp();
+            }
         }
     } else {
         const int Wv = W / VEC;
@@ -256,8 +273,11 @@ extern "C" int cwfa_permute(const float* x, float* y, const int32_t* perm, int a
         if (vec) permute_kernel<2, 4><<<grid, threads, 0, st>>>(x, y, perm, C, H, W);
         else permute_kernel<2, 1><<<grid, threads, 0, st>>>(x, y, perm, C, H, W);
     } else {
-        dim3 grid3(ceil_div(gx, 8) > 0 ? ceil_div(gx, 8) : 1, planes);
-        permute_kernel<3, 1><<<grid3, 256, (size_t)W * 4 * 9, st>>>(x, y, perm, C, H, W);
+        int g3 = ceil_div(H, 8);                   // 8 rows (one per warp) per block pass; ~8 resident blocks per SM overall
+        if (g3 > gx) g3 = gx;
+        dim3 grid3(g3 > 0 ? g3 : 1, planes);
+        if ((W % 4 == 0) && aligned16(x) && aligned16(y)) permute_kernel<3, 4><<<grid3, 256, (size_t)W * 4 * 9, st>>>(x, y, perm, C, H, W);
+        else permute_kernel<3, 1><<<grid3, 256, (size_t)W * 4 * 9, st>>>(x, y, perm, C, H, W);
     }
     return check_launch("permute");
 }

@@ -205,19 +205,17 @@ def batchnorm_c8(x: C8, gamma, beta, running_mean, running_var, *, batch_stats: 
         _lib.call("cwfa_c8_bn_apply", x.data.data_ptr(), scale.data_ptr(), shift.data_ptr(), y.data.data_ptr(),
                   None if yp is None else yp.data.data_ptr(), N, Cp, H, W, x.is_bf16, _stream())
         return (y, yp) if pool else y
-    if batch_stats:
-        stats = torch.empty(2 * Cp, device=dev, dtype=torch.float32)
+    scale = torch.empty(Cp, device=dev, dtype=torch.float32)
+    shift = torch.empty(Cp, device=dev, dtype=torch.float32)
+    if batch_stats:                                          # statistics pass + ONE finalize launch straight to scale / shift
         ws = torch.empty(lib.cwfa_c8_stats_workspace_floats(Cp), device=dev, dtype=torch.float32)
-        _lib.call("cwfa_c8_channel_stats", x.data.data_ptr(), stats.data_ptr(), ws.data_ptr(), N, Cp, H * W, x.is_bf16, _stream())
-        count = float(N * H * W)
+        _lib.call("cwfa_c8_bn_batch_scale_shift", x.data.data_ptr(), _ck(gamma.detach()).data_ptr(), _ck(beta.detach()).data_ptr(),
+                  float(eps), scale.data_ptr(), shift.data_ptr(), ws.data_ptr(), N, Cp, H * W, x.is_bf16, _stream())
     else:
         rm, rv = _ck(running_mean.detach()), _ck(running_var.detach())
         stats = torch.cat([rm, rv + rm * rm]).contiguous()
-        count = 1.0
-    scale = torch.empty(Cp, device=dev, dtype=torch.float32)
-    shift = torch.empty(Cp, device=dev, dtype=torch.float32)
-    _lib.call("cwfa_bn_finalize_f32", stats.data_ptr(), _ck(gamma.detach()).data_ptr(), _ck(beta.detach()).data_ptr(),
-              scale.data_ptr(), shift.data_ptr(), Cp, count, float(eps), _stream())
+        _lib.call("cwfa_bn_finalize_f32", stats.data_ptr(), _ck(gamma.detach()).data_ptr(), _ck(beta.detach()).data_ptr(),
+                  scale.data_ptr(), shift.data_ptr(), Cp, 1.0, float(eps), _stream())
     y = C8.empty(N, x.C, H, W, dev, x.kind, Cp)
     yp = C8.empty(N, x.C, H // 2, W // 2, dev, x.kind, Cp) if pool else None
     _lib.call("cwfa_c8_bn_apply", x.data.data_ptr(), scale.data_ptr(), shift.data_ptr(), y.data.data_ptr(),

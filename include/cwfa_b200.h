@@ -192,6 +192,11 @@ int cwfa_resblock_tc_batched(const void* x_c8, void* y_c8, int n_sets, const voi
 int cwfa_c8_stats_workspace_floats(int Cp);
 int cwfa_c8_channel_stats(const void* x, float* stats, float* workspace, int N, int Cp, int64_t P,
                           int is_bf16, void* stream);
+/* BatchNorm in batch-statistics mode on a C8 tensor: per-channel sums (cwfa_c8_channel_stats' first pass) and, in the same
+ * finalize launch, scale = gamma / sqrt(var + eps), shift = beta - mean * scale (biased variance, unet.py:100-107).
+ * workspace: cwfa_c8_stats_workspace_floats(Cp) floats. */
+int cwfa_c8_bn_batch_scale_shift(const void* x, const float* gamma, const float* beta, float eps, float* scale, float* shift,
+                                 float* workspace, int N, int Cp, int64_t P, int is_bf16, void* stream);
 int cwfa_c8_bn_apply(const void* x, const float* scale, const float* shift, void* y, void* ypool,
                      int N, int Cp, int H, int W, int is_bf16, void* stream);
 /* col2im of a 3x3 convolution evaluated as ONE 1x1 tensor-core convolution to 9 partial products per output channel

@@ -188,3 +188,16 @@ def test_batchnorm_train_mode_updates_running_statistics_like_torch():
     ops.batchnorm(xg, ours.weight, ours.bias, ours.running_mean, ours.running_var, batch_stats=True, eps=ours.eps, momentum=ours.momentum,
                   update_running=True, num_batches_tracked=ours.num_batches_tracked).sum().backward()
     assert max_abs(ours.running_mean, ref.running_mean) < 1e-6 and int(ours.num_batches_tracked) == 4
+
+
+@pytest.mark.parametrize("B,C,H,W", [(1, 6, 40, 512), (2, 3, 17, 36), (1, 5, 9, 10), (1, 2, 33, 7)])
+def test_permute_gathers_bit_exact_on_every_axis(B, C, H, W):
+    """K4 gather kernels (16-byte paths when W % 4 == 0, scalar otherwise) against index_select: PermuteRandom is axis 1
+    (fixed_transforms.py:37-41), PermuteDim axes 2 / 3 (INN_utils.py:73-81)."""
+    from cwfa_b200 import ops
+    g = torch.Generator().manual_seed(B * 100 + W)
+    x = torch.randn(B, C, H, W, generator=g).to(DEV)
+    for axis, n in ((1, C), (2, H), (3, W)):
+        perm = torch.randperm(n, generator=g)
+        y = ops.permute(x, perm, axis)
+        assert torch.equal(y, x.index_select(axis, perm.to(DEV)))
