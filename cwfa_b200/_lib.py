@@ -71,6 +71,8 @@ _SIGS = {
     "cwfa_conv2d_dgrad_weights_f32": [vp, vp, i32, i32, i32, i32, vp],
     "cwfa_wgrad_tc": [vp, vp, vp, vp] + [i32] * 10 + [vp],
     "cwfa_elu_bwd_f32": [vp, vp, vp, i64, vp],
+    "cwfa_dy_prep_workspace_floats": [i32, i32],
+    "cwfa_dy_prep": [vp, vp, vp, vp, vp, vp, i32, i32, i32, i64, i32, vp],
     "cwfa_axpby_f32": [vp, vp, vp, f32, f32, i64, vp],
     "cwfa_prelu_f32": [vp, vp, vp, i64, vp],
     "cwfa_reduce_workspace_blocks": [],

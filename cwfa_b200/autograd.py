@@ -235,21 +235,20 @@ class _Conv2dTC(_F):
     def backward(ctx, dy):
         from . import tc
         x, w, y, x8d = ctx.saved_tensors
-        dv = ops._ck(dy)
-        if ctx.act == ops.ACT_ELU:
-            g = torch.empty_like(dv)
-            _lib.call("cwfa_elu_bwd_f32", dv.data_ptr(), y.data_ptr(), g.data_ptr(), dv.numel(), _stream())
-            dv = g
         need_x, need_w, need_b, need_r = ctx.needs_input_grad[:4]
         Cout, Cin, KH, KW = w.shape
-        dv8 = tc.to_c8(dv, ctx.kind) if (need_x or (need_w and ctx.wgrad_tc)) else None
+        elu = ctx.act == ops.ACT_ELU
+        need_f32 = (need_r and ctx.has_res) or (need_w and not ctx.wgrad_tc)       # residual cotangent / fp32 weight gradient
+        # ONE pass over dy: ELU adjoint, C8 conversion for the MMAs, bias gradient (csrc/backward.cu: dy_prep_kernel)
+        dv8, dv, db = tc.dy_prep(dy, y if elu else None, ctx.kind, want_f32=need_f32 and elu, want_bias=need_b)
+        if need_f32 and not elu:
+            dv = ops._ck(dy)
         dx = None
         if need_x:
             dx = tc.conv_tc(dv8, _packed_for(ctx.w_ref, None, ctx.kind, transposed_for_dgrad=True), out_nchw=True)
         dw = None
         if need_w:
             dw = conv2d_wgrad_tc(tc.C8(x8d, Cin, ctx.kind), dv8, Cin, Cout, KH) if ctx.wgrad_tc else conv2d_wgrad(x, dv, KH, KW)
-        db = channel_sum(dv) if need_b else None
         dr = dv if (need_r and ctx.has_res) else None
         return dx, dw, db, dr, None, None, None
 

@@ -877,14 +877,16 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, uint16_t* __res
                                     int KC, int num_kb, int BN, int nblks, int transposed, int Cout_p,
                                     uint32_t* __restrict__ kmask) {
     const int KCc = KC / 8;
-    const size_t total = (size_t)nblks * num_kb * T * KCc * BN * 8;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int e = (int)(i % 8);
-        const int nn = (int)((i / 8) % BN);
-        const int chunk = (int)((i / (8 * (size_t)BN)) % KCc);
-        const int tap = (int)((i / (8 * (size_t)BN * KCc)) % T);
-        const int kb = (int)((i / (8 * (size_t)BN * KCc * T)) % num_kb);
-        const int nb = (int)(i / (8 * (size_t)BN * KCc * T * num_kb));
+    // 32-bit index arithmetic (the host checks total < 2^31): one thread per packed element, mixed-radix decode
+    const uint32_t total = (uint32_t)nblks * num_kb * T * KCc * BN * 8;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        uint32_t r = i;
+        const int e = (int)(r & 7u); r >>= 3;
+        const int nn = (int)(r % (uint32_t)BN); r /= (uint32_t)BN;
+        const int chunk = (int)(r % (uint32_t)KCc); r /= (uint32_t)KCc;
+        const int tap = (int)(r % (uint32_t)T); r /= (uint32_t)T;
+        const int kb = (int)(r % (uint32_t)num_kb);
+        const int nb = (int)(r / (uint32_t)num_kb);
         const int co = nb * BN + nn;
         const int ci = kb * KC + chunk * 8 + e;
         float v = 0.f;
@@ -934,6 +936,7 @@ extern "C" int cwfa_tc_pack_weights(const float* w, void* packed, int Cout, int 
     }
     const int T = KH * KW, num_kb = Cin_p / KC, nblks = tot_p / BN;
     const size_t total = (size_t)nblks * num_kb * T * (KC / 8) * BN * 8;
+    if (total >= ((size_t)1 << 31)) { set_error("tc_pack_weights: more than 2^31 packed elements"); return CWFA_EINVAL; }
     int blocks = (int)((total + 255) / 256);
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
     uint32_t* kmask = reinterpret_cast<uint32_t*>((uint16_t*)packed + total);        // total * 2 bytes is a multiple of 16

@@ -57,6 +57,23 @@ def from_c8(x: C8) -> torch.Tensor:
     return y
 
 
+def dy_prep(dy: torch.Tensor, y: Optional[torch.Tensor], kind: str, *, want_f32: bool = False, want_bias: bool = False):
+    """One pass over a convolution's output cotangent (autograd of ``nn.Conv2d``): ``g = dy * ELU'(y)`` (``y`` given) or ``dy``,
+    returned as the C8 tensor the data / weight gradient kernels read, optionally as fp32 NCHW, plus its per-channel sums
+    (the bias gradient).  Returns ``(g8, g32 or None, db or None)``."""
+    dy = _ck(dy, "dy")
+    N, C, H, W = dy.shape
+    g8 = C8.empty(N, C, H, W, dy.device, kind)
+    g32 = torch.empty_like(dy) if want_f32 else None
+    db = ws = None
+    if want_bias:
+        db = torch.empty(C, device=dy.device, dtype=torch.float32)
+        ws = torch.empty(_lib.load().cwfa_dy_prep_workspace_floats(N, g8.Cp), device=dy.device, dtype=torch.float32)
+    _lib.call("cwfa_dy_prep", dy.data_ptr(), None if y is None else _ck(y, "y").data_ptr(), g8.data.data_ptr(), _p(g32), _p(db), _p(ws),
+              N, C, g8.Cp, H * W, g8.is_bf16, _stream())
+    return g8, g32, db
+
+
 def pick_bn(cout_p: int) -> int:
     """Largest legal N tile (multiple of 16, <= 256) that divides the padded output channels."""
     for bn in (256, 128, 96, 64, 48, 32, 16):

@@ -298,6 +298,14 @@ int cwfa_wgrad_tc(const void* x_c8, const void* dy_c8, float* dw, float* workspa
                   int Cout, int Cout_p, int KH, int KW, int is_bf16, void* stream);
 /* ELU(alpha=1) adjoint from the layer OUTPUT y: dv = dy * (y > 0 ? 1 : y + 1)  (dv may alias dy). */
 int cwfa_elu_bwd_f32(const float* dy, const float* y, float* dv, int64_t n, void* stream);
+/* Cotangent preparation of a tensor-core convolution's backward pass in ONE pass over dy: g = dy * ELU'(y) when y != NULL (else
+ * g = dy), written as the C8 half tensor g8 [N][Cp/8][P][8] the data / weight gradient MMAs read (channels >= C zero), optionally
+ * also as fp32 NCHW (g32, may be NULL), and db[c] = sum over (n, pixels) of g = the bias gradient (db may be NULL; deterministic
+ * two-stage sum).  workspace: cwfa_dy_prep_workspace_floats(N, Cp) floats (needed when db != NULL).
+ * Replaces cwfa_elu_bwd_f32 + cwfa_nchw_to_c8 + cwfa_channel_stats in the autograd of nn.Conv2d (CWFA.py:996). */
+int cwfa_dy_prep_workspace_floats(int N, int Cp);
+int cwfa_dy_prep(const float* dy, const float* y, void* g8, float* g32, float* db, float* workspace, int N, int C, int Cp,
+                 int64_t P, int is_bf16, void* stream);
 /* out = alpha*a + beta*b (b may be NULL). */
 int cwfa_axpby_f32(const float* a, const float* b, float* out, float alpha, float beta, int64_t n, void* stream);
 /* nn.PReLU() with one shared slope (networks.py:209) as a stand-alone op and its adjoint: dv = v > 0 ? dy : a*dy,

@@ -703,3 +703,23 @@ def test_lrnn_step_with_mean_volume_vs_oracle_and_reference(golden_tiny, golden_
     assert abs(float(loss) - float(g["loss"])) < 1e-4 * abs(float(g["loss"]))
     assert branch[kb] < 2e-3 and unet[ku] < 5e-2
     check_against_golden({k: v.cpu() for k, v in ours.items()}, g["grads"], 5e-2)
+
+
+@pytest.mark.parametrize("kind", ["bf16", "fp16"])
+@pytest.mark.parametrize("N,C,H,W", [(1, 64, 32, 32), (2, 6, 9, 14), (1, 3, 5, 7), (1, 96, 16, 20), (1, 17, 8, 8)])
+@pytest.mark.parametrize("elu", [True, False])
+def test_dy_prep_fused_cotangent_pass(kind, N, C, H, W, elu):
+    """``tc.dy_prep`` (ELU adjoint + C8 conversion + bias gradient in one pass) against the three separate steps, incl. channel
+    counts whose last 8-channel chunk is partly or wholly padding and odd pixel counts (scalar path)."""
+    from cwfa_b200 import tc
+    g = torch.Generator().manual_seed(C * 10 + W)
+    dy = torch.randn(N, C, H, W, generator=g).to(DEV)
+    y = (torch.randn(N, C, H, W, generator=g) * 0.7).to(DEV) if elu else None
+    ref = dy * torch.where(y > 0, torch.ones_like(y), y + 1.0) if elu else dy
+    g8, g32, db = tc.dy_prep(dy, y, kind, want_f32=True, want_bias=True)
+    assert torch.equal(g32, ref)
+    assert torch.equal(g8.data, tc.to_c8(ref, kind).data)                 # same rounding, zero channel padding
+    want = ref.double().sum(dim=(0, 2, 3))
+    assert float((db.double() - want).abs().max()) <= 1e-5 * max(1.0, float(want.abs().max()))
+    g8b, none32, noneb = tc.dy_prep(dy, y, kind)
+    assert none32 is None and noneb is None and torch.equal(g8b.data, g8.data)
