@@ -45,6 +45,9 @@ _SIGS = {
     "cwfa_bn_partial_finalize": [vp, i32, i32, i32, i32, i32, vp, vp, f32, vp, vp, vp, vp],
     "cwfa_resblock_tc": [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp],
     "cwfa_c8_stats_workspace_floats": [i32],
+    "cwfa_c8_prelu": [vp, vp, vp, i32, i32, i64, i32, vp],
+    "cwfa_c8_prelu_bwd": [vp, vp, vp, vp, vp, vp, i32, i32, i64, i32, vp],
+    "cwfa_c8_elu_bwd": [vp, vp, vp, vp, vp, i32, i32, i64, i32, vp],
     "cwfa_c8_channel_stats": [vp, vp, vp, i32, i32, i64, i32, vp],
     "cwfa_c8_bn_batch_scale_shift": [vp, vp, vp, f32, vp, vp, vp, i32, i32, i64, i32, vp],
     "cwfa_c8_bn_apply": [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],

@@ -253,6 +253,79 @@ class _Conv2dTC(_F):
         return dx, dw, db, dr, None, None, None
 
 
+class _SubnetTC(_F):
+    """A whole coupling sub-network (1x1 in -> 3 x [3x3 + ELU, 1x1 + skip + ELU] -> 3x3 out, networks.py:624-638,659-671) as ONE
+    autograd node whose activations AND cotangents stay in the C8 half layout: every convolution reads and writes C8 (ELU and
+    the skip add in its epilogue), the adjoint walks back with ``elu_bwd_c8`` (+ bias sums) -> data-gradient conv (skip add in
+    the epilogue) -> tensor-core weight gradient from the saved C8 operands.  The per-convolution node chain converted an fp32
+    NCHW tensor to C8 before every convolution and after every adjoint (12 % of a training step)."""
+
+    @staticmethod
+    def forward(ctx, inp, kind, *params):
+        from . import tc
+        (w_in, b_in), blocks, (w_out, b_out) = (params[0], params[1]), [params[2 + 4 * k: 6 + 4 * k] for k in range(3)], (params[14], params[15])
+        x8 = tc.to_c8(_f32(inp), kind)
+        b = tc.conv_tc(x8, _packed_for(w_in, b_in, kind))
+        saved = [x8.data, b.data]
+        for (w3, b3, w1, b1) in blocks:
+            t = tc.conv_tc(b, _packed_for(w3, b3, kind), act=ops.ACT_ELU)
+            b = tc.conv_tc(t, _packed_for(w1, b1, kind), act=ops.ACT_ELU, res=b, res_mode=1)
+            saved += [t.data, b.data]
+        y = tc.conv_tc(b, _packed_for(w_out, b_out, kind), out_nchw=True)
+        ctx.save_for_backward(*saved)
+        ctx.params, ctx.kind, ctx.Cin, ctx.n = params, kind, inp.shape[1], w_in.shape[0]
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        from . import tc
+        kind, n, Cin, params = ctx.kind, ctx.n, ctx.Cin, ctx.params
+        sv = ctx.saved_tensors
+        C8 = lambda d, c: tc.C8(d, c, kind)
+        x8, bs, ts = C8(sv[0], Cin), [C8(sv[1 + 2 * k], n) for k in range(4)], [C8(sv[2 + 2 * k], n) for k in range(3)]
+        w_out = params[14]
+        grads = [None] * 16
+        dy8, _, grads[15] = tc.dy_prep(dy, None, kind, want_bias=True)
+        grads[14] = conv2d_wgrad_tc(bs[3], dy8, n, w_out.shape[0], w_out.shape[2])
+        d = tc.conv_tc(dy8, _packed_for(w_out, None, kind, transposed_for_dgrad=True))            # cotangent of b_3 (post-ELU)
+        for k in (2, 1, 0):
+            w3, b3, w1, b1 = params[2 + 4 * k: 6 + 4 * k]
+            g, st = tc.elu_bwd_c8(d, bs[k + 1])                                                   # through ELU(conv1x1(t) + b_k)
+            grads[5 + 4 * k] = st[:n].clone()
+            grads[4 + 4 * k] = conv2d_wgrad_tc(ts[k], g, n, n, 1)
+            dt = tc.conv_tc(g, _packed_for(w1, None, kind, transposed_for_dgrad=True))
+            gt, st = tc.elu_bwd_c8(dt, ts[k])                                                     # through ELU(conv3x3(b_k))
+            grads[3 + 4 * k] = st[:n].clone()
+            grads[2 + 4 * k] = conv2d_wgrad_tc(bs[k], gt, n, n, 3)
+            d = tc.conv_tc(gt, _packed_for(w3, None, kind, transposed_for_dgrad=True), res=g, res_mode=1)   # + the skip branch
+        w_in = params[0]
+        grads[1] = tc.channel_sums_c8(d)[:n]
+        grads[0] = conv2d_wgrad_tc(x8, d, Cin, n, w_in.shape[2])
+        dx = tc.conv_tc(d, _packed_for(w_in, None, kind, transposed_for_dgrad=True), out_nchw=True) if ctx.needs_input_grad[0] else None
+        return (dx, None) + tuple(grads)
+
+
+# CWFA_SUBNET_NODE=0 keeps one autograd node per convolution (A/B measurements)
+_SUBNET_NODE = __import__("os").environ.get("CWFA_SUBNET_NODE", "1") == "1"
+
+
+def subnet_tc_supported(inp, convs) -> bool:
+    """The C8-native sub-network node needs a half training precision, CUDA tensors, 64 internal channels' worth of odd
+    square kernels with biases -- the reference's sub-network."""
+    if not _SUBNET_NODE or _PRECISION == "fp32" or not torch.is_grad_enabled() or not inp.is_cuda or inp.dim() != 4:
+        return False
+    return all(c.bias is not None and c.weight.shape[2] == c.weight.shape[3] and c.weight.shape[2] in (1, 3) for c in convs)
+
+
+def subnet_tc(inp, conv_in, blocks, conv_out):
+    """``conv_out(trunk(conv_in(inp)))`` of wavelet_flow_subnetwork2D through the single C8-native node."""
+    params = [conv_in.weight, conv_in.bias]
+    for c3, c1 in blocks:
+        params += [c3.weight, c3.bias, c1.weight, c1.bias]
+    params += [conv_out.weight, conv_out.bias]
+    return _SubnetTC.apply(inp, _PRECISION, *params)
+
+
 class _GeluAdd(_F):
     """y = gelu(v) + r (exact erf GELU + the ConvNeXt skip, networks.py:492,503)."""
 
@@ -632,8 +705,67 @@ def depth_stencil3d_banded(x, w1, b1, slope, w2, b2):
     return conv2d(hid, W2, b2.expand(D))
 
 
+def _dgrad_weights(w: torch.Tensor) -> torch.Tensor:
+    """(Cout,Cin,K,K) -> the flipped / transposed (Cin,Cout,K,K) weights whose forward convolution is the data gradient."""
+    Cout, Cin, KH, KW = w.shape
+    wt = torch.empty((Cin, Cout, KH, KW), device=w.device, dtype=torch.float32)
+    _lib.call("cwfa_conv2d_dgrad_weights_f32", w.data_ptr(), wt.data_ptr(), Cout, Cin, KH, KW, _stream())
+    return wt
+
+
+class _StencilBandedTC(_F):
+    """The banded depth stencil of ``depth_stencil3d_banded`` as ONE autograd node whose 32 D-channel hidden tensor lives only
+    in the C8 half layout: conv (C8 out) -> PReLU on C8 -> conv, and in the adjoint data gradient (C8 out) -> PReLU adjoint on
+    C8 (+ bias / slope sums) -> the two tensor-core weight gradients straight from the saved C8 operands.  The generic node
+    chain moved the 1.6 GB fp32 NCHW form of that tensor six times per step (conv epilogue, PReLU, conversion, and the same
+    three on the way back).  Banded weight gradients are folded back onto the (Cm, 27) parameters here (adjoint of the gather)."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, slope, w2, b2, kind):
+        from . import tc
+        D, Cm = x.shape[1], w1.shape[0]
+        kd, mask = _band_index(D, x.device)
+        g1 = _f32(w1)[:, 0].index_select(3, kd).reshape(Cm, 3, 3, D, D) * mask       # [c, h, w, d, d']
+        g2 = _f32(w2)[0].index_select(3, kd).reshape(Cm, 3, 3, D, D) * mask
+        W1 = g1.permute(3, 0, 4, 1, 2).reshape(D * Cm, D, 3, 3).contiguous()          # [(d,c), d', h, w]
+        W2 = g2.permute(3, 4, 0, 1, 2).reshape(D, D * Cm, 3, 3).contiguous()          # [d, (d',c), h, w]
+        x8 = tc.to_c8(_f32(x), kind)
+        pre8 = tc.conv_tc(x8, tc.PackedConv(W1, _f32(b1).repeat(D), kind))
+        hid8 = tc.prelu_c8(pre8, slope)
+        y = tc.conv_tc(hid8, tc.PackedConv(W2, _f32(b2).expand(D).contiguous(), kind), out_nchw=True)
+        ctx.save_for_backward(x8.data, pre8.data, hid8.data, W1, W2, slope.detach(), kd, mask)
+        ctx.kind, ctx.D, ctx.Cm, ctx.slope_shape = kind, D, Cm, slope.shape
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        from . import tc
+        x8d, pre8d, hid8d, W1, W2, slope, kd, mask = ctx.saved_tensors
+        D, Cm, kind = ctx.D, ctx.Cm, ctx.kind
+        H = D * Cm
+        dy8, _, dbD = tc.dy_prep(dy, None, kind, want_bias=True)
+        d_hid8 = tc.conv_tc(dy8, tc.PackedConv(_dgrad_weights(W2), None, kind))
+        g8, stats = tc.prelu_bwd_c8(d_hid8, tc.C8(pre8d, H, kind), slope)
+        db1 = stats[:H].view(D, Cm).sum(0)
+        dslope = stats[g8.Cp:g8.Cp + H].sum().reshape(ctx.slope_shape)
+        dW2 = conv2d_wgrad_tc(tc.C8(hid8d, H, kind), dy8, H, D, 3)                      # (D, D*Cm, 3, 3)
+        dx = tc.conv_tc(g8, tc.PackedConv(_dgrad_weights(W1), None, kind), out_nchw=True)
+        dW1 = conv2d_wgrad_tc(tc.C8(x8d, D, kind), g8, D, H, 3)                         # (D*Cm, D, 3, 3)
+        dg1 = (dW1.reshape(D, Cm, D, 3, 3).permute(1, 3, 4, 0, 2) * mask).reshape(Cm, 3, 3, D * D)
+        dg2 = (dW2.reshape(D, D, Cm, 3, 3).permute(2, 3, 4, 0, 1) * mask).reshape(Cm, 3, 3, D * D)
+        dw1 = torch.zeros((Cm, 3, 3, 3), device=dy.device, dtype=torch.float32).index_add_(3, kd, dg1).unsqueeze(1)
+        dw2 = torch.zeros((Cm, 3, 3, 3), device=dy.device, dtype=torch.float32).index_add_(3, kd, dg2).unsqueeze(0)
+        return dx, dw1, db1, dslope, dw2, dbD.sum().reshape(1), None
+
+
+# CWFA_STENCIL_NODE=0 keeps the generic conv2d -> PReLU -> conv2d node chain (A/B measurements)
+_STENCIL_NODE = __import__("os").environ.get("CWFA_STENCIL_NODE", "1") == "1"
+
+
 def depth_stencil3d(x, w1, b1, slope, w2, b2):
     if _PRECISION != "fp32":
+        if _STENCIL_NODE and slope.numel() == 1 and w1.shape[1] == 1 and tuple(w1.shape[2:]) == (3, 3, 3) and b1 is not None and b2 is not None:
+            return _StencilBandedTC.apply(x, w1, b1, slope, w2, b2, _PRECISION)
         return depth_stencil3d_banded(x, w1, b1, slope, w2, b2)
     return _DepthStencil.apply(x, w1, b1, slope, w2, b2)
 

@@ -284,6 +284,126 @@ extern "C" int cwfa_c8_col2im3x3(const void* g, const float* bias, void* out, in
     return check_launch("c8_col2im3x3");
 }
 
+// PReLU on a C8 tensor and its adjoint (training path of the conditioning net's banded depth stencil: the 32 D-channel hidden
+// tensor stays in the C8 half layout between the two tensor-core convolutions instead of making fp32 NCHW round trips).
+template <bool BF16>
+__global__ void __launch_bounds__(256) c8_prelu_kernel(const uint4* __restrict__ x, const float* __restrict__ slope,
+                                                       uint4* __restrict__ y, int64_t n16) {
+    const float a = __ldg(slope);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n16; i += stride) {
+        float v[8];
+        unpack8<BF16>(__ldg(x + i), v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = v[j] >= 0.f ? v[j] : a * v[j];
+        y[i] = pack8<BF16>(v);
+    }
+}
+// g = dy * PReLU'(pre); per-channel sums s[c] = sum g (bias gradient of the producing conv), q[c] = sum dy * min(pre, 0)
+// (slope gradient), in the workspace layout of c8_stats_kernel (finalised by c8_stats_finalize_kernel)
+template <bool BF16, int MODE>
+__global__ void __launch_bounds__(256) c8_prelu_bwd_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ pre,
+                                                           const float* __restrict__ slope, uint4* __restrict__ g,
+                                                           float* __restrict__ ws, int N, int chunks, int64_t P) {
+    const int ch = blockIdx.y;
+    const float a = MODE == 0 ? __ldg(slope) : 0.f;
+    float s[8], q[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+    // MODE 0: PReLU'(pre) = pre < 0 ? a : 1, q += dy * min(pre, 0).  MODE 1: ELU' from the OUTPUT y: y > 0 ? 1 : y + 1.
+    auto adj = [&](float (&dv)[8], const float (&pv)[8]) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if constexpr (MODE == 0) {
+                const bool neg = pv[j] < 0.f;
+                q[j] = fmaf(dv[j], neg ? pv[j] : 0.f, q[j]);
+                dv[j] = neg ? a * dv[j] : dv[j];
+            } else {
+                dv[j] *= pv[j] > 0.f ? 1.f : pv[j] + 1.f;
+            }
+            s[j] += dv[j];
+        }
+    };
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int n = 0; n < N; ++n) {
+        const int64_t base = ((int64_t)n * chunks + ch) * P;
+        for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < P; i += 2 * stride) {
+            const bool two = i + stride < P;
+            const uint4 d0 = __ldg(dy + base + i), p0 = __ldg(pre + base + i);
+            const uint4 d1 = two ? __ldg(dy + base + i + stride) : make_uint4(0, 0, 0, 0);
+            const uint4 p1 = two ? __ldg(pre + base + i + stride) : make_uint4(0, 0, 0, 0);
+            float dv[8], pv[8];
+            unpack8<BF16>(d0, dv);
+            unpack8<BF16>(p0, pv);
+            adj(dv, pv);
+            g[base + i] = pack8<BF16>(dv);
+            if (two) {
+                unpack8<BF16>(d1, dv);
+                unpack8<BF16>(p1, pv);
+                adj(dv, pv);
+                g[base + i + stride] = pack8<BF16>(dv);
+            }
+        }
+    }
+    __shared__ float red[8][16];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        s[j] = warp_sum(s[j]);
+        q[j] = warp_sum(q[j]);
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { red[w][j] = s[j]; red[w][8 + j] = q[j]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 16) {
+        float t = 0.f;
+        for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
+        ws[((int64_t)ch * gridDim.x + blockIdx.x) * 16 + threadIdx.x] = t;
+    }
+}
+
+extern "C" int cwfa_c8_prelu(const void* x, const float* slope, void* y, int N, int Cp, int64_t P, int is_bf16, void* stream) {
+    if (!x || !slope || !y || N <= 0 || Cp <= 0 || (Cp % 8) || P <= 0) { set_error("c8_prelu: bad arguments"); return CWFA_EINVAL; }
+    const int64_t n16 = (int64_t)N * (Cp / 8) * P;
+    int blocks = (int)((n16 + 255) / 256);
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    if (is_bf16) c8_prelu_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>((const uint4*)x, slope, (uint4*)y, n16);
+    else c8_prelu_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>((const uint4*)x, slope, (uint4*)y, n16);
+    return check_launch("c8_prelu");
+}
+
+static int c8_act_bwd(const void* dy, const void* v, const float* slope, void* g, float* stats, float* workspace, int N, int Cp,
+                      int64_t P, int is_bf16, int elu, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!dy || !v || (!elu && !slope) || !g || !stats || !workspace || N <= 0 || Cp <= 0 || (Cp % 8) || P <= 0 || Cp / 8 > 65535) {
+        set_error("c8 activation adjoint: bad arguments");
+        return CWFA_EINVAL;
+    }
+    dim3 grid(kC8StatBlocks, Cp / 8);
+    const uint4 *d4 = (const uint4*)dy, *v4 = (const uint4*)v;
+    if (elu) {
+        if (is_bf16) c8_prelu_bwd_kernel<true, 1><<<grid, 256, 0, st>>>(d4, v4, slope, (uint4*)g, workspace, N, Cp / 8, P);
+        else c8_prelu_bwd_kernel<false, 1><<<grid, 256, 0, st>>>(d4, v4, slope, (uint4*)g, workspace, N, Cp / 8, P);
+    } else {
+        if (is_bf16) c8_prelu_bwd_kernel<true, 0><<<grid, 256, 0, st>>>(d4, v4, slope, (uint4*)g, workspace, N, Cp / 8, P);
+        else c8_prelu_bwd_kernel<false, 0><<<grid, 256, 0, st>>>(d4, v4, slope, (uint4*)g, workspace, N, Cp / 8, P);
+    }
+    int rc = check_launch("c8_act_bwd");
+    if (rc) return rc;
+    c8_stats_finalize_kernel<<<ceil_div(Cp, 128), 128, 0, st>>>(workspace, stats, Cp, kC8StatBlocks);
+    return check_launch("c8_act_bwd_finalize");
+}
+extern "C" int cwfa_c8_prelu_bwd(const void* dy, const void* pre, const float* slope, void* g, float* stats, float* workspace,
+                                 int N, int Cp, int64_t P, int is_bf16, void* stream) {
+    return c8_act_bwd(dy, pre, slope, g, stats, workspace, N, Cp, P, is_bf16, 0, stream);
+}
+extern "C" int cwfa_c8_elu_bwd(const void* dy, const void* y, void* g, float* stats, float* workspace, int N, int Cp, int64_t P,
+                               int is_bf16, void* stream) {
+    return c8_act_bwd(dy, y, nullptr, g, stats, workspace, N, Cp, P, is_bf16, 1, stream);
+}
+
 extern "C" int cwfa_c8_stats_workspace_floats(int Cp) { return (Cp / 8) * kC8StatBlocks * 16; }
 
 extern "C" int cwfa_c8_channel_stats(const void* x, float* stats, float* workspace, int N, int Cp, int64_t P,

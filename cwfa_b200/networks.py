@@ -94,7 +94,17 @@ class wavelet_flow_subnetwork2D(nn.Module):
         kind = packed.fast_kind(inp)
         if kind is not None:                     # inference with set_inference_precision('bf16'|'fp16'): tcgen05 kernels
             return self.packed_executor(kind).from_nchw(inp)
-        return _conv(self.block72[1], self.trunk(_conv(self.block12, inp)))
+        return self._train_path(inp, self.block12, self.block72[1])
+
+    def _train_path(self, inp, conv_in, conv_out):
+        """conv_out(trunk(conv_in(inp))) with gradients: one C8-native autograd node under a half training precision
+        (``autograd._SubnetTC``), else one node per convolution."""
+        from . import autograd as ag
+        blocks = [(getattr(self, nm)[0], getattr(self, nm)[2]) for nm in ("block2", "block4", "block6")]
+        convs = [conv_in, conv_out] + [c for b in blocks for c in b]
+        if ag.subnet_tc_supported(inp, convs):
+            return ag.subnet_tc(inp, conv_in, blocks, conv_out)
+        return _conv(conv_out, self.trunk(_conv(conv_in, inp)))
 
 
 class wavelet_flow_subnetwork2D_first(wavelet_flow_subnetwork2D):
@@ -114,7 +124,7 @@ class wavelet_flow_subnetwork2D_first(wavelet_flow_subnetwork2D):
         kind = packed.fast_kind(inp)
         if kind is not None:
             return self.packed_executor(kind).from_nchw(cond.contiguous()), low, -1.0 / math.sqrt(2)
-        b7 = _conv(self.block7[1], self.trunk(_conv(self.block1, cond.contiguous())))
+        b7 = self._train_path(cond.contiguous(), self.block1, self.block7[1])
         return b7, low, -1.0 / math.sqrt(2)
 
     def forward(self, inp):

@@ -74,6 +74,48 @@ def dy_prep(dy: torch.Tensor, y: Optional[torch.Tensor], kind: str, *, want_f32:
     return g8, g32, db
 
 
+def prelu_c8(x: C8, slope: torch.Tensor) -> C8:
+    """PReLU with a scalar slope (read on the device) on a C8 tensor."""
+    y = C8(torch.empty_like(x.data), x.C, x.kind)
+    _lib.call("cwfa_c8_prelu", x.data.data_ptr(), _ck(slope.detach(), "slope").data_ptr(), y.data.data_ptr(), x.N, x.Cp, x.H * x.W,
+              x.is_bf16, _stream())
+    return y
+
+
+def prelu_bwd_c8(dy: C8, pre: C8, slope: torch.Tensor):
+    """Adjoint of ``prelu_c8``: ``g = dy * PReLU'(pre)`` (C8) and ``stats`` (2 * Cp,): per-channel ``sum g`` then per-channel
+    ``sum dy * min(pre, 0)`` (summed over channels = the slope gradient)."""
+    if dy.data.shape != pre.data.shape or dy.kind != pre.kind:
+        raise ValueError("prelu_bwd_c8: layout mismatch")
+    g = C8(torch.empty_like(dy.data), dy.C, dy.kind)
+    stats = torch.empty(2 * dy.Cp, device=dy.data.device, dtype=torch.float32)
+    ws = torch.empty(_lib.load().cwfa_c8_stats_workspace_floats(dy.Cp), device=dy.data.device, dtype=torch.float32)
+    _lib.call("cwfa_c8_prelu_bwd", dy.data.data_ptr(), pre.data.data_ptr(), _ck(slope.detach(), "slope").data_ptr(), g.data.data_ptr(),
+              stats.data_ptr(), ws.data_ptr(), dy.N, dy.Cp, dy.H * dy.W, dy.is_bf16, _stream())
+    return g, stats
+
+
+def elu_bwd_c8(dy: C8, y: C8):
+    """ELU adjoint from the activation's output: ``g = dy * (y > 0 ? 1 : y + 1)`` (C8) and ``stats`` whose first Cp entries are
+    the per-channel sums of g."""
+    if dy.data.shape != y.data.shape or dy.kind != y.kind:
+        raise ValueError("elu_bwd_c8: layout mismatch")
+    g = C8(torch.empty_like(dy.data), dy.C, dy.kind)
+    stats = torch.empty(2 * dy.Cp, device=dy.data.device, dtype=torch.float32)
+    ws = torch.empty(_lib.load().cwfa_c8_stats_workspace_floats(dy.Cp), device=dy.data.device, dtype=torch.float32)
+    _lib.call("cwfa_c8_elu_bwd", dy.data.data_ptr(), y.data.data_ptr(), g.data.data_ptr(), stats.data_ptr(), ws.data_ptr(),
+              dy.N, dy.Cp, dy.H * dy.W, dy.is_bf16, _stream())
+    return g, stats
+
+
+def channel_sums_c8(x: C8) -> torch.Tensor:
+    """Per-channel sums over (N, H, W) of a C8 tensor -> (Cp,) fp32 (deterministic two-stage reduction)."""
+    stats = torch.empty(2 * x.Cp, device=x.data.device, dtype=torch.float32)
+    ws = torch.empty(_lib.load().cwfa_c8_stats_workspace_floats(x.Cp), device=x.data.device, dtype=torch.float32)
+    _lib.call("cwfa_c8_channel_stats", x.data.data_ptr(), stats.data_ptr(), ws.data_ptr(), x.N, x.Cp, x.H * x.W, x.is_bf16, _stream())
+    return stats[:x.Cp]
+
+
 def pick_bn(cout_p: int) -> int:
     """Largest legal N tile (multiple of 16, <= 256) that divides the padded output channels."""
     for bn in (256, 128, 96, 64, 48, 32, 16):

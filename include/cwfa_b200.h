@@ -189,6 +189,18 @@ int cwfa_resblock_tc_batched(const void* x_c8, void* y_c8, int n_sets, const voi
  * (workspace >= cwfa_c8_stats_workspace_floats(Cp) floats; feed to cwfa_bn_finalize_f32), and BatchNorm
  * apply y = x*scale+shift, optionally also writing the 2x2 max-pooled tensor (unet.py:79).
  * scale / shift must be 16-byte aligned; N * Cp/8 <= 65535. */
+/* PReLU on a C8 tensor (y = x >= 0 ? x : slope[0] * x) and its adjoint g = dy * PReLU'(pre) with the per-channel sums
+ * stats[c] = sum g (bias gradient of the producing convolution), stats[Cp + c] = sum dy * min(pre, 0) (its sum over c is the
+ * slope gradient); workspace: cwfa_c8_stats_workspace_floats(Cp).  Training path of the conditioning net's depth stencil
+ * (networks.py:221-225): the hidden tensor stays in the C8 half layout between the two tensor-core convolutions. */
+int cwfa_c8_prelu(const void* x, const float* slope, void* y, int N, int Cp, int64_t P, int is_bf16, void* stream);
+int cwfa_c8_prelu_bwd(const void* dy, const void* pre, const float* slope, void* g, float* stats, float* workspace, int N,
+                      int Cp, int64_t P, int is_bf16, void* stream);
+/* ELU adjoint on C8 tensors from the activation's OUTPUT y: g = dy * (y > 0 ? 1 : y + 1); stats[c] = sum g (the bias gradient of
+ * the convolution whose epilogue applied the ELU), stats[Cp + c] = 0.  Training path of the coupling sub-networks
+ * (networks.py:624-638) with activations and cotangents kept in the C8 layout. */
+int cwfa_c8_elu_bwd(const void* dy, const void* y, void* g, float* stats, float* workspace, int N, int Cp, int64_t P, int is_bf16,
+                    void* stream);
 int cwfa_c8_stats_workspace_floats(int Cp);
 int cwfa_c8_channel_stats(const void* x, float* stats, float* workspace, int N, int Cp, int64_t P,
                           int is_bf16, void* stream);

@@ -723,3 +723,77 @@ def test_dy_prep_fused_cotangent_pass(kind, N, C, H, W, elu):
     assert float((db.double() - want).abs().max()) <= 1e-5 * max(1.0, float(want.abs().max()))
     g8b, none32, noneb = tc.dy_prep(dy, y, kind)
     assert none32 is None and noneb is None and torch.equal(g8b.data, g8.data)
+
+
+@pytest.mark.parametrize("kind,tol", [("bf16", 4e-2), ("fp16", 6e-3)])
+@pytest.mark.parametrize("first", [False, True])
+def test_subnet_c8_native_node_matches_per_conv_nodes_and_fp32(kind, tol, first):
+    """``autograd._SubnetTC`` (activations and cotangents in C8 through the whole sub-network) against the chain of one node per
+    convolution at the same precision and against the fp32 path: output, input gradient and all 16 parameter gradients."""
+    from cwfa_b200 import autograd as ag, networks
+    torch.manual_seed(7)
+    net = (networks.wavelet_flow_subnetwork2D_first if first else networks.wavelet_flow_subnetwork2D)(24, 24).to(DEV)
+    gen = torch.Generator().manual_seed(11)
+    with torch.no_grad():
+        for p in net.parameters():
+            p.copy_((torch.randn(p.shape, generator=gen) * (0.5 / max(1.0, float(p[0].numel()) ** 0.5) if p.dim() > 1 else 0.1)).to(DEV))
+    x0 = torch.randn(2, 24, 20, 28, generator=gen).to(DEV)
+    r = torch.randn(2, 12 if first else 24, 20, 28, generator=gen).to(DEV)
+
+    def run(prec, node):
+        prev, old = ag.set_training_precision(prec), ag._SUBNET_NODE
+        ag._SUBNET_NODE = node
+        try:
+            net.zero_grad(set_to_none=True)
+            x = x0.clone().requires_grad_(True)
+            y = net.forward_split(x)[0] if first else net(x)
+            (y * r).sum().backward()
+            names = [n for n, p in net.named_parameters() if p.grad is not None]
+            return y.detach(), x.grad.clone(), {n: dict(net.named_parameters())[n].grad.clone() for n in names}
+        finally:
+            ag.set_training_precision(prev)
+            ag._SUBNET_NODE = old
+
+    y32, dx32, g32 = run("fp32", False)
+    yn, dxn, gn = run(kind, True)
+    yc, dxc, gc = run(kind, False)
+    assert set(gn) == set(gc) == set(g32) and len(gn) == 16
+    assert rel_l2(yn, y32) < tol and rel_l2(dxn, dx32) < tol
+    worst = 0.0
+    for n in gn:
+        e_node, e_chain = rel_l2(gn[n], g32[n]), rel_l2(gc[n], g32[n])
+        worst = max(worst, e_node)
+        assert e_node < max(tol, 2.0 * e_chain), (n, e_node, e_chain)
+    print(f"subnet node {kind} first={first}: out {rel_l2(yn, y32):.2e}, dx {rel_l2(dxn, dx32):.2e}, worst parameter gradient {worst:.2e} "
+          f"(per-conv chain: dx {rel_l2(dxc, dx32):.2e})")
+
+
+@pytest.mark.parametrize("kind,tol", [("bf16", 3e-2), ("fp16", 4e-3)])
+def test_stencil_c8_native_node_matches_generic_chain_and_fp32(kind, tol):
+    """``autograd._StencilBandedTC`` (hidden tensor only in C8) against the generic conv -> PReLU -> conv chain and the fp32 stencil."""
+    from cwfa_b200 import autograd as ag
+    gen = torch.Generator().manual_seed(3)
+    mk = lambda *s, sc=1.0: (torch.randn(*s, generator=gen) * sc).to(DEV)
+    D, Cm = 12, 32
+    x0, r = mk(1, D, 18, 22), mk(1, D, 18, 22)
+    P = [mk(Cm, 1, 3, 3, 3, sc=0.3), mk(Cm, sc=0.2), torch.tensor([0.25], device=DEV), mk(1, Cm, 3, 3, 3, sc=0.1), mk(1, sc=0.2)]
+
+    def run(prec, node):
+        prev, old = ag.set_training_precision(prec), ag._STENCIL_NODE
+        ag._STENCIL_NODE = node
+        try:
+            x = x0.clone().requires_grad_(True)
+            ps = [p.clone().requires_grad_(True) for p in P]
+            y = ag.depth_stencil3d(x, ps[0], ps[1], ps[2], ps[3], ps[4])
+            (y * r).sum().backward()
+            return [y.detach(), x.grad] + [p.grad for p in ps]
+        finally:
+            ag.set_training_precision(prev)
+            ag._STENCIL_NODE = old
+
+    ref, node, chain = run("fp32", False), run(kind, True), run(kind, False)
+    names = ["out", "dx", "dw1", "db1", "dslope", "dw2", "db2"]
+    for nm, a, b, c in zip(names, node, chain, ref):
+        e_node, e_chain = rel_l2(a, c), rel_l2(b, c)
+        print(f"stencil node {kind} {nm}: {e_node:.2e} (generic chain {e_chain:.2e})")
+        assert e_node < max(tol, 2.0 * e_chain), nm
