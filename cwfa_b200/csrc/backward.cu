@@ -287,6 +287,28 @@ extern "C" int cwfa_prelu_bwd_f32(const float* dy, const float* v, const float* 
 //   s = kk atan(a_s) -> d a_s = ds kk / (1 + a_s^2)  (raw: d a_s = ds);  t = t_scale a_t
 // ------------------------------------------------------------------------------------------
 template <bool INV>
+__device__ __forceinline__ void affine_bwd_one(float as, float tv, float g, float xv, float gj, float kk, float t_scale, int raw,
+                                               float k_in, float& gx, float& gt, float& gs) {
+    const float th = raw == 2 ? tanhf(k_in * as) : 0.f;
+    const float s = raw == 1 ? as : (raw == 2 ? kk * th : kk * atanf(as));
+    float gsv;
+    if (INV) {
+        const float e = expf(-s);
+        const float y = (xv - t_scale * tv) * e;
+        gx = g * e;
+        gt = -gx;
+        gsv = -g * y - gj;
+    } else {
+        const float e = expf(s);
+        gx = g * e;
+        gt = g;
+        gsv = gx * xv + gj;
+    }
+    gt *= t_scale;
+    gs = raw == 1 ? gsv : (raw == 2 ? gsv * kk * k_in * (1.f - th * th) : gsv * kk / fmaf(as, as, 1.f));
+}
+// VEC = 4: 16-byte accesses on all seven streams (needs n, the leading dimensions and the pointers 16-byte aligned)
+template <bool INV, int VEC>
 __global__ void __launch_bounds__(256) affine_bwd_kernel(const float* __restrict__ x, const float* __restrict__ a_s,
                                                          const float* __restrict__ a_t, const float* __restrict__ dy,
                                                          const float* __restrict__ g_logdet, float* __restrict__ dx,
@@ -299,28 +321,27 @@ __global__ void __launch_bounds__(256) affine_bwd_kernel(const float* __restrict
     const float* ts = a_t + (int64_t)b * ld_t;
     const float* gs = dy + (int64_t)b * n;
     const float gj = g_logdet ? __ldg(g_logdet + b) : 0.f;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const float as = ss[i];
-        const float th = raw == 2 ? tanhf(k_in * as) : 0.f;
-        const float s = raw == 1 ? as : (raw == 2 ? kk * th : kk * atanf(as));
-        const float g = gs[i];
-        const float xv = xs ? xs[i] : 0.f;
-        float gx, gt, gsv;
-        if (INV) {
-            const float e = expf(-s);
-            const float y = (xv - t_scale * ts[i]) * e;
-            gx = g * e;
-            gt = -gx;
-            gsv = -g * y - gj;
+    const int64_t nv = n / VEC;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nv; i += (int64_t)gridDim.x * blockDim.x) {
+        if constexpr (VEC == 4) {
+            const float4 as = __ldg(reinterpret_cast<const float4*>(ss) + i), tv = __ldg(reinterpret_cast<const float4*>(ts) + i);
+            const float4 g = __ldg(reinterpret_cast<const float4*>(gs) + i);
+            const float4 xv = xs ? __ldg(reinterpret_cast<const float4*>(xs) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 ox, ot, os;
+            affine_bwd_one<INV>(as.x, tv.x, g.x, xv.x, gj, kk, t_scale, raw, k_in, ox.x, ot.x, os.x);
+            affine_bwd_one<INV>(as.y, tv.y, g.y, xv.y, gj, kk, t_scale, raw, k_in, ox.y, ot.y, os.y);
+            affine_bwd_one<INV>(as.z, tv.z, g.z, xv.z, gj, kk, t_scale, raw, k_in, ox.z, ot.z, os.z);
+            affine_bwd_one<INV>(as.w, tv.w, g.w, xv.w, gj, kk, t_scale, raw, k_in, ox.w, ot.w, os.w);
+            if (dx) reinterpret_cast<float4*>(dx + (int64_t)b * n)[i] = ox;
+            if (da_t) reinterpret_cast<float4*>(da_t + (int64_t)b * ld_dt)[i] = ot;
+            if (da_s) reinterpret_cast<float4*>(da_s + (int64_t)b * ld_ds)[i] = os;
         } else {
-            const float e = expf(s);
-            gx = g * e;
-            gt = g;
-            gsv = gx * xv + gj;
+            float ox, ot, os;
+            affine_bwd_one<INV>(ss[i], ts[i], gs[i], xs ? xs[i] : 0.f, gj, kk, t_scale, raw, k_in, ox, ot, os);
+            if (dx) dx[(int64_t)b * n + i] = ox;
+            if (da_t) da_t[(int64_t)b * ld_dt + i] = ot;
+            if (da_s) da_s[(int64_t)b * ld_ds + i] = os;
         }
-        if (dx) dx[(int64_t)b * n + i] = gx;
-        if (da_t) da_t[(int64_t)b * ld_dt + i] = gt * t_scale;
-        if (da_s) da_s[(int64_t)b * ld_ds + i] = raw == 1 ? gsv : (raw == 2 ? gsv * kk * k_in * (1.f - th * th) : gsv * kk / fmaf(as, as, 1.f));
     }
 }
 extern "C" int cwfa_affine_bwd(const float* x, const float* a_s, const float* a_t, const float* dy, const float* g_logdet,
@@ -331,10 +352,20 @@ extern "C" int cwfa_affine_bwd(const float* x, const float* a_s, const float* a_
     if (B <= 0 || ch <= 0 || P <= 0 || !a_s || !a_t || !dy) { set_error("affine_bwd: bad args"); return CWFA_EINVAL; }
     if (!x && !inverse) { set_error("affine_bwd: x may be NULL only in inverse mode"); return CWFA_EINVAL; }
     const int64_t n = (int64_t)ch * P;
-    dim3 grid(ew_blocks(n) < kNumSMs * 4 ? ew_blocks(n) : kNumSMs * 4, B);
     const float kk = raw == 2 ? clamp : clamp * k_atan;
-    if (inverse) affine_bwd_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, a_s, a_t, dy, g_logdet, dx, da_s, da_t, n, ld_s, ld_t, ld_ds, ld_dt, kk, t_scale, raw, k_atan);
-    else affine_bwd_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(x, a_s, a_t, dy, g_logdet, dx, da_s, da_t, n, ld_s, ld_t, ld_ds, ld_dt, kk, t_scale, raw, k_atan);
+    const bool vec = (n % 4 == 0) && (ld_s % 4 == 0) && (ld_t % 4 == 0) && (ld_ds % 4 == 0) && (ld_dt % 4 == 0) && aligned16(a_s) &&
+                     aligned16(a_t) && aligned16(dy) && (!x || aligned16(x)) && (!dx || aligned16(dx)) && (!da_s || aligned16(da_s)) &&
+                     (!da_t || aligned16(da_t));
+    const int64_t items = vec ? n / 4 : n;
+    dim3 grid(ew_blocks(items) < kNumSMs * 8 ? ew_blocks(items) : kNumSMs * 8, B);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (vec) {
+        if (inverse) affine_bwd_kernel<true, 4><<<grid, 256, 0, st>>>(x, a_s, a_t, dy, g_logdet, dx, da_s, da_t, n, ld_s, ld_t, ld_ds, ld_dt, kk, t_scale, raw, k_atan);
+        else affine_bwd_kernel<false, 4><<<grid, 256, 0, st>>>(x, a_s, a_t, dy, g_logdet, dx, da_s, da_t, n, ld_s, ld_t, ld_ds, ld_dt, kk, t_scale, raw, k_atan);
+    } else {
+        if (inverse) affine_bwd_kernel<true, 1><<<grid, 256, 0, st>>>(x, a_s, a_t, dy, g_logdet, dx, da_s, da_t, n, ld_s, ld_t, ld_ds, ld_dt, kk, t_scale, raw, k_atan);
+        else affine_bwd_kernel<false, 1><<<grid, 256, 0, st>>>(x, a_s, a_t, dy, g_logdet, dx, da_s, da_t, n, ld_s, ld_t, ld_ds, ld_dt, kk, t_scale, raw, k_atan);
+    }
     return check_launch("affine_bwd");
 }
 
