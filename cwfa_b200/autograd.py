@@ -751,11 +751,13 @@ class _StencilBandedTC(_F):
         dW2 = conv2d_wgrad_tc(tc.C8(hid8d, H, kind), dy8, H, D, 3)                      # (D, D*Cm, 3, 3)
         dx = tc.conv_tc(g8, tc.PackedConv(_dgrad_weights(W1), None, kind), out_nchw=True)
         dW1 = conv2d_wgrad_tc(tc.C8(x8d, D, kind), g8, D, H, 3)                         # (D*Cm, D, 3, 3)
-        dg1 = (dW1.reshape(D, Cm, D, 3, 3).permute(1, 3, 4, 0, 2) * mask).reshape(Cm, 3, 3, D * D)
-        dg2 = (dW2.reshape(D, D, Cm, 3, 3).permute(2, 3, 4, 0, 1) * mask).reshape(Cm, 3, 3, D * D)
-        dw1 = torch.zeros((Cm, 3, 3, 3), device=dy.device, dtype=torch.float32).index_add_(3, kd, dg1).unsqueeze(1)
-        dw2 = torch.zeros((Cm, 3, 3, 3), device=dy.device, dtype=torch.float32).index_add_(3, kd, dg2).unsqueeze(0)
-        return dx, dw1, db1, dslope, dw2, dbD.sum().reshape(1), None
+        # adjoint of the banded gather: depth tap kd collects the (kd - 1)-th diagonal of the (d, d') block -- plain sums, so the
+        # result is bit-reproducible (index_add_ accumulates with atomics in arbitrary order)
+        dg1 = dW1.reshape(D, Cm, D, 3, 3).permute(1, 3, 4, 0, 2)                        # [c, h, w, d, d']
+        dg2 = dW2.reshape(D, D, Cm, 3, 3).permute(2, 3, 4, 0, 1)
+        dw1 = torch.stack([dg1.diagonal(offset=k - 1, dim1=3, dim2=4).sum(-1) for k in range(3)], dim=-1).unsqueeze(1)
+        dw2 = torch.stack([dg2.diagonal(offset=k - 1, dim1=3, dim2=4).sum(-1) for k in range(3)], dim=-1).unsqueeze(0)
+        return dx, dw1.contiguous(), db1, dslope, dw2.contiguous(), dbD.sum().reshape(1), None
 
 
 # CWFA_STENCIL_NODE=0 keeps the generic conv2d -> PReLU -> conv2d node chain (A/B measurements)

@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16", "fp16"])
     ap.add_argument("--json", default=None)
+    ap.add_argument("--graph", action="store_true", help="capture the whole step as a CUDA graph (trainer graph=True)")
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -42,9 +43,9 @@ def main():
     model = cwfa_b200.CWFAModel(n_depths=D, volume_side_size=S, INN_max_down_steps=steps_total, seed=0).to(dev)
     if a.lrnn:
         from cwfa_b200.training import LRNNTrainer
-        lt = LRNNTrainer(model, precision=a.precision)
+        lt = LRNNTrainer(model, precision=a.precision, graph=a.graph)
     else:
-        tr = FlowLevelTrainer(model, n, precision=a.precision)
+        tr = FlowLevelTrainer(model, n, precision=a.precision, graph=a.graph)
     C = D // 2 ** n
     g = torch.Generator(device="cpu").manual_seed(1000 + rank)             # every rank its own frame
     mk = lambda *s, sc=1.0: (torch.randn(*s, generator=g) * sc).to(dev)
@@ -80,7 +81,7 @@ def main():
         ms = float(t)
     losses.append(float(parts["loss"]))
     if rank == 0:
-        out = {"metric": "flow-level training steps/s (fwd NLL + inverse MSE + backward + Lion)", "precision": a.precision, "level": "lrnn" if a.lrnn else n,
+        out = {"metric": "flow-level training steps/s (fwd NLL + inverse MSE + backward + Lion)", "precision": a.precision, "graph": bool(a.graph), "level": "lrnn" if a.lrnn else n,
                "value": world * a.batch * 1000.0 / ms, "unit": "frames/s", "ms_per_step": ms, "n_gpus": world, "batch_per_gpu": a.batch,
                "side": S, "depths": D, "launches_per_step": (_lib.launch_count - l0) / a.steps, "collectives_per_step": tr.collectives,
                "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30, "losses": losses}

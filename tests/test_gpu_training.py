@@ -797,3 +797,41 @@ def test_stencil_c8_native_node_matches_generic_chain_and_fp32(kind, tol):
         e_node, e_chain = rel_l2(a, c), rel_l2(b, c)
         print(f"stencil node {kind} {nm}: {e_node:.2e} (generic chain {e_chain:.2e})")
         assert e_node < max(tol, 2.0 * e_chain), nm
+
+
+@pytest.mark.parametrize("which", ["level", "lrnn"])
+def test_graph_captured_step_equals_eager_steps(golden_tiny, golden_train, which):
+    """``graph=True``: the captured whole-step graph (forward + backward + Lion) leaves exactly the parameters, optimiser state and
+    BatchNorm buffers that the same number of eager steps leaves -- including the FIRST call (warm-up steps are undone)."""
+    import copy
+    import cwfa_b200
+    from cwfa_b200.training import FlowLevelTrainer, LRNNTrainer
+    cfg = golden_tiny["config"]
+    D, S, MAX = cfg["D"], cfg["S"], cfg["MAX"]
+    gen = torch.Generator().manual_seed(21)
+    mk = lambda *s, sc=1.0: (torch.randn(*s, generator=gen) * sc).to(DEV)
+    views = mk(2, 29, S, S)
+    if which == "level":
+        args = (mk(2, D, S, S), views, mk(2, D // 2, S, S, sc=0.1), mk(2, D // 2, S, S))
+    else:
+        args = (mk(2, D // 2 ** (MAX - 1), S, S), views)
+    results = []
+    from cwfa_b200 import networks
+    slope0 = networks._SHARED_PRELU.weight.data.clone()    # the reference's ONE PReLU shared by every ResidualBlock / LRNN (a default
+    for graph in (False, True):                             # argument, networks.py:209): training it in run 1 must not leak into run 2
+        with torch.no_grad():
+            networks._SHARED_PRELU.weight.data.copy_(slope0.to(networks._SHARED_PRELU.weight.device))
+        model = cwfa_b200.CWFAModel(n_depths=D, volume_side_size=S, INN_max_down_steps=MAX, seed=0).to(DEV)
+        tr = (FlowLevelTrainer(model, 0, lr=1e-3, lr_cond=1e-3, precision="bf16", graph=graph) if which == "level"
+              else LRNNTrainer(model, lr=1e-3, precision="bf16", graph=graph))
+        losses = [float(tr.step(*args)["loss"]) for _ in range(3)]
+        sd = copy.deepcopy({k: v.clone() for k, v in model.state_dict().items()})
+        moms = [g["exp_avg"].clone() for o in tr._optimizers() for g in o.param_groups]
+        results.append((losses, sd, moms))
+        tr.release()
+    (l0, sd0, m0), (l1, sd1, m1) = results
+    assert l0 == l1
+    assert all(torch.equal(sd0[k], sd1[k]) for k in sd0)
+    assert all(torch.equal(a, b) for a, b in zip(m0, m1))
+    with torch.no_grad():
+        networks._SHARED_PRELU.weight.data.copy_(slope0.to(networks._SHARED_PRELU.weight.device))
