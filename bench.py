@@ -627,6 +627,11 @@ def main():
             train.update(level0_ms_per_step=ms0, level0_frames_per_s=world * 1000.0 / ms0, level0_collectives_per_step=tr.collectives,
                          level0_allreduce_bytes=int(sum(g_.numel() for o in (tr.optimizer, tr.optimizer_cond) for g_ in o.flat_grads()) * 4))
             tr.release()
+            if world == 1:            # the same step captured as ONE CUDA graph (trainer graph=True; eager under data parallelism)
+                trg = FlowLevelTrainer(model, 0, precision=args.kind, graph=True)
+                train.update(level0_graph_ms_per_step=timed(lambda: trg.step(gt, vw, mv0, vin), 2, 5))
+                trg.release()
+                del trg
             del tr, gt, mv0, vin
             nd = C // 2 ** (args.down_steps - 1)
             gt_l = mk(nd)
@@ -635,6 +640,11 @@ def main():
             train.update(lrnn_ms_per_step=ms1, lrnn_frames_per_s=world * 1000.0 / ms1, lrnn_collectives_per_step=lt.collectives,
                          lrnn_allreduce_bytes=int(sum(g_.numel() for g_ in lt.optimizer.flat_grads()) * 4))
             lt.release()
+            if world == 1:
+                ltg = LRNNTrainer(model, precision=args.kind, graph=True)
+                train.update(lrnn_graph_ms_per_step=timed(lambda: ltg.step(gt_l, vw), 2, 3))
+                ltg.release()
+                del ltg
             del lt, gt_l, vw
             torch.cuda.empty_cache()
         except Exception as ex:       # a secondary figure must never take the headline line down
@@ -684,7 +694,8 @@ def main():
                   "forward_nll_note": "BASELINE.json configs[2]: 4-level forward pyramid + per-level log-det / sum z^2 / NLL, batch 8, 1 GPU; eager and as one CUDA-graph replay (levels as parallel branches)",
                   "train": train,
                   "train_note": "BASELINE.json configs[3]: one frame per rank; flow level 0 (96 -> 48+48 ch): forward NLL + inverse MSE + backward + gradient all-reduce (NCCL) + Lion; "
-                                "LRNN step likewise; tensor-core convs (fwd, dgrad, wgrad); frames/s = ranks / max-over-ranks step time",
+                                "LRNN step likewise; tensor-core convs (fwd, dgrad, wgrad); frames/s = ranks / max-over-ranks step time; *_graph_ms_per_step (1 GPU): the same "
+                                "step captured as ONE CUDA graph (trainer graph=True, bit-identical to the eager steps)",
                   "stream": stream_rows, "stream_error": stream_err,
                   "stream_note": "BASELINE.json configs[4]: frames with seed = frame id sharded contiguously over the ranks (128 per rank unless --stream), 2 graph instances in flight, "
                                  "batch = frames per graph replay; latency = input copy issued -> output written (rank 0, CUDA events)"},

@@ -408,13 +408,16 @@ class _GraphedStep:
     step; the replay takes 14.3 ms).  The capture is preceded by two eager warm-up steps whose effect on the parameters, the
     optimiser state and the module buffers is undone, so the first call still performs exactly ONE step.  Re-captured when an
     input shape or a hyper-parameter (lr, betas, weight decay) changes.  Not used with a ``GradScaler`` (its skip decision is made
-    on the host).  The returned tensors are static: they are overwritten by the next step."""
+    on the host) nor under data parallelism (world size > 1 keeps the eager step with the bucketed all-reduce under backward).  The returned tensors are static: they are overwritten by the next step."""
 
     def _graph_init(self, graph: bool):
         self._graph_on, self._cg, self._cg_key, self._static, self._parts = bool(graph), None, None, None, None
 
     def _graph_usable(self) -> bool:
-        return self._graph_on and self.scaler is None
+        if not self._graph_on or self.scaler is not None:
+            return False
+        import torch.distributed as dist        # data parallel: eager step with the bucketed all-reduce under backward (capturing the
+        return not (dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1)   # NCCL calls hung on 2 GPUs)
 
     def _hyper_key(self):
         return tuple((g["lr"], tuple(g["betas"]), g["weight_decay"]) for o in self._optimizers() for g in o.param_groups)

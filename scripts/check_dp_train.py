@@ -19,6 +19,7 @@ import cwfa_b200                                                        # noqa: 
 from cwfa_b200.training import FlowLevelTrainer, flow_level_loss       # noqa: E402
 
 K, D, S = 3, 16, 64
+GRAPH = "--graph" in sys.argv          # graph=True on the trainers: falls back to the eager step under data parallelism
 
 
 def frame(f, dev):
@@ -52,7 +53,7 @@ def main():
         tr.release()
         model.load_state_dict(init)
     dist.barrier()
-    tr = FlowLevelTrainer(model, 0, lr=1e-4, lr_cond=1e-4)
+    tr = FlowLevelTrainer(model, 0, lr=1e-4, lr_cond=1e-4, graph=GRAPH)
     inputs = frame(rank, dev)
     losses = [float(tr.step(*inputs)["loss"]) for _ in range(K)]
     mine = params_of(model)
@@ -60,7 +61,7 @@ def main():
     dist.all_gather(gathered, mine.to(dev))
     if rank == 0:
         same_on_all_ranks = all(torch.equal(gathered[0], g) for g in gathered)
-        out = {"world": world, "steps": K, "collectives_per_step": tr.collectives, "replicas_identical": bool(same_on_all_ranks),
+        out = {"world": world, "steps": K, "graph": GRAPH, "collectives_per_step": tr.collectives, "replicas_identical": bool(same_on_all_ranks),
                "max_abs_param_diff_vs_single_process": float((mine - ref).abs().max()),
                "params_changed_by_training": float((ref - params_of_init(init, model)).abs().max()), "losses_rank0": losses}
         print(json.dumps(out))
