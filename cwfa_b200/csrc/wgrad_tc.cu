@@ -165,8 +165,16 @@ __global__ void __launch_bounds__(256) wgrad_tc_finalize_kernel(const float* __r
     const int64_t n = (int64_t)Cout * Cin * KK;
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
-    double s = 0.0;
-    for (int k = 0; k < nparts; ++k) s += (double)part[(int64_t)k * n + i];
+    // four interleaved accumulators (fixed association: still bit-reproducible) keep four partial loads in flight instead of one
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int k = 0;
+    for (; k + 3 < nparts; k += 4) {
+        const float a = __ldg(part + (int64_t)k * n + i), b = __ldg(part + (int64_t)(k + 1) * n + i);
+        const float c = __ldg(part + (int64_t)(k + 2) * n + i), d = __ldg(part + (int64_t)(k + 3) * n + i);
+        s0 += (double)a; s1 += (double)b; s2 += (double)c; s3 += (double)d;
+    }
+    for (; k < nparts; ++k) s0 += (double)__ldg(part + (int64_t)k * n + i);
+    const double s = (s0 + s1) + (s2 + s3);
     const int co = (int)(i % Cout), ci = (int)((i / Cout) % Cin), t = (int)(i / ((int64_t)Cout * Cin));
     out[((int64_t)co * Cin + ci) * KK + t] = (float)s;
 }
