@@ -12,8 +12,9 @@
 //      Epilogue: PReLU, zero outside the volume, pack, store h[r][32] over the A1 buffer (K-major chunks of 8 channels).
 //   3. GEMM2, same trick: Q[r][kh, kw] = sum_kd sum_c w2[c, kh, kw, kd] h[c][r + kd - 1]  (6 MMAs of N = 16 per 128 rows;
 //      the spatial taps are the N dimension).
-//   4. Q (fp16) goes to a 3-pixel-row ring in shared memory; the output row y - 1 is the 9-term gather
-//      out[y, x, d] = b2 + sum_{kh, kw} Q[(y + kh - 1), (x + kw - 1), d][kh, kw]  (the col2im of the scatter form), written as C8.
+//   4. Q (fp16) goes to a 3-pixel-row ring in shared memory; an output row is the 9-term gather
+//      out[y, x, d] = b2 + sum_{kh, kw} Q[(y + kh - 1), (x + kw - 1), d][kh, kw]  (the col2im of the scatter form), written as C8;
+//      the gather of row y - 2 runs while the tensor pipe works on GEMM1 of pixel-row y.
 // Phases are separated by block barriers; two CTAs per SM overlap one CTA's tensor phases with the other's epilogues.
 #include "tc_common.cuh"
 #include "cwfa_b200_debug.h"
@@ -109,10 +110,12 @@ __global__ void __launch_bounds__(kThreads, MINB) stencil3d_tc_kernel(const StPa
     store_xrow(2, fetch_xrow(2));
     __syncthreads();
 
-    for (int py = -1; py <= th; ++py) {
-        const uint4 x_next = fetch_xrow(py + 4);                   // lands in the ring while GEMM2 runs
+    for (int py = -1; py <= th + 1; ++py) {
+        const bool cur = py <= th;                                  // the last iteration only flushes the final output row
+        uint4 x_next = make_uint4(0, 0, 0, 0);
+        if (cur) x_next = fetch_xrow(py + 4);                       // lands in the ring while GEMM2 runs
         // ---- 1. im2col of the nine spatial taps (+ the two bias ones) for every row of this pixel-row (chunk planes 0, 1)
-        {
+        if (cur) {
             const unsigned short* x_m = xs + ((py + 1) & 3) * p.xs_halves;
             const unsigned short* x_c = xs + ((py + 2) & 3) * p.xs_halves;
             const unsigned short* x_p = xs + ((py + 3) & 3) * p.xs_halves;
@@ -133,7 +136,7 @@ __global__ void __launch_bounds__(kThreads, MINB) stencil3d_tc_kernel(const StPa
         __syncthreads();
         stamp(1);
         // ---- 2. GEMM1: hidden[r] = sum_kd A1[r + kd - 1] * W1[kd]^T  (N = 32, K = 16 per depth tap)
-        if (tid == 0) {
+        if (cur && tid == 0) {
             tc_fence_after();
             for (int m = 0; m < n_mt; ++m)
 #pragma unroll
@@ -142,6 +145,43 @@ __global__ void __launch_bounds__(kThreads, MINB) stencil3d_tc_kernel(const StPa
                                      desc_lo(sW + kd * 1024, 512), hi128, id32, kd);
             tc_commit(bar);
         }
+        // ---- output row y0 + py - 2: gather of the nine shifted partials (two depths per thread) -- its pixel-rows py - 3 .. py - 1
+        // are complete, so it runs UNDER GEMM1 of pixel-row py instead of after epilogue 2
+        const int yo = py - 2;
+        if (yo >= 0 && yo < th) {
+            const int Dp = p.cout_chunks * 8, Dh = Dp >> 1;
+            const uint32_t dh_magic = 65536u / (uint32_t)Dh + 1u;
+            const __half* q_m = q + ((yo + 0) % 3) * 9 * QP;       // pixel-row yo - 1 -> slot (yo - 1 + 1) % 3
+            const __half* q_c = q + ((yo + 1) % 3) * 9 * QP;
+            const __half* q_p = q + ((yo + 2) % 3) * 9 * QP;
+            for (int i = tid; i < tw * Dh; i += kThreads) {
+                const int px = (int)(((uint32_t)i * dh_magic) >> 16), d = 2 * (i - px * Dh);
+                float s0v = 0.f, s1v = 0.f;
+                if (d < D) {
+                    const int o = px * Dq + d;
+                    s0v = b2;
+                    s1v = b2;
+#pragma unroll
+                    for (int kw = 0; kw < 3; ++kw) {
+                        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(q_m + (0 * 3 + kw) * QP + o + kw * Dq));
+                        const float2 b = __half22float2(*reinterpret_cast<const __half2*>(q_c + (1 * 3 + kw) * QP + o + kw * Dq));
+                        const float2 c = __half22float2(*reinterpret_cast<const __half2*>(q_p + (2 * 3 + kw) * QP + o + kw * Dq));
+                        s0v += a.x + b.x + c.x;
+                        s1v += a.y + b.y + c.y;
+                    }
+                    if (d + 1 >= D) s1v = 0.f;
+                }
+                reinterpret_cast<uint32_t*>(stage)[i] = pack2<BF16>(s0v, s1v);
+            }
+            __syncthreads();
+            for (int i = tid; i < tw * p.cout_chunks; i += kThreads) {
+                const int ch = i / tw, px = i - ch * tw;
+                p.y[((size_t)(n * p.cout_chunks + ch) * p.H + y0 + yo) * p.W + x0 + px] =
+                    *reinterpret_cast<const uint4*>(stage + px * Dp + ch * 8);
+            }
+        }
+        stamp(6);
+        if (!cur) break;
         mbar_wait(bar, phase);
         phase ^= 1;
         tc_fence_after();
@@ -211,41 +251,6 @@ __global__ void __launch_bounds__(kThreads, MINB) stencil3d_tc_kernel(const StPa
         tc_fence_before();
         __syncthreads();
         stamp(5);
-        // ---- 4. output row y0 + py - 1: gather of the nine shifted partials, two depths per thread
-        const int yo = py - 1;
-        if (yo >= 0 && yo < th) {
-            const int Dp = p.cout_chunks * 8, Dh = Dp >> 1;
-            const uint32_t dh_magic = 65536u / (uint32_t)Dh + 1u;
-            const __half* q_m = q + ((yo + 0) % 3) * 9 * QP;       // pixel-row yo - 1 -> slot (yo - 1 + 1) % 3
-            const __half* q_c = q + ((yo + 1) % 3) * 9 * QP;
-            const __half* q_p = q + ((yo + 2) % 3) * 9 * QP;
-            for (int i = tid; i < tw * Dh; i += kThreads) {
-                const int px = (int)(((uint32_t)i * dh_magic) >> 16), d = 2 * (i - px * Dh);
-                float s0v = 0.f, s1v = 0.f;
-                if (d < D) {
-                    const int o = px * Dq + d;
-                    s0v = b2;
-                    s1v = b2;
-#pragma unroll
-                    for (int kw = 0; kw < 3; ++kw) {
-                        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(q_m + (0 * 3 + kw) * QP + o + kw * Dq));
-                        const float2 b = __half22float2(*reinterpret_cast<const __half2*>(q_c + (1 * 3 + kw) * QP + o + kw * Dq));
-                        const float2 c = __half22float2(*reinterpret_cast<const __half2*>(q_p + (2 * 3 + kw) * QP + o + kw * Dq));
-                        s0v += a.x + b.x + c.x;
-                        s1v += a.y + b.y + c.y;
-                    }
-                    if (d + 1 >= D) s1v = 0.f;
-                }
-                reinterpret_cast<uint32_t*>(stage)[i] = pack2<BF16>(s0v, s1v);
-            }
-            __syncthreads();
-            for (int i = tid; i < tw * p.cout_chunks; i += kThreads) {
-                const int ch = i / tw, px = i - ch * tw;
-                p.y[((size_t)(n * p.cout_chunks + ch) * p.H + y0 + yo) * p.W + x0 + px] =
-                    *reinterpret_cast<const uint4*>(stage + px * Dp + ch * 8);
-            }
-        }
-        stamp(6);
     }
     if (p.prof && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) {
         for (int k = 0; k < 7; ++k) p.prof[k] = (unsigned long long)t_ph[k];
