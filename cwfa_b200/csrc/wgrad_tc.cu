@@ -159,22 +159,36 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const __grid_co
     }
 }
 
-// dW[co][ci][t] = sum_k part[k][t][ci][co]  (fixed order, double accumulation; reads follow the partial layout)
+// dW[co][ci][t] = sum_k part[k][t][ci][co]  (fixed order, double accumulation; reads follow the partial layout).
+// One block = 256 / S consecutive elements x S slices of the partial index: slice s sums the partials k = s, s + S, ... with four
+// loads in flight (a warp load = 128 contiguous bytes), the slices are then added in a fixed order through shared memory.
+// S = 8 when there are many partials (64-channel convs: 74 or 148): one thread per element walking all of them was latency-bound
+// (18 us per 64 -> 64 3x3 gradient); S = 1 for the wide U-Net convs (1-4 partials of up to 38 MB: bandwidth-bound as they are).
 __global__ void __launch_bounds__(256) wgrad_tc_finalize_kernel(const float* __restrict__ part, float* __restrict__ out,
-                                                                int Cout, int Cin, int KK, int nparts) {
+                                                                int Cout, int Cin, int KK, int nparts, int S) {
+    __shared__ double red[256];
     const int64_t n = (int64_t)Cout * Cin * KK;
-    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    // four interleaved accumulators (fixed association: still bit-reproducible) keep four partial loads in flight instead of one
+    const int E = 256 / S, e = threadIdx.x % E, slice = threadIdx.x / E;
+    const int64_t i = blockIdx.x * (int64_t)E + e;
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    int k = 0;
-    for (; k + 3 < nparts; k += 4) {
-        const float a = __ldg(part + (int64_t)k * n + i), b = __ldg(part + (int64_t)(k + 1) * n + i);
-        const float c = __ldg(part + (int64_t)(k + 2) * n + i), d = __ldg(part + (int64_t)(k + 3) * n + i);
-        s0 += (double)a; s1 += (double)b; s2 += (double)c; s3 += (double)d;
+    if (i < n) {
+        int k = slice;
+        for (; k + 3 * S < nparts; k += 4 * S) {
+            const float a = __ldg(part + (int64_t)k * n + i), b = __ldg(part + (int64_t)(k + S) * n + i);
+            const float c = __ldg(part + (int64_t)(k + 2 * S) * n + i), d = __ldg(part + (int64_t)(k + 3 * S) * n + i);
+            s0 += (double)a; s1 += (double)b; s2 += (double)c; s3 += (double)d;
+        }
+        for (; k < nparts; k += S) s0 += (double)__ldg(part + (int64_t)k * n + i);
     }
-    for (; k < nparts; ++k) s0 += (double)__ldg(part + (int64_t)k * n + i);
-    const double s = (s0 + s1) + (s2 + s3);
+    double s = (s0 + s1) + (s2 + s3);
+    if (S > 1) {                                   // block-uniform
+        red[threadIdx.x] = s;
+        __syncthreads();
+        if (slice != 0) return;
+        s = 0.0;
+        for (int j = 0; j < S; ++j) s += red[j * E + e];
+    }
+    if (i >= n) return;
     const int co = (int)(i % Cout), ci = (int)((i / Cout) % Cin), t = (int)(i / ((int64_t)Cout * Cin));
     out[((int64_t)co * Cin + ci) * KK + t] = (float)s;
 }
@@ -244,6 +258,7 @@ extern "C" int cwfa_wgrad_tc(const void* x_c8, const void* dy_c8, float* dw, flo
     rc = check_launch("wgrad_tc");
     if (rc) return rc;
     const int64_t n = (int64_t)Cout * Cin * KH * KW;
-    wgrad_tc_finalize_kernel<<<ceil_div(n, 256), 256, 0, st>>>(workspace, dw, Cout, Cin, KH * KW, pl.chunks);
+    const int slices = pl.chunks >= 32 ? 8 : (pl.chunks >= 8 ? 4 : 1);
+    wgrad_tc_finalize_kernel<<<(unsigned)ceil_div(n, 256 / slices), 256, 0, st>>>(workspace, dw, Cout, Cin, KH * KW, pl.chunks, slices);
     return check_launch("wgrad_tc_finalize");
 }
