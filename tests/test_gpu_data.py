@@ -37,6 +37,23 @@ def test_extract_views_full_size_property():
     assert torch.equal(out, O.extract_views(img, coords, [512, 512]))
 
 
+@pytest.mark.parametrize("side", [128, 256])
+def test_extract_views_wide_views_clipped_windows(side):
+    """Wide views (the 16-byte store path): windows clipped at every border, an image width that is not a multiple of 4 (the
+    source misalignment then changes from row to row), batch 2, fp32 / fp16 images, with and without normalisation -- bit-exact
+    against the oracle's restatement of XLFMDataset.extract_views."""
+    from cwfa_b200.data import extract_views
+    Hi, Wi = 700, 1002
+    img = seeded_randn((2, 1, Hi, Wi), 31)
+    h = side // 2
+    coords = [[10, 17], [Hi - 5, Wi - 9], [h, h], [Hi - h, Wi - h], [h + 1, Wi - 3], [Hi - 2, h + 3], [350, 501], [351, 502], [352, 503]]
+    ref = O.extract_views(img, coords, [side, side])
+    assert torch.equal(extract_views(img.to(DEV), coords, [side, side]).cpu(), ref)
+    mean, std = 0.25, 1.75
+    assert torch.equal(extract_views(img.to(DEV), coords, [side, side], mean, std).cpu(), (ref - mean) / std)
+    assert torch.equal(extract_views(img.half().to(DEV), coords, [side, side]).cpu(), O.extract_views(img.half(), coords, [side, side]).float())
+
+
 def test_evaluate_inn_forward_vs_reference_golden(golden_tiny):
     model = build_tiny_model(golden_tiny, DEV)
     cfg = golden_tiny["config"]
