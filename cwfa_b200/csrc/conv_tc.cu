@@ -172,6 +172,7 @@ struct TcParams {
     int MB, BN;
     uint32_t a_bytes, a_stride, b_bytes;
     int a_stages, b_stages;
+    int b_resident;            // 1: ALL weight tiles (num_kb x taps) of the single n-block stay in shared memory for the CTA's lifetime
     int total_items;           // (n-block, sample, tile) work items, walked persistently with stride gridDim.x
     int acc_bufs;              // TMEM accumulator buffers (2 = the MMAs of item i+1 overlap the epilogue of item i)
     int act, res_mode, out_mode;   // out_mode 0: C8 half   1: NCHW fp32   2: C8 half, 2x2 transposed-conv scatter
@@ -207,6 +208,7 @@ __device__ __forceinline__ void stamp(const TcParams& p, int slot) {
 }
 
 constexpr int kMaxBStages = 8;
+constexpr int kMaxAStages = 8;       // A (halo tile) ring: 2 stages normally; up to 8 small tiles in flight with resident weights
 constexpr int kStatSplits = 74;      // second-stage partials of the fused BatchNorm statistics (stage-1 grid = channel blocks x 74)
 constexpr int kThreads = 320;        // warp0 TMA, warp1 MMA, warps 2..9 epilogue (8 epilogue warps; the WIDE variant has 16)
 constexpr int kHeaderBytes = 2048;   // barriers, tmem slot, bias stage
@@ -281,6 +283,23 @@ __device__ __forceinline__ void issue_tap(uint32_t d_base, uint32_t bn, uint32_t
     }
 }
 
+// All taps of one k-block with RESIDENT weights (tap tiles consecutive in shared memory): no barrier between the taps, so the
+// elected lane issues the whole k-block in one straight loop.  (The per-tap form -- warp-wide wait, switch, __syncwarp -- costs
+// ~260 cycles per tap on the issuing warp even when nothing blocks: measured by issuing no MMAs at all; more than the 1-4
+// small MMAs of a tap of the conditioning-net convolutions.)
+template <int MB, int KS>
+__device__ __forceinline__ void issue_kblock(uint32_t d_base, uint32_t bn, uint32_t a_row, uint32_t a_hi, uint32_t a_kstep, uint32_t bw,
+                                             int KH, int KW, uint32_t b_lo, uint32_t b_hi, uint32_t b_kstep, uint32_t b_tap_units,
+                                             uint32_t idesc, uint32_t acc_first, uint32_t mask) {
+    for (int kh = 0; kh < KH; ++kh, a_row += bw) {
+        uint32_t a_lo0 = a_row;
+        for (int kw = 0; kw < KW; ++kw, ++a_lo0, b_lo += b_tap_units) {
+            issue_tap<MB, KS>(d_base, bn, a_lo0, a_hi, a_kstep, b_lo, b_hi, b_kstep, idesc, acc_first, mask);
+            acc_first = 1u;
+        }
+    }
+}
+
 // WIDE: 16 epilogue warps (576 threads) for tiles that fill all 512 TMEM columns (one CTA per SM, nothing to
 // overlap the epilogue with): halves the non-overlapped drain time of the N=256 U-Net convolutions.
 // CPL: 0 = plain conv; 1..4 = fused coupling epilogue with (direction, shift source) fixed at compile time
@@ -299,8 +318,8 @@ __global__ void __launch_bounds__(WIDE ? 576 : kThreads, WIDE ? 1 : 2) conv_tc_k
     // [0,2048): barriers + tmem slot + bias stage; then A ring, then B ring
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
     const uint32_t bar0 = smem_u32(bars);
-    auto a_full = [&](int s) { return bar0 + 8u * s; };                 // 2
-    auto a_empty = [&](int s) { return bar0 + 8u * (2 + s); };          // 2
+    auto a_full = [&](int s) { return bar0 + 8u * (32 + s); };          // kMaxAStages (slots 0-3 of the first layout are unused)
+    auto a_empty = [&](int s) { return bar0 + 8u * (48 + s); };         // kMaxAStages
     auto b_full = [&](int s) { return bar0 + 8u * (4 + s); };           // 8
     auto b_empty = [&](int s) { return bar0 + 8u * (12 + s); };         // 8
     auto acc_full = [&](int b) { return bar0 + 8u * (20 + b); };        // 2
@@ -349,7 +368,7 @@ __global__ void __launch_bounds__(WIDE ? 576 : kThreads, WIDE ? 1 : 2) conv_tc_k
 
     if (threadIdx.x == 0) stamp(p, 0);
     if (threadIdx.x == 0) {
-        for (int s = 0; s < 2; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
+        for (int s = 0; s < kMaxAStages; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
         for (int s = 0; s < kMaxBStages; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), kEpiThreads / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -372,28 +391,55 @@ __global__ void __launch_bounds__(WIDE ? 576 : kThreads, WIDE ? 1 : 2) conv_tc_k
             const int ph = p.KH / 2, pw = p.KW / 2;
             int sa = 0, sb = 0;                      // running ring positions (no divisions): the rings run straight through item boundaries,
             uint32_t pa = 0, pb = 0;                 // ring pass parities
-            ItemPos pos = split_digits((int)blockIdx.x);
-            for (int item = blockIdx.x; item < total; item += gridDim.x, advance(pos)) {   // so the next item's operands load during this epilogue
-                const int nblk = pos.nblk, n = pos.n, h0 = pos.ty * 16, w0 = pos.tx * 8 * p.MB;
-                const uint8_t* src = p.w_packed + (size_t)nblk * p.num_kb * T * p.b_bytes;
-                const uint32_t* km = p.kmask + nblk * p.num_kb;
-                uint32_t km_next = __ldg(km);
-                for (int kb = 0; kb < p.num_kb; ++kb) {
-                    uint32_t kmask = km_next;
-                    if (kb + 1 < p.num_kb) km_next = __ldg(km + kb + 1);          // prefetched: off the per-k-block critical path
-                    if (kb == 0 && kmask == 0) kmask = 1u;                        // same rule as the MMA issuer
-                    if (kmask == 0) { src += (size_t)T * p.b_bytes; continue; }   // all-zero weight block: neither operand is loaded
-                    mbar_wait(a_empty(sa), pa ^ 1);
-                    mbar_expect_tx(a_full(sa), p.a_bytes);
-                    tma_load_4d(a_base + sa * p.a_stride, &tmap, a_full(sa), (w0 - pw) * 8, h0 - ph, kb * p.KCc, n);
-                    if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
-                    for (int tap = 0; tap < T; ++tap, src += p.b_bytes) {
-                        mbar_wait(b_empty(sb), pb ^ 1);
-                        mbar_expect_tx(b_full(sb), p.b_bytes);
-                        bulk_load(b_base + sb * p.b_bytes, src, p.b_bytes, b_full(sb));
-                        if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
+            // The A (halo tile) loads run ONE (item, k-block) AHEAD of the weight taps: the tile of the next k-block / item is
+            // requested before the taps of the current one are pushed.  With the A load in front of its own taps the producer
+            // could lead the MMAs by at most b_stages taps -- less than one small item (9 taps of a few hundred bytes, 3-4 MMAs
+            // each), so every item of the small 3x3 / 7x7 convolutions exposed a full TMA round trip (16-24 us for convolutions
+            // whose traffic is a 3-8 us pass).
+            struct Cur { ItemPos pos; int item, kb; };
+            auto load_a = [&](const Cur& c) {
+                mbar_wait(a_empty(sa), pa ^ 1);
+                mbar_expect_tx(a_full(sa), p.a_bytes);
+                tma_load_4d(a_base + sa * p.a_stride, &tmap, a_full(sa), (c.pos.tx * 8 * p.MB - pw) * 8, c.pos.ty * 16 - ph, c.kb * p.KCc, c.pos.n);
+                if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
+            };
+            auto k_nonzero = [&](const Cur& c) {     // same rule as the MMA issuer: all-zero weight blocks are skipped, k-block 0 never is
+                return c.kb == 0 || __ldg(p.kmask + c.pos.nblk * p.num_kb + c.kb) != 0u;
+            };
+            auto next = [&](Cur& c) {                // advance to the next NONZERO (item, k-block); false past the last item
+                for (;;) {
+                    if (++c.kb == p.num_kb) {
+                        c.kb = 0;
+                        c.item += gridDim.x;
+                        advance(c.pos);
                     }
+                    if (c.item >= total) return false;
+                    if (k_nonzero(c)) return true;
                 }
+            };
+            Cur cur{split_digits((int)blockIdx.x), (int)blockIdx.x, 0};
+            bool have = cur.item < total;
+            if (have && p.b_resident) {              // every weight tile once, all on ONE barrier (stage s = k-block * taps + tap)
+                const uint32_t tiles_b = (uint32_t)(p.num_kb * T);
+                mbar_expect_tx(b_full(0), tiles_b * p.b_bytes);
+                for (uint32_t s_ = 0; s_ < tiles_b; ++s_)
+                    bulk_load(b_base + s_ * p.b_bytes, p.w_packed + (size_t)s_ * p.b_bytes, p.b_bytes, b_full(0));
+            }
+            if (have) load_a(cur);
+            while (have) {
+                Cur nxt = cur;
+                const bool have_next = next(nxt);
+                if (have_next && p.a_stages > 1) load_a(nxt);
+                const uint8_t* src = p.w_packed + ((size_t)cur.pos.nblk * p.num_kb + cur.kb) * T * p.b_bytes;
+                for (int tap = 0; tap < (p.b_resident ? 0 : T); ++tap, src += p.b_bytes) {
+                    mbar_wait(b_empty(sb), pb ^ 1);
+                    mbar_expect_tx(b_full(sb), p.b_bytes);
+                    bulk_load(b_base + sb * p.b_bytes, src, p.b_bytes, b_full(sb));
+                    if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
+                }
+                if (have_next && p.a_stages == 1) load_a(nxt);   // one A stage: it is free only after this k-block's MMAs (old order)
+                cur = nxt;
+                have = have_next;
             }
         }
     } else if (warp == 1) {
@@ -413,6 +459,13 @@ __global__ void __launch_bounds__(WIDE ? 576 : kThreads, WIDE ? 1 : 2) conv_tc_k
         int sa = 0, sb = 0, li = 0;
         uint32_t pa = 0, pb = 0;
         if (leader) { stamp(p, 2); stamp(p, 3); }                // (the operand waits are no longer stamped: hot loop)
+        // Resident weights (small single-n-block convs): no per-tap ring handshake at all.  Streaming a few-hundred-byte tap
+        // through the ring costs a bulk-copy + commit round trip (~1.5-2 us / 8 stages = ~290 ns per tap) against ~50 ns of MMAs.
+        const bool resident = p.b_resident != 0;
+        if (resident && (int)blockIdx.x < total) {
+            mbar_wait(b_full(0), 0);
+            tc_fence_after();
+        }
         ItemPos pos = split_digits((int)blockIdx.x);
         for (int item = blockIdx.x; item < total; item += gridDim.x, ++li, advance(pos)) {
         const int buf = p.acc_bufs == 2 ? (li & 1) : 0;
@@ -429,6 +482,29 @@ __global__ void __launch_bounds__(WIDE ? 576 : kThreads, WIDE ? 1 : 2) conv_tc_k
             if (kb == 0 && kmask == 0) kmask = 1u;               // the accumulator must be written at least once per item
             if (kmask == 0) continue;                            // all-zero weight block: skipped by the producer as well
             mbar_wait(a_full(sa), pa);
+            if (resident) {
+                tc_fence_after();
+                if (leader) {
+                    const uint32_t a_row0 = (((a_base + sa * p.a_stride) & 0x3FFFFu) >> 4) | a_lbo_enc;
+                    const uint32_t b_lo = b_ring_lo + (uint32_t)(kb * T) * b_stage_units;
+                    const uint32_t bw = (uint32_t)p.BW;
+                    switch ((p.MB - 1) * 4 + (ksteps - 1)) {
+                        case 0: issue_kblock<1, 1>(d_base, p.BN, a_row0, a_hi, a_kstep, bw, p.KH, p.KW, b_lo, b_hi, b_kstep, b_stage_units, idesc, acc_first, kmask); break;
+                        case 1: issue_kblock<1, 2>(d_base, p.BN, a_row0, a_hi, a_kstep, bw, p.KH, p.KW, b_lo, b_hi, b_kstep, b_stage_units, idesc, acc_first, kmask); break;
+                        case 2: issue_kblock<1, 3>(d_base, p.BN, a_row0, a_hi, a_kstep, bw, p.KH, p.KW, b_lo, b_hi, b_kstep, b_stage_units, idesc, acc_first, kmask); break;
+                        case 3: issue_kblock<1, 4>(d_base, p.BN, a_row0, a_hi, a_kstep, bw, p.KH, p.KW, b_lo, b_hi, b_kstep, b_stage_units, idesc, acc_first, kmask); break;
+                        case 4: issue_kblock<2, 1>(d_base, p.BN, a_row0, a_hi, a_kstep, bw, p.KH, p.KW, b_lo, b_hi, b_kstep, b_stage_units, idesc, acc_first, kmask); break;
+                        case 5: issue_kblock<2, 2>(d_base, p.BN, a_row0, a_hi, a_kstep, bw, p.KH, p.KW, b_lo, b_hi, b_kstep, b_stage_units, idesc, acc_first, kmask); break;
+                        case 6: issue_kblock<2, 3>(d_base, p.BN, a_row0, a_hi, a_kstep, bw, p.KH, p.KW, b_lo, b_hi, b_kstep, b_stage_units, idesc, acc_first, kmask); break;
+                        default: issue_kblock<2, 4>(d_base, p.BN, a_row0, a_hi, a_kstep, bw, p.KH, p.KW, b_lo, b_hi, b_kstep, b_stage_units, idesc, acc_first, kmask); break;
+                    }
+                    tc_commit(a_empty(sa));
+                }
+                acc_first = 1u;
+                __syncwarp();
+                if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
+                continue;
+            }
             // descriptor low words in 16-byte units; taps advance by one pixel (kw) / one tile row (kh)
             uint32_t a_row = (((a_base + sa * p.a_stride) & 0x3FFFFu) >> 4) | a_lbo_enc;
             for (int kh = 0; kh < p.KH; ++kh, a_row += (uint32_t)p.BW) {
@@ -1054,6 +1130,24 @@ static int conv_tc_launch(const void* x_c8, const void* w_packed, const float* b
         if (hdr + 2 * p.a_stride + p.b_bytes > budget_max) p.a_stages = 1;
         if (bs > 3) bs = 3;        // measured: a 4th 32 KB weight stage slows the N = 256 convs (L1 carve-out 228 KB instead of 196 KB)
         while (bs > 1 && hdr + p.a_stages * p.a_stride + bs * p.b_bytes > budget_max) --bs;
+    }
+    // Small convolutions with ONE n-block whose whole weight set fits next to the A ring keep it resident (two CTAs per SM when
+    // the tile allows it): the per-tap ring round trip is what bounded them (3x3 convs of 6-48 channels: 16-24 us each).
+    p.b_resident = 0;
+    {
+        const int nblks = (out_mode == 2 ? 4 : 1) * Cout_p / BN;
+        const uint32_t budget = can_pair ? budget_two : budget_max;
+        if (nblks == 1 && stats == nullptr && (uint64_t)hdr + 2ull * p.a_stride + (uint64_t)total_b * p.b_bytes <= budget &&
+            (uint64_t)total_b * p.b_bytes < (1u << 20)) {
+            p.b_resident = 1;
+            p.a_stages = 2;
+            bs = total_b;
+            // these convolutions are small-channel streaming passes: what bounds them is the number of halo-tile bytes in flight
+            // per SM (two 10-20 KB tiles per CTA covered ~1/4 of the HBM latency-bandwidth product), so the A ring takes the
+            // rest of the budget
+            while (p.a_stages < kMaxAStages && (uint64_t)hdr + (uint64_t)(p.a_stages + 1) * p.a_stride + (uint64_t)total_b * p.b_bytes <= budget)
+                ++p.a_stages;
+        }
     }
     const uint32_t fixed = hdr + p.a_stages * p.a_stride;
     if (fixed + bs * p.b_bytes > budget_max) { set_error("conv_tc: tile does not fit shared memory"); return CWFA_EINVAL; }

@@ -15,6 +15,7 @@ SHAPES = [  # cin, cout, k, H, W, mb, bn
     (256, 256, 3, 512, 512, 2, 128), (48, 1536, 3, 512, 512, 2, 256), (48, 1536, 3, 512, 512, 2, 128), (1536, 48, 3, 512, 512, 2, 48),
     (1536, 48, 3, 512, 512, 1, 48), (16, 256, 3, 512, 512, 2, 128), (512, 512, 3, 256, 256, 2, 128), (64, 96, 3, 512, 512, 2, 96), (64, 96, 3, 512, 512, 1, 96), (64, 48, 3, 512, 512, 2, 48),
     (512, 1024, 1, 256, 256, 2, 256), (1024, 2048, 1, 128, 128, 2, 256), (512, 1024, 1, 256, 256, 1, 128),
+    (6, 6, 3, 512, 512, 2, 16), (6, 6, 7, 512, 512, 2, 16), (6, 6, 3, 512, 512, 1, 16),
 ]
 
 def run(cin, cout, k, H, W, mb, bn, act=ops.ACT_ELU, reps=3):
