@@ -391,55 +391,38 @@ __global__ void __launch_bounds__(WIDE ? 576 : kThreads, WIDE ? 1 : 2) conv_tc_k
             const int ph = p.KH / 2, pw = p.KW / 2;
             int sa = 0, sb = 0;                      // running ring positions (no divisions): the rings run straight through item boundaries,
             uint32_t pa = 0, pb = 0;                 // ring pass parities
-            // The A (halo tile) loads run ONE (item, k-block) AHEAD of the weight taps: the tile of the next k-block / item is
-            // requested before the taps of the current one are pushed.  With the A load in front of its own taps the producer
-            // could lead the MMAs by at most b_stages taps -- less than one small item (9 taps of a few hundred bytes, 3-4 MMAs
-            // each), so every item of the small 3x3 / 7x7 convolutions exposed a full TMA round trip (16-24 us for convolutions
-            // whose traffic is a 3-8 us pass).
-            struct Cur { ItemPos pos; int item, kb; };
-            auto load_a = [&](const Cur& c) {
-                mbar_wait(a_empty(sa), pa ^ 1);
-                mbar_expect_tx(a_full(sa), p.a_bytes);
-                tma_load_4d(a_base + sa * p.a_stride, &tmap, a_full(sa), (c.pos.tx * 8 * p.MB - pw) * 8, c.pos.ty * 16 - ph, c.kb * p.KCc, c.pos.n);
-                if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
-            };
-            auto k_nonzero = [&](const Cur& c) {     // same rule as the MMA issuer: all-zero weight blocks are skipped, k-block 0 never is
-                return c.kb == 0 || __ldg(p.kmask + c.pos.nblk * p.num_kb + c.kb) != 0u;
-            };
-            auto next = [&](Cur& c) {                // advance to the next NONZERO (item, k-block); false past the last item
-                for (;;) {
-                    if (++c.kb == p.num_kb) {
-                        c.kb = 0;
-                        c.item += gridDim.x;
-                        advance(c.pos);
-                    }
-                    if (c.item >= total) return false;
-                    if (k_nonzero(c)) return true;
-                }
-            };
-            Cur cur{split_digits((int)blockIdx.x), (int)blockIdx.x, 0};
-            bool have = cur.item < total;
-            if (have && p.b_resident) {              // every weight tile once, all on ONE barrier (stage s = k-block * taps + tap)
+            // Weight taps follow their own A tile in program order (an A load placed ahead of the PREVIOUS k-block's taps would
+            // block on a_empty, i.e. on the MMAs of k-block kb - 1, before the taps of k-block kb are requested: measured -9 % on
+            // the U-Net convolutions).  With resident weights there are no tap loads and the loop only keeps the A ring full.
+            ItemPos pos = split_digits((int)blockIdx.x);
+            if ((int)blockIdx.x < total && p.b_resident) {   // every weight tile once, all on ONE barrier (stage s = k-block * taps + tap)
                 const uint32_t tiles_b = (uint32_t)(p.num_kb * T);
                 mbar_expect_tx(b_full(0), tiles_b * p.b_bytes);
                 for (uint32_t s_ = 0; s_ < tiles_b; ++s_)
                     bulk_load(b_base + s_ * p.b_bytes, p.w_packed + (size_t)s_ * p.b_bytes, p.b_bytes, b_full(0));
             }
-            if (have) load_a(cur);
-            while (have) {
-                Cur nxt = cur;
-                const bool have_next = next(nxt);
-                if (have_next && p.a_stages > 1) load_a(nxt);
-                const uint8_t* src = p.w_packed + ((size_t)cur.pos.nblk * p.num_kb + cur.kb) * T * p.b_bytes;
-                for (int tap = 0; tap < (p.b_resident ? 0 : T); ++tap, src += p.b_bytes) {
-                    mbar_wait(b_empty(sb), pb ^ 1);
-                    mbar_expect_tx(b_full(sb), p.b_bytes);
-                    bulk_load(b_base + sb * p.b_bytes, src, p.b_bytes, b_full(sb));
-                    if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
+            for (int item = blockIdx.x; item < total; item += gridDim.x, advance(pos)) {   // the next item's operands load during this epilogue
+                const int nblk = pos.nblk, n = pos.n, h0 = pos.ty * 16, w0 = pos.tx * 8 * p.MB;
+                const uint8_t* src = p.w_packed + (size_t)nblk * p.num_kb * T * p.b_bytes;
+                const uint32_t* km = p.kmask + nblk * p.num_kb;
+                uint32_t km_next = __ldg(km);
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    uint32_t kmask = km_next;
+                    if (kb + 1 < p.num_kb) km_next = __ldg(km + kb + 1);          // prefetched: off the per-k-block critical path
+                    if (kb == 0 && kmask == 0) kmask = 1u;                        // same rule as the MMA issuer
+                    if (kmask == 0) { src += (size_t)T * p.b_bytes; continue; }   // all-zero weight block: neither operand is loaded
+                    mbar_wait(a_empty(sa), pa ^ 1);
+                    mbar_expect_tx(a_full(sa), p.a_bytes);
+                    tma_load_4d(a_base + sa * p.a_stride, &tmap, a_full(sa), (w0 - pw) * 8, h0 - ph, kb * p.KCc, n);
+                    if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
+                    if (p.b_resident) continue;
+                    for (int tap = 0; tap < T; ++tap, src += p.b_bytes) {
+                        mbar_wait(b_empty(sb), pb ^ 1);
+                        mbar_expect_tx(b_full(sb), p.b_bytes);
+                        bulk_load(b_base + sb * p.b_bytes, src, p.b_bytes, b_full(sb));
+                        if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
+                    }
                 }
-                if (have_next && p.a_stages == 1) load_a(nxt);   // one A stage: it is free only after this k-block's MMAs (old order)
-                cur = nxt;
-                have = have_next;
             }
         }
     } else if (warp == 1) {
