@@ -300,13 +300,32 @@ __device__ __forceinline__ void issue_kblock(uint32_t d_base, uint32_t bn, uint3
     }
 }
 
+// Dispatcher over the compile-time (MB, K-steps) forms, called by the elected lane once per k-block.  (An out-of-line
+// `__noinline__` version spilled MORE in the callers -- live values saved around the call -- than this inlined one.)
+__device__ __forceinline__ void issue_kblock_any(int key, uint32_t d_base, uint32_t bn, uint32_t a_row, uint32_t a_hi, uint32_t a_kstep,
+                                              uint32_t bw, int KH, int KW, uint32_t b_lo, uint32_t b_hi, uint32_t b_kstep,
+                                              uint32_t b_tap_units, uint32_t idesc, uint32_t acc_first, uint32_t mask) {
+    switch (key) {
+        case 0: issue_kblock<1, 1>(d_base, bn, a_row, a_hi, a_kstep, bw, KH, KW, b_lo, b_hi, b_kstep, b_tap_units, idesc, acc_first, mask); break;
+        case 1: issue_kblock<1, 2>(d_base, bn, a_row, a_hi, a_kstep, bw, KH, KW, b_lo, b_hi, b_kstep, b_tap_units, idesc, acc_first, mask); break;
+        case 2: issue_kblock<1, 3>(d_base, bn, a_row, a_hi, a_kstep, bw, KH, KW, b_lo, b_hi, b_kstep, b_tap_units, idesc, acc_first, mask); break;
+        case 3: issue_kblock<1, 4>(d_base, bn, a_row, a_hi, a_kstep, bw, KH, KW, b_lo, b_hi, b_kstep, b_tap_units, idesc, acc_first, mask); break;
+        case 4: issue_kblock<2, 1>(d_base, bn, a_row, a_hi, a_kstep, bw, KH, KW, b_lo, b_hi, b_kstep, b_tap_units, idesc, acc_first, mask); break;
+        case 5: issue_kblock<2, 2>(d_base, bn, a_row, a_hi, a_kstep, bw, KH, KW, b_lo, b_hi, b_kstep, b_tap_units, idesc, acc_first, mask); break;
+        case 6: issue_kblock<2, 3>(d_base, bn, a_row, a_hi, a_kstep, bw, KH, KW, b_lo, b_hi, b_kstep, b_tap_units, idesc, acc_first, mask); break;
+        default: issue_kblock<2, 4>(d_base, bn, a_row, a_hi, a_kstep, bw, KH, KW, b_lo, b_hi, b_kstep, b_tap_units, idesc, acc_first, mask); break;
+    }
+}
+
 // WIDE: 16 epilogue warps (576 threads) for tiles that fill all 512 TMEM columns (one CTA per SM, nothing to
 // overlap the epilogue with): halves the non-overlapped drain time of the N=256 U-Net convolutions.
 // CPL: 0 = plain conv; 1..4 = fused coupling epilogue with (direction, shift source) fixed at compile time
 // (1 fwd / conv t, 2 inv / conv t, 3 fwd / external t, 4 inv / external t) so the element loop carries no flag tests.
 // FAST: 0 = generic epilogue (any activation / residual / output mode); 1, 2 = lean epilogue for the bandwidth-heavy
 // common case "C8 output, no residual" with activation none (1) or PReLU (2): ~3x fewer instructions per value.
-template <bool BF16, int CPL, bool WIDE, int FAST>
+// RES: resident-weights mode (small single-n-block multi-tap convs) as its own instantiation, so that the ring-path kernels keep
+// exactly their register allocation.
+template <bool BF16, int CPL, bool WIDE, int FAST, bool RES = false>
 __global__ void __launch_bounds__(WIDE ? 576 : kThreads, WIDE ? 1 : 2) conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
     constexpr bool COUPLING = CPL != 0;
     constexpr bool CPL_INV = CPL == 2 || CPL == 4;
@@ -395,7 +414,7 @@ __global__ void __launch_bounds__(WIDE ? 576 : kThreads, WIDE ? 1 : 2) conv_tc_k
             // block on a_empty, i.e. on the MMAs of k-block kb - 1, before the taps of k-block kb are requested: measured -9 % on
             // the U-Net convolutions).  With resident weights there are no tap loads and the loop only keeps the A ring full.
             ItemPos pos = split_digits((int)blockIdx.x);
-            if ((int)blockIdx.x < total && p.b_resident) {   // every weight tile once, all on ONE barrier (stage s = k-block * taps + tap)
+            if (RES && (int)blockIdx.x < total) {   // every weight tile once, all on ONE barrier (stage s = k-block * taps + tap)
                 const uint32_t tiles_b = (uint32_t)(p.num_kb * T);
                 mbar_expect_tx(b_full(0), tiles_b * p.b_bytes);
                 for (uint32_t s_ = 0; s_ < tiles_b; ++s_)
@@ -415,12 +434,13 @@ __global__ void __launch_bounds__(WIDE ? 576 : kThreads, WIDE ? 1 : 2) conv_tc_k
                     mbar_expect_tx(a_full(sa), p.a_bytes);
                     tma_load_4d(a_base + sa * p.a_stride, &tmap, a_full(sa), (w0 - pw) * 8, h0 - ph, kb * p.KCc, n);
                     if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
-                    if (p.b_resident) continue;
-                    for (int tap = 0; tap < T; ++tap, src += p.b_bytes) {
-                        mbar_wait(b_empty(sb), pb ^ 1);
-                        mbar_expect_tx(b_full(sb), p.b_bytes);
-                        bulk_load(b_base + sb * p.b_bytes, src, p.b_bytes, b_full(sb));
-                        if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
+                    if constexpr (!RES) {
+                        for (int tap = 0; tap < T; ++tap, src += p.b_bytes) {
+                            mbar_wait(b_empty(sb), pb ^ 1);
+                            mbar_expect_tx(b_full(sb), p.b_bytes);
+                            bulk_load(b_base + sb * p.b_bytes, src, p.b_bytes, b_full(sb));
+                            if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
+                        }
                     }
                 }
             }
@@ -444,7 +464,7 @@ __global__ void __launch_bounds__(WIDE ? 576 : kThreads, WIDE ? 1 : 2) conv_tc_k
         if (leader) { stamp(p, 2); stamp(p, 3); }                // (the operand waits are no longer stamped: hot loop)
         // Resident weights (small single-n-block convs): no per-tap ring handshake at all.  Streaming a few-hundred-byte tap
         // through the ring costs a bulk-copy + commit round trip (~1.5-2 us / 8 stages = ~290 ns per tap) against ~50 ns of MMAs.
-        const bool resident = p.b_resident != 0;
+        constexpr bool resident = RES;
         if (resident && (int)blockIdx.x < total) {
             mbar_wait(b_full(0), 0);
             tc_fence_after();
@@ -465,22 +485,14 @@ __global__ void __launch_bounds__(WIDE ? 576 : kThreads, WIDE ? 1 : 2) conv_tc_k
             if (kb == 0 && kmask == 0) kmask = 1u;               // the accumulator must be written at least once per item
             if (kmask == 0) continue;                            // all-zero weight block: skipped by the producer as well
             mbar_wait(a_full(sa), pa);
-            if (resident) {
+            if constexpr (resident) {
                 tc_fence_after();
                 if (leader) {
                     const uint32_t a_row0 = (((a_base + sa * p.a_stride) & 0x3FFFFu) >> 4) | a_lbo_enc;
                     const uint32_t b_lo = b_ring_lo + (uint32_t)(kb * T) * b_stage_units;
                     const uint32_t bw = (uint32_t)p.BW;
-                    switch ((p.MB - 1) * 4 + (ksteps - 1)) {
-                        case 0: issue_kblock<1, 1>(d_base, p.BN, a_row0, a_hi, a_kstep, bw, p.KH, p.KW, b_lo, b_hi, b_kstep, b_stage_units, idesc, acc_first, kmask); break;
-                        case 1: issue_kblock<1, 2>(d_base, p.BN, a_row0, a_hi, a_kstep, bw, p.KH, p.KW, b_lo, b_hi, b_kstep, b_stage_units, idesc, acc_first, kmask); break;
-                        case 2: issue_kblock<1, 3>(d_base, p.BN, a_row0, a_hi, a_kstep, bw, p.KH, p.KW, b_lo, b_hi, b_kstep, b_stage_units, idesc, acc_first, kmask); break;
-                        case 3: issue_kblock<1, 4>(d_base, p.BN, a_row0, a_hi, a_kstep, bw, p.KH, p.KW, b_lo, b_hi, b_kstep, b_stage_units, idesc, acc_first, kmask); break;
-                        case 4: issue_kblock<2, 1>(d_base, p.BN, a_row0, a_hi, a_kstep, bw, p.KH, p.KW, b_lo, b_hi, b_kstep, b_stage_units, idesc, acc_first, kmask); break;
-                        case 5: issue_kblock<2, 2>(d_base, p.BN, a_row0, a_hi, a_kstep, bw, p.KH, p.KW, b_lo, b_hi, b_kstep, b_stage_units, idesc, acc_first, kmask); break;
-                        case 6: issue_kblock<2, 3>(d_base, p.BN, a_row0, a_hi, a_kstep, bw, p.KH, p.KW, b_lo, b_hi, b_kstep, b_stage_units, idesc, acc_first, kmask); break;
-                        default: issue_kblock<2, 4>(d_base, p.BN, a_row0, a_hi, a_kstep, bw, p.KH, p.KW, b_lo, b_hi, b_kstep, b_stage_units, idesc, acc_first, kmask); break;
-                    }
+                    issue_kblock_any((p.MB - 1) * 4 + (ksteps - 1), d_base, p.BN, a_row0, a_hi, a_kstep, bw, p.KH, p.KW, b_lo, b_hi, b_kstep,
+                                     b_stage_units, idesc, acc_first, kmask);
                     tc_commit(a_empty(sa));
                 }
                 acc_first = 1u;
@@ -1120,16 +1132,14 @@ static int conv_tc_launch(const void* x_c8, const void* w_packed, const float* b
     {
         const int nblks = (out_mode == 2 ? 4 : 1) * Cout_p / BN;
         const uint32_t budget = can_pair ? budget_two : budget_max;
-        if (nblks == 1 && stats == nullptr && (uint64_t)hdr + 2ull * p.a_stride + (uint64_t)total_b * p.b_bytes <= budget &&
+        // 1x1 convolutions gain nothing (one tap per item either way).  The A ring stays at two stages: a deeper ring measured
+        // +-0 for the small convs, and filling the 113 KB budget pushes the SM's shared-memory carve-out to its maximum, which
+        // costs the epilogues their L1 (64 -> 64 1x1 + GELU + residual: 33.9 -> 41.9 us; level-0 training step +2.4 %).
+        if (nblks == 1 && KH * KW > 1 && stats == nullptr && out_mode != 3 && MB * BN <= 256 && (uint64_t)hdr + 2ull * p.a_stride + (uint64_t)total_b * p.b_bytes <= budget &&
             (uint64_t)total_b * p.b_bytes < (1u << 20)) {
             p.b_resident = 1;
             p.a_stages = 2;
             bs = total_b;
-            // these convolutions are small-channel streaming passes: what bounds them is the number of halo-tile bytes in flight
-            // per SM (two 10-20 KB tiles per CTA covered ~1/4 of the HBM latency-bandwidth product), so the A ring takes the
-            // rest of the budget
-            while (p.a_stages < kMaxAStages && (uint64_t)hdr + (uint64_t)(p.a_stages + 1) * p.a_stride + (uint64_t)total_b * p.b_bytes <= budget)
-                ++p.a_stages;
         }
     }
     const uint32_t fixed = hdr + p.a_stages * p.a_stride;
@@ -1184,8 +1194,15 @@ static int conv_tc_launch(const void* x_c8, const void* w_packed, const float* b
              {conv_tc_kernel<true, 0, true, 0>, conv_tc_kernel<true, 0, true, 1>, conv_tc_kernel<true, 0, true, 2>}}};
         kern = table[is_bf16 ? 1 : 0][wide ? 1 : 0][fast];
         ki = (is_bf16 ? 6 : 0) + (wide ? 3 : 0) + fast;
+        if (p.b_resident) {
+            static const KernT table_res[2][3] = {
+                {conv_tc_kernel<false, 0, false, 0, true>, conv_tc_kernel<false, 0, false, 1, true>, conv_tc_kernel<false, 0, false, 2, true>},
+                {conv_tc_kernel<true, 0, false, 0, true>, conv_tc_kernel<true, 0, false, 1, true>, conv_tc_kernel<true, 0, false, 2, true>}};
+            kern = table_res[is_bf16 ? 1 : 0][fast];
+            ki = 20 + (is_bf16 ? 3 : 0) + fast;
+        }
     }
-    static bool attr_done[20] = {};
+    static bool attr_done[26] = {};
     if (!attr_done[ki]) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         attr_done[ki] = true;
