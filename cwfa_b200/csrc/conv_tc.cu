@@ -208,7 +208,7 @@ __device__ __forceinline__ void stamp(const TcParams& p, int slot) {
 }
 
 constexpr int kMaxBStages = 8;
-constexpr int kMaxAStages = 8;       // A (halo tile) ring: 2 stages normally; up to 8 small tiles in flight with resident weights
+constexpr int kMaxAStages = 8;       // barrier slots of the A (halo tile) ring; every shared-memory plan uses 1 or 2 stages (a deeper ring measured +-0)
 constexpr int kStatSplits = 74;      // second-stage partials of the fused BatchNorm statistics (stage-1 grid = channel blocks x 74)
 constexpr int kThreads = 320;        // warp0 TMA, warp1 MMA, warps 2..9 epilogue (8 epilogue warps; the WIDE variant has 16)
 constexpr int kHeaderBytes = 2048;   // barriers, tmem slot, bias stage
