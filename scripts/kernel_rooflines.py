@@ -78,6 +78,18 @@ conv_case(256, 256, 3, 512, 512)
 conv_case(512, 512, 3, 256, 256)
 conv_case(1024, 1024, 3, 128, 128)
 conv_case(64, 64, 7, 512, 512)
+def small_conv_case(cin, cout, k):
+    """Small-channel convs of the conditioning nets / mean-volume branch: streaming passes, rated against HBM (operand + output bytes)."""
+    per = P * (tc.pad16(cin) + tc.pad16(cout)) * 2
+    n_ = max(2, min(32, (300 << 20) // per + 1))
+    xin_ = [tc.to_c8(torch.randn(1, cin, 512, 512, device=DEV)) for _ in range(n_)]
+    pc_ = tc.PackedConv(torch.randn(cout, cin, k, k, device=DEV) * 0.05, torch.zeros(cout, device=DEV))
+    sl_ = torch.tensor([0.2], device=DEV)
+    hbm(f"conv_tc {cin}->{cout} {k}x{k} @512x512 (resident weights; C8 bytes in + out)", per, lambda i: tc.conv_tc(xin_[i], pc_, act=ops.ACT_PRELU, slope=sl_), n_)
+small_conv_case(29, 48, 3)
+small_conv_case(48, 48, 3)
+small_conv_case(6, 6, 3)
+small_conv_case(6, 6, 7)
 n = 8
 xin = [tc.to_c8(torch.randn(1, 64, 512, 512, device=DEV)) for _ in range(n)]
 p3 = tc.PackedConv(torch.randn(64, 64, 3, 3, device=DEV) * 0.04, torch.zeros(64, device=DEV), bn=64)
